@@ -1,0 +1,156 @@
+/*
+ * kore_b200.h -- C ABI of libkoreb200.so, the B200-native shift-and-invert
+ * eigen / linear solver that replaces the SLEPc EPS / ST / PETSc KSP + MUMPS
+ * block of Kore's bin/solve.py.
+ *
+ * The reference has no FFI of its own for this path: it reaches PETSc/SLEPc
+ * through petsc4py/slepc4py object calls.  Each entry point below names the
+ * reference call(s) it replaces (file:line under /root/reference).
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; complex128 is `double[2]` (re, im),
+ *     passed as `const double*` of length 2*count (numpy complex128 layout);
+ *   - every pointer is CALLER-OWNED HOST memory unless the name ends in
+ *     `_dev`; the library copies during the call; outputs go to caller
+ *     buffers;
+ *   - every function returns 0 on success, a KB_E* code otherwise; the
+ *     message is available from kb_last_error(h) (petsc4py would raise on a
+ *     non-zero PetscErrorCode);
+ *   - a handle owns one GPU, one CUDA stream and all its device memory;
+ *     calls on one handle are not re-entrant, different handles may be driven
+ *     from different host threads;
+ *   - there is no CPU fallback: kb_create fails with KB_ENODEVICE when no
+ *     sm_100 device is visible.
+ */
+#ifndef KORE_B200_H
+#define KORE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kb_context* kb_handle;
+
+enum {
+  KB_OK = 0,
+  KB_EINVAL = 1,      /* bad argument / call order                                   */
+  KB_ENODEVICE = 2,   /* no usable GPU                                                */
+  KB_ECUDA = 3,       /* CUDA runtime error                                           */
+  KB_ENOMEM = 4,      /* device or host allocation failed                             */
+  KB_ESINGULAR = 5,   /* zero / non-finite pivot (MUMPS would report INFOG(1) = -10)  */
+  KB_ESTRUCTURE = 6,  /* (perm,nodeptr) does not make the pencil block tridiagonal    */
+  KB_ENCCL = 7        /* NCCL error on the l-sharded path                             */
+};
+
+/* SLEPc.EPS.Which as selected at bin/solve.py:99-117 (par.which_eigenpairs). */
+enum {
+  KB_WHICH_LM = 0, KB_WHICH_SM = 1, KB_WHICH_LR = 2, KB_WHICH_SR = 3, KB_WHICH_LI = 4,
+  KB_WHICH_SI = 5, KB_WHICH_TM = 6, KB_WHICH_TR = 7, KB_WHICH_TI = 8
+};
+
+/* Integer options for kb_set_option. */
+enum {
+  KB_OPT_EQUILIBRATE = 1, /* 0/1: power-of-two row+column scaling of A - sigma B (default 1)   */
+  KB_OPT_REFINE = 2,      /* max iterative-refinement steps per solve (default 1)             */
+  KB_OPT_PURIFY = 3,      /* 0/1: x <- OP x on extracted eigenvectors (SLEPc EPSSetPurify)    */
+  KB_OPT_SEED = 4,        /* seed of the random Arnoldi start vector when v0 == NULL          */
+  KB_OPT_PANEL = 5        /* Gauss-Jordan panel width override (0 = automatic)                */
+};
+
+/* PETSc.Sys / slepc4py.init (solve.py:15-16, 31-34): create a solver context
+ * bound to CUDA device `device`. */
+int kb_create(kb_handle* h, int device);
+
+/* MA.destroy / MB.destroy / K.destroy (solve.py:201-202, 236-239). */
+int kb_destroy(kb_handle h);
+
+const char* kb_last_error(kb_handle h);
+
+int kb_set_option(kb_handle h, int option, int64_t value);
+
+/* Mat create/setValuesCSR/assembly for A and B (solve.py:43-59, 69-85).
+ * n x n CSR, int32 or int64 indices selected by index_bytes (4 or 8).
+ * A values are complex128.  B may be NULL (forced problem, solve.py:209-227);
+ * b_is_complex selects float64 (0, what assemble.py writes) or complex128 (1). */
+int kb_set_pencil(kb_handle h, int64_t n, int index_bytes,
+                  const void* a_indptr, const void* a_indices, const double* a_values,
+                  const void* b_indptr, const void* b_indices, const void* b_values,
+                  int b_is_complex);
+
+/* Replaces the fill-reducing ordering / analysis phase of MUMPS (PCSetUp(LU),
+ * inside E.solve() solve.py:123 and K.solve solve.py:227): the caller supplies
+ * the l-major chain ordering.  perm[k] = original index of chain position k;
+ * node p owns chain rows nodeptr[p] .. nodeptr[p+1]-1; nnodes = P.
+ * Fails with KB_ESTRUCTURE if a nonzero couples nodes further than 1 apart. */
+int kb_set_chain(kb_handle h, const int64_t* perm, const int64_t* nodeptr, int64_t nnodes);
+
+/* l-sharding across the ranks of one node: this rank owns the
+ * contiguous node range of rank `rank` out of `nranks`; nccl_unique_id is the
+ * 128-byte ncclUniqueId created by rank 0 (kb_nccl_unique_id) and distributed
+ * by the host (torch.distributed).  Replaces PETSc's MPI row ownership
+ * (solve.py:50, 76) and MUMPS' distributed fronts.  Call after kb_set_chain,
+ * before kb_factor. */
+int kb_nccl_unique_id(void* id128);
+int kb_set_sharding(kb_handle h, int rank, int nranks, const void* nccl_unique_id);
+
+/* STSetUp + KSPSetUp + PCSetUp(LU) numeric factorisation (inside E.solve(),
+ * solve.py:123; K.solve, solve.py:227): T = A - sigma B in chain layout,
+ * block LU with explicit inverses of the Schur blocks. sigma = {re, im}. */
+int kb_factor(kb_handle h, const double* sigma);
+
+/* KSP preonly + PC lu application (K.solve(bvec,x), solve.py:227; ST apply
+ * inside EPSSolve): x = T^{-1} rhs for nrhs right-hand sides, column-major
+ * n x nrhs complex128, original (Kore) ordering. */
+int kb_solve(kb_handle h, const double* rhs, double* x, int nrhs);
+
+/* y = (A - sigma B)^{-1} B x : one application of the Krylov operator
+ * (MatMult + KSPSolve inside EPSSolve).  Exposed for tests and baselines. */
+int kb_apply_op(kb_handle h, const double* x, double* y);
+
+/* y = A x (which=0) or y = B x (which=1), original ordering (MatMult). */
+int kb_matvec(kb_handle h, int which, const double* x, double* y);
+
+/* E.setDimensions / setTolerances / setWhichEigenpairs / setTarget / solve /
+ * getConverged / getEigenpair (solve.py:91-149).  Krylov-Schur on
+ * (A - sigma B)^{-1} B with the shift of the last kb_factor; eigenvalues are
+ * back-transformed lambda = sigma + 1/theta and sorted by `which` relative to
+ * `target`.  ncv = 0 selects SLEPc's default max(2 nev, nev + 15).
+ * v0 may be NULL (seeded random).  On return *nconv pairs (possibly > nev, as
+ * EPSGetConverged, but <= max_pairs) are stored: evals[2*i], evecs column i
+ * (n complex128, unit 2-norm, original ordering), resid[i] =
+ * ||A x - lambda B x|| / (|lambda| ||B x||).  Non-convergence is not an error:
+ * *nconv < nev is returned (solve.py:140-199). */
+int kb_eigs(kb_handle h, int nev, int ncv, double tol, int maxit, int which,
+            const double* target, int true_residual, const double* v0,
+            int max_pairs, double* evals, double* evecs, int* nconv, int* its,
+            double* resid);
+
+/* Statistics of the last kb_factor / kb_solve / kb_eigs, for timing.dat-style
+ * reporting and the roofline: all times are CUDA-event milliseconds on the
+ * handle's stream. */
+typedef struct {
+  double factor_ms;       /* last kb_factor                                   */
+  double solve_ms;        /* last chain solve (fwd+bwd, all refinement steps) */
+  double eigs_ms;         /* last kb_eigs total                               */
+  double eigs_solve_ms;   /* time of chain solves inside last kb_eigs         */
+  int64_t op_applies;     /* operator applications in last kb_eigs            */
+  int64_t solve_calls;    /* chain solves (incl. refinement) in last kb_eigs  */
+  int64_t kernel_launches;/* kernels launched by this handle since creation   */
+  int64_t factor_bytes;   /* device bytes held by the factors                 */
+  double factor_flops;    /* real flops executed by the last kb_factor        */
+  double solve_bytes;     /* algorithmic bytes of one chain solve             */
+  double refine_resid;    /* last relative linear residual seen in refinement */
+} kb_stats;
+int kb_get_stats(kb_handle h, kb_stats* out);
+
+/* Device-resident entry points for the benchmark's HBM-resident leg: vectors
+ * are device pointers (n complex128) in ORIGINAL ordering. */
+int kb_solve_dev(kb_handle h, const double* rhs_dev, double* x_dev, int nrhs);
+int kb_stream(kb_handle h, void** cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KORE_B200_H */

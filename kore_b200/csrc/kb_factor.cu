@@ -1,0 +1,508 @@
+// Numeric factorisation of T = A - sigma B in chain (block-tridiagonal) layout.
+//
+// Replaces: STSetUp (T = A - sigma B, MatAXPY) + KSPSetUp + PCSetUp(LU) numeric
+// phase of MUMPS / SuperLU_DIST, i.e. the dominant cost inside E.solve()
+// (/root/reference/bin/solve.py:123) and K.solve (solve.py:227).
+//
+// Algorithm (block Thomas with explicit inverses):
+//     S_0 = D_0,   M_p = S_p^{-1},   S_{p+1} = D_{p+1} - L_{p+1,p} (M_p U_{p,p+1})
+// D_p / L / U are the diagonal / sub / super blocks of the chain CSR; the
+// couplings L, U are sparse (banded), so the only O(b^3) work per node is the
+// in-place blocked Gauss-Jordan inversion of the dense Schur block S_p with
+// partial (row) pivoting inside the block:  8 b^3 real flops per node.
+#include <math.h>
+#include <stdio.h>
+
+#include "kb_internal.cuh"
+
+// ---------------------------------------------------------------------------
+// T = A - sigma B, equilibration
+// ---------------------------------------------------------------------------
+__global__ void kb_build_T(int64_t nnz, const double2* __restrict__ A, const double2* __restrict__ B,
+                           double2 sigma, double2* __restrict__ T) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nnz) return;
+  double2 t = A[k];
+  zfms(t, sigma, B[k]);
+  T[k] = t;
+}
+
+__device__ __forceinline__ double kb_pow2_recip(double m) {
+  // largest power of two r with r*m < 1 (m > 0), r = 1 for m == 0 / non-finite
+  if (!(m > 0.0) || isinf(m)) return 1.0;
+  int e;
+  frexp(m, &e);
+  return ldexp(1.0, -e);
+}
+
+// one warp per row: r = 2^-e(max|T_row|), row scaled in place
+__global__ void kb_row_scale(int n, const int64_t* __restrict__ rowptr, double2* __restrict__ T,
+                             double* __restrict__ rscale, int enable) {
+  int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  int64_t a = rowptr[row], b = rowptr[row + 1];
+  double m = 0.0;
+  for (int64_t k = a + lane; k < b; k += 32) {
+    double2 v = T[k];
+    m = fmax(m, fmax(fabs(v.x), fabs(v.y)));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  double r = enable ? kb_pow2_recip(m) : 1.0;
+  if (lane == 0) rscale[row] = r;
+  if (r != 1.0)
+    for (int64_t k = a + lane; k < b; k += 32) T[k] = zscale(T[k], r);
+}
+
+__global__ void kb_col_max(int64_t nnz, const int* __restrict__ col, const double2* __restrict__ T,
+                           unsigned long long* __restrict__ maxbits) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nnz) return;
+  double2 v = T[k];
+  double m = fmax(fabs(v.x), fabs(v.y));
+  atomicMax(&maxbits[col[k]], (unsigned long long)__double_as_longlong(m));
+}
+
+__global__ void kb_col_scale_vec(int n, const unsigned long long* __restrict__ maxbits,
+                                 double* __restrict__ cscale, int enable) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double m = __longlong_as_double((long long)maxbits[i]);
+  cscale[i] = enable ? kb_pow2_recip(m) : 1.0;
+}
+
+__global__ void kb_col_apply(int64_t nnz, const int* __restrict__ col, const double* __restrict__ cscale,
+                             double2* __restrict__ T) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nnz) return;
+  double c = cscale[col[k]];
+  if (c != 1.0) T[k] = zscale(T[k], c);
+}
+
+// ---------------------------------------------------------------------------
+// Schur block: S[i,:] = D_p[i,:] - sum_k L_{p,p-1}[i,k] W[k,:]     (one CTA per row)
+// ---------------------------------------------------------------------------
+__global__ void kb_schur_row(double2* __restrict__ S, int b, int o, const double2* __restrict__ W,
+                             int oprev, const int64_t* __restrict__ rowptr,
+                             const int64_t* __restrict__ dstart, const int64_t* __restrict__ ustart,
+                             const int* __restrict__ col, const double2* __restrict__ T) {
+  const int i = blockIdx.x;
+  const int gi = o + i;
+  const int64_t l0 = rowptr[gi], d0 = dstart[gi], u0 = ustart[gi];
+  double2* Srow = S + (size_t)i * b;
+  for (int j = threadIdx.x; j < b; j += blockDim.x) {
+    double2 acc = zmake(0.0, 0.0);
+    if (W) {
+      for (int64_t k = l0; k < d0; ++k) {
+        double2 l = __ldg(&T[k]);
+        int c = __ldg(&col[k]) - oprev;
+        zfms(acc, l, W[(size_t)c * b + j]);
+      }
+    }
+    Srow[j] = acc;
+  }
+  __syncthreads();
+  for (int64_t k = d0 + threadIdx.x; k < u0; k += blockDim.x) {
+    int c = col[k] - o;
+    Srow[c] = zadd(Srow[c], T[k]);
+  }
+}
+
+// W = M_p U_{p,p+1}: W[i,j] = sum_{k in col j of U} M[i,k] U[k,j]   (one CTA per row i)
+__global__ void kb_w_rows(const double2* __restrict__ M, int b, int o, double2* __restrict__ W,
+                          int bnext, int onext, const int64_t* __restrict__ ucptr,
+                          const int* __restrict__ urow, const int64_t* __restrict__ upos,
+                          const double2* __restrict__ T) {
+  extern __shared__ double2 mrow[];
+  const int i = blockIdx.x;
+  for (int j = threadIdx.x; j < b; j += blockDim.x) mrow[j] = M[(size_t)i * b + j];
+  __syncthreads();
+  for (int j = threadIdx.x; j < bnext; j += blockDim.x) {
+    int c = onext + j;
+    double2 acc = zmake(0.0, 0.0);
+    for (int64_t e = ucptr[c]; e < ucptr[c + 1]; ++e) zfma(acc, mrow[urow[e] - o], T[upos[e]]);
+    W[(size_t)i * bnext + j] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Blocked in-place Gauss-Jordan inversion with partial pivoting
+// ---------------------------------------------------------------------------
+// Panel step: columns [k0, k0+nbv) of all n rows live in registers, one (or RPT)
+// row(s) per thread.  On exit Gp (n x NB, row-major) holds the nontrivial columns
+// of the composite Gauss-Jordan transform, srcrow[i] the pre-panel row that now
+// sits at position i, and orig[] the running row permutation of the whole
+// inversion.
+template <int NB, int RPT, int MAXT>
+__global__ void __launch_bounds__(MAXT)
+kb_gj_panel(const double2* __restrict__ Ain, int n, int k0, int nbv, double2* __restrict__ Gp,
+            int* __restrict__ orig, int* __restrict__ srcrow, int* __restrict__ info) {
+  extern __shared__ int s_src[];  // n ints
+  __shared__ double2 prow[NB];
+  __shared__ double2 swp[NB];
+  __shared__ double wv[32];
+  __shared__ int wi[32];
+  const int T = blockDim.x;
+  const int t = threadIdx.x;
+  const int lane = t & 31, wid = t >> 5, nw = (T + 31) >> 5;
+
+  double2 a[RPT][NB];
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    int i = t + r * T;
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+      a[r][j] = (i < n && j < nbv) ? Ain[(size_t)i * n + k0 + j] : zmake(0.0, 0.0);
+  }
+  for (int i = t; i < n; i += T) s_src[i] = i;
+  if (k0 == 0)
+    for (int i = t; i < n; i += T) orig[i] = i;
+  __syncthreads();
+
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    if (k < nbv) {
+      const int gk = k0 + k;
+      // ---- pivot search over positions >= gk
+      double bv = -1.0;
+      int bi = 0x7fffffff;
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) {
+        int i = t + r * T;
+        if (i >= gk && i < n) {
+          double m = zabs2(a[r][k]);
+          if (m > bv || (m == bv && i < bi)) {  // NaN never wins: an all-NaN column is flagged below
+            bv = m;
+            bi = i;
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) {
+          bv = ov;
+          bi = oi;
+        }
+      }
+      if (lane == 0) {
+        wv[wid] = bv;
+        wi[wid] = bi;
+      }
+      __syncthreads();
+      bv = wv[0];
+      bi = wi[0];
+      for (int w = 1; w < nw; ++w) {
+        double ov = wv[w];
+        int oi = wi[w];
+        if (ov > bv || (ov == bv && oi < bi)) {
+          bv = ov;
+          bi = oi;
+        }
+      }
+      const int rp = bi;
+      if (t == 0) {
+        if (!(bv > 0.0) || isinf(bv) || rp >= n) atomicExch(info, gk + 1);
+      }
+      const int rps = (rp < n) ? rp : gk;  // keep going on breakdown; host reports KB_ESINGULAR
+      // ---- publish scaled pivot row, and the row being displaced from position gk
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) {
+        int i = t + r * T;
+        if (i == rps) {
+          double2 pinv = zinv(a[r][k]);
+#pragma unroll
+          for (int j = 0; j < NB; ++j) prow[j] = (j == k) ? pinv : zmul(a[r][j], pinv);
+        }
+        if (i == gk && rps != gk) {
+#pragma unroll
+          for (int j = 0; j < NB; ++j) swp[j] = a[r][j];
+        }
+      }
+      if (t == 0) {
+        int tmp = s_src[gk];
+        s_src[gk] = s_src[rps];
+        s_src[rps] = tmp;
+        int to = orig[gk];
+        orig[gk] = orig[rps];
+        orig[rps] = to;
+      }
+      __syncthreads();
+      // ---- eliminate
+      const double2 pk = prow[k];
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) {
+        int i = t + r * T;
+        if (i < n) {
+          if (i == gk) {
+#pragma unroll
+            for (int j = 0; j < NB; ++j) a[r][j] = prow[j];
+          } else {
+            if (i == rps) {
+#pragma unroll
+              for (int j = 0; j < NB; ++j) a[r][j] = swp[j];
+            }
+            double2 f = a[r][k];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+              if (j != k) zfms(a[r][j], f, prow[j]);
+            }
+            a[r][k] = zneg(zmul(f, pk));
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    int i = t + r * T;
+    if (i < n) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) Gp[(size_t)i * NB + j] = a[r][j];
+    }
+  }
+  for (int i = t; i < n; i += T) srcrow[i] = s_src[i];
+}
+
+// Update step (out of place): for every non-panel column j
+//   Aout[i,j] = (i in panel rows ? 0 : Ain[src(i),j]) + sum_k Gp[i,k] Ain[src(k0+k),j]
+// and Aout[i, panel] = Gp[i,:].   Tile TM x TN per CTA, 256 threads, (TM/16) x 4 per thread.
+template <int NB, int TM>
+__global__ void __launch_bounds__(256)
+kb_gj_update(const double2* __restrict__ Ain, double2* __restrict__ Aout, int n, int k0, int nbv,
+             const double2* __restrict__ Gp, const int* __restrict__ srcrow) {
+  constexpr int TN = 64;
+  constexpr int RM = TM / 16;  // rows per thread
+  __shared__ double2 Gs[TM][NB];
+  __shared__ double2 Rs[NB][TN];
+  __shared__ int src_s[TM];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int row0 = blockIdx.y * TM, col0 = blockIdx.x * TN;
+
+  for (int e = tid; e < TM * NB; e += 256) {
+    int i = e / NB, k = e % NB;
+    int gi = row0 + i;
+    Gs[i][k] = (gi < n && k < nbv) ? Gp[(size_t)gi * NB + k] : zmake(0.0, 0.0);
+  }
+  for (int e = tid; e < NB * TN; e += 256) {
+    int k = e / TN, j = e % TN;
+    int gj = col0 + j;
+    Rs[k][j] = (k < nbv && gj < n) ? Ain[(size_t)srcrow[k0 + k] * n + gj] : zmake(0.0, 0.0);
+  }
+  for (int i = tid; i < TM; i += 256) src_s[i] = (row0 + i < n) ? srcrow[row0 + i] : 0;
+  __syncthreads();
+
+  double2 acc[RM][4];
+#pragma unroll
+  for (int a = 0; a < RM; ++a) {
+    int i = ty + 16 * a;
+    int gi = row0 + i;
+    bool prow_ = (gi >= k0 && gi < k0 + nbv);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      int gj = col0 + tx + 16 * c;
+      acc[a][c] = (gi < n && gj < n && !prow_) ? Ain[(size_t)src_s[i] * n + gj] : zmake(0.0, 0.0);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    double2 g[RM], rr[4];
+#pragma unroll
+    for (int a = 0; a < RM; ++a) g[a] = Gs[ty + 16 * a][k];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) rr[c] = Rs[k][tx + 16 * c];
+#pragma unroll
+    for (int a = 0; a < RM; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) zfma(acc[a][c], g[a], rr[c]);
+  }
+#pragma unroll
+  for (int a = 0; a < RM; ++a) {
+    int i = ty + 16 * a;
+    int gi = row0 + i;
+    if (gi >= n) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      int gj = col0 + tx + 16 * c;
+      if (gj >= n) continue;
+      double2 v = acc[a][c];
+      if (gj >= k0 && gj < k0 + nbv) v = Gs[i][gj - k0];
+      Aout[(size_t)gi * n + gj] = v;
+    }
+  }
+}
+
+// M[r, orig[i]] = X[r, i]  (undo the row pivoting as a column permutation)
+__global__ void kb_store_inverse(const double2* __restrict__ X, int n, const int* __restrict__ orig,
+                                 double2* __restrict__ M) {
+  int r = blockIdx.x;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) M[(size_t)r * n + orig[i]] = X[(size_t)r * n + i];
+}
+
+// ---------------------------------------------------------------------------
+// host drivers
+// ---------------------------------------------------------------------------
+template <int NB, int RPT, int MAXT>
+static void launch_panel(kb_context* h, const double2* in, int n, int k0, int nbv) {
+  int T = (n + RPT - 1) / RPT;
+  T = ((T + 31) / 32) * 32;
+  if (T > MAXT) T = MAXT;
+  kb_gj_panel<NB, RPT, MAXT><<<1, T, n * sizeof(int), h->stream>>>(in, n, k0, nbv, h->d_Gp.p, h->d_orig.p,
+                                                                  h->d_srcrow.p, h->d_info.p);
+}
+
+template <int NB>
+static void launch_update(kb_context* h, const double2* in, double2* out, int n, int k0, int nbv) {
+  constexpr int TM = 32;
+  dim3 grid((n + 63) / 64, (n + TM - 1) / TM);
+  kb_gj_update<NB, TM><<<grid, 256, 0, h->stream>>>(in, out, n, k0, nbv, h->d_Gp.p, h->d_srcrow.p);
+}
+
+int kbi_panel_width(const kb_context* h, int n) {
+  if (h->opt_panel == 4 || h->opt_panel == 8 || h->opt_panel == 16) {
+    int nb = h->opt_panel;
+    if (nb == 16 && n <= 640) return 16;
+    if (nb >= 8 && n <= 1024) return 8;
+    return 4;
+  }
+  if (n <= 640) return 16;
+  if (n <= 1024) return 8;
+  return 4;
+}
+
+// In-place inverse of the n x n row-major matrix in S0 (S1 = scratch of the same
+// size).  Returns the buffer that holds (Pi S)^{-1}; d_orig holds Pi.
+static int gj_invert(kb_context* h, double2* S0, double2* S1, int n, double2** result) {
+  if (n > 4096) return kb_fail(h, KB_EINVAL, "chain node of %d rows exceeds the supported 4096", n);
+  const int NB = kbi_panel_width(h, n);
+  double2* in = S0;
+  double2* out = S1;
+  for (int k0 = 0; k0 < n; k0 += NB) {
+    int nbv = n - k0 < NB ? n - k0 : NB;
+    if (NB == 16) {
+      launch_panel<16, 1, 640>(h, in, n, k0, nbv);
+      launch_update<16>(h, in, out, n, k0, nbv);
+    } else if (NB == 8) {
+      launch_panel<8, 1, 1024>(h, in, n, k0, nbv);
+      launch_update<8>(h, in, out, n, k0, nbv);
+    } else {
+      if (n <= 1024)
+        launch_panel<4, 1, 1024>(h, in, n, k0, nbv);
+      else if (n <= 2048)
+        launch_panel<4, 2, 1024>(h, in, n, k0, nbv);
+      else
+        launch_panel<4, 4, 1024>(h, in, n, k0, nbv);
+      launch_update<4>(h, in, out, n, k0, nbv);
+    }
+    h->launches += 2;
+    double2* t = in;
+    in = out;
+    out = t;
+  }
+  KB_LAUNCH_CHECK(h);
+  *result = in;
+  return KB_OK;
+}
+
+int kbi_factor(kb_context* h, zcomplex sigma) {
+  if (!h->chain_set) return kb_fail(h, KB_EINVAL, "kb_set_chain must be called before kb_factor");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const int64_t n = h->n, nnz = h->nnz, P = h->P;
+  const int64_t bmax = h->bmax;
+  h->factored = false;
+  h->sigma = sigma;
+
+  cudaEvent_t e0, e1;
+  KB_CUDA(h, cudaEventCreate(&e0));
+  KB_CUDA(h, cudaEventCreate(&e1));
+  KB_CUDA(h, cudaEventRecord(e0, s));
+
+  // ---- T = A - sigma B, equilibrated
+  {
+    int thr = 256;
+    int64_t blk = (nnz + thr - 1) / thr;
+    kb_build_T<<<(unsigned)blk, thr, 0, s>>>(nnz, h->d_Aval.p, h->d_Bval.p,
+                                             zmake(sigma.real(), sigma.imag()), h->d_Tval.p);
+    int64_t wblk = (n * 32 + thr - 1) / thr;
+    kb_row_scale<<<(unsigned)wblk, thr, 0, s>>>((int)n, h->d_rowptr.p, h->d_Tval.p, h->d_rscale.p,
+                                                h->opt_equil);
+    KB_CUDA(h, cudaMemsetAsync(h->d_maxbits.p, 0, n * sizeof(unsigned long long), s));
+    kb_col_max<<<(unsigned)blk, thr, 0, s>>>(nnz, h->d_col.p, h->d_Tval.p, h->d_maxbits.p);
+    kb_col_scale_vec<<<(unsigned)((n + thr - 1) / thr), thr, 0, s>>>((int)n, h->d_maxbits.p,
+                                                                     h->d_cscale.p, h->opt_equil);
+    kb_col_apply<<<(unsigned)blk, thr, 0, s>>>(nnz, h->d_col.p, h->d_cscale.p, h->d_Tval.p);
+    h->launches += 5;
+    KB_LAUNCH_CHECK(h);
+  }
+
+  // ---- storage for the explicit inverses
+  h->Moff.assign(P + 1, 0);
+  for (int64_t p = 0; p < P; ++p) {
+    int64_t b = h->nodeptr[p + 1] - h->nodeptr[p];
+    h->Moff[p + 1] = h->Moff[p] + b * b;
+  }
+  if (h->d_M.alloc((size_t)h->Moff[P]) != cudaSuccess)
+    return kb_fail(h, KB_ENOMEM, "cannot allocate %.2f GB for the chain factors",
+                   h->Moff[P] * 16.0 / 1e9);
+  KB_CUDA(h, h->d_S0.alloc((size_t)bmax * bmax));
+  KB_CUDA(h, h->d_S1.alloc((size_t)bmax * bmax));
+  KB_CUDA(h, h->d_W.alloc((size_t)bmax * bmax));
+  KB_CUDA(h, h->d_Gp.alloc((size_t)bmax * 16));
+  KB_CUDA(h, h->d_orig.alloc(bmax));
+  KB_CUDA(h, h->d_srcrow.alloc(bmax));
+  KB_CUDA(h, h->d_info.alloc(1));
+  KB_CUDA(h, cudaMemsetAsync(h->d_info.p, 0, sizeof(int), s));
+
+  double flops = 0.0;
+  for (int64_t p = 0; p < P; ++p) {
+    const int o = (int)h->nodeptr[p];
+    const int b = (int)(h->nodeptr[p + 1] - h->nodeptr[p]);
+    const int oprev = p > 0 ? (int)h->nodeptr[p - 1] : 0;
+    kb_schur_row<<<b, 128, 0, s>>>(h->d_S0.p, b, o, p > 0 ? h->d_W.p : nullptr, oprev, h->d_rowptr.p,
+                                   h->d_dstart.p, h->d_ustart.p, h->d_col.p, h->d_Tval.p);
+    h->launches++;
+    double2* X = nullptr;
+    KB_TRY(gj_invert(h, h->d_S0.p, h->d_S1.p, b, &X));
+    double2* Mp = h->d_M.p + h->Moff[p];
+    kb_store_inverse<<<b, 128, 0, s>>>(X, b, h->d_orig.p, Mp);
+    h->launches++;
+    flops += 8.0 * (double)b * b * b;
+    if (p + 1 < P) {
+      const int onext = (int)h->nodeptr[p + 1];
+      const int bnext = (int)(h->nodeptr[p + 2] - h->nodeptr[p + 1]);
+      kb_w_rows<<<b, 128, b * sizeof(double2), s>>>(Mp, b, o, h->d_W.p, bnext, onext, h->d_ucptr.p,
+                                                    h->d_urow.p, h->d_upos.p, h->d_Tval.p);
+      h->launches++;
+    }
+    KB_LAUNCH_CHECK(h);
+  }
+  KB_CUDA(h, cudaEventRecord(e1, s));
+  int info = 0;
+  KB_CUDA(h, cudaMemcpyAsync(&info, h->d_info.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  KB_CUDA(h, cudaStreamSynchronize(s));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  h->stats.factor_ms = ms;
+  h->stats.factor_flops = flops;
+  h->stats.factor_bytes = h->Moff[P] * 16;
+  if (info != 0)
+    return kb_fail(h, KB_ESINGULAR,
+                   "zero or non-finite pivot in a Schur block (A - sigma B is singular to working "
+                   "precision at this shift)");
+  h->factored = true;
+  return KB_OK;
+}
+
+extern "C" int kb_factor(kb_handle h, const double* sigma) {
+  if (!h || !sigma) return KB_EINVAL;
+  if (h->nranks > 1) {
+    return kbi_factor_sharded(h, zcomplex(sigma[0], sigma[1]));
+  }
+  return kbi_factor(h, zcomplex(sigma[0], sigma[1]));
+}

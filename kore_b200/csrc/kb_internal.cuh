@@ -1,0 +1,227 @@
+// Internal declarations shared by the translation units of libkoreb200.so.
+// Not part of the C ABI (see include/kore_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <complex>
+#include <string>
+#include <vector>
+
+#include "../../include/kore_b200.h"
+
+typedef std::complex<double> zcomplex;
+
+// ---------------------------------------------------------------------------
+// complex128 device arithmetic on double2 (x = re, y = im)
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ double2 zmake(double re, double im) { return make_double2(re, im); }
+__host__ __device__ __forceinline__ double2 zadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ double2 zsub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ double2 zneg(double2 a) { return make_double2(-a.x, -a.y); }
+__host__ __device__ __forceinline__ double2 zconj(double2 a) { return make_double2(a.x, -a.y); }
+__host__ __device__ __forceinline__ double2 zmul(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__host__ __device__ __forceinline__ double2 zscale(double2 a, double s) { return make_double2(a.x * s, a.y * s); }
+// acc += a*b  (4 real FMAs)
+__device__ __forceinline__ void zfma(double2& acc, double2 a, double2 b) {
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y);
+  acc.y = fma(a.y, b.x, acc.y);
+}
+// acc -= a*b
+__device__ __forceinline__ void zfms(double2& acc, double2 a, double2 b) {
+  acc.x = fma(-a.x, b.x, acc.x);
+  acc.x = fma(a.y, b.y, acc.x);
+  acc.y = fma(-a.x, b.y, acc.y);
+  acc.y = fma(-a.y, b.x, acc.y);
+}
+// acc += conj(a)*b
+__device__ __forceinline__ void zfmac(double2& acc, double2 a, double2 b) {
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.x = fma(a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y);
+  acc.y = fma(-a.y, b.x, acc.y);
+}
+__host__ __device__ __forceinline__ double zabs2(double2 a) { return a.x * a.x + a.y * a.y; }
+__host__ __device__ __forceinline__ double2 zinv(double2 p) {
+  // scaled reciprocal (avoids overflow of |p|^2)
+  double s = fmax(fabs(p.x), fabs(p.y));
+  double xr = p.x / s, xi = p.y / s;
+  double d = (xr * xr + xi * xi) * s;
+  return make_double2(xr / d, -xi / d);
+}
+
+// ---------------------------------------------------------------------------
+// error handling
+// ---------------------------------------------------------------------------
+struct kb_context;
+int kb_fail(kb_context* h, int code, const char* fmt, ...);
+
+#define KB_CUDA(h, expr)                                                                   \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return kb_fail((h), KB_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                     __FILE__, __LINE__);                                                  \
+  } while (0)
+
+#define KB_TRY(expr)              \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != KB_OK) return _rc; \
+  } while (0)
+
+#define KB_LAUNCH_CHECK(h)                                                                     \
+  do {                                                                                         \
+    cudaError_t _e = cudaGetLastError();                                                       \
+    if (_e != cudaSuccess)                                                                     \
+      return kb_fail((h), KB_ECUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                     __FILE__, __LINE__);                                                      \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// device buffer that frees itself
+// ---------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t count = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    count = 0;
+  }
+  cudaError_t alloc(size_t n) {
+    if (n <= count && p) return cudaSuccess;
+    release();
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
+    if (e == cudaSuccess) count = n;
+    return e;
+  }
+  size_t bytes() const { return count * sizeof(T); }
+};
+
+struct HostCSR {
+  int64_t n = 0;
+  std::vector<int64_t> indptr;
+  std::vector<int64_t> indices;
+  std::vector<zcomplex> values;
+  bool present = false;
+};
+
+// One contiguous run of chain nodes factored by block-Thomas on this GPU.
+struct kb_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+
+  // options
+  int opt_equil = 1;
+  int opt_refine = 1;
+  int opt_refine_eigs = 0;
+  int opt_purify = 1;
+  int64_t opt_seed = 1;
+  int opt_panel = 0;
+
+  // pencil as given (host, original ordering)
+  int64_t n = 0;
+  HostCSR A, B;
+  bool b_is_complex = false;
+
+  // chain
+  bool chain_set = false;
+  int64_t P = 0;
+  std::vector<int64_t> nodeptr;  // P+1
+  std::vector<int64_t> perm;     // chain position -> original index
+  int64_t bmax = 0;
+
+  // device: permutation
+  DevBuf<int> d_perm;  // n
+
+  // device: chain CSR on the union pattern of A and B (rows sorted by chain column)
+  int64_t nnz = 0;
+  DevBuf<int64_t> d_rowptr;  // n+1
+  DevBuf<int> d_col;         // nnz (chain column)
+  DevBuf<int> d_rowidx;      // nnz (chain row of each entry)
+  DevBuf<double2> d_Aval;    // nnz
+  DevBuf<double2> d_Bval;    // nnz (B scattered on the union pattern; zero where absent)
+  DevBuf<double2> d_Tval;    // nnz (equilibrated A - sigma B)
+  DevBuf<int64_t> d_dstart;  // n: first entry of row in its own node
+  DevBuf<int64_t> d_ustart;  // n: first entry of row in the next node
+  // U blocks (row node p, column node p+1) by column
+  int64_t nnzU = 0;
+  DevBuf<int64_t> d_ucptr;  // n+1
+  DevBuf<int> d_urow;       // nnzU chain row
+  DevBuf<int64_t> d_upos;   // nnzU position in d_Tval
+  // B alone in chain order for the Arnoldi SpMV
+  int64_t nnzB = 0;
+  DevBuf<int64_t> d_browptr;
+  DevBuf<int> d_bcol;
+  DevBuf<double> d_bval_r;    // real B (assemble.py writes float64)
+  DevBuf<double2> d_bval_c;   // complex B
+  // A alone in chain order for true residuals
+  int64_t nnzA = 0;
+  DevBuf<int64_t> d_arowptr;
+  DevBuf<int> d_acol;
+  DevBuf<double2> d_aval;
+
+  // equilibration (powers of two), chain order
+  DevBuf<double> d_rscale, d_cscale;
+  DevBuf<unsigned long long> d_maxbits;  // n scratch for column maxima
+
+  // factors
+  bool factored = false;
+  zcomplex sigma = 0;
+  std::vector<int64_t> Moff;  // P+1 offsets (in complex elements) of M_p in d_M
+  DevBuf<double2> d_M;
+  // factor workspaces
+  DevBuf<double2> d_S0, d_S1, d_W, d_Gp;
+  DevBuf<int> d_orig, d_srcrow, d_piv, d_info;
+
+  // solve workspaces (chain order, scaled space)
+  DevBuf<double2> d_r, d_y, d_res, d_x0, d_in, d_out;
+  DevBuf<double> d_partial;
+
+  // Krylov workspaces
+  DevBuf<double2> d_V;  // n x (ncv+1), column-major
+  DevBuf<double2> d_w, d_w2, d_h, d_hpart, d_Q;
+
+  // sharding
+  int rank = 0, nranks = 1;
+  void* nccl_comm = nullptr;
+
+  kb_stats stats;
+  int64_t launches = 0;
+
+  kb_context() { memset(&stats, 0, sizeof(stats)); }
+};
+
+static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+// ---- kb_factor.cu
+int kbi_factor(kb_context* h, zcomplex sigma);
+// ---- kb_solve.cu
+//  chain solve in scaled/permuted space: d_y <- T'^{-1} d_r (d_r preserved)
+int kbi_chain_solve(kb_context* h, const double2* r_dev, double2* x_dev, int refine);
+//  full operator on chain-ordered device vectors: out = C T'^{-1} R B in
+int kbi_apply_op_chain(kb_context* h, const double2* in_chain, double2* out_chain, int refine);
+int kbi_spmv_B_chain(kb_context* h, const double2* x, double2* y, bool scale_rows);
+int kbi_spmv_A_chain(kb_context* h, const double2* x, double2* y);
+int kbi_to_chain(kb_context* h, const double2* x_orig_dev, double2* x_chain_dev);
+int kbi_from_chain(kb_context* h, const double2* x_chain_dev, double2* x_orig_dev);
+int kbi_solve_workspace(kb_context* h);
+// ---- kb_shard.cu
+int kbi_factor_sharded(kb_context* h, zcomplex sigma);
+int kbi_chain_solve_sharded(kb_context* h, const double2* r_dev, double2* x_dev, int refine);
+void kbi_nccl_destroy(kb_context* h);
+__global__ void kb_norm2_partial(int n, const double2* __restrict__ v, double* __restrict__ out);

@@ -1,0 +1,357 @@
+// Context life-cycle, pencil ingestion and the chain (l-major) layout build.
+//
+// Replaces: PETSc Mat create / setValuesCSR / assembly for A and B
+// (/root/reference/bin/solve.py:43-59, 69-85) and the analysis (ordering)
+// phase of the sparse direct solver (PCSetUp(LU) inside E.solve(),
+// solve.py:123).  The ordering is not computed: the caller hands in Kore's own
+// l-major chain (kore_b200/chain.py), which makes A - sigma B block tridiagonal.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <thread>
+
+#include "kb_internal.cuh"
+
+int kb_fail(kb_context* h, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  return code;
+}
+
+static thread_local std::string g_create_err;
+
+extern "C" int kb_create(kb_handle* out, int device) {
+  if (!out) return KB_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_err = "no CUDA device visible (libkoreb200 has no CPU fallback)";
+    return KB_ENODEVICE;
+  }
+  if (device < 0 || device >= ndev) {
+    g_create_err = "device index out of range";
+    return KB_ENODEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) {
+    g_create_err = "device is not sm_100 class; this library is built for sm_100a only";
+    return KB_ENODEVICE;
+  }
+  kb_context* h = new kb_context();
+  h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    g_create_err = "cannot create CUDA stream";
+    delete h;
+    return KB_ECUDA;
+  }
+  *out = h;
+  return KB_OK;
+}
+
+extern "C" int kb_destroy(kb_handle h) {
+  if (!h) return KB_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) {
+    cudaStreamSynchronize(h->stream);
+    cudaStreamDestroy(h->stream);
+  }
+  kbi_nccl_destroy(h);
+  delete h;
+  return KB_OK;
+}
+
+extern "C" const char* kb_last_error(kb_handle h) {
+  if (!h) return g_create_err.c_str();
+  return h->err.c_str();
+}
+
+extern "C" int kb_set_option(kb_handle h, int option, int64_t value) {
+  if (!h) return KB_EINVAL;
+  switch (option) {
+    case KB_OPT_EQUILIBRATE: h->opt_equil = value != 0; break;
+    case KB_OPT_REFINE: h->opt_refine = (int)std::max<int64_t>(0, value); break;
+    case KB_OPT_PURIFY: h->opt_purify = value != 0; break;
+    case KB_OPT_SEED: h->opt_seed = value; break;
+    case KB_OPT_PANEL: h->opt_panel = (int)value; break;
+    case 6: h->opt_refine_eigs = (int)std::max<int64_t>(0, value); break;
+    default: return kb_fail(h, KB_EINVAL, "unknown option %d", option);
+  }
+  return KB_OK;
+}
+
+extern "C" int kb_get_stats(kb_handle h, kb_stats* out) {
+  if (!h || !out) return KB_EINVAL;
+  h->stats.kernel_launches = h->launches;
+  *out = h->stats;
+  return KB_OK;
+}
+
+extern "C" int kb_stream(kb_handle h, void** s) {
+  if (!h || !s) return KB_EINVAL;
+  *s = (void*)h->stream;
+  return KB_OK;
+}
+
+static int ingest(kb_context* h, HostCSR& M, int64_t n, int index_bytes, const void* indptr,
+                  const void* indices, const void* values, bool is_complex, const char* name) {
+  M.n = n;
+  M.indptr.resize(n + 1);
+  if (index_bytes == 4) {
+    const int32_t* p = (const int32_t*)indptr;
+    for (int64_t i = 0; i <= n; ++i) M.indptr[i] = p[i];
+  } else {
+    const int64_t* p = (const int64_t*)indptr;
+    for (int64_t i = 0; i <= n; ++i) M.indptr[i] = p[i];
+  }
+  if (M.indptr[0] != 0) return kb_fail(h, KB_EINVAL, "%s: indptr[0] != 0", name);
+  for (int64_t i = 0; i < n; ++i)
+    if (M.indptr[i + 1] < M.indptr[i]) return kb_fail(h, KB_EINVAL, "%s: indptr not monotone", name);
+  int64_t nnz = M.indptr[n];
+  M.indices.resize(nnz);
+  if (index_bytes == 4) {
+    const int32_t* p = (const int32_t*)indices;
+    for (int64_t k = 0; k < nnz; ++k) M.indices[k] = p[k];
+  } else {
+    const int64_t* p = (const int64_t*)indices;
+    for (int64_t k = 0; k < nnz; ++k) M.indices[k] = p[k];
+  }
+  for (int64_t k = 0; k < nnz; ++k)
+    if (M.indices[k] < 0 || M.indices[k] >= n)
+      return kb_fail(h, KB_EINVAL, "%s: column index out of range", name);
+  M.values.resize(nnz);
+  if (is_complex) {
+    const double* v = (const double*)values;
+    for (int64_t k = 0; k < nnz; ++k) M.values[k] = zcomplex(v[2 * k], v[2 * k + 1]);
+  } else {
+    const double* v = (const double*)values;
+    for (int64_t k = 0; k < nnz; ++k) M.values[k] = zcomplex(v[k], 0.0);
+  }
+  M.present = true;
+  return KB_OK;
+}
+
+extern "C" int kb_set_pencil(kb_handle h, int64_t n, int index_bytes, const void* a_indptr,
+                             const void* a_indices, const double* a_values, const void* b_indptr,
+                             const void* b_indices, const void* b_values, int b_is_complex) {
+  if (!h) return KB_EINVAL;
+  if (n <= 0 || n > 0x7fffffff) return kb_fail(h, KB_EINVAL, "n out of range");
+  if (index_bytes != 4 && index_bytes != 8) return kb_fail(h, KB_EINVAL, "index_bytes must be 4 or 8");
+  if (!a_indptr || !a_indices || !a_values) return kb_fail(h, KB_EINVAL, "A is required");
+  h->n = n;
+  h->chain_set = false;
+  h->factored = false;
+  KB_TRY(ingest(h, h->A, n, index_bytes, a_indptr, a_indices, a_values, true, "A"));
+  h->B = HostCSR();
+  h->b_is_complex = b_is_complex != 0;
+  if (b_indptr) {
+    if (!b_indices || !b_values) return kb_fail(h, KB_EINVAL, "B indices/values missing");
+    KB_TRY(ingest(h, h->B, n, index_bytes, b_indptr, b_indices, b_values, b_is_complex != 0, "B"));
+  }
+  return KB_OK;
+}
+
+namespace {
+struct Ent {
+  int col;
+  zcomplex a, b;
+  bool ina, inb;
+};
+
+template <typename T>
+cudaError_t upload(DevBuf<T>& d, const std::vector<T>& v, cudaStream_t s) {
+  cudaError_t e = d.alloc(v.size());
+  if (e != cudaSuccess) return e;
+  if (v.empty()) return cudaSuccess;
+  return cudaMemcpyAsync(d.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+}
+}  // namespace
+
+extern "C" int kb_set_chain(kb_handle h, const int64_t* perm, const int64_t* nodeptr, int64_t nnodes) {
+  if (!h) return KB_EINVAL;
+  if (!h->A.present) return kb_fail(h, KB_EINVAL, "kb_set_pencil must be called first");
+  const int64_t n = h->n;
+  if (!perm || !nodeptr || nnodes <= 0) return kb_fail(h, KB_EINVAL, "bad chain arguments");
+  if (nodeptr[0] != 0 || nodeptr[nnodes] != n) return kb_fail(h, KB_EINVAL, "nodeptr must span [0,n]");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  h->P = nnodes;
+  h->nodeptr.assign(nodeptr, nodeptr + nnodes + 1);
+  h->perm.assign(perm, perm + n);
+  h->bmax = 0;
+  for (int64_t p = 0; p < nnodes; ++p) {
+    int64_t b = nodeptr[p + 1] - nodeptr[p];
+    if (b <= 0) return kb_fail(h, KB_EINVAL, "empty chain node %lld", (long long)p);
+    h->bmax = std::max(h->bmax, b);
+  }
+  std::vector<int64_t> iperm(n, -1);
+  for (int64_t k = 0; k < n; ++k) {
+    if (perm[k] < 0 || perm[k] >= n || iperm[perm[k]] != -1)
+      return kb_fail(h, KB_EINVAL, "perm is not a permutation");
+    iperm[perm[k]] = k;
+  }
+  std::vector<int> node_of(n);
+  for (int64_t p = 0; p < nnodes; ++p)
+    for (int64_t i = nodeptr[p]; i < nodeptr[p + 1]; ++i) node_of[i] = (int)p;
+
+  // ---- union pattern, chain order, rows sorted by chain column (host threads)
+  const HostCSR& A = h->A;
+  const HostCSR& B = h->B;
+  std::vector<int64_t> rowcount(n, 0);
+  std::vector<std::vector<Ent>> rows(n);
+  int nthr = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  std::vector<int> bad(nthr, 0);
+  auto work = [&](int t) {
+    std::vector<Ent> tmp;
+    for (int64_t i = t; i < n; i += nthr) {
+      int64_t o = perm[i];
+      tmp.clear();
+      for (int64_t k = A.indptr[o]; k < A.indptr[o + 1]; ++k)
+        tmp.push_back(Ent{(int)iperm[A.indices[k]], A.values[k], zcomplex(0, 0), true, false});
+      if (B.present)
+        for (int64_t k = B.indptr[o]; k < B.indptr[o + 1]; ++k)
+          tmp.push_back(Ent{(int)iperm[B.indices[k]], zcomplex(0, 0), B.values[k], false, true});
+      std::stable_sort(tmp.begin(), tmp.end(), [](const Ent& x, const Ent& y) { return x.col < y.col; });
+      std::vector<Ent>& out = rows[i];
+      out.clear();
+      for (const Ent& e : tmp) {
+        if (!out.empty() && out.back().col == e.col) {
+          out.back().a += e.a;
+          out.back().b += e.b;
+          out.back().ina |= e.ina;
+          out.back().inb |= e.inb;
+        } else {
+          out.push_back(e);
+        }
+        int d = node_of[e.col] - node_of[i];
+        if (d > 1 || d < -1) bad[t] = 1;
+      }
+      rowcount[i] = (int64_t)out.size();
+    }
+  };
+  {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthr; ++t) pool.emplace_back(work, t);
+    for (auto& th : pool) th.join();
+  }
+  for (int t = 0; t < nthr; ++t)
+    if (bad[t])
+      return kb_fail(h, KB_ESTRUCTURE,
+                     "pencil is not block tridiagonal under the given chain (a nonzero couples nodes "
+                     "more than one apart)");
+
+  std::vector<int64_t> rowptr(n + 1, 0);
+  for (int64_t i = 0; i < n; ++i) rowptr[i + 1] = rowptr[i] + rowcount[i];
+  const int64_t nnz = rowptr[n];
+  h->nnz = nnz;
+  std::vector<int> col(nnz), rowidx(nnz);
+  std::vector<double2> aval(nnz), bval(nnz);
+  std::vector<int64_t> dstart(n), ustart(n);
+  std::vector<int64_t> ucount(n + 1, 0);
+  int64_t nnzA = 0, nnzB = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    int64_t k = rowptr[i];
+    int p = node_of[i];
+    int64_t ds = -1, us = -1;
+    for (const Ent& e : rows[i]) {
+      col[k] = e.col;
+      rowidx[k] = (int)i;
+      aval[k] = make_double2(e.a.real(), e.a.imag());
+      bval[k] = make_double2(e.b.real(), e.b.imag());
+      int q = node_of[e.col];
+      if (q >= p && ds < 0) ds = k;
+      if (q > p && us < 0) us = k;
+      if (q > p) ucount[e.col + 1]++;
+      nnzA += e.ina;
+      nnzB += e.inb;
+      ++k;
+    }
+    if (us < 0) us = rowptr[i + 1];
+    if (ds < 0) ds = us;
+    dstart[i] = ds;
+    ustart[i] = us;
+  }
+  // U by column
+  for (int64_t c = 0; c < n; ++c) ucount[c + 1] += ucount[c];
+  const int64_t nnzU = ucount[n];
+  h->nnzU = nnzU;
+  std::vector<int> urow(nnzU);
+  std::vector<int64_t> upos(nnzU);
+  {
+    std::vector<int64_t> fill(ucount.begin(), ucount.end() - 1);
+    for (int64_t i = 0; i < n; ++i)
+      for (int64_t k = ustart[i]; k < rowptr[i + 1]; ++k) {
+        int64_t dst = fill[col[k]]++;
+        urow[dst] = (int)i;
+        upos[dst] = k;
+      }
+  }
+  // A alone and B alone (chain order) for SpMV
+  std::vector<int64_t> arowptr(n + 1, 0), browptr(n + 1, 0);
+  std::vector<int> acol, bcol;
+  std::vector<double2> av, bvc;
+  std::vector<double> bvr;
+  acol.reserve(nnzA);
+  av.reserve(nnzA);
+  bcol.reserve(nnzB);
+  for (int64_t i = 0; i < n; ++i) {
+    for (const Ent& e : rows[i]) {
+      if (e.ina) {
+        acol.push_back(e.col);
+        av.push_back(make_double2(e.a.real(), e.a.imag()));
+      }
+      if (e.inb) {
+        bcol.push_back(e.col);
+        if (h->b_is_complex)
+          bvc.push_back(make_double2(e.b.real(), e.b.imag()));
+        else
+          bvr.push_back(e.b.real());
+      }
+    }
+    arowptr[i + 1] = (int64_t)acol.size();
+    browptr[i + 1] = (int64_t)bcol.size();
+    std::vector<Ent>().swap(rows[i]);
+  }
+  h->nnzA = (int64_t)acol.size();
+  h->nnzB = (int64_t)bcol.size();
+
+  std::vector<int> perm32(n);
+  for (int64_t k = 0; k < n; ++k) perm32[k] = (int)perm[k];
+
+  cudaStream_t s = h->stream;
+  KB_CUDA(h, upload(h->d_perm, perm32, s));
+  KB_CUDA(h, upload(h->d_rowptr, rowptr, s));
+  KB_CUDA(h, upload(h->d_col, col, s));
+  KB_CUDA(h, upload(h->d_rowidx, rowidx, s));
+  KB_CUDA(h, upload(h->d_Aval, aval, s));
+  KB_CUDA(h, upload(h->d_Bval, bval, s));
+  KB_CUDA(h, h->d_Tval.alloc(nnz));
+  KB_CUDA(h, upload(h->d_dstart, dstart, s));
+  KB_CUDA(h, upload(h->d_ustart, ustart, s));
+  KB_CUDA(h, upload(h->d_ucptr, ucount, s));
+  KB_CUDA(h, upload(h->d_urow, urow, s));
+  KB_CUDA(h, upload(h->d_upos, upos, s));
+  KB_CUDA(h, upload(h->d_arowptr, arowptr, s));
+  KB_CUDA(h, upload(h->d_acol, acol, s));
+  KB_CUDA(h, upload(h->d_aval, av, s));
+  KB_CUDA(h, upload(h->d_browptr, browptr, s));
+  KB_CUDA(h, upload(h->d_bcol, bcol, s));
+  if (h->b_is_complex)
+    KB_CUDA(h, upload(h->d_bval_c, bvc, s));
+  else
+    KB_CUDA(h, upload(h->d_bval_r, bvr, s));
+  KB_CUDA(h, h->d_rscale.alloc(n));
+  KB_CUDA(h, h->d_cscale.alloc(n));
+  KB_CUDA(h, h->d_maxbits.alloc(n));
+  KB_CUDA(h, cudaStreamSynchronize(s));
+
+  h->chain_set = true;
+  h->factored = false;
+  return KB_OK;
+}

@@ -1,0 +1,344 @@
+// Application of the factored chain: forward / backward block substitution,
+// iterative refinement, the B (and A) SpMV and the public solve entry points.
+//
+// Replaces: KSP preonly + PC lu solve phase of MUMPS (K.solve(bvec,x),
+// /root/reference/bin/solve.py:227, and every ST application inside
+// E.solve(), solve.py:123) and PETSc MatMult (w = B v inside EPSSolve).
+//
+//   forward :  y_p = M_p ( r_p - L_{p,p-1} y_{p-1} )          p = 0 .. P-1
+//   backward:  x_p = y_p - M_p ( U_{p,p+1} x_{p+1} )          p = P-2 .. 0
+// Both sweeps are HBM-bound: each reads every explicit inverse M_p once
+// (16 b_p^2 bytes per node per sweep).
+#include <math.h>
+
+#include "kb_internal.cuh"
+
+#define KB_NODE_WARPS 4
+
+// MODE 0: forward, MODE 1: backward (in place on y).
+template <int MODE>
+__global__ void __launch_bounds__(KB_NODE_WARPS * 32)
+kb_node_apply(const double2* __restrict__ M, int b, int o, const double2* __restrict__ r,
+              double2* __restrict__ y, const int64_t* __restrict__ rowptr,
+              const int64_t* __restrict__ dstart, const int64_t* __restrict__ ustart,
+              const int* __restrict__ col, const double2* __restrict__ T) {
+  extern __shared__ double2 tvec[];  // b entries
+  for (int i = threadIdx.x; i < b; i += blockDim.x) {
+    int gi = o + i;
+    double2 acc;
+    if (MODE == 0) {
+      acc = r[gi];
+      for (int64_t k = rowptr[gi], e = dstart[gi]; k < e; ++k) zfms(acc, T[k], y[col[k]]);
+    } else {
+      acc = zmake(0.0, 0.0);
+      for (int64_t k = ustart[gi], e = rowptr[gi + 1]; k < e; ++k) zfma(acc, T[k], y[col[k]]);
+    }
+    tvec[i] = acc;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int row = blockIdx.x * KB_NODE_WARPS + wid;
+  if (row >= b) return;
+  const double2* Mrow = M + (size_t)row * b;
+  double2 acc0 = zmake(0.0, 0.0), acc1 = zmake(0.0, 0.0);
+  int j = lane;
+  for (; j + 32 < b; j += 64) {
+    double2 m0 = __ldcs(&Mrow[j]);
+    double2 m1 = __ldcs(&Mrow[j + 32]);
+    zfma(acc0, m0, tvec[j]);
+    zfma(acc1, m1, tvec[j + 32]);
+  }
+  if (j < b) zfma(acc0, __ldcs(&Mrow[j]), tvec[j]);
+  acc0 = zadd(acc0, acc1);
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    acc0.x += __shfl_xor_sync(0xffffffffu, acc0.x, s);
+    acc0.y += __shfl_xor_sync(0xffffffffu, acc0.y, s);
+  }
+  if (lane == 0) {
+    if (MODE == 0)
+      y[o + row] = acc0;
+    else
+      y[o + row] = zsub(y[o + row], acc0);
+  }
+}
+
+// y = alpha_rows .* (CSR x)   (one warp per row).  VT = double or double2 values.
+template <typename VT>
+__device__ __forceinline__ double2 kb_valmul(VT v, double2 x);
+template <>
+__device__ __forceinline__ double2 kb_valmul<double>(double v, double2 x) { return zscale(x, v); }
+template <>
+__device__ __forceinline__ double2 kb_valmul<double2>(double2 v, double2 x) { return zmul(v, x); }
+
+// MODE 0: y = s .* (M x); MODE 1: y = r - M x
+template <typename VT, int MODE>
+__global__ void kb_spmv(int n, const int64_t* __restrict__ rowptr, const int* __restrict__ col,
+                        const VT* __restrict__ val, const double2* __restrict__ x,
+                        const double* __restrict__ rowscale, const double2* __restrict__ r,
+                        double2* __restrict__ y) {
+  int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  double2 acc = zmake(0.0, 0.0);
+  for (int64_t k = rowptr[row] + lane, e = rowptr[row + 1]; k < e; k += 32)
+    acc = zadd(acc, kb_valmul<VT>(val[k], x[col[k]]));
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, s);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, s);
+  }
+  if (lane == 0) {
+    if (MODE == 0) {
+      double sc = rowscale ? rowscale[row] : 1.0;
+      y[row] = zscale(acc, sc);
+    } else {
+      y[row] = zsub(r[row], acc);
+    }
+  }
+}
+
+// out[k] = scale[k] * in[perm[k]]   (original -> chain)
+__global__ void kb_gather_scale(int n, const int* __restrict__ perm, const double* __restrict__ scale,
+                                const double2* __restrict__ in, double2* __restrict__ out) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  double s = scale ? scale[k] : 1.0;
+  out[k] = zscale(in[perm[k]], s);
+}
+// out[perm[k]] = scale[k] * in[k]   (chain -> original)
+__global__ void kb_scatter_scale(int n, const int* __restrict__ perm, const double* __restrict__ scale,
+                                 const double2* __restrict__ in, double2* __restrict__ out) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  double s = scale ? scale[k] : 1.0;
+  out[perm[k]] = zscale(in[k], s);
+}
+__global__ void kb_scale_vec(int n, const double* __restrict__ scale, const double2* __restrict__ in,
+                             double2* __restrict__ out) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  out[k] = zscale(in[k], scale[k]);
+}
+__global__ void kb_axpy1(int n, const double2* __restrict__ dx, double2* __restrict__ x) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  x[k] = zadd(x[k], dx[k]);
+}
+// partial sums of |v|^2 per block -> out[blockIdx]
+__global__ void kb_norm2_partial(int n, const double2* __restrict__ v, double* __restrict__ out) {
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) acc += zabs2(v[k]);
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (threadIdx.x == 0) out[blockIdx.x] = acc;
+  }
+}
+
+
+// one forward + backward sweep: y <- T'^{-1} r   (scaled chain space)
+static int chain_sweeps(kb_context* h, const double2* r, double2* y) {
+  cudaStream_t s = h->stream;
+  const int64_t P = h->P;
+  for (int64_t p = 0; p < P; ++p) {
+    int o = (int)h->nodeptr[p], b = (int)(h->nodeptr[p + 1] - h->nodeptr[p]);
+    kb_node_apply<0><<<(b + KB_NODE_WARPS - 1) / KB_NODE_WARPS, KB_NODE_WARPS * 32, b * sizeof(double2), s>>>(
+        h->d_M.p + h->Moff[p], b, o, r, y, h->d_rowptr.p, h->d_dstart.p, h->d_ustart.p, h->d_col.p,
+        h->d_Tval.p);
+  }
+  for (int64_t p = P - 2; p >= 0; --p) {
+    int o = (int)h->nodeptr[p], b = (int)(h->nodeptr[p + 1] - h->nodeptr[p]);
+    kb_node_apply<1><<<(b + KB_NODE_WARPS - 1) / KB_NODE_WARPS, KB_NODE_WARPS * 32, b * sizeof(double2), s>>>(
+        h->d_M.p + h->Moff[p], b, o, r, y, h->d_rowptr.p, h->d_dstart.p, h->d_ustart.p, h->d_col.p,
+        h->d_Tval.p);
+  }
+  h->launches += 2 * P - 1;
+  KB_LAUNCH_CHECK(h);
+  return KB_OK;
+}
+
+int kbi_solve_workspace(kb_context* h) {
+  const int64_t n = h->n;
+  KB_CUDA(h, h->d_r.alloc(n));
+  KB_CUDA(h, h->d_y.alloc(n));
+  KB_CUDA(h, h->d_res.alloc(n));
+  KB_CUDA(h, h->d_x0.alloc(n));
+  KB_CUDA(h, h->d_in.alloc(n));
+  KB_CUDA(h, h->d_out.alloc(n));
+  KB_CUDA(h, h->d_partial.alloc(1024));
+  return KB_OK;
+}
+
+int kbi_chain_solve(kb_context* h, const double2* r_dev, double2* x_dev, int refine) {
+  if (!h->factored) return kb_fail(h, KB_EINVAL, "kb_factor must succeed before solving");
+  if (h->nranks > 1) {
+    return kbi_chain_solve_sharded(h, r_dev, x_dev, refine);
+  }
+  cudaStream_t s = h->stream;
+  const int n = (int)h->n;
+  KB_TRY(chain_sweeps(h, r_dev, x_dev));
+  h->stats.solve_calls++;
+  for (int it = 0; it < refine; ++it) {
+    kb_spmv<double2, 1><<<nblk((int64_t)n * 32, 256), 256, 0, s>>>(n, h->d_rowptr.p, h->d_col.p, h->d_Tval.p,
+                                                                   x_dev, nullptr, r_dev, h->d_res.p);
+    KB_TRY(chain_sweeps(h, h->d_res.p, h->d_x0.p));
+    kb_axpy1<<<nblk(n, 256), 256, 0, s>>>(n, h->d_x0.p, x_dev);
+    h->launches += 2;
+    h->stats.solve_calls++;
+  }
+  KB_LAUNCH_CHECK(h);
+  return KB_OK;
+}
+
+int kbi_spmv_B_chain(kb_context* h, const double2* x, double2* y, bool scale_rows) {
+  cudaStream_t s = h->stream;
+  const int n = (int)h->n;
+  if (!h->B.present) return kb_fail(h, KB_EINVAL, "pencil has no B matrix");
+  const double* rs = scale_rows ? h->d_rscale.p : nullptr;
+  if (h->b_is_complex)
+    kb_spmv<double2, 0><<<nblk((int64_t)n * 32, 256), 256, 0, s>>>(n, h->d_browptr.p, h->d_bcol.p, h->d_bval_c.p,
+                                                                   x, rs, nullptr, y);
+  else
+    kb_spmv<double, 0><<<nblk((int64_t)n * 32, 256), 256, 0, s>>>(n, h->d_browptr.p, h->d_bcol.p, h->d_bval_r.p, x,
+                                                                  rs, nullptr, y);
+  h->launches++;
+  KB_LAUNCH_CHECK(h);
+  return KB_OK;
+}
+
+int kbi_spmv_A_chain(kb_context* h, const double2* x, double2* y) {
+  const int n = (int)h->n;
+  kb_spmv<double2, 0><<<nblk((int64_t)n * 32, 256), 256, 0, h->stream>>>(n, h->d_arowptr.p, h->d_acol.p,
+                                                                         h->d_aval.p, x, nullptr, nullptr, y);
+  h->launches++;
+  KB_LAUNCH_CHECK(h);
+  return KB_OK;
+}
+
+int kbi_to_chain(kb_context* h, const double2* x_orig, double2* x_chain) {
+  const int n = (int)h->n;
+  kb_gather_scale<<<nblk(n, 256), 256, 0, h->stream>>>(n, h->d_perm.p, nullptr, x_orig, x_chain);
+  h->launches++;
+  KB_LAUNCH_CHECK(h);
+  return KB_OK;
+}
+int kbi_from_chain(kb_context* h, const double2* x_chain, double2* x_orig) {
+  const int n = (int)h->n;
+  kb_scatter_scale<<<nblk(n, 256), 256, 0, h->stream>>>(n, h->d_perm.p, nullptr, x_chain, x_orig);
+  h->launches++;
+  KB_LAUNCH_CHECK(h);
+  return KB_OK;
+}
+
+// out = C T'^{-1} R B in      (chain order, unscaled vectors)
+int kbi_apply_op_chain(kb_context* h, const double2* in_chain, double2* out_chain, int refine) {
+  const int n = (int)h->n;
+  KB_TRY(kbi_solve_workspace(h));
+  KB_TRY(kbi_spmv_B_chain(h, in_chain, h->d_r.p, true));
+  KB_TRY(kbi_chain_solve(h, h->d_r.p, h->d_y.p, refine));
+  kb_scale_vec<<<nblk(n, 256), 256, 0, h->stream>>>(n, h->d_cscale.p, h->d_y.p, out_chain);
+  h->launches++;
+  KB_LAUNCH_CHECK(h);
+  return KB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// public entry points
+// ---------------------------------------------------------------------------
+static int solve_dev_impl(kb_context* h, const double2* rhs_dev, double2* x_dev, int nrhs) {
+  cudaStream_t s = h->stream;
+  const int n = (int)h->n;
+  KB_TRY(kbi_solve_workspace(h));
+  cudaEvent_t e0, e1;
+  KB_CUDA(h, cudaEventCreate(&e0));
+  KB_CUDA(h, cudaEventCreate(&e1));
+  KB_CUDA(h, cudaEventRecord(e0, s));
+  for (int c = 0; c < nrhs; ++c) {
+    kb_gather_scale<<<nblk(n, 256), 256, 0, s>>>(n, h->d_perm.p, h->d_rscale.p, rhs_dev + (size_t)c * n,
+                                                 h->d_r.p);
+    KB_TRY(kbi_chain_solve(h, h->d_r.p, h->d_y.p, h->opt_refine));
+    kb_scatter_scale<<<nblk(n, 256), 256, 0, s>>>(n, h->d_perm.p, h->d_cscale.p, h->d_y.p,
+                                                  x_dev + (size_t)c * n);
+    h->launches += 2;
+  }
+  KB_CUDA(h, cudaEventRecord(e1, s));
+  KB_CUDA(h, cudaStreamSynchronize(s));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  h->stats.solve_ms = ms / (nrhs > 0 ? nrhs : 1);
+  double bytes = 0.0;
+  for (int64_t p = 0; p < h->P; ++p) {
+    double b = (double)(h->nodeptr[p + 1] - h->nodeptr[p]);
+    bytes += 2.0 * 16.0 * b * b;
+  }
+  h->stats.solve_bytes = bytes + 3.0 * 16.0 * n;
+  return KB_OK;
+}
+
+extern "C" int kb_solve_dev(kb_handle h, const double* rhs_dev, double* x_dev, int nrhs) {
+  if (!h || !rhs_dev || !x_dev || nrhs < 1) return KB_EINVAL;
+  if (!h->factored) return kb_fail(h, KB_EINVAL, "kb_factor must succeed before kb_solve");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  return solve_dev_impl(h, (const double2*)rhs_dev, (double2*)x_dev, nrhs);
+}
+
+extern "C" int kb_solve(kb_handle h, const double* rhs, double* x, int nrhs) {
+  if (!h || !rhs || !x || nrhs < 1) return KB_EINVAL;
+  if (!h->factored) return kb_fail(h, KB_EINVAL, "kb_factor must succeed before kb_solve");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  const size_t cnt = (size_t)h->n * nrhs;
+  DevBuf<double2> d_rhs, d_x;
+  KB_CUDA(h, d_rhs.alloc(cnt));
+  KB_CUDA(h, d_x.alloc(cnt));
+  KB_CUDA(h, cudaMemcpyAsync(d_rhs.p, rhs, cnt * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+  KB_TRY(solve_dev_impl(h, d_rhs.p, d_x.p, nrhs));
+  KB_CUDA(h, cudaMemcpyAsync(x, d_x.p, cnt * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return KB_OK;
+}
+
+extern "C" int kb_apply_op(kb_handle h, const double* x, double* y) {
+  if (!h || !x || !y) return KB_EINVAL;
+  if (!h->factored) return kb_fail(h, KB_EINVAL, "kb_factor must succeed before kb_apply_op");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  const int n = (int)h->n;
+  KB_TRY(kbi_solve_workspace(h));
+  DevBuf<double2> d_a, d_b;
+  KB_CUDA(h, d_a.alloc(n));
+  KB_CUDA(h, d_b.alloc(n));
+  KB_CUDA(h, cudaMemcpyAsync(d_a.p, x, (size_t)n * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+  KB_TRY(kbi_to_chain(h, d_a.p, h->d_in.p));
+  KB_TRY(kbi_apply_op_chain(h, h->d_in.p, h->d_out.p, h->opt_refine));
+  KB_TRY(kbi_from_chain(h, h->d_out.p, d_b.p));
+  KB_CUDA(h, cudaMemcpyAsync(y, d_b.p, (size_t)n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return KB_OK;
+}
+
+extern "C" int kb_matvec(kb_handle h, int which, const double* x, double* y) {
+  if (!h || !x || !y) return KB_EINVAL;
+  if (!h->chain_set) return kb_fail(h, KB_EINVAL, "kb_set_chain must be called before kb_matvec");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  const int n = (int)h->n;
+  KB_TRY(kbi_solve_workspace(h));
+  DevBuf<double2> d_a, d_b;
+  KB_CUDA(h, d_a.alloc(n));
+  KB_CUDA(h, d_b.alloc(n));
+  KB_CUDA(h, cudaMemcpyAsync(d_a.p, x, (size_t)n * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+  KB_TRY(kbi_to_chain(h, d_a.p, h->d_in.p));
+  if (which == 0)
+    KB_TRY(kbi_spmv_A_chain(h, h->d_in.p, h->d_out.p));
+  else
+    KB_TRY(kbi_spmv_B_chain(h, h->d_in.p, h->d_out.p, false));
+  KB_TRY(kbi_from_chain(h, h->d_out.p, d_b.p));
+  KB_CUDA(h, cudaMemcpyAsync(y, d_b.p, (size_t)n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return KB_OK;
+}

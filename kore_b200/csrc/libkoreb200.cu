@@ -1,0 +1,7 @@
+// Single translation unit of libkoreb200.so (kernels are launched across the
+// files below, so they are compiled together instead of with -rdc).
+#include "kb_setup.cu"
+#include "kb_factor.cu"
+#include "kb_solve.cu"
+#include "kb_eigs.cu"
+#include "kb_shard.cu"

@@ -1,0 +1,239 @@
+"""ctypes binding of libkoreb200.so (the C ABI declared in include/kore_b200.h).
+
+This is the thin host layer the north-star asks for: Python calls a C-ABI
+library; numpy owns the host buffers; there is NO CPU fallback -- if the
+shared library is missing or no B200 is visible, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "libkoreb200.so")
+
+KB_OK, KB_EINVAL, KB_ENODEVICE, KB_ECUDA, KB_ENOMEM, KB_ESINGULAR, KB_ESTRUCTURE, KB_ENCCL = range(8)
+ERRNAMES = ["KB_OK", "KB_EINVAL", "KB_ENODEVICE", "KB_ECUDA", "KB_ENOMEM", "KB_ESINGULAR",
+            "KB_ESTRUCTURE", "KB_ENCCL"]
+
+# SLEPc.EPS.Which as used at bin/solve.py:99-117
+WHICH = {"LM": 0, "SM": 1, "LR": 2, "SR": 3, "LI": 4, "SI": 5, "TM": 6, "TR": 7, "TI": 8}
+
+OPT_EQUILIBRATE, OPT_REFINE, OPT_PURIFY, OPT_SEED, OPT_PANEL, OPT_REFINE_EIGS = 1, 2, 3, 4, 5, 6
+
+# every symbol include/kore_b200.h declares
+EXPORTS = [
+    "kb_create", "kb_destroy", "kb_last_error", "kb_set_option", "kb_set_pencil", "kb_set_chain",
+    "kb_nccl_unique_id", "kb_set_sharding", "kb_factor", "kb_solve", "kb_apply_op", "kb_matvec",
+    "kb_eigs", "kb_get_stats", "kb_solve_dev", "kb_stream",
+]
+
+
+class KoreB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        self.code = code
+        name = ERRNAMES[code] if 0 <= code < len(ERRNAMES) else str(code)
+        super().__init__("%s: %s" % (name, msg))
+
+
+class KbStats(C.Structure):
+    _fields_ = [
+        ("factor_ms", C.c_double), ("solve_ms", C.c_double), ("eigs_ms", C.c_double),
+        ("eigs_solve_ms", C.c_double), ("op_applies", C.c_int64), ("solve_calls", C.c_int64),
+        ("kernel_launches", C.c_int64), ("factor_bytes", C.c_int64), ("factor_flops", C.c_double),
+        ("solve_bytes", C.c_double), ("refine_resid", C.c_double),
+    ]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def build(verbose=False):
+    """Compile libkoreb200.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", _ROOT, "kore_b200/libkoreb200.so"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout)
+    if r.returncode != 0:
+        raise RuntimeError("building libkoreb200.so failed")
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load():
+    """dlopen the library and attach prototypes.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise KoreB200Error(KB_ENODEVICE,
+                            "libkoreb200.so is not built (run `make` or __graft_entry__.build()); "
+                            "there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, i64, dp = C.c_void_p, C.c_int64, C.POINTER(C.c_double)
+    lib.kb_create.argtypes = [C.POINTER(vp), C.c_int]
+    lib.kb_destroy.argtypes = [vp]
+    lib.kb_last_error.argtypes = [vp]
+    lib.kb_last_error.restype = C.c_char_p
+    lib.kb_set_option.argtypes = [vp, C.c_int, i64]
+    lib.kb_set_pencil.argtypes = [vp, i64, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int]
+    lib.kb_set_chain.argtypes = [vp, vp, vp, i64]
+    lib.kb_nccl_unique_id.argtypes = [vp]
+    lib.kb_set_sharding.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.kb_factor.argtypes = [vp, vp]
+    lib.kb_solve.argtypes = [vp, vp, vp, C.c_int]
+    lib.kb_apply_op.argtypes = [vp, vp, vp]
+    lib.kb_matvec.argtypes = [vp, C.c_int, vp, vp]
+    lib.kb_eigs.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, vp, C.c_int, vp,
+                            C.c_int, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int), vp]
+    lib.kb_get_stats.argtypes = [vp, C.POINTER(KbStats)]
+    lib.kb_solve_dev.argtypes = [vp, vp, vp, C.c_int]
+    lib.kb_stream.argtypes = [vp, C.POINTER(vp)]
+    lib.kb_dbg_schur.argtypes = [C.c_int, vp, C.c_int, vp, vp, vp, vp]
+    for name in EXPORTS + ["kb_dbg_schur"]:
+        if name != "kb_last_error":
+            getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Solver:
+    """One GPU, one pencil (A, B), one chain layout; factor / solve / eigs.
+
+    Mirrors the sequence of calls bin/solve.py makes on PETSc/SLEPc objects:
+    Mat assembly -> (analysis) -> numeric factorisation -> solve / EPSSolve."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.kb_create(C.byref(h), int(device))
+        if rc != KB_OK:
+            raise KoreB200Error(rc, self.lib.kb_last_error(None).decode())
+        self.h = h
+        self.n = 0
+        self._keep = []
+
+    def _check(self, rc):
+        if rc != KB_OK:
+            raise KoreB200Error(rc, self.lib.kb_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.kb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_option(self, opt, value):
+        self._check(self.lib.kb_set_option(self.h, int(opt), int(value)))
+
+    def set_pencil(self, A, B=None):
+        """A, B: scipy.sparse CSR (A complex128; B float64 or complex128 or None)."""
+        A = A.tocsr()
+        n = A.shape[0]
+        idx_dtype = np.int64 if (A.indices.dtype == np.int64 or A.indptr.dtype == np.int64) else np.int32
+        ap = np.ascontiguousarray(A.indptr, dtype=idx_dtype)
+        ai = np.ascontiguousarray(A.indices, dtype=idx_dtype)
+        av = np.ascontiguousarray(A.data, dtype=np.complex128)
+        bp = bi = bv = None
+        bcomplex = 0
+        if B is not None:
+            B = B.tocsr()
+            bp = np.ascontiguousarray(B.indptr, dtype=idx_dtype)
+            bi = np.ascontiguousarray(B.indices, dtype=idx_dtype)
+            if np.iscomplexobj(B.data):
+                bv = np.ascontiguousarray(B.data, dtype=np.complex128)
+                bcomplex = 1
+            else:
+                bv = np.ascontiguousarray(B.data, dtype=np.float64)
+        self._check(self.lib.kb_set_pencil(self.h, n, np.dtype(idx_dtype).itemsize, _ptr(ap), _ptr(ai),
+                                           _ptr(av), _ptr(bp), _ptr(bi), _ptr(bv), bcomplex))
+        self.n = n
+
+    def set_chain(self, perm, nodeptr):
+        perm = np.ascontiguousarray(perm, dtype=np.int64)
+        nodeptr = np.ascontiguousarray(nodeptr, dtype=np.int64)
+        self._check(self.lib.kb_set_chain(self.h, _ptr(perm), _ptr(nodeptr), len(nodeptr) - 1))
+
+    def set_sharding(self, rank, nranks, unique_id):
+        self._check(self.lib.kb_set_sharding(self.h, int(rank), int(nranks), _ptr(unique_id)))
+
+    def factor(self, sigma):
+        s = np.array([complex(sigma)], dtype=np.complex128)
+        self._check(self.lib.kb_factor(self.h, _ptr(s)))
+
+    def solve(self, rhs):
+        rhs = np.asarray(rhs, dtype=np.complex128)
+        one = rhs.ndim == 1
+        R = np.asfortranarray(rhs.reshape(self.n, -1))
+        X = np.empty_like(R, order="F")
+        self._check(self.lib.kb_solve(self.h, _ptr(R), _ptr(X), R.shape[1]))
+        return X[:, 0].copy() if one else X
+
+    def apply_op(self, x):
+        x = np.ascontiguousarray(x, dtype=np.complex128)
+        y = np.empty_like(x)
+        self._check(self.lib.kb_apply_op(self.h, _ptr(x), _ptr(y)))
+        return y
+
+    def matvec(self, which, x):
+        x = np.ascontiguousarray(x, dtype=np.complex128)
+        y = np.empty_like(x)
+        self._check(self.lib.kb_matvec(self.h, 0 if which == "A" else 1, _ptr(x), _ptr(y)))
+        return y
+
+    def eigs(self, nev, which="TM", target=None, ncv=0, tol=1e-15, maxit=50, true_residual=False,
+             v0=None, max_pairs=None):
+        """Returns (eigenvalues[nconv], eigenvectors[n, nconv], info)."""
+        if ncv <= 0:
+            ncv = max(2 * nev, nev + 15)
+        max_pairs = max_pairs or ncv
+        evals = np.zeros(max_pairs, dtype=np.complex128)
+        evecs = np.zeros((self.n, max_pairs), dtype=np.complex128, order="F")
+        resid = np.zeros(max_pairs, dtype=np.float64)
+        nconv = C.c_int(0)
+        its = C.c_int(0)
+        tgt = None if target is None else np.array([complex(target)], dtype=np.complex128)
+        if v0 is not None:
+            v0 = np.ascontiguousarray(v0, dtype=np.complex128)
+        self._check(self.lib.kb_eigs(self.h, int(nev), int(ncv), float(tol), int(maxit), WHICH[which],
+                                     _ptr(tgt), int(bool(true_residual)), _ptr(v0), int(max_pairs),
+                                     _ptr(evals), _ptr(evecs), C.byref(nconv), C.byref(its), _ptr(resid)))
+        k = nconv.value
+        info = dict(nconv=k, its=its.value, ncv=ncv, resid=resid[:k].copy())
+        info.update(self.stats())
+        return evals[:k].copy(), np.ascontiguousarray(evecs[:, :k]), info
+
+    def stats(self):
+        st = KbStats()
+        self._check(self.lib.kb_get_stats(self.h, C.byref(st)))
+        return st.asdict()
+
+    def solve_dev(self, rhs_ptr, x_ptr, nrhs=1):
+        """Device-pointer variant (torch tensors' data_ptr())."""
+        self._check(self.lib.kb_solve_dev(self.h, C.c_void_p(rhs_ptr), C.c_void_p(x_ptr), int(nrhs)))
+
+    def stream(self):
+        s = C.c_void_p()
+        self._check(self.lib.kb_stream(self.h, C.byref(s)))
+        return s.value

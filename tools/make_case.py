@@ -1,0 +1,111 @@
+#!/usr/bin/env python3
+"""Produce the matrices the reference would hand to SLEPc, in THIS container.
+
+Runs the UNMODIFIED reference stages (bin/submatrices.py, bin/assemble.py and,
+for magnetic runs, bin/compute_profiles.py) from /root/reference in a scratch
+directory, with a parameters file derived from one of the reference's own
+params files plus `key=value` overrides, and a single-rank mpi4py stand-in
+(tests/fixtures/mpi4py) on PYTHONPATH.  Nothing from the reference is copied
+into this repository: only the resulting A.npz / B.npz / B_forced.npz (and a
+meta.json describing the chain layout inputs) are written to --out.
+
+Usage:
+  tools/make_case.py --params tests/spinover/params.spinover --out /tmp/c1 [k=v ...]
+
+Reference pipeline: runKore.sh:14-16; tests/koretest.py:8-43.
+"""
+import argparse
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+
+REF = os.environ.get("KORE_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+STANDIN = os.path.join(HERE, "..", "tests", "fixtures")
+
+
+def patch_params(text, overrides):
+    """Replace top-level `name = value` assignments (the same thing the
+    reference's own drivers do with sed, tests/dormy2004/find_Rac.py:31,44)."""
+    for k, v in overrides.items():
+        pat = re.compile(r"^(%s)\s*=.*$" % re.escape(k), re.M)
+        if not pat.search(text):
+            raise SystemExit("parameter %s not found in params file" % k)
+        # replace only the LAST active assignment (later ones win in Python)
+        matches = list(pat.finditer(text))
+        m = matches[-1]
+        text = text[: m.start()] + "%s = %s" % (k, v) + text[m.end():]
+    return text
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--params", default="bin/parameters.py",
+                    help="params file relative to the reference root")
+    ap.add_argument("--out", required=True)
+    ap.add_argument("--ncpus", type=int, default=8)
+    ap.add_argument("--keep", action="store_true")
+    ap.add_argument("overrides", nargs="*")
+    a = ap.parse_args()
+
+    ov = {}
+    for o in a.overrides:
+        k, v = o.split("=", 1)
+        ov[k] = v
+
+    work = tempfile.mkdtemp(prefix="korecase_")
+    shutil.copytree(os.path.join(REF, "bin"), os.path.join(work, "bin"))
+    subprocess.check_call(["chmod", "-R", "u+w", work])
+    with open(os.path.join(REF, a.params)) as f:
+        ptxt = f.read()
+    ptxt = patch_params(ptxt, ov)
+    with open(os.path.join(work, "bin", "parameters.py"), "w") as f:
+        f.write(ptxt)
+
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.path.abspath(STANDIN) + os.pathsep + env.get("PYTHONPATH", "")
+    env["PYTHONWARNINGS"] = "ignore"
+
+    def run(*cmd):
+        subprocess.check_call(list(cmd), cwd=work, env=env,
+                              stdout=subprocess.DEVNULL)
+
+    # parameters needed by the driver afterwards
+    probe = subprocess.check_output(
+        [sys.executable, "-c",
+         "import sys; sys.path.insert(0,'bin'); import parameters as p, utils as u, json;"
+         "print(json.dumps(dict(hydro=p.hydro,magnetic=p.magnetic,thermal=p.thermal,"
+         "compositional=p.compositional,m=p.m,lmax=p.lmax,N=p.N,symm=p.symm,ricb=p.ricb,"
+         "forcing=p.forcing,nev=p.nev,maxit=p.maxit,tol=p.tol,which_eigenpairs=p.which_eigenpairs,"
+         "rtau=p.tau.real,itau=p.tau.imag,B0=p.B0,Ek=p.Ek,N1=u.N1,n=u.n,sizmat=u.sizmat,"
+         "symmB0=u.symmB0,anelastic=p.anelastic,forcing_frequency=p.forcing_frequency)))"],
+        cwd=work, env=env).decode().strip().splitlines()[-1]
+    meta = json.loads(probe)
+
+    if meta["magnetic"] == 1 or meta["anelastic"] == 1:
+        run(sys.executable, "bin/compute_profiles.py")
+    run(sys.executable, "bin/submatrices.py", str(a.ncpus))
+    run(sys.executable, "bin/assemble.py")
+
+    os.makedirs(a.out, exist_ok=True)
+    for fn in ("A.npz", "B.npz", "B_forced.npz"):
+        src = os.path.join(work, fn)
+        if os.path.exists(src):
+            shutil.copy(src, os.path.join(a.out, fn))
+    with open(os.path.join(a.out, "meta.json"), "w") as f:
+        json.dump(meta, f, indent=1, sort_keys=True)
+    with open(os.path.join(a.out, "parameters.py"), "w") as f:
+        f.write(ptxt)
+    if a.keep:
+        print("scratch kept at", work)
+    else:
+        shutil.rmtree(work)
+    print(json.dumps(meta))
+
+
+if __name__ == "__main__":
+    main()
