@@ -274,6 +274,16 @@ extern "C" int kb_eigs(kb_handle h, int nev, int ncv, double tol, int maxit, int
   KB_CUDA(h, cudaEventRecord(e0, s));
   h->stats.op_applies = 0;
   h->stats.solve_calls = 0;
+  h->stats.eigs_solve_ms = 0.0;
+  h->time_sweeps = true;
+  struct SweepTimerGuard {
+    kb_context* h;
+    ~SweepTimerGuard() {
+      h->time_sweeps = false;
+      for (cudaEvent_t e : h->sweep_events) cudaEventDestroy(e);
+      h->sweep_events.clear();
+    }
+  } sweep_guard{h};
 
   KB_TRY(kbi_solve_workspace(h));
 
@@ -508,6 +518,11 @@ extern "C" int kb_eigs(kb_handle h, int nev, int ncv, double tol, int maxit, int
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   h->stats.eigs_ms = ms;
+  for (size_t i = 0; i + 1 < h->sweep_events.size(); i += 2) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, h->sweep_events[i], h->sweep_events[i + 1]) == cudaSuccess)
+      h->stats.eigs_solve_ms += t;
+  }
   return KB_OK;
 }
 

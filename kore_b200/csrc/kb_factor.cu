@@ -137,7 +137,8 @@ template <int NB, int RPT, int MAXT>
 __global__ void __launch_bounds__(MAXT)
 kb_gj_panel(const double2* __restrict__ Ain, int n, int k0, int nbv, double2* __restrict__ Gp,
             int* __restrict__ orig, int* __restrict__ srcrow, int* __restrict__ info) {
-  extern __shared__ int s_src[];  // n ints
+  extern __shared__ int s_src[];  // n ints: pre-panel row at each position; then n ints: orig
+  int* s_orig = s_src + n;
   __shared__ double2 prow[NB];
   __shared__ double2 swp[NB];
   __shared__ double wv[32];
@@ -154,116 +155,125 @@ kb_gj_panel(const double2* __restrict__ Ain, int n, int k0, int nbv, double2* __
     for (int j = 0; j < NB; ++j)
       a[r][j] = (i < n && j < nbv) ? Ain[(size_t)i * n + k0 + j] : zmake(0.0, 0.0);
   }
-  for (int i = t; i < n; i += T) s_src[i] = i;
-  if (k0 == 0)
-    for (int i = t; i < n; i += T) orig[i] = i;
+  for (int i = t; i < n; i += T) {
+    s_src[i] = i;
+    s_orig[i] = (k0 == 0) ? i : orig[i];
+  }
   __syncthreads();
 
+  // The column loop is NOT unrolled: after each step the register row is rotated
+  // left by one, so the active column is always a[.][0] and the loop body (about
+  // 9 KB of SASS instead of 140 KB) stays resident in the instruction cache.
+#pragma unroll 1
+  for (int k = 0; k < nbv; ++k) {
+    const int gk = k0 + k;
+    // ---- pivot search over positions >= gk
+    double bv = -1.0;
+    int bi = 0x7fffffff;
 #pragma unroll
-  for (int k = 0; k < NB; ++k) {
-    if (k < nbv) {
-      const int gk = k0 + k;
-      // ---- pivot search over positions >= gk
-      double bv = -1.0;
-      int bi = 0x7fffffff;
-#pragma unroll
-      for (int r = 0; r < RPT; ++r) {
-        int i = t + r * T;
-        if (i >= gk && i < n) {
-          double m = zabs2(a[r][k]);
-          if (m > bv || (m == bv && i < bi)) {  // NaN never wins: an all-NaN column is flagged below
-            bv = m;
-            bi = i;
-          }
+    for (int r = 0; r < RPT; ++r) {
+      int i = t + r * T;
+      if (i >= gk && i < n) {
+        double m = zabs2(a[r][0]);
+        if (m > bv || (m == bv && i < bi)) {  // NaN never wins: an all-NaN column is flagged below
+          bv = m;
+          bi = i;
         }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > bv || (ov == bv && oi < bi)) {
-          bv = ov;
-          bi = oi;
-        }
-      }
-      if (lane == 0) {
-        wv[wid] = bv;
-        wi[wid] = bi;
-      }
-      __syncthreads();
-      bv = wv[0];
-      bi = wi[0];
-      for (int w = 1; w < nw; ++w) {
-        double ov = wv[w];
-        int oi = wi[w];
-        if (ov > bv || (ov == bv && oi < bi)) {
-          bv = ov;
-          bi = oi;
-        }
-      }
-      const int rp = bi;
-      if (t == 0) {
-        if (!(bv > 0.0) || isinf(bv) || rp >= n) atomicExch(info, gk + 1);
-      }
-      const int rps = (rp < n) ? rp : gk;  // keep going on breakdown; host reports KB_ESINGULAR
-      // ---- publish scaled pivot row, and the row being displaced from position gk
-#pragma unroll
-      for (int r = 0; r < RPT; ++r) {
-        int i = t + r * T;
-        if (i == rps) {
-          double2 pinv = zinv(a[r][k]);
-#pragma unroll
-          for (int j = 0; j < NB; ++j) prow[j] = (j == k) ? pinv : zmul(a[r][j], pinv);
-        }
-        if (i == gk && rps != gk) {
-#pragma unroll
-          for (int j = 0; j < NB; ++j) swp[j] = a[r][j];
-        }
-      }
-      if (t == 0) {
-        int tmp = s_src[gk];
-        s_src[gk] = s_src[rps];
-        s_src[rps] = tmp;
-        int to = orig[gk];
-        orig[gk] = orig[rps];
-        orig[rps] = to;
-      }
-      __syncthreads();
-      // ---- eliminate
-      const double2 pk = prow[k];
-#pragma unroll
-      for (int r = 0; r < RPT; ++r) {
-        int i = t + r * T;
-        if (i < n) {
-          if (i == gk) {
-#pragma unroll
-            for (int j = 0; j < NB; ++j) a[r][j] = prow[j];
-          } else {
-            if (i == rps) {
-#pragma unroll
-              for (int j = 0; j < NB; ++j) a[r][j] = swp[j];
-            }
-            double2 f = a[r][k];
-#pragma unroll
-            for (int j = 0; j < NB; ++j) {
-              if (j != k) zfms(a[r][j], f, prow[j]);
-            }
-            a[r][k] = zneg(zmul(f, pk));
-          }
-        }
-      }
-      __syncthreads();
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) {
+        bv = ov;
+        bi = oi;
+      }
+    }
+    if (lane == 0) {
+      wv[wid] = bv;
+      wi[wid] = bi;
+    }
+    __syncthreads();
+    bv = lane < nw ? wv[lane] : -1.0;
+    bi = lane < nw ? wi[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) {
+        bv = ov;
+        bi = oi;
+      }
+    }
+    const int rp = bi;
+    if (t == 0) {
+      if (!(bv > 0.0) || isinf(bv) || rp >= n) atomicExch(info, gk + 1);
+    }
+    const int rps = (rp < n) ? rp : gk;  // keep going on breakdown; host reports KB_ESINGULAR
+    // ---- publish the (unscaled) pivot row, and the row being displaced from position gk
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      int i = t + r * T;
+      if (i == rps) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) prow[j] = a[r][j];
+      }
+      if (i == gk && rps != gk) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) swp[j] = a[r][j];
+      }
+    }
+    if (t == 0) {
+      int tmp = s_src[gk];
+      s_src[gk] = s_src[rps];
+      s_src[rps] = tmp;
+      int to = s_orig[gk];
+      s_orig[gk] = s_orig[rps];
+      s_orig[rps] = to;
+    }
+    __syncthreads();
+    // ---- eliminate (every thread forms 1/pivot itself: no serial section), then rotate
+    const double2 pinv = zinv1(prow[0]);
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      int i = t + r * T;
+      if (i < n) {
+        if (i == gk) {
+          a[r][0] = pinv;
+#pragma unroll
+          for (int j = 1; j < NB; ++j) a[r][j] = zmul(prow[j], pinv);
+        } else {
+          if (i == rps) {
+#pragma unroll
+            for (int j = 0; j < NB; ++j) a[r][j] = swp[j];
+          }
+          double2 g = zmul(a[r][0], pinv);
+#pragma unroll
+          for (int j = 1; j < NB; ++j) zfms(a[r][j], g, prow[j]);
+          a[r][0] = zneg(g);
+        }
+      }
+      double2 first = a[r][0];
+#pragma unroll
+      for (int j = 0; j + 1 < NB; ++j) a[r][j] = a[r][j + 1];
+      a[r][NB - 1] = first;
+    }
+    __syncthreads();
   }
+  // register slot j now holds panel column (j + nbv) mod NB
 #pragma unroll
   for (int r = 0; r < RPT; ++r) {
     int i = t + r * T;
     if (i < n) {
 #pragma unroll
-      for (int j = 0; j < NB; ++j) Gp[(size_t)i * NB + j] = a[r][j];
+      for (int j = 0; j < NB; ++j) Gp[(size_t)i * NB + ((j + nbv) % NB)] = a[r][j];
     }
   }
-  for (int i = t; i < n; i += T) srcrow[i] = s_src[i];
+  for (int i = t; i < n; i += T) {
+    srcrow[i] = s_src[i];
+    orig[i] = s_orig[i];
+  }
 }
 
 // Update step (out of place): for every non-panel column j
@@ -350,7 +360,7 @@ static void launch_panel(kb_context* h, const double2* in, int n, int k0, int nb
   int T = (n + RPT - 1) / RPT;
   T = ((T + 31) / 32) * 32;
   if (T > MAXT) T = MAXT;
-  kb_gj_panel<NB, RPT, MAXT><<<1, T, n * sizeof(int), h->stream>>>(in, n, k0, nbv, h->d_Gp.p, h->d_orig.p,
+  kb_gj_panel<NB, RPT, MAXT><<<1, T, 2 * n * sizeof(int), h->stream>>>(in, n, k0, nbv, h->d_Gp.p, h->d_orig.p,
                                                                   h->d_srcrow.p, h->d_info.p);
 }
 
@@ -415,6 +425,7 @@ int kbi_factor(kb_context* h, zcomplex sigma) {
   const int64_t bmax = h->bmax;
   h->factored = false;
   h->sigma = sigma;
+  kbi_drop_graphs(h);
 
   cudaEvent_t e0, e1;
   KB_CUDA(h, cudaEventCreate(&e0));

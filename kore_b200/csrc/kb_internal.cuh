@@ -56,6 +56,12 @@ __host__ __device__ __forceinline__ double2 zinv(double2 p) {
   return make_double2(xr / d, -xi / d);
 }
 
+// reciprocal with a single division (operands are equilibrated: no scaling needed)
+__host__ __device__ __forceinline__ double2 zinv1(double2 p) {
+  double d = 1.0 / (p.x * p.x + p.y * p.y);
+  return make_double2(p.x * d, -p.y * d);
+}
+
 // ---------------------------------------------------------------------------
 // error handling
 // ---------------------------------------------------------------------------
@@ -189,12 +195,24 @@ struct kb_context {
   DevBuf<int> d_orig, d_srcrow, d_piv, d_info;
 
   // solve workspaces (chain order, scaled space)
-  DevBuf<double2> d_r, d_y, d_res, d_x0, d_in, d_out;
+  DevBuf<double2> d_r, d_y, d_res, d_x0, d_in, d_out, d_t;
   DevBuf<double> d_partial;
 
   // Krylov workspaces
   DevBuf<double2> d_V;  // n x (ncv+1), column-major
   DevBuf<double2> d_w, d_w2, d_h, d_hpart, d_Q;
+
+  // captured sweep graphs, keyed by the (rhs, solution) buffers
+  struct SweepGraph {
+    const double2* r;
+    double2* y;
+    void* exec;
+  };
+  std::vector<SweepGraph> sweep_graphs;
+
+  // CUDA-event timing of the chain sweeps inside kb_eigs
+  bool time_sweeps = false;
+  std::vector<cudaEvent_t> sweep_events;
 
   // sharding
   int rank = 0, nranks = 1;
@@ -220,6 +238,7 @@ int kbi_spmv_A_chain(kb_context* h, const double2* x, double2* y);
 int kbi_to_chain(kb_context* h, const double2* x_orig_dev, double2* x_chain_dev);
 int kbi_from_chain(kb_context* h, const double2* x_chain_dev, double2* x_orig_dev);
 int kbi_solve_workspace(kb_context* h);
+void kbi_drop_graphs(kb_context* h);
 // ---- kb_shard.cu
 int kbi_factor_sharded(kb_context* h, zcomplex sigma);
 int kbi_chain_solve_sharded(kb_context* h, const double2* r_dev, double2* x_dev, int refine);

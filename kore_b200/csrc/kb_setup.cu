@@ -64,6 +64,7 @@ extern "C" int kb_destroy(kb_handle h) {
     cudaStreamDestroy(h->stream);
   }
   kbi_nccl_destroy(h);
+  kbi_drop_graphs(h);
   delete h;
   return KB_OK;
 }

@@ -15,51 +15,88 @@
 
 #define KB_NODE_WARPS 4
 
-// MODE 0: forward, MODE 1: backward (in place on y).
+// Sparse coupling of one node (one warp per row, lanes over the row's entries):
+//   MODE 0 (forward):  t_i = r_i - sum_k L_{p,p-1}[i,k] y[k]
+//   MODE 1 (backward): t_i =       sum_k U_{p,p+1}[i,k] y[k]
 template <int MODE>
-__global__ void __launch_bounds__(KB_NODE_WARPS * 32)
-kb_node_apply(const double2* __restrict__ M, int b, int o, const double2* __restrict__ r,
-              double2* __restrict__ y, const int64_t* __restrict__ rowptr,
-              const int64_t* __restrict__ dstart, const int64_t* __restrict__ ustart,
-              const int* __restrict__ col, const double2* __restrict__ T) {
-  extern __shared__ double2 tvec[];  // b entries
-  for (int i = threadIdx.x; i < b; i += blockDim.x) {
-    int gi = o + i;
-    double2 acc;
-    if (MODE == 0) {
-      acc = r[gi];
-      for (int64_t k = rowptr[gi], e = dstart[gi]; k < e; ++k) zfms(acc, T[k], y[col[k]]);
-    } else {
-      acc = zmake(0.0, 0.0);
-      for (int64_t k = ustart[gi], e = rowptr[gi + 1]; k < e; ++k) zfma(acc, T[k], y[col[k]]);
-    }
-    tvec[i] = acc;
+__global__ void __launch_bounds__(256)
+kb_node_tvec(int b, int o, const double2* __restrict__ r, const double2* __restrict__ y,
+             double2* __restrict__ t, const int64_t* __restrict__ rowptr,
+             const int64_t* __restrict__ dstart, const int64_t* __restrict__ ustart,
+             const int* __restrict__ col, const double2* __restrict__ T) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= b) return;
+  const int gi = o + i;
+  int64_t k0, k1;
+  if (MODE == 0) {
+    k0 = rowptr[gi];
+    k1 = dstart[gi];
+  } else {
+    k0 = ustart[gi];
+    k1 = rowptr[gi + 1];
   }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int row = blockIdx.x * KB_NODE_WARPS + wid;
-  if (row >= b) return;
-  const double2* Mrow = M + (size_t)row * b;
-  double2 acc0 = zmake(0.0, 0.0), acc1 = zmake(0.0, 0.0);
-  int j = lane;
-  for (; j + 32 < b; j += 64) {
-    double2 m0 = __ldcs(&Mrow[j]);
-    double2 m1 = __ldcs(&Mrow[j + 32]);
-    zfma(acc0, m0, tvec[j]);
-    zfma(acc1, m1, tvec[j + 32]);
-  }
-  if (j < b) zfma(acc0, __ldcs(&Mrow[j]), tvec[j]);
-  acc0 = zadd(acc0, acc1);
+  double2 acc = zmake(0.0, 0.0);
+  for (int64_t k = k0 + lane; k < k1; k += 32) zfma(acc, T[k], y[col[k]]);
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) {
-    acc0.x += __shfl_xor_sync(0xffffffffu, acc0.x, s);
-    acc0.y += __shfl_xor_sync(0xffffffffu, acc0.y, s);
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, s);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, s);
   }
-  if (lane == 0) {
-    if (MODE == 0)
-      y[o + row] = acc0;
-    else
-      y[o + row] = zsub(y[o + row], acc0);
+  if (lane == 0) t[gi] = (MODE == 0) ? zsub(r[gi], acc) : acc;
+}
+
+// Dense part of one node.  A CTA of 8 warps owns KB_NODE_ROWS rows of M_p; two
+// warps share a row (half each) and every lane keeps 8 independent 16-byte loads
+// in flight, so one CTA per SM has ~32 KB outstanding (HBM latency x bandwidth).
+//   MODE 0: y_p = M_p t_p          MODE 1: y_p -= M_p t_p
+#define KB_NODE_ROWS 4
+template <int MODE>
+__global__ void __launch_bounds__(256)
+kb_node_gemv(const double2* __restrict__ M, int b, int o, const double2* __restrict__ t,
+             double2* __restrict__ y) {
+  extern __shared__ double2 tvec[];  // b entries
+  __shared__ double2 part[8];
+  for (int i = threadIdx.x; i < b; i += blockDim.x) tvec[i] = t[o + i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int row = blockIdx.x * KB_NODE_ROWS + (wid >> 1);
+  const int half = wid & 1;
+  const int hb = (b + 1) >> 1;
+  const int j0 = half ? hb : 0, j1 = half ? b : hb;
+  double2 acc = zmake(0.0, 0.0);
+  if (row < b) {
+    const double2* Mrow = M + (size_t)row * b;
+    for (int j = j0 + lane; j < j1; j += 256) {
+      double2 m[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        int jj = j + 32 * u;
+        m[u] = jj < j1 ? __ldcs(&Mrow[jj]) : zmake(0.0, 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        int jj = j + 32 * u;
+        if (jj < j1) zfma(acc, m[u], tvec[jj]);
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, s);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, s);
+  }
+  if (lane == 0) part[wid] = acc;
+  __syncthreads();
+  if (threadIdx.x < KB_NODE_ROWS) {
+    int rr = blockIdx.x * KB_NODE_ROWS + threadIdx.x;
+    if (rr < b) {
+      double2 v = zadd(part[2 * threadIdx.x], part[2 * threadIdx.x + 1]);
+      if (MODE == 0)
+        y[o + rr] = v;
+      else
+        y[o + rr] = zsub(y[o + rr], v);
+    }
   }
 }
 
@@ -141,24 +178,63 @@ __global__ void kb_norm2_partial(int n, const double2* __restrict__ v, double* _
 }
 
 
-// one forward + backward sweep: y <- T'^{-1} r   (scaled chain space)
-static int chain_sweeps(kb_context* h, const double2* r, double2* y) {
+// one forward + backward sweep: y <- T'^{-1} r   (scaled chain space), raw launches
+static int chain_sweeps_launch(kb_context* h, const double2* r, double2* y) {
   cudaStream_t s = h->stream;
   const int64_t P = h->P;
+  double2* t = h->d_t.p;
   for (int64_t p = 0; p < P; ++p) {
     int o = (int)h->nodeptr[p], b = (int)(h->nodeptr[p + 1] - h->nodeptr[p]);
-    kb_node_apply<0><<<(b + KB_NODE_WARPS - 1) / KB_NODE_WARPS, KB_NODE_WARPS * 32, b * sizeof(double2), s>>>(
-        h->d_M.p + h->Moff[p], b, o, r, y, h->d_rowptr.p, h->d_dstart.p, h->d_ustart.p, h->d_col.p,
-        h->d_Tval.p);
+    kb_node_tvec<0><<<(b + 7) / 8, 256, 0, s>>>(b, o, r, y, t, h->d_rowptr.p, h->d_dstart.p, h->d_ustart.p,
+                                                h->d_col.p, h->d_Tval.p);
+    kb_node_gemv<0><<<(b + KB_NODE_ROWS - 1) / KB_NODE_ROWS, 256, b * sizeof(double2), s>>>(
+        h->d_M.p + h->Moff[p], b, o, t, y);
   }
   for (int64_t p = P - 2; p >= 0; --p) {
     int o = (int)h->nodeptr[p], b = (int)(h->nodeptr[p + 1] - h->nodeptr[p]);
-    kb_node_apply<1><<<(b + KB_NODE_WARPS - 1) / KB_NODE_WARPS, KB_NODE_WARPS * 32, b * sizeof(double2), s>>>(
-        h->d_M.p + h->Moff[p], b, o, r, y, h->d_rowptr.p, h->d_dstart.p, h->d_ustart.p, h->d_col.p,
-        h->d_Tval.p);
+    kb_node_tvec<1><<<(b + 7) / 8, 256, 0, s>>>(b, o, r, y, t, h->d_rowptr.p, h->d_dstart.p, h->d_ustart.p,
+                                                h->d_col.p, h->d_Tval.p);
+    kb_node_gemv<1><<<(b + KB_NODE_ROWS - 1) / KB_NODE_ROWS, 256, b * sizeof(double2), s>>>(
+        h->d_M.p + h->Moff[p], b, o, t, y);
   }
-  h->launches += 2 * P - 1;
   KB_LAUNCH_CHECK(h);
+  return KB_OK;
+}
+
+void kbi_drop_graphs(kb_context* h) {
+  for (auto& g : h->sweep_graphs)
+    if (g.exec) cudaGraphExecDestroy((cudaGraphExec_t)g.exec);
+  h->sweep_graphs.clear();
+}
+
+// The 2(2P-1) launches of a sweep pair are captured once per (r, y) buffer pair
+// and replayed as a CUDA graph: the chain is latency-bound, so per-launch CPU
+// and driver overhead is what the graph removes.
+static int chain_sweeps(kb_context* h, const double2* r, double2* y) {
+  cudaStream_t s = h->stream;
+  h->launches += 2 * (2 * h->P - 1);
+  for (auto& g : h->sweep_graphs)
+    if (g.r == r && g.y == y) {
+      KB_CUDA(h, cudaGraphLaunch((cudaGraphExec_t)g.exec, s));
+      return KB_OK;
+    }
+  if (h->sweep_graphs.size() >= 8) return chain_sweeps_launch(h, r, y);
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  KB_CUDA(h, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  int rc = chain_sweeps_launch(h, r, y);
+  cudaError_t e = cudaStreamEndCapture(s, &graph);
+  if (rc != KB_OK) return rc;
+  if (e != cudaSuccess) return kb_fail(h, KB_ECUDA, "graph capture failed: %s", cudaGetErrorString(e));
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return kb_fail(h, KB_ECUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+  kb_context::SweepGraph g;
+  g.r = r;
+  g.y = y;
+  g.exec = (void*)exec;
+  h->sweep_graphs.push_back(g);
+  KB_CUDA(h, cudaGraphLaunch(exec, s));
   return KB_OK;
 }
 
@@ -167,6 +243,7 @@ int kbi_solve_workspace(kb_context* h) {
   KB_CUDA(h, h->d_r.alloc(n));
   KB_CUDA(h, h->d_y.alloc(n));
   KB_CUDA(h, h->d_res.alloc(n));
+  KB_CUDA(h, h->d_t.alloc(n));
   KB_CUDA(h, h->d_x0.alloc(n));
   KB_CUDA(h, h->d_in.alloc(n));
   KB_CUDA(h, h->d_out.alloc(n));
@@ -181,6 +258,14 @@ int kbi_chain_solve(kb_context* h, const double2* r_dev, double2* x_dev, int ref
   }
   cudaStream_t s = h->stream;
   const int n = (int)h->n;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (h->time_sweeps) {
+    KB_CUDA(h, cudaEventCreate(&ev0));
+    KB_CUDA(h, cudaEventCreate(&ev1));
+    h->sweep_events.push_back(ev0);
+    h->sweep_events.push_back(ev1);
+    KB_CUDA(h, cudaEventRecord(ev0, s));
+  }
   KB_TRY(chain_sweeps(h, r_dev, x_dev));
   h->stats.solve_calls++;
   for (int it = 0; it < refine; ++it) {
@@ -191,6 +276,7 @@ int kbi_chain_solve(kb_context* h, const double2* r_dev, double2* x_dev, int ref
     h->launches += 2;
     h->stats.solve_calls++;
   }
+  if (ev1) KB_CUDA(h, cudaEventRecord(ev1, s));
   KB_LAUNCH_CHECK(h);
   return KB_OK;
 }

