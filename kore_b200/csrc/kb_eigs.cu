@@ -518,6 +518,7 @@ extern "C" int kb_eigs(kb_handle h, int nev, int ncv, double tol, int maxit, int
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   h->stats.eigs_ms = ms;
+  KB_TRY(kbi_check_sweep_error(h));
   for (size_t i = 0; i + 1 < h->sweep_events.size(); i += 2) {
     float t = 0.f;
     if (cudaEventElapsedTime(&t, h->sweep_events[i], h->sweep_events[i + 1]) == cudaSuccess)

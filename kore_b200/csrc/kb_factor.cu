@@ -82,7 +82,8 @@ __global__ void kb_col_apply(int64_t nnz, const int* __restrict__ col, const dou
 // ---------------------------------------------------------------------------
 // Schur block: S[i,:] = D_p[i,:] - sum_k L_{p,p-1}[i,k] W[k,:]     (one CTA per row)
 // ---------------------------------------------------------------------------
-__global__ void kb_schur_row(double2* __restrict__ S, int b, int o, const double2* __restrict__ W,
+__global__ void kb_schur_row(double2* __restrict__ S, double2* __restrict__ PT, int nb0, int b, int o,
+                             const double2* __restrict__ W,
                              int oprev, const int64_t* __restrict__ rowptr,
                              const int64_t* __restrict__ dstart, const int64_t* __restrict__ ustart,
                              const int* __restrict__ col, const double2* __restrict__ T) {
@@ -106,6 +107,9 @@ __global__ void kb_schur_row(double2* __restrict__ S, int b, int o, const double
     int c = col[k] - o;
     Srow[c] = zadd(Srow[c], T[k]);
   }
+  // first Gauss-Jordan panel, column-major, for kb_gj_panel
+  __syncthreads();
+  for (int j = threadIdx.x; j < nb0 && j < b; j += blockDim.x) PT[(size_t)j * b + i] = Srow[j];
 }
 
 // W = M_p U_{p,p+1}: W[i,j] = sum_{k in col j of U} M[i,k] U[k,j]   (one CTA per row i)
@@ -129,19 +133,110 @@ __global__ void kb_w_rows(const double2* __restrict__ M, int b, int o, double2* 
 // Blocked in-place Gauss-Jordan inversion with partial pivoting
 // ---------------------------------------------------------------------------
 // Panel step: columns [k0, k0+nbv) of all n rows live in registers, one (or RPT)
-// row(s) per thread.  On exit Gp (n x NB, row-major) holds the nontrivial columns
+// row(s) per thread; they arrive in the column-major side buffer PT (NB x n) that
+// the previous update step wrote, so loads and stores are coalesced.  On exit GpT
+// (NB x n) holds the nontrivial columns
 // of the composite Gauss-Jordan transform, srcrow[i] the pre-panel row that now
 // sits at position i, and orig[] the running row permutation of the whole
 // inversion.
+//
+// One column step = pivot search (integer keys: the high word of |a|^2, reduced
+// with redux.sync -- any entry within 2^-20 of the column maximum is an equally
+// good partial pivot), publish the pivot row through shared memory, eliminate.
+// The column loop is unrolled by two only and the register row is rotated by two
+// slots per trip, so the loop body stays small enough for the instruction cache
+// (a fully unrolled NB = 16 body is 140 KB of SASS and ran 2x slower).
+template <int NB, int RPT, int C>
+__device__ __forceinline__ void kb_gj_column(double2 (&a)[RPT][NB], const int gk, const int n, const int t,
+                                             const int T, const int lane, const int wid, const int nw,
+                                             double2* prow, double2* swp, unsigned* wk, int* wi,
+                                             int* s_src, int* s_orig, int* info) {
+  // ---- pivot search over positions >= gk
+  unsigned key = 0u;
+  int bi = 0x7fffffff;
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    int i = t + r * T;
+    if (i >= gk && i < n) {
+      unsigned kk = (unsigned)__double2hiint(zabs2(a[r][C])) + 1u;
+      if (kk > key) {
+        key = kk;
+        bi = i;
+      }
+    }
+  }
+  unsigned wmax = __reduce_max_sync(0xffffffffu, key);
+  unsigned who = __ballot_sync(0xffffffffu, key == wmax);
+  int wrow = __shfl_sync(0xffffffffu, bi, __ffs(who) - 1);
+  if (lane == 0) {
+    wk[wid] = wmax;
+    wi[wid] = wrow;
+  }
+  __syncthreads();
+  unsigned k2 = lane < nw ? wk[lane] : 0u;
+  int r2 = lane < nw ? wi[lane] : 0x7fffffff;
+  unsigned gmax = __reduce_max_sync(0xffffffffu, k2);
+  who = __ballot_sync(0xffffffffu, k2 == gmax);
+  const int rp = __shfl_sync(0xffffffffu, r2, __ffs(who) - 1);
+  // key 0: no candidate; 1: |pivot|^2 is zero/denormal; >= 0x7ff00001: inf or NaN
+  if (t == 0 && (gmax <= 1u || gmax >= 0x7ff00001u || rp >= n)) atomicExch(info, gk + 1);
+  const int rps = (rp < n) ? rp : gk;  // keep going on breakdown; host reports KB_ESINGULAR
+  // ---- publish the (unscaled) pivot row, and the row being displaced from position gk
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    int i = t + r * T;
+    if (i == rps) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) prow[j] = a[r][j];
+    }
+    if (i == gk && rps != gk) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) swp[j] = a[r][j];
+    }
+  }
+  if (t == 0) {
+    int tmp = s_src[gk];
+    s_src[gk] = s_src[rps];
+    s_src[rps] = tmp;
+    int to = s_orig[gk];
+    s_orig[gk] = s_orig[rps];
+    s_orig[rps] = to;
+  }
+  __syncthreads();
+  // ---- eliminate (every thread forms 1/pivot itself: no serial section)
+  const double2 pinv = zinv1(prow[C]);
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    int i = t + r * T;
+    if (i < n) {
+      if (i == gk) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) a[r][j] = (j == C) ? pinv : zmul(prow[j], pinv);
+      } else {
+        if (i == rps) {
+#pragma unroll
+          for (int j = 0; j < NB; ++j) a[r][j] = swp[j];
+        }
+        double2 g = zmul(a[r][C], pinv);
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+          if (j != C) zfms(a[r][j], g, prow[j]);
+        a[r][C] = zneg(g);
+      }
+    }
+  }
+  __syncthreads();
+}
+
 template <int NB, int RPT, int MAXT>
 __global__ void __launch_bounds__(MAXT)
-kb_gj_panel(const double2* __restrict__ Ain, int n, int k0, int nbv, double2* __restrict__ Gp,
+kb_gj_panel(const double2* __restrict__ PT, int n, int k0, int nbv, double2* __restrict__ GpT,
             int* __restrict__ orig, int* __restrict__ srcrow, int* __restrict__ info) {
   extern __shared__ int s_src[];  // n ints: pre-panel row at each position; then n ints: orig
   int* s_orig = s_src + n;
   __shared__ double2 prow[NB];
   __shared__ double2 swp[NB];
-  __shared__ double wv[32];
+  __shared__ unsigned wk[32];
   __shared__ int wi[32];
   const int T = blockDim.x;
   const int t = threadIdx.x;
@@ -153,7 +248,7 @@ kb_gj_panel(const double2* __restrict__ Ain, int n, int k0, int nbv, double2* __
     int i = t + r * T;
 #pragma unroll
     for (int j = 0; j < NB; ++j)
-      a[r][j] = (i < n && j < nbv) ? Ain[(size_t)i * n + k0 + j] : zmake(0.0, 0.0);
+      a[r][j] = (i < n && j < nbv) ? PT[(size_t)j * n + i] : zmake(0.0, 0.0);
   }
   for (int i = t; i < n; i += T) {
     s_src[i] = i;
@@ -161,113 +256,30 @@ kb_gj_panel(const double2* __restrict__ Ain, int n, int k0, int nbv, double2* __
   }
   __syncthreads();
 
-  // The column loop is NOT unrolled: after each step the register row is rotated
-  // left by one, so the active column is always a[.][0] and the loop body (about
-  // 9 KB of SASS instead of 140 KB) stays resident in the instruction cache.
+  int rot = 0;
 #pragma unroll 1
-  for (int k = 0; k < nbv; ++k) {
-    const int gk = k0 + k;
-    // ---- pivot search over positions >= gk
-    double bv = -1.0;
-    int bi = 0x7fffffff;
+  for (int k = 0; k < nbv; k += 2) {
+    kb_gj_column<NB, RPT, 0>(a, k0 + k, n, t, T, lane, wid, nw, prow, swp, wk, wi, s_src, s_orig, info);
+    if (k + 1 < nbv)
+      kb_gj_column<NB, RPT, 1>(a, k0 + k + 1, n, t, T, lane, wid, nw, prow, swp, wk, wi, s_src, s_orig, info);
+    // rotate the register row left by two: the next active columns are slots 0 and 1 again
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
-      int i = t + r * T;
-      if (i >= gk && i < n) {
-        double m = zabs2(a[r][0]);
-        if (m > bv || (m == bv && i < bi)) {  // NaN never wins: an all-NaN column is flagged below
-          bv = m;
-          bi = i;
-        }
-      }
+      double2 f0 = a[r][0], f1 = a[r][1];
+#pragma unroll
+      for (int j = 0; j + 2 < NB; ++j) a[r][j] = a[r][j + 2];
+      a[r][NB - 2] = f0;
+      a[r][NB - 1] = f1;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > bv || (ov == bv && oi < bi)) {
-        bv = ov;
-        bi = oi;
-      }
-    }
-    if (lane == 0) {
-      wv[wid] = bv;
-      wi[wid] = bi;
-    }
-    __syncthreads();
-    bv = lane < nw ? wv[lane] : -1.0;
-    bi = lane < nw ? wi[lane] : 0x7fffffff;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > bv || (ov == bv && oi < bi)) {
-        bv = ov;
-        bi = oi;
-      }
-    }
-    const int rp = bi;
-    if (t == 0) {
-      if (!(bv > 0.0) || isinf(bv) || rp >= n) atomicExch(info, gk + 1);
-    }
-    const int rps = (rp < n) ? rp : gk;  // keep going on breakdown; host reports KB_ESINGULAR
-    // ---- publish the (unscaled) pivot row, and the row being displaced from position gk
-#pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-      int i = t + r * T;
-      if (i == rps) {
-#pragma unroll
-        for (int j = 0; j < NB; ++j) prow[j] = a[r][j];
-      }
-      if (i == gk && rps != gk) {
-#pragma unroll
-        for (int j = 0; j < NB; ++j) swp[j] = a[r][j];
-      }
-    }
-    if (t == 0) {
-      int tmp = s_src[gk];
-      s_src[gk] = s_src[rps];
-      s_src[rps] = tmp;
-      int to = s_orig[gk];
-      s_orig[gk] = s_orig[rps];
-      s_orig[rps] = to;
-    }
-    __syncthreads();
-    // ---- eliminate (every thread forms 1/pivot itself: no serial section), then rotate
-    const double2 pinv = zinv1(prow[0]);
-#pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-      int i = t + r * T;
-      if (i < n) {
-        if (i == gk) {
-          a[r][0] = pinv;
-#pragma unroll
-          for (int j = 1; j < NB; ++j) a[r][j] = zmul(prow[j], pinv);
-        } else {
-          if (i == rps) {
-#pragma unroll
-            for (int j = 0; j < NB; ++j) a[r][j] = swp[j];
-          }
-          double2 g = zmul(a[r][0], pinv);
-#pragma unroll
-          for (int j = 1; j < NB; ++j) zfms(a[r][j], g, prow[j]);
-          a[r][0] = zneg(g);
-        }
-      }
-      double2 first = a[r][0];
-#pragma unroll
-      for (int j = 0; j + 1 < NB; ++j) a[r][j] = a[r][j + 1];
-      a[r][NB - 1] = first;
-    }
-    __syncthreads();
+    rot += 2;
   }
-  // register slot j now holds panel column (j + nbv) mod NB
+  // register slot j now holds panel column (j + rot) mod NB
 #pragma unroll
   for (int r = 0; r < RPT; ++r) {
     int i = t + r * T;
     if (i < n) {
 #pragma unroll
-      for (int j = 0; j < NB; ++j) Gp[(size_t)i * NB + ((j + nbv) % NB)] = a[r][j];
+      for (int j = 0; j < NB; ++j) GpT[(size_t)((j + rot) % NB) * n + i] = a[r][j];
     }
   }
   for (int i = t; i < n; i += T) {
@@ -282,7 +294,7 @@ kb_gj_panel(const double2* __restrict__ Ain, int n, int k0, int nbv, double2* __
 template <int NB, int TM>
 __global__ void __launch_bounds__(256)
 kb_gj_update(const double2* __restrict__ Ain, double2* __restrict__ Aout, int n, int k0, int nbv,
-             const double2* __restrict__ Gp, const int* __restrict__ srcrow) {
+             const double2* __restrict__ GpT, const int* __restrict__ srcrow, double2* __restrict__ PTnext) {
   constexpr int TN = 64;
   constexpr int RM = TM / 16;  // rows per thread
   __shared__ double2 Gs[TM][NB];
@@ -293,9 +305,9 @@ kb_gj_update(const double2* __restrict__ Ain, double2* __restrict__ Aout, int n,
   const int row0 = blockIdx.y * TM, col0 = blockIdx.x * TN;
 
   for (int e = tid; e < TM * NB; e += 256) {
-    int i = e / NB, k = e % NB;
+    int k = e / TM, i = e % TM;
     int gi = row0 + i;
-    Gs[i][k] = (gi < n && k < nbv) ? Gp[(size_t)gi * NB + k] : zmake(0.0, 0.0);
+    Gs[i][k] = (gi < n && k < nbv) ? GpT[(size_t)k * n + gi] : zmake(0.0, 0.0);
   }
   for (int e = tid; e < NB * TN; e += 256) {
     int k = e / TN, j = e % TN;
@@ -341,6 +353,8 @@ kb_gj_update(const double2* __restrict__ Ain, double2* __restrict__ Aout, int n,
       double2 v = acc[a][c];
       if (gj >= k0 && gj < k0 + nbv) v = Gs[i][gj - k0];
       Aout[(size_t)gi * n + gj] = v;
+      // the next panel's columns also go, column-major, to the panel kernel's input buffer
+      if (gj >= k0 + NB && gj < k0 + 2 * NB) PTnext[(size_t)(gj - k0 - NB) * n + gi] = v;
     }
   }
 }
@@ -356,11 +370,11 @@ __global__ void kb_store_inverse(const double2* __restrict__ X, int n, const int
 // host drivers
 // ---------------------------------------------------------------------------
 template <int NB, int RPT, int MAXT>
-static void launch_panel(kb_context* h, const double2* in, int n, int k0, int nbv) {
+static void launch_panel(kb_context* h, int n, int k0, int nbv) {
   int T = (n + RPT - 1) / RPT;
   T = ((T + 31) / 32) * 32;
   if (T > MAXT) T = MAXT;
-  kb_gj_panel<NB, RPT, MAXT><<<1, T, 2 * n * sizeof(int), h->stream>>>(in, n, k0, nbv, h->d_Gp.p, h->d_orig.p,
+  kb_gj_panel<NB, RPT, MAXT><<<1, T, 2 * n * sizeof(int), h->stream>>>(h->d_PT.p, n, k0, nbv, h->d_Gp.p, h->d_orig.p,
                                                                   h->d_srcrow.p, h->d_info.p);
 }
 
@@ -368,7 +382,7 @@ template <int NB>
 static void launch_update(kb_context* h, const double2* in, double2* out, int n, int k0, int nbv) {
   constexpr int TM = 32;
   dim3 grid((n + 63) / 64, (n + TM - 1) / TM);
-  kb_gj_update<NB, TM><<<grid, 256, 0, h->stream>>>(in, out, n, k0, nbv, h->d_Gp.p, h->d_srcrow.p);
+  kb_gj_update<NB, TM><<<grid, 256, 0, h->stream>>>(in, out, n, k0, nbv, h->d_Gp.p, h->d_srcrow.p, h->d_PT.p);
 }
 
 int kbi_panel_width(const kb_context* h, int n) {
@@ -393,18 +407,18 @@ static int gj_invert(kb_context* h, double2* S0, double2* S1, int n, double2** r
   for (int k0 = 0; k0 < n; k0 += NB) {
     int nbv = n - k0 < NB ? n - k0 : NB;
     if (NB == 16) {
-      launch_panel<16, 1, 640>(h, in, n, k0, nbv);
+      launch_panel<16, 2, 320>(h, n, k0, nbv);
       launch_update<16>(h, in, out, n, k0, nbv);
     } else if (NB == 8) {
-      launch_panel<8, 1, 1024>(h, in, n, k0, nbv);
+      launch_panel<8, 2, 512>(h, n, k0, nbv);
       launch_update<8>(h, in, out, n, k0, nbv);
     } else {
       if (n <= 1024)
-        launch_panel<4, 1, 1024>(h, in, n, k0, nbv);
+        launch_panel<4, 2, 512>(h, n, k0, nbv);
       else if (n <= 2048)
-        launch_panel<4, 2, 1024>(h, in, n, k0, nbv);
+        launch_panel<4, 4, 512>(h, n, k0, nbv);
       else
-        launch_panel<4, 4, 1024>(h, in, n, k0, nbv);
+        launch_panel<4, 4, 1024>(h, n, k0, nbv);
       launch_update<4>(h, in, out, n, k0, nbv);
     }
     h->launches += 2;
@@ -463,6 +477,7 @@ int kbi_factor(kb_context* h, zcomplex sigma) {
   KB_CUDA(h, h->d_S1.alloc((size_t)bmax * bmax));
   KB_CUDA(h, h->d_W.alloc((size_t)bmax * bmax));
   KB_CUDA(h, h->d_Gp.alloc((size_t)bmax * 16));
+  KB_CUDA(h, h->d_PT.alloc((size_t)bmax * 16));
   KB_CUDA(h, h->d_orig.alloc(bmax));
   KB_CUDA(h, h->d_srcrow.alloc(bmax));
   KB_CUDA(h, h->d_info.alloc(1));
@@ -473,7 +488,8 @@ int kbi_factor(kb_context* h, zcomplex sigma) {
     const int o = (int)h->nodeptr[p];
     const int b = (int)(h->nodeptr[p + 1] - h->nodeptr[p]);
     const int oprev = p > 0 ? (int)h->nodeptr[p - 1] : 0;
-    kb_schur_row<<<b, 128, 0, s>>>(h->d_S0.p, b, o, p > 0 ? h->d_W.p : nullptr, oprev, h->d_rowptr.p,
+    kb_schur_row<<<b, 128, 0, s>>>(h->d_S0.p, h->d_PT.p, kbi_panel_width(h, b), b, o,
+                                   p > 0 ? h->d_W.p : nullptr, oprev, h->d_rowptr.p,
                                    h->d_dstart.p, h->d_ustart.p, h->d_col.p, h->d_Tval.p);
     h->launches++;
     double2* X = nullptr;
@@ -491,6 +507,7 @@ int kbi_factor(kb_context* h, zcomplex sigma) {
     }
     KB_LAUNCH_CHECK(h);
   }
+  KB_TRY(kbi_sweep_prepare(h));
   KB_CUDA(h, cudaEventRecord(e1, s));
   int info = 0;
   KB_CUDA(h, cudaMemcpyAsync(&info, h->d_info.p, sizeof(int), cudaMemcpyDeviceToHost, s));

@@ -191,7 +191,17 @@ struct kb_context {
   std::vector<int64_t> Moff;  // P+1 offsets (in complex elements) of M_p in d_M
   DevBuf<double2> d_M;
   // factor workspaces
-  DevBuf<double2> d_S0, d_S1, d_W, d_Gp;
+  DevBuf<double2> d_S0, d_S1, d_W, d_Gp, d_PT;
+  // ELL copies of the couplings + node tables for the persistent sweep kernel
+  int WL = 0, WU = 0;
+  DevBuf<double2> d_Lval, d_Uval;
+  DevBuf<int> d_Lcol, d_Ucol;
+  DevBuf<int64_t> d_nodeptr, d_Moff;
+  DevBuf<unsigned> d_flags;
+  DevBuf<int> d_sweep_err;
+  DevBuf<long long> d_sweep_timing;
+  int sweep_grid = 0;
+  int opt_sweep = 1;
   DevBuf<int> d_orig, d_srcrow, d_piv, d_info;
 
   // solve workspaces (chain order, scaled space)
@@ -238,7 +248,11 @@ int kbi_spmv_A_chain(kb_context* h, const double2* x, double2* y);
 int kbi_to_chain(kb_context* h, const double2* x_orig_dev, double2* x_chain_dev);
 int kbi_from_chain(kb_context* h, const double2* x_chain_dev, double2* x_orig_dev);
 int kbi_solve_workspace(kb_context* h);
+int kbi_check_sweep_error(kb_context* h);
 void kbi_drop_graphs(kb_context* h);
+// ---- kb_sweep.cu
+int kbi_sweep_prepare(kb_context* h);
+int kbi_sweep_persistent(kb_context* h, const double2* r, double2* y);
 // ---- kb_shard.cu
 int kbi_factor_sharded(kb_context* h, zcomplex sigma);
 int kbi_chain_solve_sharded(kb_context* h, const double2* r_dev, double2* x_dev, int refine);

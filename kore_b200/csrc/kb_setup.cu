@@ -83,6 +83,7 @@ extern "C" int kb_set_option(kb_handle h, int option, int64_t value) {
     case KB_OPT_SEED: h->opt_seed = value; break;
     case KB_OPT_PANEL: h->opt_panel = (int)value; break;
     case 6: h->opt_refine_eigs = (int)std::max<int64_t>(0, value); break;
+    case 7: h->opt_sweep = value != 0; break;
     default: return kb_fail(h, KB_EINVAL, "unknown option %d", option);
   }
   return KB_OK;
@@ -255,7 +256,7 @@ extern "C" int kb_set_chain(kb_handle h, const int64_t* perm, const int64_t* nod
   std::vector<double2> aval(nnz), bval(nnz);
   std::vector<int64_t> dstart(n), ustart(n);
   std::vector<int64_t> ucount(n + 1, 0);
-  int64_t nnzA = 0, nnzB = 0;
+  int64_t nnzA = 0, nnzB = 0, wl = 0, wu = 0;
   for (int64_t i = 0; i < n; ++i) {
     int64_t k = rowptr[i];
     int p = node_of[i];
@@ -277,6 +278,8 @@ extern "C" int kb_set_chain(kb_handle h, const int64_t* perm, const int64_t* nod
     if (ds < 0) ds = us;
     dstart[i] = ds;
     ustart[i] = us;
+    wl = std::max<int64_t>(wl, ds - rowptr[i]);
+    wu = std::max<int64_t>(wu, rowptr[i + 1] - us);
   }
   // U by column
   for (int64_t c = 0; c < n; ++c) ucount[c + 1] += ucount[c];
@@ -352,6 +355,8 @@ extern "C" int kb_set_chain(kb_handle h, const int64_t* perm, const int64_t* nod
   KB_CUDA(h, h->d_maxbits.alloc(n));
   KB_CUDA(h, cudaStreamSynchronize(s));
 
+  h->WL = (int)wl;
+  h->WU = (int)wu;
   h->chain_set = true;
   h->factored = false;
   return KB_OK;

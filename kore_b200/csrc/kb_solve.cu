@@ -212,6 +212,7 @@ void kbi_drop_graphs(kb_context* h) {
 // and driver overhead is what the graph removes.
 static int chain_sweeps(kb_context* h, const double2* r, double2* y) {
   cudaStream_t s = h->stream;
+  if (h->opt_sweep && h->sweep_grid > 0) return kbi_sweep_persistent(h, r, y);
   h->launches += 2 * (2 * h->P - 1);
   for (auto& g : h->sweep_graphs)
     if (g.r == r && g.y == y) {
@@ -238,13 +239,32 @@ static int chain_sweeps(kb_context* h, const double2* r, double2* y) {
   return KB_OK;
 }
 
+int kbi_check_sweep_error(kb_context* h) {
+  // call after a stream synchronisation
+  if (!h->d_sweep_err.p) return KB_OK;
+  int e = 0;
+  KB_CUDA(h, cudaMemcpy(&e, h->d_sweep_err.p, sizeof(int), cudaMemcpyDeviceToHost));
+  if (e) {
+    cudaMemset(h->d_sweep_err.p, 0, sizeof(int));
+    return kb_fail(h, KB_ECUDA, "grid barrier of the persistent sweep kernel timed out");
+  }
+  return KB_OK;
+}
+
 int kbi_solve_workspace(kb_context* h) {
   const int64_t n = h->n;
   KB_CUDA(h, h->d_r.alloc(n));
-  KB_CUDA(h, h->d_y.alloc(n));
+  // solution buffers carry a zero sentinel at [n] (padding target of the ELL couplings)
+  if (h->d_y.count < (size_t)n + 1) {
+    KB_CUDA(h, h->d_y.alloc(n + 1));
+    KB_CUDA(h, cudaMemsetAsync(h->d_y.p, 0, (size_t)(n + 1) * sizeof(double2), h->stream));
+  }
+  if (h->d_x0.count < (size_t)n + 1) {
+    KB_CUDA(h, h->d_x0.alloc(n + 1));
+    KB_CUDA(h, cudaMemsetAsync(h->d_x0.p, 0, (size_t)(n + 1) * sizeof(double2), h->stream));
+  }
   KB_CUDA(h, h->d_res.alloc(n));
   KB_CUDA(h, h->d_t.alloc(n));
-  KB_CUDA(h, h->d_x0.alloc(n));
   KB_CUDA(h, h->d_in.alloc(n));
   KB_CUDA(h, h->d_out.alloc(n));
   KB_CUDA(h, h->d_partial.alloc(1024));
@@ -365,7 +385,7 @@ static int solve_dev_impl(kb_context* h, const double2* rhs_dev, double2* x_dev,
     bytes += 2.0 * 16.0 * b * b;
   }
   h->stats.solve_bytes = bytes + 3.0 * 16.0 * n;
-  return KB_OK;
+  return kbi_check_sweep_error(h);
 }
 
 extern "C" int kb_solve_dev(kb_handle h, const double* rhs_dev, double* x_dev, int nrhs) {

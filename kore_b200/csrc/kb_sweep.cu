@@ -1,0 +1,411 @@
+// Persistent chain-sweep kernel: the whole forward + backward block substitution
+// of one solve in ONE cooperative launch, one CTA per SM.
+//
+// Replaces the per-node launches of kb_solve.cu (2(2P-1) kernels per solve) on the
+// path that dominates the Krylov phase: the MUMPS solve phase inside every ST
+// application of E.solve() (/root/reference/bin/solve.py:123).
+//
+// The chain is a sequence of 2P-1 dependent node steps; each step is
+//   A) t = r_p - L_{p,p-1} y_{p-1}   (fwd)   |   t = U_{p,p+1} x_{p+1}   (bwd)
+//   B) y_p = M_p t                   (fwd)   |   x_p = y_p - M_p t       (bwd)
+// Every CTA owns a fixed slice of rows of every node.  A needs the whole previous
+// result and B the whole t, so each step has two grid-wide synchronisations; they
+// are counter barriers (one release-add per CTA, one polling thread per CTA).
+// The HBM stream of the explicit inverses M_p is decoupled from that latency
+// chain by bulk L2 prefetches (cp.async.bulk.prefetch.L2) issued two steps ahead.
+// The couplings are read from an ELL copy (fixed width per pencil, built at
+// factor time) so that a CTA's slice is one contiguous range.
+#include <stdlib.h>
+
+#include "kb_internal.cuh"
+
+#define KB_SWEEP_THREADS 256
+#define KB_SPIN_LIMIT (1 << 22)
+#define KB_FLAG_STRIDE 8  // 32-byte slots
+
+struct KbSweepParams {
+  const double2* M;
+  const int64_t* Moff;
+  const int64_t* nodeptr;
+  int P;
+  const double2* r;
+  double2* y;
+  double2* t;
+  const double2* Lval;
+  const int* Lcol;
+  int WL;
+  const double2* Uval;
+  const int* Ucol;
+  int WU;
+  unsigned* flags;
+  int* err;
+  long long* timing;  // optional: 5 accumulated cycle counters per CTA (debug)
+  int bmax;
+};
+
+__device__ __forceinline__ void kb_st_release(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned kb_ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void kb_prefetch_l2(const void* p, size_t bytes) {
+  // p 16-byte aligned, bytes a multiple of 16
+  if (bytes == 0) return;
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"((unsigned)bytes) : "memory");
+}
+
+// Grid-wide barrier: one release-add per CTA on a single counter, one polling thread
+// per CTA (a flag array polled by every CTA was measured 10x slower: ~22 000 polling
+// loads per round contend on a handful of L2 slices).  bar.sync + red.release.gpu is
+// cumulative over the CTA's earlier writes, ld.acquire.gpu + bar.sync publishes the
+// other CTAs' writes to the whole CTA; no extra fences.  `epoch` counts from 1.
+__device__ __forceinline__ void kb_grid_sync(unsigned* ctr, unsigned epoch, int* err) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned target = epoch * gridDim.x;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+    unsigned v;
+    int spins = 0;
+    do {
+      v = kb_ld_acquire(ctr);
+      // fail fast: once any CTA has timed out, nobody waits any more
+      if ((++spins & 1023) == 0 && *(volatile int*)err != 0) break;
+    } while (v < target && spins < KB_SPIN_LIMIT);
+    if (v < target) atomicExch(err, 1);
+  }
+  __syncthreads();
+}
+
+// ---- mbarrier + 1-D bulk (TMA) copy helpers
+__device__ __forceinline__ unsigned kb_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void kb_mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(kb_smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void kb_mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(kb_smem_addr(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void kb_bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   kb_smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(kb_smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void kb_mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned done = 0;
+  int spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(kb_smem_addr(bar)), "r"(parity)
+        : "memory");
+  } while (!done && ++spins < KB_SPIN_LIMIT);
+}
+
+// rows of a b-row node owned by this CTA
+__device__ __forceinline__ void kb_my_rows(int b, int& row0, int& row1) {
+  int rpc = (b + gridDim.x - 1) / gridDim.x;
+  row0 = min(b, (int)blockIdx.x * rpc);
+  row1 = min(b, row0 + rpc);
+}
+
+__device__ __forceinline__ void kb_step_node(const KbSweepParams& q, int s, bool& fwd, int& p) {
+  fwd = s < q.P;
+  p = fwd ? s : 2 * q.P - 2 - s;
+}
+
+// STAGED: this CTA's slice of M_p is brought into shared memory by a bulk (TMA)
+// copy issued one step ahead (double buffered); otherwise it is read straight from
+// global/L2 (slices too large for two stages).
+template <bool STAGED>
+__global__ void __launch_bounds__(KB_SWEEP_THREADS, 1) kb_sweep_persistent(KbSweepParams q, int slice_elems) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double2* tvec = (double2*)smem_raw;                       // q.bmax entries
+  double2* stage0 = tvec + ((q.bmax + 7) & ~7);             // STAGED: 2 x slice_elems
+  // node tables (offset of every node, offset of every M_p) cached in shared memory: they sit
+  // on the critical path of every step otherwise
+  int64_t* s_moff = (int64_t*)(stage0 + (STAGED ? 2 * (size_t)slice_elems : 0));
+  int* s_nptr = (int*)(s_moff + (q.P + 1));
+  __shared__ double2 part[8][8];
+  __shared__ __align__(8) uint64_t mbar[2];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int P = q.P;
+  const int S = 2 * P - 1;
+  unsigned epoch = 0;
+  unsigned uses[2] = {0u, 0u};  // completed uses of each stage (mbarrier phase parity), uniform per CTA
+  long long tacc[5] = {0, 0, 0, 0, 0};
+  long long tc0 = clock64();
+#define KB_TICK(slot)         \
+  {                           \
+    long long _c = clock64(); \
+    tacc[slot] += _c - tc0;   \
+    tc0 = _c;                 \
+  }
+
+  for (int i = tid; i <= q.P; i += KB_SWEEP_THREADS) {
+    s_moff[i] = q.Moff[i];
+    s_nptr[i] = (int)q.nodeptr[i];
+  }
+  __syncthreads();
+  if (STAGED) {
+    if (tid == 0) {
+      kb_mbar_init(&mbar[0], 1);
+      kb_mbar_init(&mbar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {  // stage the first step's slice
+      bool f0;
+      int p0;
+      kb_step_node(q, 0, f0, p0);
+      const int b0 = (s_nptr[p0 + 1] - s_nptr[p0]);
+      int a0, a1;
+      kb_my_rows(b0, a0, a1);
+      unsigned bytes = (unsigned)((size_t)(a1 - a0) * b0 * sizeof(double2));
+      if (bytes) {
+        kb_mbar_expect_tx(&mbar[0], bytes);
+        kb_bulk_g2s(stage0, q.M + s_moff[p0] + (size_t)a0 * b0, bytes, &mbar[0]);
+      }
+    }
+  }
+
+  for (int s = 0; s < S; ++s) {
+    bool fwd;
+    int p;
+    kb_step_node(q, s, fwd, p);
+    const int o = s_nptr[p];
+    const int b = (s_nptr[p + 1] - s_nptr[p]);
+    int row0, row1;
+    kb_my_rows(b, row0, row1);
+
+    // ---- next step's slice: bulk copy into the other stage (its last readers finished
+    //      before the previous grid barrier), or an L2 prefetch two steps ahead
+    if (STAGED) {
+      if (tid == 0 && s + 1 < S) {
+        bool f1;
+        int p1;
+        kb_step_node(q, s + 1, f1, p1);
+        const int b1 = (s_nptr[p1 + 1] - s_nptr[p1]);
+        int a0, a1;
+        kb_my_rows(b1, a0, a1);
+        unsigned bytes = (unsigned)((size_t)(a1 - a0) * b1 * sizeof(double2));
+        if (bytes) {
+          uint64_t* mb = &mbar[(s + 1) & 1];
+          kb_mbar_expect_tx(mb, bytes);
+          kb_bulk_g2s(stage0 + (size_t)((s + 1) & 1) * slice_elems, q.M + s_moff[p1] + (size_t)a0 * b1, bytes, mb);
+        }
+      }
+    }
+    if (tid == 32 && s + 2 < S) {
+      bool f2;
+      int p2;
+      kb_step_node(q, s + 2, f2, p2);
+      const int o2 = s_nptr[p2];
+      const int b2 = (s_nptr[p2 + 1] - s_nptr[p2]);
+      int a0, a1;
+      kb_my_rows(b2, a0, a1);
+      if (a1 > a0) {
+        const double2* m = q.M + s_moff[p2] + (size_t)a0 * b2;
+        size_t bytes = (size_t)(a1 - a0) * b2 * sizeof(double2);
+        while (bytes > 0) {
+          size_t c = bytes > 65536 ? 65536 : bytes;
+          kb_prefetch_l2(m, c);
+          m = (const double2*)((const char*)m + c);
+          bytes -= c;
+        }
+        const int W = f2 ? q.WL : q.WU;
+        const double2* v = (f2 ? q.Lval : q.Uval) + (size_t)(o2 + a0) * W;
+        kb_prefetch_l2(v, (size_t)(a1 - a0) * W * sizeof(double2));
+        const int* c = (f2 ? q.Lcol : q.Ucol) + (size_t)(o2 + a0) * W;
+        uintptr_t c0 = (uintptr_t)c & ~(uintptr_t)15;
+        uintptr_t c1 = ((uintptr_t)(c + (size_t)(a1 - a0) * W) + 15) & ~(uintptr_t)15;
+        kb_prefetch_l2((const void*)c0, (size_t)(c1 - c0));
+      }
+    }
+    KB_TICK(0);
+
+    // ---- phase A: sparse coupling for the rows this CTA owns (one warp per row)
+    {
+      const int W = fwd ? q.WL : q.WU;
+      const double2* val = fwd ? q.Lval : q.Uval;
+      const int* col = fwd ? q.Lcol : q.Ucol;
+      for (int i = row0 + wid; i < row1; i += KB_SWEEP_THREADS / 32) {
+        const int gi = o + i;
+        double2 acc = zmake(0.0, 0.0);
+        for (int k = lane; k < W; k += 32) {
+          double2 v = val[(size_t)gi * W + k];
+          int c = col[(size_t)gi * W + k];
+          zfma(acc, v, __ldcg(&q.y[c]));
+        }
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) {
+          acc.x += __shfl_xor_sync(0xffffffffu, acc.x, sft);
+          acc.y += __shfl_xor_sync(0xffffffffu, acc.y, sft);
+        }
+        if (lane == 0) q.t[gi] = fwd ? zsub(q.r[gi], acc) : acc;
+      }
+    }
+    KB_TICK(1);
+    kb_grid_sync(q.flags, ++epoch, q.err);
+    KB_TICK(2);
+
+    // ---- phase B: dense rows of M_p against the full t
+    for (int j = tid; j < b; j += KB_SWEEP_THREADS) tvec[j] = __ldcg(&q.t[o + j]);
+    if (STAGED && row1 > row0) {
+      kb_mbar_wait(&mbar[s & 1], uses[s & 1] & 1u);
+      uses[s & 1]++;
+    }
+    __syncthreads();
+    const double2* Mp = STAGED ? (stage0 + (size_t)(s & 1) * slice_elems) : (q.M + s_moff[p] + (size_t)row0 * b);
+    for (int rb = 0; rb < row1 - row0; rb += 8) {
+      const int nr = min(8, row1 - row0 - rb);
+      double2 acc[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] = zmake(0.0, 0.0);
+      for (int j = tid; j < b; j += KB_SWEEP_THREADS) {
+        const double2 tj = tvec[j];
+        double2 m[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (STAGED)
+            m[u] = u < nr ? Mp[(size_t)(rb + u) * b + j] : zmake(0.0, 0.0);
+          else
+            m[u] = u < nr ? __ldcs(&Mp[(size_t)(rb + u) * b + j]) : zmake(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) zfma(acc[u], m[u], tj);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) {
+          acc[u].x += __shfl_xor_sync(0xffffffffu, acc[u].x, sft);
+          acc[u].y += __shfl_xor_sync(0xffffffffu, acc[u].y, sft);
+        }
+        if (lane == 0) part[u][wid] = acc[u];
+      }
+      __syncthreads();
+      if (tid < nr) {
+        double2 v = zmake(0.0, 0.0);
+#pragma unroll
+        for (int w = 0; w < KB_SWEEP_THREADS / 32; ++w) v = zadd(v, part[tid][w]);
+        const int gi = o + row0 + rb + tid;
+        q.y[gi] = fwd ? v : zsub(__ldcg(&q.y[gi]), v);
+      }
+      __syncthreads();
+    }
+    KB_TICK(3);
+    kb_grid_sync(q.flags, ++epoch, q.err);
+    KB_TICK(4);
+  }
+  if (q.timing && tid == 0)
+    for (int k = 0; k < 5; ++k) q.timing[blockIdx.x * 5 + k] = tacc[k];
+}
+
+// ELL copies of the couplings (built at factor time from the equilibrated T):
+// row gi, slot k:  L part = entries [rowptr, dstart), U part = [ustart, rowptr+1).
+// Padding: value 0, column n (the vector buffers carry a zero sentinel at [n]).
+__global__ void kb_pack_ell(int n, int WL, int WU, const int64_t* __restrict__ rowptr,
+                            const int64_t* __restrict__ dstart, const int64_t* __restrict__ ustart,
+                            const int* __restrict__ col, const double2* __restrict__ T,
+                            double2* __restrict__ Lval, int* __restrict__ Lcol, double2* __restrict__ Uval,
+                            int* __restrict__ Ucol) {
+  int gi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (gi >= n) return;
+  int64_t l0 = rowptr[gi], l1 = dstart[gi], u0 = ustart[gi], u1 = rowptr[gi + 1];
+  for (int k = lane; k < WL; k += 32) {
+    bool ok = l0 + k < l1;
+    Lval[(size_t)gi * WL + k] = ok ? T[l0 + k] : zmake(0.0, 0.0);
+    Lcol[(size_t)gi * WL + k] = ok ? col[l0 + k] : n;
+  }
+  for (int k = lane; k < WU; k += 32) {
+    bool ok = u0 + k < u1;
+    Uval[(size_t)gi * WU + k] = ok ? T[u0 + k] : zmake(0.0, 0.0);
+    Ucol[(size_t)gi * WU + k] = ok ? col[u0 + k] : n;
+  }
+}
+
+int kbi_sweep_prepare(kb_context* h) {
+  // called at the end of kb_factor: ELL copies + device copies of the node tables
+  cudaStream_t s = h->stream;
+  const int n = (int)h->n;
+  const int WL = h->WL > 0 ? h->WL : 1, WU = h->WU > 0 ? h->WU : 1;
+  KB_CUDA(h, h->d_Lval.alloc((size_t)n * WL));
+  KB_CUDA(h, h->d_Lcol.alloc((size_t)n * WL + 4));
+  KB_CUDA(h, h->d_Uval.alloc((size_t)n * WU));
+  KB_CUDA(h, h->d_Ucol.alloc((size_t)n * WU + 4));
+  kb_pack_ell<<<nblk((int64_t)n * 32, 256), 256, 0, s>>>(n, WL, WU, h->d_rowptr.p, h->d_dstart.p, h->d_ustart.p,
+                                                         h->d_col.p, h->d_Tval.p, h->d_Lval.p, h->d_Lcol.p,
+                                                         h->d_Uval.p, h->d_Ucol.p);
+  h->launches++;
+  KB_LAUNCH_CHECK(h);
+  KB_CUDA(h, h->d_nodeptr.alloc(h->P + 1));
+  KB_CUDA(h, h->d_Moff.alloc(h->P + 1));
+  KB_CUDA(h, cudaMemcpyAsync(h->d_nodeptr.p, h->nodeptr.data(), (h->P + 1) * sizeof(int64_t),
+                             cudaMemcpyHostToDevice, s));
+  KB_CUDA(h, cudaMemcpyAsync(h->d_Moff.p, h->Moff.data(), (h->P + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  KB_CUDA(h, h->d_flags.alloc(256 * KB_FLAG_STRIDE));
+  KB_CUDA(h, h->d_sweep_err.alloc(1));
+  if (getenv("KB_SWEEP_TIMING")) KB_CUDA(h, h->d_sweep_timing.alloc(256 * 5));
+  KB_CUDA(h, cudaMemsetAsync(h->d_sweep_err.p, 0, sizeof(int), s));
+  if (h->sweep_grid == 0) {
+    int dev = h->device, sms = 0, coop = 0;
+    KB_CUDA(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    KB_CUDA(h, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    h->sweep_grid = coop ? (sms < KB_SWEEP_THREADS ? sms : KB_SWEEP_THREADS) : -1;
+  }
+  return KB_OK;
+}
+
+// y <- T'^{-1} r in one cooperative launch.  y must have n+1 entries with y[n] == 0.
+int kbi_sweep_persistent(kb_context* h, const double2* r, double2* y) {
+  cudaStream_t s = h->stream;
+  KbSweepParams q;
+  q.M = h->d_M.p;
+  q.Moff = h->d_Moff.p;
+  q.nodeptr = h->d_nodeptr.p;
+  q.P = (int)h->P;
+  q.r = r;
+  q.y = y;
+  q.t = h->d_t.p;
+  q.Lval = h->d_Lval.p;
+  q.Lcol = h->d_Lcol.p;
+  q.WL = h->WL > 0 ? h->WL : 1;
+  q.Uval = h->d_Uval.p;
+  q.Ucol = h->d_Ucol.p;
+  q.WU = h->WU > 0 ? h->WU : 1;
+  q.flags = h->d_flags.p;
+  q.err = h->d_sweep_err.p;
+  q.timing = h->d_sweep_timing.p;
+  q.bmax = (int)h->bmax;
+  const int G = h->sweep_grid;
+  const int rpc = (int)((h->bmax + G - 1) / G);
+  int slice_elems = (int)(((int64_t)rpc * h->bmax + 7) & ~(int64_t)7);
+  const size_t tv = (size_t)((h->bmax + 7) & ~(int64_t)7) * sizeof(double2);
+  const size_t tabs = (size_t)(h->P + 1) * (sizeof(int64_t) + sizeof(int)) + 16;
+  size_t smem_staged = tv + 2 * (size_t)slice_elems * sizeof(double2) + tabs;
+  const bool staged = smem_staged <= 200 * 1024;
+  size_t smem = staged ? smem_staged : tv + tabs;
+  if (smem > 220 * 1024) return kb_fail(h, KB_EINVAL, "chain too long for the persistent sweep tables");
+  const void* fn = staged ? (const void*)kb_sweep_persistent<true> : (const void*)kb_sweep_persistent<false>;
+  if (smem > 48 * 1024) KB_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  KB_CUDA(h, cudaMemsetAsync(h->d_flags.p, 0, 256 * KB_FLAG_STRIDE * sizeof(unsigned), s));
+  void* args[] = {(void*)&q, (void*)&slice_elems};
+  KB_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(G), dim3(KB_SWEEP_THREADS), args, smem, s));
+  h->launches++;
+  return KB_OK;
+}
+
+// debug: cycle counters of the last persistent sweep (needs KB_SWEEP_TIMING=1 at factor time)
+extern "C" int kb_dbg_sweep_timing(kb_handle h, long long* out, int max_ctas) {
+  if (!h || !h->d_sweep_timing.p) return KB_EINVAL;
+  cudaStreamSynchronize(h->stream);
+  int g = h->sweep_grid < max_ctas ? h->sweep_grid : max_ctas;
+  cudaMemcpy(out, h->d_sweep_timing.p, (size_t)g * 5 * sizeof(long long), cudaMemcpyDeviceToHost);
+  return g;
+}

@@ -2,6 +2,7 @@
 // files below, so they are compiled together instead of with -rdc).
 #include "kb_setup.cu"
 #include "kb_factor.cu"
+#include "kb_sweep.cu"
 #include "kb_solve.cu"
 #include "kb_eigs.cu"
 #include "kb_shard.cu"

@@ -1,0 +1,171 @@
+#!/usr/bin/env python3
+"""Drop-in for Kore's bin/solve.py on a B200.
+
+Same inputs, same outputs, same parameter semantics:
+
+    cd <run dir with A.npz and B.npz | B_forced.npz, and bin/parameters.py>
+    python -m kore_b200.solve $opts          # instead of: mpiexec -n k ./bin/solve.py $opts
+
+Reads  : A.npz, B.npz (eigen problem) or B_forced.npz (forced problem)   solve.py:40, 65, 209
+         bin/parameters.py  (forcing, nev, tol, maxit, which_eigenpairs, tau, hydro, magnetic,
+                             thermal, compositional, m, lmax, N, symm, ricb, B0)
+         argv: PETSc-style options (-st_type sinvert, -eps_*; solver-package options are
+               accepted and ignored, see kore_b200/eps.py)
+Writes : eigenvalues0.dat, real_/imag_{flow,magnetic,temperature,composition}.field,
+         timing.dat (appended), no_conv_solution (when nothing converged)   solve.py:194-199, 275-311
+The EPS / ST / KSP block (solve.py:91-123, 220-227) is replaced by libkoreb200 through the
+facades in kore_b200/eps.py; everything else keeps the reference's file formats.
+"""
+from __future__ import annotations
+
+import os
+import sys
+from timeit import default_timer as timer
+
+import numpy as np
+import scipy.sparse as ss
+
+
+def load_csr(filename):
+    """bin/utils.py:1253-1256 (same .npz keys)."""
+    z = np.load(filename)
+    return ss.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=tuple(z["shape"]))
+
+
+def import_parameters(rundir):
+    """`import parameters as par` exactly as the reference resolves it: bin/ of the run dir."""
+    for d in (os.path.join(rundir, "bin"), rundir):
+        if os.path.exists(os.path.join(d, "parameters.py")):
+            sys.path.insert(0, d)
+            break
+    import parameters as par  # noqa: E402
+    return par
+
+
+def kore_sizes(par):
+    """N1, n, sizmat, symmB0 as bin/utils.py:26-57 derives them from parameters."""
+    N, ricb = int(par.N), par.ricb
+    N1 = int(N / 2) * int(1 + np.sign(ricb)) + int((N % 2) * np.sign(ricb))
+    n = int(N1 * (par.lmax - par.m + 1) / 2)
+    sizmat = 2 * n * par.hydro + 2 * n * par.magnetic + n * par.thermal + n * par.compositional
+    B0 = getattr(par, "B0", "axial")
+    if B0 in ("axial", "dipole", "G21 dipole", "Luo_S1"):
+        symmB0 = -1
+    elif B0 == "Luo_S2":
+        symmB0 = 1
+    elif B0 == "FDM":
+        symmB0 = int((-1) ** par.B0_l)
+    else:
+        symmB0 = -1
+    return N1, n, sizmat, symmB0
+
+
+def field_slices(par, n):
+    """Row ranges of each field in the solution vector (solve.py:163-190, 243-261)."""
+    out = []
+    if par.hydro == 1:
+        out.append(("flow", 0, 2 * n))
+    if par.magnetic == 1:
+        o = 2 * n * par.hydro
+        out.append(("magnetic", o, o + 2 * n))
+    if par.thermal == 1:
+        o = 2 * n * par.hydro + 2 * n * par.magnetic
+        out.append(("temperature", o, o + n))
+    if par.compositional == 1:
+        o = 2 * n * par.hydro + 2 * n * par.magnetic + n * par.thermal
+        out.append(("composition", o, o + n))
+    return out
+
+
+def write_fields(par, n, vec):
+    """One solution per column, np.savetxt default format (solve.py:283-306)."""
+    for name, a, b in field_slices(par, n):
+        with open("real_%s.field" % name, "wb") as f:
+            np.savetxt(f, np.real(vec[a:b, :]))
+        with open("imag_%s.field" % name, "wb") as f:
+            np.savetxt(f, np.imag(vec[a:b, :]))
+
+
+def main(argv=None, device=0):
+    from . import eps as kb
+
+    argv = list(sys.argv[1:] if argv is None else argv)
+    tic = timer()
+    rundir = os.getcwd()
+    par = import_parameters(rundir)
+    opts = kb.Options(argv)
+    N1, n, sizmat, symmB0 = kore_sizes(par)
+
+    A = load_csr("A.npz")
+    if A.shape[0] != sizmat:
+        raise SystemExit("A.npz is %d x %d but parameters.py implies sizmat = %d" % (A.shape + (sizmat,)))
+    layout = kb.ChainLayout.from_kore(A, N1, par.m, par.lmax, par.symm, symmB0, par.hydro, par.magnetic,
+                                      par.thermal, par.compositional)
+    success = 0
+
+    if par.forcing == 0:  # ------------------------------------------------ eigenvalue problem
+        B = load_csr("B.npz")
+        E = kb.EPS(device)
+        E.create()
+        E.setOperators(A, B)
+        E.setChainLayout(layout)
+        E.setProblemType(kb.EPS.ProblemType.GNHEP)
+        E.setDimensions(par.nev)
+        E.setTolerances(par.tol, par.maxit)
+        if par.which_eigenpairs not in _WHICH:
+            raise SystemExit("unknown which_eigenpairs %r" % (par.which_eigenpairs,))
+        E.setWhichEigenpairs(par.which_eigenpairs)
+        E.setTarget(par.tau)
+        E.setFromOptions(opts)
+        E.solve()
+
+        nconv = E.getConverged()
+        if nconv > 0:
+            k = np.zeros((1, nconv), dtype=complex)
+            vec = np.zeros((sizmat, nconv), dtype=complex)
+            v = np.zeros(sizmat, dtype=complex)
+            for i in range(nconv):
+                k[0, i] = E.getEigenpair(i, v)
+                vec[:, i] = v
+            eigval = np.hstack([np.real(k).T, np.imag(k).T])
+            with open("eigenvalues0.dat", "wb") as f:
+                np.savetxt(f, eigval)
+            write_fields(par, n, vec)
+            success = nconv
+        else:
+            print("No converged solution found")
+            np.savetxt("no_conv_solution", [0])
+        st = E.getStats()
+        E.destroy()
+    else:  # ------------------------------------------------------------- forced problem
+        b0 = load_csr("B_forced.npz")
+        bvec = np.asarray(b0[:, 0].todense()).ravel().astype(complex)
+        x = np.zeros(sizmat, dtype=complex)
+        K = kb.KSP(device)
+        K.create()
+        K.setOperators(A)
+        K.setChainLayout(layout)
+        K.setTolerances(rtol=par.tol, max_it=par.maxit)
+        K.setFromOptions(opts)
+        K.solve(bvec, x)
+        st = K.getStats()
+        K.destroy()
+        if not np.all(np.isfinite(x)):
+            print("Solver crashed, got nan's!")
+        else:
+            success = 1
+            print("Solution(s) computed")
+            write_fields(par, n, x.reshape(-1, 1))
+
+    toc = timer()
+    print("Solve done in", toc - tic, "seconds",
+          "(GPU: factor %.1f ms, eigs %.1f ms)" % (st.get("factor_ms", 0.0), st.get("eigs_ms", 0.0)))
+    with open("timing.dat", "ab") as f:
+        np.savetxt(f, np.array([toc - tic]))
+    return 0 if success >= 0 else 1
+
+
+_WHICH = ("LM", "SM", "LR", "SR", "LI", "SI", "TM", "TR", "TI")
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -13,9 +13,9 @@ pytestmark = pytest.mark.gpu
 EIG_CASES = ["spinover", "magnetic_small", "forced_small_eig", "m0_small", "dormy", "jones"]
 
 
-def make_solver(lib, case, sigma=None, **opts):
+def make_solver(lib, case, sigma=None, opts=None):
     s = lib.Solver(0)
-    for k, v in opts.items():
+    for k, v in (opts or {}).items():
         s.set_option(k, v)
     s.set_pencil(case.A, case.B)
     s.set_chain(case.perm, case.nodeptr)
@@ -184,3 +184,18 @@ def test_bad_chain_rejected(lib):
         s.set_chain(perm, nodeptr)
     assert e.value.code == lib.KB_ESTRUCTURE
     s.close()
+
+
+@pytest.mark.parametrize("name", ["spinover", "dormy", "magnetic_small"])
+def test_persistent_sweep_matches_per_node_kernels(lib, name):
+    # the cooperative one-launch sweep and the per-node (graph-replayed) kernels are two
+    # implementations of the same block substitution
+    case = load_case(name)
+    rhs = case.oracle["solve_rhs"]
+    xs = []
+    for mode in (0, 1):
+        with make_solver(lib, case, opts={lib.OPT_SWEEP: mode, lib.OPT_REFINE: 0}) as s:
+            xs.append(s.solve(rhs))
+            xs.append(s.solve(rhs))  # second call: warm graph / flags reuse
+    assert np.array_equal(xs[0], xs[1]) and np.array_equal(xs[2], xs[3])
+    assert np.linalg.norm(xs[0] - xs[2]) <= 1e-12 * np.linalg.norm(xs[0])

@@ -1,0 +1,94 @@
+"""The bin/solve.py twin (kore_b200/solve.py): option parsing and file contract on CPU,
+the full run through the GPU library under -m gpu."""
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_case
+
+
+def write_run_dir(tmp_path, name):
+    c = load_case(name)
+    m = c.meta
+    d = tmp_path / name
+    (d / "bin").mkdir(parents=True)
+    for fn in ("A.npz", "B.npz", "B_forced.npz"):
+        src = os.path.join(GOLDEN, name, fn)
+        if os.path.exists(src):
+            shutil.copy(src, d / fn)
+    keys = ["hydro", "magnetic", "thermal", "compositional", "m", "lmax", "N", "symm", "ricb", "forcing",
+            "nev", "maxit", "tol", "rtau", "itau"]
+    lines = ["%s = %r" % (k, m[k]) for k in keys]
+    lines += ["which_eigenpairs = %r" % m["which_eigenpairs"], "B0 = %r" % m["B0"], "tau = rtau + itau*1j"]
+    (d / "bin" / "parameters.py").write_text("\n".join(lines) + "\n")
+    return c, d
+
+
+def test_options_parser():
+    from kore_b200.eps import Options
+    o = Options("-st_type sinvert -st_pc_factor_mat_solver_type mumps -mat_mumps_icntl_14 1000 "
+                "-eps_true_residual -eps_balance twoside -eps_error_relative ::ascii_info_detail "
+                "-eps_nev 7 -eps_tol 1e-10 -eps_target 0.1+1.5i -nbl 12".split())
+    assert o.getString("st_type") == "sinvert"
+    assert o.getInt("mat_mumps_icntl_14") == 1000
+    assert o.hasName("eps_true_residual") and o.hasName("eps_error_relative")
+    assert o.getInt("eps_nev") == 7 and o.getReal("eps_tol") == 1e-10
+    assert o.getScalar("eps_target") == 0.1 + 1.5j
+    assert o.getInt("nbl") == 12 and o.getInt("missing", 3) == 3
+
+
+@pytest.mark.parametrize("name", ["spinover", "dormy", "jones", "magnetic_small"])
+def test_sizes_and_field_slices_follow_reference(name):
+    import types
+    from kore_b200 import solve as drv
+    c = load_case(name)
+    par = types.SimpleNamespace(**c.meta)
+    N1, n, sizmat, symmB0 = drv.kore_sizes(par)
+    assert (N1, n, sizmat, symmB0) == (c.meta["N1"], c.meta["n"], c.meta["sizmat"], c.meta["symmB0"])
+    sl = drv.field_slices(par, n)
+    assert sl[0] == ("flow", 0, 2 * n)
+    assert sl[-1][2] == sizmat
+
+
+@pytest.mark.gpu
+def test_eigen_run_writes_reference_files(tmp_path, monkeypatch, lib):
+    import sys
+    c, d = write_run_dir(tmp_path, "spinover")
+    monkeypatch.chdir(d)
+    sys.modules.pop("parameters", None)
+    from kore_b200 import solve as drv
+    assert drv.main(["-st_type", "sinvert", "-eps_error_relative", "::ascii_info_detail"]) == 0
+    sys.modules.pop("parameters", None)
+    eig = np.loadtxt("eigenvalues0.dat").reshape(-1, 2)
+    # tests/test_spinover.py:21-29
+    best = eig[np.argmax(eig[:, 0])]
+    np.testing.assert_allclose(best, c.meta["reference_golden"]["eig"], rtol=1e-8, atol=1e-20)
+    n = c.meta["n"]
+    ru, iu = np.loadtxt("real_flow.field"), np.loadtxt("imag_flow.field")
+    assert ru.reshape(2 * n, -1).shape == (2 * n, eig.shape[0]) and iu.shape == ru.shape
+    assert not os.path.exists("real_magnetic.field") and not os.path.exists("no_conv_solution")
+    assert np.loadtxt("timing.dat").size == 1
+    # the written vectors are eigenvectors of the pencil
+    x = (ru + 1j * iu).reshape(2 * n, -1)[:, 0]
+    lam = eig[0, 0] + 1j * eig[0, 1]
+    bx = c.B @ x
+    assert np.linalg.norm(c.A @ x - lam * bx) <= 1e-10 * abs(lam) * np.linalg.norm(bx)
+
+
+@pytest.mark.gpu
+def test_forced_run_writes_single_column(tmp_path, monkeypatch, lib):
+    import sys
+    c, d = write_run_dir(tmp_path, "forced_small")
+    monkeypatch.chdir(d)
+    sys.modules.pop("parameters", None)
+    from kore_b200 import solve as drv
+    assert drv.main(["-ksp_type", "preonly", "-pc_type", "lu"]) == 0
+    sys.modules.pop("parameters", None)
+    n = c.meta["n"]
+    x = np.loadtxt("real_flow.field") + 1j * np.loadtxt("imag_flow.field")
+    assert x.shape == (2 * n,)
+    xo = c.oracle["forced_x"]
+    assert np.linalg.norm(x - xo) <= 1e-9 * np.linalg.norm(xo)
+    assert not os.path.exists("eigenvalues0.dat")
