@@ -431,22 +431,10 @@ static int gj_invert(kb_context* h, double2* S0, double2* S1, int n, double2** r
   return KB_OK;
 }
 
-int kbi_factor(kb_context* h, zcomplex sigma) {
-  if (!h->chain_set) return kb_fail(h, KB_EINVAL, "kb_set_chain must be called before kb_factor");
-  KB_CUDA(h, cudaSetDevice(h->device));
+// T = A - sigma B on the union pattern, then power-of-two row and column equilibration
+int kbi_build_T(kb_context* h, zcomplex sigma) {
   cudaStream_t s = h->stream;
-  const int64_t n = h->n, nnz = h->nnz, P = h->P;
-  const int64_t bmax = h->bmax;
-  h->factored = false;
-  h->sigma = sigma;
-  kbi_drop_graphs(h);
-
-  cudaEvent_t e0, e1;
-  KB_CUDA(h, cudaEventCreate(&e0));
-  KB_CUDA(h, cudaEventCreate(&e1));
-  KB_CUDA(h, cudaEventRecord(e0, s));
-
-  // ---- T = A - sigma B, equilibrated
+  const int64_t n = h->n, nnz = h->nnz;
   {
     int thr = 256;
     int64_t blk = (nnz + thr - 1) / thr;
@@ -464,15 +452,12 @@ int kbi_factor(kb_context* h, zcomplex sigma) {
     KB_LAUNCH_CHECK(h);
   }
 
-  // ---- storage for the explicit inverses
-  h->Moff.assign(P + 1, 0);
-  for (int64_t p = 0; p < P; ++p) {
-    int64_t b = h->nodeptr[p + 1] - h->nodeptr[p];
-    h->Moff[p + 1] = h->Moff[p] + b * b;
-  }
-  if (h->d_M.alloc((size_t)h->Moff[P]) != cudaSuccess)
-    return kb_fail(h, KB_ENOMEM, "cannot allocate %.2f GB for the chain factors",
-                   h->Moff[P] * 16.0 / 1e9);
+  return KB_OK;
+}
+
+int kbi_factor_workspace(kb_context* h) {
+  cudaStream_t s = h->stream;
+  const int64_t bmax = h->bmax;
   KB_CUDA(h, h->d_S0.alloc((size_t)bmax * bmax));
   KB_CUDA(h, h->d_S1.alloc((size_t)bmax * bmax));
   KB_CUDA(h, h->d_W.alloc((size_t)bmax * bmax));
@@ -482,6 +467,36 @@ int kbi_factor(kb_context* h, zcomplex sigma) {
   KB_CUDA(h, h->d_srcrow.alloc(bmax));
   KB_CUDA(h, h->d_info.alloc(1));
   KB_CUDA(h, cudaMemsetAsync(h->d_info.p, 0, sizeof(int), s));
+  return KB_OK;
+}
+
+int kbi_factor(kb_context* h, zcomplex sigma) {
+  if (!h->chain_set) return kb_fail(h, KB_EINVAL, "kb_set_chain must be called before kb_factor");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const int64_t n = h->n, nnz = h->nnz, P = h->P;
+  const int64_t bmax = h->bmax;
+  h->factored = false;
+  h->sigma = sigma;
+  kbi_drop_graphs(h);
+
+  cudaEvent_t e0, e1;
+  KB_CUDA(h, cudaEventCreate(&e0));
+  KB_CUDA(h, cudaEventCreate(&e1));
+  KB_CUDA(h, cudaEventRecord(e0, s));
+
+  KB_TRY(kbi_build_T(h, sigma));
+
+  // ---- storage for the explicit inverses
+  h->Moff.assign(P + 1, 0);
+  for (int64_t p = 0; p < P; ++p) {
+    int64_t b = h->nodeptr[p + 1] - h->nodeptr[p];
+    h->Moff[p + 1] = h->Moff[p] + b * b;
+  }
+  if (h->d_M.alloc((size_t)h->Moff[P]) != cudaSuccess)
+    return kb_fail(h, KB_ENOMEM, "cannot allocate %.2f GB for the chain factors",
+                   h->Moff[P] * 16.0 / 1e9);
+  KB_TRY(kbi_factor_workspace(h));
 
   double flops = 0.0;
   for (int64_t p = 0; p < P; ++p) {

@@ -169,6 +169,10 @@ struct kb_context {
   DevBuf<int64_t> d_ucptr;  // n+1
   DevBuf<int> d_urow;       // nnzU chain row
   DevBuf<int64_t> d_upos;   // nnzU position in d_Tval
+  // L blocks (row node p, column node p-1) by column
+  DevBuf<int64_t> d_lcptr;
+  DevBuf<int> d_lrow;
+  DevBuf<int64_t> d_lpos;
   // B alone in chain order for the Arnoldi SpMV
   int64_t nnzB = 0;
   DevBuf<int64_t> d_browptr;
@@ -224,9 +228,19 @@ struct kb_context {
   bool time_sweeps = false;
   std::vector<cudaEvent_t> sweep_events;
 
-  // sharding
+  // sharding (l-sharded path, kb_shard.cu)
   int rank = 0, nranks = 1;
   void* nccl_comm = nullptr;
+  std::vector<int64_t> seg_lo, seg_hi;        // node range of every rank
+  int64_t int_lo = 0, int_hi = 0;             // this rank's interior nodes [int_lo, int_hi)
+  int64_t top_sep = -1, bot_sep = -1;         // separator node above / below (-1: none)
+  std::vector<int64_t> Voff;                  // offsets of V_p / G_p (interior nodes) in d_Vsp / d_Gsp
+  DevBuf<double2> d_Vsp, d_Gsp;               // spikes: V_p (b_p x b_t), G_p (b_t x b_p)
+  DevBuf<double2> d_F, d_H, d_Acc;            // factor-time workspaces
+  DevBuf<double2> d_contrib, d_contrib_all;   // reduced-system blocks: mine / all ranks
+  DevBuf<double2> d_Mr, d_Csub, d_Csup;       // reduced system: inverses and couplings (G-1 nodes)
+  DevBuf<double2> d_sepvec, d_sepvec_all;     // per-solve separator contributions
+  DevBuf<double2> d_redz;                     // reduced-solve scratch
 
   kb_stats stats;
   int64_t launches = 0;
@@ -238,6 +252,9 @@ static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / 
 
 // ---- kb_factor.cu
 int kbi_factor(kb_context* h, zcomplex sigma);
+int kbi_build_T(kb_context* h, zcomplex sigma);
+int kbi_factor_workspace(kb_context* h);
+int kbi_panel_width(const kb_context* h, int n);
 // ---- kb_solve.cu
 //  chain solve in scaled/permuted space: d_y <- T'^{-1} d_r (d_r preserved)
 int kbi_chain_solve(kb_context* h, const double2* r_dev, double2* x_dev, int refine);
@@ -256,5 +273,6 @@ int kbi_sweep_persistent(kb_context* h, const double2* r, double2* y);
 // ---- kb_shard.cu
 int kbi_factor_sharded(kb_context* h, zcomplex sigma);
 int kbi_chain_solve_sharded(kb_context* h, const double2* r_dev, double2* x_dev, int refine);
+int kbi_sharded_sweeps(kb_context* h, const double2* r, double2* y);
 void kbi_nccl_destroy(kb_context* h);
 __global__ void kb_norm2_partial(int n, const double2* __restrict__ v, double* __restrict__ out);

@@ -255,7 +255,7 @@ extern "C" int kb_set_chain(kb_handle h, const int64_t* perm, const int64_t* nod
   std::vector<int> col(nnz), rowidx(nnz);
   std::vector<double2> aval(nnz), bval(nnz);
   std::vector<int64_t> dstart(n), ustart(n);
-  std::vector<int64_t> ucount(n + 1, 0);
+  std::vector<int64_t> ucount(n + 1, 0), lcount(n + 1, 0);
   int64_t nnzA = 0, nnzB = 0, wl = 0, wu = 0;
   for (int64_t i = 0; i < n; ++i) {
     int64_t k = rowptr[i];
@@ -270,6 +270,7 @@ extern "C" int kb_set_chain(kb_handle h, const int64_t* perm, const int64_t* nod
       if (q >= p && ds < 0) ds = k;
       if (q > p && us < 0) us = k;
       if (q > p) ucount[e.col + 1]++;
+      if (q < p) lcount[e.col + 1]++;
       nnzA += e.ina;
       nnzB += e.inb;
       ++k;
@@ -294,6 +295,20 @@ extern "C" int kb_set_chain(kb_handle h, const int64_t* perm, const int64_t* nod
         int64_t dst = fill[col[k]]++;
         urow[dst] = (int)i;
         upos[dst] = k;
+      }
+  }
+  // L blocks by column (needed by the l-sharded spikes: V_s = M_s L_{s,s-1})
+  for (int64_t c = 0; c < n; ++c) lcount[c + 1] += lcount[c];
+  const int64_t nnzL = lcount[n];
+  std::vector<int> lrow(nnzL);
+  std::vector<int64_t> lpos(nnzL);
+  {
+    std::vector<int64_t> fill(lcount.begin(), lcount.end() - 1);
+    for (int64_t i = 0; i < n; ++i)
+      for (int64_t k = rowptr[i]; k < dstart[i]; ++k) {
+        int64_t dst = fill[col[k]]++;
+        lrow[dst] = (int)i;
+        lpos[dst] = k;
       }
   }
   // A alone and B alone (chain order) for SpMV
@@ -341,6 +356,9 @@ extern "C" int kb_set_chain(kb_handle h, const int64_t* perm, const int64_t* nod
   KB_CUDA(h, upload(h->d_ucptr, ucount, s));
   KB_CUDA(h, upload(h->d_urow, urow, s));
   KB_CUDA(h, upload(h->d_upos, upos, s));
+  KB_CUDA(h, upload(h->d_lcptr, lcount, s));
+  KB_CUDA(h, upload(h->d_lrow, lrow, s));
+  KB_CUDA(h, upload(h->d_lpos, lpos, s));
   KB_CUDA(h, upload(h->d_arowptr, arowptr, s));
   KB_CUDA(h, upload(h->d_acol, acol, s));
   KB_CUDA(h, upload(h->d_aval, av, s));

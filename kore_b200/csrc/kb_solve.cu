@@ -212,6 +212,7 @@ void kbi_drop_graphs(kb_context* h) {
 // and driver overhead is what the graph removes.
 static int chain_sweeps(kb_context* h, const double2* r, double2* y) {
   cudaStream_t s = h->stream;
+  if (h->nranks > 1) return kbi_sharded_sweeps(h, r, y);
   if (h->opt_sweep && h->sweep_grid > 0) return kbi_sweep_persistent(h, r, y);
   h->launches += 2 * (2 * h->P - 1);
   for (auto& g : h->sweep_graphs)
@@ -273,9 +274,6 @@ int kbi_solve_workspace(kb_context* h) {
 
 int kbi_chain_solve(kb_context* h, const double2* r_dev, double2* x_dev, int refine) {
   if (!h->factored) return kb_fail(h, KB_EINVAL, "kb_factor must succeed before solving");
-  if (h->nranks > 1) {
-    return kbi_chain_solve_sharded(h, r_dev, x_dev, refine);
-  }
   cudaStream_t s = h->stream;
   const int n = (int)h->n;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
