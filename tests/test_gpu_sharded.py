@@ -1,0 +1,24 @@
+"""GPU, >= 2 devices: the l-sharded path (NCCL) against the committed oracle values.
+Skipped on a single-GPU box; run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_sharded.py -m gpu`."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def test_two_rank_lsharded_parity():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29533",
+           os.path.join(ROOT, "tools", "run_sharded_check.py"), "spinover", "magnetic_small", "dormy"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0
+    assert r.stdout.count(" OK") >= 6 and "FAIL" not in r.stdout
