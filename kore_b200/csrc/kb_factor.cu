@@ -12,6 +12,7 @@
 // partial (row) pivoting inside the block:  8 b^3 real flops per node.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "kb_internal.cuh"
 
@@ -80,24 +81,34 @@ __global__ void kb_col_apply(int64_t nnz, const int* __restrict__ col, const dou
 }
 
 // ---------------------------------------------------------------------------
-// Schur block: S[i,:] = D_p[i,:] - sum_k L_{p,p-1}[i,k] W[k,:]     (one CTA per row)
+// Schur block (one CTA per row):
+//   S[i,:] = D_p[i,:] - sum_k L_{p,p-1}[i,k] W1[k,:] - sum_k U_{p,p+1}[i,k] W2[k,:]
+// W1 = M_{p-1} U_{p-1,p} (downward chain), W2 = M'_{p+1} L_{p+1,p} (upward chain);
+// either may be null.  The first Gauss-Jordan panel is also written column-major.
 // ---------------------------------------------------------------------------
 __global__ void kb_schur_row(double2* __restrict__ S, double2* __restrict__ PT, int nb0, int b, int o,
-                             const double2* __restrict__ W,
-                             int oprev, const int64_t* __restrict__ rowptr,
-                             const int64_t* __restrict__ dstart, const int64_t* __restrict__ ustart,
-                             const int* __restrict__ col, const double2* __restrict__ T) {
+                             const double2* __restrict__ W1, int o1, const double2* __restrict__ W2, int o2,
+                             const int64_t* __restrict__ rowptr, const int64_t* __restrict__ dstart,
+                             const int64_t* __restrict__ ustart, const int* __restrict__ col,
+                             const double2* __restrict__ T) {
   const int i = blockIdx.x;
   const int gi = o + i;
-  const int64_t l0 = rowptr[gi], d0 = dstart[gi], u0 = ustart[gi];
+  const int64_t l0 = rowptr[gi], d0 = dstart[gi], u0 = ustart[gi], e0 = rowptr[gi + 1];
   double2* Srow = S + (size_t)i * b;
   for (int j = threadIdx.x; j < b; j += blockDim.x) {
     double2 acc = zmake(0.0, 0.0);
-    if (W) {
+    if (W1) {
       for (int64_t k = l0; k < d0; ++k) {
         double2 l = __ldg(&T[k]);
-        int c = __ldg(&col[k]) - oprev;
-        zfms(acc, l, W[(size_t)c * b + j]);
+        int c = __ldg(&col[k]) - o1;
+        zfms(acc, l, W1[(size_t)c * b + j]);
+      }
+    }
+    if (W2) {
+      for (int64_t k = u0; k < e0; ++k) {
+        double2 u = __ldg(&T[k]);
+        int c = __ldg(&col[k]) - o2;
+        zfms(acc, u, W2[(size_t)c * b + j]);
       }
     }
     Srow[j] = acc;
@@ -231,7 +242,9 @@ __device__ __forceinline__ void kb_gj_column(double2 (&a)[RPT][NB], const int gk
 template <int NB, int RPT, int MAXT>
 __global__ void __launch_bounds__(MAXT)
 kb_gj_panel(const double2* __restrict__ PT, int n, int k0, int nbv, double2* __restrict__ GpT,
-            int* __restrict__ orig, int* __restrict__ srcrow, int* __restrict__ info) {
+            int* __restrict__ orig, int* __restrict__ srcrow, int* __restrict__ info,
+            long long* __restrict__ dbg) {
+  const long long c0 = clock64();
   extern __shared__ int s_src[];  // n ints: pre-panel row at each position; then n ints: orig
   int* s_orig = s_src + n;
   __shared__ double2 prow[NB];
@@ -256,6 +269,7 @@ kb_gj_panel(const double2* __restrict__ PT, int n, int k0, int nbv, double2* __r
   }
   __syncthreads();
 
+  const long long c1 = clock64();
   int rot = 0;
 #pragma unroll 1
   for (int k = 0; k < nbv; k += 2) {
@@ -273,6 +287,7 @@ kb_gj_panel(const double2* __restrict__ PT, int n, int k0, int nbv, double2* __r
     }
     rot += 2;
   }
+  const long long c2 = clock64();
   // register slot j now holds panel column (j + rot) mod NB
 #pragma unroll
   for (int r = 0; r < RPT; ++r) {
@@ -285,6 +300,13 @@ kb_gj_panel(const double2* __restrict__ PT, int n, int k0, int nbv, double2* __r
   for (int i = t; i < n; i += T) {
     srcrow[i] = s_src[i];
     orig[i] = s_orig[i];
+  }
+  if (dbg && t == 0) {
+    const long long c3 = clock64();
+    atomicAdd((unsigned long long*)&dbg[0], (unsigned long long)(c1 - c0));
+    atomicAdd((unsigned long long*)&dbg[1], (unsigned long long)(c2 - c1));
+    atomicAdd((unsigned long long*)&dbg[2], (unsigned long long)(c3 - c2));
+    atomicAdd((unsigned long long*)&dbg[3], 1ULL);
   }
 }
 
@@ -369,20 +391,42 @@ __global__ void kb_store_inverse(const double2* __restrict__ X, int n, const int
 // ---------------------------------------------------------------------------
 // host drivers
 // ---------------------------------------------------------------------------
+// Workspace + stream of one elimination chain (two chains run concurrently in the
+// two-sided factorisation).
+struct GjWs {
+  cudaStream_t st;
+  double2 *S0, *S1, *W, *Gp, *PT;
+  int *orig, *srcrow;
+};
+
+GjWs kbi_ws_main(kb_context* h) {
+  GjWs w;
+  w.st = h->stream;
+  w.S0 = h->d_S0.p;
+  w.S1 = h->d_S1.p;
+  w.W = h->d_W.p;
+  w.Gp = h->d_Gp.p;
+  w.PT = h->d_PT.p;
+  w.orig = h->d_orig.p;
+  w.srcrow = h->d_srcrow.p;
+  return w;
+}
+
 template <int NB, int RPT, int MAXT>
-static void launch_panel(kb_context* h, int n, int k0, int nbv) {
+static void launch_panel(kb_context* h, const GjWs& w, int n, int k0, int nbv) {
   int T = (n + RPT - 1) / RPT;
   T = ((T + 31) / 32) * 32;
   if (T > MAXT) T = MAXT;
-  kb_gj_panel<NB, RPT, MAXT><<<1, T, 2 * n * sizeof(int), h->stream>>>(h->d_PT.p, n, k0, nbv, h->d_Gp.p, h->d_orig.p,
-                                                                  h->d_srcrow.p, h->d_info.p);
+  kb_gj_panel<NB, RPT, MAXT><<<1, T, 2 * n * sizeof(int), w.st>>>(w.PT, n, k0, nbv, w.Gp, w.orig, w.srcrow,
+                                                                 h->d_info.p, h->d_sweep_timing.p);
 }
 
 template <int NB>
-static void launch_update(kb_context* h, const double2* in, double2* out, int n, int k0, int nbv) {
+static void launch_update(kb_context* h, const GjWs& w, const double2* in, double2* out, int n, int k0, int nbv) {
   constexpr int TM = 32;
   dim3 grid((n + 63) / 64, (n + TM - 1) / TM);
-  kb_gj_update<NB, TM><<<grid, 256, 0, h->stream>>>(in, out, n, k0, nbv, h->d_Gp.p, h->d_srcrow.p, h->d_PT.p);
+  kb_gj_update<NB, TM><<<grid, 256, 0, w.st>>>(in, out, n, k0, nbv, w.Gp, w.srcrow, w.PT);
+  (void)h;
 }
 
 int kbi_panel_width(const kb_context* h, int n) {
@@ -397,29 +441,30 @@ int kbi_panel_width(const kb_context* h, int n) {
   return 4;
 }
 
-// In-place inverse of the n x n row-major matrix in S0 (S1 = scratch of the same
-// size).  Returns the buffer that holds (Pi S)^{-1}; d_orig holds Pi.
-static int gj_invert(kb_context* h, double2* S0, double2* S1, int n, double2** result) {
+// In-place inverse of the n x n row-major matrix in w.S0 (w.S1 = scratch of the same
+// size; w.PT must hold the first panel column-major).  Returns the buffer that holds
+// (Pi S)^{-1}; w.orig holds Pi.
+static int gj_invert(kb_context* h, const GjWs& w, int n, double2** result) {
   if (n > 4096) return kb_fail(h, KB_EINVAL, "chain node of %d rows exceeds the supported 4096", n);
   const int NB = kbi_panel_width(h, n);
-  double2* in = S0;
-  double2* out = S1;
+  double2* in = w.S0;
+  double2* out = w.S1;
   for (int k0 = 0; k0 < n; k0 += NB) {
     int nbv = n - k0 < NB ? n - k0 : NB;
     if (NB == 16) {
-      launch_panel<16, 2, 320>(h, n, k0, nbv);
-      launch_update<16>(h, in, out, n, k0, nbv);
+      launch_panel<16, 2, 320>(h, w, n, k0, nbv);
+      launch_update<16>(h, w, in, out, n, k0, nbv);
     } else if (NB == 8) {
-      launch_panel<8, 2, 512>(h, n, k0, nbv);
-      launch_update<8>(h, in, out, n, k0, nbv);
+      launch_panel<8, 2, 512>(h, w, n, k0, nbv);
+      launch_update<8>(h, w, in, out, n, k0, nbv);
     } else {
       if (n <= 1024)
-        launch_panel<4, 2, 512>(h, n, k0, nbv);
+        launch_panel<4, 2, 512>(h, w, n, k0, nbv);
       else if (n <= 2048)
-        launch_panel<4, 4, 512>(h, n, k0, nbv);
+        launch_panel<4, 4, 512>(h, w, n, k0, nbv);
       else
-        launch_panel<4, 4, 1024>(h, n, k0, nbv);
-      launch_update<4>(h, in, out, n, k0, nbv);
+        launch_panel<4, 4, 1024>(h, w, n, k0, nbv);
+      launch_update<4>(h, w, in, out, n, k0, nbv);
     }
     h->launches += 2;
     double2* t = in;
@@ -451,7 +496,6 @@ int kbi_build_T(kb_context* h, zcomplex sigma) {
     h->launches += 5;
     KB_LAUNCH_CHECK(h);
   }
-
   return KB_OK;
 }
 
@@ -467,6 +511,44 @@ int kbi_factor_workspace(kb_context* h) {
   KB_CUDA(h, h->d_srcrow.alloc(bmax));
   KB_CUDA(h, h->d_info.alloc(1));
   KB_CUDA(h, cudaMemsetAsync(h->d_info.p, 0, sizeof(int), s));
+  if (getenv("KB_SWEEP_TIMING")) {
+    KB_CUDA(h, h->d_sweep_timing.alloc(256 * 8));
+    KB_CUDA(h, cudaMemsetAsync(h->d_sweep_timing.p, 0, 256 * 8 * sizeof(long long), s));
+  }
+  return KB_OK;
+}
+
+// One node of an elimination chain: Schur block, inversion, store, coupling product for
+// the next node of the chain.  dir = +1: downward (uses L_{p,p-1} W, produces M_p U_{p,p+1});
+// dir = -1: upward (uses U_{p,p+1} W, produces M'_p L_{p,p-1}).
+static int factor_node(kb_context* h, const GjWs& w, int64_t p, int dir, bool first, bool produce_next) {
+  const int o = (int)h->nodeptr[p];
+  const int b = (int)(h->nodeptr[p + 1] - h->nodeptr[p]);
+  const int64_t q = p - dir;  // node eliminated just before p on this chain
+  const int oq = (!first) ? (int)h->nodeptr[q] : 0;
+  kb_schur_row<<<b, 128, 0, w.st>>>(w.S0, w.PT, kbi_panel_width(h, b), b, o,
+                                    (!first && dir > 0) ? w.W : nullptr, oq,
+                                    (!first && dir < 0) ? w.W : nullptr, oq, h->d_rowptr.p, h->d_dstart.p,
+                                    h->d_ustart.p, h->d_col.p, h->d_Tval.p);
+  h->launches++;
+  double2* X = nullptr;
+  KB_TRY(gj_invert(h, w, b, &X));
+  double2* Mp = h->d_M.p + h->Moff[p];
+  kb_store_inverse<<<b, 128, 0, w.st>>>(X, b, w.orig, Mp);
+  h->launches++;
+  if (produce_next) {
+    const int64_t nx = p + dir;
+    const int onext = (int)h->nodeptr[nx];
+    const int bnext = (int)(h->nodeptr[nx + 1] - h->nodeptr[nx]);
+    if (dir > 0)
+      kb_w_rows<<<b, 128, b * sizeof(double2), w.st>>>(Mp, b, o, w.W, bnext, onext, h->d_ucptr.p, h->d_urow.p,
+                                                       h->d_upos.p, h->d_Tval.p);
+    else
+      kb_w_rows<<<b, 128, b * sizeof(double2), w.st>>>(Mp, b, o, w.W, bnext, onext, h->d_lcptr.p, h->d_lrow.p,
+                                                       h->d_lpos.p, h->d_Tval.p);
+    h->launches++;
+  }
+  KB_LAUNCH_CHECK(h);
   return KB_OK;
 }
 
@@ -474,7 +556,7 @@ int kbi_factor(kb_context* h, zcomplex sigma) {
   if (!h->chain_set) return kb_fail(h, KB_EINVAL, "kb_set_chain must be called before kb_factor");
   KB_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
-  const int64_t n = h->n, nnz = h->nnz, P = h->P;
+  const int64_t P = h->P;
   const int64_t bmax = h->bmax;
   h->factored = false;
   h->sigma = sigma;
@@ -497,30 +579,74 @@ int kbi_factor(kb_context* h, zcomplex sigma) {
     return kb_fail(h, KB_ENOMEM, "cannot allocate %.2f GB for the chain factors",
                    h->Moff[P] * 16.0 / 1e9);
   KB_TRY(kbi_factor_workspace(h));
+  GjWs top = kbi_ws_main(h);
 
+  // Two-sided ("burn at both ends") elimination: nodes 0..mid-1 are eliminated downward
+  // and nodes P-1..mid+1 upward on two streams; the chains are independent until the
+  // middle node, so every latency-bound step of one overlaps the other's.  The solve
+  // must use the matching two-sided sweep (kb_sweep.cu); the per-node and barrier
+  // sweeps and the l-sharded path need the one-sided factors (mid = P-1).
+  const bool two_sided = h->nranks == 1 && h->opt_sweep == 1 && P >= 4;
+  const int64_t mid = two_sided ? P / 2 : P - 1;
+  h->mid = mid;
   double flops = 0.0;
   for (int64_t p = 0; p < P; ++p) {
-    const int o = (int)h->nodeptr[p];
-    const int b = (int)(h->nodeptr[p + 1] - h->nodeptr[p]);
-    const int oprev = p > 0 ? (int)h->nodeptr[p - 1] : 0;
-    kb_schur_row<<<b, 128, 0, s>>>(h->d_S0.p, h->d_PT.p, kbi_panel_width(h, b), b, o,
-                                   p > 0 ? h->d_W.p : nullptr, oprev, h->d_rowptr.p,
-                                   h->d_dstart.p, h->d_ustart.p, h->d_col.p, h->d_Tval.p);
-    h->launches++;
-    double2* X = nullptr;
-    KB_TRY(gj_invert(h, h->d_S0.p, h->d_S1.p, b, &X));
-    double2* Mp = h->d_M.p + h->Moff[p];
-    kb_store_inverse<<<b, 128, 0, s>>>(X, b, h->d_orig.p, Mp);
-    h->launches++;
-    flops += 8.0 * (double)b * b * b;
-    if (p + 1 < P) {
-      const int onext = (int)h->nodeptr[p + 1];
-      const int bnext = (int)(h->nodeptr[p + 2] - h->nodeptr[p + 1]);
-      kb_w_rows<<<b, 128, b * sizeof(double2), s>>>(Mp, b, o, h->d_W.p, bnext, onext, h->d_ucptr.p,
-                                                    h->d_urow.p, h->d_upos.p, h->d_Tval.p);
-      h->launches++;
+    double b = (double)(h->nodeptr[p + 1] - h->nodeptr[p]);
+    flops += 8.0 * b * b * b;
+  }
+  if (two_sided) {
+    if (!h->stream2) KB_CUDA(h, cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    KB_CUDA(h, h->d_S0b.alloc((size_t)bmax * bmax));
+    KB_CUDA(h, h->d_S1b.alloc((size_t)bmax * bmax));
+    KB_CUDA(h, h->d_Wb.alloc((size_t)bmax * bmax));
+    KB_CUDA(h, h->d_Gpb.alloc((size_t)bmax * 16));
+    KB_CUDA(h, h->d_PTb.alloc((size_t)bmax * 16));
+    KB_CUDA(h, h->d_origb.alloc(bmax));
+    KB_CUDA(h, h->d_srcrowb.alloc(bmax));
+    GjWs bot;
+    bot.st = h->stream2;
+    bot.S0 = h->d_S0b.p;
+    bot.S1 = h->d_S1b.p;
+    bot.W = h->d_Wb.p;
+    bot.Gp = h->d_Gpb.p;
+    bot.PT = h->d_PTb.p;
+    bot.orig = h->d_origb.p;
+    bot.srcrow = h->d_srcrowb.p;
+    cudaEvent_t fork, join;
+    KB_CUDA(h, cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+    KB_CUDA(h, cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+    KB_CUDA(h, cudaEventRecord(fork, s));
+    KB_CUDA(h, cudaStreamWaitEvent(h->stream2, fork, 0));
+    // interleave the host-side launches of the two chains so both streams stay fed
+    int64_t pt = 0, pb = P - 1;
+    while (pt < mid || pb > mid) {
+      if (pt < mid) {
+        KB_TRY(factor_node(h, top, pt, +1, pt == 0, true));
+        ++pt;
+      }
+      if (pb > mid) {
+        KB_TRY(factor_node(h, bot, pb, -1, pb == P - 1, true));
+        --pb;
+      }
     }
-    KB_LAUNCH_CHECK(h);
+    KB_CUDA(h, cudaEventRecord(join, h->stream2));
+    KB_CUDA(h, cudaStreamWaitEvent(s, join, 0));
+    // middle node: couplings from both sides
+    {
+      const int o = (int)h->nodeptr[mid], b = (int)(h->nodeptr[mid + 1] - h->nodeptr[mid]);
+      kb_schur_row<<<b, 128, 0, s>>>(top.S0, top.PT, kbi_panel_width(h, b), b, o, top.W,
+                                     (int)h->nodeptr[mid - 1], bot.W, (int)h->nodeptr[mid + 1], h->d_rowptr.p,
+                                     h->d_dstart.p, h->d_ustart.p, h->d_col.p, h->d_Tval.p);
+      double2* X = nullptr;
+      KB_TRY(gj_invert(h, top, b, &X));
+      kb_store_inverse<<<b, 128, 0, s>>>(X, b, top.orig, h->d_M.p + h->Moff[mid]);
+      h->launches += 2;
+      KB_LAUNCH_CHECK(h);
+    }
+    cudaEventDestroy(fork);
+    cudaEventDestroy(join);
+  } else {
+    for (int64_t p = 0; p < P; ++p) KB_TRY(factor_node(h, top, p, +1, p == 0, p + 1 < P));
   }
   KB_TRY(kbi_sweep_prepare(h));
   KB_CUDA(h, cudaEventRecord(e1, s));

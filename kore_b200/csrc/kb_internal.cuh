@@ -196,6 +196,11 @@ struct kb_context {
   DevBuf<double2> d_M;
   // factor workspaces
   DevBuf<double2> d_S0, d_S1, d_W, d_Gp, d_PT;
+  // second elimination chain (two-sided factorisation)
+  cudaStream_t stream2 = nullptr;
+  DevBuf<double2> d_S0b, d_S1b, d_Wb, d_Gpb, d_PTb;
+  DevBuf<int> d_origb, d_srcrowb;
+  int64_t mid = 0;  // middle node of the two-sided elimination (P-1: one-sided)
   // ELL copies of the couplings + node tables for the persistent sweep kernel
   int WL = 0, WU = 0;
   DevBuf<double2> d_Lval, d_Uval;
@@ -209,7 +214,7 @@ struct kb_context {
   DevBuf<int> d_orig, d_srcrow, d_piv, d_info;
 
   // solve workspaces (chain order, scaled space)
-  DevBuf<double2> d_r, d_y, d_res, d_x0, d_in, d_out, d_t;
+  DevBuf<double2> d_r, d_y, d_res, d_x0, d_in, d_out, d_t, d_t2, d_yf;
   DevBuf<double> d_partial;
 
   // Krylov workspaces
@@ -270,6 +275,7 @@ void kbi_drop_graphs(kb_context* h);
 // ---- kb_sweep.cu
 int kbi_sweep_prepare(kb_context* h);
 int kbi_sweep_persistent(kb_context* h, const double2* r, double2* y);
+int kbi_sweep_dataflow(kb_context* h, const double2* r, double2* y);
 // ---- kb_shard.cu
 int kbi_factor_sharded(kb_context* h, zcomplex sigma);
 int kbi_chain_solve_sharded(kb_context* h, const double2* r_dev, double2* x_dev, int refine);

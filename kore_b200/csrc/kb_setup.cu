@@ -63,6 +63,10 @@ extern "C" int kb_destroy(kb_handle h) {
     cudaStreamSynchronize(h->stream);
     cudaStreamDestroy(h->stream);
   }
+  if (h->stream2) {
+    cudaStreamSynchronize(h->stream2);
+    cudaStreamDestroy(h->stream2);
+  }
   kbi_nccl_destroy(h);
   kbi_drop_graphs(h);
   delete h;
@@ -83,7 +87,7 @@ extern "C" int kb_set_option(kb_handle h, int option, int64_t value) {
     case KB_OPT_SEED: h->opt_seed = value; break;
     case KB_OPT_PANEL: h->opt_panel = (int)value; break;
     case 6: h->opt_refine_eigs = (int)std::max<int64_t>(0, value); break;
-    case 7: h->opt_sweep = value != 0; break;
+    case 7: h->opt_sweep = (int)value; break;
     default: return kb_fail(h, KB_EINVAL, "unknown option %d", option);
   }
   return KB_OK;

@@ -336,11 +336,11 @@ int kbi_factor_sharded(kb_context* h, zcomplex sigma) {
     const int o = noff(h, p), b = nsize(h, p);
     const int oprev = p > lo ? noff(h, p - 1) : 0;
     kb_schur_row<<<b, 128, 0, s>>>(h->d_S0.p, h->d_PT.p, kbi_panel_width(h, b), b, o,
-                                   p > lo ? h->d_W.p : nullptr, oprev, h->d_rowptr.p, h->d_dstart.p,
+                                   p > lo ? h->d_W.p : nullptr, oprev, nullptr, 0, h->d_rowptr.p, h->d_dstart.p,
                                    h->d_ustart.p, h->d_col.p, h->d_Tval.p);
     h->launches++;
     double2* X = nullptr;
-    KB_TRY(gj_invert(h, h->d_S0.p, h->d_S1.p, b, &X));
+    KB_TRY(gj_invert(h, kbi_ws_main(h), b, &X));
     double2* Mp = h->d_M.p + h->Moff[p];
     kb_store_inverse<<<b, 128, 0, s>>>(X, b, h->d_orig.p, Mp);
     h->launches++;
@@ -394,8 +394,8 @@ int kbi_factor_sharded(kb_context* h, zcomplex sigma) {
       const int ob = noff(h, h->bot_sep), bb = nsize(h, h->bot_sep);
       kb_w_rows<<<be, 128, be * sizeof(double2), s>>>(Me, be, oe, h->d_W.p, bb, ob, h->d_ucptr.p, h->d_urow.p,
                                                       h->d_upos.p, h->d_Tval.p);
-      kb_schur_row<<<bb, 128, 0, s>>>(h->d_contrib.p, h->d_PT.p, 0, bb, ob, h->d_W.p, oe, h->d_rowptr.p,
-                                      h->d_dstart.p, h->d_ustart.p, h->d_col.p, h->d_Tval.p);
+      kb_schur_row<<<bb, 128, 0, s>>>(h->d_contrib.p, h->d_PT.p, 0, bb, ob, h->d_W.p, oe, nullptr, 0,
+                                      h->d_rowptr.p, h->d_dstart.p, h->d_ustart.p, h->d_col.p, h->d_Tval.p);
       h->launches += 2;
       if (has_top) {
         const double2* Ve = h->d_Vsp.p + h->Voff[e];
@@ -432,7 +432,7 @@ int kbi_factor_sharded(kb_context* h, zcomplex sigma) {
     }
     kb_first_panel<<<nblk(bs, 128), 128, 0, s>>>(h->d_S0.p, bs, kbi_panel_width(h, bs), h->d_PT.p);
     double2* X = nullptr;
-    KB_TRY(gj_invert(h, h->d_S0.p, h->d_S1.p, bs, &X));
+    KB_TRY(gj_invert(h, kbi_ws_main(h), bs, &X));
     kb_store_inverse<<<bs, 128, 0, s>>>(X, bs, h->d_orig.p, h->d_Mr.p + (size_t)j * slot);
     h->launches += 2;
     flops += 8.0 * (double)bs * bs * bs;

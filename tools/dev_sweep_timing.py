@@ -14,13 +14,13 @@ for i in range(3):
     x = s.solve(rhs)
 print("solve_ms", s.stats()["solve_ms"])
 L = lib.load()
-out = np.zeros(256 * 5, dtype=np.int64)
+out = np.zeros(256 * 8, dtype=np.int64)
 L.kb_dbg_sweep_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
 g = L.kb_dbg_sweep_timing(s.h, out.ctypes.data, 256)
-t = out[: g * 5].reshape(g, 5)
+t = out[: g * 8].reshape(g, 8)
 steps = 2 * P - 1
-names = ["pre", "phaseA", "bar1", "phaseB", "bar2"]
+names = ["pre", "phaseA(poll y)", "poll t", "sync after shfl", "final+store", "gemv j-loop", "shuffles", "-"]
 print("per-step cycles (mean over CTAs; CTA0; max):")
-for k in range(5):
-    print("  %-7s mean %8.0f  cta0 %8.0f  max %8.0f" % (names[k], t[:, k].mean() / steps, t[0, k] / steps, t[:, k].max() / steps))
+for k in range(8):
+    print("  %-15s mean %8.0f  cta0 %8.0f  max %8.0f" % (names[k], t[:, k].mean() / steps, t[0, k] / steps, t[:, k].max() / steps))
 print("  total per step %.0f cycles" % (t.sum(axis=1).mean() / steps))
