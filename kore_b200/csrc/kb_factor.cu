@@ -19,13 +19,15 @@
 // ---------------------------------------------------------------------------
 // T = A - sigma B, equilibration
 // ---------------------------------------------------------------------------
-__global__ void kb_build_T(int64_t nnz, const double2* __restrict__ A, const double2* __restrict__ B,
-                           double2 sigma, double2* __restrict__ T) {
+// T -= sigma B on the union pattern (T starts as a copy of A; every B entry has its own slot)
+template <typename VT>
+__global__ void kb_sub_sigma_B(int64_t nnzB, const VT* __restrict__ bval, const int* __restrict__ bmap,
+                               double2 sigma, double2* __restrict__ T) {
   int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= nnz) return;
-  double2 t = A[k];
-  zfms(t, sigma, B[k]);
-  T[k] = t;
+  if (k >= nnzB) return;
+  double2 t = T[bmap[k]];
+  zfms(t, sigma, kb_as_complex(bval[k]));
+  T[bmap[k]] = t;
 }
 
 __device__ __forceinline__ double kb_pow2_recip(double m) {
@@ -483,8 +485,15 @@ int kbi_build_T(kb_context* h, zcomplex sigma) {
   {
     int thr = 256;
     int64_t blk = (nnz + thr - 1) / thr;
-    kb_build_T<<<(unsigned)blk, thr, 0, s>>>(nnz, h->d_Aval.p, h->d_Bval.p,
-                                             zmake(sigma.real(), sigma.imag()), h->d_Tval.p);
+    KB_CUDA(h, cudaMemcpyAsync(h->d_Tval.p, h->d_Aval.p, (size_t)nnz * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+    if (h->B.present && h->nnzB > 0) {
+      const double2 sg = zmake(sigma.real(), sigma.imag());
+      unsigned bblk = (unsigned)((h->nnzB + thr - 1) / thr);
+      if (h->b_is_complex)
+        kb_sub_sigma_B<double2><<<bblk, thr, 0, s>>>(h->nnzB, h->d_bval_c.p, h->d_bmap.p, sg, h->d_Tval.p);
+      else
+        kb_sub_sigma_B<double><<<bblk, thr, 0, s>>>(h->nnzB, h->d_bval_r.p, h->d_bmap.p, sg, h->d_Tval.p);
+    }
     int64_t wblk = (n * 32 + thr - 1) / thr;
     kb_row_scale<<<(unsigned)wblk, thr, 0, s>>>((int)n, h->d_rowptr.p, h->d_Tval.p, h->d_rscale.p,
                                                 h->opt_equil);

@@ -47,6 +47,8 @@ __device__ __forceinline__ void zfmac(double2& acc, double2 a, double2 b) {
   acc.y = fma(a.x, b.y, acc.y);
   acc.y = fma(-a.y, b.x, acc.y);
 }
+__host__ __device__ __forceinline__ double2 kb_as_complex(double v) { return make_double2(v, 0.0); }
+__host__ __device__ __forceinline__ double2 kb_as_complex(double2 v) { return v; }
 __host__ __device__ __forceinline__ double zabs2(double2 a) { return a.x * a.x + a.y * a.y; }
 __host__ __device__ __forceinline__ double2 zinv(double2 p) {
   // scaled reciprocal (avoids overflow of |p|^2)
@@ -158,9 +160,8 @@ struct kb_context {
   int64_t nnz = 0;
   DevBuf<int64_t> d_rowptr;  // n+1
   DevBuf<int> d_col;         // nnz (chain column)
-  DevBuf<int> d_rowidx;      // nnz (chain row of each entry)
   DevBuf<double2> d_Aval;    // nnz
-  DevBuf<double2> d_Bval;    // nnz (B scattered on the union pattern; zero where absent)
+  DevBuf<int> d_bmap;        // nnzB: position of every B entry in the union pattern
   DevBuf<double2> d_Tval;    // nnz (equilibrated A - sigma B)
   DevBuf<int64_t> d_dstart;  // n: first entry of row in its own node
   DevBuf<int64_t> d_ustart;  // n: first entry of row in the next node
@@ -179,11 +180,6 @@ struct kb_context {
   DevBuf<int> d_bcol;
   DevBuf<double> d_bval_r;    // real B (assemble.py writes float64)
   DevBuf<double2> d_bval_c;   // complex B
-  // A alone in chain order for true residuals
-  int64_t nnzA = 0;
-  DevBuf<int64_t> d_arowptr;
-  DevBuf<int> d_acol;
-  DevBuf<double2> d_aval;
 
   // equilibration (powers of two), chain order
   DevBuf<double> d_rscale, d_cscale;

@@ -167,8 +167,8 @@ extern "C" int kb_set_pencil(kb_handle h, int64_t n, int index_bytes, const void
 namespace {
 struct Ent {
   int col;
-  zcomplex a, b;
-  bool ina, inb;
+  int src;  // 0: A entry, 1: B entry
+  zcomplex v;
 };
 
 template <typename T>
@@ -177,6 +177,17 @@ cudaError_t upload(DevBuf<T>& d, const std::vector<T>& v, cudaStream_t s) {
   if (e != cudaSuccess) return e;
   if (v.empty()) return cudaSuccess;
   return cudaMemcpyAsync(d.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+}
+
+template <typename F>
+void parallel_rows(int64_t n, int nthr, F f) {
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nthr; ++t)
+    pool.emplace_back([=]() {
+      int64_t lo = n * t / nthr, hi = n * (t + 1) / nthr;
+      f(t, lo, hi);
+    });
+  for (auto& th : pool) th.join();
 }
 }  // namespace
 
@@ -196,153 +207,156 @@ extern "C" int kb_set_chain(kb_handle h, const int64_t* perm, const int64_t* nod
     if (b <= 0) return kb_fail(h, KB_EINVAL, "empty chain node %lld", (long long)p);
     h->bmax = std::max(h->bmax, b);
   }
-  std::vector<int64_t> iperm(n, -1);
+  std::vector<int> iperm(n, -1);
   for (int64_t k = 0; k < n; ++k) {
     if (perm[k] < 0 || perm[k] >= n || iperm[perm[k]] != -1)
       return kb_fail(h, KB_EINVAL, "perm is not a permutation");
-    iperm[perm[k]] = k;
+    iperm[perm[k]] = (int)k;
   }
   std::vector<int> node_of(n);
   for (int64_t p = 0; p < nnodes; ++p)
     for (int64_t i = nodeptr[p]; i < nodeptr[p + 1]; ++i) node_of[i] = (int)p;
 
-  // ---- union pattern, chain order, rows sorted by chain column (host threads)
   const HostCSR& A = h->A;
   const HostCSR& B = h->B;
-  std::vector<int64_t> rowcount(n, 0);
-  std::vector<std::vector<Ent>> rows(n);
-  int nthr = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-  std::vector<int> bad(nthr, 0);
-  auto work = [&](int t) {
-    std::vector<Ent> tmp;
-    for (int64_t i = t; i < n; i += nthr) {
-      int64_t o = perm[i];
-      tmp.clear();
-      for (int64_t k = A.indptr[o]; k < A.indptr[o + 1]; ++k)
-        tmp.push_back(Ent{(int)iperm[A.indices[k]], A.values[k], zcomplex(0, 0), true, false});
-      if (B.present)
-        for (int64_t k = B.indptr[o]; k < B.indptr[o + 1]; ++k)
-          tmp.push_back(Ent{(int)iperm[B.indices[k]], zcomplex(0, 0), B.values[k], false, true});
-      std::stable_sort(tmp.begin(), tmp.end(), [](const Ent& x, const Ent& y) { return x.col < y.col; });
-      std::vector<Ent>& out = rows[i];
-      out.clear();
-      for (const Ent& e : tmp) {
-        if (!out.empty() && out.back().col == e.col) {
-          out.back().a += e.a;
-          out.back().b += e.b;
-          out.back().ina |= e.ina;
-          out.back().inb |= e.inb;
-        } else {
-          out.push_back(e);
-        }
-        int d = node_of[e.col] - node_of[i];
-        if (d > 1 || d < -1) bad[t] = 1;
-      }
-      rowcount[i] = (int64_t)out.size();
-    }
+  const int nthr = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+
+  // merged (union of A and B), column-sorted row i of the chain-ordered pencil
+  auto merged_row = [&](int64_t i, std::vector<Ent>& buf) {
+    const int64_t o = perm[i];
+    buf.clear();
+    for (int64_t k = A.indptr[o]; k < A.indptr[o + 1]; ++k) buf.push_back(Ent{iperm[A.indices[k]], 0, A.values[k]});
+    if (B.present)
+      for (int64_t k = B.indptr[o]; k < B.indptr[o + 1]; ++k) buf.push_back(Ent{iperm[B.indices[k]], 1, B.values[k]});
+    std::sort(buf.begin(), buf.end(), [](const Ent& x, const Ent& y) {
+      return x.col < y.col || (x.col == y.col && x.src < y.src);
+    });
   };
-  {
-    std::vector<std::thread> pool;
-    for (int t = 0; t < nthr; ++t) pool.emplace_back(work, t);
-    for (auto& th : pool) th.join();
-  }
+
+  // ---- pass 1: row lengths of the union pattern, structure check
+  std::vector<int64_t> rowptr(n + 1, 0), browptr(n + 1, 0);
+  std::vector<int> bad(nthr, 0);
+  parallel_rows(n, nthr, [&](int t, int64_t lo, int64_t hi) {
+    std::vector<Ent> buf;
+    buf.reserve(256);
+    for (int64_t i = lo; i < hi; ++i) {
+      merged_row(i, buf);
+      int64_t cnt = 0, cntb = 0;
+      int last = -1;
+      const int pi = node_of[i];
+      for (const Ent& e : buf) {
+        if (e.col != last) {
+          ++cnt;
+          last = e.col;
+          int d = node_of[e.col] - pi;
+          if (d > 1 || d < -1) bad[t] = 1;
+        }
+        if (e.src == 1) ++cntb;
+      }
+      rowptr[i + 1] = cnt;
+      browptr[i + 1] = cntb;
+    }
+  });
   for (int t = 0; t < nthr; ++t)
     if (bad[t])
       return kb_fail(h, KB_ESTRUCTURE,
                      "pencil is not block tridiagonal under the given chain (a nonzero couples nodes "
                      "more than one apart)");
-
-  std::vector<int64_t> rowptr(n + 1, 0);
-  for (int64_t i = 0; i < n; ++i) rowptr[i + 1] = rowptr[i] + rowcount[i];
-  const int64_t nnz = rowptr[n];
-  h->nnz = nnz;
-  std::vector<int> col(nnz), rowidx(nnz);
-  std::vector<double2> aval(nnz), bval(nnz);
-  std::vector<int64_t> dstart(n), ustart(n);
-  std::vector<int64_t> ucount(n + 1, 0), lcount(n + 1, 0);
-  int64_t nnzA = 0, nnzB = 0, wl = 0, wu = 0;
   for (int64_t i = 0; i < n; ++i) {
-    int64_t k = rowptr[i];
-    int p = node_of[i];
-    int64_t ds = -1, us = -1;
-    for (const Ent& e : rows[i]) {
-      col[k] = e.col;
-      rowidx[k] = (int)i;
-      aval[k] = make_double2(e.a.real(), e.a.imag());
-      bval[k] = make_double2(e.b.real(), e.b.imag());
-      int q = node_of[e.col];
-      if (q >= p && ds < 0) ds = k;
-      if (q > p && us < 0) us = k;
-      if (q > p) ucount[e.col + 1]++;
-      if (q < p) lcount[e.col + 1]++;
-      nnzA += e.ina;
-      nnzB += e.inb;
-      ++k;
-    }
-    if (us < 0) us = rowptr[i + 1];
-    if (ds < 0) ds = us;
-    dstart[i] = ds;
-    ustart[i] = us;
-    wl = std::max<int64_t>(wl, ds - rowptr[i]);
-    wu = std::max<int64_t>(wu, rowptr[i + 1] - us);
+    rowptr[i + 1] += rowptr[i];
+    browptr[i + 1] += browptr[i];
   }
-  // U by column
-  for (int64_t c = 0; c < n; ++c) ucount[c + 1] += ucount[c];
-  const int64_t nnzU = ucount[n];
-  h->nnzU = nnzU;
-  std::vector<int> urow(nnzU);
-  std::vector<int64_t> upos(nnzU);
-  {
-    std::vector<int64_t> fill(ucount.begin(), ucount.end() - 1);
-    for (int64_t i = 0; i < n; ++i)
-      for (int64_t k = ustart[i]; k < rowptr[i + 1]; ++k) {
-        int64_t dst = fill[col[k]]++;
-        urow[dst] = (int)i;
-        upos[dst] = k;
+  const int64_t nnz = rowptr[n], nnzB = browptr[n];
+  h->nnz = nnz;
+  h->nnzB = nnzB;
+
+  // ---- pass 2: fill
+  std::vector<int> col((size_t)nnz), bcol((size_t)nnzB), bmap((size_t)nnzB);
+  std::vector<double2> aval((size_t)nnz);
+  std::vector<double2> bvc;
+  std::vector<double> bvr;
+  if (h->b_is_complex)
+    bvc.resize((size_t)nnzB);
+  else
+    bvr.resize((size_t)nnzB);
+  std::vector<int64_t> dstart(n), ustart(n);
+  std::vector<int64_t> wlt(nthr, 0), wut(nthr, 0);
+  parallel_rows(n, nthr, [&](int t, int64_t lo, int64_t hi) {
+    std::vector<Ent> buf;
+    buf.reserve(256);
+    for (int64_t i = lo; i < hi; ++i) {
+      merged_row(i, buf);
+      int64_t k = rowptr[i] - 1, kb = browptr[i];
+      int last = -1;
+      const int pi = node_of[i];
+      int64_t ds = -1, us = -1;
+      for (const Ent& e : buf) {
+        if (e.col != last) {
+          ++k;
+          last = e.col;
+          col[k] = e.col;
+          aval[k] = make_double2(0.0, 0.0);
+          const int q = node_of[e.col];
+          if (q >= pi && ds < 0) ds = k;
+          if (q > pi && us < 0) us = k;
+        }
+        if (e.src == 0) {
+          aval[k].x += e.v.real();
+          aval[k].y += e.v.imag();
+        } else {
+          bcol[kb] = e.col;
+          bmap[kb] = (int)k;
+          if (h->b_is_complex)
+            bvc[kb] = make_double2(e.v.real(), e.v.imag());
+          else
+            bvr[kb] = e.v.real();
+          ++kb;
+        }
       }
+      if (us < 0) us = rowptr[i + 1];
+      if (ds < 0) ds = us;
+      dstart[i] = ds;
+      ustart[i] = us;
+      wlt[t] = std::max<int64_t>(wlt[t], ds - rowptr[i]);
+      wut[t] = std::max<int64_t>(wut[t], rowptr[i + 1] - us);
+    }
+  });
+  int64_t wl = 0, wu = 0;
+  for (int t = 0; t < nthr; ++t) {
+    wl = std::max(wl, wlt[t]);
+    wu = std::max(wu, wut[t]);
   }
-  // L blocks by column (needed by the l-sharded spikes: V_s = M_s L_{s,s-1})
-  for (int64_t c = 0; c < n; ++c) lcount[c + 1] += lcount[c];
-  const int64_t nnzL = lcount[n];
-  std::vector<int> lrow(nnzL);
-  std::vector<int64_t> lpos(nnzL);
+  if (nnz > 0x7fffffff) return kb_fail(h, KB_EINVAL, "more than 2^31 nonzeros are not supported");
+
+  // ---- couplings by column (U: row node p, column node p+1; L: column node p-1)
+  std::vector<int64_t> ucount(n + 1, 0), lcount(n + 1, 0);
+  for (int64_t i = 0; i < n; ++i) {
+    for (int64_t k = rowptr[i]; k < dstart[i]; ++k) lcount[col[k] + 1]++;
+    for (int64_t k = ustart[i]; k < rowptr[i + 1]; ++k) ucount[col[k] + 1]++;
+  }
+  for (int64_t c = 0; c < n; ++c) {
+    ucount[c + 1] += ucount[c];
+    lcount[c + 1] += lcount[c];
+  }
+  const int64_t nnzU = ucount[n], nnzL = lcount[n];
+  h->nnzU = nnzU;
+  std::vector<int> urow((size_t)nnzU), lrow((size_t)nnzL);
+  std::vector<int64_t> upos((size_t)nnzU), lpos((size_t)nnzL);
   {
-    std::vector<int64_t> fill(lcount.begin(), lcount.end() - 1);
-    for (int64_t i = 0; i < n; ++i)
+    std::vector<int64_t> fu(ucount.begin(), ucount.end() - 1), fl(lcount.begin(), lcount.end() - 1);
+    for (int64_t i = 0; i < n; ++i) {
       for (int64_t k = rowptr[i]; k < dstart[i]; ++k) {
-        int64_t dst = fill[col[k]]++;
+        int64_t dst = fl[col[k]]++;
         lrow[dst] = (int)i;
         lpos[dst] = k;
       }
-  }
-  // A alone and B alone (chain order) for SpMV
-  std::vector<int64_t> arowptr(n + 1, 0), browptr(n + 1, 0);
-  std::vector<int> acol, bcol;
-  std::vector<double2> av, bvc;
-  std::vector<double> bvr;
-  acol.reserve(nnzA);
-  av.reserve(nnzA);
-  bcol.reserve(nnzB);
-  for (int64_t i = 0; i < n; ++i) {
-    for (const Ent& e : rows[i]) {
-      if (e.ina) {
-        acol.push_back(e.col);
-        av.push_back(make_double2(e.a.real(), e.a.imag()));
-      }
-      if (e.inb) {
-        bcol.push_back(e.col);
-        if (h->b_is_complex)
-          bvc.push_back(make_double2(e.b.real(), e.b.imag()));
-        else
-          bvr.push_back(e.b.real());
+      for (int64_t k = ustart[i]; k < rowptr[i + 1]; ++k) {
+        int64_t dst = fu[col[k]]++;
+        urow[dst] = (int)i;
+        upos[dst] = k;
       }
     }
-    arowptr[i + 1] = (int64_t)acol.size();
-    browptr[i + 1] = (int64_t)bcol.size();
-    std::vector<Ent>().swap(rows[i]);
   }
-  h->nnzA = (int64_t)acol.size();
-  h->nnzB = (int64_t)bcol.size();
 
   std::vector<int> perm32(n);
   for (int64_t k = 0; k < n; ++k) perm32[k] = (int)perm[k];
@@ -351,9 +365,7 @@ extern "C" int kb_set_chain(kb_handle h, const int64_t* perm, const int64_t* nod
   KB_CUDA(h, upload(h->d_perm, perm32, s));
   KB_CUDA(h, upload(h->d_rowptr, rowptr, s));
   KB_CUDA(h, upload(h->d_col, col, s));
-  KB_CUDA(h, upload(h->d_rowidx, rowidx, s));
   KB_CUDA(h, upload(h->d_Aval, aval, s));
-  KB_CUDA(h, upload(h->d_Bval, bval, s));
   KB_CUDA(h, h->d_Tval.alloc(nnz));
   KB_CUDA(h, upload(h->d_dstart, dstart, s));
   KB_CUDA(h, upload(h->d_ustart, ustart, s));
@@ -363,11 +375,9 @@ extern "C" int kb_set_chain(kb_handle h, const int64_t* perm, const int64_t* nod
   KB_CUDA(h, upload(h->d_lcptr, lcount, s));
   KB_CUDA(h, upload(h->d_lrow, lrow, s));
   KB_CUDA(h, upload(h->d_lpos, lpos, s));
-  KB_CUDA(h, upload(h->d_arowptr, arowptr, s));
-  KB_CUDA(h, upload(h->d_acol, acol, s));
-  KB_CUDA(h, upload(h->d_aval, av, s));
   KB_CUDA(h, upload(h->d_browptr, browptr, s));
   KB_CUDA(h, upload(h->d_bcol, bcol, s));
+  KB_CUDA(h, upload(h->d_bmap, bmap, s));
   if (h->b_is_complex)
     KB_CUDA(h, upload(h->d_bval_c, bvc, s));
   else

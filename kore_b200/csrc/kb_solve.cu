@@ -318,8 +318,8 @@ int kbi_spmv_B_chain(kb_context* h, const double2* x, double2* y, bool scale_row
 
 int kbi_spmv_A_chain(kb_context* h, const double2* x, double2* y) {
   const int n = (int)h->n;
-  kb_spmv<double2, 0><<<nblk((int64_t)n * 32, 256), 256, 0, h->stream>>>(n, h->d_arowptr.p, h->d_acol.p,
-                                                                         h->d_aval.p, x, nullptr, nullptr, y);
+  kb_spmv<double2, 0><<<nblk((int64_t)n * 32, 256), 256, 0, h->stream>>>(n, h->d_rowptr.p, h->d_col.p,
+                                                                         h->d_Aval.p, x, nullptr, nullptr, y);
   h->launches++;
   KB_LAUNCH_CHECK(h);
   return KB_OK;
