@@ -480,7 +480,7 @@ extern "C" int kb_eigs(kb_handle h, int nev, int ncv, double tol, int maxit, int
     h->launches++;
     KB_CUDA(h, cudaStreamSynchronize(s));
     if (h->opt_purify) {
-      KB_TRY(kbi_apply_op_chain(h, x, K.w, h->opt_refine));
+      KB_TRY(kbi_apply_op_chain(h, x, K.w, h->opt_refine_eigs));
       h->stats.op_applies++;
       KB_CUDA(h, cudaMemcpyAsync(x, K.w, (size_t)n * sizeof(double2), cudaMemcpyDeviceToDevice, s));
     }

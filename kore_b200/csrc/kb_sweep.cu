@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(KB_SWEEP_THREADS, 1) kb_sweep_dataflow(KbFlowP
   double2* stage0 = tvec + ((q.bmax + 7) & ~7);
   int64_t* s_moff = (int64_t*)(stage0 + (STAGED ? 2 * (size_t)slice_elems : 0));
   int* s_nptr = (int*)(s_moff + (q.P + 1));
-  __shared__ double2 part[8][8];
+  __shared__ double2 part[16][8];
   __shared__ __align__(8) uint64_t mbar[2];
   constexpr int NW = KB_SWEEP_THREADS / 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -449,6 +449,12 @@ __global__ void __launch_bounds__(KB_SWEEP_THREADS, 1) kb_sweep_dataflow(KbFlowP
 
   // coupling entry of this lane for the first row this warp handles in the NEXT step
   // (software-pipelined: it does not depend on the chain, only its operand does)
+  // Half-warp mode (coupling width <= 16, e.g. 15 for hydro): lanes 0-15 serve row
+  // row0 + 2*wid, lanes 16-31 row row0 + 2*wid + 1, so one pass covers 16 rows per CTA.
+  const bool halfw = q.WL <= 16 && q.WU <= 16;
+  const int hl = halfw ? (lane & 15) : lane;          // lane within the (half-)warp
+  const int hsel = halfw ? (lane >> 4) : 0;           // which of the warp's two rows
+  const int rows_per_pass = halfw ? 2 * NW : NW;
   double2 pv = zmake(0.0, 0.0);
   int pc = 0;
   auto preload = [&](int sn) {
@@ -462,9 +468,9 @@ __global__ void __launch_bounds__(KB_SWEEP_THREADS, 1) kb_sweep_dataflow(KbFlowP
     const int W = useL ? q.WL : q.WU;
     int r0, r1;
     kb_group_rows(s_nptr[pn + 1] - s_nptr[pn], gsize, grank, r0, r1);
-    const int i = r0 + wid;
-    if (i < r1 && lane < W) {
-      const size_t e = (size_t)(s_nptr[pn] + i) * W + lane;
+    const int i = r0 + (halfw ? 2 * wid + hsel : wid);
+    if (i < r1 && hl < W) {
+      const size_t e = (size_t)(s_nptr[pn] + i) * W + hl;
       pv = (useL ? q.Lval : q.Uval)[e];
       pc = (useL ? q.Lcol : q.Ucol)[e];
     }
@@ -481,6 +487,11 @@ __global__ void __launch_bounds__(KB_SWEEP_THREADS, 1) kb_sweep_dataflow(KbFlowP
     kb_group_rows(b, gsize, grank, row0, row1);
     KB_TICK(0);
 
+    // own rows of the forward result, needed by the backward update at the end of the step:
+    // fetched now, off the critical path (this CTA wrote them during its forward sweep)
+    double2 yown = zmake(0.0, 0.0);
+    if (!fwd && tid < row1 - row0 && tid < 2 * NW) yown = kb_poll(&q.yf[o + row0 + tid], q.err);
+
     // ---- phase A: t rows owned by this CTA; the inputs are polled entry by entry
     {
       const double2* src = fwd ? q.yf : q.x;
@@ -489,28 +500,38 @@ __global__ void __launch_bounds__(KB_SWEEP_THREADS, 1) kb_sweep_dataflow(KbFlowP
       const int W = useL ? q.WL : q.WU;
       const double2* val = useL ? q.Lval : q.Uval;
       const int* col = useL ? q.Lcol : q.Ucol;
-      for (int i = row0 + wid; i < row1; i += NW) {
-        const int gi = o + i;
+      for (int ib = row0; ib < row1; ib += rows_per_pass) {
+        const int i = ib + (halfw ? 2 * wid + hsel : wid);
+        const bool active = i < row1;
+        const int gi = o + (active ? i : row0);
         double2 acc = zmake(0.0, 0.0);
-        if (mode == KB_MID) {
-          for (int k = lane; k < q.WL; k += 32)
-            zfma(acc, q.Lval[(size_t)gi * q.WL + k], kb_poll(&src[q.Lcol[(size_t)gi * q.WL + k]], q.err));
-          for (int k = lane; k < q.WU; k += 32)
-            zfma(acc, q.Uval[(size_t)gi * q.WU + k], kb_poll(&src[q.Ucol[(size_t)gi * q.WU + k]], q.err));
-        } else if (i == row0 + wid) {
-          if (lane < W) zfma(acc, pv, kb_poll(&src[pc], q.err));
-          for (int k = lane + 32; k < W; k += 32)
-            zfma(acc, val[(size_t)gi * W + k], kb_poll(&src[col[(size_t)gi * W + k]], q.err));
-        } else {
-          for (int k = lane; k < W; k += 32)
-            zfma(acc, val[(size_t)gi * W + k], kb_poll(&src[col[(size_t)gi * W + k]], q.err));
+        if (active) {
+          if (mode == KB_MID) {
+            for (int k = hl; k < q.WL; k += (halfw ? 16 : 32))
+              zfma(acc, q.Lval[(size_t)gi * q.WL + k], kb_poll(&src[q.Lcol[(size_t)gi * q.WL + k]], q.err));
+            for (int k = hl; k < q.WU; k += (halfw ? 16 : 32))
+              zfma(acc, q.Uval[(size_t)gi * q.WU + k], kb_poll(&src[q.Ucol[(size_t)gi * q.WU + k]], q.err));
+          } else if (ib == row0) {
+            if (hl < W) zfma(acc, pv, kb_poll(&src[pc], q.err));
+            if (!halfw)
+              for (int k = lane + 32; k < W; k += 32)
+                zfma(acc, val[(size_t)gi * W + k], kb_poll(&src[col[(size_t)gi * W + k]], q.err));
+          } else {
+            for (int k = hl; k < W; k += (halfw ? 16 : 32))
+              zfma(acc, val[(size_t)gi * W + k], kb_poll(&src[col[(size_t)gi * W + k]], q.err));
+          }
+        }
+        // reduce within the half-warp (xor 8..1) or the warp (xor 16..1)
+        if (!halfw) {
+          acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
+          acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
         }
 #pragma unroll
-        for (int sft = 16; sft > 0; sft >>= 1) {
+        for (int sft = 8; sft > 0; sft >>= 1) {
           acc.x += __shfl_xor_sync(0xffffffffu, acc.x, sft);
           acc.y += __shfl_xor_sync(0xffffffffu, acc.y, sft);
         }
-        if (lane == 0) tdst[gi] = fwd ? zsub(q.r[gi], acc) : acc;
+        if (active && hl == 0) tdst[gi] = fwd ? zsub(q.r[gi], acc) : acc;
       }
     }
     KB_TICK(1);
@@ -597,17 +618,18 @@ __global__ void __launch_bounds__(KB_SWEEP_THREADS, 1) kb_sweep_dataflow(KbFlowP
       __syncthreads();
       KB_TICK(2);
       const double2* Mp = STAGED ? (stage0 + (size_t)(s & 1) * slice_elems) : (q.M + s_moff[p] + (size_t)row0 * b);
-      // a warp takes one row (or one 1/nsplit part of a row): one shuffle reduction per warp
-      for (int rb = 0; rb < row1 - row0; rb += NW) {
-        const int nr = min(NW, row1 - row0 - rb);
-        const int nsplit = NW / nr;  // >= 1
-        const int myrow = wid / nsplit, mypart = wid % nsplit;
-        double2 acc = zmake(0.0, 0.0);
-        if (myrow < nr) {
+      // a warp takes whole rows (row = wid, wid + 8, ...; up to 16 rows per pass), or a
+      // 1/nsplit part of a row when the CTA owns fewer rows than warps: one shuffle
+      // reduction per row per warp, ONE block barrier per pass
+      for (int rb = 0; rb < row1 - row0; rb += 2 * NW) {
+        const int nr = min(2 * NW, row1 - row0 - rb);
+        const int nsplit = nr >= NW ? 1 : NW / nr;  // >= 1
+        for (int rr = wid / nsplit; rr < nr; rr += NW / nsplit) {
+          const int mypart = wid % nsplit;
           const int seg = (b + nsplit - 1) / nsplit;
           const int j0 = mypart * seg, j1 = min(b, j0 + seg);
-          const double2* Mrow = Mp + (size_t)(rb + myrow) * b;
-          double2 acc1 = zmake(0.0, 0.0);
+          const double2* Mrow = Mp + (size_t)(rb + rr) * b;
+          double2 acc = zmake(0.0, 0.0), acc1 = zmake(0.0, 0.0);
           int j = j0 + lane;
           for (; j + 32 < j1; j += 64) {
             double2 m0 = STAGED ? Mrow[j] : __ldcs(&Mrow[j]);
@@ -617,13 +639,13 @@ __global__ void __launch_bounds__(KB_SWEEP_THREADS, 1) kb_sweep_dataflow(KbFlowP
           }
           if (j < j1) zfma(acc, STAGED ? Mrow[j] : __ldcs(&Mrow[j]), tvec[j]);
           acc = zadd(acc, acc1);
-        }
 #pragma unroll
-        for (int sft = 16; sft > 0; sft >>= 1) {
-          acc.x += __shfl_xor_sync(0xffffffffu, acc.x, sft);
-          acc.y += __shfl_xor_sync(0xffffffffu, acc.y, sft);
+          for (int sft = 16; sft > 0; sft >>= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, sft);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, sft);
+          }
+          if (lane == 0) part[rr][mypart] = acc;
         }
-        if (lane == 0 && myrow < nr) part[myrow][mypart] = acc;
         __syncthreads();
         KB_TICK(3);
         if (tid < nr) {
@@ -635,7 +657,7 @@ __global__ void __launch_bounds__(KB_SWEEP_THREADS, 1) kb_sweep_dataflow(KbFlowP
           else if (mode == KB_MID)
             q.x[gi] = v;
           else
-            q.x[gi] = zsub(kb_poll(&q.yf[gi], q.err), v);
+            q.x[gi] = zsub(rb == 0 ? yown : kb_poll(&q.yf[gi], q.err), v);
         }
         __syncthreads();
       }
