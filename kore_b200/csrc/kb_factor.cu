@@ -312,6 +312,9 @@ kb_gj_panel(const double2* __restrict__ PT, int n, int k0, int nbv, double2* __r
   }
 }
 
+#ifndef KB_UPDATE_TM
+#define KB_UPDATE_TM 64
+#endif
 // Update step (out of place): for every non-panel column j
 //   Aout[i,j] = (i in panel rows ? 0 : Ain[src(i),j]) + sum_k Gp[i,k] Ain[src(k0+k),j]
 // and Aout[i, panel] = Gp[i,:].   Tile TM x TN per CTA, 256 threads, (TM/16) x 4 per thread.
@@ -425,7 +428,7 @@ static void launch_panel(kb_context* h, const GjWs& w, int n, int k0, int nbv) {
 
 template <int NB>
 static void launch_update(kb_context* h, const GjWs& w, const double2* in, double2* out, int n, int k0, int nbv) {
-  constexpr int TM = 32;
+  constexpr int TM = KB_UPDATE_TM;
   dim3 grid((n + 63) / 64, (n + TM - 1) / TM);
   kb_gj_update<NB, TM><<<grid, 256, 0, w.st>>>(in, out, n, k0, nbv, w.Gp, w.srcrow, w.PT);
   (void)h;
