@@ -159,12 +159,24 @@ __global__ void kb_w_rows(const double2* __restrict__ M, int b, int o, double2* 
 // The column loop is unrolled by two only and the register row is rotated by two
 // slots per trip, so the loop body stays small enough for the instruction cache
 // (a fully unrolled NB = 16 body is 140 KB of SASS and ran 2x slower).
+// Shared state of the panel kernel.  prow/swp/best are double-buffered by column parity
+// so that a column needs only TWO block barriers (after the pivot vote, after the
+// pivot-row publication): the buffers written for column k+1 are not the ones column k
+// is still reading.
+template <int NB>
+struct KbPanelShared {
+  double2 prow[2][NB];
+  double2 swp[2][NB];
+  unsigned long long best[2];  // (key << 32) | ~row : atomicMax picks the largest key, lowest row
+};
+
 template <int NB, int RPT, int C>
 __device__ __forceinline__ void kb_gj_column(double2 (&a)[RPT][NB], const int gk, const int n, const int t,
-                                             const int T, const int lane, const int wid, const int nw,
-                                             double2* prow, double2* swp, unsigned* wk, int* wi,
-                                             int* s_src, int* s_orig, int* info) {
-  // ---- pivot search over positions >= gk
+                                             const int T, const int lane, KbPanelShared<NB>& sh, int* s_src,
+                                             int* s_orig, int* info) {
+  const int par = gk & 1;
+  // ---- pivot vote over positions >= gk: integer key = high word of |a|^2 (+1), packed with
+  //      the row so that one shared-memory atomicMax per warp elects the pivot
   unsigned key = 0u;
   int bi = 0x7fffffff;
 #pragma unroll
@@ -178,84 +190,109 @@ __device__ __forceinline__ void kb_gj_column(double2 (&a)[RPT][NB], const int gk
       }
     }
   }
-  unsigned wmax = __reduce_max_sync(0xffffffffu, key);
-  unsigned who = __ballot_sync(0xffffffffu, key == wmax);
-  int wrow = __shfl_sync(0xffffffffu, bi, __ffs(who) - 1);
-  if (lane == 0) {
-    wk[wid] = wmax;
-    wi[wid] = wrow;
+#ifdef KB_ABL_NOSEARCH
+  key = (t == 0) ? 5u : 0u;
+  bi = gk;
+#endif
+  {
+    unsigned long long packed = ((unsigned long long)key << 32) | (unsigned)(~(unsigned)bi);
+    // warp-level max of the packed value (two 32-bit redux steps keep it exact)
+    unsigned wmax = __reduce_max_sync(0xffffffffu, key);
+    unsigned lo = (key == wmax) ? (unsigned)(~(unsigned)bi) : 0u;
+    unsigned wlo = __reduce_max_sync(0xffffffffu, lo);
+    packed = ((unsigned long long)wmax << 32) | wlo;
+    if (lane == 0 && wmax != 0u) atomicMax(&sh.best[par], packed);
   }
   __syncthreads();
-  unsigned k2 = lane < nw ? wk[lane] : 0u;
-  int r2 = lane < nw ? wi[lane] : 0x7fffffff;
-  unsigned gmax = __reduce_max_sync(0xffffffffu, k2);
-  who = __ballot_sync(0xffffffffu, k2 == gmax);
-  const int rp = __shfl_sync(0xffffffffu, r2, __ffs(who) - 1);
+  const unsigned long long best = sh.best[par];
+  const unsigned gmax = (unsigned)(best >> 32);
+  const int rp = (int)(~(unsigned)(best & 0xffffffffu));
   // key 0: no candidate; 1: |pivot|^2 is zero/denormal; >= 0x7ff00001: inf or NaN
-  if (t == 0 && (gmax <= 1u || gmax >= 0x7ff00001u || rp >= n)) atomicExch(info, gk + 1);
-  const int rps = (rp < n) ? rp : gk;  // keep going on breakdown; host reports KB_ESINGULAR
+  const bool broken = gmax <= 1u || gmax >= 0x7ff00001u || rp >= n || rp < gk;
+  const int rps = broken ? gk : rp;  // keep going on breakdown; host reports KB_ESINGULAR
   // ---- publish the (unscaled) pivot row, and the row being displaced from position gk
 #pragma unroll
   for (int r = 0; r < RPT; ++r) {
     int i = t + r * T;
     if (i == rps) {
 #pragma unroll
-      for (int j = 0; j < NB; ++j) prow[j] = a[r][j];
+      for (int j = 0; j < NB; ++j) sh.prow[par][j] = a[r][j];
     }
     if (i == gk && rps != gk) {
 #pragma unroll
-      for (int j = 0; j < NB; ++j) swp[j] = a[r][j];
+      for (int j = 0; j < NB; ++j) sh.swp[par][j] = a[r][j];
     }
   }
-  if (t == 0) {
+  // bookkeeping by the last thread (its warp owns the fewest live rows); it also re-arms the
+  // vote slot that column gk+1 will use
+  if (t == T - 1) {
+    if (broken) atomicExch(info, gk + 1);
     int tmp = s_src[gk];
     s_src[gk] = s_src[rps];
     s_src[rps] = tmp;
     int to = s_orig[gk];
     s_orig[gk] = s_orig[rps];
     s_orig[rps] = to;
+    sh.best[par ^ 1] = 0ull;
   }
   __syncthreads();
-  // ---- eliminate (every thread forms 1/pivot itself: no serial section)
-  const double2 pinv = zinv1(prow[C]);
+  // ---- eliminate.  Every thread forms 1/pivot itself (no serial section) and the pivot
+  //      row goes through the same arithmetic as the others with (base, g) = (0, -1/pivot),
+  //      so there is no divergent branch:  a[j] = base[j] - g * prow[j]
+  const double2 pinv = zinv_fast(sh.prow[par][C]);
+  double2 g[RPT];
+  bool live[RPT];
 #pragma unroll
   for (int r = 0; r < RPT; ++r) {
     int i = t + r * T;
-    if (i < n) {
-      if (i == gk) {
+    live[r] = i < n;
+    const bool is_piv = (i == gk);
+    if (i == rps && rps != gk) {
 #pragma unroll
-        for (int j = 0; j < NB; ++j) a[r][j] = (j == C) ? pinv : zmul(prow[j], pinv);
-      } else {
-        if (i == rps) {
+      for (int j = 0; j < NB; ++j) a[r][j] = sh.swp[par][j];
+    }
+    g[r] = is_piv ? zneg(pinv) : zmul(a[r][C], pinv);
+    if (is_piv) {
 #pragma unroll
-          for (int j = 0; j < NB; ++j) a[r][j] = swp[j];
-        }
-        double2 g = zmul(a[r][C], pinv);
-#pragma unroll
-        for (int j = 0; j < NB; ++j)
-          if (j != C) zfms(a[r][j], g, prow[j]);
-        a[r][C] = zneg(g);
-      }
+      for (int j = 0; j < NB; ++j) a[r][j] = zmake(0.0, 0.0);
     }
   }
-  __syncthreads();
+#ifndef KB_ABL_NOELIM
+  // the pivot row is read in chunks of four entries (a compiler barrier between chunks keeps
+  // ptxas from hoisting all sixteen loads and spilling the register rows)
+#pragma unroll
+  for (int j0 = 0; j0 < NB; j0 += 4) {
+    double2 pr[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) pr[u] = sh.prow[par][j0 + u];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      if (live[r]) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (j0 + u != C) zfms(a[r][j0 + u], g[r], pr[u]);
+      }
+    }
+    asm volatile("" ::: "memory");
+  }
+#endif
+#pragma unroll
+  for (int r = 0; r < RPT; ++r)
+    if (live[r]) a[r][C] = zneg(g[r]);
 }
 
 template <int NB, int RPT, int MAXT>
-__global__ void __launch_bounds__(MAXT)
+__global__ void __launch_bounds__(MAXT, 1)
 kb_gj_panel(const double2* __restrict__ PT, int n, int k0, int nbv, double2* __restrict__ GpT,
             int* __restrict__ orig, int* __restrict__ srcrow, int* __restrict__ info,
             long long* __restrict__ dbg) {
   const long long c0 = clock64();
   extern __shared__ int s_src[];  // n ints: pre-panel row at each position; then n ints: orig
   int* s_orig = s_src + n;
-  __shared__ double2 prow[NB];
-  __shared__ double2 swp[NB];
-  __shared__ unsigned wk[32];
-  __shared__ int wi[32];
+  __shared__ KbPanelShared<NB> sh;
   const int T = blockDim.x;
   const int t = threadIdx.x;
-  const int lane = t & 31, wid = t >> 5, nw = (T + 31) >> 5;
+  const int lane = t & 31;
 
   double2 a[RPT][NB];
 #pragma unroll
@@ -269,16 +306,21 @@ kb_gj_panel(const double2* __restrict__ PT, int n, int k0, int nbv, double2* __r
     s_src[i] = i;
     s_orig[i] = (k0 == 0) ? i : orig[i];
   }
+  if (t == 0) {
+    sh.best[0] = 0ull;
+    sh.best[1] = 0ull;
+  }
   __syncthreads();
 
   const long long c1 = clock64();
   int rot = 0;
 #pragma unroll 1
   for (int k = 0; k < nbv; k += 2) {
-    kb_gj_column<NB, RPT, 0>(a, k0 + k, n, t, T, lane, wid, nw, prow, swp, wk, wi, s_src, s_orig, info);
+    kb_gj_column<NB, RPT, 0>(a, k0 + k, n, t, T, lane, sh, s_src, s_orig, info);
     if (k + 1 < nbv)
-      kb_gj_column<NB, RPT, 1>(a, k0 + k + 1, n, t, T, lane, wid, nw, prow, swp, wk, wi, s_src, s_orig, info);
+      kb_gj_column<NB, RPT, 1>(a, k0 + k + 1, n, t, T, lane, sh, s_src, s_orig, info);
     // rotate the register row left by two: the next active columns are slots 0 and 1 again
+#ifndef KB_ABL_NOROT
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
       double2 f0 = a[r][0], f1 = a[r][1];
@@ -287,8 +329,10 @@ kb_gj_panel(const double2* __restrict__ PT, int n, int k0, int nbv, double2* __r
       a[r][NB - 2] = f0;
       a[r][NB - 1] = f1;
     }
+#endif
     rot += 2;
   }
+  __syncthreads();
   const long long c2 = clock64();
   // register slot j now holds panel column (j + rot) mod NB
 #pragma unroll

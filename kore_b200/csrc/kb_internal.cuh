@@ -64,6 +64,12 @@ __host__ __device__ __forceinline__ double2 zinv1(double2 p) {
   return make_double2(p.x * d, -p.y * d);
 }
 
+// reciprocal through the hardware double-precision reciprocal (correctly rounded 1/d)
+__device__ __forceinline__ double2 zinv_fast(double2 p) {
+  double d = __drcp_rn(p.x * p.x + p.y * p.y);
+  return make_double2(p.x * d, -p.y * d);
+}
+
 // ---------------------------------------------------------------------------
 // error handling
 // ---------------------------------------------------------------------------

@@ -14,7 +14,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libkoreb200.so")
+LIB_PATH = os.environ.get("KB_LIB_PATH", os.path.join(_HERE, "libkoreb200.so"))
 
 KB_OK, KB_EINVAL, KB_ENODEVICE, KB_ECUDA, KB_ENOMEM, KB_ESINGULAR, KB_ESTRUCTURE, KB_ENCCL = range(8)
 ERRNAMES = ["KB_OK", "KB_EINVAL", "KB_ENODEVICE", "KB_ECUDA", "KB_ENOMEM", "KB_ESINGULAR",
