@@ -281,13 +281,13 @@ __device__ __forceinline__ void kb_gj_column(double2 (&a)[RPT][NB], const int gk
     if (live[r]) a[r][C] = zneg(g[r]);
 }
 
-template <int NB, int RPT, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1)
-kb_gj_panel(const double2* __restrict__ PT, int n, int k0, int nbv, double2* __restrict__ GpT,
-            int* __restrict__ orig, int* __restrict__ srcrow, int* __restrict__ info,
-            long long* __restrict__ dbg) {
+// Body of the panel step (see kb_gj_column).  COHERENT: the inputs were written by other
+// CTAs of the SAME kernel (fused update + look-ahead panel), so they are read through L2.
+template <int NB, int RPT, bool COHERENT>
+__device__ __forceinline__ void kb_panel_body(const double2* PT, int n, int k0, int nbv, double2* __restrict__ GpT,
+                                              int* orig, int* __restrict__ srcrow, int* __restrict__ info,
+                                              long long* __restrict__ dbg, int* s_src) {
   const long long c0 = clock64();
-  extern __shared__ int s_src[];  // n ints: pre-panel row at each position; then n ints: orig
   int* s_orig = s_src + n;
   __shared__ KbPanelShared<NB> sh;
   const int T = blockDim.x;
@@ -300,11 +300,11 @@ kb_gj_panel(const double2* __restrict__ PT, int n, int k0, int nbv, double2* __r
     int i = t + r * T;
 #pragma unroll
     for (int j = 0; j < NB; ++j)
-      a[r][j] = (i < n && j < nbv) ? PT[(size_t)j * n + i] : zmake(0.0, 0.0);
+      a[r][j] = (i < n && j < nbv) ? (COHERENT ? __ldcg(&PT[(size_t)j * n + i]) : PT[(size_t)j * n + i]) : zmake(0.0, 0.0);
   }
   for (int i = t; i < n; i += T) {
     s_src[i] = i;
-    s_orig[i] = (k0 == 0) ? i : orig[i];
+    s_orig[i] = (k0 == 0) ? i : (COHERENT ? __ldcg(&orig[i]) : orig[i]);
   }
   if (t == 0) {
     sh.best[0] = 0ull;
@@ -356,6 +356,15 @@ kb_gj_panel(const double2* __restrict__ PT, int n, int k0, int nbv, double2* __r
   }
 }
 
+template <int NB, int RPT, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
+kb_gj_panel(const double2* __restrict__ PT, int n, int k0, int nbv, double2* __restrict__ GpT,
+            int* __restrict__ orig, int* __restrict__ srcrow, int* __restrict__ info,
+            long long* __restrict__ dbg) {
+  extern __shared__ int s_dyn[];  // n ints: pre-panel row at each position; then n ints: orig
+  kb_panel_body<NB, RPT, false>(PT, n, k0, nbv, GpT, orig, srcrow, info, dbg, s_dyn);
+}
+
 #ifndef KB_UPDATE_TM
 #define KB_UPDATE_TM 64
 #endif
@@ -363,30 +372,38 @@ kb_gj_panel(const double2* __restrict__ PT, int n, int k0, int nbv, double2* __r
 //   Aout[i,j] = (i in panel rows ? 0 : Ain[src(i),j]) + sum_k Gp[i,k] Ain[src(k0+k),j]
 // and Aout[i, panel] = Gp[i,:].   Tile TM x TN per CTA, 256 threads, (TM/16) x 4 per thread.
 template <int NB, int TM>
-__global__ void __launch_bounds__(256)
-kb_gj_update(const double2* __restrict__ Ain, double2* __restrict__ Aout, int n, int k0, int nbv,
-             const double2* __restrict__ GpT, const int* __restrict__ srcrow, double2* __restrict__ PTnext) {
+struct KbTileShared {
+  double2 Gs[TM][NB];
+  double2 Rs[NB][64];
+  int src_s[TM];
+};
+
+// One TM x 64 tile of the rank-NB update; called by all threads of the CTA (it contains a
+// block barrier), worked on by the first 256.
+template <int NB, int TM>
+__device__ __forceinline__ void kb_update_tile(const double2* __restrict__ Ain, double2* __restrict__ Aout, int n,
+                                               int k0, int nbv, const double2* __restrict__ GpT,
+                                               const int* __restrict__ srcrow, double2* __restrict__ PTnext,
+                                               int row0, int col0, KbTileShared<NB, TM>& ts) {
   constexpr int TN = 64;
   constexpr int RM = TM / 16;  // rows per thread
-  __shared__ double2 Gs[TM][NB];
-  __shared__ double2 Rs[NB][TN];
-  __shared__ int src_s[TM];
   const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;
-  const int row0 = blockIdx.y * TM, col0 = blockIdx.x * TN;
-
-  for (int e = tid; e < TM * NB; e += 256) {
-    int k = e / TM, i = e % TM;
-    int gi = row0 + i;
-    Gs[i][k] = (gi < n && k < nbv) ? GpT[(size_t)k * n + gi] : zmake(0.0, 0.0);
+  const int tx = tid & 15, ty = (tid >> 4) & 15;
+  if (tid < 256) {
+    for (int e = tid; e < TM * NB; e += 256) {
+      int k = e / TM, i = e % TM;
+      int gi = row0 + i;
+      ts.Gs[i][k] = (gi < n && k < nbv) ? GpT[(size_t)k * n + gi] : zmake(0.0, 0.0);
+    }
+    for (int e = tid; e < NB * TN; e += 256) {
+      int k = e / TN, j = e % TN;
+      int gj = col0 + j;
+      ts.Rs[k][j] = (k < nbv && gj < n) ? Ain[(size_t)srcrow[k0 + k] * n + gj] : zmake(0.0, 0.0);
+    }
+    for (int i = tid; i < TM; i += 256) ts.src_s[i] = (row0 + i < n) ? srcrow[row0 + i] : 0;
   }
-  for (int e = tid; e < NB * TN; e += 256) {
-    int k = e / TN, j = e % TN;
-    int gj = col0 + j;
-    Rs[k][j] = (k < nbv && gj < n) ? Ain[(size_t)srcrow[k0 + k] * n + gj] : zmake(0.0, 0.0);
-  }
-  for (int i = tid; i < TM; i += 256) src_s[i] = (row0 + i < n) ? srcrow[row0 + i] : 0;
   __syncthreads();
+  if (tid >= 256) return;
 
   double2 acc[RM][4];
 #pragma unroll
@@ -397,16 +414,16 @@ kb_gj_update(const double2* __restrict__ Ain, double2* __restrict__ Aout, int n,
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       int gj = col0 + tx + 16 * c;
-      acc[a][c] = (gi < n && gj < n && !prow_) ? Ain[(size_t)src_s[i] * n + gj] : zmake(0.0, 0.0);
+      acc[a][c] = (gi < n && gj < n && !prow_) ? Ain[(size_t)ts.src_s[i] * n + gj] : zmake(0.0, 0.0);
     }
   }
 #pragma unroll
   for (int k = 0; k < NB; ++k) {
     double2 g[RM], rr[4];
 #pragma unroll
-    for (int a = 0; a < RM; ++a) g[a] = Gs[ty + 16 * a][k];
+    for (int a = 0; a < RM; ++a) g[a] = ts.Gs[ty + 16 * a][k];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) rr[c] = Rs[k][tx + 16 * c];
+    for (int c = 0; c < 4; ++c) rr[c] = ts.Rs[k][tx + 16 * c];
 #pragma unroll
     for (int a = 0; a < RM; ++a)
 #pragma unroll
@@ -422,11 +439,74 @@ kb_gj_update(const double2* __restrict__ Ain, double2* __restrict__ Aout, int n,
       int gj = col0 + tx + 16 * c;
       if (gj >= n) continue;
       double2 v = acc[a][c];
-      if (gj >= k0 && gj < k0 + nbv) v = Gs[i][gj - k0];
+      if (gj >= k0 && gj < k0 + nbv) v = ts.Gs[i][gj - k0];
       Aout[(size_t)gi * n + gj] = v;
       // the next panel's columns also go, column-major, to the panel kernel's input buffer
       if (gj >= k0 + NB && gj < k0 + 2 * NB) PTnext[(size_t)(gj - k0 - NB) * n + gi] = v;
     }
+  }
+}
+
+template <int NB, int TM>
+__global__ void __launch_bounds__(256)
+kb_gj_update(const double2* __restrict__ Ain, double2* __restrict__ Aout, int n, int k0, int nbv,
+             const double2* __restrict__ GpT, const int* __restrict__ srcrow, double2* __restrict__ PTnext) {
+  __shared__ KbTileShared<NB, TM> ts;
+  kb_update_tile<NB, TM>(Ain, Aout, n, k0, nbv, GpT, srcrow, PTnext, blockIdx.y * TM, blockIdx.x * 64, ts);
+}
+
+// Fused step with look-ahead: the tiles of update k (Gp_k) and, as one extra CTA, the panel of
+// step k+1.  The tiles of the column block that holds the next panel are scheduled first and
+// count themselves in `ready`; the panel CTA starts as soon as they are done, so the rest of
+// the update overlaps the (latency-bound, single-SM) panel instead of preceding it.
+template <int NB, int RPT, int TM, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
+kb_gj_fused(const double2* __restrict__ Ain, double2* __restrict__ Aout, int n, int k0, int nbv,
+            const double2* __restrict__ GpT, const int* __restrict__ srcrow, double2* PT, int has_next,
+            int nbv_next, double2* __restrict__ GpT_next, int* __restrict__ srcrow_next, int* orig,
+            int* __restrict__ info, unsigned* ready, long long* __restrict__ dbg) {
+  extern __shared__ int s_dyn[];
+  __shared__ KbTileShared<NB, TM> ts;
+  const int nrt = (n + TM - 1) / TM, nct = (n + 63) / 64, ntiles = nrt * nct;
+  const int bid = blockIdx.x;
+  if (bid < ntiles) {
+    const int ct_next = (k0 + NB) / 64;
+    int tc, tr;
+    const bool prio = has_next && ct_next < nct;
+    if (prio) {
+      if (bid < nrt) {
+        tc = ct_next;
+        tr = bid;
+      } else {
+        int idx = bid - nrt;
+        tc = idx / nrt;
+        if (tc >= ct_next) ++tc;
+        tr = idx % nrt;
+      }
+    } else {
+      tc = bid / nrt;
+      tr = bid % nrt;
+    }
+    kb_update_tile<NB, TM>(Ain, Aout, n, k0, nbv, GpT, srcrow, PT, tr * TM, tc * 64, ts);
+    if (prio && tc == ct_next) {
+      // all 256 workers of this tile have stored their part of the next panel
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ready, 1u);
+      }
+    }
+  } else {
+    if (threadIdx.x == 0) {
+      int spins = 0;
+      while (*(volatile unsigned*)ready < (unsigned)nrt && ++spins < (1 << 24)) {
+      }
+      if (*(volatile unsigned*)ready < (unsigned)nrt) atomicExch(info, n + 1);
+      __threadfence();
+    }
+    __syncthreads();
+    kb_panel_body<NB, RPT, true>(PT, n, k0 + NB, nbv_next, GpT_next, orig, srcrow_next, info, dbg, s_dyn);
+    if (threadIdx.x == 0) *ready = 0u;
   }
 }
 
@@ -446,6 +526,9 @@ struct GjWs {
   cudaStream_t st;
   double2 *S0, *S1, *W, *Gp, *PT;
   int *orig, *srcrow;
+  double2* Gp2;     // second panel buffer (look-ahead)
+  int* srcrow2;
+  unsigned* ready;  // next-panel tile counter of the fused step
 };
 
 GjWs kbi_ws_main(kb_context* h) {
@@ -458,6 +541,9 @@ GjWs kbi_ws_main(kb_context* h) {
   w.PT = h->d_PT.p;
   w.orig = h->d_orig.p;
   w.srcrow = h->d_srcrow.p;
+  w.Gp2 = h->d_Gp.p + (size_t)h->bmax * 16;
+  w.srcrow2 = h->d_srcrow.p + h->bmax;
+  w.ready = h->d_ready.p;
   return w;
 }
 
@@ -498,6 +584,36 @@ static int gj_invert(kb_context* h, const GjWs& w, int n, double2** result) {
   const int NB = kbi_panel_width(h, n);
   double2* in = w.S0;
   double2* out = w.S1;
+  if (NB == 16 && !getenv("KB_NO_LOOKAHEAD")) {
+    // first panel alone, then one fused kernel per step: update k + look-ahead panel k+1
+    constexpr int TM = KB_UPDATE_TM;
+    const int nrt = (n + TM - 1) / TM, nct = (n + 63) / 64;
+    int T = (n + 1) / 2;
+    T = ((T + 31) / 32) * 32;
+    if (T < 256) T = 256;
+    if (T > 320) T = 320;
+    launch_panel<16, 2, 320>(h, w, n, 0, n < NB ? n : NB);
+    h->launches++;
+    double2* gp[2] = {w.Gp, w.Gp2};
+    int* sr[2] = {w.srcrow, w.srcrow2};
+    int sidx = 0;
+    for (int k0 = 0; k0 < n; k0 += NB, ++sidx) {
+      const int nbv = n - k0 < NB ? n - k0 : NB;
+      const int knext = k0 + NB;
+      const int has_next = knext < n ? 1 : 0;
+      const int nbv_next = has_next ? (n - knext < NB ? n - knext : NB) : 0;
+      kb_gj_fused<16, 2, TM, 320><<<nrt * nct + has_next, T, 2 * n * sizeof(int), w.st>>>(
+          in, out, n, k0, nbv, gp[sidx & 1], sr[sidx & 1], w.PT, has_next, nbv_next, gp[(sidx + 1) & 1],
+          sr[(sidx + 1) & 1], w.orig, h->d_info.p, w.ready, h->d_sweep_timing.p);
+      h->launches++;
+      double2* t = in;
+      in = out;
+      out = t;
+    }
+    KB_LAUNCH_CHECK(h);
+    *result = in;
+    return KB_OK;
+  }
   for (int k0 = 0; k0 < n; k0 += NB) {
     int nbv = n - k0 < NB ? n - k0 : NB;
     if (NB == 16) {
@@ -561,10 +677,12 @@ int kbi_factor_workspace(kb_context* h) {
   KB_CUDA(h, h->d_S0.alloc((size_t)bmax * bmax));
   KB_CUDA(h, h->d_S1.alloc((size_t)bmax * bmax));
   KB_CUDA(h, h->d_W.alloc((size_t)bmax * bmax));
-  KB_CUDA(h, h->d_Gp.alloc((size_t)bmax * 16));
+  KB_CUDA(h, h->d_Gp.alloc((size_t)bmax * 32));
   KB_CUDA(h, h->d_PT.alloc((size_t)bmax * 16));
   KB_CUDA(h, h->d_orig.alloc(bmax));
-  KB_CUDA(h, h->d_srcrow.alloc(bmax));
+  KB_CUDA(h, h->d_srcrow.alloc(2 * bmax));
+  KB_CUDA(h, h->d_ready.alloc(4));
+  KB_CUDA(h, cudaMemsetAsync(h->d_ready.p, 0, 4 * sizeof(unsigned), s));
   KB_CUDA(h, h->d_info.alloc(1));
   KB_CUDA(h, cudaMemsetAsync(h->d_info.p, 0, sizeof(int), s));
   if (getenv("KB_SWEEP_TIMING")) {
@@ -655,10 +773,10 @@ int kbi_factor(kb_context* h, zcomplex sigma) {
     KB_CUDA(h, h->d_S0b.alloc((size_t)bmax * bmax));
     KB_CUDA(h, h->d_S1b.alloc((size_t)bmax * bmax));
     KB_CUDA(h, h->d_Wb.alloc((size_t)bmax * bmax));
-    KB_CUDA(h, h->d_Gpb.alloc((size_t)bmax * 16));
+    KB_CUDA(h, h->d_Gpb.alloc((size_t)bmax * 32));
     KB_CUDA(h, h->d_PTb.alloc((size_t)bmax * 16));
     KB_CUDA(h, h->d_origb.alloc(bmax));
-    KB_CUDA(h, h->d_srcrowb.alloc(bmax));
+    KB_CUDA(h, h->d_srcrowb.alloc(2 * bmax));
     GjWs bot;
     bot.st = h->stream2;
     bot.S0 = h->d_S0b.p;
@@ -668,6 +786,9 @@ int kbi_factor(kb_context* h, zcomplex sigma) {
     bot.PT = h->d_PTb.p;
     bot.orig = h->d_origb.p;
     bot.srcrow = h->d_srcrowb.p;
+    bot.Gp2 = h->d_Gpb.p + (size_t)bmax * 16;
+    bot.srcrow2 = h->d_srcrowb.p + bmax;
+    bot.ready = h->d_ready.p + 1;
     cudaEvent_t fork, join;
     KB_CUDA(h, cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
     KB_CUDA(h, cudaEventCreateWithFlags(&join, cudaEventDisableTiming));

@@ -202,6 +202,7 @@ struct kb_context {
   cudaStream_t stream2 = nullptr;
   DevBuf<double2> d_S0b, d_S1b, d_Wb, d_Gpb, d_PTb;
   DevBuf<int> d_origb, d_srcrowb;
+  DevBuf<unsigned> d_ready;
   int64_t mid = 0;  // middle node of the two-sided elimination (P-1: one-sided)
   // ELL copies of the couplings + node tables for the persistent sweep kernel
   int WL = 0, WU = 0;
