@@ -323,7 +323,11 @@ def run_ours(args):
         "kernel": "kb_sweep_dataflow (one cooperative launch = one two-sided fwd+bwd pass over all M_p)",
         "bound": "hbm", "achieved": achieved, "peak": peak,
         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-        "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "unit": "GB/s", "frac": achieved / peak,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed
+        # `ncu --set full` capture (profiles/r1_ncu_full_kb_sweep_dataflow_P600_b600.raw.csv):
+        # 7.065 GB + 28.5 MB at P = b = 600 -- the factors are read twice (forward and backward)
+        "traffic": 7.0932e9 if (args.P == 600 and args.b == 600 and world == 1) else None,
         "algorithmic_bytes_per_sweep": alg_bytes, "ms_per_sweep": per_sweep_ms,
         "sweep_share_of_step": sweep_ms / max(1e-9, float(np.sum(dev_ms))),
         "factor_share_of_step": factor_ms / max(1e-9, float(np.sum(dev_ms))),

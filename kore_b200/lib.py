@@ -209,7 +209,15 @@ class Solver:
             ncv = max(2 * nev, nev + 15)
         max_pairs = max_pairs or ncv
         evals = np.zeros(max_pairs, dtype=np.complex128)
-        evecs = np.zeros((self.n, max_pairs), dtype=np.complex128, order="F") if want_vectors else None
+        evecs = None
+        if want_vectors:
+            # the receive buffer is kept on the Solver: a fresh 16 n ncv-byte allocation per call
+            # costs more in page faults than the device-to-host copies themselves
+            ev = getattr(self, "_evecs", None)
+            if ev is None or ev.shape != (self.n, max_pairs):
+                ev = np.empty((self.n, max_pairs), dtype=np.complex128, order="F")
+                self._evecs = ev
+            evecs = ev
         resid = np.zeros(max_pairs, dtype=np.float64)
         nconv = C.c_int(0)
         its = C.c_int(0)
@@ -222,7 +230,7 @@ class Solver:
         k = nconv.value
         info = dict(nconv=k, its=its.value, ncv=ncv, resid=resid[:k].copy())
         info.update(self.stats())
-        return evals[:k].copy(), (np.ascontiguousarray(evecs[:, :k]) if want_vectors else None), info
+        return evals[:k].copy(), (np.array(evecs[:, :k], order="F") if want_vectors else None), info
 
     def stats(self):
         st = KbStats()

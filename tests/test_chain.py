@@ -65,3 +65,12 @@ def test_synthetic_has_kore_structure():
     # deterministic
     A2, B2, _, _ = synthetic.synthetic_pencil(12, 24)
     assert (A != A2).nnz == 0 and (B != B2).nnz == 0
+
+
+def test_sweep_deal_covers_all_items_once():
+    from kore_b200 import sweep
+    items = list(range(256))
+    for world in (1, 2, 4, 8):
+        parts = [sweep.deal(items, r, world) for r in range(world)]
+        assert sorted(sum(parts, [])) == items
+        assert max(map(len, parts)) - min(map(len, parts)) <= 1

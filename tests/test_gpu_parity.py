@@ -202,3 +202,25 @@ def test_persistent_sweep_matches_per_node_kernels(lib, name):
     # conditioning level, not bitwise
     assert np.linalg.norm(xs[0] - xs[2]) <= 1e-9 * np.linalg.norm(xs[0])
     assert np.linalg.norm(xs[0] - xs[4]) <= 1e-12 * np.linalg.norm(xs[0])
+
+
+def test_forced_frequency_sweep_throughput_mode(lib):
+    # config 5 in miniature: one pencil, several forcing frequencies, each a refactor + solve;
+    # two "ranks" deal the frequencies between them and together cover the sweep
+    import scipy.sparse.linalg as ssl
+    from kore_b200 import sweep
+    cf = load_case("forced_small")
+    ce = load_case("forced_small_eig")
+    b = np.asarray(cf.bf.todense()).ravel().astype(np.complex128)
+    omegas = np.linspace(-2.0, 2.0, 6)
+    got = {}
+    for rank in (0, 1):
+        om, X, times = sweep.forced_sweep(ce.A, ce.B, b, omegas, ce.perm, ce.nodeptr, rank=rank, world=2)
+        assert len(om) == 3 and np.all(times > 0)
+        for k, w in enumerate(om):
+            got[float(w)] = X[:, k]
+    assert sorted(got) == sorted(float(w) for w in omegas)
+    for w, x in got.items():
+        T = (ce.A - 1j * w * ce.B).tocsc()
+        xo = ssl.splu(T).solve(b)
+        assert np.linalg.norm(x - xo) <= 1e-9 * np.linalg.norm(xo)
