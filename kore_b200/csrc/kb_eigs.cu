@@ -300,7 +300,8 @@ extern "C" int kb_eigs(kb_handle h, int nev, int ncv, double tol, int maxit, int
   KB_CUDA(h, h->d_h.alloc(4 * (ncv + 2)));
   KB_CUDA(h, h->d_hpart.alloc((size_t)(ncv + 1) * K.nchunks));
   KB_CUDA(h, h->d_Q.alloc((size_t)ncv * ncv));
-  DevBuf<double> d_normpart, d_beta;
+  DevBuf<double>& d_normpart = h->d_normpart;
+  DevBuf<double>& d_beta = h->d_beta;
   KB_CUDA(h, d_normpart.alloc(std::max(K.nblocks, 3 * 512)));
   KB_CUDA(h, d_beta.alloc(4));
   K.V = h->d_V.p;
@@ -311,15 +312,11 @@ extern "C" int kb_eigs(kb_handle h, int nev, int ncv, double tol, int maxit, int
   K.Qdev = h->d_Q.p;
   K.normpart = d_normpart.p;
   K.beta_dev = d_beta.p;
-  KB_CUDA(h, cudaMallocHost((void**)&K.h_host, (size_t)(ncv + 1) * (ncv + 1) * sizeof(double2)));
-  KB_CUDA(h, cudaMallocHost((void**)&K.beta_host, (ncv + 1) * sizeof(double)));
-  struct Pinned {
-    Krylov& k;
-    ~Pinned() {
-      if (k.h_host) cudaFreeHost(k.h_host);
-      if (k.beta_host) cudaFreeHost(k.beta_host);
-    }
-  } pinned_guard{K};
+  // pinned mirrors live on the context (65 x 65 entries cover every supported ncv)
+  if (!h->pinned_h) KB_CUDA(h, cudaMallocHost((void**)&h->pinned_h, (size_t)66 * 66 * sizeof(double2)));
+  if (!h->pinned_beta) KB_CUDA(h, cudaMallocHost((void**)&h->pinned_beta, 66 * sizeof(double)));
+  K.h_host = (double2*)h->pinned_h;
+  K.beta_host = (double*)h->pinned_beta;
 
   // ---- start vector: v0 (or seeded random) mapped to chain order, pushed through
   //      the operator once so that it lies in range(OP) (no null(B) component), unit norm
@@ -467,7 +464,7 @@ extern "C" int kb_eigs(kb_handle h, int nev, int ncv, double tol, int maxit, int
   double2* x = h->d_w2.p;
   double2* ax = h->d_w2.p + n;
   double2* bx = h->d_w2.p + 2 * (size_t)n;
-  DevBuf<double2> d_xo;
+  DevBuf<double2>& d_xo = h->d_xo;
   KB_CUDA(h, d_xo.alloc(n));
   const int rb = 256;
   std::vector<double> rpart(3 * rb);

@@ -222,7 +222,10 @@ struct kb_context {
 
   // Krylov workspaces
   DevBuf<double2> d_V;  // n x (ncv+1), column-major
-  DevBuf<double2> d_w, d_w2, d_h, d_hpart, d_Q;
+  DevBuf<double2> d_w, d_w2, d_h, d_hpart, d_Q, d_xo;
+  DevBuf<double> d_normpart, d_beta;
+  void* pinned_h = nullptr;
+  void* pinned_beta = nullptr;
 
   // captured sweep graphs, keyed by the (rhs, solution) buffers
   struct SweepGraph {

@@ -69,6 +69,8 @@ extern "C" int kb_destroy(kb_handle h) {
   }
   kbi_nccl_destroy(h);
   kbi_drop_graphs(h);
+  if (h->pinned_h) cudaFreeHost(h->pinned_h);
+  if (h->pinned_beta) cudaFreeHost(h->pinned_beta);
   delete h;
   return KB_OK;
 }
@@ -106,6 +108,18 @@ extern "C" int kb_stream(kb_handle h, void** s) {
   return KB_OK;
 }
 
+template <typename F>
+static void parallel_for(int64_t n, F f) {
+  const int nthr = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  if (n < (1 << 16)) {
+    f(0, n);
+    return;
+  }
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nthr; ++t) pool.emplace_back([=]() { f(n * t / nthr, n * (t + 1) / nthr); });
+  for (auto& th : pool) th.join();
+}
+
 static int ingest(kb_context* h, HostCSR& M, int64_t n, int index_bytes, const void* indptr,
                   const void* indices, const void* values, bool is_complex, const char* name) {
   M.n = n;
@@ -120,26 +134,37 @@ static int ingest(kb_context* h, HostCSR& M, int64_t n, int index_bytes, const v
   if (M.indptr[0] != 0) return kb_fail(h, KB_EINVAL, "%s: indptr[0] != 0", name);
   for (int64_t i = 0; i < n; ++i)
     if (M.indptr[i + 1] < M.indptr[i]) return kb_fail(h, KB_EINVAL, "%s: indptr not monotone", name);
-  int64_t nnz = M.indptr[n];
+  const int64_t nnz = M.indptr[n];
   M.indices.resize(nnz);
-  if (index_bytes == 4) {
-    const int32_t* p = (const int32_t*)indices;
-    for (int64_t k = 0; k < nnz; ++k) M.indices[k] = p[k];
-  } else {
-    const int64_t* p = (const int64_t*)indices;
-    for (int64_t k = 0; k < nnz; ++k) M.indices[k] = p[k];
-  }
-  for (int64_t k = 0; k < nnz; ++k)
-    if (M.indices[k] < 0 || M.indices[k] >= n)
-      return kb_fail(h, KB_EINVAL, "%s: column index out of range", name);
   M.values.resize(nnz);
-  if (is_complex) {
+  std::vector<int> badv(64, 0);
+  int64_t* idst = M.indices.data();
+  zcomplex* vdst = M.values.data();
+  int* badp = badv.data();
+  parallel_for(nnz, [=](int64_t lo, int64_t hi) {
+    int bad = 0;
+    if (index_bytes == 4) {
+      const int32_t* p = (const int32_t*)indices;
+      for (int64_t k = lo; k < hi; ++k) {
+        idst[k] = p[k];
+        bad |= (p[k] < 0 || p[k] >= n);
+      }
+    } else {
+      const int64_t* p = (const int64_t*)indices;
+      for (int64_t k = lo; k < hi; ++k) {
+        idst[k] = p[k];
+        bad |= (p[k] < 0 || p[k] >= n);
+      }
+    }
     const double* v = (const double*)values;
-    for (int64_t k = 0; k < nnz; ++k) M.values[k] = zcomplex(v[2 * k], v[2 * k + 1]);
-  } else {
-    const double* v = (const double*)values;
-    for (int64_t k = 0; k < nnz; ++k) M.values[k] = zcomplex(v[k], 0.0);
-  }
+    if (is_complex)
+      for (int64_t k = lo; k < hi; ++k) vdst[k] = zcomplex(v[2 * k], v[2 * k + 1]);
+    else
+      for (int64_t k = lo; k < hi; ++k) vdst[k] = zcomplex(v[k], 0.0);
+    if (bad) badp[(lo >> 10) & 63] = 1;
+  });
+  for (int b : badv)
+    if (b) return kb_fail(h, KB_EINVAL, "%s: column index out of range", name);
   M.present = true;
   return KB_OK;
 }
@@ -237,22 +262,33 @@ extern "C" int kb_set_chain(kb_handle h, const int64_t* perm, const int64_t* nod
   std::vector<int64_t> rowptr(n + 1, 0), browptr(n + 1, 0);
   std::vector<int> bad(nthr, 0);
   parallel_rows(n, nthr, [&](int t, int64_t lo, int64_t hi) {
-    std::vector<Ent> buf;
-    buf.reserve(256);
+    // union length without sorting: a per-thread marker remembers which chain columns the
+    // row's A entries (and earlier B entries) have already claimed
+    std::vector<int64_t> mark(n, -1);
     for (int64_t i = lo; i < hi; ++i) {
-      merged_row(i, buf);
-      int64_t cnt = 0, cntb = 0;
-      int last = -1;
+      const int64_t o = perm[i];
       const int pi = node_of[i];
-      for (const Ent& e : buf) {
-        if (e.col != last) {
+      int64_t cnt = 0, cntb = 0;
+      for (int64_t k = A.indptr[o]; k < A.indptr[o + 1]; ++k) {
+        const int c = iperm[A.indices[k]];
+        if (mark[c] != i) {
+          mark[c] = i;
           ++cnt;
-          last = e.col;
-          int d = node_of[e.col] - pi;
+          int d = node_of[c] - pi;
           if (d > 1 || d < -1) bad[t] = 1;
         }
-        if (e.src == 1) ++cntb;
       }
+      if (B.present)
+        for (int64_t k = B.indptr[o]; k < B.indptr[o + 1]; ++k) {
+          const int c = iperm[B.indices[k]];
+          ++cntb;
+          if (mark[c] != i) {
+            mark[c] = i;
+            ++cnt;
+            int d = node_of[c] - pi;
+            if (d > 1 || d < -1) bad[t] = 1;
+          }
+        }
       rowptr[i + 1] = cnt;
       browptr[i + 1] = cntb;
     }

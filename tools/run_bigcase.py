@@ -28,7 +28,7 @@ def main():
     n = A.shape[0]
     tau = complex(m["rtau"], m["itau"])
     nev = m["nev"]
-    ncv = ko.default_ncv(nev)
+    ncv = max(ko.default_ncv(nev), 24)
     perm, nodeptr = chain.chain_from_params(m["N1"], m["m"], m["lmax"], m["symm"], m["symmB0"], m["hydro"],
                                             m["magnetic"], m["thermal"], m["compositional"])
     out = dict(case=os.path.basename(d.rstrip("/")), n=n, nnzA=int(A.nnz), nnzB=int(B.nnz), nev=nev, ncv=ncv,
@@ -66,7 +66,8 @@ def main():
         out["cpu_solve_s"] = time.perf_counter() - t0
         out["solve_rel_diff"] = float(np.linalg.norm(x - xo) / np.linalg.norm(xo))
         t0 = time.perf_counter()
-        lam_o, X_o, info_o = ko.eigs(A, B, tau, nev, m["which_eigenpairs"], ncv=ncv, tol=1e-12, v0=v0, op=op)
+        lam_o, X_o, info_o = ko.eigs(A, B, tau, nev, m["which_eigenpairs"],
+                                     ncv=(ncv if m["which_eigenpairs"] == "TM" else None), tol=1e-12, v0=v0, op=op)
         out["cpu_eigs_s"] = time.perf_counter() - t0
         out["cpu_applies"] = int(info_o["napply"])
         out["cpu_max_resid"] = float(ko.residuals(A, B, lam_o, X_o).max())
