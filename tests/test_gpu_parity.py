@@ -224,3 +224,21 @@ def test_forced_frequency_sweep_throughput_mode(lib):
         T = (ce.A - 1j * w * ce.B).tocsc()
         xo = ssl.splu(T).solve(b)
         assert np.linalg.norm(x - xo) <= 1e-9 * np.linalg.norm(xo)
+
+
+@pytest.mark.parametrize("name", ["dormy", "spinover"])
+def test_true_residual_convergence(lib, name):
+    # find_Rac.py:18 runs with -eps_true_residual: the convergence test is then
+    # ||A x - lam B x|| <= tol |lam| ||x|| on the Ritz vectors instead of the Arnoldi estimate
+    import kore_oracle as ko
+    case = load_case(name)
+    m = case.meta
+    with make_solver(lib, case) as s:
+        lam, X, info = s.eigs(m["nev"], which=m["which_eigenpairs"], target=case.tau, tol=1e-13,
+                              maxit=m["maxit"], true_residual=True)
+    assert info["nconv"] >= m["nev"], info
+    for lo in case.oracle["eig"]:
+        assert np.min(np.abs(lam - lo)) / abs(lo) < 1e-9
+    r = np.array([np.linalg.norm(case.A @ X[:, i] - lam[i] * (case.B @ X[:, i])) / abs(lam[i])
+                  for i in range(m["nev"])])
+    assert np.all(r < 1e-12), r
