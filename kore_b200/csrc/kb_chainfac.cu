@@ -1,0 +1,478 @@
+// Persistent chain factorisation: the whole two-sided block-Thomas elimination of
+// T = A - sigma B in ONE cooperative launch.
+//
+// Replaces the numeric factorisation of MUMPS / SuperLU_DIST inside E.solve()
+// (/root/reference/bin/solve.py:123) and K.solve (solve.py:227); same algebra as
+// kb_factor.cu (explicit inverses M_p = S_p^-1 of the Schur blocks, Gauss-Jordan with
+// partial pivoting inside the block), different execution model:
+//
+//   * the CTAs of the grid form one group per elimination chain (top-down and
+//     bottom-up, "burn at both ends"); a group walks its chain node by node;
+//   * inside a node, CTA c owns the column strip [c w, (c+1) w) of the b x b Schur
+//     block for the whole inversion and keeps it IN REGISTERS, one matrix row per
+//     thread (w = 8 or 9 columns = 32/36 registers);
+//   * step k of the blocked Gauss-Jordan elimination: the owner of strip k runs the
+//     panel (pivot search, row swaps, elimination over its w columns) on its registers
+//     and publishes the composite transform G_k (b x w) and the pivot list through
+//     L2; every other CTA applies  A <- P_k A + G_k R_k  to its strip, R_k being the
+//     pivot rows of its own strip (exchanged through shared memory);
+//   * there are no kernel boundaries and no grid-wide barriers inside a node: a
+//     release-store of a step counter publishes G_k, consumers poll it; the owner of
+//     strip k+1 runs ahead of the others (look-ahead comes for free);
+//   * Schur-block formation S = D - C_pq (M_q C_qp) is done strip-wise by the same
+//     CTAs from the sparse couplings, so the dense block never exists in memory
+//     before it is inverted; only M_p is written (16 b^2 bytes per node).
+//
+// tests/strip_gj_model.py is the NumPy statement of the strip algebra (net row
+// permutation per step, slot exchange, running permutation).
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "kb_internal.cuh"
+
+#define KF_NB 9       // columns per strip (compile-time bound of the register row)
+#define KF_WMIN 8     // narrowest strip used (fewer, fatter steps for small nodes)
+#define KF_MAXT 640   // threads per CTA = largest supported node
+#define KF_WP 9       // row pitch (double2) of the W strip in shared memory (odd: conflict-free)
+#define KF_SPIN (1 << 22)
+
+struct KfParams {
+  int P, mid;
+  const int64_t* nodeptr;
+  const int64_t* Moff;
+  double2* M;
+  const int64_t* rowptr;
+  const int64_t* dstart;
+  const int64_t* ustart;
+  const int* col;
+  const double2* T;
+  const int64_t* ucptr;
+  const int* urow;
+  const int64_t* upos;
+  const int64_t* lcptr;
+  const int* lrow;
+  const int64_t* lpos;
+  double2* Gbuf[2];   // per group: bmax x bmax, column-major (column = global pivot column)
+  int* pivbuf[2];     // per group: 16 ints per step
+  unsigned* sync;     // per group 96 words: [0] published steps, [32] barrier arrivals, [64] chain done
+  int* info;
+  int* err;
+  long long* dbg;     // optional: 8 cycle counters per CTA
+  int bmax;
+  int G0;             // CTAs of group 0 (the rest form group 1)
+};
+
+__device__ __forceinline__ unsigned kf_ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void kf_st_release(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// thread 0 waits until *ctr >= target; everybody leaves through the block barrier
+__device__ __forceinline__ void kf_wait(const unsigned* ctr, unsigned target, int* err) {
+  if (threadIdx.x == 0) {
+    int spins = 0;
+    while (kf_ld_acquire(ctr) < target) {
+      if ((++spins & 255) == 0 && (*(volatile int*)err != 0 || spins > KF_SPIN)) {
+        atomicExch(err, 1);
+        break;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void kf_group_barrier(unsigned* ctr, unsigned target, int* err) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+    int spins = 0;
+    while (kf_ld_acquire(ctr) < target) {
+      if ((++spins & 255) == 0 && (*(volatile int*)err != 0 || spins > KF_SPIN)) {
+        atomicExch(err, 1);
+        break;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+struct KfShared {
+  double2 slots[2][KF_NB][KF_NB];            // pivot rows of this CTA's strip for the step being applied
+  double2 cand[2][KF_MAXT / 32][KF_NB + 1];  // per-warp pivot candidate row (+ 1/pivot)
+  unsigned long long candkey[2][32];         // (key << 32) | ~row of every warp's candidate
+  int piv[16];                               // pivots of the panel being factored
+};
+
+// S strip -= C_pq (M_q C_qp)[:, strip].  kind 0: q = p-1 (C_qp = U by column, C_pq = the
+// sub-diagonal part of the rows of p); kind 1: q = p+1 (C_qp = L by column, C_pq = the
+// super-diagonal part of the rows).
+template <int NB>
+__device__ __forceinline__ void kf_schur_term(const KfParams& q, double2 (&a)[NB], int kind, int p, int qn, int j0,
+                                              int ws, double2* Ws) {
+  const int t = threadIdx.x;
+  const int o = (int)q.nodeptr[p], b = (int)q.nodeptr[p + 1] - o;
+  const int oq = (int)q.nodeptr[qn], bq = (int)q.nodeptr[qn + 1] - oq;
+  const double2* Mq = q.M + q.Moff[qn];
+  const int64_t* cptr = kind == 0 ? q.ucptr : q.lcptr;
+  const int* crow = kind == 0 ? q.urow : q.lrow;
+  const int64_t* cpos = kind == 0 ? q.upos : q.lpos;
+  // W[k, jj] = sum_e M_q[k, row_e] C_qp[row_e, j0 + jj]   (thread k = row of node q)
+  if (t < bq) {
+    const double2* Mrow = Mq + (size_t)t * bq;
+    for (int jj = 0; jj < ws; ++jj) {
+      const int gc = o + j0 + jj;
+      const int64_t e0 = __ldg(&cptr[gc]), e1 = __ldg(&cptr[gc + 1]);
+      double2 acc = zmake(0.0, 0.0);
+      for (int64_t e = e0; e < e1; ++e) {
+        const int rr = __ldg(&crow[e]) - oq;
+        const double2 cv = __ldg(&q.T[__ldg(&cpos[e])]);
+        zfma(acc, __ldcg(&Mrow[rr]), cv);
+      }
+      Ws[(size_t)t * KF_WP + jj] = acc;
+    }
+  }
+  __syncthreads();
+  if (t < b) {
+    const int gi = o + t;
+    const int64_t k0 = kind == 0 ? __ldg(&q.rowptr[gi]) : __ldg(&q.ustart[gi]);
+    const int64_t k1 = kind == 0 ? __ldg(&q.dstart[gi]) : __ldg(&q.rowptr[gi + 1]);
+    for (int64_t k = k0; k < k1; ++k) {
+      const int cq = __ldg(&q.col[k]) - oq;
+      const double2 v = __ldg(&q.T[k]);
+      const double2* wr = Ws + (size_t)cq * KF_WP;
+#pragma unroll
+      for (int jj = 0; jj < NB; ++jj)
+        if (jj < ws) zfms(a[jj], v, wr[jj]);
+    }
+  }
+  __syncthreads();
+}
+
+template <int NB>
+__global__ void __launch_bounds__(KF_MAXT, 1) kb_chain_factor(KfParams q) {
+  extern __shared__ __align__(16) unsigned char kf_smem[];
+  KfShared& sh = *(KfShared*)kf_smem;
+  int* s_orig = (int*)(kf_smem + sizeof(KfShared));
+  double2* Ws = (double2*)(kf_smem + sizeof(KfShared) + (((size_t)q.bmax * sizeof(int) + 15) & ~(size_t)15));
+
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int NW = (int)blockDim.x >> 5;
+  const int group = (int)blockIdx.x < q.G0 ? 0 : 1;
+  const int Gc = group == 0 ? q.G0 : (int)gridDim.x - q.G0;
+  const int c = group == 0 ? (int)blockIdx.x : (int)blockIdx.x - q.G0;
+  const int P = q.P, mid = q.mid;
+  const int S = group == 0 ? mid + 1 : P - 1 - mid;
+  unsigned* pub = q.sync + group * 96;
+  unsigned* bar = q.sync + group * 96 + 32;
+  unsigned* done1 = q.sync + 96 + 64;
+  double2* Gbuf = q.Gbuf[group];
+  int* pivbuf = q.pivbuf[group];
+  const int ldg = q.bmax;
+  unsigned pubbase = 0, barcount = 0;
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tc = clock64();
+#define KF_TICK(k)                \
+  do {                            \
+    if (q.dbg) {                  \
+      long long _n = clock64();   \
+      tacc[k] += _n - tc;         \
+      tc = _n;                    \
+    }                             \
+  } while (0)
+
+  for (int s = 0; s < S; ++s) {
+    const int p = group == 0 ? s : P - 1 - s;
+    const int o = (int)q.nodeptr[p], b = (int)q.nodeptr[p + 1] - o;
+    int w = (b + Gc - 1) / Gc;
+    if (w < KF_WMIN) w = KF_WMIN;
+    const int K = (b + w - 1) / w;
+    const bool active = c < K;
+    const int j0 = c * w;
+    const int ws = active ? min(w, b - j0) : 0;
+
+    double2 a[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) a[j] = zmake(0.0, 0.0);
+
+    // the middle node needs the last node of the other chain
+    if (group == 0 && s == mid && mid < P - 1) kf_wait(done1, 1u, q.err);
+
+    // ---- Schur block, strip-wise:  S = D_p - C_pq M_q C_qp  (one or two eliminated neighbours)
+    if (active) {
+      if (group == 0 && s > 0) kf_schur_term<NB>(q, a, 0, p, p - 1, j0, ws, Ws);
+      if (group == 1 && s > 0) kf_schur_term<NB>(q, a, 1, p, p + 1, j0, ws, Ws);
+      if (group == 0 && s == mid && mid < P - 1) kf_schur_term<NB>(q, a, 1, p, p + 1, j0, ws, Ws);
+      if (t < b) {
+        // D_p[t, strip]: the row's own-node entries are sorted by column; lower bound, then <= ws entries
+        const int gi = o + t;
+        int64_t lo = __ldg(&q.dstart[gi]), hi = __ldg(&q.ustart[gi]);
+        const int64_t end = hi;
+        const int c0 = o + j0, c1 = o + j0 + ws;
+        while (lo < hi) {
+          int64_t m = (lo + hi) >> 1;
+          if (__ldg(&q.col[m]) < c0)
+            lo = m + 1;
+          else
+            hi = m;
+        }
+        for (int64_t k = lo; k < end; ++k) {
+          const int cc = __ldg(&q.col[k]);
+          if (cc >= c1) break;
+          const double2 v = __ldg(&q.T[k]);
+          const int jj = cc - c0;
+#pragma unroll
+          for (int u = 0; u < NB; ++u)
+            if (u == jj) a[u] = zadd(a[u], v);
+        }
+      }
+    }
+    KF_TICK(0);
+
+    // ---- blocked Gauss-Jordan with IMPLICIT row pivoting, one step per strip.  A row never
+    //      moves: thread t keeps original row t; `isfree` says whether it has been a pivot yet,
+    //      `mycol` which column it pivoted.  (tests/strip_gj_model.py)
+    if (active) {
+      bool isfree = t < b;
+      int mycol = 0;
+      for (int k = 0; k < K; ++k) {
+        const int k0 = k * w;
+        const int wk = min(w, b - k0);
+        if (k == c) {
+          // ================= panel: this CTA's own strip =================
+          // vote for column 0
+          {
+            const unsigned key = isfree ? (unsigned)__double2hiint(zabs2(a[0])) + 1u : 0u;
+            const unsigned wmax = __reduce_max_sync(0xffffffffu, key);
+            const unsigned wlo = __reduce_max_sync(0xffffffffu, (key == wmax) ? ~(unsigned)t : 0u);
+            if (wmax != 0u && key == wmax && ~(unsigned)t == wlo) {
+#pragma unroll
+              for (int j = 0; j < NB; ++j) sh.cand[0][wid][j] = a[j];
+              sh.cand[0][wid][NB] = zinv_fast(a[0]);
+            }
+            if (lane == 0) sh.candkey[0][wid] = wmax ? (((unsigned long long)wmax << 32) | wlo) : 0ull;
+          }
+#pragma unroll
+          for (int cc = 0; cc < NB; ++cc) {
+            if (cc < wk) {
+              const int par = cc & 1;
+              const int gk = k0 + cc;
+              __syncthreads();
+              const unsigned long long ck = (lane < NW) ? sh.candkey[par][lane] : 0ull;
+              const unsigned khi = (unsigned)(ck >> 32), klo = (unsigned)ck;
+              const unsigned mhi = __reduce_max_sync(0xffffffffu, khi);
+              const unsigned mlo = __reduce_max_sync(0xffffffffu, (khi == mhi) ? klo : 0u);
+              int rp = (int)(~mlo);
+              // key 0: no candidate; 1: |pivot|^2 zero/denormal; >= 0x7ff00001: inf or NaN
+              const bool broken = mhi <= 1u || mhi >= 0x7ff00001u || rp >= b || rp < 0;
+              if (broken) rp = -1;  // skip the column; the host reports KB_ESINGULAR
+              const double2* prow = sh.cand[par][broken ? 0 : (rp >> 5)];
+              const double2 pinv = broken ? zmake(0.0, 0.0) : prow[NB];
+              if (t == (int)blockDim.x - 1) {
+                if (broken) atomicExch(q.info, o + gk + 1);
+                sh.piv[cc] = rp;
+                s_orig[gk] = broken ? 0 : rp;
+              }
+              const bool isp = (t == rp);
+              const double2 g = (isp || broken) ? zmake(0.0, 0.0) : zmul(a[cc], pinv);
+              // next column first, so that its pivot vote overlaps the rest of the elimination
+              unsigned key = 0u, wmax = 0u, wlo = 0u;
+              if (cc + 1 < NB) {
+                zfms(a[cc + 1], g, prow[cc + 1]);
+                if (cc + 1 < wk) {
+                  key = (isfree && !isp) ? (unsigned)__double2hiint(zabs2(a[cc + 1])) + 1u : 0u;
+                  wmax = __reduce_max_sync(0xffffffffu, key);
+                  wlo = __reduce_max_sync(0xffffffffu, (key == wmax) ? ~(unsigned)t : 0u);
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < NB; ++j)
+                if (j != cc && j != cc + 1) zfms(a[j], g, prow[j]);
+              if (!broken) a[cc] = zneg(g);
+              if (isp) {
+                // the pivot row itself: row / pivot, and 1 / pivot in the pivot column
+#pragma unroll
+                for (int j = 0; j < NB; ++j) a[j] = (j == cc) ? pinv : zmul(a[j], pinv);
+                isfree = false;
+                mycol = gk;
+              }
+              if (cc + 1 < NB && cc + 1 < wk) {
+                if (wmax != 0u && key == wmax && ~(unsigned)t == wlo) {
+#pragma unroll
+                  for (int j = 0; j < NB; ++j) sh.cand[par ^ 1][wid][j] = a[j];
+                  sh.cand[par ^ 1][wid][NB] = zinv_fast(a[cc + 1]);
+                }
+                if (lane == 0) sh.candkey[par ^ 1][wid] = wmax ? (((unsigned long long)wmax << 32) | wlo) : 0ull;
+              }
+            }
+          }
+          // publish G_k (the strip itself) and the pivots
+          if (t < b) {
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+              if (j < wk) Gbuf[(size_t)(k0 + j) * ldg + t] = a[j];
+          }
+          __syncthreads();
+          if (t < 16) pivbuf[k * 16 + t] = (t < wk) ? sh.piv[t] : -1;
+          __syncthreads();
+          if (t == 0) kf_st_release(pub, pubbase + (unsigned)k + 1u);
+          KF_TICK(1);
+        } else {
+          // ================= consumer: apply step k to this strip =================
+          //   A[i,:] <- (i is a pivot row of the step ? 0 : A[i,:]) + sum_c G[i,c] A[piv_c,:]
+          kf_wait(pub, pubbase + (unsigned)k + 1u, q.err);
+          KF_TICK(2);
+          int pv[NB];
+          {
+            const int4* pp = (const int4*)(pivbuf + k * 16);
+            const int4 v0 = __ldcg(pp), v1 = __ldcg(pp + 1), v2 = __ldcg(pp + 2);
+            const int tmp[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+            for (int j = 0; j < NB; ++j) pv[j] = tmp[j];
+          }
+          double2 g[NB];
+#pragma unroll
+          for (int j = 0; j < NB; ++j)
+            g[j] = (j < wk && t < b) ? __ldcg(&Gbuf[(size_t)(k0 + j) * ldg + t]) : zmake(0.0, 0.0);
+          const int par = k & 1;
+          bool isp = false;
+#pragma unroll
+          for (int cc = 0; cc < NB; ++cc) {
+            if (cc < wk && pv[cc] == t) {
+              isp = true;
+              isfree = false;
+              mycol = k0 + cc;
+#pragma unroll
+              for (int j = 0; j < NB; ++j) sh.slots[par][cc][j] = a[j];
+            }
+          }
+          if (t == (int)blockDim.x - 1) {
+#pragma unroll
+            for (int cc = 0; cc < NB; ++cc)
+              if (cc < wk) s_orig[k0 + cc] = pv[cc] < 0 ? 0 : pv[cc];
+          }
+          __syncthreads();
+          if (isp) {
+#pragma unroll
+            for (int j = 0; j < NB; ++j) a[j] = zmake(0.0, 0.0);
+          }
+#pragma unroll
+          for (int cc = 0; cc < NB; ++cc) {
+            if (cc < wk && pv[cc] >= 0) {
+              const double2* rr = sh.slots[par][cc];
+#pragma unroll
+              for (int j = 0; j < NB; ++j) zfma(a[j], g[cc], rr[j]);
+            }
+          }
+          KF_TICK(3);
+        }
+      }
+      // ---- the strips now hold Y with Y[piv_c, :] = X[c, :], X = (Pi S)^-1, so
+      //      M_p[mycol(t), piv_j] = Y[t, j]   (s_orig[j] = row that pivoted column j)
+      __syncthreads();
+      if (t < b) {
+        double2* Mrow = q.M + q.Moff[p] + (size_t)mycol * b;
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+          if (j < ws) Mrow[s_orig[j0 + j]] = a[j];
+      }
+    }
+    pubbase += (unsigned)K;
+    barcount += (unsigned)Gc;
+    kf_group_barrier(bar, barcount, q.err);
+    KF_TICK(4);
+  }
+  if (group == 1 && c == 0 && t == 0 && S > 0) kf_st_release(done1, 1u);
+  if (q.dbg && t == 0)
+    for (int k = 0; k < 8; ++k) q.dbg[(size_t)blockIdx.x * 8 + k] = tacc[k];
+#undef KF_TICK
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+bool kbi_chainfac_supported(const kb_context* h) {
+  if (getenv("KB_NO_CHAINFAC")) return false;
+  if (h->opt_factor == 0) return false;
+  if (h->bmax > KF_MAXT) return false;
+  // every strip must fit the register row: ceil(bmax / CTAs per chain) <= KF_NB
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) != cudaSuccess) return false;
+  if (getenv("KB_CHAINFAC_GRID")) {
+    int g = atoi(getenv("KB_CHAINFAC_GRID"));
+    if (g >= 2 && g < sms) sms = g;
+  }
+  const int gc = sms / 2;
+  if (gc < 1 || (h->bmax + gc - 1) / gc > KF_NB) return false;
+  return true;
+}
+
+// Factor the whole chain (T must have been built).  two_sided: eliminate from both ends
+// towards node mid; otherwise top-down only (mid = P-1).
+int kbi_chainfac_run(kb_context* h, bool two_sided) {
+  cudaStream_t s = h->stream;
+  const int64_t P = h->P, bmax = h->bmax;
+  int dev = h->device, sms = 0, coop = 0;
+  KB_CUDA(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  KB_CUDA(h, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  if (!coop) return kb_fail(h, KB_ECUDA, "device does not support cooperative launches");
+  int G = sms;
+  if (getenv("KB_CHAINFAC_GRID")) {
+    int g = atoi(getenv("KB_CHAINFAC_GRID"));
+    if (g >= 2 && g < G) G = g;
+  }
+  KfParams q;
+  q.P = (int)P;
+  q.mid = (int)h->mid;
+  q.nodeptr = h->d_nodeptr.p;
+  q.Moff = h->d_Moff.p;
+  q.M = h->d_M.p;
+  q.rowptr = h->d_rowptr.p;
+  q.dstart = h->d_dstart.p;
+  q.ustart = h->d_ustart.p;
+  q.col = h->d_col.p;
+  q.T = h->d_Tval.p;
+  q.ucptr = h->d_ucptr.p;
+  q.urow = h->d_urow.p;
+  q.upos = h->d_upos.p;
+  q.lcptr = h->d_lcptr.p;
+  q.lrow = h->d_lrow.p;
+  q.lpos = h->d_lpos.p;
+  const int ngroups = two_sided ? 2 : 1;
+  KB_CUDA(h, h->d_kfG.alloc((size_t)ngroups * bmax * bmax));
+  const int64_t maxsteps = (bmax + KF_WMIN - 1) / KF_WMIN + 1;
+  KB_CUDA(h, h->d_kfpiv.alloc((size_t)ngroups * maxsteps * 16));
+  KB_CUDA(h, h->d_kfsync.alloc(192));
+  KB_CUDA(h, cudaMemsetAsync(h->d_kfsync.p, 0, 192 * sizeof(unsigned), s));
+  KB_CUDA(h, h->d_info.alloc(1));
+  KB_CUDA(h, cudaMemsetAsync(h->d_info.p, 0, sizeof(int), s));
+  q.Gbuf[0] = h->d_kfG.p;
+  q.Gbuf[1] = two_sided ? h->d_kfG.p + (size_t)bmax * bmax : h->d_kfG.p;
+  q.pivbuf[0] = h->d_kfpiv.p;
+  q.pivbuf[1] = two_sided ? h->d_kfpiv.p + maxsteps * 16 : h->d_kfpiv.p;
+  q.sync = h->d_kfsync.p;
+  q.info = h->d_info.p;
+  q.err = (int*)(h->d_kfsync.p + 190);  // word 190 of the sync block: time-out flag
+  q.dbg = nullptr;
+  if (getenv("KB_SWEEP_TIMING")) {
+    KB_CUDA(h, h->d_sweep_timing.alloc(256 * 8));
+    KB_CUDA(h, cudaMemsetAsync(h->d_sweep_timing.p, 0, 256 * 8 * sizeof(long long), s));
+    q.dbg = h->d_sweep_timing.p;
+  }
+  q.bmax = (int)bmax;
+  q.G0 = two_sided ? (G + 1) / 2 : G;
+  int T = (int)((bmax + 31) / 32) * 32;
+  if (T < 64) T = 64;
+  const size_t smem = sizeof(KfShared) + (((size_t)bmax * sizeof(int) + 15) & ~(size_t)15) +
+                      (size_t)bmax * KF_WP * sizeof(double2);
+  const void* fn = (const void*)kb_chain_factor<KF_NB>;
+  KB_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* args[] = {(void*)&q};
+  KB_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(G), dim3(T), args, smem, s));
+  h->launches++;
+  return KB_OK;
+}

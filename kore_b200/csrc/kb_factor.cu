@@ -752,7 +752,8 @@ int kbi_factor(kb_context* h, zcomplex sigma) {
   if (h->d_M.alloc((size_t)h->Moff[P]) != cudaSuccess)
     return kb_fail(h, KB_ENOMEM, "cannot allocate %.2f GB for the chain factors",
                    h->Moff[P] * 16.0 / 1e9);
-  KB_TRY(kbi_factor_workspace(h));
+  const bool chainfac = kbi_chainfac_supported(h);
+  if (!chainfac) KB_TRY(kbi_factor_workspace(h));
   GjWs top = kbi_ws_main(h);
 
   // Two-sided ("burn at both ends") elimination: nodes 0..mid-1 are eliminated downward
@@ -768,7 +769,14 @@ int kbi_factor(kb_context* h, zcomplex sigma) {
     double b = (double)(h->nodeptr[p + 1] - h->nodeptr[p]);
     flops += 8.0 * b * b * b;
   }
-  if (two_sided) {
+  if (chainfac) {
+    // one persistent launch for the whole elimination (kb_chainfac.cu)
+    KB_CUDA(h, h->d_nodeptr.alloc(P + 1));
+    KB_CUDA(h, h->d_Moff.alloc(P + 1));
+    KB_CUDA(h, cudaMemcpyAsync(h->d_nodeptr.p, h->nodeptr.data(), (P + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    KB_CUDA(h, cudaMemcpyAsync(h->d_Moff.p, h->Moff.data(), (P + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    KB_TRY(kbi_chainfac_run(h, two_sided));
+  } else if (two_sided) {
     if (!h->stream2) KB_CUDA(h, cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
     KB_CUDA(h, h->d_S0b.alloc((size_t)bmax * bmax));
     KB_CUDA(h, h->d_S1b.alloc((size_t)bmax * bmax));
@@ -837,6 +845,13 @@ int kbi_factor(kb_context* h, zcomplex sigma) {
   h->stats.factor_ms = ms;
   h->stats.factor_flops = flops;
   h->stats.factor_bytes = h->Moff[P] * 16;
+  if (chainfac) {
+    int kerr = 0;
+    KB_CUDA(h, cudaMemcpy(&kerr, h->d_kfsync.p + 190, sizeof(int), cudaMemcpyDeviceToHost));
+    if (kerr != 0) {
+      return kb_fail(h, KB_ECUDA, "the persistent factorisation kernel timed out waiting on a peer CTA");
+    }
+  }
   if (info != 0)
     return kb_fail(h, KB_ESINGULAR,
                    "zero or non-finite pivot in a Schur block (A - sigma B is singular to working "

@@ -146,6 +146,7 @@ struct kb_context {
   int opt_purify = 1;
   int64_t opt_seed = 1;
   int opt_panel = 0;
+  int opt_factor = 1;  // 1: persistent strip kernel (kb_chainfac.cu) when the nodes fit, 0: per-step kernels
 
   // pencil as given (host, original ordering)
   int64_t n = 0;
@@ -203,6 +204,10 @@ struct kb_context {
   DevBuf<double2> d_S0b, d_S1b, d_Wb, d_Gpb, d_PTb;
   DevBuf<int> d_origb, d_srcrowb;
   DevBuf<unsigned> d_ready;
+  // persistent strip factorisation (kb_chainfac.cu)
+  DevBuf<double2> d_kfG;
+  DevBuf<int> d_kfpiv;
+  DevBuf<unsigned> d_kfsync;
   int64_t mid = 0;  // middle node of the two-sided elimination (P-1: one-sided)
   // ELL copies of the couplings + node tables for the persistent sweep kernel
   int WL = 0, WU = 0;
@@ -266,6 +271,9 @@ int kbi_factor(kb_context* h, zcomplex sigma);
 int kbi_build_T(kb_context* h, zcomplex sigma);
 int kbi_factor_workspace(kb_context* h);
 int kbi_panel_width(const kb_context* h, int n);
+// ---- kb_chainfac.cu
+bool kbi_chainfac_supported(const kb_context* h);
+int kbi_chainfac_run(kb_context* h, bool two_sided);
 // ---- kb_solve.cu
 //  chain solve in scaled/permuted space: d_y <- T'^{-1} d_r (d_r preserved)
 int kbi_chain_solve(kb_context* h, const double2* r_dev, double2* x_dev, int refine);

@@ -186,6 +186,22 @@ def test_bad_chain_rejected(lib):
     s.close()
 
 
+@pytest.mark.parametrize("name", ["spinover", "dormy", "jones", "magnetic_small"])
+def test_strip_factor_kernel_matches_per_step_kernels(lib, name):
+    # the one-launch strip factorisation (kb_chainfac.cu) and the per-step panel/update
+    # kernels (kb_factor.cu) perform the same pivoted Gauss-Jordan eliminations
+    case = load_case(name)
+    rhs = case.oracle["solve_rhs"]
+    xs = {}
+    for sweep in (0, 1):  # one-sided and two-sided elimination
+        for fac in (0, 1):
+            with make_solver(lib, case, opts={lib.OPT_SWEEP: sweep, lib.OPT_FACTOR: fac, lib.OPT_REFINE: 0}) as s:
+                xs[sweep, fac] = s.solve(rhs)
+    for sweep in (0, 1):
+        err = np.linalg.norm(xs[sweep, 0] - xs[sweep, 1]) / np.linalg.norm(xs[sweep, 0])
+        assert err <= 1e-10, (sweep, err)
+
+
 @pytest.mark.parametrize("name", ["spinover", "dormy", "magnetic_small"])
 def test_persistent_sweep_matches_per_node_kernels(lib, name):
     # the cooperative one-launch sweep and the per-node (graph-replayed) kernels are two
