@@ -58,9 +58,10 @@ struct KfParams {
   unsigned* sync;     // per group 96 words: [0] published steps, [32] barrier arrivals, [64] chain done
   int* info;
   int* err;
-  long long* dbg;     // optional: 8 cycle counters per CTA
+  long long* dbg;     // optional: 16 cycle counters per CTA
   int bmax;
   int G0;             // CTAs of group 0 (the rest form group 1)
+  int transposed;     // store M_p^T (row j of the buffer = column j of M_p) for kb_sweep1.cu
 };
 
 __device__ __forceinline__ unsigned kf_ld_acquire(const unsigned* p) {
@@ -101,9 +102,21 @@ __device__ __forceinline__ void kf_group_barrier(unsigned* ctr, unsigned target,
   __syncthreads();
 }
 
+// 1/d to ~1 ulp: hardware seed (2^-23) and two Newton steps; d is a sum of squares of
+// equilibrated entries, far from the subnormal range the .ftz seed flushes
+__device__ __forceinline__ double kf_rcp(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
 struct KfShared {
   double2 slots[2][KF_NB][KF_NB];            // pivot rows of this CTA's strip for the step being applied
-  double2 cand[2][KF_MAXT / 32][KF_NB + 1];  // per-warp pivot candidate row (+ 1/pivot)
+  double2 prow[2][KF_NB + 1];                // the pivot row of the column being eliminated (+ 1/pivot)
   unsigned long long candkey[2][32];         // (key << 32) | ~row of every warp's candidate
   int piv[16];                               // pivots of the panel being factored
 };
@@ -123,7 +136,9 @@ __device__ __forceinline__ void kf_schur_term(const KfParams& q, double2 (&a)[NB
   const int64_t* cpos = kind == 0 ? q.upos : q.lpos;
   // W[k, jj] = sum_e M_q[k, row_e] C_qp[row_e, j0 + jj]   (thread k = row of node q)
   if (t < bq) {
-    const double2* Mrow = Mq + (size_t)t * bq;
+    // element (t, rr) of M_q: row-major, or column-major when the factors are stored transposed
+    const double2* Mrow = q.transposed ? Mq + t : Mq + (size_t)t * bq;
+    const size_t mstride = q.transposed ? (size_t)bq : 1;
     for (int jj = 0; jj < ws; ++jj) {
       const int gc = o + j0 + jj;
       const int64_t e0 = __ldg(&cptr[gc]), e1 = __ldg(&cptr[gc + 1]);
@@ -131,7 +146,7 @@ __device__ __forceinline__ void kf_schur_term(const KfParams& q, double2 (&a)[NB
       for (int64_t e = e0; e < e1; ++e) {
         const int rr = __ldg(&crow[e]) - oq;
         const double2 cv = __ldg(&q.T[__ldg(&cpos[e])]);
-        zfma(acc, __ldcg(&Mrow[rr]), cv);
+        zfma(acc, __ldcg(&Mrow[(size_t)rr * mstride]), cv);
       }
       Ws[(size_t)t * KF_WP + jj] = acc;
     }
@@ -174,7 +189,7 @@ __global__ void __launch_bounds__(KF_MAXT, 1) kb_chain_factor(KfParams q) {
   int* pivbuf = q.pivbuf[group];
   const int ldg = q.bmax;
   unsigned pubbase = 0, barcount = 0;
-  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tc = clock64();
 #define KF_TICK(k)                \
   do {                            \
@@ -244,24 +259,28 @@ __global__ void __launch_bounds__(KF_MAXT, 1) kb_chain_factor(KfParams q) {
         const int wk = min(w, b - k0);
         if (k == c) {
           // ================= panel: this CTA's own strip =================
-          // vote for column 0
+          // Two block barriers per column: (1) every warp has published the key of its best
+          // free row, (2) the winning row has been published.  Each thread carries 1/|a|^2 of
+          // its own entry in the next pivot column (computed under the shadow of the
+          // elimination FMAs), so the winner publishes 1/pivot without a reciprocal on the
+          // critical path.
+          double rinv;
           {
-            const unsigned key = isfree ? (unsigned)__double2hiint(zabs2(a[0])) + 1u : 0u;
+            const double m2 = zabs2(a[0]);
+            const unsigned key = isfree ? (unsigned)__double2hiint(m2) + 1u : 0u;
             const unsigned wmax = __reduce_max_sync(0xffffffffu, key);
             const unsigned wlo = __reduce_max_sync(0xffffffffu, (key == wmax) ? ~(unsigned)t : 0u);
-            if (wmax != 0u && key == wmax && ~(unsigned)t == wlo) {
-#pragma unroll
-              for (int j = 0; j < NB; ++j) sh.cand[0][wid][j] = a[j];
-              sh.cand[0][wid][NB] = zinv_fast(a[0]);
-            }
             if (lane == 0) sh.candkey[0][wid] = wmax ? (((unsigned long long)wmax << 32) | wlo) : 0ull;
+            rinv = kf_rcp(m2);
           }
 #pragma unroll
           for (int cc = 0; cc < NB; ++cc) {
             if (cc < wk) {
               const int par = cc & 1;
               const int gk = k0 + cc;
+              KF_TICK(8);
               __syncthreads();
+              KF_TICK(9);
               const unsigned long long ck = (lane < NW) ? sh.candkey[par][lane] : 0ull;
               const unsigned khi = (unsigned)(ck >> 32), klo = (unsigned)ck;
               const unsigned mhi = __reduce_max_sync(0xffffffffu, khi);
@@ -270,23 +289,32 @@ __global__ void __launch_bounds__(KF_MAXT, 1) kb_chain_factor(KfParams q) {
               // key 0: no candidate; 1: |pivot|^2 zero/denormal; >= 0x7ff00001: inf or NaN
               const bool broken = mhi <= 1u || mhi >= 0x7ff00001u || rp >= b || rp < 0;
               if (broken) rp = -1;  // skip the column; the host reports KB_ESINGULAR
-              const double2* prow = sh.cand[par][broken ? 0 : (rp >> 5)];
-              const double2 pinv = broken ? zmake(0.0, 0.0) : prow[NB];
+              const bool isp = (t == rp);
+              if (isp) {
+#pragma unroll
+                for (int j = 0; j < NB; ++j) sh.prow[par][j] = a[j];
+                sh.prow[par][NB] = zmake(a[cc].x * rinv, -a[cc].y * rinv);
+              }
               if (t == (int)blockDim.x - 1) {
                 if (broken) atomicExch(q.info, o + gk + 1);
                 sh.piv[cc] = rp;
                 s_orig[gk] = broken ? 0 : rp;
               }
-              const bool isp = (t == rp);
+              __syncthreads();
+              KF_TICK(10);
+              const double2* prow = sh.prow[par];
+              const double2 pinv = broken ? zmake(0.0, 0.0) : prow[NB];
               const double2 g = (isp || broken) ? zmake(0.0, 0.0) : zmul(a[cc], pinv);
               // next column first, so that its pivot vote overlaps the rest of the elimination
-              unsigned key = 0u, wmax = 0u, wlo = 0u;
               if (cc + 1 < NB) {
                 zfms(a[cc + 1], g, prow[cc + 1]);
                 if (cc + 1 < wk) {
-                  key = (isfree && !isp) ? (unsigned)__double2hiint(zabs2(a[cc + 1])) + 1u : 0u;
-                  wmax = __reduce_max_sync(0xffffffffu, key);
-                  wlo = __reduce_max_sync(0xffffffffu, (key == wmax) ? ~(unsigned)t : 0u);
+                  const double m2 = zabs2(a[cc + 1]);
+                  const unsigned key = (isfree && !isp) ? (unsigned)__double2hiint(m2) + 1u : 0u;
+                  const unsigned wmax = __reduce_max_sync(0xffffffffu, key);
+                  const unsigned wlo = __reduce_max_sync(0xffffffffu, (key == wmax) ? ~(unsigned)t : 0u);
+                  if (lane == 0) sh.candkey[par ^ 1][wid] = wmax ? (((unsigned long long)wmax << 32) | wlo) : 0ull;
+                  rinv = kf_rcp(m2);
                 }
               }
 #pragma unroll
@@ -300,16 +328,10 @@ __global__ void __launch_bounds__(KF_MAXT, 1) kb_chain_factor(KfParams q) {
                 isfree = false;
                 mycol = gk;
               }
-              if (cc + 1 < NB && cc + 1 < wk) {
-                if (wmax != 0u && key == wmax && ~(unsigned)t == wlo) {
-#pragma unroll
-                  for (int j = 0; j < NB; ++j) sh.cand[par ^ 1][wid][j] = a[j];
-                  sh.cand[par ^ 1][wid][NB] = zinv_fast(a[cc + 1]);
-                }
-                if (lane == 0) sh.candkey[par ^ 1][wid] = wmax ? (((unsigned long long)wmax << 32) | wlo) : 0ull;
-              }
+              KF_TICK(11);
             }
           }
+          KF_TICK(8);
           // publish G_k (the strip itself) and the pivots
           if (t < b) {
 #pragma unroll
@@ -339,6 +361,7 @@ __global__ void __launch_bounds__(KF_MAXT, 1) kb_chain_factor(KfParams q) {
           for (int j = 0; j < NB; ++j)
             g[j] = (j < wk && t < b) ? __ldcg(&Gbuf[(size_t)(k0 + j) * ldg + t]) : zmake(0.0, 0.0);
           const int par = k & 1;
+          KF_TICK(12);
           bool isp = false;
 #pragma unroll
           for (int cc = 0; cc < NB; ++cc) {
@@ -355,7 +378,9 @@ __global__ void __launch_bounds__(KF_MAXT, 1) kb_chain_factor(KfParams q) {
             for (int cc = 0; cc < NB; ++cc)
               if (cc < wk) s_orig[k0 + cc] = pv[cc] < 0 ? 0 : pv[cc];
           }
+          KF_TICK(13);
           __syncthreads();
+          KF_TICK(14);
           if (isp) {
 #pragma unroll
             for (int j = 0; j < NB; ++j) a[j] = zmake(0.0, 0.0);
@@ -375,10 +400,14 @@ __global__ void __launch_bounds__(KF_MAXT, 1) kb_chain_factor(KfParams q) {
       //      M_p[mycol(t), piv_j] = Y[t, j]   (s_orig[j] = row that pivoted column j)
       __syncthreads();
       if (t < b) {
-        double2* Mrow = q.M + q.Moff[p] + (size_t)mycol * b;
+        double2* Mp = q.M + q.Moff[p];
 #pragma unroll
-        for (int j = 0; j < NB; ++j)
-          if (j < ws) Mrow[s_orig[j0 + j]] = a[j];
+        for (int j = 0; j < NB; ++j) {
+          if (j < ws) {
+            const int cj = s_orig[j0 + j];
+            Mp[q.transposed ? (size_t)cj * b + mycol : (size_t)mycol * b + cj] = a[j];
+          }
+        }
       }
     }
     pubbase += (unsigned)K;
@@ -388,7 +417,7 @@ __global__ void __launch_bounds__(KF_MAXT, 1) kb_chain_factor(KfParams q) {
   }
   if (group == 1 && c == 0 && t == 0 && S > 0) kf_st_release(done1, 1u);
   if (q.dbg && t == 0)
-    for (int k = 0; k < 8; ++k) q.dbg[(size_t)blockIdx.x * 8 + k] = tacc[k];
+    for (int k = 0; k < 16; ++k) q.dbg[(size_t)blockIdx.x * 16 + k] = tacc[k];
 #undef KF_TICK
 }
 
@@ -413,7 +442,7 @@ bool kbi_chainfac_supported(const kb_context* h) {
 
 // Factor the whole chain (T must have been built).  two_sided: eliminate from both ends
 // towards node mid; otherwise top-down only (mid = P-1).
-int kbi_chainfac_run(kb_context* h, bool two_sided) {
+int kbi_chainfac_run(kb_context* h, bool two_sided, bool transposed) {
   cudaStream_t s = h->stream;
   const int64_t P = h->P, bmax = h->bmax;
   int dev = h->device, sms = 0, coop = 0;
@@ -459,12 +488,13 @@ int kbi_chainfac_run(kb_context* h, bool two_sided) {
   q.err = (int*)(h->d_kfsync.p + 190);  // word 190 of the sync block: time-out flag
   q.dbg = nullptr;
   if (getenv("KB_SWEEP_TIMING")) {
-    KB_CUDA(h, h->d_sweep_timing.alloc(256 * 8));
-    KB_CUDA(h, cudaMemsetAsync(h->d_sweep_timing.p, 0, 256 * 8 * sizeof(long long), s));
+    KB_CUDA(h, h->d_sweep_timing.alloc(256 * 16));
+    KB_CUDA(h, cudaMemsetAsync(h->d_sweep_timing.p, 0, 256 * 16 * sizeof(long long), s));
     q.dbg = h->d_sweep_timing.p;
   }
   q.bmax = (int)bmax;
   q.G0 = two_sided ? (G + 1) / 2 : G;
+  q.transposed = transposed ? 1 : 0;
   int T = (int)((bmax + 31) / 32) * 32;
   if (T < 64) T = 64;
   const size_t smem = sizeof(KfShared) + (((size_t)bmax * sizeof(int) + 15) & ~(size_t)15) +
@@ -475,4 +505,13 @@ int kbi_chainfac_run(kb_context* h, bool two_sided) {
   KB_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(G), dim3(T), args, smem, s));
   h->launches++;
   return KB_OK;
+}
+
+// debug: cycle counters of the last persistent factorisation (needs KB_SWEEP_TIMING=1)
+extern "C" int kb_dbg_factor_timing(kb_handle h, long long* out, int max_ctas) {
+  if (!h || !h->d_sweep_timing.p || h->d_sweep_timing.count < 256 * 16) return KB_EINVAL;
+  cudaStreamSynchronize(h->stream);
+  int g = max_ctas < 256 ? max_ctas : 256;
+  cudaMemcpy(out, h->d_sweep_timing.p, (size_t)g * 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+  return g;
 }

@@ -733,6 +733,8 @@ int kbi_factor(kb_context* h, zcomplex sigma) {
   const int64_t P = h->P;
   const int64_t bmax = h->bmax;
   h->factored = false;
+  h->M_transposed = false;
+  h->rng_valid = false;
   h->sigma = sigma;
   kbi_drop_graphs(h);
 
@@ -775,7 +777,16 @@ int kbi_factor(kb_context* h, zcomplex sigma) {
     KB_CUDA(h, h->d_Moff.alloc(P + 1));
     KB_CUDA(h, cudaMemcpyAsync(h->d_nodeptr.p, h->nodeptr.data(), (P + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
     KB_CUDA(h, cudaMemcpyAsync(h->d_Moff.p, h->Moff.data(), (P + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-    KB_TRY(kbi_chainfac_run(h, two_sided));
+    // transposed factors feed the one-hop sweep (kb_sweep1.cu); every other sweep reads M_p row-major
+    int sms = 0;
+    KB_CUDA(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    int sg = sms < 256 ? sms : 256;
+    if (getenv("KB_SWEEP_GRID")) {
+      int gsz = atoi(getenv("KB_SWEEP_GRID"));
+      if (gsz >= 1 && gsz < sg) sg = gsz;
+    }
+    h->M_transposed = h->opt_sweep == 1 && kbi_onehop_supported(h, sg, two_sided, nullptr, nullptr);
+    KB_TRY(kbi_chainfac_run(h, two_sided, h->M_transposed));
   } else if (two_sided) {
     if (!h->stream2) KB_CUDA(h, cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
     KB_CUDA(h, h->d_S0b.alloc((size_t)bmax * bmax));

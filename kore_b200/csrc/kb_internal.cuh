@@ -208,6 +208,12 @@ struct kb_context {
   DevBuf<double2> d_kfG;
   DevBuf<int> d_kfpiv;
   DevBuf<unsigned> d_kfsync;
+  bool M_transposed = false;  // d_M holds M_p^T (strip kernel + one-hop sweep, kb_sweep1.cu)
+  DevBuf<double2> d_ring;     // partial-product ring + exchange buffers of the one-hop sweep
+  DevBuf<unsigned> d_k1flags; // publication flags of the one-hop sweep (one 256-byte line per CTA)
+  unsigned k1_epoch = 0, k1_epoch1 = 0;
+  DevBuf<int4> d_rng;         // coupling ranges per (CTA, step) of the one-hop sweep
+  bool rng_valid = false;
   int64_t mid = 0;  // middle node of the two-sided elimination (P-1: one-sided)
   // ELL copies of the couplings + node tables for the persistent sweep kernel
   int WL = 0, WU = 0;
@@ -273,7 +279,7 @@ int kbi_factor_workspace(kb_context* h);
 int kbi_panel_width(const kb_context* h, int n);
 // ---- kb_chainfac.cu
 bool kbi_chainfac_supported(const kb_context* h);
-int kbi_chainfac_run(kb_context* h, bool two_sided);
+int kbi_chainfac_run(kb_context* h, bool two_sided, bool transposed);
 // ---- kb_solve.cu
 //  chain solve in scaled/permuted space: d_y <- T'^{-1} d_r (d_r preserved)
 int kbi_chain_solve(kb_context* h, const double2* r_dev, double2* x_dev, int refine);
@@ -290,6 +296,9 @@ void kbi_drop_graphs(kb_context* h);
 int kbi_sweep_prepare(kb_context* h);
 int kbi_sweep_persistent(kb_context* h, const double2* r, double2* y);
 int kbi_sweep_dataflow(kb_context* h, const double2* r, double2* y);
+// ---- kb_sweep1.cu
+bool kbi_onehop_supported(const kb_context* h, int G, bool two_sided, int* slice_elems_out, size_t* smem_out);
+int kbi_sweep_onehop(kb_context* h, const double2* r, double2* y);
 // ---- kb_shard.cu
 int kbi_factor_sharded(kb_context* h, zcomplex sigma);
 int kbi_chain_solve_sharded(kb_context* h, const double2* r_dev, double2* x_dev, int refine);

@@ -18,8 +18,8 @@ out = np.zeros(256 * 8, dtype=np.int64)
 L.kb_dbg_sweep_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
 g = L.kb_dbg_sweep_timing(s.h, out.ctypes.data, 256)
 t = out[: g * 8].reshape(g, 8)
-steps = 2 * P - 1
-names = ["pre", "phaseA(poll y)", "poll t", "sync after shfl", "final+store", "gemv j-loop", "shuffles", "-"]
+steps = P
+names = ["pre", "collect", "couple", "stage wait", "gemv+publish", "shadow", "-", "-"] if not os.environ.get("KB_NO_ONEHOP") else ["pre", "phaseA(poll y)", "poll t", "sync after shfl", "final+store", "gemv j-loop", "shuffles", "-"]
 print("per-step cycles (mean over CTAs; CTA0; max):")
 for k in range(8):
     print("  %-15s mean %8.0f  cta0 %8.0f  max %8.0f" % (names[k], t[:, k].mean() / steps, t[0, k] / steps, t[:, k].max() / steps))
