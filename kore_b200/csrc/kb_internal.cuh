@@ -133,6 +133,15 @@ struct HostCSR {
   bool present = false;
 };
 
+// The caller's CSR as uploaded by kb_set_pencil (device), input of the device-side layout build.
+struct KbRawCSR {
+  int64_t n = 0, nnz = 0;
+  int index_bytes = 4;
+  bool is_complex = false, present = false;
+  DevBuf<int64_t> indptr;
+  DevBuf<unsigned char> indices, values;
+};
+
 // One contiguous run of chain nodes factored by block-Thomas on this GPU.
 struct kb_context {
   int device = 0;
@@ -151,6 +160,7 @@ struct kb_context {
   // pencil as given (host, original ordering)
   int64_t n = 0;
   HostCSR A, B;
+  KbRawCSR rawA, rawB;  // device copies (layout built on the device unless KB_HOST_LAYOUT is set)
   bool b_is_complex = false;
 
   // chain
@@ -277,6 +287,10 @@ int kbi_factor(kb_context* h, zcomplex sigma);
 int kbi_build_T(kb_context* h, zcomplex sigma);
 int kbi_factor_workspace(kb_context* h);
 int kbi_panel_width(const kb_context* h, int n);
+// ---- kb_layout.cu
+int kbi_upload_raw(kb_context* h, KbRawCSR& M, int64_t n, int index_bytes, const void* indptr, const void* indices,
+                   const void* values, bool is_complex, const char* name);
+int kbi_layout_device(kb_context* h);
 // ---- kb_chainfac.cu
 bool kbi_chainfac_supported(const kb_context* h);
 int kbi_chainfac_run(kb_context* h, bool two_sided, bool transposed);

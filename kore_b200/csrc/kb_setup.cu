@@ -180,13 +180,25 @@ extern "C" int kb_set_pencil(kb_handle h, int64_t n, int index_bytes, const void
   h->n = n;
   h->chain_set = false;
   h->factored = false;
-  KB_TRY(ingest(h, h->A, n, index_bytes, a_indptr, a_indices, a_values, true, "A"));
   h->B = HostCSR();
+  h->A = HostCSR();
+  h->rawA.present = false;
+  h->rawB.present = false;
   h->b_is_complex = b_is_complex != 0;
-  if (b_indptr) {
-    if (!b_indices || !b_values) return kb_fail(h, KB_EINVAL, "B indices/values missing");
-    KB_TRY(ingest(h, h->B, n, index_bytes, b_indptr, b_indices, b_values, b_is_complex != 0, "B"));
+  if (b_indptr && (!b_indices || !b_values)) return kb_fail(h, KB_EINVAL, "B indices/values missing");
+  if (!getenv("KB_HOST_LAYOUT")) {
+    // the CSR triplets go to the device as they are; kb_set_chain builds the layout there
+    KB_CUDA(h, cudaSetDevice(h->device));
+    KB_TRY(kbi_upload_raw(h, h->rawA, n, index_bytes, a_indptr, a_indices, a_values, true, "A"));
+    h->A.present = true;
+    if (b_indptr) {
+      KB_TRY(kbi_upload_raw(h, h->rawB, n, index_bytes, b_indptr, b_indices, b_values, b_is_complex != 0, "B"));
+      h->B.present = true;
+    }
+    return KB_OK;
   }
+  KB_TRY(ingest(h, h->A, n, index_bytes, a_indptr, a_indices, a_values, true, "A"));
+  if (b_indptr) KB_TRY(ingest(h, h->B, n, index_bytes, b_indptr, b_indices, b_values, b_is_complex != 0, "B"));
   return KB_OK;
 }
 
@@ -232,6 +244,12 @@ extern "C" int kb_set_chain(kb_handle h, const int64_t* perm, const int64_t* nod
     int64_t b = nodeptr[p + 1] - nodeptr[p];
     if (b <= 0) return kb_fail(h, KB_EINVAL, "empty chain node %lld", (long long)p);
     h->bmax = std::max(h->bmax, b);
+  }
+  if (h->rawA.present) {
+    KB_TRY(kbi_layout_device(h));
+    h->chain_set = true;
+    h->factored = false;
+    return KB_OK;
   }
   std::vector<int> iperm(n, -1);
   for (int64_t k = 0; k < n; ++k) {

@@ -1,5 +1,6 @@
 // Single translation unit of libkoreb200.so (kernels are launched across the
 // files below, so they are compiled together instead of with -rdc).
+#include "kb_layout.cu"
 #include "kb_setup.cu"
 #include "kb_chainfac.cu"
 #include "kb_factor.cu"

@@ -186,6 +186,30 @@ def test_bad_chain_rejected(lib):
     s.close()
 
 
+@pytest.mark.parametrize("name", ["spinover", "dormy", "jones", "magnetic_small", "m0_small"])
+def test_device_layout_matches_host_layout(lib, name, monkeypatch):
+    # the chain layout built on the device (radix sort of (row, column) keys, kb_layout.cu) and
+    # the host build (kb_setup.cu) must produce the same arrays: every result is bit-identical
+    case = load_case(name)
+    rhs = case.oracle["solve_rhs"] if "solve_rhs" in case.oracle else None
+    out = []
+    for host in (False, True):
+        if host:
+            monkeypatch.setenv("KB_HOST_LAYOUT", "1")
+        else:
+            monkeypatch.delenv("KB_HOST_LAYOUT", raising=False)
+        with make_solver(lib, case, opts={lib.OPT_REFINE: 0}) as s:
+            x = np.arange(1, case.A.shape[0] + 1) * (1 + 0.5j)
+            res = [s.matvec("A", x)]
+            if case.B is not None:
+                res.append(s.matvec("B", x))
+            if rhs is not None:
+                res.append(s.solve(rhs))
+            out.append(res)
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("name", ["spinover", "dormy", "jones", "magnetic_small"])
 def test_strip_factor_kernel_matches_per_step_kernels(lib, name):
     # the one-launch strip factorisation (kb_chainfac.cu) and the per-step panel/update
