@@ -41,6 +41,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "eigenpairs_per_s (shift-invert factor + Krylov-Schur, nev=10, complex128)"
 UNIT = "eigenpairs/s"
+# DRAM bytes of one kb_sweep_onehop launch at P = b = 600 (ncu --set full, profiles/)
+SWEEP_TRAFFIC_P600_B600 = None
 
 
 def env_int(name, default):
@@ -111,6 +113,27 @@ def make_workload(P, b):
     A, B, perm, nodeptr = synthetic.synthetic_pencil(P, b)
     v0 = synthetic.start_vector(A.shape[0], 1)
     return A, B, perm, nodeptr, v0
+
+
+def pin_csr(M):
+    """The same CSR with data / indices / indptr in pinned (page-locked) host memory, so that the
+    end-to-end leg copies its inputs from pinned buffers (PyTorch is only the allocator here)."""
+    import scipy.sparse as sp
+    import torch
+
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t.numpy(), t
+
+    keep = []
+    arrs = []
+    for a in (M.data, M.indices, M.indptr):
+        v, t = pin(a)
+        arrs.append(v)
+        keep.append(t)
+    out = sp.csr_matrix((arrs[0], arrs[1], arrs[2]), shape=M.shape, copy=False)
+    out._kb_pinned = keep  # keep the pinned tensors alive
+    return out
 
 
 def algorithmic_solve_bytes(P, b, w=7):
@@ -280,6 +303,11 @@ def run_ours(args):
     # each step re-ingests the host CSR, rebuilds the chain layout, uploads, factors, solves
     # and copies the eigenvectors back.  One untimed pass first (device allocations).
     s2 = lib.Solver(local)
+    try:
+        A, B = pin_csr(A), pin_csr(B)
+        pinned = True
+    except Exception:
+        pinned = False
 
     def e2e_step():
         s2.set_pencil(A, B)
@@ -320,14 +348,14 @@ def run_ours(args):
     per_sweep_ms = sweep_ms / max(1, sweeps)
     achieved = alg_bytes / (per_sweep_ms * 1e-3) / 1e9 if per_sweep_ms > 0 else 0.0
     roofline = {
-        "kernel": "kb_sweep_dataflow (one cooperative launch = one two-sided fwd+bwd pass over all M_p)",
+        "kernel": "kb_sweep_onehop (one cooperative launch = one two-sided fwd+bwd pass over all M_p^T)",
         "bound": "hbm", "achieved": achieved, "peak": peak,
         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
         "unit": "GB/s", "frac": achieved / peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed
-        # `ncu --set full` capture (profiles/r1_ncu_full_kb_sweep_dataflow_P600_b600.raw.csv):
-        # 7.065 GB + 28.5 MB at P = b = 600 -- the factors are read twice (forward and backward)
-        "traffic": 7.0932e9 if (args.P == 600 and args.b == 600 and world == 1) else None,
+        # `ncu --set full` capture (profiles/r1_ncu_full_kb_sweep_onehop_P600_b600.raw.csv):
+        # the factors are read twice (forward and backward)
+        "traffic": SWEEP_TRAFFIC_P600_B600 if (args.P == 600 and args.b == 600 and world == 1) else None,
         "algorithmic_bytes_per_sweep": alg_bytes, "ms_per_sweep": per_sweep_ms,
         "sweep_share_of_step": sweep_ms / max(1e-9, float(np.sum(dev_ms))),
         "factor_share_of_step": factor_ms / max(1e-9, float(np.sum(dev_ms))),
@@ -345,7 +373,8 @@ def run_ours(args):
         "max_residual": resid_max, "wall_s_timed_region": wall,
         "clocks": clk, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "s_per_step": e2e_wall / e2e_steps},
+                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "s_per_step": e2e_wall / e2e_steps,
+                "host_buffers": "pinned" if pinned else "pageable"},
         "roofline": roofline,
     }
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -172,18 +172,39 @@ __global__ void kl_coupling_out(int64_t N, int n, const unsigned long long* __re
   posout[i] = (int64_t)pos[i];
 }
 
+// Temporary device buffer from the stream-ordered pool (the pool keeps the memory between
+// calls: cudaMalloc / cudaFree of the ~0.7 GB of sort buffers per layout build cost more
+// than the build itself)
+template <typename T>
+struct PoolBuf {
+  T* p = nullptr;
+  cudaStream_t s = nullptr;
+  PoolBuf() {}
+  PoolBuf(const PoolBuf&) = delete;
+  PoolBuf& operator=(const PoolBuf&) = delete;
+  ~PoolBuf() {
+    if (p) cudaFreeAsync(p, s);
+  }
+  cudaError_t alloc(size_t n, cudaStream_t st) {
+    s = st;
+    if (n == 0) n = 1;
+    return cudaMallocAsync((void**)&p, n * sizeof(T), st);
+  }
+};
+
 struct Tmp {
   void* p = nullptr;
   size_t bytes = 0;
+  cudaStream_t s = nullptr;
   ~Tmp() {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, s);
   }
   cudaError_t need(size_t b) {
     if (b <= bytes) return cudaSuccess;
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, s);
     p = nullptr;
     bytes = 0;
-    cudaError_t e = cudaMalloc(&p, b);
+    cudaError_t e = cudaMallocAsync(&p, b, s);
     if (e == cudaSuccess) bytes = b;
     return e;
   }
@@ -196,7 +217,7 @@ int bits_for(unsigned long long maxkey) {
 }
 
 // exclusive scan of n+1 ints in place (cnt[n] must be 0 on entry; cnt[n] = total on exit)
-int scan_counts(kb_context* h, DevBuf<int>& cnt, int n, Tmp& tmp, cudaStream_t s) {
+int scan_counts(kb_context* h, PoolBuf<int>& cnt, int n, Tmp& tmp, cudaStream_t s) {
   size_t tb = 0;
   KB_CUDA(h, cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, cnt.p, n + 1, s));
   KB_CUDA(h, tmp.need(tb));
@@ -252,6 +273,7 @@ int kbi_layout_device(kb_context* h) {
   const int64_t NA = A.nnz, NB = B.present ? B.nnz : 0, N = NA + NB;
   const int thr = 256;
   Tmp tmp;
+  tmp.s = s;
 
   // ---- permutation, node of every chain position
   std::vector<int> perm32(n);
@@ -263,22 +285,22 @@ int kbi_layout_device(kb_context* h) {
   KB_CUDA(h, cudaMemcpyAsync(h->d_perm.p, perm32.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
   KB_CUDA(h, h->d_nodeptr.alloc(P + 1));
   KB_CUDA(h, cudaMemcpyAsync(h->d_nodeptr.p, h->nodeptr.data(), (P + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-  DevBuf<int> iperm, node_of, bad;
-  KB_CUDA(h, iperm.alloc(n));
-  KB_CUDA(h, node_of.alloc(n));
-  KB_CUDA(h, bad.alloc(1));
+  PoolBuf<int> iperm, node_of, bad;
+  KB_CUDA(h, iperm.alloc(n, s));
+  KB_CUDA(h, node_of.alloc(n, s));
+  KB_CUDA(h, bad.alloc(1, s));
   KB_CUDA(h, cudaMemsetAsync(iperm.p, 0xff, (size_t)n * sizeof(int), s));
   KB_CUDA(h, cudaMemsetAsync(bad.p, 0, sizeof(int), s));
   kl_iperm<<<nblk(n, thr), thr, 0, s>>>(n, h->d_perm.p, iperm.p, bad.p);
   kl_node_of<<<(unsigned)P, 128, 0, s>>>((int)P, h->d_nodeptr.p, node_of.p);
 
   // ---- keys + one stable sort
-  DevBuf<unsigned long long> keys, keys2;
-  DevBuf<unsigned> pay, pay2;
-  KB_CUDA(h, keys.alloc(N > 0 ? N : 1));
-  KB_CUDA(h, keys2.alloc(N > 0 ? N : 1));
-  KB_CUDA(h, pay.alloc(N > 0 ? N : 1));
-  KB_CUDA(h, pay2.alloc(N > 0 ? N : 1));
+  PoolBuf<unsigned long long> keys, keys2;
+  PoolBuf<unsigned> pay, pay2;
+  KB_CUDA(h, keys.alloc(N, s));
+  KB_CUDA(h, keys2.alloc(N, s));
+  KB_CUDA(h, pay.alloc(N, s));
+  KB_CUDA(h, pay2.alloc(N, s));
   const unsigned wblk = nblk((int64_t)n * 32, thr);
   if (A.index_bytes == 4)
     kl_keys<int32_t><<<wblk, thr, 0, s>>>(n, A.indptr.p, (const int32_t*)A.indices.p, iperm.p, keys.p, pay.p, 0, 0u, bad.p);
@@ -300,11 +322,11 @@ int kbi_layout_device(kb_context* h) {
     KB_CUDA(h, cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys.p, keys2.p, pay.p, pay2.p, (int)N, 0, kbits, s));
   }
   // sorted: keys2 / pay2
-  DevBuf<int> head, isb, hscan, bscan;
-  KB_CUDA(h, head.alloc(N + 1));
-  KB_CUDA(h, isb.alloc(N + 1));
-  KB_CUDA(h, hscan.alloc(N + 1));
-  KB_CUDA(h, bscan.alloc(N + 1));
+  PoolBuf<int> head, isb, hscan, bscan;
+  KB_CUDA(h, head.alloc(N + 1, s));
+  KB_CUDA(h, isb.alloc(N + 1, s));
+  KB_CUDA(h, hscan.alloc(N + 1, s));
+  KB_CUDA(h, bscan.alloc(N + 1, s));
   KB_CUDA(h, cudaMemsetAsync(head.p + N, 0, sizeof(int), s));
   KB_CUDA(h, cudaMemsetAsync(isb.p + N, 0, sizeof(int), s));
   kl_heads<<<nblk(N, thr), thr, 0, s>>>(N, keys2.p, pay2.p, head.p, isb.p);
@@ -336,9 +358,9 @@ int kbi_layout_device(kb_context* h) {
     KB_CUDA(h, h->d_bval_c.alloc(nnzB > 0 ? nnzB : 1));
   else
     KB_CUDA(h, h->d_bval_r.alloc(nnzB > 0 ? nnzB : 1));
-  DevBuf<int> rowcnt, browcnt;
-  KB_CUDA(h, rowcnt.alloc(n + 1));
-  KB_CUDA(h, browcnt.alloc(n + 1));
+  PoolBuf<int> rowcnt, browcnt;
+  KB_CUDA(h, rowcnt.alloc(n + 1, s));
+  KB_CUDA(h, browcnt.alloc(n + 1, s));
   KB_CUDA(h, cudaMemsetAsync(rowcnt.p, 0, (size_t)(n + 1) * sizeof(int), s));
   KB_CUDA(h, cudaMemsetAsync(browcnt.p, 0, (size_t)(n + 1) * sizeof(int), s));
   if (h->b_is_complex)
@@ -361,18 +383,18 @@ int kbi_layout_device(kb_context* h) {
   // ---- split points, coupling widths
   KB_CUDA(h, h->d_dstart.alloc(n));
   KB_CUDA(h, h->d_ustart.alloc(n));
-  DevBuf<int> wbuf;
-  KB_CUDA(h, wbuf.alloc(2));
+  PoolBuf<int> wbuf;
+  KB_CUDA(h, wbuf.alloc(2, s));
   KB_CUDA(h, cudaMemsetAsync(wbuf.p, 0, 2 * sizeof(int), s));
   kl_splits<<<nblk(n, thr), thr, 0, s>>>(n, h->d_rowptr.p, h->d_col.p, node_of.p, h->d_dstart.p, h->d_ustart.p,
                                          wbuf.p, wbuf.p + 1);
 
   // ---- couplings by column (U: row node p, column node p+1; L: column node p-1)
-  DevBuf<unsigned long long> counter;
-  KB_CUDA(h, counter.alloc(1));
+  PoolBuf<unsigned long long> counter;
+  KB_CUDA(h, counter.alloc(1, s));
   for (int which = 0; which < 2; ++which) {
-    DevBuf<int> colcnt;
-    KB_CUDA(h, colcnt.alloc(n + 1));
+    PoolBuf<int> colcnt;
+    KB_CUDA(h, colcnt.alloc(n + 1, s));
     KB_CUDA(h, cudaMemsetAsync(colcnt.p, 0, (size_t)(n + 1) * sizeof(int), s));
     KB_CUDA(h, cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), s));
     // the sort buffers of step 2 are large enough (couplings are a subset of the union pattern)
@@ -397,7 +419,6 @@ int kbi_layout_device(kb_context* h) {
     kl_widen<<<nblk(n + 1, thr), thr, 0, s>>>(n, colcnt.p, cptr.p);
     if (nc > 0) kl_coupling_out<<<nblk((int64_t)nc, thr), thr, 0, s>>>((int64_t)nc, n, keys2.p, pay2.p, crow.p, cpos.p);
     if (which == 0) h->nnzU = (int64_t)nc;
-    KB_CUDA(h, cudaStreamSynchronize(s));  // colcnt goes out of scope
   }
 
   int wh[2] = {0, 0};

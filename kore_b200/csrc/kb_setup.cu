@@ -52,6 +52,14 @@ extern "C" int kb_create(kb_handle* out, int device) {
     delete h;
     return KB_ECUDA;
   }
+  {
+    // temporaries of the layout build come from the stream-ordered pool; keep what it has
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   *out = h;
   return KB_OK;
 }
