@@ -42,7 +42,7 @@ sys.path.insert(0, ROOT)
 METRIC = "eigenpairs_per_s (shift-invert factor + Krylov-Schur, nev=10, complex128)"
 UNIT = "eigenpairs/s"
 # DRAM bytes of one kb_sweep_onehop launch at P = b = 600 (ncu --set full, profiles/)
-SWEEP_TRAFFIC_P600_B600 = None
+SWEEP_TRAFFIC_P600_B600 = 7.081519e9 + 0.831415e9  # dram__bytes_read.sum + dram__bytes_write.sum
 
 
 def env_int(name, default):
