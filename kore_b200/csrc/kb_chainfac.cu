@@ -61,6 +61,7 @@ struct KfParams {
   long long* dbg;     // optional: 16 cycle counters per CTA
   int bmax;
   int G0;             // CTAs of group 0 (the rest form group 1)
+  int stagger_ns;     // consumers other than the next owner hold their loads of G_k back by this much
   int transposed;     // store M_p^T (row j of the buffer = column j of M_p) for kb_sweep1.cu
 };
 
@@ -347,6 +348,8 @@ __global__ void __launch_bounds__(KF_MAXT, 1) kb_chain_factor(KfParams q) {
           // ================= consumer: apply step k to this strip =================
           //   A[i,:] <- (i is a pivot row of the step ? 0 : A[i,:]) + sum_c G[i,c] A[piv_c,:]
           kf_wait(pub, pubbase + (unsigned)k + 1u, q.err);
+          // the owner of the next strip is on the critical path: it reads G_k from an idle L2
+          if (q.stagger_ns > 0 && c != k + 1) __nanosleep((unsigned)q.stagger_ns);
           KF_TICK(2);
           int pv[NB];
           {
@@ -495,6 +498,7 @@ int kbi_chainfac_run(kb_context* h, bool two_sided, bool transposed) {
   q.bmax = (int)bmax;
   q.G0 = two_sided ? (G + 1) / 2 : G;
   q.transposed = transposed ? 1 : 0;
+  q.stagger_ns = getenv("KB_CHAINFAC_STAGGER") ? atoi(getenv("KB_CHAINFAC_STAGGER")) : 1000;
   int T = (int)((bmax + 31) / 32) * 32;
   if (T < 64) T = 64;
   const size_t smem = sizeof(KfShared) + (((size_t)bmax * sizeof(int) + 15) & ~(size_t)15) +
