@@ -15,6 +15,10 @@ Cases (SURVEY.md 8d "parity inputs"):
   forced_small    default params + forcing=7, m=2, N=40     (C5 structure, reduced size)
   forced_small_eig  same physics, forcing=0 (A_eig, B_eig for the omega sweep identity)
   m0_small        m=0, symm=1, N=40                         (ll = 1..lmax+1 layout)
+
+dormy additionally gets A1.npz = dA/dRa_gap (the buoyancy entries, 84 656 nonzeros) from two more
+runs of the reference assembler at Ra_gap = 1.6e6 and 1.7e6, for the critical-Rayleigh search
+(kore_b200/rac.py; find_Rac.py re-assembles at every trial Ra, A is affine in Ra_gap).
 """
 import json
 import os
@@ -52,9 +56,35 @@ REFERENCE_GOLDENS = {
 }
 
 
+# Ra_gap of the committed A.npz (tests/dormy2004/params.dormy04:177)
+RA_GAP_REF = {"dormy": 1654042.168683}
+
+
 def recompress(src, dst):
     z = np.load(src)
     np.savez_compressed(dst, **{k: z[k] for k in z.files})
+
+
+def make_rayleigh_slope(name, params, out, Ra_ref):
+    """A1 = (A(Ra_hi) - A(Ra_lo)) / (Ra_hi - Ra_lo), checked against the committed A(Ra_ref)."""
+    lo, hi = 1.6e6, 1.7e6
+    mats = {}
+    for Ra in (lo, hi):
+        tmp = "/tmp/golden_%s_ra%d" % (name, int(Ra))
+        shutil.rmtree(tmp, ignore_errors=True)
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "make_case.py"),
+                               "--params", params, "--out", tmp, "Ra_gap=%r" % Ra])
+        mats[Ra] = ko.load_csr(os.path.join(tmp, "A.npz"))
+    A1 = (mats[hi] - mats[lo]) / (hi - lo)
+    A1.eliminate_zeros()
+    A1 = A1.tocsr()
+    A1.sort_indices()
+    Aref = ko.load_csr(os.path.join(out, "A.npz"))
+    err = abs(mats[lo] + (Ra_ref - lo) * A1 - Aref).max() / abs(Aref).max()
+    assert err < 1e-15, err
+    np.savez_compressed(os.path.join(out, "A1.npz"), data=A1.data, indices=A1.indices,
+                        indptr=A1.indptr, shape=np.array(A1.shape))
+    print(name, "A1 nnz=%d affine check %.1e" % (A1.nnz, err))
 
 
 def main():
@@ -76,6 +106,8 @@ def main():
         meta["params_file"] = params
         if name in REFERENCE_GOLDENS:
             meta["reference_golden"] = REFERENCE_GOLDENS[name]
+        if name in RA_GAP_REF:
+            meta["Ra_gap"] = RA_GAP_REF[name]
         json.dump(meta, open(os.path.join(out, "meta.json"), "w"), indent=1, sort_keys=True)
 
         A = ko.load_csr(os.path.join(out, "A.npz"))
@@ -98,6 +130,8 @@ def main():
             b = ko.load_csr(os.path.join(out, "B_forced.npz"))
             store["forced_x"] = ko.forced_solve(A, b)
         np.savez_compressed(os.path.join(out, "oracle.npz"), **store)
+        if name == "dormy":
+            make_rayleigh_slope(name, params, out, RA_GAP_REF[name])
         print(name, "n=%d nnz=%d" % (n, A.nnz), {k: (v.shape if hasattr(v, "shape") else v) for k, v in store.items()})
 
 

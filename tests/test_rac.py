@@ -1,0 +1,129 @@
+"""Critical-Rayleigh search (BASELINE.json config 2, tests/dormy2004/find_Rac.py).
+
+CPU: the search logic, the affine pencil A(Ra), and the oracle driven through the same search
+reproduces the reference's golden row `tests/dormy2004/reference.dormy04:1` digit for digit.
+GPU (-m gpu): the same search through the C ABI reproduces that row too."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_case
+
+GOLDEN_ROW = "2.000e-05 0.35 1.65404e+06 9 -1.10162e-02"  # tests/dormy2004/reference.dormy04:1
+RA_MIN = 1.6e6  # find_Rac.py:21
+
+
+def dormy_pencil():
+    import kore_oracle as ko
+    from kore_b200 import rac
+    c = load_case("dormy")
+    A1 = ko.load_csr(os.path.join(GOLDEN, "dormy", "A1.npz"))
+    pos, val = rac.slope_positions(c.A, A1)
+    return c, rac.RayleighPencil(c.A, c.meta["Ra_gap"], pos, val, c.B), A1
+
+
+def test_bracket_walks_up_and_down():
+    from kore_b200 import rac
+    calls = []
+
+    def f(x, a):
+        calls.append(x)
+        return a * (x - 6.2185)
+
+    x = rac.bracket_brentq(f, 6.2, args=(1.0,), tol=1e-9)
+    assert abs(x - 6.2185) < 1e-8
+    # first growth rate negative -> walked upwards in steps of dx = 0.01 before Brent
+    assert calls[1] == pytest.approx(6.21) and calls[2] == pytest.approx(6.22)
+    calls.clear()
+    x = rac.bracket_brentq(f, 6.25, args=(1.0,), tol=1e-9)
+    assert abs(x - 6.2185) < 1e-8 and calls[1] == pytest.approx(6.24)
+    # a supplied x2 that brackets is used as it is; one that does not restarts from the nearer end
+    calls.clear()
+    x = rac.bracket_brentq(f, 6.0, x2=6.5, args=(1.0,), tol=1e-9)
+    assert abs(x - 6.2185) < 1e-8 and calls[:2] == [6.0, 6.5]
+    calls.clear()
+    x = rac.bracket_brentq(f, 6.0, x2=6.1, args=(1.0,), tol=1e-9)
+    assert abs(x - 6.2185) < 1e-8 and calls[2] == pytest.approx(6.11)
+    with pytest.raises(RuntimeError):
+        rac.bracket_brentq(lambda x: 1.0 + x * x, 0.0, max_walk=20)
+
+
+def test_rayleigh_pencil_is_the_assembled_matrix():
+    # A(Ra) rebuilt from (A_ref, A1) equals what scipy computes, on A's own pattern, for any Ra;
+    # unsorted column order inside rows is handled
+    from kore_b200 import rac
+    c, pen, A1 = dormy_pencil()
+    for Ra in (1.6e6, c.meta["Ra_gap"], 1.7e6):
+        want = (c.A + (Ra - c.meta["Ra_gap"]) * A1).tocsr()
+        got = pen.at(Ra)
+        assert np.array_equal(got.indices, c.A.indices) and np.array_equal(got.indptr, c.A.indptr)
+        assert abs(got - want).max() <= 1e-16 * abs(want).max()
+    # affine_from_two recovers the same slope from two assemblies
+    lo, hi = pen.at(1.6e6).copy(), pen.at(1.7e6).copy()
+    pos, val = rac.affine_from_two(lo, 1.6e6, hi, 1.7e6)
+    assert np.array_equal(np.sort(pos), np.sort(pen.pos))
+    o1, o2 = np.argsort(pos), np.argsort(pen.pos)
+    assert np.allclose(val[o1], pen.val[o2], rtol=1e-9, atol=0)
+    with pytest.raises(ValueError):
+        import scipy.sparse as sp
+        rac.slope_positions(sp.identity(4, format="csr", dtype=complex), sp.csr_matrix(np.ones((4, 4))))
+
+
+def test_critical_params_row_format(tmp_path):
+    from kore_b200 import rac
+    p = tmp_path / "critical_params.dat"
+    rac.write_critical_params(p, 2e-5, 0.35, 1654042.2, 9, -0.01101623)
+    assert p.read_text().strip() == GOLDEN_ROW
+
+
+def test_oracle_search_reproduces_reference_row(tmp_path):
+    """The oracle (SciPy SuperLU + ARPACK) behind the product's search logic lands on the
+    reference's Ra_c and omega_c to every digit the golden holds."""
+    import kore_oracle as ko
+    from kore_b200 import rac
+    c, pen, _ = dormy_pencil()
+    m = c.meta
+
+    class OracleGrowth:
+        cache = {}
+
+        def __call__(self, x):
+            Ra = 10.0 ** x
+            if Ra not in self.cache:
+                lam, _, _ = ko.eigs(pen.at(Ra), c.B, c.tau, m["nev"], m["which_eigenpairs"])
+                self.cache[Ra] = lam[np.argmax(lam.real)]
+            return self.cache[Ra].real
+
+    g = OracleGrowth()
+    Ra_c, omega_c, sigma_c = rac.find_rac(g, RA_MIN)
+    assert len(g.cache) < 20
+    p = tmp_path / "critical_params.dat"
+    rac.write_critical_params(p, m["Ek"], m["ricb"], Ra_c, m["m"], omega_c)
+    assert p.read_text().strip() == GOLDEN_ROW
+    assert abs(sigma_c) < 1e-6 * abs(omega_c)
+    assert Ra_c == pytest.approx(m["Ra_gap"], rel=5e-6)  # params.dormy04:177 holds more digits
+
+
+@pytest.mark.gpu
+def test_gpu_search_reproduces_reference_row(lib, tmp_path):
+    from kore_b200 import rac
+    c, pen, _ = dormy_pencil()
+    m = c.meta
+    with rac.GrowthRate(pen, c.perm, c.nodeptr, c.tau, m["nev"], m["which_eigenpairs"], tol=m["tol"],
+                        maxit=m["maxit"]) as g:
+        Ra_c, omega_c, sigma_c = rac.find_rac(g, RA_MIN)
+        hist = list(g.history)
+    assert 3 <= len(hist) < 20
+    p = tmp_path / "critical_params.dat"
+    rac.write_critical_params(p, m["Ek"], m["ricb"], Ra_c, m["m"], omega_c)
+    assert p.read_text().strip() == GOLDEN_ROW
+    assert abs(sigma_c) < 1e-6 * abs(omega_c)
+    assert Ra_c == pytest.approx(m["Ra_gap"], rel=5e-6)
+    # the marginal eigenvalue at the golden Ra is the oracle's
+    lam_o = c.oracle["eig"][np.argmax(c.oracle["eig"].real)]
+    with rac.GrowthRate(pen, c.perm, c.nodeptr, c.tau, m["nev"], m["which_eigenpairs"], tol=m["tol"],
+                        maxit=m["maxit"]) as g:
+        g(np.log10(m["Ra_gap"]))
+        lam = list(g.cache.values())[0]
+    assert abs(lam - lam_o) <= 1e-9 * abs(lam_o)
