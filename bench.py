@@ -309,14 +309,28 @@ def run_ours(args):
     except Exception:
         pinned = False
 
+    phases = {"set_pencil_s": 0.0, "set_chain_s": 0.0, "factor_s": 0.0, "eigs_and_d2h_s": 0.0}
+
     def e2e_step():
+        # wall clock of every C-ABI call of the step (each returns after its device work is done)
+        ta = time.perf_counter()
         s2.set_pencil(A, B)
+        tb = time.perf_counter()
         s2.set_chain(perm, nodeptr)
+        tc = time.perf_counter()
         s2.factor(sigma)
-        return s2.eigs(args.nev, "TM", target=sigma, ncv=args.ncv, tol=args.tol, maxit=args.maxit,
-                       v0=v0, want_vectors=True)
+        torch.cuda.synchronize()
+        td = time.perf_counter()
+        out = s2.eigs(args.nev, "TM", target=sigma, ncv=args.ncv, tol=args.tol, maxit=args.maxit,
+                      v0=v0, want_vectors=True)
+        te = time.perf_counter()
+        for k, dt in zip(phases, (tb - ta, tc - tb, td - tc, te - td)):
+            phases[k] += dt
+        return out
 
     e2e_step()
+    for k in phases:
+        phases[k] = 0.0
     barrier()
     t0 = time.perf_counter()
     e2e_pairs = 0
@@ -374,7 +388,8 @@ def run_ours(args):
         "clocks": clk, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "s_per_step": e2e_wall / e2e_steps,
-                "host_buffers": "pinned" if pinned else "pageable"},
+                "host_buffers": "pinned" if pinned else "pageable",
+                "phases_s_per_step": {k: v / e2e_steps for k, v in phases.items()}},
         "roofline": roofline,
     }
     if rank == 0 and world == 1 and not args.no_cpu:
