@@ -150,6 +150,15 @@ int kb_get_stats(kb_handle h, kb_stats* out);
 int kb_solve_dev(kb_handle h, const double* rhs_dev, double* x_dev, int nrhs);
 int kb_stream(kb_handle h, void** cuda_stream);
 
+/* np.savetxt(f, X) with its defaults, as the field and eigenvalue writers use it
+ * (solve.py:275-311: '%.18e', one space, '\n'): element (i, j) = data[i*row_stride +
+ * j*col_stride] (strides in doubles, so the real or imaginary part of a column-major
+ * complex block is written without a copy).  Host code, `nthreads` formatting threads
+ * (0 = all); the bytes are np.savetxt's.  append != 0 opens the file in append mode
+ * (timing.dat, solve.py:309-311). */
+int kb_savetxt(const char* path, const double* data, int64_t rows, int64_t cols, int64_t row_stride,
+               int64_t col_stride, int append, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

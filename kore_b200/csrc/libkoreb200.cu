@@ -9,3 +9,4 @@
 #include "kb_solve.cu"
 #include "kb_eigs.cu"
 #include "kb_shard.cu"
+#include "kb_io.cu"

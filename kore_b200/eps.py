@@ -13,6 +13,7 @@ import numpy as np
 
 from . import chain as _chain
 from . import lib as _lib
+from .lib import savetxt  # noqa: F401  (np.savetxt-compatible threaded writer, kb_savetxt)
 
 
 class Options:

@@ -29,7 +29,7 @@ OPT_EQUILIBRATE, OPT_REFINE, OPT_PURIFY, OPT_SEED, OPT_PANEL, OPT_REFINE_EIGS, O
 EXPORTS = [
     "kb_create", "kb_destroy", "kb_last_error", "kb_set_option", "kb_set_pencil", "kb_set_chain",
     "kb_nccl_unique_id", "kb_set_sharding", "kb_factor", "kb_solve", "kb_apply_op", "kb_matvec",
-    "kb_eigs", "kb_get_stats", "kb_solve_dev", "kb_stream",
+    "kb_eigs", "kb_get_stats", "kb_solve_dev", "kb_stream", "kb_savetxt",
 ]
 
 
@@ -95,12 +95,38 @@ def load():
     lib.kb_get_stats.argtypes = [vp, C.POINTER(KbStats)]
     lib.kb_solve_dev.argtypes = [vp, vp, vp, C.c_int]
     lib.kb_stream.argtypes = [vp, C.POINTER(vp)]
+    lib.kb_savetxt.argtypes = [C.c_char_p, vp, i64, i64, i64, i64, C.c_int, C.c_int]
     lib.kb_dbg_schur.argtypes = [C.c_int, vp, C.c_int, vp, vp, vp, vp]
     for name in EXPORTS + ["kb_dbg_schur"]:
         if name != "kb_last_error":
             getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib
+
+
+def savetxt(path, X, part="real", append=False, nthreads=0):
+    """``np.savetxt(path, X.real | X.imag | X)`` with np.savetxt's default format, written by the
+    library's threaded formatter (kb_savetxt) straight from X's memory (any strides that are
+    multiples of 8 bytes; complex128 or float64; 1-D arrays are written as one column, like
+    np.savetxt does)."""
+    X = np.asarray(X)
+    if X.ndim == 1:
+        X = X.reshape(-1, 1)
+    if X.ndim != 2:
+        raise ValueError("savetxt expects a 1-D or 2-D array")
+    if np.iscomplexobj(X):
+        X = np.asarray(X, dtype=np.complex128)
+        base = X.real if part == "real" else X.imag  # strided float64 views, no copy
+    else:
+        base = np.asarray(X, dtype=np.float64)
+    if any(st % 8 for st in base.strides) or any(st < 0 for st in base.strides):
+        base = np.ascontiguousarray(base)
+    rows, cols = base.shape
+    rs, cs = (base.strides[0] // 8, base.strides[1] // 8) if base.size else (0, 0)
+    rc = load().kb_savetxt(os.fsencode(path), C.c_void_p(base.ctypes.data if base.size else 0), rows, cols, rs, cs,
+                           int(bool(append)), int(nthreads))
+    if rc != KB_OK:
+        raise KoreB200Error(rc, "kb_savetxt could not write %r" % (path,))
 
 
 def _ptr(a):

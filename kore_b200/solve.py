@@ -78,12 +78,13 @@ def field_slices(par, n):
 
 
 def write_fields(par, n, vec):
-    """One solution per column, np.savetxt default format (solve.py:283-306)."""
+    """One solution per column, np.savetxt default format (solve.py:283-306), written by the
+    library's threaded formatter (kb_savetxt: the same bytes, ~20x faster than np.savetxt, which
+    at the E = 1e-8 size would otherwise cost several times the solve itself)."""
+    from . import lib as _lib
     for name, a, b in field_slices(par, n):
-        with open("real_%s.field" % name, "wb") as f:
-            np.savetxt(f, np.real(vec[a:b, :]))
-        with open("imag_%s.field" % name, "wb") as f:
-            np.savetxt(f, np.imag(vec[a:b, :]))
+        _lib.savetxt("real_%s.field" % name, vec[a:b, :], "real")
+        _lib.savetxt("imag_%s.field" % name, vec[a:b, :], "imag")
 
 
 def main(argv=None, device=0):
@@ -128,8 +129,7 @@ def main(argv=None, device=0):
                 k[0, i] = E.getEigenpair(i, v)
                 vec[:, i] = v
             eigval = np.hstack([np.real(k).T, np.imag(k).T])
-            with open("eigenvalues0.dat", "wb") as f:
-                np.savetxt(f, eigval)
+            kb.savetxt("eigenvalues0.dat", eigval)
             write_fields(par, n, vec)
             success = nconv
         else:
