@@ -734,6 +734,7 @@ int kbi_factor(kb_context* h, zcomplex sigma) {
   const int64_t bmax = h->bmax;
   h->factored = false;
   h->M_transposed = false;
+  h->fold_ready = false;
   h->rng_valid = false;
   h->sigma = sigma;
   kbi_drop_graphs(h);
@@ -845,6 +846,7 @@ int kbi_factor(kb_context* h, zcomplex sigma) {
     for (int64_t p = 0; p < P; ++p) KB_TRY(factor_node(h, top, p, +1, p == 0, p + 1 < P));
   }
   KB_TRY(kbi_sweep_prepare(h));
+  if (h->opt_fold) KB_TRY(kbi_fold_prepare(h));
   KB_CUDA(h, cudaEventRecord(e1, s));
   int info = 0;
   KB_CUDA(h, cudaMemcpyAsync(&info, h->d_info.p, sizeof(int), cudaMemcpyDeviceToHost, s));

@@ -224,6 +224,14 @@ struct kb_context {
   unsigned k1_epoch = 0, k1_epoch1 = 0;
   DevBuf<int4> d_rng;         // coupling ranges per (CTA, step) of the one-hop sweep
   bool rng_valid = false;
+  // folded sweep (kb_sweep2.cu): FL_p = L M_p, FU_p = U M_p, step schedules, exchange ring
+  int opt_fold = 1;
+  bool fold_ready = false;
+  DevBuf<double2> d_fold;
+  DevBuf<int64_t> d_foldoff;
+  DevBuf<unsigned char> d_foldops, d_foldring;
+  int fold_npub[2] = {0, 0}, fold_nops[2] = {0, 0};
+  unsigned long long fold_epoch[2] = {0, 0};
   int64_t mid = 0;  // middle node of the two-sided elimination (P-1: one-sided)
   // ELL copies of the couplings + node tables for the persistent sweep kernel
   int WL = 0, WU = 0;
@@ -313,6 +321,10 @@ int kbi_sweep_dataflow(kb_context* h, const double2* r, double2* y);
 // ---- kb_sweep1.cu
 bool kbi_onehop_supported(const kb_context* h, int G, bool two_sided, int* slice_elems_out, size_t* smem_out);
 int kbi_sweep_onehop(kb_context* h, const double2* r, double2* y);
+// ---- kb_sweep2.cu
+bool kbi_fold_supported(const kb_context* h, int G, bool two_sided, int* slice_elems_out, size_t* smem_out);
+int kbi_fold_prepare(kb_context* h);
+int kbi_sweep_fold(kb_context* h, const double2* r, double2* y);
 // ---- kb_shard.cu
 int kbi_factor_sharded(kb_context* h, zcomplex sigma);
 int kbi_chain_solve_sharded(kb_context* h, const double2* r_dev, double2* x_dev, int refine);

@@ -99,6 +99,7 @@ extern "C" int kb_set_option(kb_handle h, int option, int64_t value) {
     case 6: h->opt_refine_eigs = (int)std::max<int64_t>(0, value); break;
     case 7: h->opt_sweep = (int)value; break;
     case 8: h->opt_factor = (int)value; break;
+    case 9: h->opt_fold = (int)value; break;
     default: return kb_fail(h, KB_EINVAL, "unknown option %d", option);
   }
   return KB_OK;

@@ -1,0 +1,606 @@
+// Folded chain sweep: the two-sided forward + backward block substitution of one solve in ONE
+// cooperative launch, split by ROWS, with a single one-way exchange of b values per chain step.
+//
+// Replaces the MUMPS solve phase inside every ST application of E.solve()
+// (/root/reference/bin/solve.py:123) and K.solve (solve.py:227).  Same algebra as kb_sweep1.cu,
+// rearranged so that the quantity that travels between the CTAs is the full input vector of the
+// next step and nothing else:
+//
+//     forward    t_0 = r_0,            t_{p'} = r_{p'} - (C_{p',p} M_p) t_p        p' = node after p
+//     middle     u_m = r_m - (L M_{m-1}) t_{m-1} - (U M_{m+1}) t_{m+1}
+//     backward   u_{p''} = t_{p''} - (C_{p'',p} M_p) u_p                          p'' = node before p
+//     solution   x_p = M_p u_p                                                     (no dependency)
+//
+// The products F = C M_p ("folded" couplings: FL_p = L_{p+1,p} M_p, FU_p = U_{p-1,p} M_p, dense,
+// row-major) are formed once per factorisation by kb_fold_couplings -- a banded-times-dense
+// product, 2 (2w+1) b^2 complex FMAs per node, bandwidth-bound.  In the sweep CTA c of a chain
+// group owns a row slice of every F: the slice arrives in shared memory by a 1-D bulk (TMA) copy
+// issued two steps ahead (L2 prefetch four steps ahead), the CTA forms its <= 10 entries of the
+// next vector with one warp per row and publishes them; every CTA of the group gathers the b
+// entries.  There is no sparse coupling phase, no partial-sum reduction across CTAs and the
+// solution x_p = M_p u_p is formed off the critical path, in the shadow of the next exchange,
+// straight from M_p^T in global memory.
+//
+// Exchange protocol: ONE hop.  An entry travels as a 32-byte element (re, tag, im, tag) written
+// with one 256-bit store and polled with 256-bit loads by its consumers; tag = solve epoch +
+// publication index, strictly increasing over the life of the handle, so a consumer can tell a
+// fresh entry from whatever the ring slot held before without any flag, counter, fence or reset.
+// Both 16-byte halves carry the tag: an entry is accepted only when both match, so the protocol
+// needs 16-byte single-copy atomicity only (what kb_sweep.cu relies on as well).  Against the
+// counter protocol of kb_sweep1.cu this removes the release fence behind 9.6 KB of partial sums,
+// the counter round trip and the separate read of the data.
+//
+// Traffic: every step reads one F (forward) or one F and M_p (backward): 3 x 16 sum b^2 bytes per
+// solve against 2 x for kb_sweep1.cu; the sweep is then bound by HBM instead of by the exchange.
+#include <stdlib.h>
+
+#include "kb_internal.cuh"
+
+#define K2_CW 10                       // chain warps: one row of the slice each
+#define K2_THREADS ((K2_CW + 1) * 32)  // + the service warp (bulk copies, L2 prefetch)
+#define K2_CT (K2_CW * 32)
+#define K2_RING 4
+#define K2_XR 10                       // most rows of a node a CTA may own
+
+struct alignas(32) K2Elem {
+  double re, tag0, im, tag1;
+};
+
+// One step of a group's schedule (built on the host, kbi_fold_prepare).
+struct K2Op {
+  long long mat_off;  // offset of F in the folded buffer (elements), -1: no product (last step)
+  int in_node;        // node whose vector (t or u) is the input; its length is the F column count
+  int out_node;       // node whose rows this step produces (-1: none)
+  int in_kind;        // 0: r of in_node; 1: own ring, publication `ia`; 2: xchg[0] + xchg[1]
+  int ia;
+  int base_kind;      // 0: none, 1: r, 2: saved t
+  int save;           // keep the output as the saved t of out_node
+  int pub;            // publication index of the output (-1: none)
+  int pubx;           // also publish into this group's cross-group buffer
+  int xnode;          // form x of this node from the input vector (-1: none)
+  int pad;
+};
+
+struct K2Params {
+  const double2* MT;
+  const int64_t* Moff;
+  const int64_t* nodeptr;
+  int P;
+  const double2* F;
+  const K2Op* ops[2];
+  int nops[2];
+  const double2* r;
+  double2* x;
+  double2* tsave;
+  K2Elem* ring[2];
+  K2Elem* xchg[2];
+  int RS;           // elements per CTA in a ring slot
+  double tag0[2];   // tag of publication -1 of each group in this solve
+  int* err;
+  long long* timing;
+  int bmax;
+  int G0;
+};
+
+__device__ __forceinline__ void k2_bar_chain() { asm volatile("bar.sync 1, %0;" ::"n"(K2_CT) : "memory"); }
+__device__ __forceinline__ void k2_bar_arrive() { asm volatile("bar.arrive 2, %0;" ::"n"(K2_THREADS) : "memory"); }
+__device__ __forceinline__ void k2_bar_wait() { asm volatile("bar.sync 2, %0;" ::"n"(K2_THREADS) : "memory"); }
+
+__device__ __forceinline__ void k2_publish(K2Elem* p, double2 v, double tag) {
+  asm volatile("st.relaxed.gpu.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(v.x), "d"(tag), "d"(v.y), "d"(tag)
+               : "memory");
+}
+
+__device__ __forceinline__ double2 k2_poll(const K2Elem* p, double tag, int* err) {
+  double re, t0, im, t1;
+  int spins = 0;
+  for (;;) {
+    asm volatile("ld.relaxed.gpu.global.v4.f64 {%0, %1, %2, %3}, [%4];"
+                 : "=d"(re), "=d"(t0), "=d"(im), "=d"(t1)
+                 : "l"(p)
+                 : "memory");
+    if (t0 == tag && t1 == tag) break;
+    if ((++spins & 255) == 0 && (*(volatile int*)err != 0 || spins > KB_SPIN_LIMIT)) {
+      atomicExch(err, 1);
+      break;
+    }
+  }
+  return zmake(re, im);
+}
+
+// owner CTA and local index of entry e of a b-row node split over `size` CTAs (inverse of
+// kb_group_rows)
+__device__ __forceinline__ void k2_owner(int b, int size, int e, int& c, int& li) {
+  const int base = b / size, rem = b - base * size;
+  const int cut = rem * (base + 1);
+  if (e < cut) {
+    c = e / (base + 1);
+    li = e - c * (base + 1);
+  } else {
+    const int e2 = e - cut;
+    c = rem + e2 / base;
+    li = e2 - (c - rem) * base;
+  }
+}
+
+__global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int slice_elems) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double2* stage0 = (double2*)smem_raw;
+  const int bpad = (q.bmax + 7) & ~7;
+  double2* vbuf = stage0 + 2 * (size_t)slice_elems;
+  double2* xred = vbuf + 2 * (size_t)bpad;  // K2_CW x K2_XR
+  int* s_nptr = (int*)(xred + K2_CW * K2_XR);
+  __shared__ __align__(8) uint64_t mbar[2];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int group = ((int)blockIdx.x < q.G0) ? 0 : 1;
+  const int gsz[2] = {q.G0, (int)gridDim.x - q.G0};
+  const int gsize = gsz[group];
+  const int grank = group == 0 ? (int)blockIdx.x : (int)blockIdx.x - q.G0;
+  const int S = q.nops[group];
+  const K2Op* ops = q.ops[group];
+  unsigned uses[2] = {0u, 0u};
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tc0 = clock64();
+#define K2_TICK(k)              \
+  do {                          \
+    if (q.timing) {             \
+      long long _t = clock64(); \
+      tacc[k] += _t - tc0;      \
+      tc0 = _t;                 \
+    }                           \
+  } while (0)
+
+  for (int i = tid; i <= q.P; i += K2_THREADS) s_nptr[i] = (int)q.nodeptr[i];
+  if (tid == 0) {
+    kb_mbar_init(&mbar[0], 1);
+    kb_mbar_init(&mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // this CTA's row slice of the F of step sn: where, how many bytes
+  auto slice_of = [&](int sn, const double2*& src, unsigned& bytes) {
+    bytes = 0;
+    src = nullptr;
+    if (sn >= S) return;
+    const long long mo = __ldg(&ops[sn].mat_off);
+    if (mo < 0) return;
+    const int inn = __ldg(&ops[sn].in_node), outn = __ldg(&ops[sn].out_node);
+    const int bi = s_nptr[inn + 1] - s_nptr[inn], bo = s_nptr[outn + 1] - s_nptr[outn];
+    int a0, a1;
+    kb_group_rows(bo, gsize, grank, a0, a1);
+    bytes = (unsigned)((size_t)(a1 - a0) * bi * sizeof(double2));
+    src = q.F + mo + (size_t)a0 * bi;
+  };
+
+  if (wid == K2_CW) {
+    // ===== service warp: stage refills behind the chain warps, L2 prefetch ahead of them =====
+    auto issue_copy = [&](int sn) {
+      const double2* src;
+      unsigned bytes;
+      slice_of(sn, src, bytes);
+      if (bytes) {
+        uint64_t* mb = &mbar[sn & 1];
+        kb_mbar_expect_tx(mb, bytes);
+        kb_bulk_g2s(stage0 + (size_t)(sn & 1) * slice_elems, src, bytes, mb);
+      }
+    };
+    auto prefetch = [&](int sn) {
+      const double2* src;
+      unsigned bytes;
+      slice_of(sn, src, bytes);
+      while (bytes > 0) {
+        const unsigned c = bytes > 65536u ? 65536u : bytes;
+        kb_prefetch_l2(src, c);
+        src = (const double2*)((const char*)src + c);
+        bytes -= c;
+      }
+    };
+    if (lane == 0) {
+      issue_copy(0);
+      issue_copy(1);
+    }
+    if (lane == 1) {
+      prefetch(2);
+      prefetch(3);
+    }
+    for (int s = 0; s < S; ++s) {
+      k2_bar_wait();  // the chain warps are done with the stage of step s
+      if (lane == 0) issue_copy(s + 2);
+      if (lane == 1) prefetch(s + 4);
+    }
+    return;
+  }
+
+  // ===== chain warps =====
+  K2Op op, nop;
+  nop = ops[0];
+  for (int s = 0; s < S; ++s) {
+    op = nop;
+    if (s + 1 < S) nop = ops[s + 1];
+    const int oi = s_nptr[op.in_node], bi = s_nptr[op.in_node + 1] - oi;
+    double2* v = vbuf + (size_t)(s & 1) * bpad;
+    K2_TICK(0);
+
+    // ---- 1. the input vector, all bi entries
+    if (op.in_kind == 0) {
+      for (int e = tid; e < bi; e += K2_CT) v[e] = q.r[oi + e];
+    } else if (op.in_kind == 1) {
+      const K2Elem* slot = q.ring[group] + (size_t)(op.ia % K2_RING) * gsize * q.RS;
+      const double tag = q.tag0[group] + (double)(op.ia + 1);
+      for (int e = tid; e < bi; e += K2_CT) {
+        int c, li;
+        k2_owner(bi, gsize, e, c, li);
+        v[e] = k2_poll(slot + (size_t)c * q.RS + li, tag, q.err);
+      }
+    } else {
+      // t of the middle node = group 0's part (r - F t, tag of its publication nops-independent:
+      // stored in the cross-group buffers with the tag of the solve) + group 1's part (-F t)
+      const double tagx0 = q.tag0[0] + 1.0, tagx1 = q.tag0[1] + 1.0;
+      for (int e = tid; e < bi; e += K2_CT) {
+        int c, li;
+        k2_owner(bi, gsz[0], e, c, li);
+        const double2 a = k2_poll(q.xchg[0] + (size_t)c * q.RS + li, tagx0, q.err);
+        k2_owner(bi, gsz[1], e, c, li);
+        const double2 b2 = k2_poll(q.xchg[1] + (size_t)c * q.RS + li, tagx1, q.err);
+        v[e] = zadd(a, b2);
+      }
+    }
+    k2_bar_chain();
+    K2_TICK(1);
+
+    // ---- 2. this CTA's rows of  base - F v, published
+    if (op.mat_off >= 0) {
+      const int oo = s_nptr[op.out_node], bo = s_nptr[op.out_node + 1] - oo;
+      int a0, a1;
+      kb_group_rows(bo, gsize, grank, a0, a1);
+      const int nr = a1 - a0;
+      if (nr > 0) {
+        kb_mbar_wait(&mbar[s & 1], uses[s & 1] & 1u);
+        uses[s & 1]++;
+        K2_TICK(2);
+        const double2* Fs = stage0 + (size_t)(s & 1) * slice_elems;
+        for (int li = wid; li < nr; li += K2_CW) {
+          const double2* row = Fs + (size_t)li * bi;
+          double2 acc0 = zmake(0.0, 0.0), acc1 = zmake(0.0, 0.0);
+          int j = lane;
+          for (; j + 32 < bi; j += 64) {
+            zfma(acc0, row[j], v[j]);
+            zfma(acc1, row[j + 32], v[j + 32]);
+          }
+          if (j < bi) zfma(acc0, row[j], v[j]);
+          acc0 = zadd(acc0, acc1);
+#pragma unroll
+          for (int sft = 16; sft > 0; sft >>= 1) {
+            acc0.x += __shfl_xor_sync(0xffffffffu, acc0.x, sft);
+            acc0.y += __shfl_xor_sync(0xffffffffu, acc0.y, sft);
+          }
+          if (lane == 0) {
+            const int gi = oo + a0 + li;
+            double2 base = zmake(0.0, 0.0);
+            if (op.base_kind == 1) base = q.r[gi];
+            if (op.base_kind == 2) base = __ldcg(&q.tsave[gi]);
+            const double2 out = zsub(base, acc0);
+            if (op.pub >= 0) {
+              const double tag = q.tag0[group] + (double)(op.pub + 1);
+              k2_publish(q.ring[group] + ((size_t)(op.pub % K2_RING) * gsize + grank) * q.RS + li, out, tag);
+            }
+            if (op.pubx) k2_publish(q.xchg[group] + (size_t)grank * q.RS + li, out, q.tag0[group] + 1.0);
+            if (op.save) __stcg(&q.tsave[gi], out);
+          }
+        }
+      }
+    }
+    K2_TICK(3);
+    k2_bar_arrive();  // the stage of step s may be refilled
+
+    // ---- 3. x of the input node's rows owned by this CTA: x = M v from M^T, in the shadow of
+    //         the exchange that feeds the next step
+    if (op.xnode >= 0) {
+      const int p = op.xnode;
+      const int b = bi;  // xnode == in_node
+      int x0, x1;
+      kb_group_rows(b, gsize, grank, x0, x1);
+      const int nx = x1 - x0;
+      if (nx > 0) {
+        const double2* MTp = q.MT + q.Moff[p] + x0;
+        double2 acc[K2_XR];
+#pragma unroll
+        for (int i = 0; i < K2_XR; ++i) acc[i] = zmake(0.0, 0.0);
+        for (int j = tid; j < b; j += K2_CT) {
+          const double2 uj = v[j];
+          const double2* seg = MTp + (size_t)j * b;
+          double2 m[K2_XR];
+#pragma unroll
+          for (int i = 0; i < K2_XR; ++i) m[i] = (i < nx) ? __ldcs(seg + i) : zmake(0.0, 0.0);
+#pragma unroll
+          for (int i = 0; i < K2_XR; ++i) zfma(acc[i], m[i], uj);
+        }
+#pragma unroll
+        for (int i = 0; i < K2_XR; ++i) {
+#pragma unroll
+          for (int sft = 16; sft > 0; sft >>= 1) {
+            acc[i].x += __shfl_xor_sync(0xffffffffu, acc[i].x, sft);
+            acc[i].y += __shfl_xor_sync(0xffffffffu, acc[i].y, sft);
+          }
+          if (lane == 0) xred[wid * K2_XR + i] = acc[i];
+        }
+      }
+      k2_bar_chain();
+      if (tid < nx) {
+        double2 sum = zmake(0.0, 0.0);
+#pragma unroll
+        for (int w = 0; w < K2_CW; ++w) sum = zadd(sum, xred[w * K2_XR + tid]);
+        q.x[oi + x0 + tid] = sum;
+      }
+    }
+    K2_TICK(4);
+  }
+  if (q.timing && tid == 0)
+    for (int k = 0; k < 8; ++k) q.timing[blockIdx.x * 8 + k] = tacc[k];
+#undef K2_TICK
+}
+
+// Folded couplings of every node:  FL_p = L_{p+1,p} M_p  (rows of node p+1)  and
+// FU_p = U_{p-1,p} M_p  (rows of node p-1), row-major, from the ELL copies of the couplings and
+// the transposed factors.  One CTA = 32 output rows (lane = row, so that for a fixed column of
+// F and coupling slot the warp reads consecutive entries of one row of M_p^T) x all columns in
+// tiles of 32, transposed through shared memory for the stores.
+__global__ void __launch_bounds__(256) kb_fold_couplings(int P, const int64_t* __restrict__ nodeptr,
+                                                         const int64_t* __restrict__ Moff,
+                                                         const double2* __restrict__ MT, const double2* __restrict__ Lval,
+                                                         const int* __restrict__ Lcol, int WL,
+                                                         const double2* __restrict__ Uval, const int* __restrict__ Ucol,
+                                                         int WU, const int64_t* __restrict__ FLoff,
+                                                         const int64_t* __restrict__ FUoff, double2* __restrict__ F) {
+  extern __shared__ __align__(16) unsigned char fold_smem[];
+  const int p = blockIdx.y, kind = blockIdx.z;  // kind 0: FL_p, 1: FU_p
+  const int pr = kind == 0 ? p + 1 : p - 1;     // node of the output rows
+  if (pr < 0 || pr >= P) return;
+  const int o = (int)nodeptr[p], b = (int)(nodeptr[p + 1] - nodeptr[p]);
+  const int orow = (int)nodeptr[pr], brow = (int)(nodeptr[pr + 1] - nodeptr[pr]);
+  const int i0 = blockIdx.x * 32;
+  if (i0 >= brow) return;
+  const int W = kind == 0 ? WL : WU;
+  const double2* val = kind == 0 ? Lval : Uval;
+  const int* col = kind == 0 ? Lcol : Ucol;
+  double2* out = F + (kind == 0 ? FLoff[p] : FUoff[p]);
+  const double2* Mp = MT + Moff[p];
+  double2* cv = (double2*)fold_smem;            // [W][32] coupling values of the 32 rows
+  int* cc = (int*)(cv + (size_t)W * 32);        // [W][32] local columns (-1: padding)
+  double2* tile = (double2*)(cc + (size_t)W * 32);  // [32 rows][33]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int e = threadIdx.x; e < W * 32; e += 256) {
+    const int k = e >> 5, i = e & 31;
+    double2 v = zmake(0.0, 0.0);
+    int c = -1;
+    if (i0 + i < brow) {
+      const size_t at = (size_t)(orow + i0 + i) * W + k;
+      const int gc = col[at] - o;
+      if (gc >= 0 && gc < b) {
+        c = gc;
+        v = val[at];
+      }
+    }
+    cv[e] = v;
+    cc[e] = c;
+  }
+  __syncthreads();
+  for (int j0 = 0; j0 < b; j0 += 32) {
+    // warp w forms columns j0 + w, j0 + w + 8, ... of the tile for the 32 rows (lane = row)
+    for (int jj = wid; jj < 32; jj += 8) {
+      const int j = j0 + jj;
+      double2 acc = zmake(0.0, 0.0);
+      if (j < b) {
+        const double2* mrow = Mp + (size_t)j * b;  // row j of M^T = column j of M
+        for (int k = 0; k < W; ++k) {
+          const int c = cc[k * 32 + lane];
+          if (c >= 0) zfma(acc, cv[k * 32 + lane], __ldg(mrow + c));
+        }
+      }
+      tile[lane * 33 + jj] = acc;
+    }
+    __syncthreads();
+    for (int ii = wid; ii < 32; ii += 8) {
+      const int i = i0 + ii, j = j0 + lane;
+      if (i < brow && j < b) out[(size_t)i * b + j] = tile[ii * 33 + lane];
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+bool kbi_fold_supported(const kb_context* h, int G, bool two_sided, int* slice_elems_out, size_t* smem_out) {
+  if (getenv("KB_NO_FOLD")) return false;
+  if (!h->M_transposed || G < 2 || h->P < 1) return false;
+  const int gmin = two_sided ? G / 2 : G;
+  if (gmin < 1) return false;
+  const int64_t rpc = (h->bmax + gmin - 1) / gmin;
+  if (rpc > K2_XR) return false;
+  const int64_t slice_elems = (rpc * h->bmax + 7) & ~(int64_t)7;
+  const size_t bpad = (size_t)((h->bmax + 7) & ~(int64_t)7);
+  const size_t smem = 2 * (size_t)slice_elems * sizeof(double2) + 2 * bpad * sizeof(double2) +
+                      (size_t)K2_CW * K2_XR * sizeof(double2) + (size_t)(h->P + 1) * sizeof(int) + 16;
+  if (smem > 220 * 1024) return false;
+  if (slice_elems_out) *slice_elems_out = (int)slice_elems;
+  if (smem_out) *smem_out = smem;
+  return true;
+}
+
+// Called at the end of kb_factor (after the ELL copies exist): folded couplings and the step
+// schedules of the two groups.  Not being able to allocate the folded buffer is not an error:
+// the solve then runs through kb_sweep1.cu.
+int kbi_fold_prepare(kb_context* h) {
+  h->fold_ready = false;
+  if (h->opt_sweep != 1 || h->nranks != 1) return KB_OK;
+  const int G = h->sweep_grid;
+  const int64_t P = h->P, mid = h->mid;
+  const bool two = mid < P - 1;
+  if (!kbi_fold_supported(h, G, two, nullptr, nullptr)) return KB_OK;
+  cudaStream_t s = h->stream;
+  // ---- folded buffer layout
+  std::vector<int64_t> FLoff(P, -1), FUoff(P, -1);
+  int64_t tot = 0;
+  auto bsz = [&](int64_t p) { return h->nodeptr[p + 1] - h->nodeptr[p]; };
+  for (int64_t p = 0; p < P; ++p) {
+    if (p + 1 < P) {
+      FLoff[p] = tot;
+      tot += bsz(p + 1) * bsz(p);
+    }
+    if (p > 0) {
+      FUoff[p] = tot;
+      tot += bsz(p - 1) * bsz(p);
+    }
+  }
+  if (h->d_fold.alloc((size_t)(tot > 0 ? tot : 1)) != cudaSuccess) {
+    cudaGetLastError();
+    return KB_OK;
+  }
+  KB_CUDA(h, h->d_foldoff.alloc(2 * P));
+  KB_CUDA(h, cudaMemcpyAsync(h->d_foldoff.p, FLoff.data(), P * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  KB_CUDA(h, cudaMemcpyAsync(h->d_foldoff.p + P, FUoff.data(), P * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  const int WL = h->WL > 0 ? h->WL : 1, WU = h->WU > 0 ? h->WU : 1;
+  const int Wm = WL > WU ? WL : WU;
+  const size_t fsm = (size_t)Wm * 32 * (sizeof(double2) + sizeof(int)) + 32 * 33 * sizeof(double2);
+  if (fsm > 200 * 1024) return KB_OK;
+  if (fsm > 48 * 1024)
+    KB_CUDA(h, cudaFuncSetAttribute((const void*)kb_fold_couplings, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)fsm));
+  dim3 grid((unsigned)((h->bmax + 31) / 32), (unsigned)P, 2);
+  kb_fold_couplings<<<grid, 256, fsm, s>>>((int)P, h->d_nodeptr.p, h->d_Moff.p, h->d_M.p, h->d_Lval.p, h->d_Lcol.p, WL,
+                                           h->d_Uval.p, h->d_Ucol.p, WU, h->d_foldoff.p, h->d_foldoff.p + P,
+                                           h->d_fold.p);
+  h->launches++;
+  KB_LAUNCH_CHECK(h);
+
+  // ---- step schedules
+  std::vector<K2Op> ops[2];
+  auto mk = [](long long mat, int in_node, int out_node, int in_kind, int ia, int base, int save, int pub, int pubx,
+               int xnode) {
+    K2Op o;
+    o.mat_off = mat;
+    o.in_node = in_node;
+    o.out_node = out_node;
+    o.in_kind = in_kind;
+    o.ia = ia;
+    o.base_kind = base;
+    o.save = save;
+    o.pub = pub;
+    o.pubx = pubx;
+    o.xnode = xnode;
+    o.pad = 0;
+    return o;
+  };
+  {
+    // group 0: nodes 0 .. mid downwards, then back up
+    int pub = 0;
+    for (int64_t p = 0; p < mid; ++p) {
+      const bool last = two && p == mid - 1;
+      ops[0].push_back(mk(FLoff[p], (int)p, (int)p + 1, p == 0 ? 0 : 1, pub - 1, 1, 1, pub, last ? 1 : 0, -1));
+      ++pub;
+    }
+    for (int64_t p = mid; p >= 1; --p) {
+      int kind = 1;
+      if (p == mid) kind = two ? 2 : (mid == 0 ? 0 : 1);
+      ops[0].push_back(mk(FUoff[p], (int)p, (int)p - 1, kind, pub - 1, p - 1 == 0 ? 1 : 2, 0, pub, 0, (int)p));
+      ++pub;
+    }
+    {
+      int kind = 1;
+      if (mid == 0) kind = two ? 2 : 0;
+      ops[0].push_back(mk(-1, 0, -1, kind, pub - 1, 0, 0, -1, 0, 0));
+    }
+    h->fold_npub[0] = pub;
+  }
+  if (two) {
+    // group 1: nodes P-1 .. mid+1 upwards, the middle node's input, then back down
+    int pub = 0;
+    for (int64_t p = P - 1; p > mid; --p) {
+      const bool tomid = p - 1 == mid;
+      ops[1].push_back(mk(FUoff[p], (int)p, (int)p - 1, p == P - 1 ? 0 : 1, pub - 1, tomid ? 0 : 1, tomid ? 0 : 1, pub,
+                          tomid ? 1 : 0, -1));
+      ++pub;
+    }
+    ops[1].push_back(mk(FLoff[mid], (int)mid, (int)mid + 1, 2, -1, mid + 1 == P - 1 ? 1 : 2, 0, pub, 0, -1));
+    ++pub;
+    for (int64_t p = mid + 1; p < P - 1; ++p) {
+      ops[1].push_back(mk(FLoff[p], (int)p, (int)p + 1, 1, pub - 1, p + 1 == P - 1 ? 1 : 2, 0, pub, 0, (int)p));
+      ++pub;
+    }
+    ops[1].push_back(mk(-1, (int)P - 1, -1, 1, pub - 1, 0, 0, -1, 0, (int)P - 1));
+    h->fold_npub[1] = pub;
+  } else {
+    h->fold_npub[1] = 0;
+  }
+  h->fold_nops[0] = (int)ops[0].size();
+  h->fold_nops[1] = (int)ops[1].size();
+  const size_t nall = ops[0].size() + ops[1].size();
+  KB_CUDA(h, h->d_foldops.alloc(nall * sizeof(K2Op)));
+  // pageable source: the copy is staged by the runtime before the call returns
+  KB_CUDA(h, cudaMemcpyAsync(h->d_foldops.p, ops[0].data(), ops[0].size() * sizeof(K2Op), cudaMemcpyHostToDevice, s));
+  if (!ops[1].empty())
+    KB_CUDA(h, cudaMemcpyAsync(h->d_foldops.p + ops[0].size() * sizeof(K2Op), ops[1].data(),
+                               ops[1].size() * sizeof(K2Op), cudaMemcpyHostToDevice, s));
+  h->fold_ready = true;
+  return KB_OK;
+}
+
+// y <- T'^{-1} r with the folded factors.  y has n+1 entries, y[n] == 0.
+int kbi_sweep_fold(kb_context* h, const double2* r, double2* y) {
+  cudaStream_t s = h->stream;
+  const int n = (int)h->n;
+  const int G = h->sweep_grid;
+  const bool two = h->mid < h->P - 1;
+  int slice_elems = 0;
+  size_t smem = 0;
+  if (!h->fold_ready || !kbi_fold_supported(h, G, two, &slice_elems, &smem))
+    return kb_fail(h, KB_EINVAL, "chain does not fit the folded sweep kernel");
+  const int G0 = two ? (G + 1) / 2 : G;
+  const int gmin = two ? G / 2 : G;
+  const int RS = (int)(((h->bmax + gmin - 1) / gmin + 3) & ~(int64_t)3);
+  const size_t ring_elems = (size_t)K2_RING * G * RS;  // both groups
+  const size_t xchg_elems = (size_t)G * RS;
+  const size_t need = (ring_elems + xchg_elems) * sizeof(K2Elem);
+  if (h->d_foldring.count < need) {
+    KB_CUDA(h, h->d_foldring.alloc(need));
+    KB_CUDA(h, cudaMemsetAsync(h->d_foldring.p, 0, need, s));  // tag 0 never matches: tags start at 1
+    h->fold_epoch[0] = h->fold_epoch[1] = 0;
+  }
+  if (h->d_yf.count < (size_t)n + 1) KB_CUDA(h, h->d_yf.alloc(n + 1));
+  K2Params q;
+  q.MT = h->d_M.p;
+  q.Moff = h->d_Moff.p;
+  q.nodeptr = h->d_nodeptr.p;
+  q.P = (int)h->P;
+  q.F = h->d_fold.p;
+  q.ops[0] = (const K2Op*)h->d_foldops.p;
+  q.ops[1] = (const K2Op*)h->d_foldops.p + h->fold_nops[0];
+  q.nops[0] = h->fold_nops[0];
+  q.nops[1] = h->fold_nops[1];
+  q.r = r;
+  q.x = y;
+  q.tsave = h->d_yf.p;
+  K2Elem* base = (K2Elem*)h->d_foldring.p;
+  q.ring[0] = base;
+  q.ring[1] = base + (size_t)K2_RING * G0 * RS;
+  q.xchg[0] = base + ring_elems;
+  q.xchg[1] = base + ring_elems + (size_t)G0 * RS;
+  q.RS = RS;
+  // publication i of a group carries tag0 + i + 1; the cross-group entries carry tag0 + 1
+  q.tag0[0] = (double)h->fold_epoch[0];
+  q.tag0[1] = (double)h->fold_epoch[1];
+  h->fold_epoch[0] += (unsigned long long)h->fold_npub[0] + 1ull;
+  h->fold_epoch[1] += (unsigned long long)h->fold_npub[1] + 1ull;
+  q.err = h->d_sweep_err.p;
+  q.timing = h->d_sweep_timing.p;
+  q.bmax = (int)h->bmax;
+  q.G0 = G0;
+  const void* fn = (const void*)kb_sweep_fold;
+  if (smem > 48 * 1024) KB_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* args[] = {(void*)&q, (void*)&slice_elems};
+  KB_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(G), dim3(K2_THREADS), args, smem, s));
+  h->launches += 1;
+  return KB_OK;
+}

@@ -23,7 +23,7 @@ ERRNAMES = ["KB_OK", "KB_EINVAL", "KB_ENODEVICE", "KB_ECUDA", "KB_ENOMEM", "KB_E
 # SLEPc.EPS.Which as used at bin/solve.py:99-117
 WHICH = {"LM": 0, "SM": 1, "LR": 2, "SR": 3, "LI": 4, "SI": 5, "TM": 6, "TR": 7, "TI": 8}
 
-OPT_EQUILIBRATE, OPT_REFINE, OPT_PURIFY, OPT_SEED, OPT_PANEL, OPT_REFINE_EIGS, OPT_SWEEP, OPT_FACTOR = 1, 2, 3, 4, 5, 6, 7, 8
+OPT_EQUILIBRATE, OPT_REFINE, OPT_PURIFY, OPT_SEED, OPT_PANEL, OPT_REFINE_EIGS, OPT_SWEEP, OPT_FACTOR, OPT_FOLD = 1, 2, 3, 4, 5, 6, 7, 8, 9
 
 # every symbol include/kore_b200.h declares
 EXPORTS = [
