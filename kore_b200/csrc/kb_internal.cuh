@@ -227,7 +227,7 @@ struct kb_context {
   // folded sweep (kb_sweep2.cu): FL_p = L M_p, FU_p = U M_p, step schedules, exchange ring
   int opt_fold = 1;
   bool fold_ready = false;
-  DevBuf<double2> d_fold;
+  DevBuf<double2> d_fold, d_uvec;
   DevBuf<int64_t> d_foldoff;
   DevBuf<unsigned char> d_foldops, d_foldring;
   int fold_npub[2] = {0, 0}, fold_nops[2] = {0, 0};

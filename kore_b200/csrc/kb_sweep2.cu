@@ -14,12 +14,17 @@
 // The products F = C M_p ("folded" couplings: FL_p = L_{p+1,p} M_p, FU_p = U_{p-1,p} M_p, dense,
 // row-major) are formed once per factorisation by kb_fold_couplings -- a banded-times-dense
 // product, 2 (2w+1) b^2 complex FMAs per node, bandwidth-bound.  In the sweep CTA c of a chain
-// group owns a row slice of every F: the slice arrives in shared memory by a 1-D bulk (TMA) copy
-// issued two steps ahead (L2 prefetch four steps ahead), the CTA forms its <= 10 entries of the
-// next vector with one warp per row and publishes them; every CTA of the group gathers the b
-// entries.  There is no sparse coupling phase, no partial-sum reduction across CTAs and the
-// solution x_p = M_p u_p is formed off the critical path, in the shadow of the next exchange,
-// straight from M_p^T in global memory.
+// group owns a row slice (<= 10 rows) of every F.  Every element of F is used exactly once per
+// solve, so the slice goes from L2 (bulk-prefetched three steps ahead) straight into registers
+// -- two rows per warp, lane = column mod 32, issued before the step's exchange is awaited --
+// and shared memory carries only the gathered vector.  (Measured alternatives: a TMA-staged
+// copy of the slice with one row per warp reads slice and vector through the 128 B/clk
+// shared-memory port, 2.2 K cycles per step; all rows per thread and a column split over the
+// CTA needs 200 double shuffles per warp, 3.9 K.)  Lane 0 of a warp publishes its rows after one
+// shuffle tree; every CTA of the group gathers the b entries.  There is no sparse coupling phase and no partial-sum reduction across CTAs.  The
+// solution x_p = M_p u_p has no dependency between nodes: the backward steps leave u in global
+// memory and kb_fold_solution forms all P products afterwards at full HBM bandwidth (lanes along
+// the rows of M_p^T, fully coalesced).
 //
 // Exchange protocol: ONE hop.  An entry travels as a 32-byte element (re, tag, im, tag) written
 // with one 256-bit store and polled with 256-bit loads by its consumers; tag = solve epoch +
@@ -30,17 +35,21 @@
 // counter protocol of kb_sweep1.cu this removes the release fence behind 9.6 KB of partial sums,
 // the counter round trip and the separate read of the data.
 //
-// Traffic: every step reads one F (forward) or one F and M_p (backward): 3 x 16 sum b^2 bytes per
-// solve against 2 x for kb_sweep1.cu; the sweep is then bound by HBM instead of by the exchange.
+// Traffic: the chain reads one F per step (2 x 16 sum b^2 bytes per solve, as kb_sweep1.cu reads
+// M_p twice) and the solution pass reads M_p once more: 3 x 16 sum b^2 in all, every byte of it
+// streamed at HBM rate instead of waiting on an exchange.
 #include <stdlib.h>
 
 #include "kb_internal.cuh"
 
-#define K2_CW 10                       // chain warps: one row of the slice each
-#define K2_THREADS ((K2_CW + 1) * 32)  // + the service warp (bulk copies, L2 prefetch)
-#define K2_CT (K2_CW * 32)
-#define K2_RING 4
-#define K2_XR 10                       // most rows of a node a CTA may own
+#define K2_CW 8                  // warps: K2_RW row warps + gather warps
+#define K2_RW 6
+#define K2_THREADS (K2_CW * 32)
+#define K2_CPL 20                // columns of a row per lane: nodes up to 32 * K2_CPL = 640 wide
+#define K2_PPT 10                // entries of the input vector polled per gather thread (640 / 64)
+#define K2_RING 4                // publication ring slots (power of two)
+#define K2_XR 10                 // most rows of a node a CTA may own: warps 0-3 take two, 4-5 one
+#define K2_AHEAD 4               // L2 prefetch distance, in steps
 
 struct alignas(32) K2Elem {
   double re, tag0, im, tag1;
@@ -54,10 +63,10 @@ struct K2Op {
   int in_kind;        // 0: r of in_node; 1: own ring, publication `ia`; 2: xchg[0] + xchg[1]
   int ia;
   int base_kind;      // 0: none, 1: r, 2: saved t
-  int save;           // keep the output as the saved t of out_node
+  int save;           // 1: keep the output as the saved t of out_node, 2: as u of out_node
   int pub;            // publication index of the output (-1: none)
   int pubx;           // also publish into this group's cross-group buffer
-  int xnode;          // form x of this node from the input vector (-1: none)
+  int xnode;          // the input vector is u of this node: keep this CTA's rows of it (-1: no)
   int pad;
 };
 
@@ -70,7 +79,7 @@ struct K2Params {
   const K2Op* ops[2];
   int nops[2];
   const double2* r;
-  double2* x;
+  double2* uvec;
   double2* tsave;
   K2Elem* ring[2];
   K2Elem* xchg[2];
@@ -81,10 +90,6 @@ struct K2Params {
   int bmax;
   int G0;
 };
-
-__device__ __forceinline__ void k2_bar_chain() { asm volatile("bar.sync 1, %0;" ::"n"(K2_CT) : "memory"); }
-__device__ __forceinline__ void k2_bar_arrive() { asm volatile("bar.arrive 2, %0;" ::"n"(K2_THREADS) : "memory"); }
-__device__ __forceinline__ void k2_bar_wait() { asm volatile("bar.sync 2, %0;" ::"n"(K2_THREADS) : "memory"); }
 
 __device__ __forceinline__ void k2_publish(K2Elem* p, double2 v, double tag) {
   asm volatile("st.relaxed.gpu.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(v.x), "d"(tag), "d"(v.y), "d"(tag)
@@ -100,6 +105,9 @@ __device__ __forceinline__ double2 k2_poll(const K2Elem* p, double tag, int* err
                  : "l"(p)
                  : "memory");
     if (t0 == tag && t1 == tag) break;
+#if defined(K2_EXP) && (K2_EXP & 2)
+    break;  // timing experiment: do not wait for the producers
+#endif
     if ((++spins & 255) == 0 && (*(volatile int*)err != 0 || spins > KB_SPIN_LIMIT)) {
       atomicExch(err, 1);
       break;
@@ -123,13 +131,18 @@ __device__ __forceinline__ void k2_owner(int b, int size, int e, int& c, int& li
   }
 }
 
+// named barriers: 2 = row warps only (their rows of the slice are in registers: the stage may
+// be refilled); 3 = gather warps arrive / row warps wait (the input vector is in shared memory)
+__device__ __forceinline__ void k2_bar_rows() { asm volatile("bar.sync 2, %0;" ::"n"(K2_RW * 32) : "memory"); }
+__device__ __forceinline__ void k2_bar_vec_arrive() { asm volatile("bar.arrive 3, %0;" ::"n"(K2_THREADS) : "memory"); }
+__device__ __forceinline__ void k2_bar_vec_wait() { asm volatile("bar.sync 3, %0;" ::"n"(K2_THREADS) : "memory"); }
+
 __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int slice_elems) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double2* stage0 = (double2*)smem_raw;
+  double2* stage0 = (double2*)smem_raw;                  // 2 stages of this CTA's row slice of F
   const int bpad = (q.bmax + 7) & ~7;
-  double2* vbuf = stage0 + 2 * (size_t)slice_elems;
-  double2* xred = vbuf + 2 * (size_t)bpad;  // K2_CW x K2_XR
-  int* s_nptr = (int*)(xred + K2_CW * K2_XR);
+  double2* vbuf = stage0 + 2 * (size_t)slice_elems;      // 2 x bpad: input vector, by step parity
+  int* s_nptr = (int*)(vbuf + 2 * (size_t)bpad);
   __shared__ __align__(8) uint64_t mbar[2];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int group = ((int)blockIdx.x < q.G0) ? 0 : 1;
@@ -138,7 +151,6 @@ __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int s
   const int grank = group == 0 ? (int)blockIdx.x : (int)blockIdx.x - q.G0;
   const int S = q.nops[group];
   const K2Op* ops = q.ops[group];
-  unsigned uses[2] = {0u, 0u};
   long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long tc0 = clock64();
 #define K2_TICK(k)              \
@@ -158,7 +170,93 @@ __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int s
   }
   __syncthreads();
 
-  // this CTA's row slice of the F of step sn: where, how many bytes
+  if (wid >= K2_RW) {
+    // ===== gather warps: poll the producers of every step's input vector =====
+    // They hold no rows, so all of a thread's entries (<= K2_PPT) are in flight together: one
+    // L2 round trip per attempt.  They run ahead of the row warps by construction: an entry of
+    // step s+1 exists only after every row warp of the group is done with step s.
+    const int pt = tid - K2_RW * 32;
+    constexpr int NP = (K2_CW - K2_RW) * 32;
+    int c_bi = -1, c_off[K2_PPT];
+    K2Op op, nop;
+    nop = ops[0];
+    for (int s = 0; s < S; ++s) {
+      op = nop;
+      if (s + 1 < S) nop = ops[s + 1];
+      const int oi = s_nptr[op.in_node], bi = s_nptr[op.in_node + 1] - oi;
+      double2* v = vbuf + (size_t)(s & 1) * bpad;
+      if (op.in_kind == 0) {
+        for (int e = pt; e < bi; e += NP) v[e] = q.r[oi + e];
+      } else if (op.in_kind == 1) {
+        const K2Elem* slot = q.ring[group] + (size_t)(op.ia & (K2_RING - 1)) * gsize * q.RS;
+        const double tag = q.tag0[group] + (double)(op.ia + 1);
+        if (c_bi != bi) {  // owner of each of this thread's entries: divisions, once per node size
+          c_bi = bi;
+#pragma unroll
+          for (int k = 0; k < K2_PPT; ++k) {
+            const int e = pt + k * NP;
+            int c = 0, li = 0;
+            if (e < bi) k2_owner(bi, gsize, e, c, li);
+            c_off[k] = c * q.RS + li;
+          }
+        }
+        unsigned pend = 0u;
+#pragma unroll
+        for (int k = 0; k < K2_PPT; ++k)
+          if (pt + k * NP < bi) pend |= 1u << k;
+        int spins = 0;
+        while (pend) {
+          double re[K2_PPT], t0[K2_PPT], im[K2_PPT], t1[K2_PPT];
+#pragma unroll
+          for (int k = 0; k < K2_PPT; ++k)
+            if (pend & (1u << k))
+              asm volatile("ld.relaxed.gpu.global.v4.f64 {%0, %1, %2, %3}, [%4];"
+                           : "=d"(re[k]), "=d"(t0[k]), "=d"(im[k]), "=d"(t1[k])
+                           : "l"(slot + c_off[k])
+                           : "memory");
+#pragma unroll
+          for (int k = 0; k < K2_PPT; ++k)
+            if ((pend & (1u << k)) && t0[k] == tag && t1[k] == tag) {
+              v[pt + k * NP] = zmake(re[k], im[k]);
+              pend &= ~(1u << k);
+            }
+#if defined(K2_EXP) && (K2_EXP & 2)
+          break;  // timing experiment: do not wait for the producers
+#endif
+          if ((++spins & 255) == 0 && (*(volatile int*)q.err != 0 || spins > KB_SPIN_LIMIT)) {
+            atomicExch(q.err, 1);
+            break;
+          }
+        }
+      } else {
+        // t of the middle node = group 0's part (r - F t) + group 1's part (-F t), both in the
+        // cross-group buffers under the first tag of the solve
+        const double tagx0 = q.tag0[0] + 1.0, tagx1 = q.tag0[1] + 1.0;
+        for (int e = pt; e < bi; e += NP) {
+          int c, li;
+          k2_owner(bi, gsz[0], e, c, li);
+          const double2 a = k2_poll(q.xchg[0] + (size_t)c * q.RS + li, tagx0, q.err);
+          k2_owner(bi, gsz[1], e, c, li);
+          const double2 b2 = k2_poll(q.xchg[1] + (size_t)c * q.RS + li, tagx1, q.err);
+          v[e] = zadd(a, b2);
+        }
+      }
+      if (op.xnode >= 0) {
+        // u of the middle node (assembled from both chains by every CTA): keep own rows
+        asm volatile("bar.sync 4, %0;" ::"n"(NP) : "memory");
+        int x0, x1;
+        kb_group_rows(bi, gsize, grank, x0, x1);
+        for (int e = x0 + pt; e < x1; e += NP) q.uvec[oi + e] = v[e];
+      }
+      __threadfence_block();
+      k2_bar_vec_arrive();
+    }
+    return;
+  }
+
+  // ===== row warps =====
+  // rows 2w, 2w+1 of the slice belong to warp w < 4, rows 8 and 9 to warps 4 and 5: every
+  // scheduler gets at most three rows
   auto slice_of = [&](int sn, const double2*& src, unsigned& bytes) {
     bytes = 0;
     src = nullptr;
@@ -172,169 +270,147 @@ __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int s
     bytes = (unsigned)((size_t)(a1 - a0) * bi * sizeof(double2));
     src = q.F + mo + (size_t)a0 * bi;
   };
-
-  if (wid == K2_CW) {
-    // ===== service warp: stage refills behind the chain warps, L2 prefetch ahead of them =====
-    auto issue_copy = [&](int sn) {
-      const double2* src;
-      unsigned bytes;
-      slice_of(sn, src, bytes);
-      if (bytes) {
-        uint64_t* mb = &mbar[sn & 1];
-        kb_mbar_expect_tx(mb, bytes);
-        kb_bulk_g2s(stage0 + (size_t)(sn & 1) * slice_elems, src, bytes, mb);
-      }
-    };
-    auto prefetch = [&](int sn) {
-      const double2* src;
-      unsigned bytes;
-      slice_of(sn, src, bytes);
-      while (bytes > 0) {
-        const unsigned c = bytes > 65536u ? 65536u : bytes;
-        kb_prefetch_l2(src, c);
-        src = (const double2*)((const char*)src + c);
-        bytes -= c;
-      }
-    };
-    if (lane == 0) {
-      issue_copy(0);
-      issue_copy(1);
+  auto issue_copy = [&](int sn) {
+    const double2* src;
+    unsigned bytes;
+    slice_of(sn, src, bytes);
+    if (bytes) {
+      uint64_t* mb = &mbar[sn & 1];
+      kb_mbar_expect_tx(mb, bytes);
+      kb_bulk_g2s(stage0 + (size_t)(sn & 1) * slice_elems, src, bytes, mb);
     }
-    if (lane == 1) {
-      prefetch(2);
-      prefetch(3);
+  };
+  auto prefetch = [&](int sn) {
+    const double2* src;
+    unsigned bytes;
+    slice_of(sn, src, bytes);
+    while (bytes > 0) {
+      const unsigned c = bytes > 65536u ? 65536u : bytes;
+      kb_prefetch_l2(src, c);
+      src = (const double2*)((const char*)src + c);
+      bytes -= c;
     }
-    for (int s = 0; s < S; ++s) {
-      k2_bar_wait();  // the chain warps are done with the stage of step s
-      if (lane == 0) issue_copy(s + 2);
-      if (lane == 1) prefetch(s + 4);
-    }
-    return;
+  };
+  if (tid == 0) {
+    issue_copy(0);
+    issue_copy(1);
   }
+  if (tid == 1)
+    for (int sn = 2; sn < K2_AHEAD; ++sn) prefetch(sn);
 
-  // ===== chain warps =====
+  unsigned uses0 = 0u, uses1 = 0u;  // fills of each stage consumed so far (mbarrier parity)
+  int c_bo = -1, c_a0 = 0, c_nr = 0;  // this CTA's rows of a bo-row node (division cached)
+  const int row0 = wid < 4 ? 2 * wid : wid + 4;
+  const int nrow = wid < 4 ? 2 : 1;
+
   K2Op op, nop;
   nop = ops[0];
   for (int s = 0; s < S; ++s) {
     op = nop;
     if (s + 1 < S) nop = ops[s + 1];
     const int oi = s_nptr[op.in_node], bi = s_nptr[op.in_node + 1] - oi;
-    double2* v = vbuf + (size_t)(s & 1) * bpad;
+    const double2* v = vbuf + (size_t)(s & 1) * bpad;
+
+    // ---- 0. everything that does not depend on the exchange, in the shadow of its flight:
+    //         this warp's rows of F from the staged slice into registers (after which the stage
+    //         is free for the slice of step s+2), the base values
+    int oo = 0, a0 = 0, nr = 0;
+    double2 f[2][K2_CPL];
+    double2 base[2] = {zmake(0.0, 0.0), zmake(0.0, 0.0)};
+    if (op.mat_off >= 0) {
+      oo = s_nptr[op.out_node];
+      const int bo = s_nptr[op.out_node + 1] - oo;
+      if (bo != c_bo) {
+        int a1;
+        kb_group_rows(bo, gsize, grank, c_a0, a1);
+        c_nr = a1 - c_a0;
+        c_bo = bo;
+      }
+      a0 = c_a0;
+      nr = c_nr;
+      if (nr > 0) {
+        if (s & 1) {
+          kb_mbar_wait(&mbar[1], uses1 & 1u);
+          uses1++;
+        } else {
+          kb_mbar_wait(&mbar[0], uses0 & 1u);
+          uses0++;
+        }
+        const double2* Fs = stage0 + (size_t)(s & 1) * slice_elems + (size_t)row0 * bi + lane;
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const bool rok = rr < nrow && row0 + rr < nr;
+#pragma unroll
+          for (int k = 0; k < K2_CPL; ++k)
+            f[rr][k] = (rok && lane + 32 * k < bi) ? Fs[(size_t)rr * bi + 32 * k] : zmake(0.0, 0.0);
+          if (rok && lane == 0) {
+            if (op.base_kind == 1) base[rr] = q.r[oo + a0 + row0 + rr];
+            if (op.base_kind == 2) base[rr] = __ldcg(&q.tsave[oo + a0 + row0 + rr]);
+          }
+        }
+      }
+    }
+    k2_bar_rows();  // every row warp holds its rows: the stage of step s may be refilled
+    if (tid == 0) issue_copy(s + 2);
+    if (tid == 1) prefetch(s + K2_AHEAD);
     K2_TICK(0);
 
-    // ---- 1. the input vector, all bi entries
-    if (op.in_kind == 0) {
-      for (int e = tid; e < bi; e += K2_CT) v[e] = q.r[oi + e];
-    } else if (op.in_kind == 1) {
-      const K2Elem* slot = q.ring[group] + (size_t)(op.ia % K2_RING) * gsize * q.RS;
-      const double tag = q.tag0[group] + (double)(op.ia + 1);
-      for (int e = tid; e < bi; e += K2_CT) {
-        int c, li;
-        k2_owner(bi, gsize, e, c, li);
-        v[e] = k2_poll(slot + (size_t)c * q.RS + li, tag, q.err);
-      }
-    } else {
-      // t of the middle node = group 0's part (r - F t, tag of its publication nops-independent:
-      // stored in the cross-group buffers with the tag of the solve) + group 1's part (-F t)
-      const double tagx0 = q.tag0[0] + 1.0, tagx1 = q.tag0[1] + 1.0;
-      for (int e = tid; e < bi; e += K2_CT) {
-        int c, li;
-        k2_owner(bi, gsz[0], e, c, li);
-        const double2 a = k2_poll(q.xchg[0] + (size_t)c * q.RS + li, tagx0, q.err);
-        k2_owner(bi, gsz[1], e, c, li);
-        const double2 b2 = k2_poll(q.xchg[1] + (size_t)c * q.RS + li, tagx1, q.err);
-        v[e] = zadd(a, b2);
-      }
-    }
-    k2_bar_chain();
+    // ---- 1. the input vector (gather warps)
+    k2_bar_vec_wait();
     K2_TICK(1);
 
-    // ---- 2. this CTA's rows of  base - F v, published
-    if (op.mat_off >= 0) {
-      const int oo = s_nptr[op.out_node], bo = s_nptr[op.out_node + 1] - oo;
-      int a0, a1;
-      kb_group_rows(bo, gsize, grank, a0, a1);
-      const int nr = a1 - a0;
-      if (nr > 0) {
-        kb_mbar_wait(&mbar[s & 1], uses[s & 1] & 1u);
-        uses[s & 1]++;
-        K2_TICK(2);
-        const double2* Fs = stage0 + (size_t)(s & 1) * slice_elems;
-        for (int li = wid; li < nr; li += K2_CW) {
-          const double2* row = Fs + (size_t)li * bi;
-          double2 acc0 = zmake(0.0, 0.0), acc1 = zmake(0.0, 0.0);
-          int j = lane;
-          for (; j + 32 < bi; j += 64) {
-            zfma(acc0, row[j], v[j]);
-            zfma(acc1, row[j + 32], v[j + 32]);
-          }
-          if (j < bi) zfma(acc0, row[j], v[j]);
-          acc0 = zadd(acc0, acc1);
+    // ---- 2. this warp's rows of  base - F v
+    if (op.mat_off >= 0 && row0 < nr) {
+      double2 acc[2][2];
 #pragma unroll
-          for (int sft = 16; sft > 0; sft >>= 1) {
-            acc0.x += __shfl_xor_sync(0xffffffffu, acc0.x, sft);
-            acc0.y += __shfl_xor_sync(0xffffffffu, acc0.y, sft);
-          }
-          if (lane == 0) {
-            const int gi = oo + a0 + li;
-            double2 base = zmake(0.0, 0.0);
-            if (op.base_kind == 1) base = q.r[gi];
-            if (op.base_kind == 2) base = __ldcg(&q.tsave[gi]);
-            const double2 out = zsub(base, acc0);
-            if (op.pub >= 0) {
-              const double tag = q.tag0[group] + (double)(op.pub + 1);
-              k2_publish(q.ring[group] + ((size_t)(op.pub % K2_RING) * gsize + grank) * q.RS + li, out, tag);
-            }
-            if (op.pubx) k2_publish(q.xchg[group] + (size_t)grank * q.RS + li, out, q.tag0[group] + 1.0);
-            if (op.save) __stcg(&q.tsave[gi], out);
-          }
-        }
+      for (int rr = 0; rr < 2; ++rr) acc[rr][0] = acc[rr][1] = zmake(0.0, 0.0);
+#if defined(K2_EXP) && (K2_EXP & 1)
+      // timing experiment: no products
+#pragma unroll
+      for (int k = 0; k < K2_CPL; ++k) {
+        acc[0][k & 1] = zadd(acc[0][k & 1], f[0][k]);
+        acc[1][k & 1] = zadd(acc[1][k & 1], f[1][k]);
       }
+      acc[0][0] = zadd(acc[0][0], v[lane]);
+#else
+#pragma unroll
+      for (int k = 0; k < K2_CPL; ++k) {
+        const int j = lane + 32 * k;
+        const double2 vj = j < bi ? v[j] : zmake(0.0, 0.0);
+        zfma(acc[0][k & 1], f[0][k], vj);
+        zfma(acc[1][k & 1], f[1][k], vj);
+      }
+#endif
+      K2_TICK(2);
+      // packed shuffle tree: the halves of the warp swap rows first (lanes < 16 keep row 0,
+      // lanes >= 16 row 1), then four stages inside each half: 10 double shuffles instead of 20
+      double2 a0v = zadd(acc[0][0], acc[0][1]), a1v = zadd(acc[1][0], acc[1][1]);
+      const bool hi = lane >= 16;
+      double2 keep = hi ? a1v : a0v, give = hi ? a0v : a1v;
+      keep.x += __shfl_xor_sync(0xffffffffu, give.x, 16);
+      keep.y += __shfl_xor_sync(0xffffffffu, give.y, 16);
+#pragma unroll
+      for (int sft = 8; sft > 0; sft >>= 1) {
+        keep.x += __shfl_xor_sync(0xffffffffu, keep.x, sft);
+        keep.y += __shfl_xor_sync(0xffffffffu, keep.y, sft);
+      }
+      const int rr = hi ? 1 : 0;
+      const int li = row0 + rr;
+      const double bx = __shfl_sync(0xffffffffu, base[1].x, 0), by = __shfl_sync(0xffffffffu, base[1].y, 0);
+      if ((lane & 15) == 0 && rr < nrow && li < nr) {
+        const int gi = oo + a0 + li;
+        const double2 bs = hi ? zmake(bx, by) : base[0];
+        const double2 out = zsub(bs, keep);
+        if (op.pub >= 0) {
+          const double tag = q.tag0[group] + (double)(op.pub + 1);
+          k2_publish(q.ring[group] + ((size_t)(op.pub & (K2_RING - 1)) * gsize + grank) * q.RS + li, out, tag);
+        }
+        if (op.pubx) k2_publish(q.xchg[group] + (size_t)grank * q.RS + li, out, q.tag0[group] + 1.0);
+        if (op.save == 1) __stcg(&q.tsave[gi], out);
+        if (op.save == 2) q.uvec[gi] = out;
+      }
+      K2_TICK(3);
     }
-    K2_TICK(3);
-    k2_bar_arrive();  // the stage of step s may be refilled
-
-    // ---- 3. x of the input node's rows owned by this CTA: x = M v from M^T, in the shadow of
-    //         the exchange that feeds the next step
-    if (op.xnode >= 0) {
-      const int p = op.xnode;
-      const int b = bi;  // xnode == in_node
-      int x0, x1;
-      kb_group_rows(b, gsize, grank, x0, x1);
-      const int nx = x1 - x0;
-      if (nx > 0) {
-        const double2* MTp = q.MT + q.Moff[p] + x0;
-        double2 acc[K2_XR];
-#pragma unroll
-        for (int i = 0; i < K2_XR; ++i) acc[i] = zmake(0.0, 0.0);
-        for (int j = tid; j < b; j += K2_CT) {
-          const double2 uj = v[j];
-          const double2* seg = MTp + (size_t)j * b;
-          double2 m[K2_XR];
-#pragma unroll
-          for (int i = 0; i < K2_XR; ++i) m[i] = (i < nx) ? __ldcs(seg + i) : zmake(0.0, 0.0);
-#pragma unroll
-          for (int i = 0; i < K2_XR; ++i) zfma(acc[i], m[i], uj);
-        }
-#pragma unroll
-        for (int i = 0; i < K2_XR; ++i) {
-#pragma unroll
-          for (int sft = 16; sft > 0; sft >>= 1) {
-            acc[i].x += __shfl_xor_sync(0xffffffffu, acc[i].x, sft);
-            acc[i].y += __shfl_xor_sync(0xffffffffu, acc[i].y, sft);
-          }
-          if (lane == 0) xred[wid * K2_XR + i] = acc[i];
-        }
-      }
-      k2_bar_chain();
-      if (tid < nx) {
-        double2 sum = zmake(0.0, 0.0);
-#pragma unroll
-        for (int w = 0; w < K2_CW; ++w) sum = zadd(sum, xred[w * K2_XR + tid]);
-        q.x[oi + x0 + tid] = sum;
-      }
-    }
-    K2_TICK(4);
   }
   if (q.timing && tid == 0)
     for (int k = 0; k < 8; ++k) q.timing[blockIdx.x * 8 + k] = tacc[k];
@@ -409,6 +485,50 @@ __global__ void __launch_bounds__(256) kb_fold_couplings(int P, const int64_t* _
   }
 }
 
+// x_p = M_p u_p for every node, from the transposed factors: x_i = sum_j M^T[j][i] u_j.  One CTA
+// = 32 consecutive rows i of one node (lane = row: a warp reads 512 contiguous bytes of a row
+// of M_p^T per j), the 8 warps split j, partial sums meet in shared memory.
+__global__ void __launch_bounds__(256) kb_fold_solution(const int64_t* __restrict__ nodeptr,
+                                                        const int64_t* __restrict__ Moff,
+                                                        const double2* __restrict__ MT, const double2* __restrict__ u,
+                                                        double2* __restrict__ x) {
+  extern __shared__ __align__(16) unsigned char xs_smem[];
+  double2* us = (double2*)xs_smem;  // b
+  __shared__ double2 part[8][32];
+  const int p = blockIdx.y;
+  const int o = (int)nodeptr[p], b = (int)(nodeptr[p + 1] - nodeptr[p]);
+  const int i0 = blockIdx.x * 32;
+  if (i0 >= b) return;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int j = threadIdx.x; j < b; j += 256) us[j] = u[o + j];
+  __syncthreads();
+  const int i = i0 + lane;
+  const double2* col = MT + Moff[p] + i;
+  double2 acc0 = zmake(0.0, 0.0), acc1 = zmake(0.0, 0.0);
+  if (i < b) {
+    int j = wid;
+    for (; j + 56 < b; j += 64) {
+      double2 m[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m[k] = __ldcs(col + (size_t)(j + 8 * k) * b);
+#pragma unroll
+      for (int k = 0; k < 8; k += 2) {
+        zfma(acc0, m[k], us[j + 8 * k]);
+        zfma(acc1, m[k + 1], us[j + 8 * k + 8]);
+      }
+    }
+    for (; j < b; j += 8) zfma(acc0, __ldcs(col + (size_t)j * b), us[j]);
+  }
+  part[wid][lane] = zadd(acc0, acc1);
+  __syncthreads();
+  if (wid == 0 && i < b) {
+    double2 sum = part[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) sum = zadd(sum, part[w][lane]);
+    x[o + i] = sum;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -418,11 +538,11 @@ bool kbi_fold_supported(const kb_context* h, int G, bool two_sided, int* slice_e
   const int gmin = two_sided ? G / 2 : G;
   if (gmin < 1) return false;
   const int64_t rpc = (h->bmax + gmin - 1) / gmin;
-  if (rpc > K2_XR) return false;
+  if (rpc > K2_XR || h->bmax > 32 * K2_CPL || h->bmax > K2_PPT * (K2_CW - K2_RW) * 32) return false;
   const int64_t slice_elems = (rpc * h->bmax + 7) & ~(int64_t)7;
   const size_t bpad = (size_t)((h->bmax + 7) & ~(int64_t)7);
   const size_t smem = 2 * (size_t)slice_elems * sizeof(double2) + 2 * bpad * sizeof(double2) +
-                      (size_t)K2_CW * K2_XR * sizeof(double2) + (size_t)(h->P + 1) * sizeof(int) + 16;
+                      (size_t)(h->P + 1) * sizeof(int) + 16;
   if (smem > 220 * 1024) return false;
   if (slice_elems_out) *slice_elems_out = (int)slice_elems;
   if (smem_out) *smem_out = smem;
@@ -504,14 +624,11 @@ int kbi_fold_prepare(kb_context* h) {
     for (int64_t p = mid; p >= 1; --p) {
       int kind = 1;
       if (p == mid) kind = two ? 2 : (mid == 0 ? 0 : 1);
-      ops[0].push_back(mk(FUoff[p], (int)p, (int)p - 1, kind, pub - 1, p - 1 == 0 ? 1 : 2, 0, pub, 0, (int)p));
+      ops[0].push_back(
+          mk(FUoff[p], (int)p, (int)p - 1, kind, pub - 1, p - 1 == 0 ? 1 : 2, 2, pub, 0, p == mid ? (int)p : -1));
       ++pub;
     }
-    {
-      int kind = 1;
-      if (mid == 0) kind = two ? 2 : 0;
-      ops[0].push_back(mk(-1, 0, -1, kind, pub - 1, 0, 0, -1, 0, 0));
-    }
+    if (mid == 0) ops[0].push_back(mk(-1, 0, -1, 0, -1, 0, 0, -1, 0, 0));  // single node: u_0 = r_0
     h->fold_npub[0] = pub;
   }
   if (two) {
@@ -523,13 +640,12 @@ int kbi_fold_prepare(kb_context* h) {
                           tomid ? 1 : 0, -1));
       ++pub;
     }
-    ops[1].push_back(mk(FLoff[mid], (int)mid, (int)mid + 1, 2, -1, mid + 1 == P - 1 ? 1 : 2, 0, pub, 0, -1));
+    ops[1].push_back(mk(FLoff[mid], (int)mid, (int)mid + 1, 2, -1, mid + 1 == P - 1 ? 1 : 2, 2, pub, 0, -1));
     ++pub;
     for (int64_t p = mid + 1; p < P - 1; ++p) {
-      ops[1].push_back(mk(FLoff[p], (int)p, (int)p + 1, 1, pub - 1, p + 1 == P - 1 ? 1 : 2, 0, pub, 0, (int)p));
+      ops[1].push_back(mk(FLoff[p], (int)p, (int)p + 1, 1, pub - 1, p + 1 == P - 1 ? 1 : 2, 2, pub, 0, -1));
       ++pub;
     }
-    ops[1].push_back(mk(-1, (int)P - 1, -1, 1, pub - 1, 0, 0, -1, 0, (int)P - 1));
     h->fold_npub[1] = pub;
   } else {
     h->fold_npub[1] = 0;
@@ -580,7 +696,8 @@ int kbi_sweep_fold(kb_context* h, const double2* r, double2* y) {
   q.nops[0] = h->fold_nops[0];
   q.nops[1] = h->fold_nops[1];
   q.r = r;
-  q.x = y;
+  KB_CUDA(h, h->d_uvec.alloc((size_t)n + 1));
+  q.uvec = h->d_uvec.p;
   q.tsave = h->d_yf.p;
   K2Elem* base = (K2Elem*)h->d_foldring.p;
   q.ring[0] = base;
@@ -601,6 +718,10 @@ int kbi_sweep_fold(kb_context* h, const double2* r, double2* y) {
   if (smem > 48 * 1024) KB_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* args[] = {(void*)&q, (void*)&slice_elems};
   KB_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(G), dim3(K2_THREADS), args, smem, s));
-  h->launches += 1;
+  dim3 xgrid((unsigned)((h->bmax + 31) / 32), (unsigned)h->P);
+  kb_fold_solution<<<xgrid, 256, (size_t)h->bmax * sizeof(double2), s>>>(h->d_nodeptr.p, h->d_Moff.p, h->d_M.p,
+                                                                        h->d_uvec.p, y);
+  h->launches += 2;
+  KB_LAUNCH_CHECK(h);
   return KB_OK;
 }
