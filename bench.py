@@ -41,8 +41,11 @@ sys.path.insert(0, ROOT)
 
 METRIC = "eigenpairs_per_s (shift-invert factor + Krylov-Schur, nev=10, complex128)"
 UNIT = "eigenpairs/s"
-# DRAM bytes of one kb_sweep_onehop launch at P = b = 600 (ncu --set full, profiles/)
-SWEEP_TRAFFIC_P600_B600 = 7.081519e9 + 0.831415e9  # dram__bytes_read.sum + dram__bytes_write.sum
+# DRAM bytes of one chain sweep at P = b = 600 = one kb_sweep_fold launch (6.912 GB read, 0.019 GB
+# written: the folded couplings FL/FU once each) + one kb_fold_solution launch (3.462 GB read,
+# 0.008 GB written: M_p once); dram__bytes_read.sum + dram__bytes_write.sum of the
+# `ncu --set full` capture profiles/r1c_ncu_full_fold_kernels_P600_b600.raw.csv
+SWEEP_TRAFFIC_P600_B600 = (6.912419e9 + 0.019201e9) + (3.461783e9 + 0.008198e9)
 
 
 def env_int(name, default):
@@ -362,14 +365,18 @@ def run_ours(args):
     per_sweep_ms = sweep_ms / max(1, sweeps)
     achieved = alg_bytes / (per_sweep_ms * 1e-3) / 1e9 if per_sweep_ms > 0 else 0.0
     roofline = {
-        "kernel": "kb_sweep_onehop (one cooperative launch = one two-sided fwd+bwd pass over all M_p^T)",
+        "kernel": "chain sweep = kb_sweep_fold (one cooperative launch: two-sided forward + backward "
+                  "recurrence on the folded couplings) + kb_fold_solution (x_p = M_p u_p, all nodes)",
         "bound": "hbm", "achieved": achieved, "peak": peak,
         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
         "unit": "GB/s", "frac": achieved / peak,
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed
-        # `ncu --set full` capture (profiles/r1_ncu_full_kb_sweep_onehop_P600_b600.raw.csv):
-        # the factors are read twice (forward and backward)
+        # measured DRAM bytes of one sweep (see SWEEP_TRAFFIC_P600_B600): 2.85 x the algorithmic
+        # bytes BY DESIGN -- FL_p, FU_p and M_p are each streamed once so that no chain step waits
+        # on a cross-CTA reduction; achieved / peak by actual traffic is
+        # `traffic_frac`
         "traffic": SWEEP_TRAFFIC_P600_B600 if (args.P == 600 and args.b == 600 and world == 1) else None,
+        "traffic_frac": (SWEEP_TRAFFIC_P600_B600 / (per_sweep_ms * 1e-3) / 1e9 / peak
+                         if (args.P == 600 and args.b == 600 and world == 1 and per_sweep_ms > 0) else None),
         "algorithmic_bytes_per_sweep": alg_bytes, "ms_per_sweep": per_sweep_ms,
         "sweep_share_of_step": sweep_ms / max(1e-9, float(np.sum(dev_ms))),
         "factor_share_of_step": factor_ms / max(1e-9, float(np.sum(dev_ms))),

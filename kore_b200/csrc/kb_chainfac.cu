@@ -63,6 +63,10 @@ struct KfParams {
   int G0;             // CTAs of group 0 (the rest form group 1)
   int stagger_ns;     // consumers other than the next owner hold their loads of G_k back by this much
   int transposed;     // store M_p^T (row j of the buffer = column j of M_p) for kb_sweep1.cu
+  // per-column stream of the elementary transforms to the owner of the NEXT strip: 32-byte
+  // tagged elements (re, tag, im, tag), [2 strip parities][KF_NB columns][bmax rows] per group;
+  // null: the next owner waits for the composite G_k like everybody else
+  double* Sbuf[2];
 };
 
 __device__ __forceinline__ unsigned kf_ld_acquire(const unsigned* p) {
@@ -113,6 +117,33 @@ __device__ __forceinline__ double kf_rcp(double d) {
   e = fma(-d, r, 1.0);
   r = fma(r, e, r);
   return r;
+}
+
+// Tagged element of the column stream: written with one 256-bit store, polled with 256-bit
+// loads.  tag = (running column number within the chain) * 1024 + (pivot row + 1): unique per
+// column of a factorisation (the buffer is zeroed before the launch), identical in both 16-byte
+// halves so that a torn read is never accepted, and it tells the reader the pivot row.
+__device__ __forceinline__ void kf_stream_put(double* p, double2 v, double tag) {
+  asm volatile("st.relaxed.gpu.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(v.x), "d"(tag), "d"(v.y), "d"(tag)
+               : "memory");
+}
+__device__ __forceinline__ double2 kf_stream_get(const double* p, double tagbase, int& piv, int* err) {
+  double re, t0, im, t1;
+  int spins = 0;
+  for (;;) {
+    asm volatile("ld.relaxed.gpu.global.v4.f64 {%0, %1, %2, %3}, [%4];"
+                 : "=d"(re), "=d"(t0), "=d"(im), "=d"(t1)
+                 : "l"(p)
+                 : "memory");
+    if (t0 == t1 && t0 >= tagbase && t0 < tagbase + 1024.0) break;
+    if ((++spins & 255) == 0 && (*(volatile int*)err != 0 || spins > KF_SPIN)) {
+      atomicExch(err, 1);
+      t0 = tagbase;
+      break;
+    }
+  }
+  piv = (int)(t0 - tagbase) - 1;
+  return zmake(re, im);
 }
 
 struct KfShared {
@@ -190,6 +221,7 @@ __global__ void __launch_bounds__(KF_MAXT, 1) kb_chain_factor(KfParams q) {
   int* pivbuf = q.pivbuf[group];
   const int ldg = q.bmax;
   unsigned pubbase = 0, barcount = 0;
+  long long colbase = 0;  // columns eliminated by this group before the current node
   long long tacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tc = clock64();
 #define KF_TICK(k)                \
@@ -266,6 +298,9 @@ __global__ void __launch_bounds__(KF_MAXT, 1) kb_chain_factor(KfParams q) {
           // elimination FMAs), so the winner publishes 1/pivot without a reciprocal on the
           // critical path.
           double rinv;
+          // column stream of this strip: slot of this row, tag of column 0 with pivot code 0
+          double* sput = q.Sbuf[group] ? q.Sbuf[group] + 4 * ((size_t)((k & 1) * KF_NB) * ldg + t) : nullptr;
+          const double stag = (double)((colbase + k0 + 1) * 1024);
           {
             const double m2 = zabs2(a[0]);
             const unsigned key = isfree ? (unsigned)__double2hiint(m2) + 1u : 0u;
@@ -306,6 +341,10 @@ __global__ void __launch_bounds__(KF_MAXT, 1) kb_chain_factor(KfParams q) {
               const double2* prow = sh.prow[par];
               const double2 pinv = broken ? zmake(0.0, 0.0) : prow[NB];
               const double2 g = (isp || broken) ? zmake(0.0, 0.0) : zmul(a[cc], pinv);
+              // the elementary transform of this column goes to the owner of the next strip right
+              // away (multiplier of this row, 1/pivot on the pivot row): it trails the panel by one
+              // L2 hop instead of waiting for the whole strip
+              if (sput && t < b) kf_stream_put(sput + 4 * (size_t)cc * ldg, isp ? pinv : g, stag + (double)(1024 * cc + rp + 1));
               // next column first, so that its pivot vote overlaps the rest of the elimination
               if (cc + 1 < NB) {
                 zfms(a[cc + 1], g, prow[cc + 1]);
@@ -333,7 +372,9 @@ __global__ void __launch_bounds__(KF_MAXT, 1) kb_chain_factor(KfParams q) {
             }
           }
           KF_TICK(8);
-          // publish G_k (the strip itself) and the pivots
+          // publish G_k (the strip itself) and the pivots -- only when the consumers apply the
+          // composite transform (no column stream)
+          if (!q.Sbuf[group]) {
           if (t < b) {
 #pragma unroll
             for (int j = 0; j < NB; ++j)
@@ -343,7 +384,69 @@ __global__ void __launch_bounds__(KF_MAXT, 1) kb_chain_factor(KfParams q) {
           if (t < 16) pivbuf[k * 16 + t] = (t < wk) ? sh.piv[t] : -1;
           __syncthreads();
           if (t == 0) kf_st_release(pub, pubbase + (unsigned)k + 1u);
+          }
           KF_TICK(1);
+        } else if (q.Sbuf[group]) {
+          // ================= consumer: apply step k column by column from the stream =========
+          //   A[i,:] <- A[i,:] - g_i A[piv,:]  (i != piv),   A[piv,:] <- A[piv,:] / pivot
+          // The owner of the next strip trails the panel by one L2 hop per column; everybody
+          // else finds the columns already there.  Polls go out three columns at a time, so a
+          // CTA that is catching up pays one round trip per three columns.
+          KF_TICK(2);
+          const double* sbase = q.Sbuf[group] + 4 * ((size_t)((k & 1) * KF_NB) * ldg + t);
+          const double tag0 = (double)((colbase + k0 + 1) * 1024);
+#pragma unroll
+          for (int c3 = 0; c3 < NB; c3 += 3) {
+            double re[3], t0[3], im[3], t1[3];
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+              re[u] = im[u] = 0.0;
+              t0[u] = t1[u] = -1.0;
+              if (c3 + u < wk && t < b)
+                asm volatile("ld.relaxed.gpu.global.v4.f64 {%0, %1, %2, %3}, [%4];"
+                             : "=d"(re[u]), "=d"(t0[u]), "=d"(im[u]), "=d"(t1[u])
+                             : "l"(sbase + 4 * (size_t)(c3 + u) * ldg)
+                             : "memory");
+            }
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+              const int cc = c3 + u;
+              if (cc < NB && cc < wk) {
+                const double tb = tag0 + 1024.0 * cc;
+                int rp = -1;
+                double2 sv = zmake(re[u], im[u]);
+                if (t < b) {
+                  if (t0[u] == t1[u] && t0[u] >= tb && t0[u] < tb + 1024.0)
+                    rp = (int)(t0[u] - tb) - 1;
+                  else
+                    sv = kf_stream_get(sbase + 4 * (size_t)cc * ldg, tb, rp, q.err);
+                }
+                const bool isp = (t < b) && (t == rp);
+                if (isp) {
+#pragma unroll
+                  for (int j = 0; j < NB; ++j) sh.prow[cc & 1][j] = a[j];
+                  s_orig[k0 + cc] = rp;
+                  isfree = false;
+                  mycol = k0 + cc;
+                }
+                if (t == 0 && rp < 0) s_orig[k0 + cc] = 0;  // skipped column (singular block)
+                KF_TICK(5);
+                __syncthreads();
+                KF_TICK(6);
+                if (t < b && rp >= 0) {
+                  const double2* prow = sh.prow[cc & 1];
+                  if (isp) {
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) a[j] = zmul(a[j], sv);
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) zfms(a[j], sv, prow[j]);
+                  }
+                }
+              }
+            }
+          }
+          KF_TICK(3);
         } else {
           // ================= consumer: apply step k to this strip =================
           //   A[i,:] <- (i is a pivot row of the step ? 0 : A[i,:]) + sum_c G[i,c] A[piv_c,:]
@@ -414,6 +517,7 @@ __global__ void __launch_bounds__(KF_MAXT, 1) kb_chain_factor(KfParams q) {
       }
     }
     pubbase += (unsigned)K;
+    colbase += b;
     barcount += (unsigned)Gc;
     kf_group_barrier(bar, barcount, q.err);
     KF_TICK(4);
@@ -498,6 +602,14 @@ int kbi_chainfac_run(kb_context* h, bool two_sided, bool transposed) {
   q.bmax = (int)bmax;
   q.G0 = two_sided ? (G + 1) / 2 : G;
   q.transposed = transposed ? 1 : 0;
+  q.Sbuf[0] = q.Sbuf[1] = nullptr;
+  if (!getenv("KB_CHAINFAC_NOSTREAM")) {
+    const size_t per = (size_t)2 * KF_NB * bmax * 4;  // doubles per group
+    KB_CUDA(h, h->d_kfstream.alloc((size_t)ngroups * per));
+    KB_CUDA(h, cudaMemsetAsync(h->d_kfstream.p, 0, (size_t)ngroups * per * sizeof(double), s));
+    q.Sbuf[0] = h->d_kfstream.p;
+    q.Sbuf[1] = two_sided ? h->d_kfstream.p + per : h->d_kfstream.p;
+  }
   q.stagger_ns = getenv("KB_CHAINFAC_STAGGER") ? atoi(getenv("KB_CHAINFAC_STAGGER")) : 1000;
   int T = (int)((bmax + 31) / 32) * 32;
   if (T < 64) T = 64;

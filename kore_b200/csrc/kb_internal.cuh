@@ -218,6 +218,7 @@ struct kb_context {
   DevBuf<double2> d_kfG;
   DevBuf<int> d_kfpiv;
   DevBuf<unsigned> d_kfsync;
+  DevBuf<double> d_kfstream;  // column stream to the next strip owner (tagged 32-byte elements)
   bool M_transposed = false;  // d_M holds M_p^T (strip kernel + one-hop sweep, kb_sweep1.cu)
   DevBuf<double2> d_ring;     // partial-product ring + exchange buffers of the one-hop sweep
   DevBuf<unsigned> d_k1flags; // publication flags of the one-hop sweep (one 256-byte line per CTA)

@@ -19,7 +19,7 @@ L.kb_dbg_factor_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
 g = L.kb_dbg_factor_timing(s.h, out.ctypes.data, 148)
 t = out[: g * 16].reshape(g, 16)
 print("P=%d b=%d factor %.2f ms (%.2f TF/s executed)" % (P, b, st["factor_ms"], st["factor_flops"] / st["factor_ms"] / 1e9))
-names = ["schur", "panel(rest)", "wait", "apply(fma)", "store+barrier", "-", "-", "-", "P:isp scale", "P:barrier1", "P:resolve,publish,bar2",
+names = ["schur", "panel(rest)", "wait", "apply(fma)", "store+barrier", "S:poll", "S:barrier", "-", "P:isp scale", "P:barrier1", "P:resolve,publish,bar2",
          "P:fma,vote", "A:loads", "A:publish rows", "A:barrier", "-"]
 nodes = (P + 1) // 2
 for k in range(16):
