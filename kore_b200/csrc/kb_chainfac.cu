@@ -340,14 +340,26 @@ __global__ void __launch_bounds__(KF_MAXT, 1) kb_chain_factor(KfParams q) {
               KF_TICK(10);
               const double2* prow = sh.prow[par];
               const double2 pinv = broken ? zmake(0.0, 0.0) : prow[NB];
-              const double2 g = (isp || broken) ? zmake(0.0, 0.0) : zmul(a[cc], pinv);
-              // the elementary transform of this column goes to the owner of the next strip right
-              // away (multiplier of this row, 1/pivot on the pivot row): it trails the panel by one
-              // L2 hop instead of waiting for the whole strip
-              if (sput && t < b) kf_stream_put(sput + 4 * (size_t)cc * ldg, isp ? pinv : g, stag + (double)(1024 * cc + rp + 1));
+              // One branch-free update for every row:  a[j] <- base + mult * prow[j]  with
+              //   ordinary row:  base = a[j], mult = -a[cc]/pivot          (elimination)
+              //   pivot row:     base = 0,    mult = 1/pivot, prow == a    (row / pivot)
+              // so the warp of the pivot row does not run a scaling pass of its own while the other
+              // nineteen wait at the next barrier (measured: 0.2 K cycles per column)
+              const double2 mult = broken ? zmake(0.0, 0.0) : (isp ? pinv : zneg(zmul(a[cc], pinv)));
+              // the elementary transform of this column goes to the other strips right away
+              // (multiplier of this row, 1/pivot on the pivot row): the owner of the next strip
+              // trails the panel by one L2 hop instead of waiting for the whole strip
+              if (sput && t < b)
+                kf_stream_put(sput + 4 * (size_t)cc * ldg, isp ? mult : zneg(mult), stag + (double)(1024 * cc + rp + 1));
+#define KF_UPD(j)                                          \
+  do {                                                     \
+    double2 _acc = isp ? zmake(0.0, 0.0) : a[j];           \
+    zfma(_acc, mult, prow[j]);                             \
+    a[j] = _acc;                                           \
+  } while (0)
               // next column first, so that its pivot vote overlaps the rest of the elimination
               if (cc + 1 < NB) {
-                zfms(a[cc + 1], g, prow[cc + 1]);
+                KF_UPD(cc + 1);
                 if (cc + 1 < wk) {
                   const double m2 = zabs2(a[cc + 1]);
                   const unsigned key = (isfree && !isp) ? (unsigned)__double2hiint(m2) + 1u : 0u;
@@ -359,12 +371,10 @@ __global__ void __launch_bounds__(KF_MAXT, 1) kb_chain_factor(KfParams q) {
               }
 #pragma unroll
               for (int j = 0; j < NB; ++j)
-                if (j != cc && j != cc + 1) zfms(a[j], g, prow[j]);
-              if (!broken) a[cc] = zneg(g);
+                if (j != cc && j != cc + 1) KF_UPD(j);
+#undef KF_UPD
+              if (!broken) a[cc] = mult;  // -g, or 1/pivot on the pivot row
               if (isp) {
-                // the pivot row itself: row / pivot, and 1 / pivot in the pivot column
-#pragma unroll
-                for (int j = 0; j < NB; ++j) a[j] = (j == cc) ? pinv : zmul(a[j], pinv);
                 isfree = false;
                 mycol = gk;
               }
