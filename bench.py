@@ -234,6 +234,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     distributed = world > 1
     if distributed:
+        # NCCL prints its version banner on STDOUT when NCCL_DEBUG=VERSION; rank 0's stdout must be
+        # the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():

@@ -593,6 +593,29 @@ bool kbi_onehop_supported(const kb_context* h, int G, bool two_sided, int* slice
   return true;
 }
 
+// Coupling ranges of every (CTA, step) for a grid of G CTAs, G0 of them in group 0 (built once per
+// factorisation; shared with kb_sweep3.cu, which splits the chain the same way).
+int kbi_onehop_build_ranges(kb_context* h, int G, int G0) {
+  if (h->rng_valid) return KB_OK;
+  K1Params q;
+  memset(&q, 0, sizeof(q));
+  q.nodeptr = h->d_nodeptr.p;
+  q.P = (int)h->P;
+  q.mid = (int)h->mid;
+  q.Lcol = h->d_Lcol.p;
+  q.WL = h->WL > 0 ? h->WL : 1;
+  q.Ucol = h->d_Ucol.p;
+  q.WU = h->WU > 0 ? h->WU : 1;
+  q.G0 = G0;
+  q.smax = (int)(2 * h->mid + 1);
+  KB_CUDA(h, h->d_rng.alloc((size_t)G * q.smax * 2));
+  kb_onehop_ranges<<<G, K1_THREADS, 0, h->stream>>>(q, h->d_rng.p);
+  h->rng_valid = true;
+  h->launches++;
+  KB_LAUNCH_CHECK(h);
+  return KB_OK;
+}
+
 // y <- T'^{-1} r on TRANSPOSED two-sided factors.  y has n+1 entries, y[n] == 0.
 int kbi_sweep_onehop(kb_context* h, const double2* r, double2* y) {
   cudaStream_t s = h->stream;
@@ -651,13 +674,7 @@ int kbi_sweep_onehop(kb_context* h, const double2* r, double2* y) {
   q.G0 = G0;
   q.dbgflags = getenv("KB_ONEHOP_DBG") ? atoi(getenv("KB_ONEHOP_DBG")) : 0;
   q.smax = (int)(2 * h->mid + 1);
-  if (!h->rng_valid) {
-    KB_CUDA(h, h->d_rng.alloc((size_t)G * q.smax * 2));
-    q.rng = h->d_rng.p;
-    kb_onehop_ranges<<<G, K1_THREADS, 0, s>>>(q, h->d_rng.p);
-    h->rng_valid = true;
-    h->launches++;
-  }
+  KB_TRY(kbi_onehop_build_ranges(h, G, G0));
   q.rng = h->d_rng.p;
   const void* fn = (const void*)kb_sweep_onehop;
   if (smem > 48 * 1024) KB_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
