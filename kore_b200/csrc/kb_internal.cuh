@@ -233,9 +233,6 @@ struct kb_context {
   DevBuf<unsigned char> d_foldops, d_foldring;
   int fold_npub[2] = {0, 0}, fold_nops[2] = {0, 0};
   unsigned long long fold_epoch[2] = {0, 0};
-  // tagged column-split sweep (kb_sweep3.cu)
-  DevBuf<unsigned char> d_tagring;
-  unsigned long long tag_epoch[2] = {0, 0};
   int64_t mid = 0;  // middle node of the two-sided elimination (P-1: one-sided)
   // ELL copies of the couplings + node tables for the persistent sweep kernel
   int WL = 0, WU = 0;
@@ -329,9 +326,6 @@ int kbi_sweep_onehop(kb_context* h, const double2* r, double2* y);
 bool kbi_fold_supported(const kb_context* h, int G, bool two_sided, int* slice_elems_out, size_t* smem_out);
 int kbi_fold_prepare(kb_context* h);
 int kbi_sweep_fold(kb_context* h, const double2* r, double2* y);
-// ---- kb_sweep3.cu
-bool kbi_tagged_supported(const kb_context* h, int G, bool two_sided, int* slice_elems_out, size_t* smem_out);
-int kbi_sweep_tagged(kb_context* h, const double2* r, double2* y);
 // ---- kb_shard.cu
 int kbi_factor_sharded(kb_context* h, zcomplex sigma);
 int kbi_chain_solve_sharded(kb_context* h, const double2* r_dev, double2* x_dev, int refine);

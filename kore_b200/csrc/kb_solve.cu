@@ -213,8 +213,6 @@ void kbi_drop_graphs(kb_context* h) {
 static int chain_sweeps(kb_context* h, const double2* r, double2* y) {
   cudaStream_t s = h->stream;
   if (h->nranks > 1) return kbi_sharded_sweeps(h, r, y);
-  if (h->M_transposed && kbi_tagged_supported(h, h->sweep_grid, h->mid < h->P - 1, nullptr, nullptr))
-    return kbi_sweep_tagged(h, r, y);
   if (h->fold_ready) return kbi_sweep_fold(h, r, y);
   if (h->M_transposed) return kbi_sweep_onehop(h, r, y);
   if (h->opt_sweep == 1 && h->sweep_grid > 0) return kbi_sweep_dataflow(h, r, y);

@@ -7,7 +7,6 @@
 #include "kb_sweep.cu"
 #include "kb_sweep1.cu"
 #include "kb_sweep2.cu"
-#include "kb_sweep3.cu"
 #include "kb_solve.cu"
 #include "kb_eigs.cu"
 #include "kb_shard.cu"
