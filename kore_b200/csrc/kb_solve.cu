@@ -108,20 +108,21 @@ __device__ __forceinline__ double2 kb_valmul<double>(double v, double2 x) { retu
 template <>
 __device__ __forceinline__ double2 kb_valmul<double2>(double2 v, double2 x) { return zmul(v, x); }
 
-// MODE 0: y = s .* (M x); MODE 1: y = r - M x
-template <typename VT, int MODE>
+// MODE 0: y = s .* (M x); MODE 1: y = r - M x.  LPR lanes per row (a power of two <= 32): Kore's B
+// has ~10 entries per row and A ~35, so a full warp per row leaves most lanes idle.
+template <typename VT, int MODE, int LPR = 32>
 __global__ void kb_spmv(int n, const int64_t* __restrict__ rowptr, const int* __restrict__ col,
                         const VT* __restrict__ val, const double2* __restrict__ x,
                         const double* __restrict__ rowscale, const double2* __restrict__ r,
                         double2* __restrict__ y) {
-  int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  int lane = threadIdx.x & 31;
+  int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR);
+  int lane = threadIdx.x & (LPR - 1);
   if (row >= n) return;
   double2 acc = zmake(0.0, 0.0);
-  for (int64_t k = rowptr[row] + lane, e = rowptr[row + 1]; k < e; k += 32)
+  for (int64_t k = rowptr[row] + lane, e = rowptr[row + 1]; k < e; k += LPR)
     acc = zadd(acc, kb_valmul<VT>(val[k], x[col[k]]));
 #pragma unroll
-  for (int s = 16; s > 0; s >>= 1) {
+  for (int s = LPR / 2; s > 0; s >>= 1) {
     acc.x += __shfl_xor_sync(0xffffffffu, acc.x, s);
     acc.y += __shfl_xor_sync(0xffffffffu, acc.y, s);
   }
@@ -290,7 +291,7 @@ int kbi_chain_solve(kb_context* h, const double2* r_dev, double2* x_dev, int ref
   KB_TRY(chain_sweeps(h, r_dev, x_dev));
   h->stats.solve_calls++;
   for (int it = 0; it < refine; ++it) {
-    kb_spmv<double2, 1><<<nblk((int64_t)n * 32, 256), 256, 0, s>>>(n, h->d_rowptr.p, h->d_col.p, h->d_Tval.p,
+    kb_spmv<double2, 1, 16><<<nblk((int64_t)n * 16, 256), 256, 0, s>>>(n, h->d_rowptr.p, h->d_col.p, h->d_Tval.p,
                                                                    x_dev, nullptr, r_dev, h->d_res.p);
     KB_TRY(chain_sweeps(h, h->d_res.p, h->d_x0.p));
     kb_axpy1<<<nblk(n, 256), 256, 0, s>>>(n, h->d_x0.p, x_dev);
@@ -308,10 +309,10 @@ int kbi_spmv_B_chain(kb_context* h, const double2* x, double2* y, bool scale_row
   if (!h->B.present) return kb_fail(h, KB_EINVAL, "pencil has no B matrix");
   const double* rs = scale_rows ? h->d_rscale.p : nullptr;
   if (h->b_is_complex)
-    kb_spmv<double2, 0><<<nblk((int64_t)n * 32, 256), 256, 0, s>>>(n, h->d_browptr.p, h->d_bcol.p, h->d_bval_c.p,
+    kb_spmv<double2, 0, 8><<<nblk((int64_t)n * 8, 256), 256, 0, s>>>(n, h->d_browptr.p, h->d_bcol.p, h->d_bval_c.p,
                                                                    x, rs, nullptr, y);
   else
-    kb_spmv<double, 0><<<nblk((int64_t)n * 32, 256), 256, 0, s>>>(n, h->d_browptr.p, h->d_bcol.p, h->d_bval_r.p, x,
+    kb_spmv<double, 0, 8><<<nblk((int64_t)n * 8, 256), 256, 0, s>>>(n, h->d_browptr.p, h->d_bcol.p, h->d_bval_r.p, x,
                                                                   rs, nullptr, y);
   h->launches++;
   KB_LAUNCH_CHECK(h);
@@ -320,7 +321,7 @@ int kbi_spmv_B_chain(kb_context* h, const double2* x, double2* y, bool scale_row
 
 int kbi_spmv_A_chain(kb_context* h, const double2* x, double2* y) {
   const int n = (int)h->n;
-  kb_spmv<double2, 0><<<nblk((int64_t)n * 32, 256), 256, 0, h->stream>>>(n, h->d_rowptr.p, h->d_col.p,
+  kb_spmv<double2, 0, 16><<<nblk((int64_t)n * 16, 256), 256, 0, h->stream>>>(n, h->d_rowptr.p, h->d_col.p,
                                                                          h->d_Aval.p, x, nullptr, nullptr, y);
   h->launches++;
   KB_LAUNCH_CHECK(h);
