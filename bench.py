@@ -12,7 +12,7 @@ the GPU box, and the real A.npz (250 MB) is not shipped.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 N > 1 (launched by torch.distributed.run, one rank per GPU):
-  --mode shifts (default): independent shifts dealt one per GPU, no data-path
+  --mode shifts (default): independent factor + eigensolve units, one per GPU, no data-path
       collective ("scaling": "weak");
   --mode lshard: ONE pencil, l-blocks sharded across the ranks, reduced interface
       system exchanged over NCCL ("scaling": "strong").
@@ -247,7 +247,11 @@ def run_ours(args):
 
     A, B, perm, nodeptr, v0 = make_workload(args.P, args.b)
     n = A.shape[0]
-    sigma = 1j + (0.003 * rank if (distributed and args.mode == "shifts") else 0.0)
+    # throughput mode: every rank runs the same unit of work (one pencil, one shift, nev pairs) on
+    # its own GPU, so that per-GPU work does not depend on N (a different shift per rank changes
+    # the Arnoldi iteration count and with it the work per rank: 507 vs 457 ms per step at N = 2
+    # with sigma = 1j + 0.003 rank, profiles/r1d_bench_2gpu_shifts.json)
+    sigma = 1j
 
     s = lib.Solver(local)
     s.set_pencil(A, B)

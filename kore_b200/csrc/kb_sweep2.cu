@@ -49,7 +49,9 @@
 #define K2_PPT 10                // entries of the input vector polled per gather thread (640 / 64)
 #define K2_RING 4                // publication ring slots (power of two)
 #define K2_XR 10                 // most rows of a node a CTA may own: warps 0-3 take two, 4-5 one
+#ifndef K2_AHEAD
 #define K2_AHEAD 4               // L2 prefetch distance, in steps
+#endif
 
 struct alignas(32) K2Elem {
   double re, tag0, im, tag1;
