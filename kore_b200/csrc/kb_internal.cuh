@@ -71,6 +71,38 @@ __device__ __forceinline__ double2 zinv_fast(double2 p) {
 }
 
 // ---------------------------------------------------------------------------
+// spin-wait bound of every device-side wait (a peer that never arrives must not hang the GPU)
+// ---------------------------------------------------------------------------
+#define KB_SPIN_LIMIT (1 << 22)
+
+// ---- mbarrier + 1-D bulk (TMA) copy helpers
+__device__ __forceinline__ unsigned kb_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void kb_mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(kb_smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void kb_mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(kb_smem_addr(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void kb_bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   kb_smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(kb_smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void kb_mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned done = 0;
+  int spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(kb_smem_addr(bar)), "r"(parity)
+        : "memory");
+  } while (!done && ++spins < KB_SPIN_LIMIT);
+}
+
+// ---------------------------------------------------------------------------
 // error handling
 // ---------------------------------------------------------------------------
 struct kb_context;
