@@ -224,6 +224,10 @@ __global__ void __launch_bounds__(KF_MAXT, 1) kb_chain_factor(KfParams q) {
   long long colbase = 0;  // columns eliminated by this group before the current node
   long long tacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tc = clock64();
+  // Cycle counters are compiled in only with -DKB_FACTOR_TIMING (make EXTRA=-DKB_FACTOR_TIMING):
+  // even switched off at run time each tick costs ~15 predicated instructions, four per panel
+  // column, in a loop that is bound by instruction issue (ncu source page, profiles/).
+#ifdef KB_FACTOR_TIMING
 #define KF_TICK(k)                \
   do {                            \
     if (q.dbg) {                  \
@@ -232,6 +236,11 @@ __global__ void __launch_bounds__(KF_MAXT, 1) kb_chain_factor(KfParams q) {
       tc = _n;                    \
     }                             \
   } while (0)
+#else
+#define KF_TICK(k) \
+  do {             \
+  } while (0)
+#endif
 
   for (int s = 0; s < S; ++s) {
     const int p = group == 0 ? s : P - 1 - s;
