@@ -335,10 +335,16 @@ __global__ void __launch_bounds__(KF_MAXT, 1) kb_chain_factor(KfParams q) {
               const bool broken = mhi <= 1u || mhi >= 0x7ff00001u || rp >= b || rp < 0;
               if (broken) rp = -1;  // skip the column; the host reports KB_ESINGULAR
               const bool isp = (t == rp);
-              if (isp) {
+              // warp-uniform: only the warp that holds the pivot row executes the publication and
+              // the selects of the update below; a predicated-off instruction still takes an issue
+              // slot, and the panel is bound by instruction issue
+              const bool anyp = (rp >= 0) && ((rp >> 5) == wid);
+              if (anyp) {
+                if (isp) {
 #pragma unroll
-                for (int j = 0; j < NB; ++j) sh.prow[par][j] = a[j];
-                sh.prow[par][NB] = zmake(a[cc].x * rinv, -a[cc].y * rinv);
+                  for (int j = 0; j < NB; ++j) sh.prow[par][j] = a[j];
+                  sh.prow[par][NB] = zmake(a[cc].x * rinv, -a[cc].y * rinv);
+                }
               }
               if (t == (int)blockDim.x - 1) {
                 if (broken) atomicExch(q.info, o + gk + 1);
@@ -360,12 +366,13 @@ __global__ void __launch_bounds__(KF_MAXT, 1) kb_chain_factor(KfParams q) {
               // trails the panel by one L2 hop instead of waiting for the whole strip
               if (sput && t < b)
                 kf_stream_put(sput + 4 * (size_t)cc * ldg, isp ? mult : zneg(mult), stag + (double)(1024 * cc + rp + 1));
-#define KF_UPD(j)                                          \
-  do {                                                     \
-    double2 _acc = isp ? zmake(0.0, 0.0) : a[j];           \
-    zfma(_acc, mult, prow[j]);                             \
-    a[j] = _acc;                                           \
-  } while (0)
+              if (anyp) {
+                // the pivot row restarts from zero: a[j] <- 0 + (1/pivot) * a[j]
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+                  if (isp) a[j] = zmake(0.0, 0.0);
+              }
+#define KF_UPD(j) zfma(a[j], mult, prow[j])
               // next column first, so that its pivot vote overlaps the rest of the elimination
               if (cc + 1 < NB) {
                 KF_UPD(cc + 1);
