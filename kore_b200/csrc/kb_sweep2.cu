@@ -155,6 +155,9 @@ __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int s
   const K2Op* ops = q.ops[group];
   long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long tc0 = clock64();
+  // cycle counters only with -DKB_SWEEP_TICKS (make EXTRA=-DKB_SWEEP_TICKS): a disabled tick still
+  // costs ~15 predicated instructions
+#ifdef KB_SWEEP_TICKS
 #define K2_TICK(k)              \
   do {                          \
     if (q.timing) {             \
@@ -163,6 +166,11 @@ __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int s
       tc0 = _t;                 \
     }                           \
   } while (0)
+#else
+#define K2_TICK(k) \
+  do {             \
+  } while (0)
+#endif
 
   for (int i = tid; i <= q.P; i += K2_THREADS) s_nptr[i] = (int)q.nodeptr[i];
   if (tid == 0) {
