@@ -14,5 +14,10 @@ $(LIB): $(DEPS)
 ptxas: $(DEPS)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o /tmp/kb_ptxas.so $(SRC)
 
+# the same library with the in-kernel cycle counters compiled in (tools/dev_factor_timing.py,
+# tools/dev_fold_timing.py: run them with KB_LIB_PATH=kore_b200/libkoreb200_timing.so)
+timing: $(DEPS)
+	$(NVCC) $(NVFLAGS) -DKB_FACTOR_TIMING -DKB_SWEEP_TICKS -shared -o kore_b200/libkoreb200_timing.so $(SRC)
+
 clean:
 	rm -f $(LIB)

@@ -41,6 +41,63 @@ def panel_gj(strip, isfree, wk):
     return piv
 
 
+def panel_gj_stream(strip, isfree, wk):
+    """The panel as kb_chainfac.cu runs it with the column stream: the same eliminations, but
+    every column also emits its ELEMENTARY transform (pivot row r, multipliers g with 1/pivot in
+    slot r) -- what the kernel stores as tagged 32-byte elements -- instead of relying on the
+    composite left in the strip.  The pivot row restarts from zero and is updated like every
+    other row (0 + (1/pivot) * row), the form the kernel uses to keep the update branch-free."""
+    stream = []
+    for c in range(wk):
+        mag = np.where(isfree, np.abs(strip[:, c]), -1.0)
+        r = int(np.argmax(mag))
+        isfree[r] = False
+        prow = strip[r, :].copy()
+        pinv = 1.0 / prow[c]
+        mult = -strip[:, c] * pinv
+        mult[r] = pinv
+        elem = -mult
+        elem[r] = pinv                      # the streamed element: g_i, or 1/pivot on the pivot row
+        stream.append((r, elem.copy()))
+        strip[r, :] = 0.0
+        strip += np.outer(mult, prow)       # a[j] <- a[j] + mult * prow[j] for every row
+        strip[:, c] = mult                  # -g, or 1/pivot on the pivot row
+    return stream
+
+
+def apply_stream(A, stream):
+    """A consumer strip applies the streamed columns one by one (kb_chainfac.cu, consumer path):
+    A[i,:] <- A[i,:] - g_i A[piv,:] (i != piv), A[piv,:] <- A[piv,:] / pivot."""
+    for r, elem in stream:
+        prow = A[r, :].copy()
+        g = elem.copy()
+        g[r] = 0.0
+        A -= np.outer(g, prow)
+        A[r, :] = prow * elem[r]
+    return A
+
+
+def strip_invert_stream(S, w):
+    """strip_invert with the column stream in place of the composite transforms."""
+    b = S.shape[0]
+    K = (b + w - 1) // w
+    strips = [S[:, k * w:min(b, (k + 1) * w)].astype(np.complex128).copy() for k in range(K)]
+    isfree = np.ones(b, dtype=bool)
+    rowpiv = np.zeros(b, dtype=int)
+    for k in range(K):
+        k0 = k * w
+        wk = strips[k].shape[1]
+        stream = panel_gj_stream(strips[k], isfree, wk)
+        rowpiv[k0:k0 + wk] = [r for r, _ in stream]
+        for s in range(K):
+            if s != k:
+                apply_stream(strips[s], stream)
+    Y = np.concatenate(strips, axis=1)
+    M = np.empty_like(Y)
+    M[:, rowpiv] = Y[rowpiv, :]
+    return M
+
+
 def strip_invert(S, w):
     b = S.shape[0]
     K = (b + w - 1) // w

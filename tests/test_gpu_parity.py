@@ -226,6 +226,26 @@ def test_strip_factor_kernel_matches_per_step_kernels(lib, name):
         assert err <= 1e-10, (sweep, err)
 
 
+@pytest.mark.parametrize("name", ["spinover", "dormy"])
+def test_column_stream_matches_composite_transforms(lib, name, monkeypatch):
+    # the strip factorisation hands the elementary transforms of every column to the other strips
+    # as a tagged stream (default) or publishes the composite transform of a strip at its end
+    # (KB_CHAINFAC_NOSTREAM=1): same eliminations, same pivots
+    case = load_case(name)
+    rhs = case.oracle["solve_rhs"]
+    with make_solver(lib, case, opts={lib.OPT_REFINE: 0}) as s:
+        x_stream = s.solve(rhs)
+        s.factor(case.tau)  # the stream buffers are zeroed and reused
+        assert np.array_equal(x_stream, s.solve(rhs))
+    monkeypatch.setenv("KB_CHAINFAC_NOSTREAM", "1")
+    with make_solver(lib, case, opts={lib.OPT_REFINE: 0}) as s:
+        x_comp = s.solve(rhs)
+    monkeypatch.delenv("KB_CHAINFAC_NOSTREAM")
+    assert np.linalg.norm(x_stream - x_comp) <= 1e-10 * np.linalg.norm(x_comp)
+    xo = case.oracle["solve_x"]
+    assert np.linalg.norm(x_stream - xo) <= 1e-9 * np.linalg.norm(xo)
+
+
 @pytest.mark.parametrize("name", ["spinover", "dormy", "magnetic_small"])
 def test_persistent_sweep_matches_per_node_kernels(lib, name):
     # the cooperative one-launch sweep and the per-node (graph-replayed) kernels are two

@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
 """Developer probe (GPU box): cycle breakdown of the persistent strip factorisation."""
+# cycle counters need the timing build: `make timing`, then KB_LIB_PATH=kore_b200/libkoreb200_timing.so
 import sys, os, ctypes as C
 os.environ["KB_SWEEP_TIMING"] = "1"
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))

@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Dev: time the chain sweep variants on the synthetic pencil (folded vs one-hop) and check them
 against each other.  usage: dev_fold_timing.py P b"""
+# cycle counters need the timing build: `make timing`, then KB_LIB_PATH=kore_b200/libkoreb200_timing.so
 import sys, os, time, ctypes as C
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np
