@@ -31,10 +31,17 @@
 
 #include "kb_internal.cuh"
 
-#define KF_NB 9       // columns per strip (compile-time bound of the register row)
+// Two instantiations: <9, 640> for nodes up to 640 rows (strips of <= 9 columns over 74 CTAs per
+// chain: every size the benchmark names) and <10, 704> for nodes up to 704 rows (Kore's own
+// resolution rule at E = 1e-8 gives N = 676), which has 88 registers per thread and spills a
+// little.  NB = columns per strip (compile-time bound of the register row), MAXT = threads per
+// CTA = largest supported node.  The row pitch (double2) of the W strip in shared memory is
+// NB | 1 (odd: conflict-free).
+#define KF_NB 9
+#define KF_MAXT 640
+#define KF_NB_WIDE 10
+#define KF_MAXT_WIDE 704
 #define KF_WMIN 8     // narrowest strip used (fewer, fatter steps for small nodes)
-#define KF_MAXT 640   // threads per CTA = largest supported node
-#define KF_WP 9       // row pitch (double2) of the W strip in shared memory (odd: conflict-free)
 #define KF_SPIN (1 << 22)
 
 struct KfParams {
@@ -146,9 +153,10 @@ __device__ __forceinline__ double2 kf_stream_get(const double* p, double tagbase
   return zmake(re, im);
 }
 
+template <int NB>
 struct KfShared {
-  double2 slots[2][KF_NB][KF_NB];            // pivot rows of this CTA's strip for the step being applied
-  double2 prow[2][KF_NB + 1];                // the pivot row of the column being eliminated (+ 1/pivot)
+  double2 slots[2][NB][NB];                  // pivot rows of this CTA's strip for the step being applied
+  double2 prow[2][NB + 1];                   // the pivot row of the column being eliminated (+ 1/pivot)
   unsigned long long candkey[2][32];         // (key << 32) | ~row of every warp's candidate
   int piv[16];                               // pivots of the panel being factored
 };
@@ -180,7 +188,7 @@ __device__ __forceinline__ void kf_schur_term(const KfParams& q, double2 (&a)[NB
         const double2 cv = __ldg(&q.T[__ldg(&cpos[e])]);
         zfma(acc, __ldcg(&Mrow[(size_t)rr * mstride]), cv);
       }
-      Ws[(size_t)t * KF_WP + jj] = acc;
+      Ws[(size_t)t * (NB | 1) + jj] = acc;
     }
   }
   __syncthreads();
@@ -191,7 +199,7 @@ __device__ __forceinline__ void kf_schur_term(const KfParams& q, double2 (&a)[NB
     for (int64_t k = k0; k < k1; ++k) {
       const int cq = __ldg(&q.col[k]) - oq;
       const double2 v = __ldg(&q.T[k]);
-      const double2* wr = Ws + (size_t)cq * KF_WP;
+      const double2* wr = Ws + (size_t)cq * (NB | 1);
 #pragma unroll
       for (int jj = 0; jj < NB; ++jj)
         if (jj < ws) zfms(a[jj], v, wr[jj]);
@@ -200,12 +208,12 @@ __device__ __forceinline__ void kf_schur_term(const KfParams& q, double2 (&a)[NB
   __syncthreads();
 }
 
-template <int NB>
-__global__ void __launch_bounds__(KF_MAXT, 1) kb_chain_factor(KfParams q) {
+template <int NB, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) kb_chain_factor(KfParams q) {
   extern __shared__ __align__(16) unsigned char kf_smem[];
-  KfShared& sh = *(KfShared*)kf_smem;
-  int* s_orig = (int*)(kf_smem + sizeof(KfShared));
-  double2* Ws = (double2*)(kf_smem + sizeof(KfShared) + (((size_t)q.bmax * sizeof(int) + 15) & ~(size_t)15));
+  KfShared<NB>& sh = *(KfShared<NB>*)kf_smem;
+  int* s_orig = (int*)(kf_smem + sizeof(KfShared<NB>));
+  double2* Ws = (double2*)(kf_smem + sizeof(KfShared<NB>) + (((size_t)q.bmax * sizeof(int) + 15) & ~(size_t)15));
 
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const int NW = (int)blockDim.x >> 5;
@@ -308,7 +316,7 @@ __global__ void __launch_bounds__(KF_MAXT, 1) kb_chain_factor(KfParams q) {
           // critical path.
           double rinv;
           // column stream of this strip: slot of this row, tag of column 0 with pivot code 0
-          double* sput = q.Sbuf[group] ? q.Sbuf[group] + 4 * ((size_t)((k & 1) * KF_NB) * ldg + t) : nullptr;
+          double* sput = q.Sbuf[group] ? q.Sbuf[group] + 4 * ((size_t)((k & 1) * NB) * ldg + t) : nullptr;
           const double stag = (double)((colbase + k0 + 1) * 1024);
           {
             const double m2 = zabs2(a[0]);
@@ -419,7 +427,7 @@ __global__ void __launch_bounds__(KF_MAXT, 1) kb_chain_factor(KfParams q) {
           // else finds the columns already there.  Polls go out three columns at a time, so a
           // CTA that is catching up pays one round trip per three columns.
           KF_TICK(2);
-          const double* sbase = q.Sbuf[group] + 4 * ((size_t)((k & 1) * KF_NB) * ldg + t);
+          const double* sbase = q.Sbuf[group] + 4 * ((size_t)((k & 1) * NB) * ldg + t);
           const double tag0 = (double)((colbase + k0 + 1) * 1024);
 #pragma unroll
           for (int c3 = 0; c3 < NB; c3 += 3) {
@@ -560,8 +568,8 @@ __global__ void __launch_bounds__(KF_MAXT, 1) kb_chain_factor(KfParams q) {
 bool kbi_chainfac_supported(const kb_context* h) {
   if (getenv("KB_NO_CHAINFAC")) return false;
   if (h->opt_factor == 0) return false;
-  if (h->bmax > KF_MAXT) return false;
-  // every strip must fit the register row: ceil(bmax / CTAs per chain) <= KF_NB
+  if (h->bmax > KF_MAXT_WIDE) return false;
+  // every strip must fit the register row: ceil(bmax / CTAs per chain) <= KF_NB (KF_NB_WIDE)
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) != cudaSuccess) return false;
   if (getenv("KB_CHAINFAC_GRID")) {
@@ -569,7 +577,7 @@ bool kbi_chainfac_supported(const kb_context* h) {
     if (g >= 2 && g < sms) sms = g;
   }
   const int gc = sms / 2;
-  if (gc < 1 || (h->bmax + gc - 1) / gc > KF_NB) return false;
+  if (gc < 1 || (h->bmax + gc - 1) / gc > KF_NB_WIDE) return false;
   return true;
 }
 
@@ -630,7 +638,7 @@ int kbi_chainfac_run(kb_context* h, bool two_sided, bool transposed) {
   q.transposed = transposed ? 1 : 0;
   q.Sbuf[0] = q.Sbuf[1] = nullptr;
   if (!getenv("KB_CHAINFAC_NOSTREAM")) {
-    const size_t per = (size_t)2 * KF_NB * bmax * 4;  // doubles per group
+    const size_t per = (size_t)2 * KF_NB_WIDE * bmax * 4;  // doubles per group
     KB_CUDA(h, h->d_kfstream.alloc((size_t)ngroups * per));
     KB_CUDA(h, cudaMemsetAsync(h->d_kfstream.p, 0, (size_t)ngroups * per * sizeof(double), s));
     q.Sbuf[0] = h->d_kfstream.p;
@@ -639,9 +647,15 @@ int kbi_chainfac_run(kb_context* h, bool two_sided, bool transposed) {
   q.stagger_ns = getenv("KB_CHAINFAC_STAGGER") ? atoi(getenv("KB_CHAINFAC_STAGGER")) : 1000;
   int T = (int)((bmax + 31) / 32) * 32;
   if (T < 64) T = 64;
-  const size_t smem = sizeof(KfShared) + (((size_t)bmax * sizeof(int) + 15) & ~(size_t)15) +
-                      (size_t)bmax * KF_WP * sizeof(double2);
-  const void* fn = (const void*)kb_chain_factor<KF_NB>;
+  // <9, 640> whenever the node and its strips fit, <10, 704> for the wider ones
+  const int gcw = (two_sided ? q.G0 : G);
+  const bool wide = bmax > KF_MAXT || (bmax + gcw - 1) / gcw > KF_NB;
+  const int nbsel = wide ? KF_NB_WIDE : KF_NB;
+  const size_t smem = (wide ? sizeof(KfShared<KF_NB_WIDE>) : sizeof(KfShared<KF_NB>)) +
+                      (((size_t)bmax * sizeof(int) + 15) & ~(size_t)15) +
+                      (size_t)bmax * (nbsel | 1) * sizeof(double2);
+  const void* fn = wide ? (const void*)kb_chain_factor<KF_NB_WIDE, KF_MAXT_WIDE>
+                        : (const void*)kb_chain_factor<KF_NB, KF_MAXT>;
   KB_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* args[] = {(void*)&q};
   KB_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(G), dim3(T), args, smem, s));

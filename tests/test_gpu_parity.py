@@ -365,14 +365,20 @@ def test_full_size_properties(lib):
             assert abs(np.linalg.norm(X[:, i]) - 1.0) < 1e-12
 
 
-def test_wide_nodes_use_the_general_kernels(lib):
-    # nodes wider than the strip kernel's register rows (b > 640) take the per-step panel/update
-    # kernels and the row-split sweep: same answers
+@pytest.mark.parametrize("b", [676, 700, 800])
+def test_wide_nodes(lib, b):
+    # nodes of 641..704 rows take the <10, 704> instantiation of the strip kernel (Kore's own rule
+    # at E = 1e-8 gives N = 676) and the row-split sweep; wider ones the per-step panel/update
+    # kernels: same answers
     from kore_b200 import synthetic
-    s, A, B = _synthetic_solver(lib, 6, 700)
+    s, A, B = _synthetic_solver(lib, 6, b)
     with s:
         n = A.shape[0]
         T = (A - 1j * B).tocsr()
         r = B @ synthetic.start_vector(n, 3)
         x = s.solve(r)
         assert np.linalg.norm(T @ x - r) <= 1e-12 * np.linalg.norm(r)
+        s.set_option(lib.OPT_FACTOR, 0)  # per-step kernels on the same pencil
+        s.factor(1j)
+        x2 = s.solve(r)
+        assert np.linalg.norm(x - x2) <= 1e-10 * np.linalg.norm(x2)
