@@ -208,7 +208,7 @@ def run_reference(args):
         "cpu_baseline": last,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -234,10 +234,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     distributed = world > 1
     if distributed:
-        # NCCL prints its version banner on STDOUT when NCCL_DEBUG=VERSION; rank 0's stdout must be
-        # the one JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -410,7 +406,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_sample(args.P, args.b, args.nev, args.ncv, args.tol, args.cpu_nodes)
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     s.close()
     if distributed:
         dist.destroy_process_group()
@@ -435,9 +431,29 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    # Rank 0's stdout must be the ONE JSON line.  Libraries write to file descriptor 1 behind
+    # Python's back (NCCL prints "NCCL version ..." there at any NCCL_DEBUG level >= VERSION), so
+    # fd 1 points at stderr for the whole run and is switched back only around emit().
+    sys.stdout.flush()
+    _Out.real = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
+
+
+class _Out:
+    real = None
+
+
+def emit(line):
+    """Print the result line on the process's real stdout."""
+    sys.stdout.flush()
+    if _Out.real is not None:
+        os.dup2(_Out.real, 1)
+    print(json.dumps(line), flush=True)
+    if _Out.real is not None:
+        os.dup2(2, 1)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,40 @@
+"""CPU: bench.py's driver contract on the reference arm (the only arm that runs without a GPU):
+exactly ONE JSON line on stdout -- library chatter written to file descriptor 1 behind Python's
+back (NCCL's version banner) is diverted to stderr -- with the keys the driver reads."""
+import json
+import os
+import subprocess
+import sys
+import textwrap
+
+from conftest import ROOT
+
+
+def test_reference_arm_prints_one_json_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--cpu-nodes", "2"], capture_output=True, text=True, cwd=ROOT, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "eigenpairs/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_fd_level_chatter_stays_off_stdout():
+    code = textwrap.dedent("""
+        import os, sys
+        sys.path.insert(0, %r)
+        import bench
+        sys.stdout.flush(); bench._Out.real = os.dup(1); os.dup2(2, 1)
+        os.write(1, b'NCCL version 2.28.9+cuda12.9\\n')
+        bench.emit({'metric': 'x', 'value': 1})
+        os.write(1, b'late chatter\\n')
+    """ % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == '{"metric": "x", "value": 1}\n'
+    assert "NCCL version" in r.stderr and "late chatter" in r.stderr
