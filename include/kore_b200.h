@@ -56,7 +56,23 @@ enum {
   KB_OPT_REFINE = 2,      /* max iterative-refinement steps per solve (default 1)             */
   KB_OPT_PURIFY = 3,      /* 0/1: x <- OP x on extracted eigenvectors (SLEPc EPSSetPurify)    */
   KB_OPT_SEED = 4,        /* seed of the random Arnoldi start vector when v0 == NULL          */
-  KB_OPT_PANEL = 5        /* Gauss-Jordan panel width override (0 = automatic)                */
+  KB_OPT_PANEL = 5,       /* Gauss-Jordan panel width override (0 = automatic)                */
+  KB_OPT_REFINE_EIGS = 6, /* refinement steps per operator application inside kb_eigs (default 0) */
+  KB_OPT_SWEEP = 7,       /* chain-sweep kernels: 1 persistent two-sided (default), 2 persistent
+                             one-sided with grid barriers, 0 one kernel pair per node (no device-side
+                             waits).  Takes effect at the next kb_factor (the factors are laid out
+                             for the sweep that will read them).                                 */
+  KB_OPT_FACTOR = 8,      /* 1 persistent strip factorisation (default), 0 per-step kernels.
+                             Next kb_factor.                                                     */
+  KB_OPT_FOLD = 9,        /* 0/1: folded couplings for the persistent sweep (default 1; costs
+                             2 x the factor memory).  Next kb_factor.                            */
+  KB_OPT_WAIT_MS = 10,    /* time bound, in ms, of every device-side wait of the persistent
+                             kernels (default 4000).  When a wait expires the launch drains, the
+                             handle falls back to the kernels of KB_OPT_SWEEP = 0 / KB_OPT_FACTOR
+                             = 0, refactors and repeats the call (kb_stats.protocol_fallbacks).   */
+  KB_OPT_INJECT_FAULT = 11 /* tests: 1 = the next chain sweep, 2 = the next factorisation behaves
+                             as if a device-side wait had expired; 3 = the next folded sweep
+                             publishes unreadable tags, so that its waits really expire           */
 };
 
 /* PETSc.Sys / slepc4py.init (solve.py:15-16, 31-34): create a solver context
@@ -142,6 +158,9 @@ typedef struct {
   double factor_flops;    /* real flops executed by the last kb_factor        */
   double solve_bytes;     /* algorithmic bytes of one chain solve             */
   double refine_resid;    /* last relative linear residual seen in refinement */
+  int64_t protocol_fallbacks; /* times a persistent kernel timed out and the handle fell back
+                                 to the kernels without device-side waits (0 in a healthy run) */
+  int64_t wait_error;     /* code | CTA << 8 of the last expired device-side wait (0: none)  */
 } kb_stats;
 int kb_get_stats(kb_handle h, kb_stats* out);
 
@@ -158,6 +177,16 @@ int kb_stream(kb_handle h, void** cuda_stream);
  * (timing.dat, solve.py:309-311). */
 int kb_savetxt(const char* path, const double* data, int64_t rows, int64_t cols, int64_t row_stride,
                int64_t col_stride, int append, int nthreads);
+
+/* Debug / test hooks (not part of the drop-in surface).  kb_dbg_schur: the host-side complex
+ * Schur form + ordering of the projected problem (what SLEPc's DS does with LAPACK), m x m
+ * column-major complex128 in, T and Q out; which < 0: no ordering.  kb_dbg_*_timing: in-kernel
+ * cycle counters of the last persistent factorisation / sweep (library built with
+ * -DKB_FACTOR_TIMING / -DKB_SWEEP_TICKS, KB_SWEEP_TIMING=1 in the environment). */
+int kb_dbg_schur(int m, const double* H, int which, const double* sigma, const double* tau,
+                 double* T, double* Q);
+int kb_dbg_factor_timing(kb_handle h, long long* out, int max_ctas);
+int kb_dbg_sweep_timing(kb_handle h, long long* out, int max_ctas);
 
 #ifdef __cplusplus
 }

@@ -42,7 +42,8 @@
 #define KF_NB_WIDE 10
 #define KF_MAXT_WIDE 704
 #define KF_WMIN 8     // narrowest strip used (fewer, fatter steps for small nodes)
-#define KF_SPIN (1 << 22)
+#define KF_RING 4     // strips of the column stream in flight (ring slots; a power of two)
+#define KF_SYNC_WORDS 512  // sync block: 2 x 96 words of counters, time-out flag at KF_ERR_WORD, ring counters from 192
 
 struct KfParams {
   int P, mid;
@@ -62,17 +63,20 @@ struct KfParams {
   const int64_t* lpos;
   double2* Gbuf[2];   // per group: bmax x bmax, column-major (column = global pivot column)
   int* pivbuf[2];     // per group: 16 ints per step
-  unsigned* sync;     // per group 96 words: [0] published steps, [32] barrier arrivals, [64] chain done
+  unsigned* sync;     // per group 96 words: [0] published steps, [32] barrier arrivals, [64] chain done;
+                      // from word 192: one 128-byte line per (group, ring slot): consumers done with the slot
   int* info;
   int* err;
+  unsigned long long wait_ns;  // time bound of every wait of the launch
   long long* dbg;     // optional: 16 cycle counters per CTA
   int bmax;
   int G0;             // CTAs of group 0 (the rest form group 1)
   int stagger_ns;     // consumers other than the next owner hold their loads of G_k back by this much
   int transposed;     // store M_p^T (row j of the buffer = column j of M_p) for kb_sweep1.cu
-  // per-column stream of the elementary transforms to the owner of the NEXT strip: 32-byte
-  // tagged elements (re, tag, im, tag), [2 strip parities][KF_NB columns][bmax rows] per group;
-  // null: the next owner waits for the composite G_k like everybody else
+  // per-column stream of the elementary transforms to every other strip: 32-byte tagged
+  // elements (re, tag, im, tag), [KF_RING strips][NB columns][bmax rows] per group (strip k uses
+  // ring slot k mod KF_RING; its owner does not write before every consumer of strip k - KF_RING
+  // has said it is done with the slot); null: consumers wait for the composite G_k
   double* Sbuf[2];
 };
 
@@ -85,31 +89,26 @@ __device__ __forceinline__ void kf_st_release(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Bounded wait until *ctr >= target (one thread).  Out of line: the clock and the poll counter
+// must not take registers from the strip rows of the kernel below.
+__device__ __noinline__ void kf_spin_until(const unsigned* ctr, unsigned target, int* err, int code,
+                                           unsigned long long wait_ns) {
+  KbSpin sp;
+  while (kf_ld_acquire(ctr) < target)
+    if (kb_spin_expired(sp, err, code, wait_ns)) break;
+}
+
 // thread 0 waits until *ctr >= target; everybody leaves through the block barrier
-__device__ __forceinline__ void kf_wait(const unsigned* ctr, unsigned target, int* err) {
-  if (threadIdx.x == 0) {
-    int spins = 0;
-    while (kf_ld_acquire(ctr) < target) {
-      if ((++spins & 255) == 0 && (*(volatile int*)err != 0 || spins > KF_SPIN)) {
-        atomicExch(err, 1);
-        break;
-      }
-    }
-  }
+__device__ __forceinline__ void kf_wait(const unsigned* ctr, unsigned target, int* err, unsigned long long wait_ns) {
+  if (threadIdx.x == 0) kf_spin_until(ctr, target, err, KB_WERR_COUNTER, wait_ns);
   __syncthreads();
 }
 
-__device__ __forceinline__ void kf_group_barrier(unsigned* ctr, unsigned target, int* err) {
+__device__ __forceinline__ void kf_group_barrier(unsigned* ctr, unsigned target, int* err, unsigned long long wait_ns) {
   __syncthreads();
   if (threadIdx.x == 0) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
-    int spins = 0;
-    while (kf_ld_acquire(ctr) < target) {
-      if ((++spins & 255) == 0 && (*(volatile int*)err != 0 || spins > KF_SPIN)) {
-        atomicExch(err, 1);
-        break;
-      }
-    }
+    kf_spin_until(ctr, target, err, KB_WERR_GROUP_BARRIER, wait_ns);
   }
   __syncthreads();
 }
@@ -134,23 +133,23 @@ __device__ __forceinline__ void kf_stream_put(double* p, double2 v, double tag) 
   asm volatile("st.relaxed.gpu.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(v.x), "d"(tag), "d"(v.y), "d"(tag)
                : "memory");
 }
-__device__ __forceinline__ double2 kf_stream_get(const double* p, double tagbase, int& piv, int* err) {
+// Slow path of a consumer that has caught up with the panel: poll until the element carries a tag
+// of the expected column (or the launch has failed).  Out of line and without results -- the
+// caller loads the element again -- so that the clock, the poll counter and the call itself
+// take no registers from the strip rows.
+__device__ __noinline__ void kf_stream_wait(const double* p, double tagbase, int* err, unsigned long long wait_ns) {
   double re, t0, im, t1;
-  int spins = 0;
+  KbSpin sp;
   for (;;) {
     asm volatile("ld.relaxed.gpu.global.v4.f64 {%0, %1, %2, %3}, [%4];"
                  : "=d"(re), "=d"(t0), "=d"(im), "=d"(t1)
                  : "l"(p)
                  : "memory");
+    (void)re;
+    (void)im;
     if (t0 == t1 && t0 >= tagbase && t0 < tagbase + 1024.0) break;
-    if ((++spins & 255) == 0 && (*(volatile int*)err != 0 || spins > KF_SPIN)) {
-      atomicExch(err, 1);
-      t0 = tagbase;
-      break;
-    }
+    if (kb_spin_expired(sp, err, KB_WERR_STREAM, wait_ns)) break;
   }
-  piv = (int)(t0 - tagbase) - 1;
-  return zmake(re, im);
 }
 
 template <int NB>
@@ -159,6 +158,8 @@ struct KfShared {
   double2 prow[2][NB + 1];                   // the pivot row of the column being eliminated (+ 1/pivot)
   unsigned long long candkey[2][32];         // (key << 32) | ~row of every warp's candidate
   int piv[16];                               // pivots of the panel being factored
+  unsigned consbase[KF_RING];                // consumers that had released each ring slot before this node
+  unsigned bp_seen;                          // ring counter of this CTA's own strip as last read by thread 0
 };
 
 // S strip -= C_pq (M_q C_qp)[:, strip].  kind 0: q = p-1 (C_qp = U by column, C_pq = the
@@ -230,6 +231,10 @@ __global__ void __launch_bounds__(MAXT, 1) kb_chain_factor(KfParams q) {
   const int ldg = q.bmax;
   unsigned pubbase = 0, barcount = 0;
   long long colbase = 0;  // columns eliminated by this group before the current node
+  // ring counters of this group: slot j's line counts the CTAs that are done reading it
+  unsigned* cons = q.sync + 192 + group * (KF_RING * 32);
+  if (t == 0)
+    for (int j = 0; j < KF_RING; ++j) sh.consbase[j] = 0u;
   long long tacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tc = clock64();
   // Cycle counters are compiled in only with -DKB_FACTOR_TIMING (make EXTRA=-DKB_FACTOR_TIMING):
@@ -265,7 +270,7 @@ __global__ void __launch_bounds__(MAXT, 1) kb_chain_factor(KfParams q) {
     for (int j = 0; j < NB; ++j) a[j] = zmake(0.0, 0.0);
 
     // the middle node needs the last node of the other chain
-    if (group == 0 && s == mid && mid < P - 1) kf_wait(done1, 1u, q.err);
+    if (group == 0 && s == mid && mid < P - 1) kf_wait(done1, 1u, q.err, q.wait_ns);
 
     // ---- Schur block, strip-wise:  S = D_p - C_pq M_q C_qp  (one or two eliminated neighbours)
     if (active) {
@@ -299,14 +304,16 @@ __global__ void __launch_bounds__(MAXT, 1) kb_chain_factor(KfParams q) {
     KF_TICK(0);
 
     // ---- blocked Gauss-Jordan with IMPLICIT row pivoting, one step per strip.  A row never
-    //      moves: thread t keeps original row t; `isfree` says whether it has been a pivot yet,
+    //      moves: thread t keeps original row t; `mycol` < 0 says it has not been a pivot yet,
     //      `mycol` which column it pivoted.  (tests/strip_gj_model.py)
     if (active) {
-      bool isfree = t < b;
-      int mycol = 0;
+      int mycol = t < b ? -1 : 0;  // column this row has pivoted; -1: the row is still free
+      // thread 0 reads the ring counter of this CTA's own strip one step ahead (sh.bp_seen)
+      if (q.Sbuf[group] && t == 0 && c == 0) sh.bp_seen = kf_ld_acquire(cons + 0);
       for (int k = 0; k < K; ++k) {
         const int k0 = k * w;
         const int wk = min(w, b - k0);
+        if (q.Sbuf[group] && t == 0 && k + 1 == c) sh.bp_seen = kf_ld_acquire(cons + (c & (KF_RING - 1)) * 32);
         if (k == c) {
           // ================= panel: this CTA's own strip =================
           // Two block barriers per column: (1) every warp has published the key of its best
@@ -316,11 +323,20 @@ __global__ void __launch_bounds__(MAXT, 1) kb_chain_factor(KfParams q) {
           // critical path.
           double rinv;
           // column stream of this strip: slot of this row, tag of column 0 with pivot code 0
-          double* sput = q.Sbuf[group] ? q.Sbuf[group] + 4 * ((size_t)((k & 1) * NB) * ldg + t) : nullptr;
+          double* sput = q.Sbuf[group] ? q.Sbuf[group] + 4 * ((size_t)((k & (KF_RING - 1)) * NB) * ldg + t) : nullptr;
+          // Back-pressure: strip k reuses the ring slot of strip k - KF_RING; nothing is stored
+          // before every consumer of that strip has released the slot.  The counter was read
+          // one step ago (bp_seen), so in the normal case this is one compare; thread 0 holds
+          // the CTA at the first barrier of the panel otherwise.
+          if (sput && t == 0) {
+            const unsigned need = sh.consbase[k & (KF_RING - 1)] + (unsigned)(K - 1) * (unsigned)(k / KF_RING);
+            if (sh.bp_seen < need)
+              kf_spin_until(cons + (k & (KF_RING - 1)) * 32, need, q.err, KB_WERR_BACKPRESSURE, q.wait_ns);
+          }
           const double stag = (double)((colbase + k0 + 1) * 1024);
           {
             const double m2 = zabs2(a[0]);
-            const unsigned key = isfree ? (unsigned)__double2hiint(m2) + 1u : 0u;
+            const unsigned key = mycol < 0 ? (unsigned)__double2hiint(m2) + 1u : 0u;
             const unsigned wmax = __reduce_max_sync(0xffffffffu, key);
             const unsigned wlo = __reduce_max_sync(0xffffffffu, (key == wmax) ? ~(unsigned)t : 0u);
             if (lane == 0) sh.candkey[0][wid] = wmax ? (((unsigned long long)wmax << 32) | wlo) : 0ull;
@@ -386,7 +402,7 @@ __global__ void __launch_bounds__(MAXT, 1) kb_chain_factor(KfParams q) {
                 KF_UPD(cc + 1);
                 if (cc + 1 < wk) {
                   const double m2 = zabs2(a[cc + 1]);
-                  const unsigned key = (isfree && !isp) ? (unsigned)__double2hiint(m2) + 1u : 0u;
+                  const unsigned key = (mycol < 0 && !isp) ? (unsigned)__double2hiint(m2) + 1u : 0u;
                   const unsigned wmax = __reduce_max_sync(0xffffffffu, key);
                   const unsigned wlo = __reduce_max_sync(0xffffffffu, (key == wmax) ? ~(unsigned)t : 0u);
                   if (lane == 0) sh.candkey[par ^ 1][wid] = wmax ? (((unsigned long long)wmax << 32) | wlo) : 0ull;
@@ -398,10 +414,7 @@ __global__ void __launch_bounds__(MAXT, 1) kb_chain_factor(KfParams q) {
                 if (j != cc && j != cc + 1) KF_UPD(j);
 #undef KF_UPD
               if (!broken) a[cc] = mult;  // -g, or 1/pivot on the pivot row
-              if (isp) {
-                isfree = false;
-                mycol = gk;
-              }
+              if (isp) mycol = gk;
               KF_TICK(11);
             }
           }
@@ -427,7 +440,7 @@ __global__ void __launch_bounds__(MAXT, 1) kb_chain_factor(KfParams q) {
           // else finds the columns already there.  Polls go out three columns at a time, so a
           // CTA that is catching up pays one round trip per three columns.
           KF_TICK(2);
-          const double* sbase = q.Sbuf[group] + 4 * ((size_t)((k & 1) * NB) * ldg + t);
+          const double* sbase = q.Sbuf[group] + 4 * ((size_t)((k & (KF_RING - 1)) * NB) * ldg + t);
           const double tag0 = (double)((colbase + k0 + 1) * 1024);
 #pragma unroll
           for (int c3 = 0; c3 < NB; c3 += 3) {
@@ -450,17 +463,23 @@ __global__ void __launch_bounds__(MAXT, 1) kb_chain_factor(KfParams q) {
                 int rp = -1;
                 double2 sv = zmake(re[u], im[u]);
                 if (t < b) {
-                  if (t0[u] == t1[u] && t0[u] >= tb && t0[u] < tb + 1024.0)
-                    rp = (int)(t0[u] - tb) - 1;
-                  else
-                    sv = kf_stream_get(sbase + 4 * (size_t)cc * ldg, tb, rp, q.err);
+                  if (!(t0[u] == t1[u] && t0[u] >= tb && t0[u] < tb + 1024.0)) {
+                    const double* ep = sbase + 4 * (size_t)cc * ldg;
+                    kf_stream_wait(ep, tb, q.err, q.wait_ns);
+                    asm volatile("ld.relaxed.gpu.global.v4.f64 {%0, %1, %2, %3}, [%4];"
+                                 : "=d"(re[u]), "=d"(t0[u]), "=d"(im[u]), "=d"(t1[u])
+                                 : "l"(ep)
+                                 : "memory");
+                    sv = zmake(re[u], im[u]);
+                  }
+                  // (no match after the wait: the launch has failed; the column is skipped)
+                  if (t0[u] == t1[u] && t0[u] >= tb && t0[u] < tb + 1024.0) rp = (int)(t0[u] - tb) - 1;
                 }
                 const bool isp = (t < b) && (t == rp);
                 if (isp) {
 #pragma unroll
                   for (int j = 0; j < NB; ++j) sh.prow[cc & 1][j] = a[j];
                   s_orig[k0 + cc] = rp;
-                  isfree = false;
                   mycol = k0 + cc;
                 }
                 if (t == 0 && rp < 0) s_orig[k0 + cc] = 0;  // skipped column (singular block)
@@ -480,11 +499,14 @@ __global__ void __launch_bounds__(MAXT, 1) kb_chain_factor(KfParams q) {
               }
             }
           }
+          // every thread of the CTA had its elements of strip k in registers before it passed the
+          // last barrier above: the ring slot may be rewritten as far as this CTA is concerned
+          if (t == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cons + (k & (KF_RING - 1)) * 32) : "memory");
           KF_TICK(3);
         } else {
           // ================= consumer: apply step k to this strip =================
           //   A[i,:] <- (i is a pivot row of the step ? 0 : A[i,:]) + sum_c G[i,c] A[piv_c,:]
-          kf_wait(pub, pubbase + (unsigned)k + 1u, q.err);
+          kf_wait(pub, pubbase + (unsigned)k + 1u, q.err, q.wait_ns);
           // the owner of the next strip is on the critical path: it reads G_k from an idle L2
           if (q.stagger_ns > 0 && c != k + 1) __nanosleep((unsigned)q.stagger_ns);
           KF_TICK(2);
@@ -507,7 +529,6 @@ __global__ void __launch_bounds__(MAXT, 1) kb_chain_factor(KfParams q) {
           for (int cc = 0; cc < NB; ++cc) {
             if (cc < wk && pv[cc] == t) {
               isp = true;
-              isfree = false;
               mycol = k0 + cc;
 #pragma unroll
               for (int j = 0; j < NB; ++j) sh.slots[par][cc][j] = a[j];
@@ -553,7 +574,11 @@ __global__ void __launch_bounds__(MAXT, 1) kb_chain_factor(KfParams q) {
     pubbase += (unsigned)K;
     colbase += b;
     barcount += (unsigned)Gc;
-    kf_group_barrier(bar, barcount, q.err);
+    // releases of this node, per ring slot: K - 1 consumers for every strip k = slot (mod KF_RING)
+    if (t == 0 && q.Sbuf[group])
+      for (int j = 0; j < KF_RING; ++j)
+        if (j < K) sh.consbase[j] += (unsigned)(K - 1) * (unsigned)((K - j + KF_RING - 1) / KF_RING);
+    kf_group_barrier(bar, barcount, q.err, q.wait_ns);
     KF_TICK(4);
   }
   if (group == 1 && c == 0 && t == 0 && S > 0) kf_st_release(done1, 1u);
@@ -616,8 +641,8 @@ int kbi_chainfac_run(kb_context* h, bool two_sided, bool transposed) {
   KB_CUDA(h, h->d_kfG.alloc((size_t)ngroups * bmax * bmax));
   const int64_t maxsteps = (bmax + KF_WMIN - 1) / KF_WMIN + 1;
   KB_CUDA(h, h->d_kfpiv.alloc((size_t)ngroups * maxsteps * 16));
-  KB_CUDA(h, h->d_kfsync.alloc(192));
-  KB_CUDA(h, cudaMemsetAsync(h->d_kfsync.p, 0, 192 * sizeof(unsigned), s));
+  KB_CUDA(h, h->d_kfsync.alloc(KF_SYNC_WORDS));
+  KB_CUDA(h, cudaMemsetAsync(h->d_kfsync.p, 0, KF_SYNC_WORDS * sizeof(unsigned), s));
   KB_CUDA(h, h->d_info.alloc(1));
   KB_CUDA(h, cudaMemsetAsync(h->d_info.p, 0, sizeof(int), s));
   q.Gbuf[0] = h->d_kfG.p;
@@ -626,7 +651,8 @@ int kbi_chainfac_run(kb_context* h, bool two_sided, bool transposed) {
   q.pivbuf[1] = two_sided ? h->d_kfpiv.p + maxsteps * 16 : h->d_kfpiv.p;
   q.sync = h->d_kfsync.p;
   q.info = h->d_info.p;
-  q.err = (int*)(h->d_kfsync.p + 190);  // word 190 of the sync block: time-out flag
+  q.err = (int*)(h->d_kfsync.p + KF_ERR_WORD);  // time-out flag
+  q.wait_ns = h->wait_ns;
   q.dbg = nullptr;
   if (getenv("KB_SWEEP_TIMING")) {
     KB_CUDA(h, h->d_sweep_timing.alloc(256 * 16));
@@ -638,7 +664,7 @@ int kbi_chainfac_run(kb_context* h, bool two_sided, bool transposed) {
   q.transposed = transposed ? 1 : 0;
   q.Sbuf[0] = q.Sbuf[1] = nullptr;
   if (!getenv("KB_CHAINFAC_NOSTREAM")) {
-    const size_t per = (size_t)2 * KF_NB_WIDE * bmax * 4;  // doubles per group
+    const size_t per = (size_t)KF_RING * KF_NB_WIDE * bmax * 4;  // doubles per group
     KB_CUDA(h, h->d_kfstream.alloc((size_t)ngroups * per));
     KB_CUDA(h, cudaMemsetAsync(h->d_kfstream.p, 0, (size_t)ngroups * per * sizeof(double), s));
     q.Sbuf[0] = h->d_kfstream.p;

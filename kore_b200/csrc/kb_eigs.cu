@@ -144,6 +144,28 @@ kb_restart_update(int n, int mq, int q, double2* __restrict__ V, int64_t ldv, co
   }
 }
 
+// The same with Q read through the read-only cache (basis sizes whose Q does not fit shared memory
+// next to the row block: ncv beyond ~90)
+__global__ void __launch_bounds__(256)
+kb_restart_update_gq(int n, int mq, int q, double2* __restrict__ V, int64_t ldv, const double2* __restrict__ Q) {
+  extern __shared__ double2 sm[];
+  double2* vs = sm;  // KB_RS_ROWS x mq (row-major, padded)
+  const int i0 = blockIdx.x * KB_RS_ROWS;
+  const int len = min(KB_RS_ROWS, n - i0);
+  for (int e = threadIdx.x; e < mq * KB_RS_ROWS; e += blockDim.x) {
+    int c = e / KB_RS_ROWS, i = e % KB_RS_ROWS;
+    if (i < len) vs[i * (mq + 1) + c] = V[(size_t)c * ldv + i0 + i];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < q * KB_RS_ROWS; e += blockDim.x) {
+    int c = e / KB_RS_ROWS, i = e % KB_RS_ROWS;
+    if (i >= len) continue;
+    double2 acc = zmake(0.0, 0.0);
+    for (int k = 0; k < mq; ++k) zfma(acc, vs[i * (mq + 1) + k], __ldg(&Q[(size_t)c * mq + k]));
+    V[(size_t)c * ldv + i0 + i] = acc;
+  }
+}
+
 // partial sums for residuals: out[3*b+0] = |ax - lam bx|^2, +1 = |bx|^2, +2 = |x|^2
 __global__ void kb_resid_partial(int n, const double2* __restrict__ ax, const double2* __restrict__ bx,
                                  const double2* __restrict__ x, double2 lam, double* __restrict__ out) {
@@ -235,6 +257,22 @@ struct Krylov {
   }
 };
 
+// V[:, 0:q] <- V[:, 0:mq] Q on the device (Q mq x q column-major, already uploaded)
+int restart_update(kb_context* h, int n, int mq, int q, double2* V, int64_t ldv, const double2* Qdev) {
+  const size_t smem_full = (size_t)(KB_RS_ROWS * (mq + 1) + mq * q) * sizeof(double2);
+  const size_t smem_rows = (size_t)(KB_RS_ROWS * (mq + 1)) * sizeof(double2);
+  if (smem_full <= 200 * 1024) {
+    KB_CUDA(h, cudaFuncSetAttribute(kb_restart_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    kb_restart_update<<<nblk(n, KB_RS_ROWS), 256, smem_full, h->stream>>>(n, mq, q, V, ldv, Qdev);
+  } else {
+    KB_CUDA(h, cudaFuncSetAttribute(kb_restart_update_gq, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    kb_restart_update_gq<<<nblk(n, KB_RS_ROWS), 256, smem_rows, h->stream>>>(n, mq, q, V, ldv, Qdev);
+  }
+  h->launches++;
+  KB_LAUNCH_CHECK(h);
+  return KB_OK;
+}
+
 int normalize_dev(kb_context* h, int n, double2* v, double* normpart, double* beta_dev, int nblocks) {
   // v <- v / ||v||
   cudaStream_t s = h->stream;
@@ -248,10 +286,31 @@ int normalize_dev(kb_context* h, int n, double2* v, double* normpart, double* be
 
 }  // namespace
 
+// SLEPc's default basis size max(2 nev, nev + 15) stays within KB_MAX_NCV for nev <= 63
+// (the coefficient vectors of kb_multiaxpy / kb_lincomb live in 128-entry shared arrays).
+#define KB_MAX_NCV 127
+
+static int eigs_impl(kb_handle h, int nev, int ncv, double tol, int maxit, int which,
+                     const double* target, int true_residual, const double* v0, int max_pairs,
+                     double* evals, double* evecs, int* nconv_out, int* its_out, double* resid);
+
 extern "C" int kb_eigs(kb_handle h, int nev, int ncv, double tol, int maxit, int which,
                        const double* target, int true_residual, const double* v0, int max_pairs,
                        double* evals, double* evecs, int* nconv_out, int* its_out, double* resid) {
   if (!h || !evals || !nconv_out) return KB_EINVAL;
+  // a chain sweep whose device-side wait expired sends the handle to safe mode (refactored with
+  // the per-node kernels); the eigensolve is then repeated from its start vector, once
+  int rc = eigs_impl(h, nev, ncv, tol, maxit, which, target, true_residual, v0, max_pairs, evals, evecs, nconv_out,
+                     its_out, resid);
+  if (rc == KB_EPROTOCOL_RETRY)
+    rc = eigs_impl(h, nev, ncv, tol, maxit, which, target, true_residual, v0, max_pairs, evals, evecs, nconv_out,
+                   its_out, resid);
+  return rc == KB_EPROTOCOL_RETRY ? kb_fail(h, KB_ECUDA, "chain sweep failed twice") : rc;
+}
+
+static int eigs_impl(kb_handle h, int nev, int ncv, double tol, int maxit, int which,
+                     const double* target, int true_residual, const double* v0, int max_pairs,
+                     double* evals, double* evecs, int* nconv_out, int* its_out, double* resid) {
   if (!h->factored) return kb_fail(h, KB_EINVAL, "kb_factor must succeed before kb_eigs");
   if (!h->B.present) return kb_fail(h, KB_EINVAL, "kb_eigs needs a B matrix");
   if (which < KB_WHICH_LM || which > KB_WHICH_TI) return kb_fail(h, KB_EINVAL, "bad `which`");
@@ -260,7 +319,9 @@ extern "C" int kb_eigs(kb_handle h, int nev, int ncv, double tol, int maxit, int
   const int n = (int)h->n;
   if (ncv <= 0) ncv = std::max(2 * nev, nev + 15);
   if (ncv > n) ncv = n;
-  if (ncv > 64) return kb_fail(h, KB_EINVAL, "ncv > 64 is not supported");
+  if (ncv > KB_MAX_NCV)
+    return kb_fail(h, KB_EINVAL, "ncv = %d exceeds the supported basis size %d (nev <= 63 with SLEPc's default ncv)",
+                   ncv, KB_MAX_NCV);
   if (nev >= ncv) return kb_fail(h, KB_EINVAL, "nev must be < ncv");
   if (maxit < 1) maxit = 1;
   const Z tau = target ? Z(target[0], target[1]) : h->sigma;
@@ -268,10 +329,9 @@ extern "C" int kb_eigs(kb_handle h, int nev, int ncv, double tol, int maxit, int
   cudaStream_t s = h->stream;
   const int m = ncv;
 
-  cudaEvent_t e0, e1;
-  KB_CUDA(h, cudaEventCreate(&e0));
-  KB_CUDA(h, cudaEventCreate(&e1));
-  KB_CUDA(h, cudaEventRecord(e0, s));
+  KbEventPair ev;
+  KB_CUDA(h, ev.create());
+  KB_CUDA(h, cudaEventRecord(ev.e0, s));
   h->stats.op_applies = 0;
   h->stats.solve_calls = 0;
   h->stats.eigs_solve_ms = 0.0;
@@ -312,9 +372,17 @@ extern "C" int kb_eigs(kb_handle h, int nev, int ncv, double tol, int maxit, int
   K.Qdev = h->d_Q.p;
   K.normpart = d_normpart.p;
   K.beta_dev = d_beta.p;
-  // pinned mirrors live on the context (65 x 65 entries cover every supported ncv)
-  if (!h->pinned_h) KB_CUDA(h, cudaMallocHost((void**)&h->pinned_h, (size_t)66 * 66 * sizeof(double2)));
-  if (!h->pinned_beta) KB_CUDA(h, cudaMallocHost((void**)&h->pinned_beta, 66 * sizeof(double)));
+  // pinned mirrors live on the context, sized for the largest ncv seen
+  if (h->pinned_ncv < ncv) {
+    if (h->pinned_h) cudaFreeHost(h->pinned_h);
+    if (h->pinned_beta) cudaFreeHost(h->pinned_beta);
+    h->pinned_h = h->pinned_beta = nullptr;
+    h->pinned_ncv = 0;
+    KB_CUDA(h, cudaMallocHost((void**)&h->pinned_h, (size_t)(ncv + 2) * (ncv + 2) * sizeof(double2)));
+    KB_CUDA(h, cudaMallocHost((void**)&h->pinned_beta, (size_t)(ncv + 2) * sizeof(double)));
+    h->pinned_ncv = ncv;
+  }
+  if (!h->pinned_err) KB_CUDA(h, cudaMallocHost((void**)&h->pinned_err, sizeof(int)));
   K.h_host = (double2*)h->pinned_h;
   K.beta_host = (double*)h->pinned_beta;
 
@@ -354,7 +422,13 @@ extern "C" int kb_eigs(kb_handle h, int nev, int ncv, double tol, int maxit, int
       KB_TRY(K.arnoldi_step(j, h->opt_refine_eigs));
       h->stats.op_applies++;
     }
-    KB_CUDA(h, cudaStreamSynchronize(s));
+    // the sweep error flag travels with the projected matrix: a failed exchange is seen after
+    // one restart at the latest, not after maxit restarts of garbage
+    *h->pinned_err = 0;
+    if (h->d_sweep_err.p)
+      KB_CUDA(h, cudaMemcpyAsync(h->pinned_err, h->d_sweep_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    KB_TRY(kbi_sync(h));
+    if (*h->pinned_err != 0) return kbi_enter_safe_mode(h, "sweep", *h->pinned_err);
     for (int j = k; j < m; ++j) {
       for (int i = 0; i <= j; ++i) {
         double2 v = K.h_host[(size_t)j * (ncv + 1) + i];
@@ -455,12 +529,8 @@ extern "C" int kb_eigs(kb_handle h, int nev, int ncv, double tol, int maxit, int
       for (int j = 0; j < q; ++j)
         for (int i = 0; i < na; ++i) qh[(size_t)j * na + i] = zmake(Q(i, j).real(), Q(i, j).imag());
       KB_CUDA(h, cudaMemcpyAsync(K.Qdev, qh.data(), qh.size() * sizeof(double2), cudaMemcpyHostToDevice, s));
-      size_t smem = (size_t)(KB_RS_ROWS * (na + 1) + na * q) * sizeof(double2);
-      KB_CUDA(h, cudaFuncSetAttribute(kb_restart_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      kb_restart_update<<<nblk(n, KB_RS_ROWS), 256, smem, s>>>(n, na, q, K.col(nconv), K.ldv, K.Qdev);
+      KB_TRY(restart_update(h, n, na, q, K.col(nconv), K.ldv, K.Qdev));
       KB_CUDA(h, cudaMemcpyAsync(K.col(newk), K.col(m), (size_t)n * sizeof(double2), cudaMemcpyDeviceToDevice, s));
-      h->launches += 1;
-      KB_LAUNCH_CHECK(h);
       KB_CUDA(h, cudaStreamSynchronize(s));
     }
     for (int j = 0; j < m; ++j)
@@ -479,11 +549,7 @@ extern "C" int kb_eigs(kb_handle h, int nev, int ncv, double tol, int maxit, int
     for (int j = 0; j < na; ++j)
       for (int i = 0; i < na; ++i) qh[(size_t)j * na + i] = zmake(Qlast(i, j).real(), Qlast(i, j).imag());
     KB_CUDA(h, cudaMemcpyAsync(K.Qdev, qh.data(), qh.size() * sizeof(double2), cudaMemcpyHostToDevice, s));
-    size_t smem = (size_t)(KB_RS_ROWS * (na + 1) + na * na) * sizeof(double2);
-    KB_CUDA(h, cudaFuncSetAttribute(kb_restart_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    kb_restart_update<<<nblk(n, KB_RS_ROWS), 256, smem, s>>>(n, na, na, K.col(nconv_before_last), K.ldv, K.Qdev);
-    h->launches++;
-    KB_LAUNCH_CHECK(h);
+    KB_TRY(restart_update(h, n, na, na, K.col(nconv_before_last), K.ldv, K.Qdev));
     KB_CUDA(h, cudaStreamSynchronize(s));
   }
 
@@ -538,13 +604,9 @@ extern "C" int kb_eigs(kb_handle h, int nev, int ncv, double tol, int maxit, int
   }
   *nconv_out = nret;
   if (its_out) *its_out = its;
-  KB_CUDA(h, cudaEventRecord(e1, s));
-  KB_CUDA(h, cudaStreamSynchronize(s));
-  float ms = 0.f;
-  cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  h->stats.eigs_ms = ms;
+  KB_CUDA(h, cudaEventRecord(ev.e1, s));
+  KB_TRY(kbi_sync(h));
+  h->stats.eigs_ms = ev.ms();
   KB_TRY(kbi_check_sweep_error(h));
   for (size_t i = 0; i + 1 < h->sweep_events.size(); i += 2) {
     float t = 0.f;

@@ -739,10 +739,9 @@ int kbi_factor(kb_context* h, zcomplex sigma) {
   h->sigma = sigma;
   kbi_drop_graphs(h);
 
-  cudaEvent_t e0, e1;
-  KB_CUDA(h, cudaEventCreate(&e0));
-  KB_CUDA(h, cudaEventCreate(&e1));
-  KB_CUDA(h, cudaEventRecord(e0, s));
+  KbEventPair ev;
+  KB_CUDA(h, ev.create());
+  KB_CUDA(h, cudaEventRecord(ev.e0, s));
 
   KB_TRY(kbi_build_T(h, sigma));
 
@@ -847,22 +846,25 @@ int kbi_factor(kb_context* h, zcomplex sigma) {
   }
   KB_TRY(kbi_sweep_prepare(h));
   if (h->opt_fold) KB_TRY(kbi_fold_prepare(h));
-  KB_CUDA(h, cudaEventRecord(e1, s));
+  KB_CUDA(h, cudaEventRecord(ev.e1, s));
+  KB_TRY(kbi_sync(h));
   int info = 0;
-  KB_CUDA(h, cudaMemcpyAsync(&info, h->d_info.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-  KB_CUDA(h, cudaStreamSynchronize(s));
-  float ms = 0.f;
-  cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  h->stats.factor_ms = ms;
+  KB_CUDA(h, cudaMemcpy(&info, h->d_info.p, sizeof(int), cudaMemcpyDeviceToHost));
+  h->stats.factor_ms = ev.ms();
   h->stats.factor_flops = flops;
   h->stats.factor_bytes = h->Moff[P] * 16;
   if (chainfac) {
     int kerr = 0;
-    KB_CUDA(h, cudaMemcpy(&kerr, h->d_kfsync.p + 190, sizeof(int), cudaMemcpyDeviceToHost));
+    KB_CUDA(h, cudaMemcpy(&kerr, h->d_kfsync.p + KF_ERR_WORD, sizeof(int), cudaMemcpyDeviceToHost));
+    if (h->inject_fault == 2) {
+      kerr = KB_WERR_WATCHDOG;  // tests: as if a wait of the factorisation kernel had expired
+      h->inject_fault = 0;
+    }
     if (kerr != 0) {
-      return kb_fail(h, KB_ECUDA, "the persistent factorisation kernel timed out waiting on a peer CTA");
+      // a wait of the persistent kernel expired: the factors are garbage.  Per-step kernels from
+      // here on (kbi_enter_safe_mode refactors through this function with opt_factor = 0)
+      const int rc = kbi_enter_safe_mode(h, "factorisation", kerr);
+      return rc == KB_EPROTOCOL_RETRY ? KB_OK : rc;
     }
   }
   if (info != 0)

@@ -75,6 +75,54 @@ __device__ __forceinline__ double2 zinv_fast(double2 p) {
 // ---------------------------------------------------------------------------
 #define KB_SPIN_LIMIT (1 << 22)
 
+// Every device-side wait of the persistent kernels is bounded in TIME, not in polls, and gives up
+// at once when any other wait of the same launch has already failed (or the host watchdog has
+// raised the flag): a protocol failure ends the kernel within milliseconds of the first time-out
+// instead of paying one time-out per wait.  The flag word receives a code that says which wait
+// failed and where:  code | (blockIdx.x << 8).
+#define KF_ERR_WORD 190  // word of kb_context::d_kfsync that holds the factorisation kernel's flag
+#define KB_WAIT_NS_DEFAULT 4000000000ull  // 4 s: longer than any legitimate wait of any kernel here
+enum {
+  KB_WERR_GROUP_BARRIER = 1,  // kb_chainfac: end-of-node barrier of a chain group
+  KB_WERR_COUNTER = 2,        // kb_chainfac: step / chain counter
+  KB_WERR_STREAM = 3,         // kb_chainfac: tagged element of the column stream
+  KB_WERR_BACKPRESSURE = 4,   // kb_chainfac: consumers of the ring slot about to be rewritten
+  KB_WERR_GATHER = 5,         // folded sweep: entry of the next input vector
+  KB_WERR_XCHG = 6,           // folded sweep: cross-group entry of the middle node
+  KB_WERR_MBAR = 7,           // bulk (TMA) copy completion
+  KB_WERR_SWEEP = 8,          // row-split / one-hop sweeps (kb_sweep.cu, kb_sweep1.cu)
+  KB_WERR_WATCHDOG = 9        // raised by the host: kernel exceeded its deadline
+};
+
+__device__ __forceinline__ unsigned long long kb_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+struct KbSpin {
+  unsigned n = 0;
+  unsigned long long t0 = 0;
+};
+// true: stop waiting (the launch has failed, here or elsewhere).  Looks at the flag and the clock
+// after the first missed poll and then every 32 polls, so a wait that succeeds at once costs
+// nothing extra and a launch that has already failed drains at one missed poll per wait.
+__device__ __forceinline__ bool kb_spin_expired(KbSpin& s, int* err, int code, unsigned long long limit_ns) {
+  if ((++s.n & 31u) != 1u) return false;
+  if (*(volatile int*)err != 0) return true;
+  const unsigned long long now = kb_globaltimer();
+  if (s.t0 == 0) {
+    s.t0 = now;
+    return false;
+  }
+  if (now - s.t0 > limit_ns) {
+    atomicCAS(err, 0, code | ((int)blockIdx.x << 8));
+    return true;
+  }
+  return false;
+}
+__device__ __forceinline__ bool kb_launch_failed(const int* err) { return *(volatile const int*)err != 0; }
+
 // ---- mbarrier + 1-D bulk (TMA) copy helpers
 __device__ __forceinline__ unsigned kb_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void kb_mbar_init(uint64_t* bar, unsigned count) {
@@ -90,16 +138,20 @@ __device__ __forceinline__ void kb_bulk_g2s(void* dst, const void* src, unsigned
                "l"(src), "r"(bytes), "r"(kb_smem_addr(bar))
                : "memory");
 }
-__device__ __forceinline__ void kb_mbar_wait(uint64_t* bar, unsigned parity) {
+// Wait for the completion of a bulk copy.  A copy that never lands raises the launch's error flag
+// (the readers of the stage would otherwise consume whatever the stage held).
+__device__ __forceinline__ void kb_mbar_wait(uint64_t* bar, unsigned parity, int* err, unsigned long long limit_ns) {
   unsigned done = 0;
-  int spins = 0;
-  do {
+  KbSpin sp;
+  for (;;) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(kb_smem_addr(bar)), "r"(parity)
         : "memory");
-  } while (!done && ++spins < KB_SPIN_LIMIT);
+    if (done) break;
+    if (kb_spin_expired(sp, err, KB_WERR_MBAR, limit_ns)) break;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -188,6 +240,12 @@ struct kb_context {
   int64_t opt_seed = 1;
   int opt_panel = 0;
   int opt_factor = 1;  // 1: persistent strip kernel (kb_chainfac.cu) when the nodes fit, 0: per-step kernels
+  // Time bound of every device-side wait of the persistent kernels (KB_OPT_WAIT_MS).  A launch
+  // whose wait expires raises its error flag and drains; the host then switches the handle to the
+  // kernels without device-side waits (safe mode), refactors and repeats the call.
+  unsigned long long wait_ns = KB_WAIT_NS_DEFAULT;
+  bool safe_mode = false;
+  int inject_fault = 0;  // KB_OPT_INJECT_FAULT (tests): 1 = the next chain sweep, 2 = the next factorisation reports a time-out
 
   // pencil as given (host, original ordering)
   int64_t n = 0;
@@ -200,7 +258,7 @@ struct kb_context {
   int64_t P = 0;
   std::vector<int64_t> nodeptr;  // P+1
   std::vector<int64_t> perm;     // chain position -> original index
-  int64_t bmax = 0;
+  int64_t bmax = 0, bmin = 0;
 
   // device: permutation
   DevBuf<int> d_perm;  // n
@@ -280,6 +338,8 @@ struct kb_context {
 
   // solve workspaces (chain order, scaled space)
   DevBuf<double2> d_r, d_y, d_res, d_x0, d_in, d_out, d_t, d_t2, d_yf;
+  DevBuf<double2> d_io_a, d_io_b;  // staging of the host-pointer entry points
+  int64_t ws_n = -1;               // n the zero sentinels of d_y / d_x0 were written for
   DevBuf<double> d_partial;
 
   // Krylov workspaces
@@ -288,6 +348,10 @@ struct kb_context {
   DevBuf<double> d_normpart, d_beta;
   void* pinned_h = nullptr;
   void* pinned_beta = nullptr;
+  int pinned_ncv = 0;          // the pinned mirrors hold (pinned_ncv + 2)^2 / pinned_ncv + 2 entries
+  int* pinned_err = nullptr;   // host mirror of the sweep error flag, read back with every restart
+  cudaStream_t side_stream = nullptr;  // watchdog: raises the error flags while a kernel runs
+  double watchdog_ms = 0.0;    // 0: 3 x the device-side wait bound + 5 s
 
   // captured sweep graphs, keyed by the (rhs, solution) buffers
   struct SweepGraph {
@@ -323,6 +387,28 @@ struct kb_context {
 
 static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
+// A pair of timing events that cannot leak on an early return.
+struct KbEventPair {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  KbEventPair() {}
+  KbEventPair(const KbEventPair&) = delete;
+  KbEventPair& operator=(const KbEventPair&) = delete;
+  ~KbEventPair() {
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+  }
+  cudaError_t create() {
+    cudaError_t e = cudaEventCreate(&e0);
+    if (e != cudaSuccess) return e;
+    return cudaEventCreate(&e1);
+  }
+  float ms() const {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, e0, e1);
+    return t;
+  }
+};
+
 // ---- kb_factor.cu
 int kbi_factor(kb_context* h, zcomplex sigma);
 int kbi_build_T(kb_context* h, zcomplex sigma);
@@ -346,6 +432,14 @@ int kbi_to_chain(kb_context* h, const double2* x_orig_dev, double2* x_chain_dev)
 int kbi_from_chain(kb_context* h, const double2* x_chain_dev, double2* x_orig_dev);
 int kbi_solve_workspace(kb_context* h);
 int kbi_check_sweep_error(kb_context* h);
+// cudaStreamSynchronize(h->stream) with a deadline: a kernel that outlives it has the error flags
+// of the persistent kernels raised from a side stream (every device-side wait then gives up) and
+// the call fails with KB_ECUDA once the stream has drained
+int kbi_sync(kb_context* h);
+int kbi_enter_safe_mode(kb_context* h, const char* what, int wait_code);
+// internal return code: a persistent kernel reported a protocol time-out and the handle has been
+// switched to safe mode and refactored; the caller repeats its operation
+#define KB_EPROTOCOL_RETRY 1000
 void kbi_drop_graphs(kb_context* h);
 // ---- kb_sweep.cu
 int kbi_sweep_prepare(kb_context* h);
@@ -355,6 +449,7 @@ int kbi_sweep_dataflow(kb_context* h, const double2* r, double2* y);
 bool kbi_onehop_supported(const kb_context* h, int G, bool two_sided, int* slice_elems_out, size_t* smem_out);
 int kbi_sweep_onehop(kb_context* h, const double2* r, double2* y);
 // ---- kb_sweep2.cu
+int kbi_fold_grid(const kb_context* h, bool two_sided);
 bool kbi_fold_supported(const kb_context* h, int G, bool two_sided, int* slice_elems_out, size_t* smem_out);
 int kbi_fold_prepare(kb_context* h);
 int kbi_sweep_fold(kb_context* h, const double2* r, double2* y);

@@ -88,7 +88,7 @@ __global__ void kl_scatter(int64_t N, int n, const unsigned long long* __restric
     col[k] = c;
     atomicAdd(&rowcnt[row], 1);
     const int d = node_of[c] - node_of[row];
-    if (d > 1 || d < -1) atomicExch(bad, 3);
+    if (d > 1 || d < -1) atomicMax(bad, 3);
     // the A entries of the run (normally one), summed in order: deterministic
     double2 acc = make_double2(0.0, 0.0);
     for (int64_t j = i; j < N && keys[j] == key; ++j) {
@@ -103,6 +103,9 @@ __global__ void kl_scatter(int64_t N, int n, const unsigned long long* __restric
   }
   const unsigned pl = payload[i];
   if (pl >> 31) {
+    // kb_sub_sigma_B gives every B entry its own read-modify-write of its union slot: two B entries
+    // of one (row, column) would race there
+    if (i > 0 && keys[i - 1] == key && (payload[i - 1] >> 31)) atomicMax(bad, 4);
     const int kb = bscan[i];
     bcol[kb] = c;
     bmap[kb] = k;
@@ -429,6 +432,10 @@ int kbi_layout_device(kb_context* h) {
   KB_CUDA(h, h->d_maxbits.alloc(n));
   KB_CUDA(h, cudaStreamSynchronize(s));
   KB_LAUNCH_CHECK(h);
+  if (hbad == 4)
+    return kb_fail(h, KB_EINVAL,
+                   "B holds more than one entry for some (row, column): sum the duplicates first "
+                   "(scipy: B.sum_duplicates())");
   if (hbad == 3)
     return kb_fail(h, KB_ESTRUCTURE,
                    "pencil is not block tridiagonal under the given chain (a nonzero couples nodes "

@@ -79,6 +79,8 @@ extern "C" int kb_destroy(kb_handle h) {
   kbi_drop_graphs(h);
   if (h->pinned_h) cudaFreeHost(h->pinned_h);
   if (h->pinned_beta) cudaFreeHost(h->pinned_beta);
+  if (h->pinned_err) cudaFreeHost(h->pinned_err);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
   delete h;
   return KB_OK;
 }
@@ -96,10 +98,27 @@ extern "C" int kb_set_option(kb_handle h, int option, int64_t value) {
     case KB_OPT_PURIFY: h->opt_purify = value != 0; break;
     case KB_OPT_SEED: h->opt_seed = value; break;
     case KB_OPT_PANEL: h->opt_panel = (int)value; break;
-    case 6: h->opt_refine_eigs = (int)std::max<int64_t>(0, value); break;
-    case 7: h->opt_sweep = (int)value; break;
-    case 8: h->opt_factor = (int)value; break;
-    case 9: h->opt_fold = (int)value; break;
+    case KB_OPT_REFINE_EIGS: h->opt_refine_eigs = (int)std::max<int64_t>(0, value); break;
+    // The factors are laid out for the sweep that will read them (two-sided or one-sided,
+    // transposed or row-major, folded couplings or not): changing any of these invalidates them.
+    case KB_OPT_SWEEP:
+      if (value < 0 || value > 2) return kb_fail(h, KB_EINVAL, "KB_OPT_SWEEP must be 0, 1 or 2");
+      if (h->opt_sweep != (int)value) h->factored = false;
+      h->opt_sweep = (int)value;
+      break;
+    case KB_OPT_FACTOR:
+      if (h->opt_factor != (int)(value != 0)) h->factored = false;
+      h->opt_factor = value != 0;
+      break;
+    case KB_OPT_FOLD:
+      if (h->opt_fold != (int)(value != 0)) h->factored = false;
+      h->opt_fold = value != 0;
+      break;
+    case KB_OPT_WAIT_MS:
+      if (value < 1) return kb_fail(h, KB_EINVAL, "KB_OPT_WAIT_MS must be >= 1");
+      h->wait_ns = (unsigned long long)value * 1000000ull;
+      break;
+    case KB_OPT_INJECT_FAULT: h->inject_fault = (int)value; break;
     default: return kb_fail(h, KB_EINVAL, "unknown option %d", option);
   }
   return KB_OK;
@@ -249,10 +268,12 @@ extern "C" int kb_set_chain(kb_handle h, const int64_t* perm, const int64_t* nod
   h->nodeptr.assign(nodeptr, nodeptr + nnodes + 1);
   h->perm.assign(perm, perm + n);
   h->bmax = 0;
+  h->bmin = n;
   for (int64_t p = 0; p < nnodes; ++p) {
     int64_t b = nodeptr[p + 1] - nodeptr[p];
     if (b <= 0) return kb_fail(h, KB_EINVAL, "empty chain node %lld", (long long)p);
     h->bmax = std::max(h->bmax, b);
+    h->bmin = std::min(h->bmin, b);
   }
   if (h->rawA.present) {
     KB_TRY(kbi_layout_device(h));

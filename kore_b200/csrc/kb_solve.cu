@@ -10,6 +10,10 @@
 // Both sweeps are HBM-bound: each reads every explicit inverse M_p once
 // (16 b_p^2 bytes per node per sweep).
 #include <math.h>
+#include <stdio.h>
+
+#include <chrono>
+#include <thread>
 
 #include "kb_internal.cuh"
 
@@ -214,6 +218,12 @@ void kbi_drop_graphs(kb_context* h) {
 static int chain_sweeps(kb_context* h, const double2* r, double2* y) {
   cudaStream_t s = h->stream;
   if (h->nranks > 1) return kbi_sharded_sweeps(h, r, y);
+  if (h->inject_fault == 1 && h->d_sweep_err.p) {
+    // tests: behave as if a wait of this sweep had expired (every wait of the launch gives up)
+    static const int code = KB_WERR_WATCHDOG;
+    KB_CUDA(h, cudaMemcpyAsync(h->d_sweep_err.p, &code, sizeof(int), cudaMemcpyHostToDevice, s));
+    h->inject_fault = 0;
+  }
   if (h->fold_ready) return kbi_sweep_fold(h, r, y);
   if (h->M_transposed) return kbi_sweep_onehop(h, r, y);
   if (h->opt_sweep == 1 && h->sweep_grid > 0) return kbi_sweep_dataflow(h, r, y);
@@ -244,29 +254,83 @@ static int chain_sweeps(kb_context* h, const double2* r, double2* y) {
   return KB_OK;
 }
 
+// Switch the handle to the kernels that have no device-side waits (one kernel pair per node for
+// the sweeps, per-step kernels for the factorisation), refactor at the current shift and tell the
+// caller to repeat its operation.  Reached when a wait of a persistent kernel has expired
+// (wait_code says which, kb_internal.cuh) or the host watchdog has fired; never in a healthy run.
+int kbi_enter_safe_mode(kb_context* h, const char* what, int wait_code) {
+  h->stats.protocol_fallbacks++;
+  h->stats.wait_error = wait_code;
+  fprintf(stderr,
+          "libkoreb200: WARNING: a device-side wait of the persistent %s kernel expired (code %d, CTA %d); "
+          "falling back to the per-node kernels for this handle and repeating the call\n",
+          what, wait_code & 255, wait_code >> 8);
+  if (h->safe_mode)
+    return kb_fail(h, KB_ECUDA, "persistent-kernel time-out reported in safe mode (code %d)", wait_code);
+  h->safe_mode = true;
+  h->opt_factor = 0;
+  h->opt_sweep = 0;
+  h->opt_fold = 0;
+  if (h->d_sweep_err.p) KB_CUDA(h, cudaMemsetAsync(h->d_sweep_err.p, 0, sizeof(int), h->stream));
+  const bool was_factored = h->factored || what[0] == 'f';
+  h->factored = false;
+  if (was_factored) KB_TRY(kbi_factor(h, h->sigma));
+  return KB_EPROTOCOL_RETRY;
+}
+
+int kbi_sync(kb_context* h) {
+  cudaStream_t s = h->stream;
+  cudaError_t q = cudaStreamQuery(s);
+  if (q == cudaSuccess) return KB_OK;
+  const double limit_ms = h->watchdog_ms > 0.0 ? h->watchdog_ms : 3.0 * (double)h->wait_ns * 1e-6 + 5000.0;
+  for (int phase = 0; phase < 2; ++phase) {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+      q = cudaStreamQuery(s);
+      if (q == cudaSuccess) return KB_OK;
+      if (q != cudaErrorNotReady)
+        return kb_fail(h, KB_ECUDA, "stream failed: %s", cudaGetErrorString(q));
+      const double el = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      if (el > limit_ms) break;
+      if (el > 1.0) std::this_thread::sleep_for(std::chrono::microseconds(el > 50.0 ? 200 : 40));
+    }
+    if (phase == 1) break;
+    // deadline: raise the flags every device-side wait looks at, from a side stream
+    fprintf(stderr, "libkoreb200: WARNING: kernel still running after %.0f ms; watchdog raises the abort flags\n",
+            limit_ms);
+    if (!h->side_stream) KB_CUDA(h, cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+    static const int code = KB_WERR_WATCHDOG;
+    if (h->d_sweep_err.p)
+      KB_CUDA(h, cudaMemcpyAsync(h->d_sweep_err.p, &code, sizeof(int), cudaMemcpyHostToDevice, h->side_stream));
+    if (h->d_kfsync.p && h->d_kfsync.count > KF_ERR_WORD)
+      KB_CUDA(h, cudaMemcpyAsync(h->d_kfsync.p + KF_ERR_WORD, &code, sizeof(int), cudaMemcpyHostToDevice,
+                                 h->side_stream));
+    KB_CUDA(h, cudaStreamSynchronize(h->side_stream));
+  }
+  return kb_fail(h, KB_ECUDA, "a kernel does not react to the watchdog flag; the device needs a reset");
+}
+
+// Call after kbi_sync.  A raised flag means some chain sweep since the last check produced
+// garbage: the handle goes to safe mode and the caller repeats (KB_EPROTOCOL_RETRY).
 int kbi_check_sweep_error(kb_context* h) {
-  // call after a stream synchronisation
   if (!h->d_sweep_err.p) return KB_OK;
   int e = 0;
   KB_CUDA(h, cudaMemcpy(&e, h->d_sweep_err.p, sizeof(int), cudaMemcpyDeviceToHost));
-  if (e) {
-    cudaMemset(h->d_sweep_err.p, 0, sizeof(int));
-    return kb_fail(h, KB_ECUDA, "grid barrier of the persistent sweep kernel timed out");
-  }
+  if (e) return kbi_enter_safe_mode(h, "sweep", e);
   return KB_OK;
 }
 
 int kbi_solve_workspace(kb_context* h) {
   const int64_t n = h->n;
   KB_CUDA(h, h->d_r.alloc(n));
-  // solution buffers carry a zero sentinel at [n] (padding target of the ELL couplings)
-  if (h->d_y.count < (size_t)n + 1) {
+  // solution buffers carry a zero sentinel at [n] (padding target of the ELL couplings); the
+  // buffers survive a change of pencil, so the sentinel is rewritten whenever n changes
+  if (h->d_y.count < (size_t)n + 1 || h->d_x0.count < (size_t)n + 1 || h->ws_n != n) {
     KB_CUDA(h, h->d_y.alloc(n + 1));
-    KB_CUDA(h, cudaMemsetAsync(h->d_y.p, 0, (size_t)(n + 1) * sizeof(double2), h->stream));
-  }
-  if (h->d_x0.count < (size_t)n + 1) {
     KB_CUDA(h, h->d_x0.alloc(n + 1));
+    KB_CUDA(h, cudaMemsetAsync(h->d_y.p, 0, (size_t)(n + 1) * sizeof(double2), h->stream));
     KB_CUDA(h, cudaMemsetAsync(h->d_x0.p, 0, (size_t)(n + 1) * sizeof(double2), h->stream));
+    h->ws_n = n;
   }
   KB_CUDA(h, h->d_res.alloc(n));
   KB_CUDA(h, h->d_t.alloc(n));
@@ -358,14 +422,13 @@ int kbi_apply_op_chain(kb_context* h, const double2* in_chain, double2* out_chai
 // ---------------------------------------------------------------------------
 // public entry points
 // ---------------------------------------------------------------------------
-static int solve_dev_impl(kb_context* h, const double2* rhs_dev, double2* x_dev, int nrhs) {
+static int solve_dev_once(kb_context* h, const double2* rhs_dev, double2* x_dev, int nrhs) {
   cudaStream_t s = h->stream;
   const int n = (int)h->n;
   KB_TRY(kbi_solve_workspace(h));
-  cudaEvent_t e0, e1;
-  KB_CUDA(h, cudaEventCreate(&e0));
-  KB_CUDA(h, cudaEventCreate(&e1));
-  KB_CUDA(h, cudaEventRecord(e0, s));
+  KbEventPair ev;
+  KB_CUDA(h, ev.create());
+  KB_CUDA(h, cudaEventRecord(ev.e0, s));
   for (int c = 0; c < nrhs; ++c) {
     kb_gather_scale<<<nblk(n, 256), 256, 0, s>>>(n, h->d_perm.p, h->d_rscale.p, rhs_dev + (size_t)c * n,
                                                  h->d_r.p);
@@ -374,13 +437,9 @@ static int solve_dev_impl(kb_context* h, const double2* rhs_dev, double2* x_dev,
                                                   x_dev + (size_t)c * n);
     h->launches += 2;
   }
-  KB_CUDA(h, cudaEventRecord(e1, s));
-  KB_CUDA(h, cudaStreamSynchronize(s));
-  float ms = 0.f;
-  cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  h->stats.solve_ms = ms / (nrhs > 0 ? nrhs : 1);
+  KB_CUDA(h, cudaEventRecord(ev.e1, s));
+  KB_TRY(kbi_sync(h));
+  h->stats.solve_ms = ev.ms() / (nrhs > 0 ? nrhs : 1);
   double bytes = 0.0;
   for (int64_t p = 0; p < h->P; ++p) {
     double b = (double)(h->nodeptr[p + 1] - h->nodeptr[p]);
@@ -390,6 +449,13 @@ static int solve_dev_impl(kb_context* h, const double2* rhs_dev, double2* x_dev,
   return kbi_check_sweep_error(h);
 }
 
+// one repetition after a fall-back to safe mode (kbi_enter_safe_mode has refactored)
+static int solve_dev_impl(kb_context* h, const double2* rhs_dev, double2* x_dev, int nrhs) {
+  int rc = solve_dev_once(h, rhs_dev, x_dev, nrhs);
+  if (rc == KB_EPROTOCOL_RETRY) rc = solve_dev_once(h, rhs_dev, x_dev, nrhs);
+  return rc == KB_EPROTOCOL_RETRY ? kb_fail(h, KB_ECUDA, "chain sweep failed twice") : rc;
+}
+
 extern "C" int kb_solve_dev(kb_handle h, const double* rhs_dev, double* x_dev, int nrhs) {
   if (!h || !rhs_dev || !x_dev || nrhs < 1) return KB_EINVAL;
   if (!h->factored) return kb_fail(h, KB_EINVAL, "kb_factor must succeed before kb_solve");
@@ -397,17 +463,23 @@ extern "C" int kb_solve_dev(kb_handle h, const double* rhs_dev, double* x_dev, i
   return solve_dev_impl(h, (const double2*)rhs_dev, (double2*)x_dev, nrhs);
 }
 
+// staging buffers of the host-pointer entry points (kept on the handle: a cudaMalloc / cudaFree
+// pair per call costs more than a sweep)
+static int io_buffers(kb_context* h, size_t cnt) {
+  KB_CUDA(h, h->d_io_a.alloc(cnt));
+  KB_CUDA(h, h->d_io_b.alloc(cnt));
+  return KB_OK;
+}
+
 extern "C" int kb_solve(kb_handle h, const double* rhs, double* x, int nrhs) {
   if (!h || !rhs || !x || nrhs < 1) return KB_EINVAL;
   if (!h->factored) return kb_fail(h, KB_EINVAL, "kb_factor must succeed before kb_solve");
   KB_CUDA(h, cudaSetDevice(h->device));
   const size_t cnt = (size_t)h->n * nrhs;
-  DevBuf<double2> d_rhs, d_x;
-  KB_CUDA(h, d_rhs.alloc(cnt));
-  KB_CUDA(h, d_x.alloc(cnt));
-  KB_CUDA(h, cudaMemcpyAsync(d_rhs.p, rhs, cnt * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
-  KB_TRY(solve_dev_impl(h, d_rhs.p, d_x.p, nrhs));
-  KB_CUDA(h, cudaMemcpyAsync(x, d_x.p, cnt * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  KB_TRY(io_buffers(h, cnt));
+  KB_CUDA(h, cudaMemcpyAsync(h->d_io_a.p, rhs, cnt * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+  KB_TRY(solve_dev_impl(h, h->d_io_a.p, h->d_io_b.p, nrhs));
+  KB_CUDA(h, cudaMemcpyAsync(x, h->d_io_b.p, cnt * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
   KB_CUDA(h, cudaStreamSynchronize(h->stream));
   return KB_OK;
 }
@@ -417,17 +489,19 @@ extern "C" int kb_apply_op(kb_handle h, const double* x, double* y) {
   if (!h->factored) return kb_fail(h, KB_EINVAL, "kb_factor must succeed before kb_apply_op");
   KB_CUDA(h, cudaSetDevice(h->device));
   const int n = (int)h->n;
-  KB_TRY(kbi_solve_workspace(h));
-  DevBuf<double2> d_a, d_b;
-  KB_CUDA(h, d_a.alloc(n));
-  KB_CUDA(h, d_b.alloc(n));
-  KB_CUDA(h, cudaMemcpyAsync(d_a.p, x, (size_t)n * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
-  KB_TRY(kbi_to_chain(h, d_a.p, h->d_in.p));
-  KB_TRY(kbi_apply_op_chain(h, h->d_in.p, h->d_out.p, h->opt_refine));
-  KB_TRY(kbi_from_chain(h, h->d_out.p, d_b.p));
-  KB_CUDA(h, cudaMemcpyAsync(y, d_b.p, (size_t)n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
-  KB_CUDA(h, cudaStreamSynchronize(h->stream));
-  return KB_OK;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    KB_TRY(kbi_solve_workspace(h));
+    KB_TRY(io_buffers(h, n));
+    KB_CUDA(h, cudaMemcpyAsync(h->d_io_a.p, x, (size_t)n * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+    KB_TRY(kbi_to_chain(h, h->d_io_a.p, h->d_in.p));
+    KB_TRY(kbi_apply_op_chain(h, h->d_in.p, h->d_out.p, h->opt_refine));
+    KB_TRY(kbi_from_chain(h, h->d_out.p, h->d_io_b.p));
+    KB_CUDA(h, cudaMemcpyAsync(y, h->d_io_b.p, (size_t)n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+    KB_TRY(kbi_sync(h));
+    const int rc = kbi_check_sweep_error(h);
+    if (rc != KB_EPROTOCOL_RETRY) return rc;
+  }
+  return kb_fail(h, KB_ECUDA, "chain sweep failed twice");
 }
 
 extern "C" int kb_matvec(kb_handle h, int which, const double* x, double* y) {
@@ -436,17 +510,15 @@ extern "C" int kb_matvec(kb_handle h, int which, const double* x, double* y) {
   KB_CUDA(h, cudaSetDevice(h->device));
   const int n = (int)h->n;
   KB_TRY(kbi_solve_workspace(h));
-  DevBuf<double2> d_a, d_b;
-  KB_CUDA(h, d_a.alloc(n));
-  KB_CUDA(h, d_b.alloc(n));
-  KB_CUDA(h, cudaMemcpyAsync(d_a.p, x, (size_t)n * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
-  KB_TRY(kbi_to_chain(h, d_a.p, h->d_in.p));
+  KB_TRY(io_buffers(h, n));
+  KB_CUDA(h, cudaMemcpyAsync(h->d_io_a.p, x, (size_t)n * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+  KB_TRY(kbi_to_chain(h, h->d_io_a.p, h->d_in.p));
   if (which == 0)
     KB_TRY(kbi_spmv_A_chain(h, h->d_in.p, h->d_out.p));
   else
     KB_TRY(kbi_spmv_B_chain(h, h->d_in.p, h->d_out.p, false));
-  KB_TRY(kbi_from_chain(h, h->d_out.p, d_b.p));
-  KB_CUDA(h, cudaMemcpyAsync(y, d_b.p, (size_t)n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  KB_TRY(kbi_from_chain(h, h->d_out.p, h->d_io_b.p));
+  KB_CUDA(h, cudaMemcpyAsync(y, h->d_io_b.p, (size_t)n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
   KB_CUDA(h, cudaStreamSynchronize(h->stream));
   return KB_OK;
 }

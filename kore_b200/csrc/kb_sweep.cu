@@ -66,14 +66,10 @@ __device__ __forceinline__ void kb_grid_sync(unsigned* ctr, unsigned epoch, int*
   if (threadIdx.x == 0) {
     const unsigned target = epoch * gridDim.x;
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
-    unsigned v;
-    int spins = 0;
-    do {
-      v = kb_ld_acquire(ctr);
-      // fail fast: once any CTA has timed out, nobody waits any more
-      if ((++spins & 1023) == 0 && *(volatile int*)err != 0) break;
-    } while (v < target && spins < KB_SPIN_LIMIT);
-    if (v < target) atomicExch(err, 1);
+    KbSpin sp;
+    // fail fast: once any CTA has timed out, nobody waits any more
+    while (kb_ld_acquire(ctr) < target)
+      if (kb_spin_expired(sp, err, KB_WERR_SWEEP, KB_WAIT_NS_DEFAULT)) break;
   }
   __syncthreads();
 }
@@ -228,7 +224,7 @@ __global__ void __launch_bounds__(KB_SWEEP_THREADS, 1) kb_sweep_persistent(KbSwe
     // ---- phase B: dense rows of M_p against the full t
     for (int j = tid; j < b; j += KB_SWEEP_THREADS) tvec[j] = __ldcg(&q.t[o + j]);
     if (STAGED && row1 > row0) {
-      kb_mbar_wait(&mbar[s & 1], uses[s & 1] & 1u);
+      kb_mbar_wait(&mbar[s & 1], uses[s & 1] & 1u, q.err, KB_WAIT_NS_DEFAULT);
       uses[s & 1]++;
     }
     __syncthreads();
@@ -290,14 +286,11 @@ __global__ void __launch_bounds__(KB_SWEEP_THREADS, 1) kb_sweep_persistent(KbSwe
 
 __device__ __forceinline__ double2 kb_poll(const double2* p, int* err) {
   double2 v;
-  int spins = 0;
+  KbSpin sp;
   for (;;) {
     asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
     if (__double_as_longlong(v.x) != KB_SENTINEL && __double_as_longlong(v.y) != KB_SENTINEL) break;
-    if ((++spins & 1023) == 0 && (*(volatile int*)err != 0 || spins > KB_SPIN_LIMIT)) {
-      atomicExch(err, 1);
-      break;
-    }
+    if (kb_spin_expired(sp, err, KB_WERR_SWEEP, KB_WAIT_NS_DEFAULT)) break;
   }
   return v;
 }
@@ -557,7 +550,7 @@ __global__ void __launch_bounds__(KB_SWEEP_THREADS, 1) kb_sweep_dataflow(KbFlowP
 #pragma unroll
             for (int u = 0; u < 8; ++u)
               if (j0 + u * pollw * 32 < b) pending |= 1u << u;
-            int spins = 0;
+            KbSpin sp;
             while (pending) {
 #pragma unroll
               for (int u = 0; u < 8; ++u)
@@ -575,16 +568,13 @@ __global__ void __launch_bounds__(KB_SWEEP_THREADS, 1) kb_sweep_dataflow(KbFlowP
                   tvec[j0 + u * pollw * 32] = v[u];
                   pending &= ~(1u << u);
                 }
-              if (pending && (++spins & 255) == 0 && (*(volatile int*)q.err != 0 || spins > KB_SPIN_LIMIT)) {
-                atomicExch(q.err, 1);
-                break;
-              }
+              if (pending && kb_spin_expired(sp, q.err, KB_WERR_SWEEP, KB_WAIT_NS_DEFAULT)) break;
             }
           }
         }
       }
       if (STAGED) {
-        kb_mbar_wait(&mbar[s & 1], uses[s & 1] & 1u);
+        kb_mbar_wait(&mbar[s & 1], uses[s & 1] & 1u, q.err, KB_WAIT_NS_DEFAULT);
         uses[s & 1]++;
       }
       __syncthreads();

@@ -83,15 +83,12 @@ __device__ __forceinline__ void k1_bar_wait(int id) {
 // ~1.9 K cycles on B200, polling the data itself (all-to-all, 16 bytes per pair) ~3.1 K.
 __device__ __forceinline__ void k1_wait(const unsigned* ctr, unsigned target, int* err) {
   if (threadIdx.x == 0) {
-    int spins = 0;
+    KbSpin sp;
     for (;;) {
       unsigned v;
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
       if ((int)(v - target) >= 0) break;
-      if ((++spins & 255) == 0 && (*(volatile int*)err != 0 || spins > KB_SPIN_LIMIT)) {
-        atomicExch(err, 1);
-        break;
-      }
+      if (kb_spin_expired(sp, err, KB_WERR_SWEEP, KB_WAIT_NS_DEFAULT)) break;
     }
   }
   k1_bar_compute();
@@ -464,7 +461,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) kb_sweep_onehop(K1Params q, int
 
     // ---- 3. partial_c = M_p[:, C_c] t[C_c] from the staged slice of M_p^T, published
     if (nc > 0) {
-      kb_mbar_wait(&mbar[s & 1], uses[s & 1] & 1u);
+      kb_mbar_wait(&mbar[s & 1], uses[s & 1] & 1u, q.err, KB_WAIT_NS_DEFAULT);
       uses[s & 1]++;
       K1_TICK(3);
       const double2* Ms = stage0 + (size_t)(s & 1) * slice_elems;

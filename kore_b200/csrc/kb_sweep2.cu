@@ -87,7 +87,9 @@ struct K2Params {
   K2Elem* xchg[2];
   int RS;           // elements per CTA in a ring slot
   double tag0[2];   // tag of publication -1 of each group in this solve
+  double pub_skew;  // 0; tests (KB_OPT_INJECT_FAULT = 3): the publishers' tags are off, nothing ever arrives
   int* err;
+  unsigned long long wait_ns;  // time bound of every wait of the launch
   long long* timing;
   int bmax;
   int G0;
@@ -98,9 +100,9 @@ __device__ __forceinline__ void k2_publish(K2Elem* p, double2 v, double tag) {
                : "memory");
 }
 
-__device__ __forceinline__ double2 k2_poll(const K2Elem* p, double tag, int* err) {
+__device__ __forceinline__ double2 k2_poll(const K2Elem* p, double tag, int* err, unsigned long long wait_ns) {
   double re, t0, im, t1;
-  int spins = 0;
+  KbSpin sp;
   for (;;) {
     asm volatile("ld.relaxed.gpu.global.v4.f64 {%0, %1, %2, %3}, [%4];"
                  : "=d"(re), "=d"(t0), "=d"(im), "=d"(t1)
@@ -110,10 +112,7 @@ __device__ __forceinline__ double2 k2_poll(const K2Elem* p, double tag, int* err
 #if defined(K2_EXP) && (K2_EXP & 2)
     break;  // timing experiment: do not wait for the producers
 #endif
-    if ((++spins & 255) == 0 && (*(volatile int*)err != 0 || spins > KB_SPIN_LIMIT)) {
-      atomicExch(err, 1);
-      break;
-    }
+    if (kb_spin_expired(sp, err, KB_WERR_XCHG, wait_ns)) break;
   }
   return zmake(re, im);
 }
@@ -214,7 +213,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int s
 #pragma unroll
         for (int k = 0; k < K2_PPT; ++k)
           if (pt + k * NP < bi) pend |= 1u << k;
-        int spins = 0;
+        KbSpin sp;
         while (pend) {
           double re[K2_PPT], t0[K2_PPT], im[K2_PPT], t1[K2_PPT];
 #pragma unroll
@@ -233,10 +232,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int s
 #if defined(K2_EXP) && (K2_EXP & 2)
           break;  // timing experiment: do not wait for the producers
 #endif
-          if ((++spins & 255) == 0 && (*(volatile int*)q.err != 0 || spins > KB_SPIN_LIMIT)) {
-            atomicExch(q.err, 1);
-            break;
-          }
+          if (pend && kb_spin_expired(sp, q.err, KB_WERR_GATHER, q.wait_ns)) break;
         }
       } else {
         // t of the middle node = group 0's part (r - F t) + group 1's part (-F t), both in the
@@ -245,9 +241,9 @@ __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int s
         for (int e = pt; e < bi; e += NP) {
           int c, li;
           k2_owner(bi, gsz[0], e, c, li);
-          const double2 a = k2_poll(q.xchg[0] + (size_t)c * q.RS + li, tagx0, q.err);
+          const double2 a = k2_poll(q.xchg[0] + (size_t)c * q.RS + li, tagx0, q.err, q.wait_ns);
           k2_owner(bi, gsz[1], e, c, li);
-          const double2 b2 = k2_poll(q.xchg[1] + (size_t)c * q.RS + li, tagx1, q.err);
+          const double2 b2 = k2_poll(q.xchg[1] + (size_t)c * q.RS + li, tagx1, q.err, q.wait_ns);
           v[e] = zadd(a, b2);
         }
       }
@@ -340,10 +336,10 @@ __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int s
       nr = c_nr;
       if (nr > 0) {
         if (s & 1) {
-          kb_mbar_wait(&mbar[1], uses1 & 1u);
+          kb_mbar_wait(&mbar[1], uses1 & 1u, q.err, q.wait_ns);
           uses1++;
         } else {
-          kb_mbar_wait(&mbar[0], uses0 & 1u);
+          kb_mbar_wait(&mbar[0], uses0 & 1u, q.err, q.wait_ns);
           uses0++;
         }
         const double2* Fs = stage0 + (size_t)(s & 1) * slice_elems + (size_t)row0 * bi + lane;
@@ -412,7 +408,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int s
         const double2 bs = hi ? zmake(bx, by) : base[0];
         const double2 out = zsub(bs, keep);
         if (op.pub >= 0) {
-          const double tag = q.tag0[group] + (double)(op.pub + 1);
+          const double tag = q.tag0[group] + (double)(op.pub + 1) + q.pub_skew;
           k2_publish(q.ring[group] + ((size_t)(op.pub & (K2_RING - 1)) * gsize + grank) * q.RS + li, out, tag);
         }
         if (op.pubx) k2_publish(q.xchg[group] + (size_t)grank * q.RS + li, out, q.tag0[group] + 1.0);
@@ -542,8 +538,17 @@ __global__ void __launch_bounds__(256) kb_fold_solution(const int64_t* __restric
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+// CTAs of the folded sweep.  Every CTA of a chain group must own at least one row of EVERY node
+// (a CTA that publishes nothing is waited for by nobody, so nothing would bound how far it may
+// fall behind the ring): the group size is capped by the smallest node.
+int kbi_fold_grid(const kb_context* h, bool two_sided) {
+  int64_t g = h->sweep_grid;
+  const int64_t cap = two_sided ? 2 * h->bmin : h->bmin;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+
 bool kbi_fold_supported(const kb_context* h, int G, bool two_sided, int* slice_elems_out, size_t* smem_out) {
-  if (getenv("KB_NO_FOLD")) return false;
   if (!h->M_transposed || G < 2 || h->P < 1) return false;
   const int gmin = two_sided ? G / 2 : G;
   if (gmin < 1) return false;
@@ -565,9 +570,9 @@ bool kbi_fold_supported(const kb_context* h, int G, bool two_sided, int* slice_e
 int kbi_fold_prepare(kb_context* h) {
   h->fold_ready = false;
   if (h->opt_sweep != 1 || h->nranks != 1) return KB_OK;
-  const int G = h->sweep_grid;
   const int64_t P = h->P, mid = h->mid;
   const bool two = mid < P - 1;
+  const int G = kbi_fold_grid(h, two);
   if (!kbi_fold_supported(h, G, two, nullptr, nullptr)) return KB_OK;
   cudaStream_t s = h->stream;
   // ---- folded buffer layout
@@ -677,8 +682,8 @@ int kbi_fold_prepare(kb_context* h) {
 int kbi_sweep_fold(kb_context* h, const double2* r, double2* y) {
   cudaStream_t s = h->stream;
   const int n = (int)h->n;
-  const int G = h->sweep_grid;
   const bool two = h->mid < h->P - 1;
+  const int G = kbi_fold_grid(h, two);
   int slice_elems = 0;
   size_t smem = 0;
   if (!h->fold_ready || !kbi_fold_supported(h, G, two, &slice_elems, &smem))
@@ -721,6 +726,12 @@ int kbi_sweep_fold(kb_context* h, const double2* r, double2* y) {
   h->fold_epoch[0] += (unsigned long long)h->fold_npub[0] + 1ull;
   h->fold_epoch[1] += (unsigned long long)h->fold_npub[1] + 1ull;
   q.err = h->d_sweep_err.p;
+  q.wait_ns = h->wait_ns;
+  q.pub_skew = 0.0;
+  if (h->inject_fault == 3) {
+    q.pub_skew = 0.5;
+    h->inject_fault = 0;
+  }
   q.timing = h->d_sweep_timing.p;
   q.bmax = (int)h->bmax;
   q.G0 = G0;

@@ -23,13 +23,15 @@ ERRNAMES = ["KB_OK", "KB_EINVAL", "KB_ENODEVICE", "KB_ECUDA", "KB_ENOMEM", "KB_E
 # SLEPc.EPS.Which as used at bin/solve.py:99-117
 WHICH = {"LM": 0, "SM": 1, "LR": 2, "SR": 3, "LI": 4, "SI": 5, "TM": 6, "TR": 7, "TI": 8}
 
-OPT_EQUILIBRATE, OPT_REFINE, OPT_PURIFY, OPT_SEED, OPT_PANEL, OPT_REFINE_EIGS, OPT_SWEEP, OPT_FACTOR, OPT_FOLD = 1, 2, 3, 4, 5, 6, 7, 8, 9
+(OPT_EQUILIBRATE, OPT_REFINE, OPT_PURIFY, OPT_SEED, OPT_PANEL, OPT_REFINE_EIGS, OPT_SWEEP, OPT_FACTOR,
+ OPT_FOLD, OPT_WAIT_MS, OPT_INJECT_FAULT) = range(1, 12)
 
 # every symbol include/kore_b200.h declares
 EXPORTS = [
     "kb_create", "kb_destroy", "kb_last_error", "kb_set_option", "kb_set_pencil", "kb_set_chain",
     "kb_nccl_unique_id", "kb_set_sharding", "kb_factor", "kb_solve", "kb_apply_op", "kb_matvec",
     "kb_eigs", "kb_get_stats", "kb_solve_dev", "kb_stream", "kb_savetxt",
+    "kb_dbg_schur", "kb_dbg_factor_timing", "kb_dbg_sweep_timing",
 ]
 
 
@@ -46,6 +48,7 @@ class KbStats(C.Structure):
         ("eigs_solve_ms", C.c_double), ("op_applies", C.c_int64), ("solve_calls", C.c_int64),
         ("kernel_launches", C.c_int64), ("factor_bytes", C.c_int64), ("factor_flops", C.c_double),
         ("solve_bytes", C.c_double), ("refine_resid", C.c_double),
+        ("protocol_fallbacks", C.c_int64), ("wait_error", C.c_int64),
     ]
 
     def asdict(self):
@@ -97,7 +100,7 @@ def load():
     lib.kb_stream.argtypes = [vp, C.POINTER(vp)]
     lib.kb_savetxt.argtypes = [C.c_char_p, vp, i64, i64, i64, i64, C.c_int, C.c_int]
     lib.kb_dbg_schur.argtypes = [C.c_int, vp, C.c_int, vp, vp, vp, vp]
-    for name in EXPORTS + ["kb_dbg_schur"]:
+    for name in EXPORTS:
         if name != "kb_last_error":
             getattr(lib, name).restype = C.c_int
     _lib = lib
@@ -185,6 +188,11 @@ class Solver:
         bcomplex = 0
         if B is not None:
             B = B.tocsr()
+            if not B.has_canonical_format:
+                # the library gives every B entry its own slot of A - sigma B (ut.load_csr /
+                # ss.csr_matrix do not merge duplicate entries; kb_set_chain rejects them)
+                B = B.copy()
+                B.sum_duplicates()
             bp = np.ascontiguousarray(B.indptr, dtype=idx_dtype)
             bi = np.ascontiguousarray(B.indices, dtype=idx_dtype)
             if np.iscomplexobj(B.data):

@@ -103,6 +103,77 @@ class ShiftInvert:
         return self.lu.solve(self.B @ x)
 
 
+class BlockShiftInvert:
+    """The same operator as :class:`ShiftInvert` with the LU done the way a multifrontal code
+    (MUMPS, what the reference's scripts select: tests/dormy2004/find_Rac.py:18,
+    tools/subramp.sh:50) does it on this structure: dense LAPACK (``zgetrf`` / ``zgetrs``,
+    threaded BLAS-3) on the fronts of the l-chain instead of SciPy's serial scalar-supernode
+    SuperLU.  In chain order T = A - sigma B is block tridiagonal; the elimination is
+
+        S_0 = D_0,   S_p = D_p - L_p (S_{p-1}^{-1} U_{p-1}),      LU(S_p) kept,
+        forward  y_p = r_p - L_p x~_{p-1},  x~_p = S_p^{-1} y_p,
+        backward x_p = x~_p - S_p^{-1} (U_p x_{p+1}),
+
+    pivoting inside the fronts only (as accurate as SuperLU on every reference
+    matrix).  It is the CPU baseline bench.py times on the full benchmark size with all host
+    threads (``cpu_baseline.kind = "port"``) and is checked against :class:`ShiftInvert` in
+    tests/test_oracle_golden.py.  ``chain`` = (perm, nodeptr) as kb_set_chain takes them."""
+
+    def __init__(self, A, B, sigma, chain, max_nodes=None):
+        import scipy.linalg as sl
+        self._sl = sl
+        perm, nodeptr = chain
+        self.perm = np.asarray(perm)
+        self.nodeptr = np.asarray(nodeptr)
+        self.A = A.tocsr()
+        self.B = B.tocsr() if B is not None else None
+        self.sigma = complex(sigma)
+        T = self.A.astype(np.complex128)
+        if self.B is not None and self.sigma != 0:
+            T = T - self.sigma * self.B
+        Tc = T.tocsr()[self.perm][:, self.perm].tocsr()
+        P = len(self.nodeptr) - 1
+        self.P = P if max_nodes is None else min(P, int(max_nodes))
+        self.lu, self.Lc, self.Uc = [], [], []
+        W = None
+        for p in range(self.P):
+            o0, o1 = self.nodeptr[p], self.nodeptr[p + 1]
+            rows = Tc[o0:o1]
+            S = rows[:, o0:o1].toarray()
+            Lp = rows[:, self.nodeptr[p - 1]:o0].tocsr() if p > 0 else None
+            Up = rows[:, o1:self.nodeptr[p + 2]].tocsr() if p + 1 < P else None
+            if p > 0:
+                S -= Lp @ W
+            lu = sl.lu_factor(S, overwrite_a=True, check_finite=False)
+            if Up is not None and p + 1 < self.P:
+                W = sl.lu_solve(lu, Up.toarray(), overwrite_b=True, check_finite=False)
+            self.lu.append(lu)
+            self.Lc.append(Lp)
+            self.Uc.append(Up)
+        self.napply = 0
+
+    def solve(self, rhs):
+        sl, nodeptr = self._sl, self.nodeptr
+        r = np.asarray(rhs, dtype=np.complex128)[self.perm]
+        x = np.empty_like(r)
+        prev = None
+        for p in range(self.P):
+            o0, o1 = nodeptr[p], nodeptr[p + 1]
+            y = r[o0:o1] if p == 0 else r[o0:o1] - self.Lc[p] @ prev
+            prev = sl.lu_solve(self.lu[p], y, check_finite=False)
+            x[o0:o1] = prev
+        for p in range(self.P - 2, -1, -1):
+            o0, o1 = nodeptr[p], nodeptr[p + 1]
+            x[o0:o1] -= sl.lu_solve(self.lu[p], self.Uc[p] @ x[o1:nodeptr[p + 2]], check_finite=False)
+        out = np.empty_like(x)
+        out[self.perm] = x
+        return out
+
+    def apply(self, x):
+        self.napply += 1
+        return self.solve(self.B @ x)
+
+
 def residuals(A, B, lam, X):
     """BASELINE.json criterion: ||A x - lam B x|| / (|lam| ||B x||)."""
     out = np.empty(len(lam))

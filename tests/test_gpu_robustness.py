@@ -1,0 +1,133 @@
+"""GPU: the persistent kernels (strip factorisation, folded sweep) talk through spin protocols in
+L2.  These tests cover what happens when such a protocol fails -- an expired device-side wait must
+end the launch quickly, the handle must fall back to the kernels without device-side waits and the
+call must still return the right answer -- and stress the healthy path the way the driver's
+scaling run launches it (round 1's run was killed at its time limit there, SCALE_r01.json)."""
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_case
+
+pytestmark = pytest.mark.gpu
+
+
+def make_solver(lib, case, opts=None):
+    s = lib.Solver(0)
+    for k, v in (opts or {}).items():
+        s.set_option(k, v)
+    s.set_pencil(case.A, case.B)
+    s.set_chain(case.perm, case.nodeptr)
+    s.factor(case.tau)
+    return s
+
+
+@pytest.mark.parametrize("name", ["spinover", "dormy"])
+def test_flagged_sweep_falls_back_and_repeats(lib, name):
+    case = load_case(name)
+    rhs = case.oracle["solve_rhs"]
+    xo = case.oracle["solve_x"]
+    with make_solver(lib, case) as s:
+        x0 = s.solve(rhs)
+        assert s.stats()["protocol_fallbacks"] == 0
+        s.set_option(lib.OPT_INJECT_FAULT, 1)  # the next sweep reports an expired wait
+        x1 = s.solve(rhs)
+        st = s.stats()
+        assert st["protocol_fallbacks"] == 1 and (st["wait_error"] & 255) == 9
+        assert np.linalg.norm(x1 - xo) <= 1e-9 * np.linalg.norm(xo)
+        assert np.linalg.norm(x1 - x0) <= 1e-9 * np.linalg.norm(x0)
+        # the handle stays usable (per-node kernels from here on), at any shift
+        x2 = s.solve(rhs)
+        assert np.array_equal(x1, x2) and s.stats()["protocol_fallbacks"] == 1
+        s.factor(case.tau + 0.01)
+        T = (case.A - (case.tau + 0.01) * case.B).tocsr()
+        x3 = s.solve(rhs)
+        assert np.linalg.norm(T @ x3 - rhs) <= 1e-12 * np.linalg.norm(rhs)
+
+
+def test_flagged_factorisation_falls_back(lib):
+    case = load_case("spinover")
+    s = lib.Solver(0)
+    s.set_pencil(case.A, case.B)
+    s.set_chain(case.perm, case.nodeptr)
+    s.set_option(lib.OPT_INJECT_FAULT, 2)
+    s.factor(case.tau)  # strip kernel "times out" -> per-step kernels, same call
+    assert s.stats()["protocol_fallbacks"] == 1
+    x = s.solve(case.oracle["solve_rhs"])
+    xo = case.oracle["solve_x"]
+    assert np.linalg.norm(x - xo) <= 1e-9 * np.linalg.norm(xo)
+    s.close()
+
+
+def test_flagged_sweep_inside_eigs_repeats_the_eigensolve(lib):
+    case = load_case("spinover")
+    m = case.meta
+    with make_solver(lib, case) as s:
+        s.set_option(lib.OPT_INJECT_FAULT, 1)
+        lam, X, info = s.eigs(m["nev"], which=m["which_eigenpairs"], target=case.tau, tol=m["tol"], maxit=m["maxit"])
+        assert info["protocol_fallbacks"] == 1 and info["nconv"] >= m["nev"]
+        for lo in case.oracle["eig"]:
+            assert np.min(np.abs(lam - lo)) / abs(lo) < 1e-9
+
+
+def test_real_expired_wait_ends_the_launch_quickly(lib):
+    # the publishers of one folded sweep write tags nobody accepts: every gather really waits,
+    # the first to exceed the bound (50 ms here) raises the flag, all others give up at once
+    from kore_b200 import synthetic
+    A, B, perm, nodeptr = synthetic.synthetic_pencil(40, 600)
+    s = lib.Solver(0)
+    s.set_option(lib.OPT_WAIT_MS, 50)
+    s.set_pencil(A, B)
+    s.set_chain(perm, nodeptr)
+    s.factor(1j)
+    r = B @ synthetic.start_vector(A.shape[0], 3)
+    x0 = s.solve(r)
+    s.set_option(lib.OPT_INJECT_FAULT, 3)
+    t0 = time.perf_counter()
+    x1 = s.solve(r)
+    dt = time.perf_counter() - t0
+    st = s.stats()
+    s.close()
+    assert st["protocol_fallbacks"] == 1 and (st["wait_error"] & 255) in (5, 6)
+    assert np.linalg.norm(x1 - x0) <= 1e-9 * np.linalg.norm(x0)
+    # one 50 ms time-out + a refactorisation with the per-step kernels + the repeated solve
+    assert dt < 5.0, dt
+
+
+def test_repeated_factor_and_eigs_are_deterministic_full_size(lib):
+    # P = b = 600 (the benchmark's size), 30 factor + eigensolve steps on one handle: no fall-back,
+    # and every step returns bit-identical eigenvalues (a lost or late exchange would not)
+    from kore_b200 import synthetic
+    A, B, perm, nodeptr = synthetic.synthetic_pencil(600, 600)
+    v0 = synthetic.start_vector(A.shape[0], 1)
+    s = lib.Solver(0)
+    s.set_pencil(A, B)
+    s.set_chain(perm, nodeptr)
+    ref = None
+    for it in range(30):
+        s.factor(1j)
+        lam, _, info = s.eigs(10, "TM", target=1j, ncv=25, tol=1e-12, maxit=100, v0=v0, want_vectors=False)
+        assert info["nconv"] >= 10 and info["protocol_fallbacks"] == 0, (it, info)
+        if ref is None:
+            ref = lam
+        assert np.array_equal(lam, ref), it
+    s.close()
+
+
+def test_bench_under_torchrun_like_the_scaling_driver():
+    # SCALE_r01: `python -m torch.distributed.run --nproc-per-node 1 bench.py --gpus 1 ...`
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "1",
+           "--master-addr", "127.0.0.1", "--master-port", "29513", os.path.join(ROOT, "bench.py"),
+           "--gpus", "1", "--steps", "3", "--warmup", "3", "--no-cpu", "--e2e-steps", "2"]
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 1 and d["value"] > 5.0 and d["protocol_fallbacks"] == 0
+    assert d["max_residual"] < 1e-10
