@@ -89,26 +89,56 @@ __device__ __forceinline__ void kf_st_release(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Bounded wait until *ctr >= target (one thread).  Out of line: the clock and the poll counter
-// must not take registers from the strip rows of the kernel below.
-__device__ __noinline__ void kf_spin_until(const unsigned* ctr, unsigned target, int* err, int code,
-                                           unsigned long long wait_ns) {
-  KbSpin sp;
+// Bounded waits without a call and without per-thread state (the strip rows leave no registers
+// for a clock, and a call site constrains the register allocation of the whole kernel): every
+// wait is measured against a DEADLINE kept in shared memory -- `deadline[0]` for the waits of
+// thread 0 on counters (set by thread 0 itself when it starts to spin), `deadline[1]` for the
+// polls of the column stream (set by thread 0 at the top of every strip step) -- and looked at
+// only every 32nd missed poll, together with the launch's flag; `failed` is the CTA's own copy of
+// "the launch has failed" (every 4th missed poll looks at it).
+struct KfWait {
+  unsigned long long deadline[2];
+  int failed;
+};
+
+// every 32nd missed poll: true = stop waiting
+__device__ __forceinline__ bool kf_expired(int* err, int code, volatile KfWait* w, int which) {
+  if (*(volatile int*)err != 0) {
+    w->failed = 1;
+    return true;
+  }
+  if (kb_globaltimer() > w->deadline[which]) {
+    atomicCAS(err, 0, code | ((int)blockIdx.x << 8));
+    w->failed = 1;
+    return true;
+  }
+  return false;
+}
+
+// one thread: wait until *ctr >= target
+__device__ __forceinline__ void kf_spin_until(const unsigned* ctr, unsigned target, int* err, int code,
+                                              unsigned long long wait_ns, volatile KfWait* w) {
+  if (kf_ld_acquire(ctr) >= target) return;
+  if (w->failed) return;
+  w->deadline[0] = kb_globaltimer() + wait_ns;
+  int misses = 0;
   while (kf_ld_acquire(ctr) < target)
-    if (kb_spin_expired(sp, err, code, wait_ns)) break;
+    if ((++misses & 31) == 0 && kf_expired(err, code, w, 0)) break;
 }
 
 // thread 0 waits until *ctr >= target; everybody leaves through the block barrier
-__device__ __forceinline__ void kf_wait(const unsigned* ctr, unsigned target, int* err, unsigned long long wait_ns) {
-  if (threadIdx.x == 0) kf_spin_until(ctr, target, err, KB_WERR_COUNTER, wait_ns);
+__device__ __forceinline__ void kf_wait(const unsigned* ctr, unsigned target, int* err, unsigned long long wait_ns,
+                                        volatile KfWait* w) {
+  if (threadIdx.x == 0) kf_spin_until(ctr, target, err, KB_WERR_COUNTER, wait_ns, w);
   __syncthreads();
 }
 
-__device__ __forceinline__ void kf_group_barrier(unsigned* ctr, unsigned target, int* err, unsigned long long wait_ns) {
+__device__ __forceinline__ void kf_group_barrier(unsigned* ctr, unsigned target, int* err, unsigned long long wait_ns,
+                                                 volatile KfWait* w) {
   __syncthreads();
   if (threadIdx.x == 0) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
-    kf_spin_until(ctr, target, err, KB_WERR_GROUP_BARRIER, wait_ns);
+    kf_spin_until(ctr, target, err, KB_WERR_GROUP_BARRIER, wait_ns, w);
   }
   __syncthreads();
 }
@@ -133,25 +163,6 @@ __device__ __forceinline__ void kf_stream_put(double* p, double2 v, double tag) 
   asm volatile("st.relaxed.gpu.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(v.x), "d"(tag), "d"(v.y), "d"(tag)
                : "memory");
 }
-// Slow path of a consumer that has caught up with the panel: poll until the element carries a tag
-// of the expected column (or the launch has failed).  Out of line and without results -- the
-// caller loads the element again -- so that the clock, the poll counter and the call itself
-// take no registers from the strip rows.
-__device__ __noinline__ void kf_stream_wait(const double* p, double tagbase, int* err, unsigned long long wait_ns) {
-  double re, t0, im, t1;
-  KbSpin sp;
-  for (;;) {
-    asm volatile("ld.relaxed.gpu.global.v4.f64 {%0, %1, %2, %3}, [%4];"
-                 : "=d"(re), "=d"(t0), "=d"(im), "=d"(t1)
-                 : "l"(p)
-                 : "memory");
-    (void)re;
-    (void)im;
-    if (t0 == t1 && t0 >= tagbase && t0 < tagbase + 1024.0) break;
-    if (kb_spin_expired(sp, err, KB_WERR_STREAM, wait_ns)) break;
-  }
-}
-
 template <int NB>
 struct KfShared {
   double2 slots[2][NB][NB];                  // pivot rows of this CTA's strip for the step being applied
@@ -159,7 +170,7 @@ struct KfShared {
   unsigned long long candkey[2][32];         // (key << 32) | ~row of every warp's candidate
   int piv[16];                               // pivots of the panel being factored
   unsigned consbase[KF_RING];                // consumers that had released each ring slot before this node
-  unsigned bp_seen;                          // ring counter of this CTA's own strip as last read by thread 0
+  KfWait wait;                               // deadlines and failure flag of the bounded waits
 };
 
 // S strip -= C_pq (M_q C_qp)[:, strip].  kind 0: q = p-1 (C_qp = U by column, C_pq = the
@@ -233,8 +244,13 @@ __global__ void __launch_bounds__(MAXT, 1) kb_chain_factor(KfParams q) {
   long long colbase = 0;  // columns eliminated by this group before the current node
   // ring counters of this group: slot j's line counts the CTAs that are done reading it
   unsigned* cons = q.sync + 192 + group * (KF_RING * 32);
-  if (t == 0)
+  if (t == 0) {
     for (int j = 0; j < KF_RING; ++j) sh.consbase[j] = 0u;
+    sh.wait.failed = 0;
+    sh.wait.deadline[0] = sh.wait.deadline[1] = ~0ull;
+  }
+  __syncthreads();
+  volatile KfWait* kw = &sh.wait;
   long long tacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tc = clock64();
   // Cycle counters are compiled in only with -DKB_FACTOR_TIMING (make EXTRA=-DKB_FACTOR_TIMING):
@@ -270,7 +286,7 @@ __global__ void __launch_bounds__(MAXT, 1) kb_chain_factor(KfParams q) {
     for (int j = 0; j < NB; ++j) a[j] = zmake(0.0, 0.0);
 
     // the middle node needs the last node of the other chain
-    if (group == 0 && s == mid && mid < P - 1) kf_wait(done1, 1u, q.err, q.wait_ns);
+    if (group == 0 && s == mid && mid < P - 1) kf_wait(done1, 1u, q.err, q.wait_ns, kw);
 
     // ---- Schur block, strip-wise:  S = D_p - C_pq M_q C_qp  (one or two eliminated neighbours)
     if (active) {
@@ -308,12 +324,29 @@ __global__ void __launch_bounds__(MAXT, 1) kb_chain_factor(KfParams q) {
     //      `mycol` which column it pivoted.  (tests/strip_gj_model.py)
     if (active) {
       int mycol = t < b ? -1 : 0;  // column this row has pivoted; -1: the row is still free
-      // thread 0 reads the ring counter of this CTA's own strip one step ahead (sh.bp_seen)
-      if (q.Sbuf[group] && t == 0 && c == 0) sh.bp_seen = kf_ld_acquire(cons + 0);
       for (int k = 0; k < K; ++k) {
         const int k0 = k * w;
         const int wk = min(w, b - k0);
-        if (q.Sbuf[group] && t == 0 && k + 1 == c) sh.bp_seen = kf_ld_acquire(cons + (c & (KF_RING - 1)) * 32);
+        // deadline of this step's polls of the column stream
+        if (t == 0 && q.Sbuf[group] && k != c) sh.wait.deadline[1] = kb_globaltimer() + q.wait_ns;
+#ifndef KF_NO_BP
+        // Back-pressure: strip c reuses the ring slot of strip c - KF_RING; its owner stores
+        // nothing before every consumer of that strip has released the slot.  The CTA makes sure
+        // of it TWO steps before its panel (and at the first step of a node for strips 0 and 1):
+        // the acquire load costs an L2 round trip, which must happen neither in the panel nor
+        // while this CTA is the next owner (the hand-over is the critical path); two steps ahead
+        // strips c - 4 and c - 3 are complete and their consumers have long let go, so the wait
+        // itself practically never spins.  Nobody reads the slot again before strip c is written,
+        // so the early check is as good as a late one.  EVERY thread does the (same) load and
+        // the (same) wait: a wait by thread 0 alone is a divergent loop inside the strip loop,
+        // after which ptxas no longer treats the warp as converged in the panel below (no uniform
+        // datapath, convergence barriers around every branch: +14 instructions per panel column,
+        // measured +10 % on the whole factorisation).
+        if (q.Sbuf[group] && (k + 2 == c || (k == 0 && c < 2))) {
+          const unsigned need = sh.consbase[c & (KF_RING - 1)] + (unsigned)(K - 1) * (unsigned)(c / KF_RING);
+          kf_spin_until(cons + (c & (KF_RING - 1)) * 32, need, q.err, KB_WERR_BACKPRESSURE, q.wait_ns, kw);
+        }
+#endif
         if (k == c) {
           // ================= panel: this CTA's own strip =================
           // Two block barriers per column: (1) every warp has published the key of its best
@@ -324,15 +357,6 @@ __global__ void __launch_bounds__(MAXT, 1) kb_chain_factor(KfParams q) {
           double rinv;
           // column stream of this strip: slot of this row, tag of column 0 with pivot code 0
           double* sput = q.Sbuf[group] ? q.Sbuf[group] + 4 * ((size_t)((k & (KF_RING - 1)) * NB) * ldg + t) : nullptr;
-          // Back-pressure: strip k reuses the ring slot of strip k - KF_RING; nothing is stored
-          // before every consumer of that strip has released the slot.  The counter was read
-          // one step ago (bp_seen), so in the normal case this is one compare; thread 0 holds
-          // the CTA at the first barrier of the panel otherwise.
-          if (sput && t == 0) {
-            const unsigned need = sh.consbase[k & (KF_RING - 1)] + (unsigned)(K - 1) * (unsigned)(k / KF_RING);
-            if (sh.bp_seen < need)
-              kf_spin_until(cons + (k & (KF_RING - 1)) * 32, need, q.err, KB_WERR_BACKPRESSURE, q.wait_ns);
-          }
           const double stag = (double)((colbase + k0 + 1) * 1024);
           {
             const double m2 = zabs2(a[0]);
@@ -464,12 +488,23 @@ __global__ void __launch_bounds__(MAXT, 1) kb_chain_factor(KfParams q) {
                 double2 sv = zmake(re[u], im[u]);
                 if (t < b) {
                   if (!(t0[u] == t1[u] && t0[u] >= tb && t0[u] < tb + 1024.0)) {
+                    // this CTA has caught up with the panel (it is the next owner, or close):
+                    // poll.  Every 4th missed poll looks at the CTA's failure flag in shared memory,
+                    // every 32nd at the launch's flag and the clock (out of line).
                     const double* ep = sbase + 4 * (size_t)cc * ldg;
-                    kf_stream_wait(ep, tb, q.err, q.wait_ns);
-                    asm volatile("ld.relaxed.gpu.global.v4.f64 {%0, %1, %2, %3}, [%4];"
-                                 : "=d"(re[u]), "=d"(t0[u]), "=d"(im[u]), "=d"(t1[u])
-                                 : "l"(ep)
-                                 : "memory");
+                    int misses = 0;
+                    for (;;) {
+                      asm volatile("ld.relaxed.gpu.global.v4.f64 {%0, %1, %2, %3}, [%4];"
+                                   : "=d"(re[u]), "=d"(t0[u]), "=d"(im[u]), "=d"(t1[u])
+                                   : "l"(ep)
+                                   : "memory");
+                      if (t0[u] == t1[u] && t0[u] >= tb && t0[u] < tb + 1024.0) break;
+                      // (a normal wait ends within two or three polls: nothing but the poll until then)
+                      if ((++misses & 3) == 0) {
+                        if (kw->failed) break;
+                        if ((misses & 31) == 0 && kf_expired(q.err, KB_WERR_STREAM, kw, 1)) break;
+                      }
+                    }
                     sv = zmake(re[u], im[u]);
                   }
                   // (no match after the wait: the launch has failed; the column is skipped)
@@ -501,12 +536,15 @@ __global__ void __launch_bounds__(MAXT, 1) kb_chain_factor(KfParams q) {
           }
           // every thread of the CTA had its elements of strip k in registers before it passed the
           // last barrier above: the ring slot may be rewritten as far as this CTA is concerned
-          if (t == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cons + (k & (KF_RING - 1)) * 32) : "memory");
+          // (relaxed: nothing is published, and a release fence here would sit on the hand-over path)
+#ifndef KF_NO_BP
+          if (t == 0) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(cons + (k & (KF_RING - 1)) * 32) : "memory");
+#endif
           KF_TICK(3);
         } else {
           // ================= consumer: apply step k to this strip =================
           //   A[i,:] <- (i is a pivot row of the step ? 0 : A[i,:]) + sum_c G[i,c] A[piv_c,:]
-          kf_wait(pub, pubbase + (unsigned)k + 1u, q.err, q.wait_ns);
+          kf_wait(pub, pubbase + (unsigned)k + 1u, q.err, q.wait_ns, kw);
           // the owner of the next strip is on the critical path: it reads G_k from an idle L2
           if (q.stagger_ns > 0 && c != k + 1) __nanosleep((unsigned)q.stagger_ns);
           KF_TICK(2);
@@ -578,7 +616,7 @@ __global__ void __launch_bounds__(MAXT, 1) kb_chain_factor(KfParams q) {
     if (t == 0 && q.Sbuf[group])
       for (int j = 0; j < KF_RING; ++j)
         if (j < K) sh.consbase[j] += (unsigned)(K - 1) * (unsigned)((K - j + KF_RING - 1) / KF_RING);
-    kf_group_barrier(bar, barcount, q.err, q.wait_ns);
+    kf_group_barrier(bar, barcount, q.err, q.wait_ns, kw);
     KF_TICK(4);
   }
   if (group == 1 && c == 0 && t == 0 && S > 0) kf_st_release(done1, 1u);

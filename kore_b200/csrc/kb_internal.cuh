@@ -104,12 +104,20 @@ struct KbSpin {
   unsigned n = 0;
   unsigned long long t0 = 0;
 };
-// true: stop waiting (the launch has failed, here or elsewhere).  Looks at the flag and the clock
-// after the first missed poll and then every 32 polls, so a wait that succeeds at once costs
-// nothing extra and a launch that has already failed drains at one missed poll per wait.
-__device__ __forceinline__ bool kb_spin_expired(KbSpin& s, int* err, int code, unsigned long long limit_ns) {
-  if ((++s.n & 31u) != 1u) return false;
-  if (*(volatile int*)err != 0) return true;
+// true: stop waiting (the launch has failed, here or elsewhere).  The fast path of a wait is
+// untouched: nothing happens before the first missed poll, the first missed poll reads a flag in
+// SHARED memory (`cta_failed`, may be null: set once any thread of the CTA has seen the failure,
+// so that a failed launch drains at one missed poll per wait), and only every 32nd missed poll
+// reads the launch's flag in global memory and the clock.
+__device__ __forceinline__ bool kb_spin_expired(KbSpin& s, int* err, int code, unsigned long long limit_ns,
+                                                volatile int* cta_failed = nullptr) {
+  const unsigned n = ++s.n;
+  if (n == 1u) return cta_failed != nullptr && *cta_failed != 0;
+  if ((n & 31u) != 0u) return false;
+  if (*(volatile int*)err != 0) {
+    if (cta_failed) *cta_failed = 1;
+    return true;
+  }
   const unsigned long long now = kb_globaltimer();
   if (s.t0 == 0) {
     s.t0 = now;
@@ -117,6 +125,7 @@ __device__ __forceinline__ bool kb_spin_expired(KbSpin& s, int* err, int code, u
   }
   if (now - s.t0 > limit_ns) {
     atomicCAS(err, 0, code | ((int)blockIdx.x << 8));
+    if (cta_failed) *cta_failed = 1;
     return true;
   }
   return false;
@@ -138,11 +147,14 @@ __device__ __forceinline__ void kb_bulk_g2s(void* dst, const void* src, unsigned
                "l"(src), "r"(bytes), "r"(kb_smem_addr(bar))
                : "memory");
 }
-// Wait for the completion of a bulk copy.  A copy that never lands raises the launch's error flag
-// (the readers of the stage would otherwise consume whatever the stage held).
+// Wait for the completion of a bulk copy.  Never abandoned because something ELSE has failed: a
+// copy in flight lands on its own, and a CTA must not refill the stage or exit before it has (a
+// launch that is draining after an expired wait still consumes every copy it has issued).  Only
+// a copy that itself does not land within the bound raises the launch's flag.
 __device__ __forceinline__ void kb_mbar_wait(uint64_t* bar, unsigned parity, int* err, unsigned long long limit_ns) {
   unsigned done = 0;
-  KbSpin sp;
+  unsigned tries = 0;
+  unsigned long long t0 = 0;
   for (;;) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -150,7 +162,14 @@ __device__ __forceinline__ void kb_mbar_wait(uint64_t* bar, unsigned parity, int
         : "r"(kb_smem_addr(bar)), "r"(parity)
         : "memory");
     if (done) break;
-    if (kb_spin_expired(sp, err, KB_WERR_MBAR, limit_ns)) break;
+    if ((++tries & 255u) == 0u) {
+      const unsigned long long now = kb_globaltimer();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > limit_ns) {
+        atomicCAS(err, 0, KB_WERR_MBAR | ((int)blockIdx.x << 8));
+        break;
+      }
+    }
   }
 }
 

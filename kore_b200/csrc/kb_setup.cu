@@ -68,7 +68,12 @@ extern "C" int kb_destroy(kb_handle h) {
   if (!h) return KB_OK;
   cudaSetDevice(h->device);
   if (h->stream) {
-    cudaStreamSynchronize(h->stream);
+    // bounded: a kernel that does not even react to the watchdog flag must not block the host in
+    // here for ever (cudaFree would); the context is leaked and the error returned instead
+    if (kbi_sync(h) != KB_OK) {
+      fprintf(stderr, "libkoreb200: kb_destroy: the handle's stream does not drain; leaking the context\n");
+      return KB_ECUDA;
+    }
     cudaStreamDestroy(h->stream);
   }
   if (h->stream2) {

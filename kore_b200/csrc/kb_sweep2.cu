@@ -100,7 +100,8 @@ __device__ __forceinline__ void k2_publish(K2Elem* p, double2 v, double tag) {
                : "memory");
 }
 
-__device__ __forceinline__ double2 k2_poll(const K2Elem* p, double tag, int* err, unsigned long long wait_ns) {
+__device__ __forceinline__ double2 k2_poll(const K2Elem* p, double tag, int* err, unsigned long long wait_ns,
+                                           volatile int* cta_failed) {
   double re, t0, im, t1;
   KbSpin sp;
   for (;;) {
@@ -112,7 +113,7 @@ __device__ __forceinline__ double2 k2_poll(const K2Elem* p, double tag, int* err
 #if defined(K2_EXP) && (K2_EXP & 2)
     break;  // timing experiment: do not wait for the producers
 #endif
-    if (kb_spin_expired(sp, err, KB_WERR_XCHG, wait_ns)) break;
+    if (kb_spin_expired(sp, err, KB_WERR_XCHG, wait_ns, cta_failed)) break;
   }
   return zmake(re, im);
 }
@@ -132,11 +133,28 @@ __device__ __forceinline__ void k2_owner(int b, int size, int e, int& c, int& li
   }
 }
 
-// named barriers: 2 = row warps only (their rows of the slice are in registers: the stage may
-// be refilled); 3 = gather warps arrive / row warps wait (the input vector is in shared memory)
+// Named barriers.  2 = row warps only (their rows of the slice are in registers: the stage may be
+// refilled).  The input vector is a two-slot producer / consumer buffer between the gather warps
+// and the row warps with a FULL and an EMPTY barrier per slot (step parity): full (3, 5) = gather
+// warps arrive, row warps wait; empty (6, 7) = row warps arrive when they have read the slot,
+// gather warps wait before they overwrite it two steps later.  In a healthy launch the gather
+// warps cannot run more than one step ahead anyway (an entry of step s+1 exists only after this
+// CTA's row warps have published step s), but a launch whose waits have been abandoned (expired
+// wait, watchdog) has no such data dependency left, and a barrier that receives the arrivals of
+// two steps at once never completes again: the hand-shake must not depend on the data.
 __device__ __forceinline__ void k2_bar_rows() { asm volatile("bar.sync 2, %0;" ::"n"(K2_RW * 32) : "memory"); }
-__device__ __forceinline__ void k2_bar_vec_arrive() { asm volatile("bar.arrive 3, %0;" ::"n"(K2_THREADS) : "memory"); }
-__device__ __forceinline__ void k2_bar_vec_wait() { asm volatile("bar.sync 3, %0;" ::"n"(K2_THREADS) : "memory"); }
+__device__ __forceinline__ void k2_bar_full_arrive(int s) {
+  asm volatile("bar.arrive %0, %1;" ::"r"((s & 1) ? 5 : 3), "n"(K2_THREADS) : "memory");
+}
+__device__ __forceinline__ void k2_bar_full_wait(int s) {
+  asm volatile("bar.sync %0, %1;" ::"r"((s & 1) ? 5 : 3), "n"(K2_THREADS) : "memory");
+}
+__device__ __forceinline__ void k2_bar_empty_arrive(int s) {
+  asm volatile("bar.arrive %0, %1;" ::"r"((s & 1) ? 7 : 6), "n"(K2_THREADS) : "memory");
+}
+__device__ __forceinline__ void k2_bar_empty_wait(int s) {
+  asm volatile("bar.sync %0, %1;" ::"r"((s & 1) ? 7 : 6), "n"(K2_THREADS) : "memory");
+}
 
 __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int slice_elems) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -145,6 +163,8 @@ __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int s
   double2* vbuf = stage0 + 2 * (size_t)slice_elems;      // 2 x bpad: input vector, by step parity
   int* s_nptr = (int*)(vbuf + 2 * (size_t)bpad);
   __shared__ __align__(8) uint64_t mbar[2];
+  __shared__ int s_failed;  // some thread of this CTA has seen the launch fail
+  volatile int* cta_failed = &s_failed;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int group = ((int)blockIdx.x < q.G0) ? 0 : 1;
   const int gsz[2] = {q.G0, (int)gridDim.x - q.G0};
@@ -173,6 +193,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int s
 
   for (int i = tid; i <= q.P; i += K2_THREADS) s_nptr[i] = (int)q.nodeptr[i];
   if (tid == 0) {
+    s_failed = 0;
     kb_mbar_init(&mbar[0], 1);
     kb_mbar_init(&mbar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -194,6 +215,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int s
       if (s + 1 < S) nop = ops[s + 1];
       const int oi = s_nptr[op.in_node], bi = s_nptr[op.in_node + 1] - oi;
       double2* v = vbuf + (size_t)(s & 1) * bpad;
+      if (s >= 2) k2_bar_empty_wait(s);  // the row warps are done with the vector of step s - 2
       if (op.in_kind == 0) {
         for (int e = pt; e < bi; e += NP) v[e] = q.r[oi + e];
       } else if (op.in_kind == 1) {
@@ -232,7 +254,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int s
 #if defined(K2_EXP) && (K2_EXP & 2)
           break;  // timing experiment: do not wait for the producers
 #endif
-          if (pend && kb_spin_expired(sp, q.err, KB_WERR_GATHER, q.wait_ns)) break;
+          if (pend && kb_spin_expired(sp, q.err, KB_WERR_GATHER, q.wait_ns, cta_failed)) break;
         }
       } else {
         // t of the middle node = group 0's part (r - F t) + group 1's part (-F t), both in the
@@ -241,9 +263,9 @@ __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int s
         for (int e = pt; e < bi; e += NP) {
           int c, li;
           k2_owner(bi, gsz[0], e, c, li);
-          const double2 a = k2_poll(q.xchg[0] + (size_t)c * q.RS + li, tagx0, q.err, q.wait_ns);
+          const double2 a = k2_poll(q.xchg[0] + (size_t)c * q.RS + li, tagx0, q.err, q.wait_ns, cta_failed);
           k2_owner(bi, gsz[1], e, c, li);
-          const double2 b2 = k2_poll(q.xchg[1] + (size_t)c * q.RS + li, tagx1, q.err, q.wait_ns);
+          const double2 b2 = k2_poll(q.xchg[1] + (size_t)c * q.RS + li, tagx1, q.err, q.wait_ns, cta_failed);
           v[e] = zadd(a, b2);
         }
       }
@@ -255,7 +277,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int s
         for (int e = x0 + pt; e < x1; e += NP) q.uvec[oi + e] = v[e];
       }
       __threadfence_block();
-      k2_bar_vec_arrive();
+      k2_bar_full_arrive(s);
     }
     return;
   }
@@ -362,7 +384,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int s
     K2_TICK(0);
 
     // ---- 1. the input vector (gather warps)
-    k2_bar_vec_wait();
+    k2_bar_full_wait(s);
     K2_TICK(1);
 
     // ---- 2. this warp's rows of  base - F v
@@ -388,6 +410,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int s
       }
 #endif
       K2_TICK(2);
+      if (s + 2 < S) k2_bar_empty_arrive(s);  // this warp has read the vector of step s
       // packed shuffle tree: the halves of the warp swap rows first (lanes < 16 keep row 0,
       // lanes >= 16 row 1), then four stages inside each half: 10 double shuffles instead of 20
       double2 a0v = zadd(acc[0][0], acc[0][1]), a1v = zadd(acc[1][0], acc[1][1]);
@@ -416,6 +439,8 @@ __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int s
         if (op.save == 2) q.uvec[gi] = out;
       }
       K2_TICK(3);
+    } else if (s + 2 < S) {
+      k2_bar_empty_arrive(s);  // no rows of this step: nothing to read
     }
   }
   if (q.timing && tid == 0)

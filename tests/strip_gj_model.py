@@ -122,3 +122,66 @@ def strip_invert(S, w):
     M = np.empty_like(Y)
     M[:, rowpiv] = Y[rowpiv, :]
     return M
+
+
+def panel_gj_lazy(strip, isfree, scale, wk):
+    """The panel with LAZY normalisation of the pivot rows (what kb_chainfac.cu runs): a row that
+    pivots is not divided by its pivot -- it only remembers 1/pivot (`scale`) -- and is afterwards
+    updated like every other row, with the multiplier formed from its un-normalised entry:
+
+        true row = stored row * scale,      g~ = stored[i, c] / pivot' = scale^-1 g_true,
+        stored[i, :] -= g~ prow'[:]   <=>   true[i, :] -= g_true prow'[:]
+
+    so the scale cancels in every later update and is applied once, when the inverse is stored.
+    At its own pivot step the row does not change at all (multiplier 0) except that its entry in
+    the pivot column becomes 1 (true value 1/pivot).  This removes the special treatment of the
+    pivot row from the update of every column (no zeroing, no scaling pass)."""
+    stream = []
+    for c in range(wk):
+        mag = np.where(isfree, np.abs(strip[:, c]), -1.0)
+        r = int(np.argmax(mag))
+        isfree[r] = False
+        prow = strip[r, :].copy()           # a free row: stored == true
+        pinv = 1.0 / prow[c]
+        scale[r] = pinv
+        mult = -strip[:, c] * pinv
+        mult[r] = 0.0
+        elem = -mult
+        elem[r] = pinv                      # streamed: g~_i, or 1/pivot on the pivot row
+        stream.append((r, elem.copy()))
+        strip += np.outer(mult, prow)
+        strip[:, c] = mult
+        strip[r, c] = 1.0
+    return stream
+
+
+def apply_stream_lazy(A, stream):
+    """Consumer strips under lazy normalisation: A[i,:] -= g~_i A[piv,:] for i != piv; the pivot
+    row itself is left alone (its scale is taken from the stream element)."""
+    for r, elem in stream:
+        prow = A[r, :].copy()
+        g = elem.copy()
+        g[r] = 0.0
+        A -= np.outer(g, prow)
+    return A
+
+
+def strip_invert_lazy(S, w):
+    b = S.shape[0]
+    K = (b + w - 1) // w
+    strips = [S[:, k * w:min(b, (k + 1) * w)].astype(np.complex128).copy() for k in range(K)]
+    isfree = np.ones(b, dtype=bool)
+    scale = np.ones(b, dtype=np.complex128)
+    rowpiv = np.zeros(b, dtype=int)
+    for k in range(K):
+        k0 = k * w
+        wk = strips[k].shape[1]
+        stream = panel_gj_lazy(strips[k], isfree, scale, wk)
+        rowpiv[k0:k0 + wk] = [r for r, _ in stream]
+        for s in range(K):
+            if s != k:
+                apply_stream_lazy(strips[s], stream)
+    Y = np.concatenate(strips, axis=1) * scale[:, None]   # the scales are applied when M is stored
+    M = np.empty_like(Y)
+    M[:, rowpiv] = Y[rowpiv, :]
+    return M
