@@ -161,6 +161,8 @@ typedef struct {
   int64_t protocol_fallbacks; /* times a persistent kernel timed out and the handle fell back
                                  to the kernels without device-side waits (0 in a healthy run) */
   int64_t wait_error;     /* code | CTA << 8 of the last expired device-side wait (0: none)  */
+  int64_t shard_path;     /* last kb_factor: 0 one GPU, 1 l-sharded on the per-node kernels, 2 l-sharded
+                             on the strip factorisation + folded sweep (the fast path)           */
 } kb_stats;
 int kb_get_stats(kb_handle h, kb_stats* out);
 

@@ -46,7 +46,7 @@
 #define KF_SYNC_WORDS 512  // sync block: 2 x 96 words of counters, time-out flag at KF_ERR_WORD, ring counters from 192
 
 struct KfParams {
-  int P, mid;
+  int plo, P, mid;  // the chain is nodes [plo, P): group 0 walks plo .. mid, group 1 walks P-1 .. mid+1
   const int64_t* nodeptr;
   const int64_t* Moff;
   double2* M;
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(MAXT, 1) kb_chain_factor(KfParams q) {
   const int Gc = group == 0 ? q.G0 : (int)gridDim.x - q.G0;
   const int c = group == 0 ? (int)blockIdx.x : (int)blockIdx.x - q.G0;
   const int P = q.P, mid = q.mid;
-  const int S = group == 0 ? mid + 1 : P - 1 - mid;
+  const int S = group == 0 ? mid - q.plo + 1 : P - 1 - mid;
   unsigned* pub = q.sync + group * 96;
   unsigned* bar = q.sync + group * 96 + 32;
   unsigned* done1 = q.sync + 96 + 64;
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(MAXT, 1) kb_chain_factor(KfParams q) {
 #endif
 
   for (int s = 0; s < S; ++s) {
-    const int p = group == 0 ? s : P - 1 - s;
+    const int p = group == 0 ? q.plo + s : P - 1 - s;
     const int o = (int)q.nodeptr[p], b = (int)q.nodeptr[p + 1] - o;
     int w = (b + Gc - 1) / Gc;
     if (w < KF_WMIN) w = KF_WMIN;
@@ -286,13 +286,13 @@ __global__ void __launch_bounds__(MAXT, 1) kb_chain_factor(KfParams q) {
     for (int j = 0; j < NB; ++j) a[j] = zmake(0.0, 0.0);
 
     // the middle node needs the last node of the other chain
-    if (group == 0 && s == mid && mid < P - 1) kf_wait(done1, 1u, q.err, q.wait_ns, kw);
+    if (group == 0 && p == mid && mid < P - 1) kf_wait(done1, 1u, q.err, q.wait_ns, kw);
 
     // ---- Schur block, strip-wise:  S = D_p - C_pq M_q C_qp  (one or two eliminated neighbours)
     if (active) {
       if (group == 0 && s > 0) kf_schur_term<NB>(q, a, 0, p, p - 1, j0, ws, Ws);
       if (group == 1 && s > 0) kf_schur_term<NB>(q, a, 1, p, p + 1, j0, ws, Ws);
-      if (group == 0 && s == mid && mid < P - 1) kf_schur_term<NB>(q, a, 1, p, p + 1, j0, ws, Ws);
+      if (group == 0 && p == mid && mid < P - 1) kf_schur_term<NB>(q, a, 1, p, p + 1, j0, ws, Ws);
       if (t < b) {
         // D_p[t, strip]: the row's own-node entries are sorted by column; lower bound, then <= ws entries
         const int gi = o + t;
@@ -644,11 +644,13 @@ bool kbi_chainfac_supported(const kb_context* h) {
   return true;
 }
 
-// Factor the whole chain (T must have been built).  two_sided: eliminate from both ends
-// towards node mid; otherwise top-down only (mid = P-1).
-int kbi_chainfac_run(kb_context* h, bool two_sided, bool transposed) {
+// Factor the chain nodes [plo, phi) as a block-tridiagonal system of their own (T must have been
+// built; phi < 0: the whole chain).  two_sided: eliminate from both ends towards node h->mid;
+// otherwise top-down only (h->mid = phi - 1).
+int kbi_chainfac_run(kb_context* h, bool two_sided, bool transposed, int64_t plo, int64_t phi) {
   cudaStream_t s = h->stream;
-  const int64_t P = h->P, bmax = h->bmax;
+  const int64_t bmax = h->bmax;
+  if (phi < 0) phi = h->P;
   int dev = h->device, sms = 0, coop = 0;
   KB_CUDA(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   KB_CUDA(h, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
@@ -659,7 +661,8 @@ int kbi_chainfac_run(kb_context* h, bool two_sided, bool transposed) {
     if (g >= 2 && g < G) G = g;
   }
   KfParams q;
-  q.P = (int)P;
+  q.plo = (int)plo;
+  q.P = (int)phi;
   q.mid = (int)h->mid;
   q.nodeptr = h->d_nodeptr.p;
   q.Moff = h->d_Moff.p;

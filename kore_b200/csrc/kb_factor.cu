@@ -737,6 +737,9 @@ int kbi_factor(kb_context* h, zcomplex sigma) {
   h->fold_ready = false;
   h->rng_valid = false;
   h->sigma = sigma;
+  h->ch_lo = 0;
+  h->ch_hi = P;
+  h->stats.shard_path = 0;
   kbi_drop_graphs(h);
 
   KbEventPair ev;

@@ -342,7 +342,9 @@ struct kb_context {
   DevBuf<unsigned char> d_foldops, d_foldring;
   int fold_npub[2] = {0, 0}, fold_nops[2] = {0, 0};
   unsigned long long fold_epoch[2] = {0, 0};
-  int64_t mid = 0;  // middle node of the two-sided elimination (P-1: one-sided)
+  int64_t mid = 0;  // middle node of the two-sided elimination (ch_hi-1: one-sided)
+  int64_t ch_lo = 0, ch_hi = 0;  // the chain factored on this GPU: [0, P), or the rank's interior when l-sharded
+  std::vector<int64_t> FLoff, FUoff;  // offsets of FL_p / FU_p in d_fold (-1: not folded)
   // ELL copies of the couplings + node tables for the persistent sweep kernel
   int WL = 0, WU = 0;
   DevBuf<double2> d_Lval, d_Uval;
@@ -397,6 +399,11 @@ struct kb_context {
   DevBuf<double2> d_Mr, d_Csub, d_Csup;       // reduced system: inverses and couplings (G-1 nodes)
   DevBuf<double2> d_sepvec, d_sepvec_all;     // per-solve separator contributions
   DevBuf<double2> d_redz;                     // reduced-solve scratch
+  DevBuf<unsigned> d_redctr;                  // grid-barrier counter of the fused reduced solve
+  unsigned red_epoch = 0;
+  int red_grid = 0;
+  bool shard_fast = false;                    // interior factored by the strip kernel, solved by the folded sweep
+  DevBuf<double2> d_spk;                      // fast path: identity-column chains and corner blocks of T_I^{-1}
 
   kb_stats stats;
   int64_t launches = 0;
@@ -439,7 +446,7 @@ int kbi_upload_raw(kb_context* h, KbRawCSR& M, int64_t n, int index_bytes, const
 int kbi_layout_device(kb_context* h);
 // ---- kb_chainfac.cu
 bool kbi_chainfac_supported(const kb_context* h);
-int kbi_chainfac_run(kb_context* h, bool two_sided, bool transposed);
+int kbi_chainfac_run(kb_context* h, bool two_sided, bool transposed, int64_t plo = 0, int64_t phi = -1);
 // ---- kb_solve.cu
 //  chain solve in scaled/permuted space: d_y <- T'^{-1} d_r (d_r preserved)
 int kbi_chain_solve(kb_context* h, const double2* r_dev, double2* x_dev, int refine);
@@ -471,7 +478,7 @@ int kbi_sweep_onehop(kb_context* h, const double2* r, double2* y);
 int kbi_fold_grid(const kb_context* h, bool two_sided);
 bool kbi_fold_supported(const kb_context* h, int G, bool two_sided, int* slice_elems_out, size_t* smem_out);
 int kbi_fold_prepare(kb_context* h);
-int kbi_sweep_fold(kb_context* h, const double2* r, double2* y);
+int kbi_sweep_fold(kb_context* h, const double2* r, double2* y, int ends_only = 0);
 // ---- kb_shard.cu
 int kbi_factor_sharded(kb_context* h, zcomplex sigma);
 int kbi_chain_solve_sharded(kb_context* h, const double2* r_dev, double2* x_dev, int refine);

@@ -19,6 +19,8 @@
 // basis is replicated; only the operator is sharded).
 // tests/shard_model.py is the numpy statement of the same algebra.
 #include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <nccl.h>
 
 #include "kb_internal.cuh"
@@ -181,61 +183,6 @@ __global__ void kb_scatter_part(double2* __restrict__ Out, int nc, int o, int pa
   for (int64_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) Out[(size_t)i * nc + (col[k] - ocol)] = T[k];
 }
 
-// C (m x n) = alpha A (m x k) B (k x n) + beta C, row-major.  64 x 64 tile, 16-deep, 4 x 4 per thread.
-__global__ void __launch_bounds__(256)
-kb_zgemm(int m, int n, int k, double2 alpha, const double2* __restrict__ A, int lda,
-         const double2* __restrict__ B, int ldb, double2 beta, double2* __restrict__ C, int ldc) {
-  __shared__ double2 As[16][64 + 1];
-  __shared__ double2 Bs[16][64];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int row0 = blockIdx.y * 64, col0 = blockIdx.x * 64;
-  double2 acc[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) acc[a][c] = zmake(0.0, 0.0);
-  for (int kk = 0; kk < k; kk += 16) {
-    for (int e = tid; e < 64 * 16; e += 256) {
-      int i = e / 16, q = e % 16;  // A tile: 64 rows x 16 k
-      int gi = row0 + i, gk = kk + q;
-      As[q][i] = (gi < m && gk < k) ? A[(size_t)gi * lda + gk] : zmake(0.0, 0.0);
-    }
-    for (int e = tid; e < 16 * 64; e += 256) {
-      int q = e / 64, j = e % 64;  // B tile: 16 k x 64 cols
-      int gk = kk + q, gj = col0 + j;
-      Bs[q][j] = (gk < k && gj < n) ? B[(size_t)gk * ldb + gj] : zmake(0.0, 0.0);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      double2 av[4], bv[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) av[a] = As[q][ty + 16 * a];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) bv[c] = Bs[q][tx + 16 * c];
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) zfma(acc[a][c], av[a], bv[c]);
-    }
-    __syncthreads();
-  }
-  const bool has_beta = beta.x != 0.0 || beta.y != 0.0;
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    int gi = row0 + ty + 16 * a;
-    if (gi >= m) continue;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      int gj = col0 + tx + 16 * c;
-      if (gj >= n) continue;
-      double2 v = zmul(alpha, acc[a][c]);
-      if (has_beta) v = zadd(v, zmul(beta, C[(size_t)gi * ldc + gj]));
-      C[(size_t)gi * ldc + gj] = v;
-    }
-  }
-}
-
 // y (op)= Mat (m x k, ld) x      mode 0: y = Mx, 1: y -= Mx, 2: y += Mx   (one warp per row)
 __global__ void kb_dense_gemv(const double2* __restrict__ Mat, int m, int k, int ld,
                               const double2* __restrict__ x, double2* __restrict__ y, int mode) {
@@ -273,11 +220,283 @@ __global__ void kb_first_panel(const double2* __restrict__ S, int n, int nb0, do
   for (int j = 0; j < nb0 && j < n; ++j) PT[(size_t)j * n + i] = S[(size_t)i * n + j];
 }
 
+// ---------------------------------------------------------------------------
+// Batched dense products of the fast l-sharded factorisation (below): up to four independent
+// C = beta C + alpha op(A) B, one problem per blockIdx.z, row-major, 64 x 64 tiles, 16 deep,
+// 4 x 4 complex accumulators per thread, the next tile loaded into registers while the current
+// one is multiplied (one shared-memory stage: 33 KB).  op(A) = A^T reads A (k x m, row-major) by columns -- the explicit inverses
+// are stored transposed.  FP64 FMA issue is the bound: 64 DFMA per thread and k-step against 8
+// 16-byte shared-memory loads, two of which are warp broadcasts.
+// ---------------------------------------------------------------------------
+struct KbGemmProb {
+  int m, n, k, transA;
+  const double2* A;
+  int lda;
+  const double2* B;
+  int ldb;
+  double2* C;
+  int ldc;
+  double alpha, beta;
+};
+struct KbGemmBatch {
+  KbGemmProb p[4];
+};
+
+__global__ void __launch_bounds__(256) kb_zgemm_batch(KbGemmBatch batch) {
+  const KbGemmProb& g = batch.p[blockIdx.z];
+  const int m = g.m, n = g.n, k = g.k;
+  const int row0 = blockIdx.y * 64, col0 = blockIdx.x * 64;
+  if (row0 >= m || col0 >= n) return;
+  __shared__ double2 As[16][64 + 1];
+  __shared__ double2 Bs[16][64];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const double2* __restrict__ A = g.A;
+  const double2* __restrict__ B = g.B;
+  const int lda = g.lda, ldb = g.ldb;
+  double2 acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[a][c] = zmake(0.0, 0.0);
+  // element e of the A tile handled by this thread: four per tile
+  //   no transpose: (i = e / 16, q = e % 16) -> consecutive threads read consecutive k (row of A)
+  //   transpose   : (q = e / 64, i = e % 64) -> consecutive threads read consecutive i (row of A^T's source)
+  double2 ra[4], rb[4];
+  auto load_tiles = [&](int kk) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = tid + 256 * u;
+      int i, q;
+      if (g.transA) {
+        q = e >> 6;
+        i = e & 63;
+      } else {
+        i = e >> 4;
+        q = e & 15;
+      }
+      const int gi = row0 + i, gk = kk + q;
+      const bool ok = gi < m && gk < k;
+      ra[u] = ok ? (g.transA ? A[(size_t)gk * lda + gi] : A[(size_t)gi * lda + gk]) : zmake(0.0, 0.0);
+      const int qb = e >> 6, j = e & 63;
+      const int gkb = kk + qb, gj = col0 + j;
+      rb[u] = (gkb < k && gj < n) ? B[(size_t)gkb * ldb + gj] : zmake(0.0, 0.0);
+    }
+  };
+  auto store_tiles = [&]() {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = tid + 256 * u;
+      int i, q;
+      if (g.transA) {
+        q = e >> 6;
+        i = e & 63;
+      } else {
+        i = e >> 4;
+        q = e & 15;
+      }
+      As[q][i] = ra[u];
+      Bs[e >> 6][e & 63] = rb[u];
+    }
+  };
+  load_tiles(0);
+  store_tiles();
+  __syncthreads();
+  for (int kk = 0; kk < k; kk += 16) {
+    const bool more = kk + 16 < k;
+    if (more) load_tiles(kk + 16);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      double2 av[4], bv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) av[a] = As[q][ty + 16 * a];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) bv[c] = Bs[q][tx + 16 * c];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) zfma(acc[a][c], av[a], bv[c]);
+    }
+    if (more) {
+      __syncthreads();
+      store_tiles();
+      __syncthreads();
+    }
+  }
+  double2* __restrict__ C = g.C;
+  const int ldc = g.ldc;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int gi = row0 + ty + 16 * a;
+    if (gi >= m) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int gj = col0 + tx + 16 * c;
+      if (gj >= n) continue;
+      double2 v = zscale(acc[a][c], g.alpha);
+      if (g.beta != 0.0) v = zadd(v, zscale(C[(size_t)gi * ldc + gj], g.beta));
+      C[(size_t)gi * ldc + gj] = v;
+    }
+  }
+}
+
+struct GemmQueue {
+  KbGemmBatch b;
+  int count = 0, mmax = 0, nmax = 0;
+  void add(int m, int n, int k, double alpha, const double2* A, int lda, bool transA, const double2* B, int ldb,
+           double beta, double2* C, int ldc) {
+    if (m <= 0 || n <= 0) return;
+    KbGemmProb& g = b.p[count++];
+    g.m = m;
+    g.n = n;
+    g.k = k;
+    g.transA = transA ? 1 : 0;
+    g.A = A;
+    g.lda = lda;
+    g.B = B;
+    g.ldb = ldb;
+    g.C = C;
+    g.ldc = ldc;
+    g.alpha = alpha;
+    g.beta = beta;
+    if (m > mmax) mmax = m;
+    if (n > nmax) nmax = n;
+  }
+  void flush(kb_context* h) {
+    if (!count) return;
+    dim3 grid((nmax + 63) / 64, (mmax + 63) / 64, count);
+    kb_zgemm_batch<<<grid, 256, 0, h->stream>>>(b);
+    h->launches++;
+    count = mmax = nmax = 0;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Reduced (separator) solve in ONE cooperative launch.  With E_j = Mr_j Csub_j and
+// Fm_j = Mr_j Csup_{j+1} formed at factor time the block-Thomas recurrences on the G-1 separators are
+//     z_j = Mr_j rho_j - E_j z_{j-1}   (j = 0 .. G-2),      rho_j = tb_j - at_{j+1} (gathered contributions)
+//     x_j = z_j - Fm_j x_{j+1}         (j = G-3 .. 0),      x_{G-2} = z_{G-2}
+// 2 (G-1) - 1 dependent dense matrix-vector steps: one warp per row, a grid barrier per step (the
+// per-step kernels this replaces cost 0.35 ms per solve at G = 8, a third of the l-sharded solve).
+// ---------------------------------------------------------------------------
+#define KB_MAXSEP 16
+struct KbRedParams {
+  int nsep, bmax;
+  int bs[KB_MAXSEP];
+  const double2* Mr[KB_MAXSEP];
+  const double2* E[KB_MAXSEP];   // bs_j x bs_{j-1}; unused for j = 0
+  const double2* Fm[KB_MAXSEP];  // bs_j x bs_{j+1}; unused for j = nsep-1
+  double2* xout[KB_MAXSEP];      // where x_j goes (the solution vector at separator j)
+  const double2* sepvec_all;     // per rank 2 bmax entries: [at | tb]
+  double2* z;                    // nsep x bmax
+  unsigned* ctr;
+  unsigned epoch0;
+  int* err;
+  unsigned long long wait_ns;
+};
+
+__device__ __forceinline__ void kb_red_sync(unsigned* ctr, unsigned epoch, int* err, unsigned long long wait_ns) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned target = epoch * gridDim.x;
+    unsigned v;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+    KbSpin sp;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      if ((int)(v - target) >= 0) break;
+      if (kb_spin_expired(sp, err, KB_WERR_SWEEP, wait_ns)) break;
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) kb_reduced_solve_kernel(KbRedParams q) {
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * 8 + (threadIdx.x >> 5), nw = gridDim.x * 8;
+  unsigned epoch = q.epoch0;
+  const size_t bm = (size_t)q.bmax;
+  for (int j = 0; j < q.nsep; ++j) {
+    const int bs = q.bs[j], bsp = j > 0 ? q.bs[j - 1] : 0;
+    const double2* tb = q.sepvec_all + (size_t)j * 2 * bm + bm;
+    const double2* at = q.sepvec_all + (size_t)(j + 1) * 2 * bm;
+    const double2* zp = q.z + (size_t)(j > 0 ? j - 1 : 0) * bm;
+    for (int row = gw; row < bs; row += nw) {
+      double2 acc = zmake(0.0, 0.0);
+      const double2* Mrow = q.Mr[j] + (size_t)row * bs;
+#pragma unroll 4
+      for (int c = lane; c < bs; c += 32) zfma(acc, Mrow[c], zsub(tb[c], at[c]));
+      if (j > 0) {
+        const double2* Erow = q.E[j] + (size_t)row * bsp;
+#pragma unroll 4
+        for (int c = lane; c < bsp; c += 32) zfms(acc, Erow[c], __ldcg(&zp[c]));
+      }
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, sft);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, sft);
+      }
+      if (lane == 0) {
+        q.z[(size_t)j * bm + row] = acc;
+        if (j == q.nsep - 1) q.xout[j][row] = acc;
+      }
+    }
+    if (q.nsep > 1) kb_red_sync(q.ctr, ++epoch, q.err, q.wait_ns);
+  }
+  for (int j = q.nsep - 2; j >= 0; --j) {
+    const int bs = q.bs[j], bsn = q.bs[j + 1];
+    const double2* xn = q.xout[j + 1];
+    for (int row = gw; row < bs; row += nw) {
+      double2 acc = zmake(0.0, 0.0);
+      const double2* Frow = q.Fm[j] + (size_t)row * bsn;
+#pragma unroll 4
+      for (int c = lane; c < bsn; c += 32) zfma(acc, Frow[c], __ldcg(&xn[c]));
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, sft);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, sft);
+      }
+      if (lane == 0) q.xout[j][row] = zsub(__ldcg(&q.z[(size_t)j * bm + row]), acc);
+    }
+    if (j > 0) kb_red_sync(q.ctr, ++epoch, q.err, q.wait_ns);
+  }
+}
+
+// one product C = alpha A B + beta C
 static void zgemm(kb_context* h, int m, int n, int k, double alpha, const double2* A, int lda, const double2* B,
                   int ldb, double beta, double2* C, int ldc) {
-  dim3 grid((n + 63) / 64, (m + 63) / 64);
-  kb_zgemm<<<grid, 256, 0, h->stream>>>(m, n, k, zmake(alpha, 0.0), A, lda, B, ldb, zmake(beta, 0.0), C, ldc);
-  h->launches++;
+  GemmQueue q;
+  q.add(m, n, k, alpha, A, lda, false, B, ldb, beta, C, ldc);
+  q.flush(h);
+}
+
+__global__ void kb_set_identity(double2* __restrict__ A, int b) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < (int64_t)b * b) A[e] = zmake((e / b) == (e % b) ? 1.0 : 0.0, 0.0);
+}
+
+// Right-hand side of the second pass of the l-sharded solve, rows of this rank's interior:
+//   out = r - L_{f,top} y_top   on the first interior node (rows [of, of+bf)), if there is a separator above,
+//   out = r - U_{l,bot} y_bot   on the last interior node  (rows [ol, ol+bl)), if there is one below,
+//   out = r                      elsewhere.  One warp per row.
+__global__ void __launch_bounds__(256)
+kb_shard_rhs(int row_lo, int row_hi, int of, int bf, int use_l, int ol, int bl, int use_u,
+             const double2* __restrict__ r, const double2* __restrict__ y, double2* __restrict__ out,
+             const int64_t* __restrict__ rowptr, const int64_t* __restrict__ dstart,
+             const int64_t* __restrict__ ustart, const int* __restrict__ col, const double2* __restrict__ T) {
+  const int lane = threadIdx.x & 31;
+  const int gi = row_lo + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gi >= row_hi) return;
+  double2 acc = zmake(0.0, 0.0);
+  if (use_l && gi >= of && gi < of + bf)
+    for (int64_t k = rowptr[gi] + lane; k < dstart[gi]; k += 32) zfma(acc, T[k], y[col[k]]);
+  if (use_u && gi >= ol && gi < ol + bl)
+    for (int64_t k = ustart[gi] + lane; k < rowptr[gi + 1]; k += 32) zfma(acc, T[k], y[col[k]]);
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, s);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, s);
+  }
+  if (lane == 0) out[gi] = zsub(r[gi], acc);
 }
 
 static inline int nsize(const kb_context* h, int64_t p) { return (int)(h->nodeptr[p + 1] - h->nodeptr[p]); }
@@ -286,6 +505,57 @@ static inline int noff(const kb_context* h, int64_t p) { return (int)h->nodeptr[
 // ---------------------------------------------------------------------------
 // factor
 // ---------------------------------------------------------------------------
+// per-phase device times of the fast path on stderr when KB_SHARD_TIMING is set
+struct PhaseTimer {
+  bool on;
+  cudaStream_t s;
+  std::vector<cudaEvent_t> ev;
+  std::vector<const char*> names;
+  PhaseTimer(cudaStream_t st) : on(getenv("KB_SHARD_TIMING") != nullptr), s(st) { mark("start"); }
+  ~PhaseTimer() {
+    for (auto e : ev) cudaEventDestroy(e);
+  }
+  void mark(const char* name) {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    ev.push_back(e);
+    names.push_back(name);
+  }
+  void report(int rank) {
+    if (!on) return;
+    cudaStreamSynchronize(s);
+    std::string line = "libkoreb200: shard timing rank " + std::to_string(rank) + ":";
+    for (size_t i = 1; i < ev.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+      char buf[64];
+      snprintf(buf, sizeof(buf), " %s %.2f ms", names[i], ms);
+      line += buf;
+    }
+    fprintf(stderr, "%s\n", line.c_str());
+    for (auto e : ev) cudaEventDestroy(e);
+    ev.clear();
+  }
+};
+
+static int reduced_factor(kb_context* h, double* flops);
+static int factor_sharded_fast(kb_context* h, double* flops, int64_t* bytes);
+
+// The fast path needs the strip kernel and the folded sweep on this rank's interior
+static bool shard_fast_supported(kb_context* h) {
+  if (getenv("KB_SHARD_GENERAL")) return false;
+  if (h->safe_mode || h->opt_sweep != 1 || h->opt_fold == 0 || h->opt_factor == 0) return false;
+  if (!kbi_chainfac_supported(h)) return false;
+  const bool two = h->int_hi - h->int_lo >= 4;
+  const bool was = h->M_transposed;
+  h->M_transposed = true;
+  const bool ok = kbi_fold_supported(h, kbi_fold_grid(h, two), two, nullptr, nullptr);
+  h->M_transposed = was;
+  return ok;
+}
+
 int kbi_factor_sharded(kb_context* h, zcomplex sigma) {
   if (!h->chain_set) return kb_fail(h, KB_EINVAL, "kb_set_chain must be called before kb_factor");
   if (!h->nccl_comm) return kb_fail(h, KB_EINVAL, "kb_set_sharding must be called before kb_factor");
@@ -294,6 +564,9 @@ int kbi_factor_sharded(kb_context* h, zcomplex sigma) {
   const int64_t P = h->P, bmax = h->bmax;
   const int G = h->nranks, g = h->rank;
   h->factored = false;
+  h->fold_ready = false;
+  h->M_transposed = false;
+  h->shard_fast = false;
   h->sigma = sigma;
   kbi_drop_graphs(h);
 
@@ -303,6 +576,56 @@ int kbi_factor_sharded(kb_context* h, zcomplex sigma) {
   KB_CUDA(h, cudaEventRecord(e0, s));
   KB_TRY(kbi_build_T(h, sigma));
   KB_TRY(kbi_factor_workspace(h));
+
+  {
+    // storage of the interior inverses; node tables, ELL couplings and the sweep grid on the device
+    h->Moff.assign(P + 1, 0);
+    int64_t mt = 0;
+    for (int64_t p = h->int_lo; p < h->int_hi; ++p) {
+      const int64_t b = h->nodeptr[p + 1] - h->nodeptr[p];
+      h->Moff[p] = mt;
+      mt += b * b;
+    }
+    if (h->d_M.alloc((size_t)mt) != cudaSuccess)
+      return kb_fail(h, KB_ENOMEM, "cannot allocate %.2f GB for this rank's chain factors", mt * 16.0 / 1e9);
+    KB_TRY(kbi_sweep_prepare(h));
+    KB_CUDA(h, h->d_contrib.alloc(4 * (size_t)bmax * bmax));
+    KB_CUDA(h, h->d_contrib_all.alloc(4 * (size_t)bmax * bmax * G));
+    KB_CUDA(h, cudaMemsetAsync(h->d_contrib.p, 0, 4 * (size_t)bmax * bmax * sizeof(double2), s));
+  }
+  if (shard_fast_supported(h)) {
+    double flops = 0.0;
+    int64_t bytes = 0;
+    KB_TRY(factor_sharded_fast(h, &flops, &bytes));
+    PhaseTimer pt(s);
+    KB_NCCL(h, g_nccl.AllGather(h->d_contrib.p, h->d_contrib_all.p, 4 * (size_t)bmax * bmax * 2, ncclDouble,
+                                (ncclComm_t)h->nccl_comm, s));
+    pt.mark("allgather");
+    KB_TRY(reduced_factor(h, &flops));
+    pt.mark("reduced-factor");
+    pt.report(g);
+    KB_CUDA(h, cudaEventRecord(e1, s));
+    KB_TRY(kbi_sync(h));
+    int info = 0, kerr = 0;
+    KB_CUDA(h, cudaMemcpy(&info, h->d_info.p, sizeof(int), cudaMemcpyDeviceToHost));
+    KB_CUDA(h, cudaMemcpy(&kerr, h->d_kfsync.p + KF_ERR_WORD, sizeof(int), cudaMemcpyDeviceToHost));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    h->stats.factor_ms = ms;
+    h->stats.factor_flops = flops;
+    h->stats.factor_bytes = bytes;
+    if (kerr != 0)
+      return kb_fail(h, KB_ECUDA, "a device-side wait of the strip factorisation expired on rank %d (code %d, CTA %d)",
+                     g, kerr & 255, kerr >> 8);
+    if (info != 0) return kb_fail(h, KB_ESINGULAR, "zero or non-finite pivot in a Schur block on rank %d", g);
+    h->shard_fast = true;
+    h->stats.shard_path = 2;
+    h->factored = true;
+    return KB_OK;
+  }
+  h->stats.shard_path = 1;
 
   const int64_t lo = h->int_lo, hi = h->int_hi;
   const bool has_top = h->top_sep >= 0, has_bot = h->bot_sep >= 0;
@@ -415,7 +738,34 @@ int kbi_factor_sharded(kb_context* h, zcomplex sigma) {
   KB_NCCL(h, g_nccl.AllGather(h->d_contrib.p, h->d_contrib_all.p, 4 * slot * 2, ncclDouble,
                               (ncclComm_t)h->nccl_comm, s));
 
-  // ---- reduced system, factored redundantly on every rank: node j = separator of rank j
+  KB_TRY(reduced_factor(h, &flops));
+
+  KB_CUDA(h, cudaEventRecord(e1, s));
+  int info = 0;
+  KB_CUDA(h, cudaMemcpyAsync(&info, h->d_info.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  KB_CUDA(h, cudaStreamSynchronize(s));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  h->stats.factor_ms = ms;
+  h->stats.factor_flops = flops;
+  h->stats.factor_bytes = (mtot + 2 * vtot + (int64_t)slot * (G - 1)) * 16;
+  if (info != 0)
+    return kb_fail(h, KB_ESINGULAR, "zero or non-finite pivot in a Schur block on rank %d", g);
+  h->factored = true;
+  return KB_OK;
+}
+
+
+// ---- reduced (separator) system, factored redundantly on every rank: node j = separator of rank j
+static int reduced_factor(kb_context* h, double* flops_io) {
+  cudaStream_t s = h->stream;
+  const int64_t bmax = h->bmax;
+  const int G = h->nranks;
+  const size_t slot = (size_t)bmax * bmax;
+  double flops = 0.0;
+  KB_CUDA(h, h->d_F.alloc(slot));
   KB_CUDA(h, h->d_Mr.alloc(slot * (G - 1)));
   for (int j = 0; j < G - 1; ++j) {
     const int bs = nsize(h, h->seg_hi[j] - 1);
@@ -438,31 +788,362 @@ int kbi_factor_sharded(kb_context* h, zcomplex sigma) {
     flops += 8.0 * (double)bs * bs * bs;
     KB_LAUNCH_CHECK(h);
   }
+  // E_j = Mr_j Csub_j, Fm_j = Mr_j Csup_{j+1}: the fused reduced solve (kb_reduced_solve_kernel)
+  KB_CUDA(h, h->d_Csub.alloc(slot * (G - 1)));
+  KB_CUDA(h, h->d_Csup.alloc(slot * (G - 1)));
+  {
+    GemmQueue q;
+    for (int j = 0; j < G - 1; ++j) {
+      const int bs = nsize(h, h->seg_hi[j] - 1);
+      const double2* Mr = h->d_Mr.p + (size_t)j * slot;
+      if (j > 0) {
+        const int bsp = nsize(h, h->seg_hi[j - 1] - 1);
+        q.add(bs, bsp, bs, 1.0, Mr, bs, false, h->d_contrib_all.p + (size_t)j * 4 * slot + 2 * slot, bsp, 0.0,
+              h->d_Csub.p + (size_t)j * slot, bsp);
+        flops += 8.0 * (double)bs * bsp * bs;
+        if (q.count == 4) q.flush(h);
+      }
+      if (j < G - 2) {
+        const int bsn = nsize(h, h->seg_hi[j + 1] - 1);
+        q.add(bs, bsn, bs, 1.0, Mr, bs, false, h->d_contrib_all.p + (size_t)(j + 1) * 4 * slot + 3 * slot, bsn, 0.0,
+              h->d_Csup.p + (size_t)j * slot, bsn);
+        flops += 8.0 * (double)bs * bsn * bs;
+        if (q.count == 4) q.flush(h);
+      }
+    }
+    q.flush(h);
+    KB_LAUNCH_CHECK(h);
+  }
   KB_CUDA(h, h->d_sepvec.alloc(2 * bmax));
   KB_CUDA(h, h->d_sepvec_all.alloc((size_t)2 * bmax * G));
   KB_CUDA(h, h->d_redz.alloc((size_t)2 * bmax * G));
 
-  KB_CUDA(h, cudaEventRecord(e1, s));
-  int info = 0;
-  KB_CUDA(h, cudaMemcpyAsync(&info, h->d_info.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-  KB_CUDA(h, cudaStreamSynchronize(s));
-  float ms = 0.f;
-  cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  h->stats.factor_ms = ms;
-  h->stats.factor_flops = flops;
-  h->stats.factor_bytes = (mtot + 2 * vtot + (int64_t)slot * (G - 1)) * 16;
-  if (info != 0)
-    return kb_fail(h, KB_ESINGULAR, "zero or non-finite pivot in a Schur block on rank %d", g);
-  h->factored = true;
+  *flops_io += flops;
+  return KB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Fast l-sharded factorisation: the rank's interior [lo, hi) is a block-tridiagonal system of
+// its own and goes through the SAME kernels as a whole pencil on one GPU -- two-sided strip
+// factorisation (kb_chainfac.cu), folded couplings (kb_sweep2.cu).  What the separators need from
+// it are the four corner blocks of G = T_I^{-1} (f / l = first / last interior node):
+//     G_ff, G_lf = column block f of G at rows f and l;   G_fl, G_ll = column block l.
+// A column block of G is the interior solve with an identity block as right-hand side, i.e. the
+// folded sweep with b right-hand sides: chains of dense products with the folded couplings,
+//     forward   Tf_f = I, Tf_{p+1} = -FL_p Tf_p (p < m);    Tl_l = I, Tl_{p-1} = -FU_p Tl_p (p > m)
+//     backward  U_{p-1} = T_{p-1} - FU_p U_p  (up),  U_{p+1} = T_{p+1} - FL_p U_p  (down),  U_m = T_m
+//     corner    G_{f,.} = M_f U_f,   G_{l,.} = M_l U_l
+// (T = 0 on the half of the chain the identity block is not in), three b x b x b products per
+// interior node in all, issued as batches of independent products (kb_zgemm_batch).  The reduced
+// system then receives
+//     slot 0: D_bot - L_{bot,l} G_ll U_{l,bot}      slot 1: U_{top,f} G_ff L_{f,top}
+//     slot 2: -L_{bot,l} G_lf L_{f,top}             slot 3: -U_{top,f} G_fl U_{l,bot}
+// exactly as from the general path above.
+// ---------------------------------------------------------------------------
+static int factor_sharded_fast(kb_context* h, double* flops_io, int64_t* bytes_io) {
+  cudaStream_t s = h->stream;
+  PhaseTimer pt(s);
+  const int64_t P = h->P, bmax = h->bmax;
+  const int64_t lo = h->int_lo, hi = h->int_hi, nI = hi - lo;
+  const bool has_top = h->top_sep >= 0, has_bot = h->bot_sep >= 0;
+  const size_t slot = (size_t)bmax * bmax;
+  const bool two = nI >= 4;
+  h->ch_lo = lo;
+  h->ch_hi = hi;
+  h->mid = two ? lo + nI / 2 : hi - 1;
+  h->M_transposed = true;
+  KB_TRY(kbi_chainfac_run(h, two, true, lo, hi));
+  pt.mark("strip-factor");
+  KB_TRY(kbi_fold_prepare(h));
+  pt.mark("fold");
+  if (!h->fold_ready) return kb_fail(h, KB_ENOMEM, "cannot set up the folded sweep on rank %d", h->rank);
+  double flops = 0.0;
+  int64_t mtot = 0;
+  for (int64_t p = lo; p < hi; ++p) {
+    const double b = (double)nsize(h, p);
+    flops += 8.0 * b * b * b;
+    mtot += (int64_t)b * (int64_t)b;
+  }
+  *bytes_io = 3 * mtot * 16;
+  if (!has_top && !has_bot) {
+    *flops_io += flops;
+    return KB_OK;
+  }
+
+  const int64_t f = lo, l = hi - 1, m = h->mid;
+  const int bf = nsize(h, f), bl = nsize(h, l);
+  // Tf_p (b_p x bf), p = f .. m;  Tl_p (b_p x bl), p = m .. l;  two ping-pong pairs;  four corners
+  std::vector<int64_t> tfo(P, -1), tlo(P, -1);
+  int64_t tot = 0;
+  for (int64_t p = f; p <= m; ++p) {
+    tfo[p] = tot;
+    tot += (int64_t)nsize(h, p) * bf;
+  }
+  for (int64_t p = m; p <= l; ++p) {
+    tlo[p] = tot;
+    tot += (int64_t)nsize(h, p) * bl;
+  }
+  if (h->d_spk.alloc((size_t)tot + 8 * slot) != cudaSuccess)
+    return kb_fail(h, KB_ENOMEM, "cannot allocate %.2f GB of spike workspace", (tot + 8 * slot) * 16.0 / 1e9);
+  double2* base = h->d_spk.p;
+  double2* pp = base + tot;  // ping-pong buffers [0..3], corners [4..7]
+  auto Tf = [&](int64_t p) { return base + tfo[p]; };
+  auto Tl = [&](int64_t p) { return base + tlo[p]; };
+  const double2* F = h->d_fold.p;
+  auto gflops = [&](int mm, int nn, int kk) { flops += 8.0 * (double)mm * nn * kk; };
+
+  kb_set_identity<<<nblk((int64_t)bf * bf, 256), 256, 0, s>>>(Tf(f), bf);
+  kb_set_identity<<<nblk((int64_t)bl * bl, 256), 256, 0, s>>>(Tl(l), bl);
+  h->launches += 2;
+  // ---- forward
+  {
+    int64_t pf = f, pl = l;
+    while (pf < m || pl > m) {
+      GemmQueue q;
+      if (pf < m) {
+        q.add(nsize(h, pf + 1), bf, nsize(h, pf), -1.0, F + h->FLoff[pf], nsize(h, pf), false, Tf(pf), bf, 0.0,
+              Tf(pf + 1), bf);
+        gflops(nsize(h, pf + 1), bf, nsize(h, pf));
+        ++pf;
+      }
+      if (pl > m) {
+        q.add(nsize(h, pl - 1), bl, nsize(h, pl), -1.0, F + h->FUoff[pl], nsize(h, pl), false, Tl(pl), bl, 0.0,
+              Tl(pl - 1), bl);
+        gflops(nsize(h, pl - 1), bl, nsize(h, pl));
+        --pl;
+      }
+      q.flush(h);
+    }
+  }
+  pt.mark("spike-forward");
+  // ---- backward: four independent chains in lock step
+  const double2* uf_l = Tf(m);  // U of column block f at node l (down chain; = Tf_m when m == l)
+  const double2* ul_f = Tl(m);  // U of column block l at node f (up chain;   = Tl_m when m == f)
+  {
+    int64_t up = m, dn = m;     // next step: up uses FU_up (-> node up-1), down uses FL_dn (-> node dn+1)
+    int tog = 0;
+    while (up > f || dn < l) {
+      GemmQueue q;
+      if (up > f) {
+        const int bo = nsize(h, up - 1), bi = nsize(h, up);
+        // column block f: Tf_{up-1} <- Tf_{up-1} - FU_up U_up   (U_up already sits in Tf_up)
+        q.add(bo, bf, bi, -1.0, F + h->FUoff[up], bi, false, Tf(up), bf, 1.0, Tf(up - 1), bf);
+        // column block l: U_{up-1} = -FU_up U_up
+        double2* out = pp + (size_t)(tog ? 1 : 0) * slot;
+        q.add(bo, bl, bi, -1.0, F + h->FUoff[up], bi, false, ul_f, bl, 0.0, out, bl);
+        ul_f = out;
+        gflops(bo, bf, bi);
+        gflops(bo, bl, bi);
+        --up;
+      }
+      if (dn < l) {
+        const int bo = nsize(h, dn + 1), bi = nsize(h, dn);
+        // column block l: Tl_{dn+1} <- Tl_{dn+1} - FL_dn U_dn
+        q.add(bo, bl, bi, -1.0, F + h->FLoff[dn], bi, false, Tl(dn), bl, 1.0, Tl(dn + 1), bl);
+        // column block f: U_{dn+1} = -FL_dn U_dn
+        double2* out = pp + (size_t)(tog ? 3 : 2) * slot;
+        q.add(bo, bf, bi, -1.0, F + h->FLoff[dn], bi, false, uf_l, bf, 0.0, out, bf);
+        uf_l = out;
+        gflops(bo, bl, bi);
+        gflops(bo, bf, bi);
+        ++dn;
+      }
+      q.flush(h);
+      tog ^= 1;
+    }
+  }
+  // ---- corners (the inverses are stored transposed)
+  double2 *Gff = pp + 4 * slot, *Glf = pp + 5 * slot, *Gfl = pp + 6 * slot, *Gll = pp + 7 * slot;
+  {
+    const double2* Mf = h->d_M.p + h->Moff[f];
+    const double2* Ml = h->d_M.p + h->Moff[l];
+    GemmQueue q;
+    q.add(bf, bf, bf, 1.0, Mf, bf, true, Tf(f), bf, 0.0, Gff, bf);
+    q.add(bl, bf, bl, 1.0, Ml, bl, true, uf_l, bf, 0.0, Glf, bf);
+    q.add(bf, bl, bf, 1.0, Mf, bf, true, ul_f, bl, 0.0, Gfl, bl);
+    q.add(bl, bl, bl, 1.0, Ml, bl, true, Tl(l), bl, 0.0, Gll, bl);
+    q.flush(h);
+    gflops(bf, bf, bf);
+    gflops(bl, bf, bl);
+    gflops(bf, bl, bf);
+    gflops(bl, bl, bl);
+  }
+  KB_LAUNCH_CHECK(h);
+  pt.mark("spike-backward+corners");
+  // ---- contributions to the reduced system
+  const int of = noff(h, f), ol = noff(h, l);
+  double2* X = h->d_W.p;  // bmax x bmax scratch
+  if (has_bot) {
+    const int ob = noff(h, h->bot_sep), bb = nsize(h, h->bot_sep);
+    // X = G_ll U_{l,bot};  slot 0 = D_bot - L_{bot,l} X
+    kb_dense_spcols<<<bl, 128, bl * sizeof(double2), s>>>(Gll, bl, ol, X, bb, ob, h->d_ucptr.p, h->d_urow.p,
+                                                          h->d_upos.p, h->d_Tval.p, 1.0);
+    kb_schur_row<<<bb, 128, 0, s>>>(h->d_contrib.p, h->d_PT.p, 0, bb, ob, X, ol, nullptr, 0, h->d_rowptr.p,
+                                    h->d_dstart.p, h->d_ustart.p, h->d_col.p, h->d_Tval.p);
+    h->launches += 2;
+  }
+  if (has_top) {
+    const int ot = noff(h, h->top_sep), bt = nsize(h, h->top_sep);
+    // X = G_ff L_{f,top};  slot 1 = U_{top,f} X
+    kb_dense_spcols<<<bf, 128, bf * sizeof(double2), s>>>(Gff, bf, of, X, bt, ot, h->d_lcptr.p, h->d_lrow.p,
+                                                          h->d_lpos.p, h->d_Tval.p, 1.0);
+    kb_sprows_dense<<<bt, 128, 0, s>>>(h->d_contrib.p + slot, bt, ot, 1, X, of, h->d_rowptr.p, h->d_dstart.p,
+                                       h->d_ustart.p, h->d_col.p, h->d_Tval.p, 1.0, 0);
+    h->launches += 2;
+  }
+  if (has_top && has_bot) {
+    const int ot = noff(h, h->top_sep), bt = nsize(h, h->top_sep);
+    const int ob = noff(h, h->bot_sep), bb = nsize(h, h->bot_sep);
+    // X = G_lf L_{f,top} (bl x bt);  slot 2 = -L_{bot,l} X  (bb x bt)
+    kb_dense_spcols<<<bl, 128, bf * sizeof(double2), s>>>(Glf, bf, of, X, bt, ot, h->d_lcptr.p, h->d_lrow.p,
+                                                          h->d_lpos.p, h->d_Tval.p, 1.0);
+    kb_sprows_dense<<<bb, 128, 0, s>>>(h->d_contrib.p + 2 * slot, bt, ob, 0, X, ol, h->d_rowptr.p, h->d_dstart.p,
+                                       h->d_ustart.p, h->d_col.p, h->d_Tval.p, -1.0, 0);
+    // X = G_fl U_{l,bot} (bf x bb);  slot 3 = -U_{top,f} X  (bt x bb)
+    kb_dense_spcols<<<bf, 128, bl * sizeof(double2), s>>>(Gfl, bl, ol, h->d_S1.p, bb, ob, h->d_ucptr.p, h->d_urow.p,
+                                                          h->d_upos.p, h->d_Tval.p, 1.0);
+    kb_sprows_dense<<<bt, 128, 0, s>>>(h->d_contrib.p + 3 * slot, bb, ot, 1, h->d_S1.p, of, h->d_rowptr.p,
+                                       h->d_dstart.p, h->d_ustart.p, h->d_col.p, h->d_Tval.p, -1.0, 0);
+    h->launches += 4;
+  }
+  KB_LAUNCH_CHECK(h);
+  pt.mark("contributions");
+  pt.report(h->rank);
+  *flops_io += flops;
   return KB_OK;
 }
 
 // ---------------------------------------------------------------------------
 // solve: y <- T'^{-1} r, full vectors (chain order, scaled space) on every rank
 // ---------------------------------------------------------------------------
+// reduced solve (redundant on every rank) from the gathered separator contributions:
+//   z_j = Mr_j (rho_j - Csub_j z_{j-1});  x_j = z_j - Mr_j Csup_{j+1} x_{j+1};  x_j -> y at separator j
+static int reduced_solve(kb_context* h, double2* y) {
+  cudaStream_t s = h->stream;
+  const int G = h->nranks;
+  const int64_t bmax = h->bmax;
+  const size_t slot = (size_t)bmax * bmax;
+  if (G - 1 > KB_MAXSEP) return kb_fail(h, KB_EINVAL, "more than %d separators", KB_MAXSEP);
+  KbRedParams q;
+  memset(&q, 0, sizeof(q));
+  q.nsep = G - 1;
+  q.bmax = (int)bmax;
+  for (int j = 0; j < G - 1; ++j) {
+    const int64_t sp = h->seg_hi[j] - 1;
+    q.bs[j] = nsize(h, sp);
+    q.Mr[j] = h->d_Mr.p + (size_t)j * slot;
+    q.E[j] = h->d_Csub.p + (size_t)j * slot;
+    q.Fm[j] = h->d_Csup.p + (size_t)j * slot;
+    q.xout[j] = y + noff(h, sp);
+  }
+  q.sepvec_all = h->d_sepvec_all.p;
+  q.z = h->d_redz.p;
+  int sms = 0;
+  KB_CUDA(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+  int grid = (int)((bmax + 7) / 8);  // one warp per row
+  if (grid > sms) grid = sms;
+  if (h->red_grid != grid || !h->d_redctr.p) {
+    KB_CUDA(h, h->d_redctr.alloc(32));
+    KB_CUDA(h, cudaMemsetAsync(h->d_redctr.p, 0, 32 * sizeof(unsigned), s));
+    h->red_grid = grid;
+    h->red_epoch = 0;
+  }
+  q.ctr = h->d_redctr.p;
+  q.epoch0 = h->red_epoch;
+  h->red_epoch += (unsigned)(2 * (G - 1));  // >= the barriers of one launch; the counter wraps with it
+  q.err = h->d_sweep_err.p;
+  q.wait_ns = h->wait_ns;
+  void* args[] = {(void*)&q};
+  KB_CUDA(h, cudaLaunchCooperativeKernel((const void*)kb_reduced_solve_kernel, dim3(grid), dim3(256), args, 0, s));
+  h->launches++;
+  return KB_OK;
+}
+
+// every rank publishes its interior; the separators are already everywhere
+static int publish_interiors(kb_context* h, double2* y) {
+  const int G = h->nranks;
+  // Segments of equal length (interior + the separator below it, whose value every rank already
+  // holds): ONE in-place all-gather.  Otherwise a grouped broadcast per rank.
+  const int64_t cnt0 = h->nodeptr[h->seg_hi[0]] - h->nodeptr[h->seg_lo[0]];
+  bool equal = true;
+  for (int q = 1; q < G; ++q) equal = equal && (h->nodeptr[h->seg_hi[q]] - h->nodeptr[h->seg_lo[q]] == cnt0);
+  if (equal) {
+    KB_NCCL(h, g_nccl.AllGather(y + (size_t)h->rank * cnt0, y, (size_t)cnt0 * 2, ncclDouble, (ncclComm_t)h->nccl_comm,
+                                h->stream));
+    return KB_OK;
+  }
+  KB_NCCL(h, g_nccl.GroupStart());
+  for (int q = 0; q < G; ++q) {
+    int64_t qlo = h->seg_lo[q], qhi = q < G - 1 ? h->seg_hi[q] - 1 : h->seg_hi[q];
+    int64_t off = h->nodeptr[qlo], cnt = h->nodeptr[qhi] - off;
+    KB_NCCL(h, g_nccl.Broadcast(y + off, y + off, (size_t)cnt * 2, ncclDouble, q, (ncclComm_t)h->nccl_comm,
+                                h->stream));
+  }
+  KB_NCCL(h, g_nccl.GroupEnd());
+  return KB_OK;
+}
+
+// Fast l-sharded solve (factors from factor_sharded_fast):
+//   pass 1  y_I = T_I^{-1} r_I by the folded sweep on the interior; only the end nodes' values are formed
+//   gather  rank g contributes r_bot - L_{bot,l} y_l to its lower separator and U_{top,f} y_f to its upper one
+//   reduced solve (redundant) -> the separator values
+//   pass 2  x_I = T_I^{-1} (r_I - T_{I,sep} x_sep): the folded sweep again on the corrected right-hand side
+//   publish interiors
+static int sharded_sweeps_fast(kb_context* h, const double2* r, double2* y) {
+  cudaStream_t s = h->stream;
+  const int64_t lo = h->int_lo, hi = h->int_hi, bmax = h->bmax;
+  const bool has_top = h->top_sep >= 0, has_bot = h->bot_sep >= 0;
+  const int64_t f = lo, l = hi - 1;
+  const int of = noff(h, f), bf = nsize(h, f), ol = noff(h, l), bl = nsize(h, l);
+  double2* t = h->d_t.p;
+  double2* sv = h->d_sepvec.p;
+  static int timed_solves = 0;
+  PhaseTimer pt(s);
+  if (timed_solves >= 3) pt.on = false;
+  KB_CUDA(h, cudaMemsetAsync(sv, 0, 2 * bmax * sizeof(double2), s));
+  KB_TRY(kbi_sweep_fold(h, r, y, 1));
+  pt.mark("pass1");
+  if (has_top) {
+    const int ot = noff(h, h->top_sep), bt = nsize(h, h->top_sep);
+    kb_node_tvec<1><<<(bt + 7) / 8, 256, 0, s>>>(bt, ot, r, y, t, h->d_rowptr.p, h->d_dstart.p, h->d_ustart.p,
+                                                 h->d_col.p, h->d_Tval.p);
+    KB_CUDA(h, cudaMemcpyAsync(sv, t + ot, (size_t)bt * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+    h->launches++;
+  }
+  if (has_bot) {
+    const int ob = noff(h, h->bot_sep), bb = nsize(h, h->bot_sep);
+    kb_node_tvec<0><<<(bb + 7) / 8, 256, 0, s>>>(bb, ob, r, y, t, h->d_rowptr.p, h->d_dstart.p, h->d_ustart.p,
+                                                 h->d_col.p, h->d_Tval.p);
+    KB_CUDA(h, cudaMemcpyAsync(sv + bmax, t + ob, (size_t)bb * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+    h->launches++;
+  }
+  KB_LAUNCH_CHECK(h);
+  pt.mark("sep-rhs");
+  KB_NCCL(h, g_nccl.AllGather(sv, h->d_sepvec_all.p, 2 * bmax * 2, ncclDouble, (ncclComm_t)h->nccl_comm, s));
+  pt.mark("allgather");
+  KB_TRY(reduced_solve(h, y));
+  pt.mark("reduced-solve");
+  if (has_top || has_bot) {
+    const int row_lo = of, row_hi = ol + bl;
+    kb_shard_rhs<<<nblk((int64_t)(row_hi - row_lo) * 32, 256), 256, 0, s>>>(
+        row_lo, row_hi, of, bf, has_top ? 1 : 0, ol, bl, has_bot ? 1 : 0, r, y, t, h->d_rowptr.p, h->d_dstart.p,
+        h->d_ustart.p, h->d_col.p, h->d_Tval.p);
+    h->launches++;
+    KB_TRY(kbi_sweep_fold(h, t, y, 0));
+  }
+  KB_LAUNCH_CHECK(h);
+  pt.mark("pass2");
+  KB_TRY(publish_interiors(h, y));
+  pt.mark("publish");
+  if (pt.on) {
+    ++timed_solves;
+    pt.report(h->rank);
+  }
+  return KB_OK;
+}
+
 int kbi_sharded_sweeps(kb_context* h, const double2* r, double2* y) {
+  if (h->shard_fast) return sharded_sweeps_fast(h, r, y);
   cudaStream_t s = h->stream;
   const int G = h->nranks, g = h->rank;
   const int64_t lo = h->int_lo, hi = h->int_hi, bmax = h->bmax, P = h->P;
@@ -498,34 +1179,7 @@ int kbi_sharded_sweeps(kb_context* h, const double2* r, double2* y) {
   KB_LAUNCH_CHECK(h);
   KB_NCCL(h, g_nccl.AllGather(sv, h->d_sepvec_all.p, 2 * bmax * 2, ncclDouble, (ncclComm_t)h->nccl_comm, s));
 
-  // ---- reduced solve (redundant): z_j = Mr_j (rho_j - Csub_j z_{j-1});  x_j = z_j - Mr_j Csup_{j+1} x_{j+1}
-  double2* z = h->d_redz.p;             // G-1 vectors of bmax
-  double2* tmp = h->d_redz.p + (size_t)bmax * G;
-  for (int j = 0; j < G - 1; ++j) {
-    const int bs = nsize(h, h->seg_hi[j] - 1);
-    const double2* tb = h->d_sepvec_all.p + (size_t)j * 2 * bmax + bmax;     // from rank j
-    const double2* at = h->d_sepvec_all.p + (size_t)(j + 1) * 2 * bmax;      // from rank j+1
-    kb_sub<<<nblk(bs, 256), 256, 0, s>>>(bs, tb, at, tmp);
-    if (j > 0) {
-      const int bsp = nsize(h, h->seg_hi[j - 1] - 1);
-      const double2* Csub = h->d_contrib_all.p + (size_t)j * 4 * slot + 2 * slot;
-      kb_dense_gemv<<<(bs + 7) / 8, 256, 0, s>>>(Csub, bs, bsp, bsp, z + (size_t)(j - 1) * bmax, tmp, 1);
-    }
-    kb_dense_gemv<<<(bs + 7) / 8, 256, 0, s>>>(h->d_Mr.p + (size_t)j * slot, bs, bs, bs, tmp, z + (size_t)j * bmax, 0);
-    h->launches += 3;
-  }
-  for (int j = G - 3; j >= 0; --j) {
-    const int bs = nsize(h, h->seg_hi[j] - 1), bsn = nsize(h, h->seg_hi[j + 1] - 1);
-    const double2* Csup = h->d_contrib_all.p + (size_t)(j + 1) * 4 * slot + 3 * slot;  // (bs x bsn)
-    kb_dense_gemv<<<(bs + 7) / 8, 256, 0, s>>>(Csup, bs, bsn, bsn, z + (size_t)(j + 1) * bmax, tmp, 0);
-    kb_dense_gemv<<<(bs + 7) / 8, 256, 0, s>>>(h->d_Mr.p + (size_t)j * slot, bs, bs, bs, tmp, z + (size_t)j * bmax, 1);
-    h->launches += 2;
-  }
-  for (int j = 0; j < G - 1; ++j) {
-    const int64_t sp = h->seg_hi[j] - 1;
-    KB_CUDA(h, cudaMemcpyAsync(y + noff(h, sp), z + (size_t)j * bmax, (size_t)nsize(h, sp) * sizeof(double2),
-                               cudaMemcpyDeviceToDevice, s));
-  }
+  KB_TRY(reduced_solve(h, y));
 
   // ---- backward over the interior, with the spike correction
   for (int64_t p = hi - 1; p >= lo; --p) {
@@ -544,16 +1198,10 @@ int kbi_sharded_sweeps(kb_context* h, const double2* r, double2* y) {
   }
   KB_LAUNCH_CHECK(h);
 
-  // ---- every rank publishes its interior; separators are already everywhere
-  KB_NCCL(h, g_nccl.GroupStart());
-  for (int q = 0; q < G; ++q) {
-    int64_t qlo = h->seg_lo[q], qhi = q < G - 1 ? h->seg_hi[q] - 1 : h->seg_hi[q];
-    int64_t off = h->nodeptr[qlo], cnt = h->nodeptr[qhi] - off;
-    KB_NCCL(h, g_nccl.Broadcast(y + off, y + off, (size_t)cnt * 2, ncclDouble, q, (ncclComm_t)h->nccl_comm, s));
-  }
-  KB_NCCL(h, g_nccl.GroupEnd());
   (void)g;
-  return KB_OK;
+  (void)G;
+  (void)slot;
+  return publish_interiors(h, y);
 }
 
 int kbi_chain_solve_sharded(kb_context* h, const double2* r, double2* x, int refine) {

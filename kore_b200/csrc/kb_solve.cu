@@ -267,6 +267,9 @@ int kbi_enter_safe_mode(kb_context* h, const char* what, int wait_code) {
           what, wait_code & 255, wait_code >> 8);
   if (h->safe_mode)
     return kb_fail(h, KB_ECUDA, "persistent-kernel time-out reported in safe mode (code %d)", wait_code);
+  if (h->nranks > 1)
+    return kb_fail(h, KB_ECUDA, "persistent-kernel time-out on rank %d of an l-sharded pencil (code %d, CTA %d); "
+                   "set KB_SHARD_GENERAL=1 to use the per-node kernels", h->rank, wait_code & 255, wait_code >> 8);
   h->safe_mode = true;
   h->opt_factor = 0;
   h->opt_sweep = 0;

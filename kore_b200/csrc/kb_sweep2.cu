@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int s
 // the transposed factors.  One CTA = 32 output rows (lane = row, so that for a fixed column of
 // F and coupling slot the warp reads consecutive entries of one row of M_p^T) x all columns in
 // tiles of 32, transposed through shared memory for the stores.
-__global__ void __launch_bounds__(256) kb_fold_couplings(int P, const int64_t* __restrict__ nodeptr,
+__global__ void __launch_bounds__(256) kb_fold_couplings(int plo, int P, const int64_t* __restrict__ nodeptr,
                                                          const int64_t* __restrict__ Moff,
                                                          const double2* __restrict__ MT, const double2* __restrict__ Lval,
                                                          const int* __restrict__ Lcol, int WL,
@@ -461,9 +461,10 @@ __global__ void __launch_bounds__(256) kb_fold_couplings(int P, const int64_t* _
                                                          int WU, const int64_t* __restrict__ FLoff,
                                                          const int64_t* __restrict__ FUoff, double2* __restrict__ F) {
   extern __shared__ __align__(16) unsigned char fold_smem[];
-  const int p = blockIdx.y, kind = blockIdx.z;  // kind 0: FL_p, 1: FU_p
-  const int pr = kind == 0 ? p + 1 : p - 1;     // node of the output rows
+  const int p = plo + blockIdx.y, kind = blockIdx.z;  // kind 0: FL_p, 1: FU_p
+  const int pr = kind == 0 ? p + 1 : p - 1;           // node of the output rows
   if (pr < 0 || pr >= P) return;
+  if ((kind == 0 ? FLoff[p] : FUoff[p]) < 0) return;  // not wanted (l-sharded: no separator on that side)
   const int o = (int)nodeptr[p], b = (int)(nodeptr[p + 1] - nodeptr[p]);
   const int orow = (int)nodeptr[pr], brow = (int)(nodeptr[pr + 1] - nodeptr[pr]);
   const int i0 = blockIdx.x * 32;
@@ -519,14 +520,14 @@ __global__ void __launch_bounds__(256) kb_fold_couplings(int P, const int64_t* _
 // x_p = M_p u_p for every node, from the transposed factors: x_i = sum_j M^T[j][i] u_j.  One CTA
 // = 32 consecutive rows i of one node (lane = row: a warp reads 512 contiguous bytes of a row
 // of M_p^T per j), the 8 warps split j, partial sums meet in shared memory.
-__global__ void __launch_bounds__(256) kb_fold_solution(const int64_t* __restrict__ nodeptr,
+__global__ void __launch_bounds__(256) kb_fold_solution(int plo, const int64_t* __restrict__ nodeptr,
                                                         const int64_t* __restrict__ Moff,
                                                         const double2* __restrict__ MT, const double2* __restrict__ u,
                                                         double2* __restrict__ x) {
   extern __shared__ __align__(16) unsigned char xs_smem[];
   double2* us = (double2*)xs_smem;  // b
   __shared__ double2 part[8][32];
-  const int p = blockIdx.y;
+  const int p = plo + blockIdx.y;
   const int o = (int)nodeptr[p], b = (int)(nodeptr[p + 1] - nodeptr[p]);
   const int i0 = blockIdx.x * 32;
   if (i0 >= b) return;
@@ -594,22 +595,23 @@ bool kbi_fold_supported(const kb_context* h, int G, bool two_sided, int* slice_e
 // the solve then runs through kb_sweep1.cu.
 int kbi_fold_prepare(kb_context* h) {
   h->fold_ready = false;
-  if (h->opt_sweep != 1 || h->nranks != 1) return KB_OK;
-  const int64_t P = h->P, mid = h->mid;
-  const bool two = mid < P - 1;
+  if (h->opt_sweep != 1) return KB_OK;
+  // the chain factored on this GPU: nodes [lo, hi) ([0, P) unless the pencil is l-sharded)
+  const int64_t P = h->P, mid = h->mid, lo = h->ch_lo, hi = h->ch_hi;
+  const bool two = mid < hi - 1;
   const int G = kbi_fold_grid(h, two);
   if (!kbi_fold_supported(h, G, two, nullptr, nullptr)) return KB_OK;
   cudaStream_t s = h->stream;
-  // ---- folded buffer layout
+  // ---- folded buffer layout (couplings to nodes outside the chain are not folded: -1)
   std::vector<int64_t> FLoff(P, -1), FUoff(P, -1);
   int64_t tot = 0;
   auto bsz = [&](int64_t p) { return h->nodeptr[p + 1] - h->nodeptr[p]; };
-  for (int64_t p = 0; p < P; ++p) {
-    if (p + 1 < P) {
+  for (int64_t p = lo; p < hi; ++p) {
+    if (p + 1 < hi) {
       FLoff[p] = tot;
       tot += bsz(p + 1) * bsz(p);
     }
-    if (p > 0) {
+    if (p > lo) {
       FUoff[p] = tot;
       tot += bsz(p - 1) * bsz(p);
     }
@@ -621,6 +623,8 @@ int kbi_fold_prepare(kb_context* h) {
   KB_CUDA(h, h->d_foldoff.alloc(2 * P));
   KB_CUDA(h, cudaMemcpyAsync(h->d_foldoff.p, FLoff.data(), P * sizeof(int64_t), cudaMemcpyHostToDevice, s));
   KB_CUDA(h, cudaMemcpyAsync(h->d_foldoff.p + P, FUoff.data(), P * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  h->FLoff = FLoff;
+  h->FUoff = FUoff;
   const int WL = h->WL > 0 ? h->WL : 1, WU = h->WU > 0 ? h->WU : 1;
   const int Wm = WL > WU ? WL : WU;
   const size_t fsm = (size_t)Wm * 32 * (sizeof(double2) + sizeof(int)) + 32 * 33 * sizeof(double2);
@@ -628,10 +632,10 @@ int kbi_fold_prepare(kb_context* h) {
   if (fsm > 48 * 1024)
     KB_CUDA(h, cudaFuncSetAttribute((const void*)kb_fold_couplings, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)fsm));
-  dim3 grid((unsigned)((h->bmax + 31) / 32), (unsigned)P, 2);
-  kb_fold_couplings<<<grid, 256, fsm, s>>>((int)P, h->d_nodeptr.p, h->d_Moff.p, h->d_M.p, h->d_Lval.p, h->d_Lcol.p, WL,
-                                           h->d_Uval.p, h->d_Ucol.p, WU, h->d_foldoff.p, h->d_foldoff.p + P,
-                                           h->d_fold.p);
+  dim3 grid((unsigned)((h->bmax + 31) / 32), (unsigned)(hi - lo), 2);
+  kb_fold_couplings<<<grid, 256, fsm, s>>>((int)lo, (int)P, h->d_nodeptr.p, h->d_Moff.p, h->d_M.p, h->d_Lval.p,
+                                           h->d_Lcol.p, WL, h->d_Uval.p, h->d_Ucol.p, WU, h->d_foldoff.p,
+                                           h->d_foldoff.p + P, h->d_fold.p);
   h->launches++;
   KB_LAUNCH_CHECK(h);
 
@@ -654,36 +658,36 @@ int kbi_fold_prepare(kb_context* h) {
     return o;
   };
   {
-    // group 0: nodes 0 .. mid downwards, then back up
+    // group 0: nodes lo .. mid downwards, then back up
     int pub = 0;
-    for (int64_t p = 0; p < mid; ++p) {
+    for (int64_t p = lo; p < mid; ++p) {
       const bool last = two && p == mid - 1;
-      ops[0].push_back(mk(FLoff[p], (int)p, (int)p + 1, p == 0 ? 0 : 1, pub - 1, 1, 1, pub, last ? 1 : 0, -1));
+      ops[0].push_back(mk(FLoff[p], (int)p, (int)p + 1, p == lo ? 0 : 1, pub - 1, 1, 1, pub, last ? 1 : 0, -1));
       ++pub;
     }
-    for (int64_t p = mid; p >= 1; --p) {
+    for (int64_t p = mid; p >= lo + 1; --p) {
       int kind = 1;
-      if (p == mid) kind = two ? 2 : (mid == 0 ? 0 : 1);
+      if (p == mid) kind = two ? 2 : (mid == lo ? 0 : 1);
       ops[0].push_back(
-          mk(FUoff[p], (int)p, (int)p - 1, kind, pub - 1, p - 1 == 0 ? 1 : 2, 2, pub, 0, p == mid ? (int)p : -1));
+          mk(FUoff[p], (int)p, (int)p - 1, kind, pub - 1, p - 1 == lo ? 1 : 2, 2, pub, 0, p == mid ? (int)p : -1));
       ++pub;
     }
-    if (mid == 0) ops[0].push_back(mk(-1, 0, -1, 0, -1, 0, 0, -1, 0, 0));  // single node: u_0 = r_0
+    if (mid == lo) ops[0].push_back(mk(-1, (int)lo, -1, 0, -1, 0, 0, -1, 0, (int)lo));  // single node: u = r
     h->fold_npub[0] = pub;
   }
   if (two) {
-    // group 1: nodes P-1 .. mid+1 upwards, the middle node's input, then back down
+    // group 1: nodes hi-1 .. mid+1 upwards, the middle node's input, then back down
     int pub = 0;
-    for (int64_t p = P - 1; p > mid; --p) {
+    for (int64_t p = hi - 1; p > mid; --p) {
       const bool tomid = p - 1 == mid;
-      ops[1].push_back(mk(FUoff[p], (int)p, (int)p - 1, p == P - 1 ? 0 : 1, pub - 1, tomid ? 0 : 1, tomid ? 0 : 1, pub,
+      ops[1].push_back(mk(FUoff[p], (int)p, (int)p - 1, p == hi - 1 ? 0 : 1, pub - 1, tomid ? 0 : 1, tomid ? 0 : 1, pub,
                           tomid ? 1 : 0, -1));
       ++pub;
     }
-    ops[1].push_back(mk(FLoff[mid], (int)mid, (int)mid + 1, 2, -1, mid + 1 == P - 1 ? 1 : 2, 2, pub, 0, -1));
+    ops[1].push_back(mk(FLoff[mid], (int)mid, (int)mid + 1, 2, -1, mid + 1 == hi - 1 ? 1 : 2, 2, pub, 0, -1));
     ++pub;
-    for (int64_t p = mid + 1; p < P - 1; ++p) {
-      ops[1].push_back(mk(FLoff[p], (int)p, (int)p + 1, 1, pub - 1, p + 1 == P - 1 ? 1 : 2, 2, pub, 0, -1));
+    for (int64_t p = mid + 1; p < hi - 1; ++p) {
+      ops[1].push_back(mk(FLoff[p], (int)p, (int)p + 1, 1, pub - 1, p + 1 == hi - 1 ? 1 : 2, 2, pub, 0, -1));
       ++pub;
     }
     h->fold_npub[1] = pub;
@@ -703,11 +707,14 @@ int kbi_fold_prepare(kb_context* h) {
   return KB_OK;
 }
 
-// y <- T'^{-1} r with the folded factors.  y has n+1 entries, y[n] == 0.
-int kbi_sweep_fold(kb_context* h, const double2* r, double2* y) {
+// y <- T'^{-1} r with the folded factors, on the chain [ch_lo, ch_hi) of this GPU (entries of r
+// and y outside it are not touched).  y has n+1 entries, y[n] == 0.  ends_only: form the solution
+// on the first and the last node of the chain only (first pass of the l-sharded solve: the
+// separator equations need nothing else).
+int kbi_sweep_fold(kb_context* h, const double2* r, double2* y, int ends_only) {
   cudaStream_t s = h->stream;
   const int n = (int)h->n;
-  const bool two = h->mid < h->P - 1;
+  const bool two = h->mid < h->ch_hi - 1;
   const int G = kbi_fold_grid(h, two);
   int slice_elems = 0;
   size_t smem = 0;
@@ -764,9 +771,19 @@ int kbi_sweep_fold(kb_context* h, const double2* r, double2* y) {
   if (smem > 48 * 1024) KB_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* args[] = {(void*)&q, (void*)&slice_elems};
   KB_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(G), dim3(K2_THREADS), args, smem, s));
-  dim3 xgrid((unsigned)((h->bmax + 31) / 32), (unsigned)h->P);
-  kb_fold_solution<<<xgrid, 256, (size_t)h->bmax * sizeof(double2), s>>>(h->d_nodeptr.p, h->d_Moff.p, h->d_M.p,
-                                                                        h->d_uvec.p, y);
+  const size_t xsm = (size_t)h->bmax * sizeof(double2);
+  if (!ends_only) {
+    dim3 xgrid((unsigned)((h->bmax + 31) / 32), (unsigned)(h->ch_hi - h->ch_lo));
+    kb_fold_solution<<<xgrid, 256, xsm, s>>>((int)h->ch_lo, h->d_nodeptr.p, h->d_Moff.p, h->d_M.p, h->d_uvec.p, y);
+  } else {
+    dim3 xgrid((unsigned)((h->bmax + 31) / 32), 1);
+    kb_fold_solution<<<xgrid, 256, xsm, s>>>((int)h->ch_lo, h->d_nodeptr.p, h->d_Moff.p, h->d_M.p, h->d_uvec.p, y);
+    if (h->ch_hi - 1 > h->ch_lo) {
+      kb_fold_solution<<<xgrid, 256, xsm, s>>>((int)h->ch_hi - 1, h->d_nodeptr.p, h->d_Moff.p, h->d_M.p, h->d_uvec.p,
+                                               y);
+      h->launches++;
+    }
+  }
   h->launches += 2;
   KB_LAUNCH_CHECK(h);
   return KB_OK;

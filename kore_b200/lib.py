@@ -48,7 +48,7 @@ class KbStats(C.Structure):
         ("eigs_solve_ms", C.c_double), ("op_applies", C.c_int64), ("solve_calls", C.c_int64),
         ("kernel_launches", C.c_int64), ("factor_bytes", C.c_int64), ("factor_flops", C.c_double),
         ("solve_bytes", C.c_double), ("refine_resid", C.c_double),
-        ("protocol_fallbacks", C.c_int64), ("wait_error", C.c_int64),
+        ("protocol_fallbacks", C.c_int64), ("wait_error", C.c_int64), ("shard_path", C.c_int64),
     ]
 
     def asdict(self):

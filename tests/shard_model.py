@@ -89,6 +89,88 @@ class Segment:
         return x
 
 
+class FastSegment:
+    """What ONE rank computes on the fast path (factor_sharded_fast / sharded_sweeps_fast of
+    kb_shard.cu): the interior is a block-tridiagonal system of its own, factored two-sided and
+    solved by the folded sweep (tests/fold_model.py); the corner blocks of its inverse come from the
+    folded sweep with identity-block right-hand sides, written as chains of dense products; a solve
+    is two passes of the folded sweep around the reduced solve.  Same contributions as Segment."""
+
+    def __init__(self, Tp, nodeptr, ranges, g):
+        import fold_model as fm
+        G = len(ranges)
+        lo, hi = ranges[g]
+        self.g, self.G, self.nodeptr = g, G, nodeptr
+        self.top = lo - 1 if g > 0 else None
+        self.bot = hi - 1 if g < G - 1 else None
+        self.interior = list(range(lo, hi - 1 if g < G - 1 else hi))
+        blk = lambda p, q: Tp[nodeptr[p]:nodeptr[p + 1], nodeptr[q]:nodeptr[q + 1]].toarray()
+        self.blk = blk
+        I = self.interior
+        n = len(I)
+        D = [blk(p, p) for p in I]
+        L = [blk(p, p - 1) if k > 0 else None for k, p in enumerate(I)]
+        U = [blk(p, p + 1) if k < n - 1 else None for k, p in enumerate(I)]
+        self.mid = n // 2 if n >= 4 else n - 1          # kb_shard.cu: two-sided from four nodes on
+        m = self.mid
+        self.Ms = fm.two_sided_factor(D, L, U, m)
+        self.FL, self.FU = fm.fold(self.Ms, L, U)
+        self.M = {p: self.Ms[k] for k, p in enumerate(I)}
+        FL, FU, Ms = self.FL, self.FU, self.Ms
+        bf, bl = D[0].shape[0], D[-1].shape[0]
+        # forward chains of the two identity column blocks
+        Tf = {0: np.eye(bf, dtype=complex)}
+        for k in range(m):
+            Tf[k + 1] = -FL[k] @ Tf[k]
+        Tl = {n - 1: np.eye(bl, dtype=complex)}
+        for k in range(n - 1, m, -1):
+            Tl[k - 1] = -FU[k] @ Tl[k]
+        # backward: U_m = T_m; up with base Tf (column f) / zero (column l), down the other way round
+        Uf, Ul = {m: Tf[m]}, {m: Tl[m]}
+        for k in range(m, 0, -1):
+            Uf[k - 1] = Tf[k - 1] - FU[k] @ Uf[k]
+            Ul[k - 1] = -FU[k] @ Ul[k]
+        for k in range(m, n - 1):
+            Ul[k + 1] = Tl[k + 1] - FL[k] @ Ul[k]
+            Uf[k + 1] = -FL[k] @ Uf[k]
+        Gff, Glf = Ms[0] @ Uf[0], Ms[n - 1] @ Uf[n - 1]
+        Gfl, Gll = Ms[0] @ Ul[0], Ms[n - 1] @ Ul[n - 1]
+        self.corners = (Gff, Glf, Gfl, Gll)
+        f, l = I[0], I[-1]
+        self.R_above = self.acc = self.C_sub = self.C_sup = None
+        if self.bot is not None:
+            self.R_above = blk(self.bot, self.bot) - blk(self.bot, l) @ Gll @ blk(l, self.bot)
+        if self.top is not None:
+            self.acc = blk(self.top, f) @ Gff @ blk(f, self.top)
+        if self.top is not None and self.bot is not None:
+            self.C_sub = -blk(self.bot, l) @ Glf @ blk(f, self.top)
+            self.C_sup = -blk(self.top, f) @ Gfl @ blk(l, self.bot)
+
+    def _sweep(self, rhs):
+        import fold_model as fm
+        return fm.folded_sweep(self.Ms, self.FL, self.FU, rhs, self.mid)
+
+    def forward(self, r):
+        """Pass 1: the interior solve; what the separators need are its end values."""
+        npt, I = self.nodeptr, self.interior
+        self.r = [r[npt[p]:npt[p + 1]].copy() for p in I]
+        y = self._sweep(self.r)
+        a_top = self.blk(self.top, I[0]) @ y[0] if self.top is not None else None
+        b_bot = self.blk(self.bot, I[-1]) @ y[-1] if self.bot is not None else None
+        return a_top, b_bot
+
+    def backward(self, xsep):
+        """Pass 2: the interior solve with the separator values moved to the right-hand side."""
+        I = self.interior
+        rhs = [v.copy() for v in self.r]
+        if self.top is not None:
+            rhs[0] = rhs[0] - self.blk(I[0], self.top) @ xsep[self.top]
+        if self.bot is not None:
+            rhs[-1] = rhs[-1] - self.blk(I[-1], self.bot) @ xsep[self.bot]
+        x = self._sweep(rhs)
+        return {p: x[k] for k, p in enumerate(I)}
+
+
 def reduced_solve(segs, r, nodeptr):
     """Assemble and solve the separator system from every rank's contributions (what each
     rank does redundantly after the all-gather)."""
@@ -116,10 +198,11 @@ def reduced_solve(segs, r, nodeptr):
     return {seps[j]: xs[j] for j in range(G - 1)}
 
 
-def sharded_solve(Tp, nodeptr, G, r):
+def sharded_solve(Tp, nodeptr, G, r, fast=False):
     P = len(nodeptr) - 1
     ranges = chain.split_ranges(P, G)
-    segs = [Segment(Tp, nodeptr, ranges, g) for g in range(G)]
+    cls = FastSegment if fast else Segment
+    segs = [cls(Tp, nodeptr, ranges, g) for g in range(G)]
     if G > 1:
         xsep = reduced_solve(segs, r, nodeptr)
     else:

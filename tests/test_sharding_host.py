@@ -19,7 +19,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, name, q):
+def _worker(rank, world, port, name, q, fast=False):
     import torch.distributed as dist
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -35,7 +35,7 @@ def _worker(rank, world, port, name, q):
     r = c.oracle["solve_rhs"][c.perm]
     P = len(c.nodeptr) - 1
     ranges = chain.split_ranges(P, world)
-    seg = sm.Segment(Tp, c.nodeptr, ranges, rank)          # this rank's elimination only
+    seg = (sm.FastSegment if fast else sm.Segment)(Tp, c.nodeptr, ranges, rank)   # this rank's elimination only
     a_top, b_bot = seg.forward(r)
     mine = dict(R_above=seg.R_above, acc=seg.acc, C_sub=seg.C_sub, C_sup=seg.C_sup, a_top=a_top, b_bot=b_bot,
                 bot=seg.bot)
@@ -71,13 +71,14 @@ def _worker(rank, world, port, name, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name", ["m0_small", "magnetic_small"])
-def test_two_rank_sharded_solve_over_gloo(name):
+@pytest.mark.parametrize("name,fast", [("m0_small", False), ("magnetic_small", False), ("magnetic_small", True),
+                                       ("dormy", True)])
+def test_two_rank_sharded_solve_over_gloo(name, fast):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, q, fast)) for r in range(2)]
     for p in procs:
         p.start()
     out = [q.get(timeout=240) for _ in procs]
@@ -102,3 +103,27 @@ def test_single_process_model_matches_oracle_for_many_ranks():
     for G in (1, 2, 4, 8):
         x = sm.sharded_solve(Tp, c.nodeptr, G, r)
         assert np.linalg.norm(x - xo) <= 1e-9 * np.linalg.norm(xo)
+
+
+@pytest.mark.parametrize("name", ["m0_small", "dormy"])
+def test_fast_path_model_matches_oracle_and_general_contributions(name):
+    """The fast path's algebra (interior as a chain of its own, corner blocks of its inverse from
+    identity-column chains, two sweep passes) gives the same reduced-system blocks as the spike
+    recurrences of the general path and the oracle's solution, for every rank count; short
+    interiors (one to three nodes: one-sided, no product chains) included."""
+    import shard_model as sm
+    from kore_b200 import chain
+    c = load_case(name)
+    T = (c.A - c.tau * c.B).tocsr()
+    Tp = T[c.perm][:, c.perm].tocsr()
+    r = c.oracle["solve_rhs"][c.perm]
+    xo = c.oracle["solve_x"][c.perm]
+    P = len(c.nodeptr) - 1
+    for G in (2, 3, 8, P // 2):
+        x = sm.sharded_solve(Tp, c.nodeptr, G, r, fast=True)
+        assert np.linalg.norm(x - xo) <= 1e-9 * np.linalg.norm(xo), G
+    ranges = chain.split_ranges(P, 3)
+    a, b = sm.Segment(Tp, c.nodeptr, ranges, 1), sm.FastSegment(Tp, c.nodeptr, ranges, 1)
+    for name_ in ("R_above", "acc", "C_sub", "C_sup"):
+        u, v = getattr(a, name_), getattr(b, name_)
+        assert np.linalg.norm(u - v) <= 1e-9 * max(np.linalg.norm(u), 1e-300), name_

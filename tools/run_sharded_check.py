@@ -48,9 +48,13 @@ def main():
         d = max(np.min(np.abs(lam - lo)) / abs(lo) for lo in case.oracle["eig"])
         good = rel < 1e-9 and res < 1e-12 and d < 1e-9 and info["nconv"] >= m["nev"] and info["resid"].max() < 1e-9
         ok &= bool(good)
-        print("rank %d/%d %-16s solve rel %.2e resid %.2e | eig max rel diff %.2e nconv %d maxres %.1e | factor %.1f ms eigs %.1f ms %s"
-              % (rank, world, name, rel, res, d, info["nconv"], info["resid"].max(), info["factor_ms"], info["eigs_ms"],
-                 "OK" if good else "FAIL"), flush=True)
+        path = {0: "one-gpu", 1: "general", 2: "fast"}[int(s.stats()["shard_path"])]
+        if os.environ.get("KB_EXPECT_SHARD_PATH"):
+            good = good and path == os.environ["KB_EXPECT_SHARD_PATH"]
+        ok &= bool(good)
+        print("rank %d/%d %-16s [%s] solve rel %.2e resid %.2e | eig max rel diff %.2e nconv %d maxres %.1e | factor %.1f ms eigs %.1f ms %s"
+              % (rank, world, name, path, rel, res, d, info["nconv"], info["resid"].max(), info["factor_ms"],
+                 info["eigs_ms"], "OK" if good else "FAIL"), flush=True)
         s.close()
     flag = torch.tensor([1 if ok else 0])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
