@@ -310,17 +310,20 @@ def run_ours(args):
     # with sigma = 1j + 0.003 rank, profiles/r1d_bench_2gpu_shifts.json)
     sigma = 1j
 
-    s = lib.Solver(local)
-    s.set_pencil(A, B)
-    s.set_chain(perm, nodeptr)
-    if distributed and args.mode == "lshard":
+    def shard(solver):
+        """One NCCL communicator of the library per handle (id from rank 0 over torch.distributed)."""
         uid = np.zeros(128, dtype=np.uint8)
         if rank == 0:
             lib.load().kb_nccl_unique_id(uid.ctypes.data)
         t = torch.from_numpy(uid).cuda()
         dist.broadcast(t, 0)
-        uid = t.cpu().numpy()
-        s.set_sharding(rank, world, uid)
+        solver.set_sharding(rank, world, t.cpu().numpy())
+
+    s = lib.Solver(local)
+    s.set_pencil(A, B)
+    s.set_chain(perm, nodeptr)
+    if distributed and args.mode == "lshard":
+        shard(s)
 
     def step(want_vectors=False):
         s.factor(sigma)
@@ -396,6 +399,10 @@ def run_ours(args):
             phases[k] += dt
         return out
 
+    if distributed and args.mode == "lshard":
+        s2.set_pencil(A, B)
+        s2.set_chain(perm, nodeptr)
+        shard(s2)  # the communicator survives the re-ingest of every step
     e2e_step()
     for k in phases:
         phases[k] = 0.0
@@ -469,6 +476,34 @@ def run_ours(args):
                 "phases_s_per_step": {k: v / e2e_steps for k, v in phases.items()}},
         "roofline": roofline,
     }
+    if distributed and args.mode == "shifts" and not args.no_lshard:
+        # second line of evidence at N > 1: the SAME pencil l-sharded over the N GPUs (strong
+        # scaling: one factor + eigensolve, every rank owns P / N chain nodes), a few steps
+        shard(s)
+        nl = max(1, min(args.steps, 5))
+        for _ in range(2):
+            step()
+        barrier()
+        tl, fl, sw, nsw = 0.0, 0.0, 0.0, 0
+        for _ in range(nl):
+            lam_l, info_l = step()
+            tl += info_l["factor_ms"] + info_l["eigs_ms"]
+            fl += info_l["factor_ms"]
+            sw += info_l["eigs_solve_ms"]
+            nsw += info_l["solve_calls"]
+        barrier()
+        tt = torch.tensor([tl], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        tl = float(tt[0]) / 1e3
+        line["lshard"] = {
+            "what": "the same pencil l-sharded over the %d GPUs (--mode lshard): one factor + eigensolve per step, "
+                    "strong scaling against the one-GPU unit of work" % world,
+            "value": nl * min(info_l["nconv"], args.nev) / tl, "unit": UNIT, "steps": nl,
+            "ms_per_step": tl / nl * 1e3, "factor_ms": fl / nl, "ms_per_sweep": sw / max(1, nsw),
+            "shard_path": {0: "one-gpu", 1: "general", 2: "fast"}[int(s.stats()["shard_path"])],
+            "speedup_vs_one_gpu_unit": (t_dev / args.steps) / (tl / nl),
+            "max_residual": float(np.max(info_l["resid"])) if info_l["nconv"] else None,
+        }
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_for_gpu_arm(args, applies / args.steps)
     if rank == 0:
@@ -498,6 +533,8 @@ def main():
                     help="> 0: also time round 1's SciPy-SuperLU sample on this many chain nodes")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-lshard", action="store_true",
+                    help="N > 1, --mode shifts: skip the attached l-sharded measurement")
     args = ap.parse_args()
     # Rank 0's stdout must be the ONE JSON line.  Libraries write to file descriptor 1 behind
     # Python's back (NCCL prints "NCCL version ..." there at any NCCL_DEBUG level >= VERSION), so

@@ -78,6 +78,9 @@ struct KfParams {
   // ring slot k mod KF_RING; its owner does not write before every consumer of strip k - KF_RING
   // has said it is done with the slot); null: consumers wait for the composite G_k
   double* Sbuf[2];
+  // non-null: the (single) node's Schur block is this dense row-major b x b matrix instead of being
+  // formed from the sparse pencil (separator blocks of the l-sharded reduced system)
+  const double2* dense;
 };
 
 __device__ __forceinline__ unsigned kf_ld_acquire(const unsigned* p) {
@@ -293,7 +296,14 @@ __global__ void __launch_bounds__(MAXT, 1) kb_chain_factor(KfParams q) {
       if (group == 0 && s > 0) kf_schur_term<NB>(q, a, 0, p, p - 1, j0, ws, Ws);
       if (group == 1 && s > 0) kf_schur_term<NB>(q, a, 1, p, p + 1, j0, ws, Ws);
       if (group == 0 && p == mid && mid < P - 1) kf_schur_term<NB>(q, a, 1, p, p + 1, j0, ws, Ws);
-      if (t < b) {
+      if (q.dense) {
+        if (t < b) {
+          const double2* dr = q.dense + (size_t)t * b + j0;
+#pragma unroll
+          for (int u = 0; u < NB; ++u)
+            if (u < ws) a[u] = dr[u];
+        }
+      } else if (t < b) {
         // D_p[t, strip]: the row's own-node entries are sorted by column; lower bound, then <= ws entries
         const int gi = o + t;
         int64_t lo = __ldg(&q.dstart[gi]), hi = __ldg(&q.ustart[gi]);
@@ -647,7 +657,8 @@ bool kbi_chainfac_supported(const kb_context* h) {
 // Factor the chain nodes [plo, phi) as a block-tridiagonal system of their own (T must have been
 // built; phi < 0: the whole chain).  two_sided: eliminate from both ends towards node h->mid;
 // otherwise top-down only (h->mid = phi - 1).
-int kbi_chainfac_run(kb_context* h, bool two_sided, bool transposed, int64_t plo, int64_t phi) {
+int kbi_chainfac_run(kb_context* h, bool two_sided, bool transposed, int64_t plo, int64_t phi,
+                     const KbDenseNode* dense) {
   cudaStream_t s = h->stream;
   const int64_t bmax = h->bmax;
   if (phi < 0) phi = h->P;
@@ -667,6 +678,18 @@ int kbi_chainfac_run(kb_context* h, bool two_sided, bool transposed, int64_t plo
   q.nodeptr = h->d_nodeptr.p;
   q.Moff = h->d_Moff.p;
   q.M = h->d_M.p;
+  q.dense = nullptr;
+  if (dense) {
+    // a one-node chain of its own: tables {0, b} / {0} on the device, inverse to dense->out
+    q.plo = 0;
+    q.P = 1;
+    q.mid = 0;
+    q.nodeptr = dense->nodeptr;
+    q.Moff = dense->moff;
+    q.M = dense->out;
+    q.dense = dense->S;
+    two_sided = false;
+  }
   q.rowptr = h->d_rowptr.p;
   q.dstart = h->d_dstart.p;
   q.ustart = h->d_ustart.p;
@@ -683,9 +706,15 @@ int kbi_chainfac_run(kb_context* h, bool two_sided, bool transposed, int64_t plo
   const int64_t maxsteps = (bmax + KF_WMIN - 1) / KF_WMIN + 1;
   KB_CUDA(h, h->d_kfpiv.alloc((size_t)ngroups * maxsteps * 16));
   KB_CUDA(h, h->d_kfsync.alloc(KF_SYNC_WORDS));
-  KB_CUDA(h, cudaMemsetAsync(h->d_kfsync.p, 0, KF_SYNC_WORDS * sizeof(unsigned), s));
+  if (!dense) {
+    KB_CUDA(h, cudaMemsetAsync(h->d_kfsync.p, 0, KF_SYNC_WORDS * sizeof(unsigned), s));
+  } else {
+    // keep the time-out flag of the factorisation this launch belongs to
+    KB_CUDA(h, cudaMemsetAsync(h->d_kfsync.p, 0, KF_ERR_WORD * sizeof(unsigned), s));
+    KB_CUDA(h, cudaMemsetAsync(h->d_kfsync.p + KF_ERR_WORD + 1, 0, (KF_SYNC_WORDS - KF_ERR_WORD - 1) * sizeof(unsigned), s));
+  }
   KB_CUDA(h, h->d_info.alloc(1));
-  KB_CUDA(h, cudaMemsetAsync(h->d_info.p, 0, sizeof(int), s));
+  if (!dense) KB_CUDA(h, cudaMemsetAsync(h->d_info.p, 0, sizeof(int), s));  // dense nodes add to the flags
   q.Gbuf[0] = h->d_kfG.p;
   q.Gbuf[1] = two_sided ? h->d_kfG.p + (size_t)bmax * bmax : h->d_kfG.p;
   q.pivbuf[0] = h->d_kfpiv.p;
@@ -693,6 +722,7 @@ int kbi_chainfac_run(kb_context* h, bool two_sided, bool transposed, int64_t plo
   q.sync = h->d_kfsync.p;
   q.info = h->d_info.p;
   q.err = (int*)(h->d_kfsync.p + KF_ERR_WORD);  // time-out flag
+  if (dense) q.err = h->d_sweep_err.p;         // (the sync block is cleared per launch; this one is not)
   q.wait_ns = h->wait_ns;
   q.dbg = nullptr;
   if (getenv("KB_SWEEP_TIMING")) {

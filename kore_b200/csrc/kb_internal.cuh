@@ -399,6 +399,7 @@ struct kb_context {
   DevBuf<double2> d_Mr, d_Csub, d_Csup;       // reduced system: inverses and couplings (G-1 nodes)
   DevBuf<double2> d_sepvec, d_sepvec_all;     // per-solve separator contributions
   DevBuf<double2> d_redz;                     // reduced-solve scratch
+  DevBuf<int64_t> d_redtab;                   // {0, b_j} per separator + a zero: one-node chains for the strip kernel
   DevBuf<unsigned> d_redctr;                  // grid-barrier counter of the fused reduced solve
   unsigned red_epoch = 0;
   int red_grid = 0;
@@ -446,7 +447,15 @@ int kbi_upload_raw(kb_context* h, KbRawCSR& M, int64_t n, int index_bytes, const
 int kbi_layout_device(kb_context* h);
 // ---- kb_chainfac.cu
 bool kbi_chainfac_supported(const kb_context* h);
-int kbi_chainfac_run(kb_context* h, bool two_sided, bool transposed, int64_t plo = 0, int64_t phi = -1);
+// a dense b x b block inverted by the strip kernel as a one-node chain (row-major in, row-major out)
+struct KbDenseNode {
+  const double2* S;
+  double2* out;
+  const int64_t* nodeptr;  // device: {0, b}
+  const int64_t* moff;     // device: {0}
+};
+int kbi_chainfac_run(kb_context* h, bool two_sided, bool transposed, int64_t plo = 0, int64_t phi = -1,
+                     const KbDenseNode* dense = nullptr);
 // ---- kb_solve.cu
 //  chain solve in scaled/permuted space: d_y <- T'^{-1} d_r (d_r preserved)
 int kbi_chain_solve(kb_context* h, const double2* r_dev, double2* x_dev, int refine);

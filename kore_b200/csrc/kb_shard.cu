@@ -87,6 +87,8 @@ extern "C" int kb_nccl_unique_id(void* id128) {
   return KB_OK;
 }
 
+static int shard_ranges(kb_context* h);
+
 extern "C" int kb_set_sharding(kb_handle h, int rank, int nranks, const void* id128) {
   if (!h) return KB_EINVAL;
   if (nranks < 1 || rank < 0 || rank >= nranks) return kb_fail(h, KB_EINVAL, "bad rank/nranks");
@@ -111,7 +113,16 @@ extern "C" int kb_set_sharding(kb_handle h, int rank, int nranks, const void* id
   h->nccl_comm = (void*)comm;
   h->rank = rank;
   h->nranks = nranks;
-  // contiguous, near-equal node ranges (same rule as kore_b200/chain.py split_ranges)
+  return shard_ranges(h);
+}
+
+// contiguous, near-equal node ranges (same rule as kore_b200/chain.py split_ranges); derived again at
+// every factorisation, so the chain may change under an established communicator
+static int shard_ranges(kb_context* h) {
+  const int nranks = h->nranks, rank = h->rank;
+  if (h->P < 2 * nranks)
+    return kb_fail(h, KB_EINVAL, "chain of %lld nodes is too short for %d ranks (need >= 2 per rank)",
+                   (long long)h->P, nranks);
   h->seg_lo.assign(nranks, 0);
   h->seg_hi.assign(nranks, 0);
   int64_t base = h->P / nranks, rem = h->P % nranks, lo = 0;
@@ -222,9 +233,10 @@ __global__ void kb_first_panel(const double2* __restrict__ S, int n, int nb0, do
 
 // ---------------------------------------------------------------------------
 // Batched dense products of the fast l-sharded factorisation (below): up to four independent
-// C = beta C + alpha op(A) B, one problem per blockIdx.z, row-major, 64 x 64 tiles, 16 deep,
-// 4 x 4 complex accumulators per thread, the next tile loaded into registers while the current
-// one is multiplied (one shared-memory stage: 33 KB).  op(A) = A^T reads A (k x m, row-major) by columns -- the explicit inverses
+// C = beta C + alpha op(A) B, one problem per blockIdx.z, row-major.  32 x 64 tiles (190 per
+// 600 x 600 product: two to four products fill 148 SMs x 4 resident CTAs evenly), 8 deep, 4 x 4
+// complex accumulators per thread, two shared-memory stages filled by 16-byte cp.async copies
+// (zero-filled outside the matrices) so that a k-tile costs one wait and two barriers.  op(A) = A^T reads A (k x m, row-major) by columns -- the explicit inverses
 // are stored transposed.  FP64 FMA issue is the bound: 64 DFMA per thread and k-step against 8
 // 16-byte shared-memory loads, two of which are warp broadcasts.
 // ---------------------------------------------------------------------------
@@ -242,91 +254,91 @@ struct KbGemmBatch {
   KbGemmProb p[4];
 };
 
-__global__ void __launch_bounds__(256) kb_zgemm_batch(KbGemmBatch batch) {
+#define ZG_BM 32
+#define ZG_BN 64
+#define ZG_BK 8
+#define ZG_THREADS 128
+
+// 16-byte asynchronous global -> shared copy; ok == false writes zeros (src-size 0)
+__device__ __forceinline__ void zg_cp16(void* dst, const void* src, bool ok) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(kb_smem_addr(dst)), "l"(src), "r"(ok ? 16 : 0)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(ZG_THREADS, 4) kb_zgemm_batch(KbGemmBatch batch) {
   const KbGemmProb& g = batch.p[blockIdx.z];
   const int m = g.m, n = g.n, k = g.k;
-  const int row0 = blockIdx.y * 64, col0 = blockIdx.x * 64;
+  const int row0 = blockIdx.y * ZG_BM, col0 = blockIdx.x * ZG_BN;
   if (row0 >= m || col0 >= n) return;
-  __shared__ double2 As[16][64 + 1];
-  __shared__ double2 Bs[16][64];
+  // two stages; A tile k-major with an odd pitch (the rows a thread reads are 8 apart)
+  __shared__ __align__(16) double2 As[2][ZG_BK][ZG_BM + 1];
+  __shared__ __align__(16) double2 Bs[2][ZG_BK][ZG_BN];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const double2* __restrict__ A = g.A;
   const double2* __restrict__ B = g.B;
-  const int lda = g.lda, ldb = g.ldb;
+  const int lda = g.lda, ldb = g.ldb, transA = g.transA;
+  auto issue = [&](int kk, int st) {
+#pragma unroll
+    for (int u = 0; u < (ZG_BM * ZG_BK) / ZG_THREADS; ++u) {
+      const int e = tid + ZG_THREADS * u;
+      int i, q;
+      if (transA) {  // A is k x m: consecutive threads along i
+        q = e / ZG_BM;
+        i = e % ZG_BM;
+      } else {       // A is m x k: consecutive threads along k
+        i = e / ZG_BK;
+        q = e % ZG_BK;
+      }
+      const int gi = row0 + i, gk = kk + q;
+      const bool ok = gi < m && gk < k;
+      const double2* src = ok ? (transA ? A + (size_t)gk * lda + gi : A + (size_t)gi * lda + gk) : A;
+      zg_cp16(&As[st][q][i], src, ok);
+    }
+#pragma unroll
+    for (int u = 0; u < (ZG_BK * ZG_BN) / ZG_THREADS; ++u) {
+      const int e = tid + ZG_THREADS * u;
+      const int q = e / ZG_BN, j = e % ZG_BN;
+      const int gk = kk + q, gj = col0 + j;
+      const bool ok = gk < k && gj < n;
+      zg_cp16(&Bs[st][q][j], ok ? B + (size_t)gk * ldb + gj : B, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
   double2 acc[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[a][c] = zmake(0.0, 0.0);
-  // element e of the A tile handled by this thread: four per tile
-  //   no transpose: (i = e / 16, q = e % 16) -> consecutive threads read consecutive k (row of A)
-  //   transpose   : (q = e / 64, i = e % 64) -> consecutive threads read consecutive i (row of A^T's source)
-  double2 ra[4], rb[4];
-  auto load_tiles = [&](int kk) {
+  issue(0, 0);
+  int st = 0;
+  for (int kk = 0; kk < k; kk += ZG_BK) {
+    const bool more = kk + ZG_BK < k;
+    if (more) issue(kk + ZG_BK, st ^ 1);  // the other stage was released by the barrier that ended the last trip
+    if (more)
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int e = tid + 256 * u;
-      int i, q;
-      if (g.transA) {
-        q = e >> 6;
-        i = e & 63;
-      } else {
-        i = e >> 4;
-        q = e & 15;
-      }
-      const int gi = row0 + i, gk = kk + q;
-      const bool ok = gi < m && gk < k;
-      ra[u] = ok ? (g.transA ? A[(size_t)gk * lda + gi] : A[(size_t)gi * lda + gk]) : zmake(0.0, 0.0);
-      const int qb = e >> 6, j = e & 63;
-      const int gkb = kk + qb, gj = col0 + j;
-      rb[u] = (gkb < k && gj < n) ? B[(size_t)gkb * ldb + gj] : zmake(0.0, 0.0);
-    }
-  };
-  auto store_tiles = [&]() {
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int e = tid + 256 * u;
-      int i, q;
-      if (g.transA) {
-        q = e >> 6;
-        i = e & 63;
-      } else {
-        i = e >> 4;
-        q = e & 15;
-      }
-      As[q][i] = ra[u];
-      Bs[e >> 6][e & 63] = rb[u];
-    }
-  };
-  load_tiles(0);
-  store_tiles();
-  __syncthreads();
-  for (int kk = 0; kk < k; kk += 16) {
-    const bool more = kk + 16 < k;
-    if (more) load_tiles(kk + 16);
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {
+    for (int q = 0; q < ZG_BK; ++q) {
       double2 av[4], bv[4];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) av[a] = As[q][ty + 16 * a];
+      for (int a = 0; a < 4; ++a) av[a] = As[st][q][ty + 8 * a];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) bv[c] = Bs[q][tx + 16 * c];
+      for (int c = 0; c < 4; ++c) bv[c] = Bs[st][q][tx + 16 * c];
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int c = 0; c < 4; ++c) zfma(acc[a][c], av[a], bv[c]);
     }
-    if (more) {
-      __syncthreads();
-      store_tiles();
-      __syncthreads();
-    }
+    __syncthreads();
+    st ^= 1;
   }
   double2* __restrict__ C = g.C;
   const int ldc = g.ldc;
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
-    const int gi = row0 + ty + 16 * a;
+    const int gi = row0 + ty + 8 * a;
     if (gi >= m) continue;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -363,8 +375,8 @@ struct GemmQueue {
   }
   void flush(kb_context* h) {
     if (!count) return;
-    dim3 grid((nmax + 63) / 64, (mmax + 63) / 64, count);
-    kb_zgemm_batch<<<grid, 256, 0, h->stream>>>(b);
+    dim3 grid((nmax + ZG_BN - 1) / ZG_BN, (mmax + ZG_BM - 1) / ZG_BM, count);
+    kb_zgemm_batch<<<grid, ZG_THREADS, 0, h->stream>>>(b);
     h->launches++;
     count = mmax = nmax = 0;
   }
@@ -469,6 +481,37 @@ static void zgemm(kb_context* h, int m, int n, int k, double alpha, const double
   q.flush(h);
 }
 
+// debug / microbenchmark (tools/dev_zgemm.py): C = alpha op(A) B + beta C on host arrays, `batch`
+// identical problems per launch, `reps` launches timed; returns the mean ms per launch
+extern "C" int kb_dbg_zgemm(kb_handle h, int m, int n, int k, int transA, const double* A, const double* B,
+                            double* C, double alpha, double beta, int batch, int reps, double* ms_out) {
+  if (!h || batch < 1 || batch > 4) return KB_EINVAL;
+  KB_CUDA(h, cudaSetDevice(h->device));
+  const size_t na = (size_t)m * k, nb = (size_t)k * n, nc = (size_t)m * n;
+  DevBuf<double2> dA, dB, dC;
+  KB_CUDA(h, dA.alloc(na));
+  KB_CUDA(h, dB.alloc(nb));
+  KB_CUDA(h, dC.alloc(nc * batch));
+  KB_CUDA(h, cudaMemcpy(dA.p, A, na * sizeof(double2), cudaMemcpyHostToDevice));
+  KB_CUDA(h, cudaMemcpy(dB.p, B, nb * sizeof(double2), cudaMemcpyHostToDevice));
+  for (int i = 0; i < batch; ++i) KB_CUDA(h, cudaMemcpy(dC.p + i * nc, C, nc * sizeof(double2), cudaMemcpyHostToDevice));
+  KbEventPair ev;
+  KB_CUDA(h, ev.create());
+  for (int r = -1; r < reps; ++r) {
+    if (r == 0) KB_CUDA(h, cudaEventRecord(ev.e0, h->stream));
+    GemmQueue q;
+    for (int i = 0; i < batch; ++i)
+      q.add(m, n, k, alpha, dA.p, transA ? m : k, transA != 0, dB.p, n, r <= 0 ? beta : 0.0, dC.p + i * nc, n);
+    q.flush(h);
+  }
+  KB_LAUNCH_CHECK(h);
+  KB_CUDA(h, cudaEventRecord(ev.e1, h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (ms_out) *ms_out = reps > 0 ? ev.ms() / reps : 0.0;
+  KB_CUDA(h, cudaMemcpy(C, dC.p + (batch - 1) * nc, nc * sizeof(double2), cudaMemcpyDeviceToHost));
+  return KB_OK;
+}
+
 __global__ void kb_set_identity(double2* __restrict__ A, int b) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e < (int64_t)b * b) A[e] = zmake((e / b) == (e % b) ? 1.0 : 0.0, 0.0);
@@ -560,6 +603,7 @@ int kbi_factor_sharded(kb_context* h, zcomplex sigma) {
   if (!h->chain_set) return kb_fail(h, KB_EINVAL, "kb_set_chain must be called before kb_factor");
   if (!h->nccl_comm) return kb_fail(h, KB_EINVAL, "kb_set_sharding must be called before kb_factor");
   KB_CUDA(h, cudaSetDevice(h->device));
+  KB_TRY(shard_ranges(h));
   cudaStream_t s = h->stream;
   const int64_t P = h->P, bmax = h->bmax;
   const int G = h->nranks, g = h->rank;
@@ -767,6 +811,15 @@ static int reduced_factor(kb_context* h, double* flops_io) {
   double flops = 0.0;
   KB_CUDA(h, h->d_F.alloc(slot));
   KB_CUDA(h, h->d_Mr.alloc(slot * (G - 1)));
+  // separator blocks are inverted by the strip kernel as one-node chains when it supports the size
+  const bool strip = kbi_chainfac_supported(h) && !h->safe_mode && !getenv("KB_SHARD_GENERAL");
+  if (strip) {
+    std::vector<int64_t> tab(2 * (G - 1) + 1, 0);
+    for (int j = 0; j < G - 1; ++j) tab[2 * j + 1] = nsize(h, h->seg_hi[j] - 1);
+    KB_CUDA(h, h->d_redtab.alloc(tab.size()));
+    KB_CUDA(h, cudaMemcpyAsync(h->d_redtab.p, tab.data(), tab.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    KB_CUDA(h, cudaStreamSynchronize(s));  // (pageable source on the stack of this call)
+  }
   for (int j = 0; j < G - 1; ++j) {
     const int bs = nsize(h, h->seg_hi[j] - 1);
     const double2* Rabove = h->d_contrib_all.p + (size_t)j * 4 * slot;
@@ -780,11 +833,20 @@ static int reduced_factor(kb_context* h, double* flops_io) {
       zgemm(h, bsp, bs, bsp, 1.0, h->d_Mr.p + (size_t)(j - 1) * slot, bsp, Csup, bs, 0.0, h->d_F.p, bs);
       zgemm(h, bs, bs, bsp, -1.0, Csub, bsp, h->d_F.p, bs, 1.0, h->d_S0.p, bs);
     }
-    kb_first_panel<<<nblk(bs, 128), 128, 0, s>>>(h->d_S0.p, bs, kbi_panel_width(h, bs), h->d_PT.p);
-    double2* X = nullptr;
-    KB_TRY(gj_invert(h, kbi_ws_main(h), bs, &X));
-    kb_store_inverse<<<bs, 128, 0, s>>>(X, bs, h->d_orig.p, h->d_Mr.p + (size_t)j * slot);
-    h->launches += 2;
+    if (strip) {
+      KbDenseNode dn;
+      dn.S = h->d_S0.p;
+      dn.out = h->d_Mr.p + (size_t)j * slot;
+      dn.nodeptr = h->d_redtab.p + 2 * j;
+      dn.moff = h->d_redtab.p + 2 * (G - 1);
+      KB_TRY(kbi_chainfac_run(h, false, false, 0, 1, &dn));
+    } else {
+      kb_first_panel<<<nblk(bs, 128), 128, 0, s>>>(h->d_S0.p, bs, kbi_panel_width(h, bs), h->d_PT.p);
+      double2* X = nullptr;
+      KB_TRY(gj_invert(h, kbi_ws_main(h), bs, &X));
+      kb_store_inverse<<<bs, 128, 0, s>>>(X, bs, h->d_orig.p, h->d_Mr.p + (size_t)j * slot);
+      h->launches += 2;
+    }
     flops += 8.0 * (double)bs * bs * bs;
     KB_LAUNCH_CHECK(h);
   }
@@ -1050,7 +1112,9 @@ static int reduced_solve(kb_context* h, double2* y) {
   }
   q.ctr = h->d_redctr.p;
   q.epoch0 = h->red_epoch;
-  h->red_epoch += (unsigned)(2 * (G - 1));  // >= the barriers of one launch; the counter wraps with it
+  // exactly the barriers of one launch (nsep forward + nsep - 2 backward for nsep >= 2): every barrier
+  // adds gridDim.x to the counter, so the epochs of consecutive launches must be consecutive
+  h->red_epoch += (unsigned)(G - 1 > 1 ? 2 * (G - 1) - 2 : 0);
   q.err = h->d_sweep_err.p;
   q.wait_ns = h->wait_ns;
   void* args[] = {(void*)&q};
