@@ -25,14 +25,15 @@ import numpy as np
 
 
 def ell(m: int, lmax: int, vsymm: int):
-    """Degree lists (top, bottom, all); restates utils.py:174-183."""
-    lm1 = lmax - m + 1
-    s = int(vsymm * 0.5 + 0.5)
-    sg = int(np.sign(m))
-    idp = np.arange((sg + s) % 2, lm1, 2, dtype=int)
-    idt = np.arange((sg + s + 1) % 2, lm1, 2, dtype=int)
-    ll = np.arange(m + 1 - sg, lmax + 2 - sg, dtype=int)
-    return ll[idp], ll[idt], ll
+    """The spherical-harmonic degrees of the problem, split by equatorial parity: (degrees of
+    the first family, degrees of the second family, all degrees).  Same sets as the reference's
+    index rule (utils.py:174-183): lmax - m + 1 consecutive degrees starting at m (at 1 for the
+    axisymmetric case, where l = 0 carries nothing); the first family takes every other degree,
+    beginning with the first one exactly when `m > 0` and `vsymm == 1` disagree."""
+    axisymmetric = m == 0
+    degrees = np.arange(lmax - m + 1, dtype=int) + (1 if axisymmetric else m)
+    first = ((0 if axisymmetric else 1) + (1 if vsymm > 0 else 0)) % 2
+    return degrees[first::2], degrees[1 - first::2], degrees
 
 
 def section_degrees(m, lmax, symm, symmB0, hydro, magnetic, thermal, compositional):

@@ -3,10 +3,13 @@ golden fixtures.  Tolerances are BASELINE.json's: eigenvalues to relative 1e-9,
 eigen-residuals ||Ax - lam Bx|| / (|lam| ||Bx||) <= 1e-10 wherever the oracle
 itself reaches that (the oracle's own residual is stored beside its eigenvalues
 and the bar is max(1e-10, 3 x oracle)), solutions to relative 1e-9."""
+import json
+import os
+
 import numpy as np
 import pytest
 
-from conftest import load_case
+from conftest import ROOT, load_case
 
 pytestmark = pytest.mark.gpu
 
@@ -363,6 +366,13 @@ def test_full_size_properties(lib):
             res = np.linalg.norm(A @ X[:, i] - lam[i] * bx) / (abs(lam[i]) * np.linalg.norm(bx))
             assert res <= 1e-10, (i, res)
             assert abs(np.linalg.norm(X[:, i]) - 1.0) < 1e-12
+        # ... and the eigenvalues against the CPU oracle at this very size (block LU + ARPACK on the
+        # same synthetic pencil, tests/golden/synthetic_P600_b600_eigs.json, tools/make_fullsize_golden.py)
+        gold = json.load(open(os.path.join(ROOT, "tests", "golden", "synthetic_P600_b600_eigs.json")))
+        assert gold["n"] == n and gold["nev"] == 10
+        for re_, im_ in gold["eigs"]:
+            z = complex(re_, im_)
+            assert np.min(np.abs(lam - z)) <= 1e-9 * abs(z), z
 
 
 @pytest.mark.parametrize("b", [676, 700, 800])

@@ -100,7 +100,7 @@ def test_real_expired_wait_ends_the_launch_quickly(lib):
 
 
 def test_repeated_factor_and_eigs_are_deterministic_full_size(lib):
-    # P = b = 600 (the benchmark's size), 30 factor + eigensolve steps on one handle: no fall-back,
+    # P = b = 600 (the benchmark's size), 50 factor + eigensolve steps on one handle: no fall-back,
     # and every step returns bit-identical eigenvalues (a lost or late exchange would not)
     from kore_b200 import synthetic
     A, B, perm, nodeptr = synthetic.synthetic_pencil(600, 600)
@@ -109,7 +109,7 @@ def test_repeated_factor_and_eigs_are_deterministic_full_size(lib):
     s.set_pencil(A, B)
     s.set_chain(perm, nodeptr)
     ref = None
-    for it in range(30):
+    for it in range(50):
         s.factor(1j)
         lam, _, info = s.eigs(10, "TM", target=1j, ncv=25, tol=1e-12, maxit=100, v0=v0, want_vectors=False)
         assert info["nconv"] >= 10 and info["protocol_fallbacks"] == 0, (it, info)
