@@ -735,6 +735,7 @@ int kbi_factor(kb_context* h, zcomplex sigma) {
   h->factored = false;
   h->M_transposed = false;
   h->fold_ready = false;
+  h->fold_required = false;
   h->rng_valid = false;
   h->sigma = sigma;
   h->ch_lo = 0;
@@ -789,6 +790,16 @@ int kbi_factor(kb_context* h, zcomplex sigma) {
       if (gsz >= 1 && gsz < sg) sg = gsz;
     }
     h->M_transposed = h->opt_sweep == 1 && kbi_onehop_supported(h, sg, two_sided, nullptr, nullptr);
+    if (!h->M_transposed && h->opt_sweep == 1 && h->opt_fold) {
+      // nodes too wide for the one-hop sweep's two stages (641 .. 704 rows) still fit the folded
+      // sweep with a single slice stage; it reads the transposed factors as well
+      h->sweep_grid_hint = sg;
+      h->M_transposed = true;
+      const int64_t cap = two_sided ? 2 * h->bmin : h->bmin;
+      const bool ok = kbi_fold_supported(h, (int)(sg < cap ? sg : cap), two_sided, nullptr, nullptr);
+      h->M_transposed = ok;
+      h->fold_required = ok;
+    }
     KB_TRY(kbi_chainfac_run(h, two_sided, h->M_transposed));
   } else if (two_sided) {
     if (!h->stream2) KB_CUDA(h, cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
@@ -849,6 +860,9 @@ int kbi_factor(kb_context* h, zcomplex sigma) {
   }
   KB_TRY(kbi_sweep_prepare(h));
   if (h->opt_fold) KB_TRY(kbi_fold_prepare(h));
+  if (h->fold_required && !h->fold_ready)
+    return kb_fail(h, KB_ENOMEM, "cannot allocate the folded couplings (%.2f GB) that nodes of %lld rows need",
+                   2.0 * h->Moff[P] * 16.0 / 1e9, (long long)bmax);
   KB_CUDA(h, cudaEventRecord(ev.e1, s));
   KB_TRY(kbi_sync(h));
   int info = 0;

@@ -337,6 +337,8 @@ struct kb_context {
   // folded sweep (kb_sweep2.cu): FL_p = L M_p, FU_p = U M_p, step schedules, exchange ring
   int opt_fold = 1;
   bool fold_ready = false;
+  bool fold_required = false;  // the factors are transposed for the folded sweep alone (no one-hop fall-back)
+  int sweep_grid_hint = 0;
   DevBuf<double2> d_fold, d_uvec;
   DevBuf<int64_t> d_foldoff;
   DevBuf<unsigned char> d_foldops, d_foldring;

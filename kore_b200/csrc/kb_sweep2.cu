@@ -46,7 +46,9 @@
 #define K2_RW 6
 #define K2_THREADS (K2_CW * 32)
 #define K2_CPL 20                // columns of a row per lane: nodes up to 32 * K2_CPL = 640 wide
-#define K2_PPT 10                // entries of the input vector polled per gather thread (640 / 64)
+#define K2_CPL_WIDE 22           // ... and up to 704 wide (Kore's own rule at E = 1e-8 gives N = 676): second
+                                 // instantiation, a few spilled registers, ONE slice stage (two do not fit)
+// entries of the input vector polled per gather thread: 32 * CPL / 64 gather threads = CPL / 2
 #define K2_RING 4                // publication ring slots (power of two)
 #define K2_XR 10                 // most rows of a node a CTA may own: warps 0-3 take two, 4-5 one
 #ifndef K2_AHEAD
@@ -156,11 +158,17 @@ __device__ __forceinline__ void k2_bar_empty_wait(int s) {
   asm volatile("bar.sync %0, %1;" ::"r"((s & 1) ? 7 : 6), "n"(K2_THREADS) : "memory");
 }
 
+// CPL = columns of a row per lane; NST = stages of the row slice in shared memory (2: the copy of
+// step s+2 is issued when step s has its rows in registers; 1: the copy of step s+1, which then has
+// the products, the reduction and the exchange of step s to arrive from L2 -- for slices too large
+// for two stages)
+template <int CPL, int NST>
 __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int slice_elems) {
+  constexpr int K2_PPT = CPL / 2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double2* stage0 = (double2*)smem_raw;                  // 2 stages of this CTA's row slice of F
+  double2* stage0 = (double2*)smem_raw;                  // NST stages of this CTA's row slice of F
   const int bpad = (q.bmax + 7) & ~7;
-  double2* vbuf = stage0 + 2 * (size_t)slice_elems;      // 2 x bpad: input vector, by step parity
+  double2* vbuf = stage0 + NST * (size_t)slice_elems;    // 2 x bpad: input vector, by step parity
   int* s_nptr = (int*)(vbuf + 2 * (size_t)bpad);
   __shared__ __align__(8) uint64_t mbar[2];
   __shared__ int s_failed;  // some thread of this CTA has seen the launch fail
@@ -303,9 +311,10 @@ __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int s
     unsigned bytes;
     slice_of(sn, src, bytes);
     if (bytes) {
-      uint64_t* mb = &mbar[sn & 1];
+      const int st = NST == 2 ? (sn & 1) : 0;
+      uint64_t* mb = &mbar[st];
       kb_mbar_expect_tx(mb, bytes);
-      kb_bulk_g2s(stage0 + (size_t)(sn & 1) * slice_elems, src, bytes, mb);
+      kb_bulk_g2s(stage0 + (size_t)st * slice_elems, src, bytes, mb);
     }
   };
   auto prefetch = [&](int sn) {
@@ -321,7 +330,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int s
   };
   if (tid == 0) {
     issue_copy(0);
-    issue_copy(1);
+    if (NST == 2) issue_copy(1);
   }
   if (tid == 1)
     for (int sn = 2; sn < K2_AHEAD; ++sn) prefetch(sn);
@@ -343,7 +352,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int s
     //         this warp's rows of F from the staged slice into registers (after which the stage
     //         is free for the slice of step s+2), the base values
     int oo = 0, a0 = 0, nr = 0;
-    double2 f[2][K2_CPL];
+    double2 f[2][CPL];
     double2 base[2] = {zmake(0.0, 0.0), zmake(0.0, 0.0)};
     if (op.mat_off >= 0) {
       oo = s_nptr[op.out_node];
@@ -357,19 +366,19 @@ __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int s
       a0 = c_a0;
       nr = c_nr;
       if (nr > 0) {
-        if (s & 1) {
+        if (NST == 2 && (s & 1)) {
           kb_mbar_wait(&mbar[1], uses1 & 1u, q.err, q.wait_ns);
           uses1++;
         } else {
           kb_mbar_wait(&mbar[0], uses0 & 1u, q.err, q.wait_ns);
           uses0++;
         }
-        const double2* Fs = stage0 + (size_t)(s & 1) * slice_elems + (size_t)row0 * bi + lane;
+        const double2* Fs = stage0 + (size_t)(NST == 2 ? (s & 1) : 0) * slice_elems + (size_t)row0 * bi + lane;
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
           const bool rok = rr < nrow && row0 + rr < nr;
 #pragma unroll
-          for (int k = 0; k < K2_CPL; ++k)
+          for (int k = 0; k < CPL; ++k)
             f[rr][k] = (rok && lane + 32 * k < bi) ? Fs[(size_t)rr * bi + 32 * k] : zmake(0.0, 0.0);
           if (rok && lane == 0) {
             if (op.base_kind == 1) base[rr] = q.r[oo + a0 + row0 + rr];
@@ -379,7 +388,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int s
       }
     }
     k2_bar_rows();  // every row warp holds its rows: the stage of step s may be refilled
-    if (tid == 0) issue_copy(s + 2);
+    if (tid == 0) issue_copy(s + NST);
     if (tid == 1) prefetch(s + K2_AHEAD);
     K2_TICK(0);
 
@@ -395,14 +404,14 @@ __global__ void __launch_bounds__(K2_THREADS, 1) kb_sweep_fold(K2Params q, int s
 #if defined(K2_EXP) && (K2_EXP & 1)
       // timing experiment: no products
 #pragma unroll
-      for (int k = 0; k < K2_CPL; ++k) {
+      for (int k = 0; k < CPL; ++k) {
         acc[0][k & 1] = zadd(acc[0][k & 1], f[0][k]);
         acc[1][k & 1] = zadd(acc[1][k & 1], f[1][k]);
       }
       acc[0][0] = zadd(acc[0][0], v[lane]);
 #else
 #pragma unroll
-      for (int k = 0; k < K2_CPL; ++k) {
+      for (int k = 0; k < CPL; ++k) {
         const int j = lane + 32 * k;
         const double2 vj = j < bi ? v[j] : zmake(0.0, 0.0);
         zfma(acc[0][k & 1], f[0][k], vj);
@@ -579,11 +588,13 @@ bool kbi_fold_supported(const kb_context* h, int G, bool two_sided, int* slice_e
   const int gmin = two_sided ? G / 2 : G;
   if (gmin < 1) return false;
   const int64_t rpc = (h->bmax + gmin - 1) / gmin;
-  if (rpc > K2_XR || h->bmax > 32 * K2_CPL || h->bmax > K2_PPT * (K2_CW - K2_RW) * 32) return false;
+  if (rpc > K2_XR || h->bmax > 32 * K2_CPL_WIDE) return false;
   const int64_t slice_elems = (rpc * h->bmax + 7) & ~(int64_t)7;
   const size_t bpad = (size_t)((h->bmax + 7) & ~(int64_t)7);
-  const size_t smem = 2 * (size_t)slice_elems * sizeof(double2) + 2 * bpad * sizeof(double2) +
-                      (size_t)(h->P + 1) * sizeof(int) + 16;
+  // two slice stages when they fit, one otherwise
+  const size_t fixed = 2 * bpad * sizeof(double2) + (size_t)(h->P + 1) * sizeof(int) + 16;
+  size_t smem = 2 * (size_t)slice_elems * sizeof(double2) + fixed;
+  if (smem > 220 * 1024) smem = (size_t)slice_elems * sizeof(double2) + fixed;
   if (smem > 220 * 1024) return false;
   if (slice_elems_out) *slice_elems_out = (int)slice_elems;
   if (smem_out) *smem_out = smem;
@@ -767,7 +778,10 @@ int kbi_sweep_fold(kb_context* h, const double2* r, double2* y, int ends_only) {
   q.timing = h->d_sweep_timing.p;
   q.bmax = (int)h->bmax;
   q.G0 = G0;
-  const void* fn = (const void*)kb_sweep_fold;
+  const bool one_stage = smem < 2 * (size_t)slice_elems * sizeof(double2);
+  const bool wide = h->bmax > 32 * K2_CPL;
+  const void* fn = wide ? (one_stage ? (const void*)kb_sweep_fold<K2_CPL_WIDE, 1> : (const void*)kb_sweep_fold<K2_CPL_WIDE, 2>)
+                        : (one_stage ? (const void*)kb_sweep_fold<K2_CPL, 1> : (const void*)kb_sweep_fold<K2_CPL, 2>);
   if (smem > 48 * 1024) KB_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* args[] = {(void*)&q, (void*)&slice_elems};
   KB_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(G), dim3(K2_THREADS), args, smem, s));
