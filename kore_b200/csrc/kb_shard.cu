@@ -234,9 +234,9 @@ __global__ void kb_first_panel(const double2* __restrict__ S, int n, int nb0, do
 // ---------------------------------------------------------------------------
 // Batched dense products of the fast l-sharded factorisation (below): up to four independent
 // C = beta C + alpha op(A) B, one problem per blockIdx.z, row-major.  32 x 64 tiles (190 per
-// 600 x 600 product: two to four products fill 148 SMs x 4 resident CTAs evenly), 8 deep, 4 x 4
-// complex accumulators per thread, two shared-memory stages filled by 16-byte cp.async copies
-// (zero-filled outside the matrices) so that a k-tile costs one wait and two barriers.  op(A) = A^T reads A (k x m, row-major) by columns -- the explicit inverses
+// 600 x 600 product: two to four products spread evenly over 148 SMs x 4 resident CTAs), 8 deep, two
+// shared-memory stages filled by 16-byte cp.async copies (zero-filled outside the matrices) so that
+// a k-tile costs one wait and two barriers.  op(A) = A^T reads A (k x m, row-major) by columns -- the explicit inverses
 // are stored transposed.  FP64 FMA issue is the bound: 64 DFMA per thread and k-step against 8
 // 16-byte shared-memory loads, two of which are warp broadcasts.
 // ---------------------------------------------------------------------------
@@ -258,22 +258,39 @@ struct KbGemmBatch {
 #define ZG_BN 64
 #define ZG_BK 8
 #define ZG_THREADS 128
+#define ZG_PA (ZG_BK + 4)   // pitch of an A-tile row (complex elements): = 4 (mod 8), conflict-free 16-byte fragment loads
+#define ZG_PB (ZG_BN + 2)   // pitch of a B-tile row: = 2 (mod 8)
 
 // 16-byte asynchronous global -> shared copy; ok == false writes zeros (src-size 0)
 __device__ __forceinline__ void zg_cp16(void* dst, const void* src, bool ok) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(kb_smem_addr(dst)), "l"(src), "r"(ok ? 16 : 0)
                : "memory");
 }
+// FP64 tensor-core product D(8x8) += A(8x4) B(4x8): lane = 4 g + t holds A[g][t], B[t][g], D[g][2t], D[g][2t+1]
+__device__ __forceinline__ void zg_dmma(double (&d)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d[0]), "+d"(d[1])
+               : "d"(a), "d"(b));
+}
 
+// The products are contraction-bound (ncu on the SIMT version of this kernel: FP64 pipe 62.5 % active,
+// math-pipe throttle the first stall reason; a DFMA with three distinct register operands issues
+// every ~3 cycles, not 2), so they run on the FP64 tensor cores: DMMA m8n8k4 measures 37.1 TFLOP/s on
+// this part, the same peak as the DFMA pipe, at an eighth of the instructions
+// (profiles/r2p_microbench_dmma_vs_dfma_rate.txt).  A complex product is four real ones:
+//   Cre += Are Bre + (-Aim) Bim,   Cim += Are Bim + Aim Bre.
+// CTA = 4 warps side by side (one per SM sub-partition, so that the last CTAs of a launch still use
+// the whole SM), each a 32 x 16 complex tile = 4 x 2 DMMA blocks: 32 DMMAs and 6 fragment loads
+// (16 bytes: re and im together) per k-step of 4.
 __global__ void __launch_bounds__(ZG_THREADS, 4) kb_zgemm_batch(KbGemmBatch batch) {
   const KbGemmProb& g = batch.p[blockIdx.z];
   const int m = g.m, n = g.n, k = g.k;
   const int row0 = blockIdx.y * ZG_BM, col0 = blockIdx.x * ZG_BN;
   if (row0 >= m || col0 >= n) return;
-  // two stages; A tile k-major with an odd pitch (the rows a thread reads are 8 apart)
-  __shared__ __align__(16) double2 As[2][ZG_BK][ZG_BM + 1];
-  __shared__ __align__(16) double2 Bs[2][ZG_BK][ZG_BN];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  __shared__ __align__(16) double2 As[2][ZG_BM][ZG_PA];  // [row][k]
+  __shared__ __align__(16) double2 Bs[2][ZG_BK][ZG_PB];  // [k][col]
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int gq = lane >> 2, tq = lane & 3;
   const double2* __restrict__ A = g.A;
   const double2* __restrict__ B = g.B;
   const int lda = g.lda, ldb = g.ldb, transA = g.transA;
@@ -292,7 +309,7 @@ __global__ void __launch_bounds__(ZG_THREADS, 4) kb_zgemm_batch(KbGemmBatch batc
       const int gi = row0 + i, gk = kk + q;
       const bool ok = gi < m && gk < k;
       const double2* src = ok ? (transA ? A + (size_t)gk * lda + gi : A + (size_t)gi * lda + gk) : A;
-      zg_cp16(&As[st][q][i], src, ok);
+      zg_cp16(&As[st][i][q], src, ok);
     }
 #pragma unroll
     for (int u = 0; u < (ZG_BK * ZG_BN) / ZG_THREADS; ++u) {
@@ -304,11 +321,11 @@ __global__ void __launch_bounds__(ZG_THREADS, 4) kb_zgemm_batch(KbGemmBatch batc
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  double2 acc[4][4];
+  double cre[4][2][2], cim[4][2][2];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[a][c] = zmake(0.0, 0.0);
+    for (int c = 0; c < 2; ++c) cre[a][c][0] = cre[a][c][1] = cim[a][c][0] = cim[a][c][1] = 0.0;
   issue(0, 0);
   int st = 0;
   for (int kk = 0; kk < k; kk += ZG_BK) {
@@ -320,16 +337,30 @@ __global__ void __launch_bounds__(ZG_THREADS, 4) kb_zgemm_batch(KbGemmBatch batc
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 #pragma unroll
-    for (int q = 0; q < ZG_BK; ++q) {
-      double2 av[4], bv[4];
+    for (int kq = 0; kq < ZG_BK / 4; ++kq) {
+      double are[4], aim[4], nim[4], bre[2], bim[2];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) av[a] = As[st][q][ty + 8 * a];
+      for (int a = 0; a < 4; ++a) {
+        const double2 v = As[st][8 * a + gq][4 * kq + tq];
+        are[a] = v.x;
+        aim[a] = v.y;
+        nim[a] = -v.y;
+      }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) bv[c] = Bs[st][q][tx + 16 * c];
+      for (int c = 0; c < 2; ++c) {
+        const double2 v = Bs[st][4 * kq + tq][16 * wid + 8 * c + gq];
+        bre[c] = v.x;
+        bim[c] = v.y;
+      }
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) zfma(acc[a][c], av[a], bv[c]);
+        for (int c = 0; c < 2; ++c) {
+          zg_dmma(cre[a][c], are[a], bre[c]);
+          zg_dmma(cim[a][c], are[a], bim[c]);
+          zg_dmma(cre[a][c], nim[a], bim[c]);
+          zg_dmma(cim[a][c], aim[a], bre[c]);
+        }
     }
     __syncthreads();
     st ^= 1;
@@ -338,15 +369,18 @@ __global__ void __launch_bounds__(ZG_THREADS, 4) kb_zgemm_batch(KbGemmBatch batc
   const int ldc = g.ldc;
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
-    const int gi = row0 + ty + 8 * a;
+    const int gi = row0 + 8 * a + gq;
     if (gi >= m) continue;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int gj = col0 + tx + 16 * c;
-      if (gj >= n) continue;
-      double2 v = zscale(acc[a][c], g.alpha);
-      if (g.beta != 0.0) v = zadd(v, zscale(C[(size_t)gi * ldc + gj], g.beta));
-      C[(size_t)gi * ldc + gj] = v;
+    for (int c = 0; c < 2; ++c) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int gj = col0 + 16 * wid + 8 * c + 2 * tq + u;
+        if (gj >= n) continue;
+        double2 v = zmake(cre[a][c][u] * g.alpha, cim[a][c][u] * g.alpha);
+        if (g.beta != 0.0) v = zadd(v, zscale(C[(size_t)gi * ldc + gj], g.beta));
+        C[(size_t)gi * ldc + gj] = v;
+      }
     }
   }
 }
