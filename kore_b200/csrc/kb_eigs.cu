@@ -90,13 +90,21 @@ kb_multiaxpy(int n, int ncols, const double2* __restrict__ V, int64_t ldv, const
   }
 }
 
-// beta = sqrt(sum normpart); out[0] = beta; dst = w / beta
-__global__ void kb_norm_finish(int nparts, const double* __restrict__ normpart, double* __restrict__ beta) {
+// beta = sqrt(sum normpart); out[0] = beta; dst = w / beta.  take_sqrt = 0 leaves the sum of squares
+// (row-sharded vectors: the sums of the ranks are added first, kb_sqrt_inplace follows)
+__global__ void kb_norm_finish(int nparts, const double* __restrict__ normpart, double* __restrict__ beta,
+                               int take_sqrt = 1) {
   int lane = threadIdx.x;
   double acc = 0.0;
   for (int b = lane; b < nparts; b += 32) acc += normpart[b];
   for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-  if (lane == 0) beta[0] = sqrt(acc);
+  if (lane == 0) beta[0] = take_sqrt ? sqrt(acc) : acc;
+}
+__global__ void kb_sqrt_inplace(double* __restrict__ v) { v[0] = sqrt(v[0]); }
+// hsum (+)= h   (Gram-Schmidt coefficients after the sum over the ranks)
+__global__ void kb_accum_coeffs(int ncols, const double2* __restrict__ h, double2* __restrict__ hsum, int accumulate) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < ncols) hsum[c] = accumulate ? zadd(hsum[c], h[c]) : h[c];
 }
 __global__ void kb_scale_by_recip(int n, const double2* __restrict__ w, const double* __restrict__ beta,
                                   double2* __restrict__ dst) {
@@ -234,20 +242,56 @@ struct Krylov {
   // pinned host mirrors
   double2* h_host = nullptr;  // (ncv+1) entries of hsum per column -> S column
   double* beta_host = nullptr;
+  // l-sharded pencil: this rank keeps rows [r0, r0 + nl) of every basis vector (its segment of the
+  // chain); nchunks / nblocks count the LOCAL rows; coefficients and norms are summed over the ranks
+  bool sharded = false;
+  int r0 = 0, nl = 0;
+  double2* hscratch = nullptr;
 
   double2* col(int j) { return V + (size_t)j * ldv; }
+
+  // beta_dev <- ||v|| over all ranks from the per-block sums of squares in normpart
+  int finish_norm(int nparts) {
+    cudaStream_t s = h->stream;
+    kb_norm_finish<<<1, 32, 0, s>>>(nparts, normpart, beta_dev, sharded ? 0 : 1);
+    if (sharded) {
+      KB_TRY(kbi_shard_allreduce(h, beta_dev, 1));
+      kb_sqrt_inplace<<<1, 1, 0, s>>>(beta_dev);
+      h->launches++;
+    }
+    return KB_OK;
+  }
+
+  // v <- v / ||v||  (local rows)
+  int normalize(double2* v) {
+    cudaStream_t s = h->stream;
+    const int nb = std::min(nblocks, 512);
+    kb_norm2_partial<<<nb, 256, 0, s>>>(nl, v + r0, normpart);
+    KB_TRY(finish_norm(nb));
+    kb_scale_by_recip<<<nblk(nl, 256), 256, 0, s>>>(nl, v + r0, beta_dev, v + r0);
+    h->launches += 3;
+    KB_LAUNCH_CHECK(h);
+    return KB_OK;
+  }
 
   // w <- OP v_j ; orthogonalise against v_0..v_j (CGS2); S[:j+2, j]; v_{j+1} = w/beta
   int arnoldi_step(int j, int refine) {
     cudaStream_t s = h->stream;
     KB_TRY(kbi_apply_op_chain(h, col(j), w, refine));
     for (int pass = 0; pass < 2; ++pass) {
-      kb_multidot_partial<<<nchunks, KB_DOT_THREADS, 0, s>>>(n, j + 1, V, ldv, w, hpart);
-      kb_reduce_cols<<<j + 1, 32, 0, s>>>(j + 1, nchunks, hpart, hdev, hsum, pass);
-      kb_multiaxpy<<<nblocks, 256, 0, s>>>(n, j + 1, V, ldv, hdev, w, normpart);
+      kb_multidot_partial<<<nchunks, KB_DOT_THREADS, 0, s>>>(nl, j + 1, V + r0, ldv, w + r0, hpart);
+      if (!sharded) {
+        kb_reduce_cols<<<j + 1, 32, 0, s>>>(j + 1, nchunks, hpart, hdev, hsum, pass);
+      } else {
+        kb_reduce_cols<<<j + 1, 32, 0, s>>>(j + 1, nchunks, hpart, hdev, hscratch, 0);
+        KB_TRY(kbi_shard_allreduce(h, (double*)hdev, (size_t)2 * (j + 1)));
+        kb_accum_coeffs<<<1, 128, 0, s>>>(j + 1, hdev, hsum, pass);
+        h->launches++;
+      }
+      kb_multiaxpy<<<nblocks, 256, 0, s>>>(nl, j + 1, V + r0, ldv, hdev, w + r0, normpart);
     }
-    kb_norm_finish<<<1, 32, 0, s>>>(nblocks, normpart, beta_dev);
-    kb_scale_by_recip<<<nblk(n, 256), 256, 0, s>>>(n, w, beta_dev, col(j + 1));
+    KB_TRY(finish_norm(nblocks));
+    kb_scale_by_recip<<<nblk(nl, 256), 256, 0, s>>>(nl, w + r0, beta_dev, col(j + 1) + r0);
     h->launches += 8;
     KB_LAUNCH_CHECK(h);
     KB_CUDA(h, cudaMemcpyAsync(h_host + (size_t)j * (ncv + 1), hsum, (j + 1) * sizeof(double2),
@@ -340,6 +384,7 @@ static int eigs_impl(kb_handle h, int nev, int ncv, double tol, int maxit, int w
     kb_context* h;
     ~SweepTimerGuard() {
       h->time_sweeps = false;
+      h->keep_sharded = false;
       for (cudaEvent_t e : h->sweep_events) cudaEventDestroy(e);
       h->sweep_events.clear();
     }
@@ -352,8 +397,19 @@ static int eigs_impl(kb_handle h, int nev, int ncv, double tol, int maxit, int w
   K.n = n;
   K.ncv = ncv;
   K.ldv = ((int64_t)n + 15) / 16 * 16;
-  K.nchunks = (n + KB_DOT_CHUNK - 1) / KB_DOT_CHUNK;
-  K.nblocks = (int)nblk(n, 256);
+  K.sharded = h->nranks > 1;
+  K.r0 = 0;
+  K.nl = n;
+  if (K.sharded) {
+    // row-sharded basis: vectors live on the rank's segment, solves do not publish their result
+    int64_t r0, r1;
+    kbi_shard_rows(h, &r0, &r1);
+    K.r0 = (int)r0;
+    K.nl = (int)(r1 - r0);
+    h->keep_sharded = true;
+  }
+  K.nchunks = (K.nl + KB_DOT_CHUNK - 1) / KB_DOT_CHUNK;
+  K.nblocks = (int)nblk(K.nl, 256);
   KB_CUDA(h, h->d_V.alloc((size_t)K.ldv * (ncv + 1)));
   KB_CUDA(h, h->d_w.alloc(n));
   KB_CUDA(h, h->d_w2.alloc((size_t)3 * n));
@@ -368,6 +424,7 @@ static int eigs_impl(kb_handle h, int nev, int ncv, double tol, int maxit, int w
   K.w = h->d_w.p;
   K.hdev = h->d_h.p;
   K.hsum = h->d_h.p + (ncv + 2);
+  K.hscratch = h->d_h.p + 2 * (ncv + 2);
   K.hpart = h->d_hpart.p;
   K.Qdev = h->d_Q.p;
   K.normpart = d_normpart.p;
@@ -405,7 +462,7 @@ static int eigs_impl(kb_handle h, int nev, int ncv, double tol, int maxit, int w
     KB_CUDA(h, cudaStreamSynchronize(s));
     KB_TRY(kbi_apply_op_chain(h, K.w, K.col(0), h->opt_refine_eigs));
     h->stats.op_applies++;
-    KB_TRY(normalize_dev(h, n, K.col(0), K.normpart, K.beta_dev, std::min(K.nblocks, 512)));
+    KB_TRY(K.normalize(K.col(0)));
   }
 
   kbd::Mat S(m + 1, m);  // projected matrix with residual row
@@ -491,7 +548,8 @@ static int eigs_impl(kb_handle h, int nev, int ncv, double tol, int maxit, int w
         double2* axv = h->d_w2.p + n;
         double2* bxv = h->d_w2.p + 2 * (size_t)n;
         KB_CUDA(h, cudaMemcpyAsync(K.hdev, c.data(), m * sizeof(double2), cudaMemcpyHostToDevice, s));
-        kb_lincomb<<<nblk(n, 256), 256, 0, s>>>(n, m, K.V, K.ldv, K.hdev, xv);
+        kb_lincomb<<<nblk(K.nl, 256), 256, 0, s>>>(K.nl, m, K.V + K.r0, K.ldv, K.hdev, xv + K.r0);
+        if (K.sharded) KB_TRY(kbi_shard_gather_segments(h, xv));
         KB_TRY(kbi_spmv_A_chain(h, xv, axv));
         KB_TRY(kbi_spmv_B_chain(h, xv, bxv, false));
         const Z lam = sigma + 1.0 / Tm(i, i);
@@ -529,7 +587,7 @@ static int eigs_impl(kb_handle h, int nev, int ncv, double tol, int maxit, int w
       for (int j = 0; j < q; ++j)
         for (int i = 0; i < na; ++i) qh[(size_t)j * na + i] = zmake(Q(i, j).real(), Q(i, j).imag());
       KB_CUDA(h, cudaMemcpyAsync(K.Qdev, qh.data(), qh.size() * sizeof(double2), cudaMemcpyHostToDevice, s));
-      KB_TRY(restart_update(h, n, na, q, K.col(nconv), K.ldv, K.Qdev));
+      KB_TRY(restart_update(h, K.nl, na, q, K.col(nconv) + K.r0, K.ldv, K.Qdev));
       KB_CUDA(h, cudaMemcpyAsync(K.col(newk), K.col(m), (size_t)n * sizeof(double2), cudaMemcpyDeviceToDevice, s));
       KB_CUDA(h, cudaStreamSynchronize(s));
     }
@@ -549,7 +607,7 @@ static int eigs_impl(kb_handle h, int nev, int ncv, double tol, int maxit, int w
     for (int j = 0; j < na; ++j)
       for (int i = 0; i < na; ++i) qh[(size_t)j * na + i] = zmake(Qlast(i, j).real(), Qlast(i, j).imag());
     KB_CUDA(h, cudaMemcpyAsync(K.Qdev, qh.data(), qh.size() * sizeof(double2), cudaMemcpyHostToDevice, s));
-    KB_TRY(restart_update(h, n, na, na, K.col(nconv_before_last), K.ldv, K.Qdev));
+    KB_TRY(restart_update(h, K.nl, na, na, K.col(nconv_before_last) + K.r0, K.ldv, K.Qdev));
     KB_CUDA(h, cudaStreamSynchronize(s));
   }
 
@@ -570,7 +628,7 @@ static int eigs_impl(kb_handle h, int nev, int ncv, double tol, int maxit, int w
     std::vector<double2> zh(i + 1);
     for (int l = 0; l <= i; ++l) zh[l] = zmake(z[l].real(), z[l].imag());
     KB_CUDA(h, cudaMemcpyAsync(K.hdev, zh.data(), zh.size() * sizeof(double2), cudaMemcpyHostToDevice, s));
-    kb_lincomb<<<nblk(n, 256), 256, 0, s>>>(n, i + 1, K.V, K.ldv, K.hdev, x);
+    kb_lincomb<<<nblk(K.nl, 256), 256, 0, s>>>(K.nl, i + 1, K.V + K.r0, K.ldv, K.hdev, x + K.r0);
     h->launches++;
     KB_CUDA(h, cudaStreamSynchronize(s));
     if (h->opt_purify) {
@@ -578,7 +636,9 @@ static int eigs_impl(kb_handle h, int nev, int ncv, double tol, int maxit, int w
       h->stats.op_applies++;
       KB_CUDA(h, cudaMemcpyAsync(x, K.w, (size_t)n * sizeof(double2), cudaMemcpyDeviceToDevice, s));
     }
-    KB_TRY(normalize_dev(h, n, x, K.normpart, K.beta_dev, std::min(K.nblocks, 512)));
+    // the vector leaves the sharded world here: every rank holds all of it from now on
+    if (K.sharded) KB_TRY(kbi_shard_gather_segments(h, x));
+    KB_TRY(normalize_dev(h, n, x, K.normpart, K.beta_dev, std::min((int)nblk(n, 256), 512)));
     Z theta = Tm(i, i);
     Z lam = sigma + 1.0 / theta;
     evals[2 * i] = lam.real();

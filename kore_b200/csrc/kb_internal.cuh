@@ -405,6 +405,7 @@ struct kb_context {
   DevBuf<unsigned> d_redctr;                  // grid-barrier counter of the fused reduced solve
   unsigned red_epoch = 0;
   int red_grid = 0;
+  bool keep_sharded = false;                  // inside kb_eigs: solves leave their result on the rank's segment only
   bool shard_fast = false;                    // interior factored by the strip kernel, solved by the folded sweep
   DevBuf<double2> d_spk;                      // fast path: identity-column chains and corner blocks of T_I^{-1}
 
@@ -495,4 +496,8 @@ int kbi_factor_sharded(kb_context* h, zcomplex sigma);
 int kbi_chain_solve_sharded(kb_context* h, const double2* r_dev, double2* x_dev, int refine);
 int kbi_sharded_sweeps(kb_context* h, const double2* r, double2* y);
 void kbi_nccl_destroy(kb_context* h);
+void kbi_shard_rows(const kb_context* h, int64_t* row_lo, int64_t* row_hi);
+int kbi_shard_allreduce(kb_context* h, double* buf, size_t count);
+int kbi_shard_halo(kb_context* h, double2* x);
+int kbi_shard_gather_segments(kb_context* h, double2* x);
 __global__ void kb_norm2_partial(int n, const double2* __restrict__ v, double* __restrict__ out);

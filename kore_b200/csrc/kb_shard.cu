@@ -36,6 +36,9 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -56,6 +59,9 @@ bool nccl_load() {
   KB_SYM(CommDestroy, "ncclCommDestroy");
   KB_SYM(AllGather, "ncclAllGather");
   KB_SYM(Broadcast, "ncclBroadcast");
+  KB_SYM(AllReduce, "ncclAllReduce");
+  KB_SYM(Send, "ncclSend");
+  KB_SYM(Recv, "ncclRecv");
   KB_SYM(GroupStart, "ncclGroupStart");
   KB_SYM(GroupEnd, "ncclGroupEnd");
   KB_SYM(GetErrorString, "ncclGetErrorString");
@@ -1231,7 +1237,7 @@ static int sharded_sweeps_fast(kb_context* h, const double2* r, double2* y) {
   }
   KB_LAUNCH_CHECK(h);
   pt.mark("pass2");
-  KB_TRY(publish_interiors(h, y));
+  if (!h->keep_sharded) KB_TRY(publish_interiors(h, y));
   pt.mark("publish");
   if (pt.on) {
     ++timed_solves;
@@ -1299,10 +1305,69 @@ int kbi_sharded_sweeps(kb_context* h, const double2* r, double2* y) {
   (void)g;
   (void)G;
   (void)slot;
-  return publish_interiors(h, y);
+  return h->keep_sharded ? KB_OK : publish_interiors(h, y);
 }
 
 int kbi_chain_solve_sharded(kb_context* h, const double2* r, double2* x, int refine) {
   (void)refine;
   return kbi_sharded_sweeps(h, r, x);
+}
+
+// ---------------------------------------------------------------------------
+// Row-sharded Krylov basis (kb_eigs.cu with nranks > 1): every rank keeps the rows of its own
+// segment [seg_lo, seg_hi) of every basis vector; what crosses the ranks are the Gram-Schmidt
+// coefficients and norms (all-reduce of <= ncv + 1 numbers), one chain node of halo on each side for
+// the B product, and the separator contributions of the solve -- not vectors of length n.
+// ---------------------------------------------------------------------------
+void kbi_shard_rows(const kb_context* h, int64_t* row_lo, int64_t* row_hi) {
+  *row_lo = h->nodeptr[h->seg_lo[h->rank]];
+  *row_hi = h->nodeptr[h->seg_hi[h->rank]];
+}
+
+// in-place sum over the ranks of `count` doubles
+int kbi_shard_allreduce(kb_context* h, double* buf, size_t count) {
+  KB_NCCL(h, g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
+  return KB_OK;
+}
+
+// x holds this rank's segment; fetch the chain node above it and the node below it from the
+// neighbouring ranks (block-tridiagonal B and A reach no further)
+int kbi_shard_halo(kb_context* h, double2* x) {
+  const int g = h->rank, G = h->nranks;
+  const int64_t lo = h->seg_lo[g], hi = h->seg_hi[g];
+  KB_NCCL(h, g_nccl.GroupStart());
+  if (g > 0) {
+    KB_NCCL(h, g_nccl.Send(x + noff(h, lo), (size_t)nsize(h, lo) * 2, ncclDouble, g - 1, (ncclComm_t)h->nccl_comm,
+                           h->stream));
+    KB_NCCL(h, g_nccl.Recv(x + noff(h, lo - 1), (size_t)nsize(h, lo - 1) * 2, ncclDouble, g - 1,
+                           (ncclComm_t)h->nccl_comm, h->stream));
+  }
+  if (g < G - 1) {
+    KB_NCCL(h, g_nccl.Send(x + noff(h, hi - 1), (size_t)nsize(h, hi - 1) * 2, ncclDouble, g + 1,
+                           (ncclComm_t)h->nccl_comm, h->stream));
+    KB_NCCL(h, g_nccl.Recv(x + noff(h, hi), (size_t)nsize(h, hi) * 2, ncclDouble, g + 1, (ncclComm_t)h->nccl_comm,
+                           h->stream));
+  }
+  KB_NCCL(h, g_nccl.GroupEnd());
+  return KB_OK;
+}
+
+// every rank's segment of x to every rank (extraction of the eigenvectors)
+int kbi_shard_gather_segments(kb_context* h, double2* x) {
+  const int G = h->nranks;
+  const int64_t cnt0 = h->nodeptr[h->seg_hi[0]] - h->nodeptr[h->seg_lo[0]];
+  bool equal = true;
+  for (int q = 1; q < G; ++q) equal = equal && (h->nodeptr[h->seg_hi[q]] - h->nodeptr[h->seg_lo[q]] == cnt0);
+  if (equal) {
+    KB_NCCL(h, g_nccl.AllGather(x + (size_t)h->rank * cnt0, x, (size_t)cnt0 * 2, ncclDouble, (ncclComm_t)h->nccl_comm,
+                                h->stream));
+    return KB_OK;
+  }
+  KB_NCCL(h, g_nccl.GroupStart());
+  for (int q = 0; q < G; ++q) {
+    const int64_t off = h->nodeptr[h->seg_lo[q]], cnt = h->nodeptr[h->seg_hi[q]] - off;
+    KB_NCCL(h, g_nccl.Broadcast(x + off, x + off, (size_t)cnt * 2, ncclDouble, q, (ncclComm_t)h->nccl_comm, h->stream));
+  }
+  KB_NCCL(h, g_nccl.GroupEnd());
+  return KB_OK;
 }

@@ -411,9 +411,32 @@ int kbi_from_chain(kb_context* h, const double2* x_chain, double2* x_orig) {
 }
 
 // out = C T'^{-1} R B in      (chain order, unscaled vectors)
+// With h->keep_sharded (l-sharded eigensolve) `in` and `out` carry this rank's segment only: one
+// node of halo from each neighbour for the B product, the rows of the segment, the sharded solve
+// without its final publication, the column scaling of the segment.
 int kbi_apply_op_chain(kb_context* h, const double2* in_chain, double2* out_chain, int refine) {
   const int n = (int)h->n;
   KB_TRY(kbi_solve_workspace(h));
+  if (h->nranks > 1 && h->keep_sharded) {
+    cudaStream_t s = h->stream;
+    int64_t r0, r1;
+    kbi_shard_rows(h, &r0, &r1);
+    const int nl = (int)(r1 - r0);
+    KB_TRY(kbi_shard_halo(h, const_cast<double2*>(in_chain)));
+    if (h->b_is_complex)
+      kb_spmv<double2, 0, 8><<<nblk((int64_t)nl * 8, 256), 256, 0, s>>>(nl, h->d_browptr.p + r0, h->d_bcol.p, h->d_bval_c.p,
+                                                                      in_chain, h->d_rscale.p + r0, nullptr,
+                                                                      h->d_r.p + r0);
+    else
+      kb_spmv<double, 0, 8><<<nblk((int64_t)nl * 8, 256), 256, 0, s>>>(nl, h->d_browptr.p + r0, h->d_bcol.p, h->d_bval_r.p,
+                                                                     in_chain, h->d_rscale.p + r0, nullptr,
+                                                                     h->d_r.p + r0);
+    KB_TRY(kbi_chain_solve(h, h->d_r.p, h->d_y.p, 0));
+    kb_scale_vec<<<nblk(nl, 256), 256, 0, s>>>(nl, h->d_cscale.p + r0, h->d_y.p + r0, out_chain + r0);
+    h->launches += 2;
+    KB_LAUNCH_CHECK(h);
+    return KB_OK;
+  }
   KB_TRY(kbi_spmv_B_chain(h, in_chain, h->d_r.p, true));
   KB_TRY(kbi_chain_solve(h, h->d_r.p, h->d_y.p, refine));
   kb_scale_vec<<<nblk(n, 256), 256, 0, h->stream>>>(n, h->d_cscale.p, h->d_y.p, out_chain);
