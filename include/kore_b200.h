@@ -189,6 +189,11 @@ int kb_dbg_schur(int m, const double* H, int which, const double* sigma, const d
                  double* T, double* Q);
 int kb_dbg_factor_timing(kb_handle h, long long* out, int max_ctas);
 int kb_dbg_sweep_timing(kb_handle h, long long* out, int max_ctas);
+/* C = alpha op(A) B + beta C on host arrays through the batched complex128 product kernel of the
+ * l-sharded path (row-major; transA: A is k x m); `batch` identical problems per launch, `reps`
+ * timed launches, mean ms per launch in *ms (tools/dev_zgemm.py). */
+int kb_dbg_zgemm(kb_handle h, int m, int n, int k, int transA, const double* A, const double* B, double* C,
+                 double alpha, double beta, int batch, int reps, double* ms);
 
 #ifdef __cplusplus
 }

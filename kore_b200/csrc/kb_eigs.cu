@@ -90,21 +90,13 @@ kb_multiaxpy(int n, int ncols, const double2* __restrict__ V, int64_t ldv, const
   }
 }
 
-// beta = sqrt(sum normpart); out[0] = beta; dst = w / beta.  take_sqrt = 0 leaves the sum of squares
-// (row-sharded vectors: the sums of the ranks are added first, kb_sqrt_inplace follows)
-__global__ void kb_norm_finish(int nparts, const double* __restrict__ normpart, double* __restrict__ beta,
-                               int take_sqrt = 1) {
+// beta = sqrt(sum normpart); out[0] = beta; dst = w / beta
+__global__ void kb_norm_finish(int nparts, const double* __restrict__ normpart, double* __restrict__ beta) {
   int lane = threadIdx.x;
   double acc = 0.0;
   for (int b = lane; b < nparts; b += 32) acc += normpart[b];
   for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-  if (lane == 0) beta[0] = take_sqrt ? sqrt(acc) : acc;
-}
-__global__ void kb_sqrt_inplace(double* __restrict__ v) { v[0] = sqrt(v[0]); }
-// hsum (+)= h   (Gram-Schmidt coefficients after the sum over the ranks)
-__global__ void kb_accum_coeffs(int ncols, const double2* __restrict__ h, double2* __restrict__ hsum, int accumulate) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < ncols) hsum[c] = accumulate ? zadd(hsum[c], h[c]) : h[c];
+  if (lane == 0) beta[0] = sqrt(acc);
 }
 __global__ void kb_scale_by_recip(int n, const double2* __restrict__ w, const double* __restrict__ beta,
                                   double2* __restrict__ dst) {
@@ -252,13 +244,8 @@ struct Krylov {
 
   // beta_dev <- ||v|| over all ranks from the per-block sums of squares in normpart
   int finish_norm(int nparts) {
-    cudaStream_t s = h->stream;
-    kb_norm_finish<<<1, 32, 0, s>>>(nparts, normpart, beta_dev, sharded ? 0 : 1);
-    if (sharded) {
-      KB_TRY(kbi_shard_allreduce(h, beta_dev, 1));
-      kb_sqrt_inplace<<<1, 1, 0, s>>>(beta_dev);
-      h->launches++;
-    }
+    if (sharded) return kbi_shard_norm(h, nparts, normpart, beta_dev);
+    kb_norm_finish<<<1, 32, 0, h->stream>>>(nparts, normpart, beta_dev);
     return KB_OK;
   }
 
@@ -283,10 +270,7 @@ struct Krylov {
       if (!sharded) {
         kb_reduce_cols<<<j + 1, 32, 0, s>>>(j + 1, nchunks, hpart, hdev, hsum, pass);
       } else {
-        kb_reduce_cols<<<j + 1, 32, 0, s>>>(j + 1, nchunks, hpart, hdev, hscratch, 0);
-        KB_TRY(kbi_shard_allreduce(h, (double*)hdev, (size_t)2 * (j + 1)));
-        kb_accum_coeffs<<<1, 128, 0, s>>>(j + 1, hdev, hsum, pass);
-        h->launches++;
+        KB_TRY(kbi_shard_reduce_cols(h, j + 1, nchunks, hpart, hdev, hsum, hscratch, pass));
       }
       kb_multiaxpy<<<nblocks, 256, 0, s>>>(nl, j + 1, V + r0, ldv, hdev, w + r0, normpart);
     }

@@ -91,7 +91,8 @@ enum {
   KB_WERR_XCHG = 6,           // folded sweep: cross-group entry of the middle node
   KB_WERR_MBAR = 7,           // bulk (TMA) copy completion
   KB_WERR_SWEEP = 8,          // row-split / one-hop sweeps (kb_sweep.cu, kb_sweep1.cu)
-  KB_WERR_WATCHDOG = 9        // raised by the host: kernel exceeded its deadline
+  KB_WERR_WATCHDOG = 9,       // raised by the host: kernel exceeded its deadline
+  KB_WERR_MAILBOX = 10        // l-sharded path: message of a peer rank (peer-memory mailbox)
 };
 
 __device__ __forceinline__ unsigned long long kb_globaltimer() {
@@ -131,6 +132,57 @@ __device__ __forceinline__ bool kb_spin_expired(KbSpin& s, int* err, int code, u
   return false;
 }
 __device__ __forceinline__ bool kb_launch_failed(const int* err) { return *(volatile const int*)err != 0; }
+
+// ---------------------------------------------------------------------------
+// Peer-memory mailboxes of the l-sharded path (kb_shard.cu): every rank owns a buffer that all
+// other ranks of the node map through CUDA IPC and write with plain NVLink stores.  A collective
+// of a few hundred bytes (Gram-Schmidt coefficients, a norm, separator contributions, a halo node)
+// is then: store the payload into every peer's slot, fence, store the epoch into every peer's flag,
+// poll the own flags, read the own slots -- inside the kernel that produced the payload, with no
+// collective launch and no proxy thread.  Layout of one buffer:
+//   data  [2 parities][KB_MB_MAXRANKS senders][KB_MB_SLOT bytes]
+//   flags [2 parities][KB_MB_MAXRANKS senders] x one 128-byte line (unsigned epoch of the last message)
+// Consecutive collectives alternate the parity; every collective raises a flag on EVERY peer, so a
+// rank can never be more than one collective ahead of any other and two parities suffice.
+// ---------------------------------------------------------------------------
+#define KB_MB_MAXRANKS 16
+#define KB_MB_SLOT 32768
+#define KB_MB_BYTES ((size_t)2 * KB_MB_MAXRANKS * KB_MB_SLOT + (size_t)2 * KB_MB_MAXRANKS * 128)
+struct KbMailbox {
+  int rank, nranks;
+  unsigned char* base[KB_MB_MAXRANKS];  // base[q]: rank q's buffer as mapped here (base[rank]: the local one)
+};
+__device__ __forceinline__ double2* kb_mb_data(const KbMailbox& m, int owner, int par, int sender) {
+  return (double2*)(m.base[owner] + (size_t)(par * KB_MB_MAXRANKS + sender) * KB_MB_SLOT);
+}
+__device__ __forceinline__ unsigned* kb_mb_flag(const KbMailbox& m, int owner, int par, int sender) {
+  return (unsigned*)(m.base[owner] + (size_t)2 * KB_MB_MAXRANKS * KB_MB_SLOT) + (par * KB_MB_MAXRANKS + sender) * 32;
+}
+// After the CTA has stored its payloads: make them visible system-wide, then raise this rank's
+// flag on every peer (all threads call; one thread fences and stores).
+__device__ __forceinline__ void kb_mb_signal_all(const KbMailbox& m, unsigned epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const int par = (int)(epoch & 1u);
+    for (int q = 0; q < m.nranks; ++q)
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(kb_mb_flag(m, q, par, m.rank)), "r"(epoch) : "memory");
+  }
+}
+// Wait until every rank's message of this epoch has landed in the own buffer (all threads call).
+__device__ __forceinline__ void kb_mb_wait_all(const KbMailbox& m, unsigned epoch, int* err, unsigned long long wait_ns) {
+  if ((int)threadIdx.x < m.nranks) {
+    const unsigned* f = kb_mb_flag(m, m.rank, (int)(epoch & 1u), (int)threadIdx.x);
+    KbSpin sp;
+    for (;;) {
+      unsigned v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if ((int)(v - epoch) >= 0) break;
+      if (kb_spin_expired(sp, err, KB_WERR_MAILBOX, wait_ns)) break;
+    }
+  }
+  __syncthreads();
+}
 
 // ---- mbarrier + 1-D bulk (TMA) copy helpers
 __device__ __forceinline__ unsigned kb_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -402,6 +454,11 @@ struct kb_context {
   DevBuf<double2> d_sepvec, d_sepvec_all;     // per-solve separator contributions
   DevBuf<double2> d_redz;                     // reduced-solve scratch
   DevBuf<int64_t> d_redtab;                   // {0, b_j} per separator + a zero: one-node chains for the strip kernel
+  // peer-memory mailboxes (CUDA IPC): own buffer, peers' mappings, collective counter
+  DevBuf<unsigned char> d_mbox;
+  void* mb_peer[KB_MB_MAXRANKS] = {nullptr};
+  bool mb_ready = false;
+  unsigned mb_epoch = 0;
   DevBuf<unsigned> d_redctr;                  // grid-barrier counter of the fused reduced solve
   unsigned red_epoch = 0;
   int red_grid = 0;
@@ -500,4 +557,8 @@ void kbi_shard_rows(const kb_context* h, int64_t* row_lo, int64_t* row_hi);
 int kbi_shard_allreduce(kb_context* h, double* buf, size_t count);
 int kbi_shard_halo(kb_context* h, double2* x);
 int kbi_shard_gather_segments(kb_context* h, double2* x);
+// fused local reduction + sum over the ranks (peer-memory mailboxes when mapped, NCCL otherwise)
+int kbi_shard_reduce_cols(kb_context* h, int ncols, int nchunks, const double2* hpart, double2* hdev, double2* hsum,
+                          double2* scratch, int accumulate);
+int kbi_shard_norm(kb_context* h, int nparts, const double* normpart, double* beta_dev);
 __global__ void kb_norm2_partial(int n, const double2* __restrict__ v, double* __restrict__ out);

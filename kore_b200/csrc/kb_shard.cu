@@ -79,7 +79,10 @@ bool nccl_load() {
                      __FILE__, __LINE__);                                                         \
   } while (0)
 
+static void mailbox_close(kb_context* h);
+
 void kbi_nccl_destroy(kb_context* h) {
+  mailbox_close(h);
   if (h->nccl_comm && g_nccl.ok) g_nccl.CommDestroy((ncclComm_t)h->nccl_comm);
   h->nccl_comm = nullptr;
 }
@@ -94,6 +97,8 @@ extern "C" int kb_nccl_unique_id(void* id128) {
 }
 
 static int shard_ranges(kb_context* h);
+static int mailbox_setup(kb_context* h);
+static void mailbox_close(kb_context* h);
 
 extern "C" int kb_set_sharding(kb_handle h, int rank, int nranks, const void* id128) {
   if (!h) return KB_EINVAL;
@@ -119,7 +124,76 @@ extern "C" int kb_set_sharding(kb_handle h, int rank, int nranks, const void* id
   h->nccl_comm = (void*)comm;
   h->rank = rank;
   h->nranks = nranks;
+  KB_TRY(mailbox_setup(h));
   return shard_ranges(h);
+}
+
+// Map every rank's mailbox buffer into every other rank (CUDA IPC; the handles travel through one
+// ncclAllGather).  Any failure leaves mb_ready == false on ALL ranks (they agree through an
+// all-reduce) and the small collectives stay on NCCL.
+static void mailbox_close(kb_context* h) {
+  for (int q = 0; q < KB_MB_MAXRANKS; ++q) {
+    if (h->mb_peer[q] && q != h->rank) cudaIpcCloseMemHandle(h->mb_peer[q]);
+    h->mb_peer[q] = nullptr;
+  }
+  h->mb_ready = false;
+}
+
+static int mailbox_setup(kb_context* h) {
+  mailbox_close(h);
+  const int G = h->nranks, g = h->rank;
+  cudaStream_t s = h->stream;
+  int ok = (G <= KB_MB_MAXRANKS && !getenv("KB_SHARD_NCCL_ONLY")) ? 1 : 0;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (ok) {
+    ok = h->d_mbox.alloc(KB_MB_BYTES) == cudaSuccess && cudaMemsetAsync(h->d_mbox.p, 0, KB_MB_BYTES, s) == cudaSuccess &&
+         cudaStreamSynchronize(s) == cudaSuccess && cudaIpcGetMemHandle(&mine, h->d_mbox.p) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+  }
+  DevBuf<unsigned char> dh;
+  DevBuf<int> dflag;
+  KB_CUDA(h, dh.alloc(sizeof(mine) * (size_t)G));
+  KB_CUDA(h, dflag.alloc(1));
+  KB_CUDA(h, cudaMemcpyAsync(dh.p + sizeof(mine) * (size_t)g, &mine, sizeof(mine), cudaMemcpyHostToDevice, s));
+  KB_NCCL(h, g_nccl.AllGather(dh.p + sizeof(mine) * (size_t)g, dh.p, sizeof(mine), ncclChar, (ncclComm_t)h->nccl_comm, s));
+  std::vector<cudaIpcMemHandle_t> all(G);
+  KB_CUDA(h, cudaMemcpyAsync(all.data(), dh.p, sizeof(mine) * (size_t)G, cudaMemcpyDeviceToHost, s));
+  KB_CUDA(h, cudaStreamSynchronize(s));
+  if (ok) {
+    h->mb_peer[g] = h->d_mbox.p;
+    for (int q = 0; q < G && ok; ++q) {
+      if (q == g) continue;
+      void* pp = nullptr;
+      if (cudaIpcOpenMemHandle(&pp, all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+      } else {
+        h->mb_peer[q] = pp;
+      }
+    }
+  }
+  // agree: the mailboxes are used only if every rank mapped every peer
+  KB_CUDA(h, cudaMemcpyAsync(dflag.p, &ok, sizeof(int), cudaMemcpyHostToDevice, s));
+  KB_NCCL(h, g_nccl.AllReduce(dflag.p, dflag.p, 1, ncclInt, ncclMin, (ncclComm_t)h->nccl_comm, s));
+  int all_ok = 0;
+  KB_CUDA(h, cudaMemcpyAsync(&all_ok, dflag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  KB_CUDA(h, cudaStreamSynchronize(s));
+  if (!all_ok) {
+    mailbox_close(h);
+    return KB_OK;
+  }
+  h->mb_ready = true;
+  h->mb_epoch = 0;
+  return KB_OK;
+}
+
+static KbMailbox mailbox_of(const kb_context* h) {
+  KbMailbox m;
+  m.rank = h->rank;
+  m.nranks = h->nranks;
+  for (int q = 0; q < KB_MB_MAXRANKS; ++q) m.base[q] = (unsigned char*)h->mb_peer[q];
+  return m;
 }
 
 // contiguous, near-equal node ranges (same rule as kore_b200/chain.py split_ranges); derived again at
@@ -438,7 +512,14 @@ struct KbRedParams {
   const double2* E[KB_MAXSEP];   // bs_j x bs_{j-1}; unused for j = 0
   const double2* Fm[KB_MAXSEP];  // bs_j x bs_{j+1}; unused for j = nsep-1
   double2* xout[KB_MAXSEP];      // where x_j goes (the solution vector at separator j)
-  const double2* sepvec_all;     // per rank 2 bmax entries: [at | tb]
+  const double2* sepvec_all;     // per rank `sepstride` entries apart: [at | tb] (2 bmax entries)
+  size_t sepstride;
+  // mailbox mode: CTA 0 first sends this rank's contribution `sv` to every peer, every CTA waits for
+  // all of them, and sepvec_all is the own mailbox (the all-gather is part of this launch)
+  int use_mb;
+  KbMailbox mb;
+  unsigned mb_epoch;
+  const double2* sv;
   double2* z;                    // nsep x bmax
   unsigned* ctr;
   unsigned epoch0;
@@ -467,16 +548,27 @@ __global__ void __launch_bounds__(256) kb_reduced_solve_kernel(KbRedParams q) {
   const int gw = blockIdx.x * 8 + (threadIdx.x >> 5), nw = gridDim.x * 8;
   unsigned epoch = q.epoch0;
   const size_t bm = (size_t)q.bmax;
+  if (q.use_mb) {
+    if (blockIdx.x == 0) {
+      const int par = (int)(q.mb_epoch & 1u);
+      for (int r = 0; r < q.mb.nranks; ++r) {
+        double2* dst = kb_mb_data(q.mb, r, par, q.mb.rank);
+        for (int i = threadIdx.x; i < 2 * q.bmax; i += blockDim.x) dst[i] = q.sv[i];
+      }
+      kb_mb_signal_all(q.mb, q.mb_epoch);
+    }
+    kb_mb_wait_all(q.mb, q.mb_epoch, q.err, q.wait_ns);
+  }
   for (int j = 0; j < q.nsep; ++j) {
     const int bs = q.bs[j], bsp = j > 0 ? q.bs[j - 1] : 0;
-    const double2* tb = q.sepvec_all + (size_t)j * 2 * bm + bm;
-    const double2* at = q.sepvec_all + (size_t)(j + 1) * 2 * bm;
+    const double2* tb = q.sepvec_all + (size_t)j * q.sepstride + bm;
+    const double2* at = q.sepvec_all + (size_t)(j + 1) * q.sepstride;
     const double2* zp = q.z + (size_t)(j > 0 ? j - 1 : 0) * bm;
     for (int row = gw; row < bs; row += nw) {
       double2 acc = zmake(0.0, 0.0);
       const double2* Mrow = q.Mr[j] + (size_t)row * bs;
 #pragma unroll 4
-      for (int c = lane; c < bs; c += 32) zfma(acc, Mrow[c], zsub(tb[c], at[c]));
+      for (int c = lane; c < bs; c += 32) zfma(acc, Mrow[c], zsub(__ldcg(&tb[c]), __ldcg(&at[c])));
       if (j > 0) {
         const double2* Erow = q.E[j] + (size_t)row * bsp;
 #pragma unroll 4
@@ -1120,6 +1212,10 @@ static int factor_sharded_fast(kb_context* h, double* flops_io, int64_t* bytes_i
 // ---------------------------------------------------------------------------
 // reduced solve (redundant on every rank) from the gathered separator contributions:
 //   z_j = Mr_j (rho_j - Csub_j z_{j-1});  x_j = z_j - Mr_j Csup_{j+1} x_{j+1};  x_j -> y at separator j
+static bool sepvec_by_mailbox(const kb_context* h) {
+  return h->mb_ready && (size_t)2 * h->bmax * sizeof(double2) <= KB_MB_SLOT;
+}
+
 static int reduced_solve(kb_context* h, double2* y) {
   cudaStream_t s = h->stream;
   const int G = h->nranks;
@@ -1139,6 +1235,16 @@ static int reduced_solve(kb_context* h, double2* y) {
     q.xout[j] = y + noff(h, sp);
   }
   q.sepvec_all = h->d_sepvec_all.p;
+  q.sepstride = (size_t)2 * bmax;
+  q.use_mb = 0;
+  if (h->mb_ready && (size_t)2 * bmax * sizeof(double2) <= KB_MB_SLOT) {
+    q.use_mb = 1;
+    q.mb = mailbox_of(h);
+    q.mb_epoch = ++h->mb_epoch;
+    q.sv = h->d_sepvec.p;
+    q.sepvec_all = (const double2*)(h->d_mbox.p + (size_t)(q.mb_epoch & 1u) * KB_MB_MAXRANKS * KB_MB_SLOT);
+    q.sepstride = KB_MB_SLOT / sizeof(double2);
+  }
   q.z = h->d_redz.p;
   int sms = 0;
   KB_CUDA(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
@@ -1223,7 +1329,8 @@ static int sharded_sweeps_fast(kb_context* h, const double2* r, double2* y) {
   }
   KB_LAUNCH_CHECK(h);
   pt.mark("sep-rhs");
-  KB_NCCL(h, g_nccl.AllGather(sv, h->d_sepvec_all.p, 2 * bmax * 2, ncclDouble, (ncclComm_t)h->nccl_comm, s));
+  if (!sepvec_by_mailbox(h))
+    KB_NCCL(h, g_nccl.AllGather(sv, h->d_sepvec_all.p, 2 * bmax * 2, ncclDouble, (ncclComm_t)h->nccl_comm, s));
   pt.mark("allgather");
   KB_TRY(reduced_solve(h, y));
   pt.mark("reduced-solve");
@@ -1281,7 +1388,8 @@ int kbi_sharded_sweeps(kb_context* h, const double2* r, double2* y) {
     h->launches++;
   }
   KB_LAUNCH_CHECK(h);
-  KB_NCCL(h, g_nccl.AllGather(sv, h->d_sepvec_all.p, 2 * bmax * 2, ncclDouble, (ncclComm_t)h->nccl_comm, s));
+  if (!sepvec_by_mailbox(h))
+    KB_NCCL(h, g_nccl.AllGather(sv, h->d_sepvec_all.p, 2 * bmax * 2, ncclDouble, (ncclComm_t)h->nccl_comm, s));
 
   KB_TRY(reduced_solve(h, y));
 
@@ -1319,9 +1427,147 @@ int kbi_chain_solve_sharded(kb_context* h, const double2* r, double2* x, int ref
 // coefficients and norms (all-reduce of <= ncv + 1 numbers), one chain node of halo on each side for
 // the B product, and the separator contributions of the solve -- not vectors of length n.
 // ---------------------------------------------------------------------------
+__global__ void kb_reduce_cols_local(int ncols, int nchunks, const double2* __restrict__ partial, double2* __restrict__ h) {
+  const int c = blockIdx.x, lane = threadIdx.x;
+  double2 acc = zmake(0.0, 0.0);
+  for (int b = lane; b < nchunks; b += 32) acc = zadd(acc, partial[(size_t)c * nchunks + b]);
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, s);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, s);
+  }
+  if (lane == 0) h[c] = acc;
+}
+__global__ void kb_accum_cols(int ncols, const double2* __restrict__ h, double2* __restrict__ hsum, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < ncols) hsum[c] = accumulate ? zadd(hsum[c], h[c]) : h[c];
+}
+__global__ void kb_sumsq_local(int nparts, const double* __restrict__ normpart, double* __restrict__ out) {
+  const int lane = threadIdx.x;
+  double acc = 0.0;
+  for (int b = lane; b < nparts; b += 32) acc += normpart[b];
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) out[0] = acc;
+}
+__global__ void kb_sqrt1(double* __restrict__ v) { v[0] = sqrt(v[0]); }
+
 void kbi_shard_rows(const kb_context* h, int64_t* row_lo, int64_t* row_hi) {
   *row_lo = h->nodeptr[h->seg_lo[h->rank]];
   *row_hi = h->nodeptr[h->seg_hi[h->rank]];
+}
+
+// h[c] = sum over the ranks of (sum_b partial[c, b]);  hsum (+)= h.  One CTA: the local reduction,
+// the exchange through the mailboxes and the sum in rank order (bit-identical on every rank).
+__global__ void __launch_bounds__(256) kb_reduce_cols_mb(KbMailbox m, unsigned epoch, int ncols, int nchunks,
+                                                         const double2* __restrict__ partial, double2* __restrict__ h,
+                                                         double2* __restrict__ hsum, int accumulate, int* err,
+                                                         unsigned long long wait_ns) {
+  __shared__ double2 loc[128];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int c = wid; c < ncols; c += 8) {
+    double2 acc = zmake(0.0, 0.0);
+    for (int b = lane; b < nchunks; b += 32) acc = zadd(acc, partial[(size_t)c * nchunks + b]);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, s);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, s);
+    }
+    if (lane == 0) loc[c] = acc;
+  }
+  __syncthreads();
+  const int par = (int)(epoch & 1u);
+  for (int r = 0; r < m.nranks; ++r) {
+    double2* dst = kb_mb_data(m, r, par, m.rank);
+    for (int c = threadIdx.x; c < ncols; c += blockDim.x) dst[c] = loc[c];
+  }
+  kb_mb_signal_all(m, epoch);
+  kb_mb_wait_all(m, epoch, err, wait_ns);
+  for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
+    double2 sum = zmake(0.0, 0.0);
+    for (int r = 0; r < m.nranks; ++r) sum = zadd(sum, __ldcg(kb_mb_data(m, m.rank, par, r) + c));
+    h[c] = sum;
+    hsum[c] = accumulate ? zadd(hsum[c], sum) : sum;
+  }
+}
+
+// beta = sqrt(sum over the ranks of sum_b normpart[b])
+__global__ void __launch_bounds__(32) kb_norm_mb(KbMailbox m, unsigned epoch, int nparts,
+                                                 const double* __restrict__ normpart, double* __restrict__ beta, int* err,
+                                                 unsigned long long wait_ns) {
+  const int lane = threadIdx.x;
+  double acc = 0.0;
+  for (int b = lane; b < nparts; b += 32) acc += normpart[b];
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  const int par = (int)(epoch & 1u);
+  if (lane < m.nranks) kb_mb_data(m, lane, par, m.rank)[0] = zmake(acc, 0.0);
+  kb_mb_signal_all(m, epoch);
+  kb_mb_wait_all(m, epoch, err, wait_ns);
+  if (lane == 0) {
+    double t = 0.0;
+    for (int r = 0; r < m.nranks; ++r) t += __ldcg(kb_mb_data(m, m.rank, par, r)).x;
+    beta[0] = sqrt(t);
+  }
+}
+
+// halo of a row-sharded vector: first node to the rank above, last node to the rank below; every
+// rank signals every rank (the lock-step invariant of the two-parity mailboxes)
+__global__ void __launch_bounds__(256) kb_halo_mb(KbMailbox m, unsigned epoch, double2* __restrict__ x, int o_first,
+                                                  int b_first, int o_last, int b_last, int o_above, int b_above,
+                                                  int o_below, int b_below, int* err, unsigned long long wait_ns) {
+  const int par = (int)(epoch & 1u);
+  if (m.rank > 0) {
+    double2* dst = kb_mb_data(m, m.rank - 1, par, m.rank);
+    for (int i = threadIdx.x; i < b_first; i += blockDim.x) dst[i] = x[o_first + i];
+  }
+  if (m.rank < m.nranks - 1) {
+    double2* dst = kb_mb_data(m, m.rank + 1, par, m.rank);
+    for (int i = threadIdx.x; i < b_last; i += blockDim.x) dst[i] = x[o_last + i];
+  }
+  kb_mb_signal_all(m, epoch);
+  kb_mb_wait_all(m, epoch, err, wait_ns);
+  if (m.rank > 0) {
+    const double2* src = kb_mb_data(m, m.rank, par, m.rank - 1);
+    for (int i = threadIdx.x; i < b_above; i += blockDim.x) x[o_above + i] = __ldcg(src + i);
+  }
+  if (m.rank < m.nranks - 1) {
+    const double2* src = kb_mb_data(m, m.rank, par, m.rank + 1);
+    for (int i = threadIdx.x; i < b_below; i += blockDim.x) x[o_below + i] = __ldcg(src + i);
+  }
+}
+
+int kbi_shard_reduce_cols(kb_context* h, int ncols, int nchunks, const double2* hpart, double2* hdev, double2* hsum,
+                          double2* scratch, int accumulate) {
+  cudaStream_t s = h->stream;
+  if (h->mb_ready && ncols <= 128) {
+    kb_reduce_cols_mb<<<1, 256, 0, s>>>(mailbox_of(h), ++h->mb_epoch, ncols, nchunks, hpart, hdev, hsum, accumulate,
+                                        h->d_sweep_err.p, h->wait_ns);
+    h->launches++;
+    KB_LAUNCH_CHECK(h);
+    return KB_OK;
+  }
+  kb_reduce_cols_local<<<ncols, 32, 0, s>>>(ncols, nchunks, hpart, hdev);
+  KB_NCCL(h, g_nccl.AllReduce(hdev, hdev, (size_t)2 * ncols, ncclDouble, ncclSum, (ncclComm_t)h->nccl_comm, s));
+  kb_accum_cols<<<1, 128, 0, s>>>(ncols, hdev, hsum, accumulate);
+  (void)scratch;
+  h->launches += 2;
+  KB_LAUNCH_CHECK(h);
+  return KB_OK;
+}
+
+int kbi_shard_norm(kb_context* h, int nparts, const double* normpart, double* beta_dev) {
+  cudaStream_t s = h->stream;
+  if (h->mb_ready) {
+    kb_norm_mb<<<1, 32, 0, s>>>(mailbox_of(h), ++h->mb_epoch, nparts, normpart, beta_dev, h->d_sweep_err.p, h->wait_ns);
+    h->launches++;
+    KB_LAUNCH_CHECK(h);
+    return KB_OK;
+  }
+  kb_sumsq_local<<<1, 32, 0, s>>>(nparts, normpart, beta_dev);
+  KB_NCCL(h, g_nccl.AllReduce(beta_dev, beta_dev, 1, ncclDouble, ncclSum, (ncclComm_t)h->nccl_comm, s));
+  kb_sqrt1<<<1, 1, 0, s>>>(beta_dev);
+  h->launches += 2;
+  KB_LAUNCH_CHECK(h);
+  return KB_OK;
 }
 
 // in-place sum over the ranks of `count` doubles
@@ -1335,6 +1581,15 @@ int kbi_shard_allreduce(kb_context* h, double* buf, size_t count) {
 int kbi_shard_halo(kb_context* h, double2* x) {
   const int g = h->rank, G = h->nranks;
   const int64_t lo = h->seg_lo[g], hi = h->seg_hi[g];
+  if (h->mb_ready && (size_t)h->bmax * sizeof(double2) <= KB_MB_SLOT) {
+    kb_halo_mb<<<1, 256, 0, h->stream>>>(mailbox_of(h), ++h->mb_epoch, x, noff(h, lo), nsize(h, lo), noff(h, hi - 1),
+                                         nsize(h, hi - 1), g > 0 ? noff(h, lo - 1) : 0, g > 0 ? nsize(h, lo - 1) : 0,
+                                         g < G - 1 ? noff(h, hi) : 0, g < G - 1 ? nsize(h, hi) : 0, h->d_sweep_err.p,
+                                         h->wait_ns);
+    h->launches++;
+    KB_LAUNCH_CHECK(h);
+    return KB_OK;
+  }
   KB_NCCL(h, g_nccl.GroupStart());
   if (g > 0) {
     KB_NCCL(h, g_nccl.Send(x + noff(h, lo), (size_t)nsize(h, lo) * 2, ncclDouble, g - 1, (ncclComm_t)h->nccl_comm,
