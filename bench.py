@@ -176,6 +176,12 @@ def cpu_full(P, b, nev, ncv, tol, napply_sample=None, sigma=1j):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import kore_oracle as ko
     from kore_b200 import synthetic
+    # all host threads, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1 for N > 1)
+    try:
+        from threadpoolctl import threadpool_limits
+        _limits = threadpool_limits(limits=os.cpu_count())  # stays in force for the rest of the process
+    except Exception:
+        _limits = None
     A, B, perm, nodeptr = synthetic.synthetic_pencil(P, b)
     n = A.shape[0]
     v0 = synthetic.start_vector(n, 1)
