@@ -192,6 +192,10 @@ int kb_dbg_sweep_timing(kb_handle h, long long* out, int max_ctas);
 /* C = alpha op(A) B + beta C on host arrays through the batched complex128 product kernel of the
  * l-sharded path (row-major; transA: A is k x m); `batch` identical problems per launch, `reps`
  * timed launches, mean ms per launch in *ms (tools/dev_zgemm.py). */
+/* The elimination rank `rank` of `nranks` would do on this pencil, on this one GPU without a communicator,
+ * and the four blocks (4 x bmax x bmax complex128) it would contribute to the reduced separator system;
+ * path 2: strip factorisation + folded couplings + DMMA product chains, 1: per-node kernels. */
+int kb_dbg_shard_segment(kb_handle h, int rank, int nranks, const double* sigma, int path, double* blocks);
 int kb_dbg_zgemm(kb_handle h, int m, int n, int k, int transA, const double* A, const double* B, double* C,
                  double alpha, double beta, int batch, int reps, double* ms);
 

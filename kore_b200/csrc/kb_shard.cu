@@ -717,6 +717,7 @@ struct PhaseTimer {
 
 static int reduced_factor(kb_context* h, double* flops);
 static int factor_sharded_fast(kb_context* h, double* flops, int64_t* bytes);
+static int factor_sharded_general(kb_context* h, double* flops, int64_t* bytes);
 
 // The fast path needs the strip kernel and the folded sweep on this rank's interior
 static bool shard_fast_supported(kb_context* h) {
@@ -731,78 +732,42 @@ static bool shard_fast_supported(kb_context* h) {
   return ok;
 }
 
-int kbi_factor_sharded(kb_context* h, zcomplex sigma) {
-  if (!h->chain_set) return kb_fail(h, KB_EINVAL, "kb_set_chain must be called before kb_factor");
-  if (!h->nccl_comm) return kb_fail(h, KB_EINVAL, "kb_set_sharding must be called before kb_factor");
-  KB_CUDA(h, cudaSetDevice(h->device));
+// Everything of an l-sharded factorisation that precedes the elimination and needs no communication:
+// T = A - sigma B, workspaces, storage of the interior inverses, node tables / ELL couplings / sweep
+// grid on the device, this rank's (zeroed) contribution blocks.
+static int shard_prepare(kb_context* h, zcomplex sigma) {
   KB_TRY(shard_ranges(h));
   cudaStream_t s = h->stream;
   const int64_t P = h->P, bmax = h->bmax;
-  const int G = h->nranks, g = h->rank;
   h->factored = false;
   h->fold_ready = false;
   h->M_transposed = false;
   h->shard_fast = false;
   h->sigma = sigma;
   kbi_drop_graphs(h);
-
-  cudaEvent_t e0, e1;
-  KB_CUDA(h, cudaEventCreate(&e0));
-  KB_CUDA(h, cudaEventCreate(&e1));
-  KB_CUDA(h, cudaEventRecord(e0, s));
   KB_TRY(kbi_build_T(h, sigma));
   KB_TRY(kbi_factor_workspace(h));
-
-  {
-    // storage of the interior inverses; node tables, ELL couplings and the sweep grid on the device
-    h->Moff.assign(P + 1, 0);
-    int64_t mt = 0;
-    for (int64_t p = h->int_lo; p < h->int_hi; ++p) {
-      const int64_t b = h->nodeptr[p + 1] - h->nodeptr[p];
-      h->Moff[p] = mt;
-      mt += b * b;
-    }
-    if (h->d_M.alloc((size_t)mt) != cudaSuccess)
-      return kb_fail(h, KB_ENOMEM, "cannot allocate %.2f GB for this rank's chain factors", mt * 16.0 / 1e9);
-    KB_TRY(kbi_sweep_prepare(h));
-    KB_CUDA(h, h->d_contrib.alloc(4 * (size_t)bmax * bmax));
-    KB_CUDA(h, h->d_contrib_all.alloc(4 * (size_t)bmax * bmax * G));
-    KB_CUDA(h, cudaMemsetAsync(h->d_contrib.p, 0, 4 * (size_t)bmax * bmax * sizeof(double2), s));
+  h->Moff.assign(P + 1, 0);
+  int64_t mt = 0;
+  for (int64_t p = h->int_lo; p < h->int_hi; ++p) {
+    const int64_t b = h->nodeptr[p + 1] - h->nodeptr[p];
+    h->Moff[p] = mt;
+    mt += b * b;
   }
-  if (shard_fast_supported(h)) {
-    double flops = 0.0;
-    int64_t bytes = 0;
-    KB_TRY(factor_sharded_fast(h, &flops, &bytes));
-    PhaseTimer pt(s);
-    KB_NCCL(h, g_nccl.AllGather(h->d_contrib.p, h->d_contrib_all.p, 4 * (size_t)bmax * bmax * 2, ncclDouble,
-                                (ncclComm_t)h->nccl_comm, s));
-    pt.mark("allgather");
-    KB_TRY(reduced_factor(h, &flops));
-    pt.mark("reduced-factor");
-    pt.report(g);
-    KB_CUDA(h, cudaEventRecord(e1, s));
-    KB_TRY(kbi_sync(h));
-    int info = 0, kerr = 0;
-    KB_CUDA(h, cudaMemcpy(&info, h->d_info.p, sizeof(int), cudaMemcpyDeviceToHost));
-    KB_CUDA(h, cudaMemcpy(&kerr, h->d_kfsync.p + KF_ERR_WORD, sizeof(int), cudaMemcpyDeviceToHost));
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    h->stats.factor_ms = ms;
-    h->stats.factor_flops = flops;
-    h->stats.factor_bytes = bytes;
-    if (kerr != 0)
-      return kb_fail(h, KB_ECUDA, "a device-side wait of the strip factorisation expired on rank %d (code %d, CTA %d)",
-                     g, kerr & 255, kerr >> 8);
-    if (info != 0) return kb_fail(h, KB_ESINGULAR, "zero or non-finite pivot in a Schur block on rank %d", g);
-    h->shard_fast = true;
-    h->stats.shard_path = 2;
-    h->factored = true;
-    return KB_OK;
-  }
-  h->stats.shard_path = 1;
+  if (h->d_M.alloc((size_t)mt) != cudaSuccess)
+    return kb_fail(h, KB_ENOMEM, "cannot allocate %.2f GB for this rank's chain factors", mt * 16.0 / 1e9);
+  KB_TRY(kbi_sweep_prepare(h));
+  KB_CUDA(h, h->d_contrib.alloc(4 * (size_t)bmax * bmax));
+  KB_CUDA(h, h->d_contrib_all.alloc(4 * (size_t)bmax * bmax * h->nranks));
+  KB_CUDA(h, cudaMemsetAsync(h->d_contrib.p, 0, 4 * (size_t)bmax * bmax * sizeof(double2), s));
+  return KB_OK;
+}
 
+// General path: per-node kernels, one-sided elimination of the interior with spike recurrences
+// towards the separator above (nodes of any size).
+static int factor_sharded_general(kb_context* h, double* flops_io, int64_t* bytes_io) {
+  cudaStream_t s = h->stream;
+  const int64_t P = h->P, bmax = h->bmax;
   const int64_t lo = h->int_lo, hi = h->int_hi;
   const bool has_top = h->top_sep >= 0, has_bot = h->bot_sep >= 0;
   const int bt = has_top ? nsize(h, h->top_sep) : 0, ot = has_top ? noff(h, h->top_sep) : 0;
@@ -826,10 +791,6 @@ int kbi_factor_sharded(kb_context* h, zcomplex sigma) {
   KB_CUDA(h, h->d_H.alloc((size_t)bmax * bmax));
   KB_CUDA(h, h->d_Acc.alloc((size_t)bmax * bmax));
   const size_t slot = (size_t)bmax * bmax;
-  KB_CUDA(h, h->d_contrib.alloc(4 * slot));
-  KB_CUDA(h, h->d_contrib_all.alloc(4 * slot * G));
-  KB_CUDA(h, cudaMemsetAsync(h->d_contrib.p, 0, 4 * slot * sizeof(double2), s));
-
   double flops = 0.0;
   for (int64_t p = lo; p < hi; ++p) {
     const int o = noff(h, p), b = nsize(h, p);
@@ -911,28 +872,89 @@ int kbi_factor_sharded(kb_context* h, zcomplex sigma) {
                                  cudaMemcpyDeviceToDevice, s));
     KB_LAUNCH_CHECK(h);
   }
-  KB_NCCL(h, g_nccl.AllGather(h->d_contrib.p, h->d_contrib_all.p, 4 * slot * 2, ncclDouble,
+  *flops_io += flops;
+  *bytes_io = (mtot + 2 * vtot) * 16;
+  return KB_OK;
+}
+
+int kbi_factor_sharded(kb_context* h, zcomplex sigma) {
+  if (!h->chain_set) return kb_fail(h, KB_EINVAL, "kb_set_chain must be called before kb_factor");
+  if (!h->nccl_comm) return kb_fail(h, KB_EINVAL, "kb_set_sharding must be called before kb_factor");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const int64_t bmax = h->bmax;
+  const int G = h->nranks, g = h->rank;
+  KbEventPair ev;
+  KB_CUDA(h, ev.create());
+  KB_CUDA(h, cudaEventRecord(ev.e0, s));
+  KB_TRY(shard_prepare(h, sigma));
+  const bool fast = shard_fast_supported(h);
+  double flops = 0.0;
+  int64_t bytes = 0;
+  if (fast)
+    KB_TRY(factor_sharded_fast(h, &flops, &bytes));
+  else
+    KB_TRY(factor_sharded_general(h, &flops, &bytes));
+  PhaseTimer pt(s);
+  KB_NCCL(h, g_nccl.AllGather(h->d_contrib.p, h->d_contrib_all.p, 4 * (size_t)bmax * bmax * 2, ncclDouble,
                               (ncclComm_t)h->nccl_comm, s));
-
+  pt.mark("allgather");
   KB_TRY(reduced_factor(h, &flops));
-
-  KB_CUDA(h, cudaEventRecord(e1, s));
-  int info = 0;
-  KB_CUDA(h, cudaMemcpyAsync(&info, h->d_info.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-  KB_CUDA(h, cudaStreamSynchronize(s));
-  float ms = 0.f;
-  cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  h->stats.factor_ms = ms;
+  pt.mark("reduced-factor");
+  pt.report(g);
+  KB_CUDA(h, cudaEventRecord(ev.e1, s));
+  KB_TRY(kbi_sync(h));
+  int info = 0, kerr = 0;
+  KB_CUDA(h, cudaMemcpy(&info, h->d_info.p, sizeof(int), cudaMemcpyDeviceToHost));
+  if (fast) KB_CUDA(h, cudaMemcpy(&kerr, h->d_kfsync.p + KF_ERR_WORD, sizeof(int), cudaMemcpyDeviceToHost));
+  h->stats.factor_ms = ev.ms();
   h->stats.factor_flops = flops;
-  h->stats.factor_bytes = (mtot + 2 * vtot + (int64_t)slot * (G - 1)) * 16;
-  if (info != 0)
-    return kb_fail(h, KB_ESINGULAR, "zero or non-finite pivot in a Schur block on rank %d", g);
+  h->stats.factor_bytes = bytes + (int64_t)bmax * bmax * (G - 1) * 16;
+  h->stats.shard_path = fast ? 2 : 1;
+  if (kerr != 0)
+    return kb_fail(h, KB_ECUDA, "a device-side wait of the strip factorisation expired on rank %d (code %d, CTA %d)",
+                   g, kerr & 255, kerr >> 8);
+  if (info != 0) return kb_fail(h, KB_ESINGULAR, "zero or non-finite pivot in a Schur block on rank %d", g);
+  h->shard_fast = fast;
   h->factored = true;
   return KB_OK;
 }
 
+// Test hook (tests/test_gpu_parity.py, one GPU, no communicator): the elimination rank `rank` of
+// `nranks` would do on this pencil and the four blocks it would contribute to the reduced system
+// (4 x bmax x bmax complex128, slots as in factor_sharded_fast), by the fast (path = 2) or the general
+// (path = 1) kernels.  The handle is left unfactored and unsharded.
+extern "C" int kb_dbg_shard_segment(kb_handle h, int rank, int nranks, const double* sigma, int path, double* blocks) {
+  if (!h || !sigma || !blocks || nranks < 2 || rank < 0 || rank >= nranks) return KB_EINVAL;
+  if (!h->chain_set) return kb_fail(h, KB_EINVAL, "kb_set_chain must be called first");
+  if (h->nccl_comm) return kb_fail(h, KB_EINVAL, "kb_dbg_shard_segment is for unsharded handles");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  const int rank0 = h->rank, nranks0 = h->nranks;
+  h->rank = rank;
+  h->nranks = nranks;
+  double flops = 0.0;
+  int64_t bytes = 0;
+  int rc = shard_prepare(h, zcomplex(sigma[0], sigma[1]));
+  if (rc == KB_OK) {
+    if (path == 2 && !shard_fast_supported(h))
+      rc = kb_fail(h, KB_EINVAL, "the fast l-sharded path does not support this pencil");
+    else
+      rc = path == 2 ? factor_sharded_fast(h, &flops, &bytes) : factor_sharded_general(h, &flops, &bytes);
+  }
+  if (rc == KB_OK) {
+    cudaError_t e = cudaMemcpyAsync(blocks, h->d_contrib.p, 4 * (size_t)h->bmax * h->bmax * sizeof(double2),
+                                    cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) rc = kb_fail(h, KB_ECUDA, "copy of the contribution blocks failed: %s", cudaGetErrorString(e));
+  }
+  h->rank = rank0;
+  h->nranks = nranks0;
+  h->factored = false;
+  h->fold_ready = false;
+  h->shard_fast = false;
+  h->M_transposed = false;
+  return rc;
+}
 
 // ---- reduced (separator) system, factored redundantly on every rank: node j = separator of rank j
 static int reduced_factor(kb_context* h, double* flops_io) {

@@ -31,7 +31,7 @@ EXPORTS = [
     "kb_create", "kb_destroy", "kb_last_error", "kb_set_option", "kb_set_pencil", "kb_set_chain",
     "kb_nccl_unique_id", "kb_set_sharding", "kb_factor", "kb_solve", "kb_apply_op", "kb_matvec",
     "kb_eigs", "kb_get_stats", "kb_solve_dev", "kb_stream", "kb_savetxt",
-    "kb_dbg_schur", "kb_dbg_factor_timing", "kb_dbg_sweep_timing",
+    "kb_dbg_schur", "kb_dbg_factor_timing", "kb_dbg_sweep_timing", "kb_dbg_zgemm", "kb_dbg_shard_segment",
 ]
 
 
@@ -208,6 +208,7 @@ class Solver:
         perm = np.ascontiguousarray(perm, dtype=np.int64)
         nodeptr = np.ascontiguousarray(nodeptr, dtype=np.int64)
         self._check(self.lib.kb_set_chain(self.h, _ptr(perm), _ptr(nodeptr), len(nodeptr) - 1))
+        self._nodeptr = nodeptr
 
     def set_sharding(self, rank, nranks, unique_id):
         self._check(self.lib.kb_set_sharding(self.h, int(rank), int(nranks), _ptr(unique_id)))
@@ -265,6 +266,18 @@ class Solver:
         info = dict(nconv=k, its=its.value, ncv=ncv, resid=resid[:k].copy())
         info.update(self.stats())
         return evals[:k].copy(), (np.array(evecs[:, :k], order="F") if want_vectors else None), info
+
+    def dbg_shard_segment(self, rank, nranks, sigma, path="fast"):
+        """Test hook: the four blocks rank `rank` of `nranks` would contribute to the reduced
+        (separator) system of the l-sharded factorisation, computed on this one GPU without a
+        communicator (kb_dbg_shard_segment).  Returns an array (4, bmax * bmax) complex128."""
+        bmax = int(np.diff(self._nodeptr).max())
+        out = np.zeros((4, bmax * bmax), dtype=np.complex128)
+        sg = np.array([complex(sigma)], dtype=np.complex128)
+        f = self.lib.kb_dbg_shard_segment
+        f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        self._check(f(self.h, int(rank), int(nranks), _ptr(sg), 2 if path == "fast" else 1, _ptr(out)))
+        return out
 
     def stats(self):
         st = KbStats()

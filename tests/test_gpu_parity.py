@@ -392,3 +392,63 @@ def test_wide_nodes(lib, b):
         s.factor(1j)
         x2 = s.solve(r)
         assert np.linalg.norm(x - x2) <= 1e-10 * np.linalg.norm(x2)
+
+
+@pytest.mark.parametrize("name,rank,path", [("spinover", 1, "fast"), ("dormy", 1, "fast"), ("dormy", 0, "fast"),
+                                            ("dormy", 2, "fast"), ("magnetic_small", 1, "general")])
+def test_lsharded_segment_blocks_against_the_model(lib, name, rank, path):
+    """One GPU, no communicator: the elimination one rank of three does on its segment of the chain
+    -- strip factorisation and folded couplings on a node RANGE, identity-column product chains on
+    the FP64 tensor cores, coupling products -- must give the reduced-system blocks of the NumPy
+    statement of the l-sharded algebra (tests/shard_model.py).  The multi-rank runs themselves are
+    tests/test_gpu_sharded.py (two GPUs)."""
+    import shard_model as sm
+    from kore_b200 import chain
+    c = load_case(name)
+    P = len(c.nodeptr) - 1
+    nb = np.diff(c.nodeptr)
+    with lib.Solver(0) as s:
+        s.set_option(lib.OPT_EQUILIBRATE, 0)  # the model works on T itself
+        s.set_pencil(c.A, c.B)
+        s.set_chain(c.perm, c.nodeptr)
+        blocks = s.dbg_shard_segment(rank, 3, c.tau, path)
+        # the handle is usable afterwards: unsharded factor + solve
+        s.factor(c.tau)
+        x = s.solve(c.oracle["solve_rhs"])
+        assert np.linalg.norm(x - c.oracle["solve_x"]) <= 1e-9 * np.linalg.norm(c.oracle["solve_x"])
+    T = (c.A - c.tau * c.B).tocsr()
+    Tp = T[c.perm][:, c.perm].tocsr()
+    ranges = chain.split_ranges(P, 3)
+    seg = sm.FastSegment(Tp, c.nodeptr, ranges, rank)
+    bt = int(nb[seg.top]) if seg.top is not None else 0
+    bb = int(nb[seg.bot]) if seg.bot is not None else 0
+    want = {0: (seg.R_above, bb, bb), 1: (seg.acc, bt, bt), 2: (seg.C_sub, bb, bt), 3: (seg.C_sup, bt, bb)}
+    checked = 0
+    for k, (ref, rows, cols) in want.items():
+        if ref is None:
+            continue
+        got = blocks[k][:rows * cols].reshape(rows, cols)
+        assert np.linalg.norm(got - ref) <= 1e-8 * np.linalg.norm(ref), (k, np.linalg.norm(got - ref) / np.linalg.norm(ref))
+        checked += 1
+    assert checked == (4 if rank == 1 else 1)
+
+
+@pytest.mark.parametrize("shape", [(600, 600, 600, 0), (148, 74, 148, 1), (37, 5, 91, 0), (74, 148, 74, 1)])
+def test_batched_complex_product_kernel(lib, shape):
+    """kb_zgemm_batch (DMMA): C = alpha op(A) B + beta C against numpy, odd sizes and both layouts of A."""
+    import ctypes as C
+    m, n, k, tr = shape
+    rng = np.random.default_rng(m + n + k)
+    A = np.ascontiguousarray(rng.standard_normal((k, m) if tr else (m, k)) + 1j * rng.standard_normal((k, m) if tr else (m, k)))
+    B = np.ascontiguousarray(rng.standard_normal((k, n)) + 1j * rng.standard_normal((k, n)))
+    C0 = rng.standard_normal((m, n)) + 1j * rng.standard_normal((m, n))
+    with lib.Solver(0) as s:
+        f = s.lib.kb_dbg_zgemm
+        f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                      C.c_double, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        for batch in (1, 4):
+            Cc = np.ascontiguousarray(C0.copy())
+            ms = C.c_double(0.0)
+            assert f(s.h, m, n, k, tr, A.ctypes.data, B.ctypes.data, Cc.ctypes.data, -1.0, 0.5, batch, 0, C.byref(ms)) == 0
+            ref = -1.0 * ((A.T if tr else A) @ B) + 0.5 * C0
+            assert np.abs(Cc - ref).max() <= 1e-13 * np.abs(ref).max()
