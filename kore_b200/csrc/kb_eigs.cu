@@ -328,6 +328,9 @@ int normalize_dev(kb_context* h, int n, double2* v, double* normpart, double* be
 // SLEPc's default basis size max(2 nev, nev + 15) stays within KB_MAX_NCV for nev <= 63
 // (the coefficient vectors of kb_multiaxpy / kb_lincomb live in 128-entry shared arrays).
 #define KB_MAX_NCV 127
+// repeated purification of the extracted eigenvectors (see the extraction loop)
+#define KB_PURIFY_TARGET 1e-11
+#define KB_PURIFY_EXTRA 3
 
 static int eigs_impl(kb_handle h, int nev, int ncv, double tol, int maxit, int which,
                      const double* target, int true_residual, const double* v0, int max_pairs,
@@ -626,36 +629,51 @@ static int eigs_impl(kb_handle h, int nev, int ncv, double tol, int maxit, int w
     kb_lincomb<<<nblk(K.nl, 256), 256, 0, s>>>(K.nl, i + 1, K.V + K.r0, K.ldv, K.hdev, x + K.r0);
     h->launches++;
     KB_CUDA(h, cudaStreamSynchronize(s));
-    if (h->opt_purify) {
-      KB_TRY(kbi_apply_op_chain(h, x, K.w, h->opt_refine_eigs));
-      h->stats.op_applies++;
-      KB_CUDA(h, cudaMemcpyAsync(x, K.w, (size_t)n * sizeof(double2), cudaMemcpyDeviceToDevice, s));
-    }
-    // the vector leaves the sharded world here: every rank holds all of it from now on
-    if (K.sharded) KB_TRY(kbi_shard_gather_segments(h, x));
-    KB_TRY(normalize_dev(h, n, x, K.normpart, K.beta_dev, std::min((int)nblk(n, 256), 512)));
     Z theta = Tm(i, i);
     Z lam = sigma + 1.0 / theta;
     evals[2 * i] = lam.real();
     evals[2 * i + 1] = lam.imag();
-    // residual ||A x - lam B x|| / (|lam| ||B x||)
-    KB_TRY(kbi_spmv_A_chain(h, x, ax));
-    KB_TRY(kbi_spmv_B_chain(h, x, bx, false));
-    kb_resid_partial<<<rb, 256, 0, s>>>(n, ax, bx, x, zmake(lam.real(), lam.imag()), K.normpart);
-    h->launches++;
-    KB_CUDA(h, cudaMemcpyAsync(rpart.data(), K.normpart, 3 * rb * sizeof(double), cudaMemcpyDeviceToHost, s));
+    // Purification x <- OP x (SLEPc's EPSSetPurify) is one step of inverse iteration with the
+    // factorisation at hand.  On pencils whose sections differ by many orders of magnitude (thermal
+    // runs: |Bx| ~ 1e-11 |x|) one step leaves ||Ax - lam Bx|| / (|lam| ||Bx||) at 1e-9, the next one at
+    // 1e-11 .. 1e-12 (measured on the reference-assembled dormy case at N = 150, oracle and GPU
+    // alike), so the step is repeated -- with one refinement step of the linear solve -- while the
+    // residual is above KB_PURIFY_TARGET and still falling, at most KB_PURIFY_EXTRA more times.
+    // Well-scaled pencils (the benchmark's: 1e-14 after the first step) pay nothing.
+    double rnorm = 0.0, prev = 1e300;
+    for (int round = 0;; ++round) {
+      if (h->opt_purify) {
+        const int refine = (round > 0 && !K.sharded) ? 1 : h->opt_refine_eigs;
+        KB_TRY(kbi_apply_op_chain(h, x, K.w, refine));
+        h->stats.op_applies++;
+        KB_CUDA(h, cudaMemcpyAsync(x, K.w, (size_t)n * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+      }
+      // the vector leaves the sharded world here: every rank holds all of it from now on
+      if (K.sharded) KB_TRY(kbi_shard_gather_segments(h, x));
+      KB_TRY(normalize_dev(h, n, x, K.normpart, K.beta_dev, std::min((int)nblk(n, 256), 512)));
+      // residual ||A x - lam B x|| / (|lam| ||B x||)
+      KB_TRY(kbi_spmv_A_chain(h, x, ax));
+      KB_TRY(kbi_spmv_B_chain(h, x, bx, false));
+      kb_resid_partial<<<rb, 256, 0, s>>>(n, ax, bx, x, zmake(lam.real(), lam.imag()), K.normpart);
+      h->launches++;
+      KB_CUDA(h, cudaMemcpyAsync(rpart.data(), K.normpart, 3 * rb * sizeof(double), cudaMemcpyDeviceToHost, s));
+      KB_CUDA(h, cudaStreamSynchronize(s));
+      double r0 = 0, r1 = 0;
+      for (int b = 0; b < rb; ++b) {
+        r0 += rpart[3 * b];
+        r1 += rpart[3 * b + 1];
+      }
+      rnorm = std::sqrt(r0) / (std::abs(lam) * std::sqrt(r1));
+      if (!h->opt_purify || !(rnorm > KB_PURIFY_TARGET) || round >= KB_PURIFY_EXTRA || rnorm > 0.5 * prev) break;
+      prev = rnorm;
+    }
     if (evecs) {
       KB_TRY(kbi_from_chain(h, x, d_xo.p));
       KB_CUDA(h, cudaMemcpyAsync(evecs + (size_t)2 * n * i, d_xo.p, (size_t)n * sizeof(double2),
                                  cudaMemcpyDeviceToHost, s));
+      KB_CUDA(h, cudaStreamSynchronize(s));
     }
-    KB_CUDA(h, cudaStreamSynchronize(s));
-    double r0 = 0, r1 = 0;
-    for (int b = 0; b < rb; ++b) {
-      r0 += rpart[3 * b];
-      r1 += rpart[3 * b + 1];
-    }
-    if (resid) resid[i] = std::sqrt(r0) / (std::abs(lam) * std::sqrt(r1));
+    if (resid) resid[i] = rnorm;
   }
   *nconv_out = nret;
   if (its_out) *its_out = its;

@@ -1,8 +1,7 @@
 """GPU parity: libkoreb200 (through the C ABI) vs the CPU oracle on the committed
 golden fixtures.  Tolerances are BASELINE.json's: eigenvalues to relative 1e-9,
-eigen-residuals ||Ax - lam Bx|| / (|lam| ||Bx||) <= 1e-10 wherever the oracle
-itself reaches that (the oracle's own residual is stored beside its eigenvalues
-and the bar is max(1e-10, 3 x oracle)), solutions to relative 1e-9."""
+eigen-residuals ||Ax - lam Bx|| / (|lam| ||Bx||) <= 1e-10 (flat: kb_eigs repeats the
+purification step on badly scaled pencils until it holds), solutions to relative 1e-9."""
 import json
 import os
 
@@ -72,7 +71,7 @@ def test_eigenpairs_match_oracle(lib, name):
     assert np.all(np.diff(key) >= -1e-12 * max(1.0, np.max(np.abs(key))))
     # residuals: recomputed on the host from the returned vectors
     res = ko.residuals(case.A, case.B, lam, X)
-    bar = np.maximum(1e-10, 3 * np.max(case.oracle["eig_resid"]))
+    bar = 1e-10  # BASELINE.json's bar, flat (round 1: max(1e-10, 3 x the oracle's own residual))
     assert np.all(res <= bar), (res, case.oracle["eig_resid"])
     # the device-side residual is the same quantity up to rounding in the norms
     assert np.all(info["resid"] <= bar)
@@ -452,3 +451,36 @@ def test_batched_complex_product_kernel(lib, shape):
             assert f(s.h, m, n, k, tr, A.ctypes.data, B.ctypes.data, Cc.ctypes.data, -1.0, 0.5, batch, 0, C.byref(ms)) == 0
             ref = -1.0 * ((A.T if tr else A) @ B) + 0.5 * C0
             assert np.abs(Cc - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
+def test_thermal_residual_at_scale(lib):
+    """The reference-assembled thermal case at N = 150 (n = 67 500; bigcases/dormy_big, made by
+    tools/make_case.py -- 53 MB, not committed; the oracle's eigenvalues are
+    tests/golden/dormy_big_eigs.json): eigenvalues to 1e-9 and the FLAT residual bar 1e-10.  One
+    purification step leaves the residual at 1e-9 on this pencil (|Bx| ~ 1e-11 |x|), oracle and GPU
+    alike; the repeated purification of kb_eigs brings it to 1e-11."""
+    d = os.path.join(ROOT, "bigcases", "dormy_big")
+    if not os.path.exists(os.path.join(d, "A.npz")):
+        d = os.path.join(ROOT, "bigcases_run", "dormy_big")  # (bigcases/ is not shipped to the GPU box)
+    if not os.path.exists(os.path.join(d, "A.npz")):
+        pytest.skip("bigcases/dormy_big not assembled (tools/make_case.py ... N=150 lmax=308)")
+    import kore_oracle as ko
+    from kore_b200 import chain
+    m = json.load(open(os.path.join(d, "meta.json")))
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "dormy_big_eigs.json")))
+    A = ko.load_csr(os.path.join(d, "A.npz"))
+    B = ko.load_csr(os.path.join(d, "B.npz"))
+    perm, nodeptr = chain.chain_from_params(m["N1"], m["m"], m["lmax"], m["symm"], m["symmB0"], m["hydro"],
+                                            m["magnetic"], m["thermal"], m["compositional"])
+    tau = complex(m["rtau"], m["itau"])
+    with lib.Solver(0) as s:
+        s.set_pencil(A, B)
+        s.set_chain(perm, nodeptr)
+        s.factor(tau)
+        lam, X, info = s.eigs(gold["nev"], m["which_eigenpairs"], target=tau, ncv=24, tol=1e-12, maxit=100)
+    assert info["nconv"] >= gold["nev"]
+    for re_, im_ in gold["eigs"]:
+        z = complex(re_, im_)
+        assert np.min(np.abs(lam - z)) <= 1e-9 * abs(z), z
+    res = ko.residuals(A, B, lam[:gold["nev"]], X[:, :gold["nev"]])
+    assert res.max() <= 1e-10, res
