@@ -180,6 +180,53 @@ int kb_stream(kb_handle h, void** cuda_stream);
 int kb_savetxt(const char* path, const double* data, int64_t rows, int64_t cols, int64_t row_stride,
                int64_t col_stride, int append, int nthreads);
 
+/* Device-side assembly: replaces the host loops of bin/assemble.py:432-1171
+ * (B: :432-590, A: :600-1171; block formulas bin/operators.py:22-195, 386-405, 699-775; boundary
+ * rows assemble.py:1188-1345) for hydrodynamic and Boussinesq thermal set-ups.  An assembly
+ * program describes every N1 x N1 block of a matrix whose rows and columns are `nblockrows`
+ * blocks of N1 radial coefficients in Kore's own (section-major) ordering:
+ *   - radial operators as bands: ops[(k*N1 + i)*(2H+1) + d] = R_k[i][i + d - H] (0 where absent);
+ *   - block row r has the blocks blk_ptr[r] .. blk_ptr[r+1]-1, block b in block column blk_col[b]
+ *     (ascending inside a block row); its first br_chop[r] rows are boundary rows: dense rows
+ *     bc[(br_bc[r] + q)*N1 + j] of the diagonal block, nothing elsewhere;
+ *   - block b is the sum of the groups blk_grp[b] .. blk_grp[b+1]-1; group g adds
+ *       grp_sign[g] * s_{k-1} * (... s_0 * ((c_0 x_0 + c_1 x_1) + c_2 x_2 ...))
+ *     to the real (grp_part[g] = 0) or imaginary (1) part, with the scalar factors
+ *     s_j = grp_sc[4*g + j], j < grp_nsc[g] <= 4, and the terms t = grp_term[g] .. grp_term[g+1]-1:
+ *     c = term_coef[t], x = the entry of operator term_op[t].  Every product and sum is one IEEE
+ *     double operation in exactly this order (no fused multiply-add): the sequence scipy.sparse
+ *     performs for the reference's expressions, so the result equals the reference's to the bit;
+ *   - when use_final is set every entry is finally multiplied by final_scale (1 / ||B||_F,
+ *     assemble.py:583-585, 1163-1164).
+ * Entries that evaluate to exactly zero are dropped (utils.py:164).  kb_assemble makes the result
+ * the handle's pencil, as kb_set_pencil does with host CSR arrays: A (complex128) and / or B
+ * (float64 when B->is_complex == 0) stay on the device in CSR with int32 indices; call
+ * kb_set_chain next.  Either program may be NULL: the pencil then consists of the other matrix
+ * alone (forced problems have no B; B alone is assembled first to get its norm).
+ * kb_get_assembled copies the CSR of A (which = 0) or B (1) to the host: *nnz always; indptr
+ * (n + 1 int64), indices (nnz int32) and values (nnz complex128 or float64) when not NULL. */
+typedef struct {
+  int32_t N1, nblockrows, H, is_complex;
+  int32_t nop, nbc, nblk, ngrp, nterm, use_final;
+  double final_scale;
+  const double* ops;
+  const double* bc;
+  const int32_t* br_chop;
+  const int32_t* br_bc;
+  const int32_t* blk_ptr;
+  const int32_t* blk_col;
+  const int32_t* blk_grp;
+  const int32_t* grp_part;
+  const int32_t* grp_sign;
+  const int32_t* grp_nsc;
+  const double* grp_sc;
+  const int32_t* grp_term;
+  const double* term_coef;
+  const int32_t* term_op;
+} kb_asm_program;
+int kb_assemble(kb_handle h, const kb_asm_program* A, const kb_asm_program* B);
+int kb_get_assembled(kb_handle h, int which, int64_t* nnz, int64_t* indptr, int32_t* indices, double* values);
+
 /* Debug / test hooks (not part of the drop-in surface).  kb_dbg_schur: the host-side complex
  * Schur form + ordering of the projected problem (what SLEPc's DS does with LAPACK), m x m
  * column-major complex128 in, T and Q out; which < 0: no ordering.  kb_dbg_*_timing: in-kernel

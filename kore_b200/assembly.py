@@ -1,0 +1,485 @@
+"""Device-side assembly of Kore's pencil.
+
+The reference builds ``A`` and ``B`` on the host (/root/reference/bin/assemble.py:432-1171):
+for every spherical-harmonic degree ``l`` and every pair of coupled sections it forms a sparse
+N1 x N1 block as a short linear combination of banded radial operators read from ``*.mtx``
+(written by bin/submatrices.py:533-590), appends dense boundary-condition rows, concatenates
+COO triplets, converts to CSR and divides by ``||B||_F``: tens of seconds of interpreted scipy
+per assembly (45 s at E = 1e-7), then ~250 MB from disk through the host to the solver.
+
+Here the host only writes down WHAT each block is -- an *assembly program*: a table of blocks,
+each a few groups of ``(coefficient, radial operator)`` terms with their scalar factors -- and
+the library evaluates it on the GPU straight into the CSR the layout build consumes
+(csrc/kb_assemble.cu, `kb_assemble`).  The program is a few hundred KB whatever the truncation;
+re-assembly at another Rayleigh number or forcing frequency is a new coefficient table and one
+kernel pass.
+
+Bit compatibility.  Every entry of the reference's matrices is the result of a fixed sequence
+of IEEE double operations (scipy.sparse scalar products and sums evaluated left to right,
+no fused multiply-add).  The program records that sequence, not just the mathematical
+coefficient: a group is ``s_k * (... s_1 * ((c_0 x_0 + c_1 x_1) + c_2 x_2 ...))`` and the
+evaluators (the kernel, and the NumPy model in tests/assembly_model.py) perform exactly these
+operations, so the assembled CSR equals the reference's bit for bit (tests/test_assembly.py).
+
+Scope: hydrodynamic (sections u, v) and Boussinesq thermal (section h) problems, viscous,
+with or without inner core, eigenvalue (forcing = 0) and forced (A only) runs -- BASELINE.json
+configs 1, 2, 3 and 5.  Magnetic, compositional, anelastic and inviscid set-ups raise
+NotImplementedError (their pencils still enter through `kb_set_pencil`).
+
+The physics restated here (which operators enter which block with which coefficient):
+momentum equation operators.py:22-195, buoyancy :386-405, heat equation :699-775; block
+placement assemble.py:432-760, 1012-1075; boundary rows assemble.py:1188-1345 with the
+Chebyshev end-point tables of bc_variables.py:8-32.
+"""
+from __future__ import annotations
+
+import glob
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .chain import section_degrees
+
+MAX_SCALES = 4
+
+
+@dataclass
+class PhysicsParams:
+    """The entries of Kore's ``parameters`` / ``utils`` modules the assembly depends on."""
+    hydro: int = 1
+    magnetic: int = 0
+    thermal: int = 0
+    compositional: int = 0
+    anelastic: int = 0
+    m: int = 1
+    lmax: int = 8
+    N: int = 8
+    symm: int = -1
+    ricb: float = 0.35
+    rcmb: float = 1.0
+    Ek: float = 1e-3
+    bci: int = 1
+    bco: int = 1
+    bci_thermal: int = 0
+    bco_thermal: int = 0
+    heating: str = "differential"
+    forcing: int = 0
+    forcing_frequency: float = 0.0
+    Gaspard: float = 1.0
+    ViscosD: float = 1e-3
+    Beyonce: float = 0.0
+    ThermaD: float = 0.0
+
+    @classmethod
+    def from_modules(cls, par, ut=None):
+        """From an imported Kore ``parameters`` module (and ``utils`` for rcmb)."""
+        kw = {}
+        for f in cls.__dataclass_fields__:
+            if hasattr(par, f):
+                kw[f] = getattr(par, f)
+        if ut is not None and hasattr(ut, "rcmb"):
+            kw["rcmb"] = ut.rcmb
+        return cls(**kw)
+
+    @classmethod
+    def from_dict(cls, d):
+        return cls(**{k: v for k, v in d.items() if k in cls.__dataclass_fields__})
+
+    # derived (utils.py:19-45)
+    @property
+    def wf(self):
+        return 0 if self.forcing == 0 else self.forcing_frequency
+
+    @property
+    def N1(self):
+        return self.N if self.ricb > 0 else self.N // 2
+
+    @property
+    def nb(self):
+        return (self.lmax - self.m + 1) // 2
+
+    @property
+    def sizmat(self):
+        return self.N1 * self.nb * (2 * self.hydro + 2 * self.magnetic + self.thermal + self.compositional)
+
+    def check_supported(self):
+        bad = []
+        if self.magnetic:
+            bad.append("magnetic = 1")
+        if self.compositional:
+            bad.append("compositional = 1")
+        if self.anelastic:
+            bad.append("anelastic = 1")
+        if self.Ek == 0:
+            bad.append("Ek = 0 (inviscid)")
+        if not self.hydro:
+            bad.append("hydro = 0")
+        if self.forcing not in (0, 7):
+            bad.append("forcing = %d (boundary rows of that mode)" % self.forcing)
+        if self.thermal and self.ThermaD <= 0:
+            bad.append("thermal = 1 with ThermaD <= 0")
+        if self.thermal and self.heating not in ("differential", "internal"):
+            bad.append("heating = %r" % (self.heating,))
+        if bad:
+            raise NotImplementedError("device-side assembly does not cover: " + ", ".join(bad)
+                                      + " -- assemble on the host and use kb_set_pencil")
+
+
+# ---------------------------------------------------------------------------
+# radial operators
+# ---------------------------------------------------------------------------
+def load_operators(directory="."):
+    """Every ``*.mtx`` of `directory` as CSR, keyed by its label (what operators.py:10-13 does
+    with globals)."""
+    import scipy.io as sio
+    import scipy.sparse as sp
+    ops = {}
+    for fn in sorted(glob.glob(os.path.join(directory, "*.mtx"))):
+        ops[os.path.basename(fn)[:-4]] = sp.csr_matrix(sio.mmread(fn))
+    if not ops:
+        raise FileNotFoundError("no *.mtx radial operators in %r (run submatrices.py first)" % directory)
+    return ops
+
+
+def save_operators_npz(path, ops):
+    store = {}
+    for k, M in ops.items():
+        M = M.tocsr()
+        store[k + "/data"], store[k + "/indices"], store[k + "/indptr"] = M.data, M.indices, M.indptr
+        store[k + "/shape"] = np.asarray(M.shape)
+    np.savez_compressed(path, **store)
+
+
+def load_operators_npz(path):
+    import scipy.sparse as sp
+    z = np.load(path)
+    labels = sorted({k.split("/")[0] for k in z.files})
+    return {k: sp.csr_matrix((z[k + "/data"], z[k + "/indices"], z[k + "/indptr"]), shape=tuple(z[k + "/shape"]))
+            for k in labels}
+
+
+def endpoint_table(x, N, pmax, ric, rcmb):
+    """``T[k, p]`` = p-th derivative with respect to r of the Chebyshev polynomial T_k at the end
+    point x = -1 (r = ric) or x = +1 (r = rcmb), k = 0..N, p = 0..pmax:
+    T_k^(p)(+-1) = (+-1)^(k+p) prod_{i<p} (k^2 - i^2) / (2 i + 1), times (2 / (rcmb - ric))^p for
+    the change of variable.  The products are accumulated in the order bc_variables.py:8-32 uses,
+    so that the boundary rows match the reference's to the bit."""
+    T = np.zeros((N + 1, pmax + 1))
+    for k in range(N + 1):
+        T[k, 0] = x ** k
+        acc = 1.0
+        for i in range(pmax):
+            acc = acc * (k ** 2 - i ** 2) / (2 * i + 1)
+            T[k, i + 1] = x ** (k + i + 1) * acc * (2 / (rcmb - ric)) ** (i + 1)
+    return T
+
+
+# ---------------------------------------------------------------------------
+# the program
+# ---------------------------------------------------------------------------
+@dataclass
+class Group:
+    """One summand of a block: ``sign * s_k(...s_1(sum_j c_j x_j))`` added to the real (part 0)
+    or imaginary (part 1) component."""
+    part: int
+    sign: int
+    scales: list
+    terms: list  # (coefficient, operator label)
+
+
+@dataclass
+class AsmProgram:
+    """Flat arrays of an assembly program (the argument of `kb_assemble`)."""
+    N1: int
+    nblockrows: int
+    H: int
+    is_complex: bool
+    op_labels: list
+    ops: np.ndarray        # float64 [nop, N1, 2H+1]: ops[k, i, d] = R_k[i, i + d - H]
+    bc: np.ndarray         # float64 [nbc, N1]: dense boundary rows
+    br_chop: np.ndarray    # int32 [nblockrows]: boundary rows at the top of every block of this block row
+    br_bc: np.ndarray      # int32 [nblockrows]: first row of `bc` of this block row's boundary rows
+    blk_ptr: np.ndarray    # int32 [nblockrows + 1]
+    blk_col: np.ndarray    # int32 [nblk]: block column, ascending inside a block row
+    blk_grp: np.ndarray    # int32 [nblk + 1]
+    grp_part: np.ndarray   # int32 [ngrp]
+    grp_sign: np.ndarray   # int32 [ngrp]
+    grp_nsc: np.ndarray    # int32 [ngrp]
+    grp_sc: np.ndarray     # float64 [ngrp, MAX_SCALES]
+    grp_term: np.ndarray   # int32 [ngrp + 1]
+    term_coef: np.ndarray  # float64 [nterm]
+    term_op: np.ndarray    # int32 [nterm]
+    final_scale: float = 1.0
+    use_final: bool = False
+    meta: dict = field(default_factory=dict)
+
+    @property
+    def n(self):
+        return self.N1 * self.nblockrows
+
+    def with_final_scale(self, s):
+        import copy
+        q = copy.copy(self)
+        q.final_scale, q.use_final = float(s), True
+        return q
+
+
+class _Builder:
+    def __init__(self, pp: PhysicsParams, operators: dict, is_complex: bool):
+        self.pp = pp
+        self.opsrc = operators
+        self.is_complex = is_complex
+        self.labels = []
+        self.blocks = {}  # (block row, block col) -> [Group]
+
+    def op_id(self, label):
+        if label not in self.opsrc:
+            raise KeyError("radial operator %s.mtx is missing" % label)
+        if label not in self.labels:
+            self.labels.append(label)
+        return self.labels.index(label)
+
+    def add(self, brow, bcol, group: Group):
+        if len(group.scales) > MAX_SCALES:
+            raise ValueError("more than %d scalar factors in one group" % MAX_SCALES)
+        self.blocks.setdefault((int(brow), int(bcol)), []).append(group)
+
+    def finish(self, nblockrows, br_chop, br_bc, bc_rows, meta):
+        N1 = self.pp.N1
+        H = 0
+        csr = []
+        for lab in self.labels:
+            M = self.opsrc[lab].tocoo()
+            if M.shape != (N1, N1):
+                raise ValueError("operator %s is %r, expected %r" % (lab, M.shape, (N1, N1)))
+            nz = M.data != 0
+            if nz.any():
+                H = max(H, int(np.abs(M.col[nz] - M.row[nz]).max()))
+            csr.append(M)
+        if 2 * H + 1 > 31:
+            raise ValueError("radial operators wider than +-15 are not supported (found +-%d)" % H)
+        W = 2 * H + 1
+        ops = np.zeros((max(1, len(self.labels)), N1, W))
+        for k, M in enumerate(csr):
+            ops[k, M.row, M.col - M.row + H] = M.data
+        keys = sorted(self.blocks)
+        blk_ptr = np.zeros(nblockrows + 1, dtype=np.int32)
+        for (r, _) in keys:
+            blk_ptr[r + 1] += 1
+        blk_ptr = np.cumsum(blk_ptr).astype(np.int32)
+        blk_col = np.array([c for (_, c) in keys], dtype=np.int32)
+        blk_grp, gp, gs, gn, gsc, gt, tc, to = [0], [], [], [], [], [0], [], []
+        for key in keys:
+            for g in self.blocks[key]:
+                gp.append(g.part)
+                gs.append(g.sign)
+                gn.append(len(g.scales))
+                gsc.append(list(map(float, g.scales)) + [1.0] * (MAX_SCALES - len(g.scales)))
+                for (c, lab) in g.terms:
+                    tc.append(float(c))
+                    to.append(self.op_id_existing(lab))
+                gt.append(len(tc))
+            blk_grp.append(len(gp))
+        return AsmProgram(
+            N1=N1, nblockrows=nblockrows, H=H, is_complex=self.is_complex, op_labels=list(self.labels), ops=ops,
+            bc=np.ascontiguousarray(bc_rows, dtype=np.float64).reshape(-1, N1),
+            br_chop=np.asarray(br_chop, dtype=np.int32), br_bc=np.asarray(br_bc, dtype=np.int32),
+            blk_ptr=blk_ptr, blk_col=blk_col, blk_grp=np.asarray(blk_grp, dtype=np.int32),
+            grp_part=np.asarray(gp, dtype=np.int32), grp_sign=np.asarray(gs, dtype=np.int32),
+            grp_nsc=np.asarray(gn, dtype=np.int32), grp_sc=np.asarray(gsc, dtype=np.float64).reshape(-1, MAX_SCALES),
+            grp_term=np.asarray(gt, dtype=np.int32), term_coef=np.asarray(tc, dtype=np.float64),
+            term_op=np.asarray(to, dtype=np.int32), meta=meta)
+
+    def op_id_existing(self, lab):
+        return self.labels.index(lab)
+
+
+def _lin(b, *terms):
+    """[(coefficient, label)] with the labels registered."""
+    out = []
+    for c, lab in terms:
+        b.op_id(lab)
+        out.append((c, lab))
+    return out
+
+
+def _sections(pp):
+    secs = section_degrees(pp.m, pp.lmax, pp.symm, -1, pp.hydro, 0, pp.thermal, 0)
+    return {name: (base * pp.nb, np.asarray(degs)) for (name, base, degs) in secs}
+
+
+def _block_of(sec, l):
+    base, degs = sec
+    k = np.nonzero(degs == l)[0]
+    return None if k.size == 0 else base + int(k[0])
+
+
+def _boundary_rows(pp):
+    """Dense boundary rows per section (assemble.py:1188-1345, non-anelastic: the log-density
+    terms vanish) and the number of them (= the rows submatrices.py:582-588 leaves empty)."""
+    ric = pp.ricb if pp.ricb > 0 else -pp.rcmb
+    Ta = endpoint_table(-1, pp.N - 1, 4, ric, pp.rcmb)
+    Tb = endpoint_table(1, pp.N - 1, 5, ric, pp.rcmb)
+    s = (pp.symm + 1) // 2
+    if pp.ricb > 0:
+        Tbu = Tbv = Tbh = Tb
+    else:
+        ixu, ixv = (pp.m + 1 - s) % 2, (pp.m + s) % 2
+        Tbu, Tbv, Tbh = Tb[ixu::2, :], Tb[ixv::2, :], Tb[ixu::2, :]
+    rows = {}
+    u = [Tbu[:, 0]]
+    u.append(pp.rcmb * Tbu[:, 2] - 0. * Tbu[:, 1] if pp.bco == 0 else Tbu[:, 1])
+    v = [-pp.rcmb * Tbv[:, 1] + (1 + pp.rcmb * 0.) * Tbv[:, 0] if pp.bco == 0 else Tbv[:, 0]]
+    h = [Tbh[:, 0] if pp.bco_thermal == 0 else Tbh[:, 1]]
+    if pp.ricb > 0:
+        u.append(Ta[:, 0])
+        u.append(pp.ricb * Ta[:, 2] - 0. * Ta[:, 1] if pp.bci == 0 else Ta[:, 1])
+        v.append(-pp.ricb * Ta[:, 1] + (1 + pp.ricb * 0.) * Ta[:, 0] if pp.bci == 0 else Ta[:, 0])
+        h.append(Ta[:, 0] if pp.bci_thermal == 0 else Ta[:, 1])
+    rows["u"], rows["v"], rows["h"] = np.array(u), np.array(v), np.array(h)
+    return rows
+
+
+def _coriolis_down(l, m):
+    # coupling of degree l to degree l - 1 (operators.py:72, 98)
+    return (l ** 2 - 1) * np.sqrt(l ** 2 - m ** 2) / (2 * l - 1.)
+
+
+def _coriolis_up(l, m):
+    # coupling of degree l to degree l + 1 (operators.py:83, 109)
+    return l * (l + 2.) * np.sqrt((l + m + 1.) * (l - m + 1)) / (2. * l + 3.)
+
+
+def build_program_A(pp: PhysicsParams, operators: dict) -> AsmProgram:
+    """Assembly program of ``A`` (before the division by ||B||_F)."""
+    pp.check_supported()
+    secs = _sections(pp)
+    b = _Builder(pp, operators, True)
+    m, wf = pp.m, pp.wf
+    RE, IM = 0, 1
+    G, V, Bf, Td = pp.Gaspard, pp.ViscosD, pp.Beyonce, pp.ThermaD
+
+    for l in secs["u"][1]:  # ---- poloidal momentum (2curl) rows
+        l = int(l)
+        L = l * (l + 1)
+        r = _block_of(secs["u"], l)
+        b.add(r, r, Group(IM, +1, [L, wf], _lin(b, (L, "r2_D0_u"), (-2, "r3_D1_u"), (-1, "r4_D2_u"))))
+        b.add(r, r, Group(IM, +1, [2 * m, G], _lin(b, (-L, "r2_D0_u"), (2, "r3_D1_u"), (1, "r4_D2_u"))))
+        b.add(r, r, Group(RE, -1, [L, V], _lin(b, (-L * (l + 2) * (l - 1), "r0_D0_u"), (2 * L, "r2_D2_u"),
+                                               (-4, "r3_D3_u"), (-1, "r4_D4_u"))))
+        c = _block_of(secs["v"], l - 1)
+        if c is not None:
+            b.add(r, c, Group(RE, +1, [2 * _coriolis_down(l, m), G], _lin(b, (l - 1, "r3_D0_u"), (-1, "r4_D1_u"))))
+        c = _block_of(secs["v"], l + 1)
+        if c is not None:
+            b.add(r, c, Group(RE, +1, [2 * _coriolis_up(l, m), G], _lin(b, (-(l + 2), "r3_D0_u"), (-1, "r4_D1_u"))))
+        if pp.thermal:
+            b.add(r, _block_of(secs["h"], l), Group(RE, +1, [L, Bf], _lin(b, (1, "r4_D0_u"))))
+
+    for l in secs["v"][1]:  # ---- toroidal momentum (1curl) rows
+        l = int(l)
+        L = l * (l + 1)
+        r = _block_of(secs["v"], l)
+        c = _block_of(secs["u"], l - 1)
+        if c is not None:
+            b.add(r, c, Group(RE, +1, [2 * _coriolis_down(l, m), G], _lin(b, (l - 1, "r1_D0_v"), (-1, "r2_D1_v"))))
+        c = _block_of(secs["u"], l + 1)
+        if c is not None:
+            b.add(r, c, Group(RE, +1, [2 * _coriolis_up(l, m), G], _lin(b, (-(l + 2), "r1_D0_v"), (-1, "r2_D1_v"))))
+        b.add(r, r, Group(IM, +1, [L, wf], _lin(b, (1, "r2_D0_v"))))
+        b.add(r, r, Group(IM, +1, [-2 * m, G], _lin(b, (1, "r2_D0_v"))))
+        b.add(r, r, Group(RE, -1, [L, V], _lin(b, (-L, "r0_D0_v"), (2, "r1_D1_v"), (1, "r2_D2_v"))))
+
+    if pp.thermal:  # ---- heat equation rows
+        gap = pp.rcmb - pp.ricb
+        diff = pp.heating == "differential"
+        for l in secs["h"][1]:
+            l = int(l)
+            L = l * (l + 1)
+            r = _block_of(secs["h"], l)
+            c = _block_of(secs["u"], l)
+            if diff:
+                b.add(r, c, Group(RE, +1, [pp.ricb, 1. / gap, L], _lin(b, (1, "r0_D0_h"))))
+                b.add(r, r, Group(RE, +1, [Td], _lin(b, (-L, "r1_D0_h"), (2, "r2_D1_h"), (1, "r3_D2_h"))))
+                b.add(r, r, Group(IM, -1, [wf], _lin(b, (1, "r3_D0_h"))))
+            else:
+                b.add(r, c, Group(RE, +1, [L], _lin(b, (1, "r2_D0_h"))))
+                b.add(r, r, Group(RE, +1, [Td], _lin(b, (-L, "r0_D0_h"), (2, "r1_D1_h"), (1, "r2_D2_h"))))
+                b.add(r, r, Group(IM, -1, [wf], _lin(b, (1, "r2_D0_h"))))
+
+    return _finish(b, pp, secs, with_bc=True)
+
+
+def build_program_B(pp: PhysicsParams, operators: dict) -> AsmProgram:
+    """Assembly program of ``B`` (real; before the division by its Frobenius norm)."""
+    pp.check_supported()
+    secs = _sections(pp)
+    b = _Builder(pp, operators, False)
+    for l in secs["u"][1]:
+        l = int(l)
+        L = l * (l + 1)
+        r = _block_of(secs["u"], l)
+        b.add(r, r, Group(0, -1, [L], _lin(b, (L, "r2_D0_u"), (-2, "r3_D1_u"), (-1, "r4_D2_u"))))
+    for l in secs["v"][1]:
+        l = int(l)
+        r = _block_of(secs["v"], l)
+        b.add(r, r, Group(0, -1, [l * (l + 1)], _lin(b, (1, "r2_D0_v"))))
+    if pp.thermal:
+        lab = "r3_D0_h" if pp.heating == "differential" else "r2_D0_h"
+        for l in secs["h"][1]:
+            r = _block_of(secs["h"], int(l))
+            b.add(r, r, Group(0, +1, [], _lin(b, (1, lab))))
+    return _finish(b, pp, secs, with_bc=False)
+
+
+def _finish(b, pp, secs, with_bc):
+    nbr = pp.sizmat // pp.N1
+    br_chop = np.zeros(nbr, dtype=np.int32)
+    br_bc = np.full(nbr, -1, dtype=np.int32)
+    bc_rows = np.zeros((0, pp.N1))
+    if with_bc:
+        rows = _boundary_rows(pp)
+        first = {}
+        stack = []
+        at = 0
+        for name in secs:
+            first[name] = at
+            stack.append(rows[name])
+            at += rows[name].shape[0]
+        bc_rows = np.vstack(stack)
+        for name, (base, degs) in secs.items():
+            br_chop[base:base + len(degs)] = rows[name].shape[0]
+            br_bc[base:base + len(degs)] = first[name]
+    meta = {"sections": {k: (int(v[0]), [int(x) for x in v[1]]) for k, v in secs.items()}}
+    return b.finish(nbr, br_chop, br_bc, bc_rows, meta)
+
+
+def frobenius_norm(values):
+    """||B||_F the way assemble.py:583 gets it (scipy.sparse.linalg.norm of the CSR = the
+    2-norm of its value array, numpy.linalg.norm -> BLAS dot): on the same values in the same
+    order this is the reference's number to the bit."""
+    return float(np.linalg.norm(np.asarray(values)))
+
+
+def assemble(solver, pp: PhysicsParams, operators: dict):
+    """Assemble the pencil of `pp` on the GPU of `solver` (a `kore_b200.lib.Solver`) and make
+    it the handle's pencil, as `set_pencil` would with the reference-assembled CSR.
+
+    Eigenvalue runs (forcing = 0): B is assembled un-normalised, its values come back once for
+    the Frobenius norm (assemble.py:583-585; host BLAS for bit compatibility), then A and B are
+    assembled with the factor 1 / ||B||_F.  Forced runs: A only, un-normalised
+    (assemble.py:1164).  Returns a dict with the programs and the norm."""
+    progA = build_program_A(pp, operators)
+    out = {"progA": progA, "bnorm": None}
+    if pp.forcing == 0:
+        progB = build_program_B(pp, operators)
+        solver.assemble(None, progB)
+        _, _, bvals = solver.get_assembled("B")
+        bnorm = frobenius_norm(bvals)
+        out["bnorm"] = bnorm
+        out["progB"] = progB
+        solver.assemble(progA.with_final_scale(1. / bnorm), progB.with_final_scale(1. / bnorm))
+    else:
+        solver.assemble(progA, None)
+    return out

@@ -2,6 +2,7 @@
 // files below, so they are compiled together instead of with -rdc).
 #include "kb_layout.cu"
 #include "kb_setup.cu"
+#include "kb_assemble.cu"
 #include "kb_chainfac.cu"
 #include "kb_factor.cu"
 #include "kb_sweep.cu"

@@ -100,6 +100,11 @@ class ChainLayout:
             perm, nodeptr = _chain.chain_from_pattern(A.indptr, A.indices, A.shape[0], N1)
         return cls(perm, nodeptr)
 
+    @classmethod
+    def from_params(cls, N1, m, lmax, symm, symmB0=-1, hydro=1, magnetic=0, thermal=0, compositional=0):
+        """The l-major chain from the parameter set alone (no matrix on the host: device-side assembly)."""
+        return cls(*_chain.chain_from_params(N1, m, lmax, symm, symmB0, hydro, magnetic, thermal, compositional))
+
 
 class EPS:
     """SLEPc.EPS stand-in (solve.py:91-149): GNHEP, Krylov-Schur, shift-and-invert."""
@@ -124,6 +129,13 @@ class EPS:
 
     def setOperators(self, A, B):       # E.setOperators(MA, MB)                solve.py:93
         self._A, self._B = A.tocsr(), B.tocsr()
+        self._asm = None
+
+    def setAssembly(self, params, operators):
+        """(new) instead of setOperators: the pencil is assembled on the GPU from the radial
+        operators (kore_b200.assembly; replaces the assemble.py run + A.npz / B.npz)."""
+        self._asm = (params, operators)
+        self._A = self._B = None
 
     def setChainLayout(self, layout):   # (new) replaces MUMPS' analysis phase
         self._layout = layout
@@ -172,7 +184,11 @@ class EPS:
         if self._layout is None:
             raise RuntimeError("setChainLayout must be called before solve()")
         s = self._solver
-        s.set_pencil(self._A, self._B)
+        if getattr(self, "_asm", None) is not None:
+            from . import assembly as _assembly
+            _assembly.assemble(s, *self._asm)
+        else:
+            s.set_pencil(self._A, self._B)
         s.set_chain(self._layout.perm, self._layout.nodeptr)
         s.factor(self.target)
         lam, X, info = s.eigs(self.nev, which=self.which, target=self.target, ncv=self.ncv, tol=self.tol,
@@ -228,6 +244,12 @@ class KSP:
 
     def setOperators(self, A):             # K.setOperators(MA)                  solve.py:222
         self._A = A.tocsr()
+        self._asm = None
+
+    def setAssembly(self, params, operators):
+        """(new) instead of setOperators: A is assembled on the GPU (kore_b200.assembly)."""
+        self._asm = (params, operators)
+        self._A = None
 
     def setChainLayout(self, layout):
         self._layout = layout
@@ -240,7 +262,11 @@ class KSP:
 
     def solve(self, b, x):                 # K.solve(bvec, x)                    solve.py:227
         s = self._solver
-        s.set_pencil(self._A, None)
+        if getattr(self, "_asm", None) is not None:
+            from . import assembly as _assembly
+            _assembly.assemble(s, *self._asm)
+        else:
+            s.set_pencil(self._A, None)
         s.set_chain(self._layout.perm, self._layout.nodeptr)
         s.factor(0.0)
         x[...] = s.solve(np.asarray(b, dtype=np.complex128))

@@ -30,7 +30,7 @@ WHICH = {"LM": 0, "SM": 1, "LR": 2, "SR": 3, "LI": 4, "SI": 5, "TM": 6, "TR": 7,
 EXPORTS = [
     "kb_create", "kb_destroy", "kb_last_error", "kb_set_option", "kb_set_pencil", "kb_set_chain",
     "kb_nccl_unique_id", "kb_set_sharding", "kb_factor", "kb_solve", "kb_apply_op", "kb_matvec",
-    "kb_eigs", "kb_get_stats", "kb_solve_dev", "kb_stream", "kb_savetxt",
+    "kb_eigs", "kb_get_stats", "kb_solve_dev", "kb_stream", "kb_savetxt", "kb_assemble", "kb_get_assembled",
     "kb_dbg_schur", "kb_dbg_factor_timing", "kb_dbg_sweep_timing", "kb_dbg_zgemm", "kb_dbg_shard_segment",
 ]
 
@@ -53,6 +53,38 @@ class KbStats(C.Structure):
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class KbAsmProgram(C.Structure):
+    """kb_asm_program of include/kore_b200.h."""
+    _fields_ = [
+        ("N1", C.c_int32), ("nblockrows", C.c_int32), ("H", C.c_int32), ("is_complex", C.c_int32),
+        ("nop", C.c_int32), ("nbc", C.c_int32), ("nblk", C.c_int32), ("ngrp", C.c_int32),
+        ("nterm", C.c_int32), ("use_final", C.c_int32), ("final_scale", C.c_double),
+        ("ops", C.c_void_p), ("bc", C.c_void_p), ("br_chop", C.c_void_p), ("br_bc", C.c_void_p),
+        ("blk_ptr", C.c_void_p), ("blk_col", C.c_void_p), ("blk_grp", C.c_void_p),
+        ("grp_part", C.c_void_p), ("grp_sign", C.c_void_p), ("grp_nsc", C.c_void_p),
+        ("grp_sc", C.c_void_p), ("grp_term", C.c_void_p), ("term_coef", C.c_void_p),
+        ("term_op", C.c_void_p),
+    ]
+
+
+def _asm_struct(prog):
+    """(KbAsmProgram, arrays kept alive) of a kore_b200.assembly.AsmProgram."""
+    f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)    # noqa: E731
+    keep = dict(ops=f64(prog.ops), bc=f64(prog.bc), br_chop=i32(prog.br_chop), br_bc=i32(prog.br_bc),
+                blk_ptr=i32(prog.blk_ptr), blk_col=i32(prog.blk_col), blk_grp=i32(prog.blk_grp),
+                grp_part=i32(prog.grp_part), grp_sign=i32(prog.grp_sign), grp_nsc=i32(prog.grp_nsc),
+                grp_sc=f64(prog.grp_sc), grp_term=i32(prog.grp_term), term_coef=f64(prog.term_coef),
+                term_op=i32(prog.term_op))
+    st = KbAsmProgram(N1=prog.N1, nblockrows=prog.nblockrows, H=prog.H, is_complex=int(prog.is_complex),
+                      nop=keep["ops"].shape[0], nbc=keep["bc"].shape[0], nblk=len(keep["blk_col"]),
+                      ngrp=len(keep["grp_part"]), nterm=len(keep["term_op"]), use_final=int(prog.use_final),
+                      final_scale=float(prog.final_scale))
+    for k, a in keep.items():
+        setattr(st, k, a.ctypes.data)
+    return st, keep
 
 
 def build(verbose=False):
@@ -100,6 +132,8 @@ def load():
     lib.kb_stream.argtypes = [vp, C.POINTER(vp)]
     lib.kb_savetxt.argtypes = [C.c_char_p, vp, i64, i64, i64, i64, C.c_int, C.c_int]
     lib.kb_dbg_schur.argtypes = [C.c_int, vp, C.c_int, vp, vp, vp, vp]
+    lib.kb_assemble.argtypes = [vp, C.POINTER(KbAsmProgram), C.POINTER(KbAsmProgram)]
+    lib.kb_get_assembled.argtypes = [vp, C.c_int, C.POINTER(i64), vp, vp, vp]
     for name in EXPORTS:
         if name != "kb_last_error":
             getattr(lib, name).restype = C.c_int
@@ -203,6 +237,33 @@ class Solver:
         self._check(self.lib.kb_set_pencil(self.h, n, np.dtype(idx_dtype).itemsize, _ptr(ap), _ptr(ai),
                                            _ptr(av), _ptr(bp), _ptr(bi), _ptr(bv), bcomplex))
         self.n = n
+
+    def assemble(self, progA, progB=None):
+        """Assemble the pencil on the GPU from assembly programs (kore_b200.assembly) instead of
+        ingesting host CSR arrays; either may be None.  Follow with `set_chain`."""
+        sa = sb = None
+        if progA is not None:
+            sa, keep_a = _asm_struct(progA)
+        if progB is not None:
+            sb, keep_b = _asm_struct(progB)
+        self._check(self.lib.kb_assemble(self.h, C.byref(sa) if sa is not None else None,
+                                         C.byref(sb) if sb is not None else None))
+        self.n = (progA if progA is not None else progB).n
+
+    def get_assembled(self, which="A"):
+        """(indptr int64, indices int32, values) of the A or B held on the device in raw CSR form
+        (assembled there by `assemble`, or uploaded by `set_pencil`)."""
+        w = 0 if which == "A" else 1
+        nnz = C.c_int64(0)
+        self._check(self.lib.kb_get_assembled(self.h, w, C.byref(nnz), None, None, None))
+        indptr = np.empty(self.n + 1, dtype=np.int64)
+        indices = np.empty(nnz.value, dtype=np.int32)
+        # values: complex128 for A; float64 or complex128 for B -- sized for the larger, trimmed below
+        raw = np.empty(2 * nnz.value, dtype=np.float64)
+        self._check(self.lib.kb_get_assembled(self.h, w, C.byref(nnz), _ptr(indptr), _ptr(indices), _ptr(raw)))
+        cplx = w == 0 or getattr(self, "_b_complex", False)
+        values = raw.view(np.complex128) if cplx else raw[:nnz.value].copy()
+        return indptr, indices, values
 
     def set_chain(self, perm, nodeptr):
         perm = np.ascontiguousarray(perm, dtype=np.int64)

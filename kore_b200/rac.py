@@ -103,6 +103,46 @@ class RayleighPencil:
         self.A.data[self.pos] += (float(Ra) - self.Ra_ref) * self.val
         return self.A
 
+    def install(self, solver, Ra):
+        """Make (A(Ra), B) the pencil of `solver`: host update + re-ingest of the CSR."""
+        solver.set_pencil(self.at(Ra), self.B)
+
+
+def buoyancy_factor(Ra_gap, Ek, ricb, Prandtl=1):
+    """``par.Beyonce`` of a parameters.py that sets the Rayleigh number through ``Ra_gap``
+    (tests/dormy2004/params.dormy04:177-186: Ra = Ra_gap / (1 - ricb)^3, BV2 = -Ra Ek^2 / Prandtl,
+    Beyonce = BV2), operation for operation, so that a trial of the search assembles the matrix the
+    reference's sed + assemble.py round trip would."""
+    Ra = Ra_gap / (1 - ricb) ** 3
+    return -Ra * Ek ** 2 / Prandtl
+
+
+class AssembledPencil:
+    """The pencil at any Rayleigh number, assembled ON THE GPU (kore_b200.assembly, kb_assemble):
+    a trial of the search costs a new buoyancy factor in the assembly program and one pass of the
+    assembly kernels; no matrix is built, updated or copied on the host (find_Rac.py:36-55 re-runs
+    assemble.py -- tens of seconds -- and writes / re-reads A.npz for every trial).
+
+    ``pp``: `assembly.PhysicsParams` of the run; ``operators``: the radial operators
+    (`assembly.load_operators`); ``factor_of``: Ra -> the buoyancy factor (`buoyancy_factor`).
+    B does not depend on Ra: its norm is computed at the first trial and reused."""
+
+    def __init__(self, pp, operators, factor_of):
+        from . import assembly as _asm
+        self._asm = _asm
+        self.pp, self.ops, self.factor_of = pp, operators, factor_of
+        self.progB = _asm.build_program_B(pp, operators)
+        self.bnorm = None
+
+    def install(self, solver, Ra):
+        a = self._asm
+        if self.bnorm is None:
+            solver.assemble(None, self.progB)
+            self.bnorm = a.frobenius_norm(solver.get_assembled("B")[2])
+            self.progB = self.progB.with_final_scale(1. / self.bnorm)
+        q = a.PhysicsParams.from_dict({**self.pp.__dict__, "Beyonce": self.factor_of(Ra)})
+        solver.assemble(a.build_program_A(q, self.ops).with_final_scale(1. / self.bnorm), self.progB)
+
 
 class GrowthRate:
     """Largest growth rate max Re(lambda) of the ``nev`` pairs selected by ``which`` around
@@ -133,7 +173,7 @@ class GrowthRate:
 
     def eigenvalues(self, Ra):
         s = self.solver
-        s.set_pencil(self.p.at(Ra), self.p.B)
+        self.p.install(s, Ra)
         s.set_chain(self.perm, self.nodeptr)
         s.factor(self.tau)
         lam, _, info = s.eigs(self.nev, which=self.which, target=self.tau, tol=self.tol,

@@ -15,6 +15,12 @@ Writes : eigenvalues0.dat, real_/imag_{flow,magnetic,temperature,composition}.fi
          timing.dat (appended), no_conv_solution (when nothing converged)   solve.py:194-199, 275-311
 The EPS / ST / KSP block (solve.py:91-123, 220-227) is replaced by libkoreb200 through the
 facades in kore_b200/eps.py; everything else keeps the reference's file formats.
+
+With `-kb_assemble` (or when there is no A.npz but the `*.mtx` radial operators of
+bin/submatrices.py are present) the run skips bin/assemble.py as well: the pencil is assembled on
+the GPU from the radial operators (kore_b200/assembly.py; hydrodynamic and Boussinesq thermal
+set-ups) -- the same matrices, bit for bit, without A.npz / B.npz ever being written or read.
+The forced right-hand side still comes from B_forced.npz.
 """
 from __future__ import annotations
 
@@ -97,18 +103,31 @@ def main(argv=None, device=0):
     opts = kb.Options(argv)
     N1, n, sizmat, symmB0 = kore_sizes(par)
 
-    A = load_csr("A.npz")
-    if A.shape[0] != sizmat:
-        raise SystemExit("A.npz is %d x %d but parameters.py implies sizmat = %d" % (A.shape + (sizmat,)))
-    layout = kb.ChainLayout.from_kore(A, N1, par.m, par.lmax, par.symm, symmB0, par.hydro, par.magnetic,
-                                      par.thermal, par.compositional)
+    import glob
+    on_device = opts.hasName("kb_assemble") or (not os.path.exists("A.npz") and bool(glob.glob("*.mtx")))
+    A = asm_inputs = None
+    if on_device:
+        from . import assembly as _assembly
+        pp = _assembly.PhysicsParams.from_modules(par)
+        pp.check_supported()
+        asm_inputs = (pp, _assembly.load_operators("."))
+        layout = kb.ChainLayout.from_params(N1, par.m, par.lmax, par.symm, symmB0, par.hydro, par.magnetic,
+                                            par.thermal, par.compositional)
+    else:
+        A = load_csr("A.npz")
+        if A.shape[0] != sizmat:
+            raise SystemExit("A.npz is %d x %d but parameters.py implies sizmat = %d" % (A.shape + (sizmat,)))
+        layout = kb.ChainLayout.from_kore(A, N1, par.m, par.lmax, par.symm, symmB0, par.hydro, par.magnetic,
+                                          par.thermal, par.compositional)
     success = 0
 
     if par.forcing == 0:  # ------------------------------------------------ eigenvalue problem
-        B = load_csr("B.npz")
         E = kb.EPS(device)
         E.create()
-        E.setOperators(A, B)
+        if on_device:
+            E.setAssembly(*asm_inputs)
+        else:
+            E.setOperators(A, load_csr("B.npz"))
         E.setChainLayout(layout)
         E.setProblemType(kb.EPS.ProblemType.GNHEP)
         E.setDimensions(par.nev)
@@ -143,7 +162,10 @@ def main(argv=None, device=0):
         x = np.zeros(sizmat, dtype=complex)
         K = kb.KSP(device)
         K.create()
-        K.setOperators(A)
+        if on_device:
+            K.setAssembly(*asm_inputs)
+        else:
+            K.setOperators(A)
         K.setChainLayout(layout)
         K.setTolerances(rtol=par.tol, max_it=par.maxit)
         K.setFromOptions(opts)

@@ -1,0 +1,73 @@
+#!/usr/bin/env python3
+"""Fixtures of the device-side assembly tests (tests/test_assembly.py).
+
+Needs /root/reference (build container only).  For every case the UNMODIFIED reference stages
+run through tools/make_case.py --asm; stored per case: the radial operators submatrices.py wrote
+(operators.npz), the physics parameters (asm_params.json) and, for the cases that are not
+already golden fixtures, the matrices assemble.py produced (A.npz, B.npz).  The existing cases
+(spinover, dormy, jones, forced_small, m0_small) keep the A.npz / B.npz make_golden.py stored:
+same reference run, same bits (checked below).
+"""
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
+sys.path.insert(0, HERE)
+from make_golden import CASES, recompress  # noqa: E402
+
+NEW_CASES = {
+    # stress-free boundaries on both spheres
+    "asm_stressfree": ("tests/spinover/params.spinover", ["bci=0", "bco=0", "N=40"]),
+    # thermal, stress-free, flux condition at the inner boundary
+    "asm_thermal_flux": ("tests/dormy2004/params.dormy04",
+                         ["bci=0", "bco=0", "bci_thermal=1", "N=40", "lmax=40"]),
+    # internal heating
+    "asm_internal": ("tests/dormy2004/params.dormy04", ["heating='internal'", "N=40", "lmax=40", "bco_thermal=1"]),
+}
+EXISTING = ["spinover", "dormy", "jones", "forced_small", "m0_small"]
+
+
+def same_npz(a, b):
+    za, zb = np.load(a), np.load(b)
+    return all(np.array_equal(za[k], zb[k]) for k in ("data", "indices", "indptr"))
+
+
+def main():
+    only = sys.argv[1:]
+    todo = {k: CASES[k] for k in EXISTING}
+    todo.update(NEW_CASES)
+    for name, (params, ov) in todo.items():
+        if only and name not in only:
+            continue
+        out = os.path.join(HERE, name)
+        tmp = "/tmp/asmfix_" + name
+        shutil.rmtree(tmp, ignore_errors=True)
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "make_case.py"),
+                               "--params", params, "--out", tmp, "--asm"] + ov)
+        os.makedirs(out, exist_ok=True)
+        for fn in ("operators.npz", "asm_params.json"):
+            shutil.copy(os.path.join(tmp, fn), os.path.join(out, fn))
+        for fn in ("A.npz", "B.npz"):
+            src = os.path.join(tmp, fn)
+            if not os.path.exists(src):
+                continue
+            if name in NEW_CASES:
+                recompress(src, os.path.join(out, fn))
+            else:
+                assert same_npz(src, os.path.join(out, fn)), (name, fn)
+        if name in NEW_CASES:
+            meta = json.load(open(os.path.join(tmp, "meta.json")))
+            meta["make_case_overrides"] = ov
+            meta["params_file"] = params
+            json.dump(meta, open(os.path.join(out, "meta.json"), "w"), indent=1, sort_keys=True)
+        print(name, "ok")
+
+
+if __name__ == "__main__":
+    main()

@@ -127,3 +127,45 @@ def test_gpu_search_reproduces_reference_row(lib, tmp_path):
         g(np.log10(m["Ra_gap"]))
         lam = list(g.cache.values())[0]
     assert abs(lam - lam_o) <= 1e-9 * abs(lam_o)
+
+
+def _dormy_assembly_inputs():
+    import json
+    import os
+    from conftest import GOLDEN
+    from kore_b200 import assembly as asm
+    d = os.path.join(GOLDEN, "dormy")
+    pp = asm.PhysicsParams.from_dict(json.load(open(os.path.join(d, "asm_params.json"))))
+    return pp, asm.load_operators_npz(os.path.join(d, "operators.npz"))
+
+
+def test_buoyancy_factor_is_the_parameter_files():
+    # params.dormy04:177-186 evaluated by the reference's own parameters.py (stored in asm_params.json)
+    from kore_b200 import rac
+    c = load_case("dormy")
+    pp, _ = _dormy_assembly_inputs()
+    assert rac.buoyancy_factor(c.meta["Ra_gap"], pp.Ek, pp.ricb, 1) == pp.Beyonce
+
+
+@pytest.mark.gpu
+def test_gpu_search_on_device_assembled_pencils(lib, tmp_path):
+    # the same search with every trial matrix assembled on the GPU (no A.npz, no host update)
+    from kore_b200 import rac
+    c = load_case("dormy")
+    m = c.meta
+    pp, ops = _dormy_assembly_inputs()
+    pen = rac.AssembledPencil(pp, ops, lambda Ra: rac.buoyancy_factor(Ra, pp.Ek, pp.ricb, 1))
+    with rac.GrowthRate(pen, c.perm, c.nodeptr, c.tau, m["nev"], m["which_eigenpairs"], tol=m["tol"],
+                        maxit=m["maxit"]) as g:
+        Ra_c, omega_c, sigma_c = rac.find_rac(g, RA_MIN)
+        assert 3 <= len(g.history) < 20
+        # at the reference's own Ra_gap the assembled matrix is the fixture's, bit for bit
+        pen.install(g.solver, m["Ra_gap"])
+        ip, ix, v = g.solver.get_assembled("A")
+    p = tmp_path / "critical_params.dat"
+    rac.write_critical_params(p, m["Ek"], m["ricb"], Ra_c, m["m"], omega_c)
+    assert p.read_text().strip() == GOLDEN_ROW
+    assert Ra_c == pytest.approx(m["Ra_gap"], rel=5e-6)
+    A = c.A.copy()
+    A.sort_indices()
+    assert np.array_equal(ip, A.indptr) and np.array_equal(ix, A.indices) and np.array_equal(v, A.data)

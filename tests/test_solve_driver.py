@@ -92,3 +92,70 @@ def test_forced_run_writes_single_column(tmp_path, monkeypatch, lib):
     xo = c.oracle["forced_x"]
     assert np.linalg.norm(x - xo) <= 1e-9 * np.linalg.norm(xo)
     assert not os.path.exists("eigenvalues0.dat")
+
+
+def write_operator_dir(tmp_path, name):
+    """A run directory as bin/submatrices.py leaves it: parameters.py and the *.mtx radial operators,
+    no A.npz / B.npz (those would come from bin/assemble.py)."""
+    import json
+    import scipy.io as sio
+    from kore_b200 import assembly as asm
+    c = load_case(name)
+    d = tmp_path / (name + "_ops")
+    (d / "bin").mkdir(parents=True)
+    pj = json.load(open(os.path.join(GOLDEN, name, "asm_params.json")))
+    m = c.meta
+    lines = ["%s = %r" % (k, v) for k, v in pj.items() if k != "rcmb"]
+    lines += ["%s = %r" % (k, m[k]) for k in ("nev", "maxit", "tol", "rtau", "itau")]
+    lines += ["which_eigenpairs = %r" % m["which_eigenpairs"], "B0 = %r" % m["B0"], "tau = rtau + itau*1j"]
+    (d / "bin" / "parameters.py").write_text("\n".join(lines) + "\n")
+    for lab, M in asm.load_operators_npz(os.path.join(GOLDEN, name, "operators.npz")).items():
+        sio.mmwrite(str(d / (lab + ".mtx")), M)
+    if os.path.exists(os.path.join(GOLDEN, name, "B_forced.npz")):
+        shutil.copy(os.path.join(GOLDEN, name, "B_forced.npz"), d / "B_forced.npz")
+    return c, d
+
+
+def test_operator_dir_round_trips_the_operators(tmp_path):
+    # MatrixMarket text keeps every digit: what the driver reads back is what the fixture holds
+    from kore_b200 import assembly as asm
+    c, d = write_operator_dir(tmp_path, "m0_small")
+    ops = asm.load_operators(str(d))
+    ref = asm.load_operators_npz(os.path.join(GOLDEN, "m0_small", "operators.npz"))
+    assert sorted(ops) == sorted(ref)
+    for k in ref:
+        assert (ops[k] != ref[k]).nnz == 0
+
+
+@pytest.mark.gpu
+def test_eigen_run_from_radial_operators_equals_run_from_matrices(tmp_path, monkeypatch, lib):
+    # device-side assembly produces the reference's matrices bit for bit, so the two runs write the
+    # same files byte for byte
+    import sys
+    from kore_b200 import solve as drv
+    c, d1 = write_run_dir(tmp_path, "spinover")
+    monkeypatch.chdir(d1)
+    sys.modules.pop("parameters", None)
+    assert drv.main(["-st_type", "sinvert"]) == 0
+    sys.modules.pop("parameters", None)
+    c, d2 = write_operator_dir(tmp_path, "spinover")
+    monkeypatch.chdir(d2)
+    assert not os.path.exists("A.npz")
+    assert drv.main(["-st_type", "sinvert"]) == 0
+    sys.modules.pop("parameters", None)
+    for fn in ("eigenvalues0.dat", "real_flow.field", "imag_flow.field"):
+        assert (d1 / fn).read_bytes() == (d2 / fn).read_bytes(), fn
+
+
+@pytest.mark.gpu
+def test_forced_run_from_radial_operators(tmp_path, monkeypatch, lib):
+    import sys
+    from kore_b200 import solve as drv
+    c, d = write_operator_dir(tmp_path, "forced_small")
+    monkeypatch.chdir(d)
+    sys.modules.pop("parameters", None)
+    assert drv.main(["-kb_assemble"]) == 0
+    sys.modules.pop("parameters", None)
+    x = np.loadtxt("real_flow.field") + 1j * np.loadtxt("imag_flow.field")
+    xo = c.oracle["forced_x"]
+    assert np.linalg.norm(x - xo) <= 1e-9 * np.linalg.norm(xo)

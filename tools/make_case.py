@@ -49,6 +49,9 @@ def main():
     ap.add_argument("--out", required=True)
     ap.add_argument("--ncpus", type=int, default=8)
     ap.add_argument("--keep", action="store_true")
+    ap.add_argument("--asm", action="store_true",
+                    help="also store the radial operators (operators.npz) and the physics parameters "
+                         "(asm_params.json) the device-side assembly needs (kore_b200/assembly.py)")
     ap.add_argument("overrides", nargs="*")
     a = ap.parse_args()
 
@@ -100,6 +103,19 @@ def main():
         json.dump(meta, f, indent=1, sort_keys=True)
     with open(os.path.join(a.out, "parameters.py"), "w") as f:
         f.write(ptxt)
+    if a.asm:
+        sys.path.insert(0, os.path.join(HERE, ".."))
+        from kore_b200 import assembly as asm
+        asm.save_operators_npz(os.path.join(a.out, "operators.npz"), asm.load_operators(work))
+        fields = list(asm.PhysicsParams.__dataclass_fields__)
+        probe = subprocess.check_output(
+            [sys.executable, "-c",
+             "import sys; sys.path.insert(0,'bin'); import parameters as p, utils as u, json;"
+             "d={k:getattr(p,k) for k in %r if hasattr(p,k)}; d['rcmb']=u.rcmb;"
+             "print(json.dumps({k:(v.item() if hasattr(v,'item') else v) for k,v in d.items()}))" % (fields,)],
+            cwd=work, env=env).decode().strip().splitlines()[-1]
+        with open(os.path.join(a.out, "asm_params.json"), "w") as f:
+            json.dump(json.loads(probe), f, indent=1, sort_keys=True)
     if a.keep:
         print("scratch kept at", work)
     else:
