@@ -457,26 +457,30 @@ def _finish(b, pp, secs, with_bc):
 
 def frobenius_norm(values):
     """||B||_F the way assemble.py:583 gets it (scipy.sparse.linalg.norm of the CSR = the
-    2-norm of its value array, numpy.linalg.norm -> BLAS dot): on the same values in the same
-    order this is the reference's number to the bit."""
+    2-norm of its value array, numpy.linalg.norm -> BLAS dot) on the same values in the same
+    order.  This is the reference's number to the bit ON THE SAME MACHINE: a threaded BLAS splits
+    the dot product by core count, so the last bit of the norm -- and with it the last bit of
+    every entry of A / ||B||_F -- differs between hosts for the reference too."""
     return float(np.linalg.norm(np.asarray(values)))
 
 
-def assemble(solver, pp: PhysicsParams, operators: dict):
+def assemble(solver, pp: PhysicsParams, operators: dict, bnorm=None):
     """Assemble the pencil of `pp` on the GPU of `solver` (a `kore_b200.lib.Solver`) and make
     it the handle's pencil, as `set_pencil` would with the reference-assembled CSR.
 
     Eigenvalue runs (forcing = 0): B is assembled un-normalised, its values come back once for
-    the Frobenius norm (assemble.py:583-585; host BLAS for bit compatibility), then A and B are
-    assembled with the factor 1 / ||B||_F.  Forced runs: A only, un-normalised
-    (assemble.py:1164).  Returns a dict with the programs and the norm."""
+    the Frobenius norm (assemble.py:583-585; `frobenius_norm`), then A and B are assembled with
+    the factor 1 / ||B||_F.  `bnorm`: use this norm instead (a repeated assembly with the same B;
+    tests pin the norm of the machine that wrote the fixtures).  Forced runs: A only,
+    un-normalised (assemble.py:1164).  Returns a dict with the programs and the norm."""
     progA = build_program_A(pp, operators)
     out = {"progA": progA, "bnorm": None}
     if pp.forcing == 0:
         progB = build_program_B(pp, operators)
-        solver.assemble(None, progB)
-        _, _, bvals = solver.get_assembled("B")
-        bnorm = frobenius_norm(bvals)
+        if bnorm is None:
+            solver.assemble(None, progB)
+            _, _, bvals = solver.get_assembled("B")
+            bnorm = frobenius_norm(bvals)
         out["bnorm"] = bnorm
         out["progB"] = progB
         solver.assemble(progA.with_final_scale(1. / bnorm), progB.with_final_scale(1. / bnorm))

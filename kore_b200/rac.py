@@ -127,12 +127,14 @@ class AssembledPencil:
     (`assembly.load_operators`); ``factor_of``: Ra -> the buoyancy factor (`buoyancy_factor`).
     B does not depend on Ra: its norm is computed at the first trial and reused."""
 
-    def __init__(self, pp, operators, factor_of):
+    def __init__(self, pp, operators, factor_of, bnorm=None):
         from . import assembly as _asm
         self._asm = _asm
         self.pp, self.ops, self.factor_of = pp, operators, factor_of
         self.progB = _asm.build_program_B(pp, operators)
-        self.bnorm = None
+        self.bnorm = bnorm
+        if bnorm is not None:
+            self.progB = self.progB.with_final_scale(1. / bnorm)
 
     def install(self, solver, Ra):
         a = self._asm
@@ -140,7 +142,7 @@ class AssembledPencil:
             solver.assemble(None, self.progB)
             self.bnorm = a.frobenius_norm(solver.get_assembled("B")[2])
             self.progB = self.progB.with_final_scale(1. / self.bnorm)
-        q = a.PhysicsParams.from_dict({**self.pp.__dict__, "Beyonce": self.factor_of(Ra)})
+        q = a.PhysicsParams.from_dict({**self.pp.__dict__, "Beyonce": self.factor_of(Ra)})  # unknown keys dropped
         solver.assemble(a.build_program_A(q, self.ops).with_final_scale(1. / self.bnorm), self.progB)
 
 

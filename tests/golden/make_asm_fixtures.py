@@ -66,6 +66,22 @@ def main():
             meta["make_case_overrides"] = ov
             meta["params_file"] = params
             json.dump(meta, open(os.path.join(out, "meta.json"), "w"), indent=1, sort_keys=True)
+        # ||B||_F as THIS machine's BLAS computed it inside the reference run (a threaded dot product: its
+        # last bit depends on the core count): found as the norm that makes the model reproduce B.npz
+        pj = json.load(open(os.path.join(out, "asm_params.json")))
+        if os.path.exists(os.path.join(out, "B.npz")):
+            sys.path.insert(0, ROOT)
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import assembly_model as am
+            from kore_b200 import assembly as asm
+            pp = asm.PhysicsParams.from_dict(pj)
+            ops = asm.load_operators_npz(os.path.join(out, "operators.npz"))
+            pB = asm.build_program_B(pp, ops)
+            bnorm = asm.frobenius_norm(am.evaluate(pB).data)
+            z = np.load(os.path.join(out, "B.npz"))
+            assert np.array_equal(am.evaluate(pB.with_final_scale(1. / bnorm)).data, z["data"]), name
+            pj["Bnorm"] = bnorm
+            json.dump(pj, open(os.path.join(out, "asm_params.json"), "w"), indent=1, sort_keys=True)
         print(name, "ok")
 
 

