@@ -227,6 +227,25 @@ typedef struct {
 int kb_assemble(kb_handle h, const kb_asm_program* A, const kb_asm_program* B);
 int kb_get_assembled(kb_handle h, int which, int64_t* nnz, int64_t* indptr, int32_t* indices, double* values);
 
+/* Post-processing diagnostics: the per-degree volume integrals
+ * bin/utils4pp.py:794-858 (`diagnose`: flow_worker :426-488, thermal_worker :536-561) computes with a
+ * multiprocessing pool for bin/spin_doctor.py:119-147, for hydrodynamic and Boussinesq thermal
+ * solutions.  x: nsol solution vectors (complex128, Kore ordering [u | v | h], sizmat each, one after
+ * the other: the columns of the eigenvector block kb_eigs returns).  nodes: 3 x N doubles -- the
+ * Chebyshev-Gauss nodes mapped into the solution's Chebyshev domain, the radii r_k in [Ra, Rb], and the
+ * weights (pi / N) sqrt(1 - x_k^2) (Rb - Ra) / 2 (utils4pp.py:54-64, 806-826).  Outputs, per solution:
+ * flow[nll][6] for the nll = lmax - m + 1 degrees in ascending order = {kinetic energy, kinetic
+ * dissipation, internal dissipation, 0 (Lorentz), buoyancy power, 0 (compositional)} -- the columns of
+ * the reference's `udgn`; thermal[nb][3] for the poloidal degrees = {thermal energy, dissipation,
+ * advection} (`tdgn`; may be NULL when thermal == 0).  heating: 0 differential, 1 internal
+ * (utils4pp.py:404-411). */
+typedef struct {
+  int32_t N, N1, nb, m, lmax, symm, thermal, heating;
+  double ricb, rcmb;
+} kb_diag_params;
+int kb_diagnose(kb_handle h, const kb_diag_params* p, const double* nodes, const double* x, int nsol,
+                double* flow, double* thermal);
+
 /* Debug / test hooks (not part of the drop-in surface).  kb_dbg_schur: the host-side complex
  * Schur form + ordering of the projected problem (what SLEPc's DS does with LAPACK), m x m
  * column-major complex128 in, T and Q out; which < 0: no ordering.  kb_dbg_*_timing: in-kernel

@@ -671,10 +671,11 @@ int kbi_chainfac_run(kb_context* h, bool two_sided, bool transposed, int64_t plo
     int g = atoi(getenv("KB_CHAINFAC_GRID"));
     if (g >= 2 && g < G) G = g;
   }
-  {
+  if (h->nranks == 1 && !dense) {
     // no node has more than ceil(bmax / KF_WMIN) strips: CTAs beyond that would only take part in
     // the barriers (small pencils: forced_small has 5 strips per node; several such launches can
-    // then share the GPU, kore_b200/sweep.py)
+    // then share the GPU, kore_b200/sweep.py).  One-GPU factorisations only: the l-sharded path
+    // keeps the grid its 2- to 8-GPU validation ran with.
     const int kmax = (int)((bmax + KF_WMIN - 1) / KF_WMIN);
     const int need = (two_sided && !dense ? 2 : 1) * kmax;
     if (need < G) G = need < 2 ? 2 : need;

@@ -1,0 +1,83 @@
+"""Power-balance diagnostics of a solution on the GPU.
+
+The reference post-processes every solution in bin/spin_doctor.py:105-242: the eigenvector is cut
+into per-degree Chebyshev series, `utils4pp.diagnose` (utils4pp.py:794-858) integrates kinetic
+energy, viscous dissipation, buoyancy power, thermal energy / dissipation / advection degree by degree
+in a multiprocessing pool, and the sums enter the power-balance residuals the physicists use as their
+own correctness check (spin_doctor.py:227-242).  Here the integrals are one kernel launch for all
+degrees and all solutions (`kb_diagnose`, csrc/kb_diag.cu); this module prepares the quadrature
+nodes, calls it and forms the same sums and residuals.  Hydrodynamic and Boussinesq thermal
+solutions (no Lorentz / compositional terms).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import chain as _chain
+from . import lib as _lib
+
+
+def quadrature_nodes(N, ricb, rcmb=1.0, Ra=None, Rb=None):
+    """(3, N): the Chebyshev-Gauss nodes x_k = cos((k + 1/2) pi / N) mapped to r in [Ra, Rb] and then
+    into the Chebyshev domain of the solution ([ricb, rcmb], or [-rcmb, rcmb] without inner core), the
+    radii, and the weights (pi / N) sqrt(1 - x_k^2) (Rb - Ra) / 2 (utils4pp.py:15-24, 54-64, 806-822)."""
+    Ra = ricb if Ra is None else Ra
+    Rb = rcmb if Rb is None else Rb
+    k = np.arange(N)
+    xk = np.cos((k + 0.5) * np.pi / N)
+    rk = 0.5 * (Rb - Ra) * (xk + 1) + Ra
+    r0 = ricb if ricb > 0 else -rcmb
+    x0 = 2 * (rk - r0) / (rcmb - r0) - 1
+    w = (np.pi / N) * np.sqrt(1 - xk ** 2) * (Rb - Ra) / 2
+    return np.vstack([x0, rk, w])
+
+
+def diagnose(solver, X, N, lmax, m, symm, ricb, thermal=0, heating="differential", rcmb=1.0, Ra=None, Rb=None):
+    """Per-degree integrals of the solutions in the columns of X (Kore ordering [u | v | h]).
+
+    Returns (flow, therm, degrees): flow[nsol, n_l, 6] with the columns of the reference's `udgn`
+    (kinetic energy, kinetic dissipation, internal dissipation, 0, buoyancy power, 0), therm[nsol, nb, 3]
+    (`tdgn`: thermal energy, dissipation, advection), degrees = (poloidal, toroidal, all)."""
+    if heating not in ("differential", "internal"):
+        raise NotImplementedError("heating = %r" % (heating,))
+    N1 = N if ricb > 0 else N // 2
+    nb = (lmax - m + 1) // 2
+    p = _lib.KbDiagParams(N=N, N1=N1, nb=nb, m=m, lmax=lmax, symm=symm, thermal=int(bool(thermal)),
+                          heating=0 if heating == "differential" else 1, ricb=float(ricb), rcmb=float(rcmb))
+    X = np.asarray(X, dtype=np.complex128)
+    if X.ndim == 1:
+        X = X.reshape(-1, 1)
+    want = N1 * nb * (3 if thermal else 2)
+    if X.shape[0] != want:
+        raise ValueError("solutions have %d rows, the parameters imply %d (hydro%s only)"
+                         % (X.shape[0], want, " + thermal" if thermal else ""))
+    flow, therm = solver.diagnose(p, quadrature_nodes(N, ricb, rcmb, Ra, Rb), X)
+    return flow, therm, _chain.ell(m, lmax, symm)
+
+
+def power_balance(flow, therm, degrees, lam, Ek, ViscosD=None, Beyonce=0.0, ThermaD=0.0, pss=0.0):
+    """The sums and residuals of spin_doctor.py:148-242 for ONE solution: `flow` [n_l, 6], `therm`
+    [nb, 3], `lam` its eigenvalue (growth rate = real part; 0 for a forced solution).
+
+    spin_doctor.py scales the dissipation and power terms with `par.OmgTau`, which current
+    parameters.py files no longer define; with the time scale those files do define
+    (`Gaspard = 1`, viscous factor `ViscosD`, buoyancy factor `Beyonce`, thermal factor `ThermaD`,
+    parameters.py:273-277) the balances read
+        resid0: Dint + Dkin - pss = 0            (internal vs kinetic dissipation)
+        resid1: 2 sigma KE - ViscosD Dkin + Beyonce Wthm = 0
+        resid3: 2 sigma TE - ThermaD Dthm - Wadv = 0
+    each divided by its largest term."""
+    lp, lt, ll = degrees
+    ll = np.asarray(ll)
+    ViscosD = Ek if ViscosD is None else ViscosD
+    sigma = complex(lam).real
+    KE, Dkin0, Dint0, _, Wthm0, _ = flow.sum(axis=0)
+    out = {"KE": KE, "KP": flow[np.isin(ll, lp), 0].sum(), "KT": flow[np.isin(ll, lt), 0].sum(),
+           "Dkin": ViscosD * Dkin0, "Dint": ViscosD * Dint0, "Wthm": Beyonce * Wthm0}
+    out["resid0"] = abs(Dint0 + Dkin0 - pss) / max(abs(Dint0), abs(Dkin0), abs(pss))
+    out["resid1"] = abs(2 * sigma * KE - out["Dkin"] + out["Wthm"]) / max(abs(2 * sigma * KE), abs(out["Dkin"]), abs(out["Wthm"]))
+    if therm is not None and therm.size and np.any(therm):
+        TE, Dthm0, Wadv = therm.sum(axis=0)
+        out.update(TE=TE, Dthm=ThermaD * Dthm0, Wadv_thm=Wadv)
+        out["resid3"] = abs(2 * sigma * TE - out["Dthm"] - Wadv) / max(abs(2 * sigma * TE), abs(out["Dthm"]), abs(Wadv))
+    return out

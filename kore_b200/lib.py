@@ -30,7 +30,7 @@ WHICH = {"LM": 0, "SM": 1, "LR": 2, "SR": 3, "LI": 4, "SI": 5, "TM": 6, "TR": 7,
 EXPORTS = [
     "kb_create", "kb_destroy", "kb_last_error", "kb_set_option", "kb_set_pencil", "kb_set_chain",
     "kb_nccl_unique_id", "kb_set_sharding", "kb_factor", "kb_solve", "kb_apply_op", "kb_matvec",
-    "kb_eigs", "kb_get_stats", "kb_solve_dev", "kb_stream", "kb_savetxt", "kb_assemble", "kb_get_assembled",
+    "kb_eigs", "kb_get_stats", "kb_solve_dev", "kb_stream", "kb_savetxt", "kb_assemble", "kb_get_assembled", "kb_diagnose",
     "kb_dbg_schur", "kb_dbg_factor_timing", "kb_dbg_sweep_timing", "kb_dbg_zgemm", "kb_dbg_shard_segment",
 ]
 
@@ -67,6 +67,13 @@ class KbAsmProgram(C.Structure):
         ("grp_sc", C.c_void_p), ("grp_term", C.c_void_p), ("term_coef", C.c_void_p),
         ("term_op", C.c_void_p),
     ]
+
+
+class KbDiagParams(C.Structure):
+    """kb_diag_params of include/kore_b200.h."""
+    _fields_ = [("N", C.c_int32), ("N1", C.c_int32), ("nb", C.c_int32), ("m", C.c_int32), ("lmax", C.c_int32),
+                ("symm", C.c_int32), ("thermal", C.c_int32), ("heating", C.c_int32),
+                ("ricb", C.c_double), ("rcmb", C.c_double)]
 
 
 def _asm_struct(prog):
@@ -134,6 +141,7 @@ def load():
     lib.kb_dbg_schur.argtypes = [C.c_int, vp, C.c_int, vp, vp, vp, vp]
     lib.kb_assemble.argtypes = [vp, C.POINTER(KbAsmProgram), C.POINTER(KbAsmProgram)]
     lib.kb_get_assembled.argtypes = [vp, C.c_int, C.POINTER(i64), vp, vp, vp]
+    lib.kb_diagnose.argtypes = [vp, C.POINTER(KbDiagParams), vp, vp, C.c_int, vp, vp]
     for name in EXPORTS:
         if name != "kb_last_error":
             getattr(lib, name).restype = C.c_int
@@ -264,6 +272,20 @@ class Solver:
         cplx = w == 0 or getattr(self, "_b_complex", False)
         values = raw.view(np.complex128) if cplx else raw[:nnz.value].copy()
         return indptr, indices, values
+
+    def diagnose(self, params, nodes, X):
+        """kb_diagnose: per-degree integrals of the solutions in the columns of X (sizmat x nsol).
+        `params`: KbDiagParams; `nodes`: (3, N) float64.  Returns (flow[nsol, nll, 6], thermal[nsol, nb, 3])."""
+        X = np.asarray(X, dtype=np.complex128)
+        if X.ndim == 1:
+            X = X.reshape(-1, 1)
+        X = np.asfortranarray(X)
+        nsol = X.shape[1]
+        nodes = np.ascontiguousarray(nodes, dtype=np.float64)
+        flow = np.zeros((nsol, 2 * params.nb, 6))
+        thermal = np.zeros((nsol, params.nb, 3))
+        self._check(self.lib.kb_diagnose(self.h, C.byref(params), _ptr(nodes), _ptr(X), nsol, _ptr(flow), _ptr(thermal)))
+        return flow, thermal
 
     def set_chain(self, perm, nodeptr):
         perm = np.ascontiguousarray(perm, dtype=np.int64)

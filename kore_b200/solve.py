@@ -93,6 +93,28 @@ def write_fields(par, n, vec):
         _lib.savetxt("imag_%s.field" % name, vec[a:b, :], "imag")
 
 
+def write_power_balance(par, solver, vec, lam):
+    """`-kb_diagnose`: the energy / dissipation / power integrals spin_doctor.py:119-242 derives from
+    the field files, computed on the GPU straight from the solutions (kore_b200/diagnostics.py) and
+    written to power_balance.dat, one row per solution:
+    KE KP KT Dkin Dint Wthm resid0 resid1 [TE Dthm Wadv_thm resid3]."""
+    from . import diagnostics as dg
+    if par.magnetic or par.compositional or not par.hydro or getattr(par, "anelastic", 0):
+        print("-kb_diagnose covers hydrodynamic and Boussinesq thermal runs only; skipped")
+        return
+    flow, therm, degs = dg.diagnose(solver, vec, int(par.N), par.lmax, par.m, par.symm, par.ricb,
+                                    thermal=par.thermal, heating=getattr(par, "heating", "differential"))
+    rows = []
+    for i in range(vec.shape[1]):
+        pb = dg.power_balance(flow[i], therm[i] if par.thermal else None, degs, lam[i], par.Ek,
+                              getattr(par, "ViscosD", par.Ek), getattr(par, "Beyonce", 0.0), getattr(par, "ThermaD", 0.0))
+        keys = ["KE", "KP", "KT", "Dkin", "Dint", "Wthm", "resid0", "resid1"]
+        if par.thermal:
+            keys += ["TE", "Dthm", "Wadv_thm", "resid3"]
+        rows.append([pb[k] for k in keys])
+    np.savetxt("power_balance.dat", np.asarray(rows))
+
+
 def main(argv=None, device=0):
     from . import eps as kb
 
@@ -151,6 +173,8 @@ def main(argv=None, device=0):
             kb.savetxt("eigenvalues0.dat", eigval)
             write_fields(par, n, vec)
             success = nconv
+            if opts.hasName("kb_diagnose"):
+                write_power_balance(par, E._solver, vec, k[0])
         else:
             print("No converged solution found")
             np.savetxt("no_conv_solution", [0])

@@ -141,8 +141,13 @@ def test_eigen_run_from_radial_operators_equals_run_from_matrices(tmp_path, monk
     c, d2 = write_operator_dir(tmp_path, "spinover")
     monkeypatch.chdir(d2)
     assert not os.path.exists("A.npz")
-    assert drv.main(["-st_type", "sinvert"]) == 0
+    assert drv.main(["-st_type", "sinvert", "-kb_diagnose"]) == 0
     sys.modules.pop("parameters", None)
+    # -kb_diagnose: one row of energy / dissipation integrals and power-balance residuals per solution
+    pb = np.loadtxt("power_balance.dat").reshape(-1, 8)
+    eig = np.loadtxt("eigenvalues0.dat").reshape(-1, 2)
+    assert pb.shape[0] == eig.shape[0]
+    assert pb[np.argmax(eig[:, 0]), 7] < 1e-4 and np.all(pb[:, 0] > 0)
     e1, e2 = np.loadtxt(d1 / "eigenvalues0.dat"), np.loadtxt(d2 / "eigenvalues0.dat")
     assert e1.shape == e2.shape and np.max(np.abs(e1 - e2)) <= 1e-11
     for fn in ("real_flow.field", "imag_flow.field"):
