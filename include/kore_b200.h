@@ -57,7 +57,12 @@ enum {
   KB_OPT_PURIFY = 3,      /* 0/1: x <- OP x on extracted eigenvectors (SLEPc EPSSetPurify)    */
   KB_OPT_SEED = 4,        /* seed of the random Arnoldi start vector when v0 == NULL          */
   KB_OPT_PANEL = 5,       /* Gauss-Jordan panel width override (0 = automatic)                */
-  KB_OPT_REFINE_EIGS = 6, /* refinement steps per operator application inside kb_eigs (default 0) */
+  KB_OPT_REFINE_EIGS = 6, /* refinement steps per operator application inside kb_eigs; -1 (default):
+                             automatic -- the start vector's solve is refined once and, when that
+                             correction exceeds 1e-10 of the solution (kb_stats.refine_resid), every
+                             application of the run gets one step (ill-conditioned pencils: the
+                             reference-assembled E = 1e-8 one; the Ritz residuals otherwise stall
+                             above 1e-10), else none                                             */
   KB_OPT_SWEEP = 7,       /* chain-sweep kernels: 1 persistent two-sided (default), 2 persistent
                              one-sided with grid barriers, 0 one kernel pair per node (no device-side
                              waits).  Takes effect at the next kb_factor (the factors are laid out
@@ -157,7 +162,8 @@ typedef struct {
   int64_t factor_bytes;   /* device bytes held by the factors                 */
   double factor_flops;    /* real flops executed by the last kb_factor        */
   double solve_bytes;     /* algorithmic bytes of one chain solve             */
-  double refine_resid;    /* last relative linear residual seen in refinement */
+  double refine_resid;    /* kb_eigs, automatic refinement: |first correction| / |solution| of the
+                             start vector's solve (the forward error of an unrefined solve)      */
   int64_t protocol_fallbacks; /* times a persistent kernel timed out and the handle fell back
                                  to the kernels without device-side waits (0 in a healthy run) */
   int64_t wait_error;     /* code | CTA << 8 of the last expired device-side wait (0: none)  */

@@ -306,7 +306,7 @@ struct kb_context {
   // options
   int opt_equil = 1;
   int opt_refine = 1;
-  int opt_refine_eigs = 0;
+  int opt_refine_eigs = -1;  // -1: automatic (kb_eigs probes the accuracy of the unrefined solve)
   int opt_purify = 1;
   int64_t opt_seed = 1;
   int opt_panel = 0;

@@ -103,7 +103,7 @@ extern "C" int kb_set_option(kb_handle h, int option, int64_t value) {
     case KB_OPT_PURIFY: h->opt_purify = value != 0; break;
     case KB_OPT_SEED: h->opt_seed = value; break;
     case KB_OPT_PANEL: h->opt_panel = (int)value; break;
-    case KB_OPT_REFINE_EIGS: h->opt_refine_eigs = (int)std::max<int64_t>(0, value); break;
+    case KB_OPT_REFINE_EIGS: h->opt_refine_eigs = (int)std::max<int64_t>(-1, value); break;
     // The factors are laid out for the sweep that will read them (two-sided or one-sided,
     // transposed or row-major, folded couplings or not): changing any of these invalidates them.
     case KB_OPT_SWEEP:
