@@ -66,6 +66,8 @@ class PhysicsParams:
     heating: str = "differential"
     forcing: int = 0
     forcing_frequency: float = 0.0
+    forcing_amplitude_cmb: float = 0.0
+    forcing_amplitude_icb: float = 0.0
     Gaspard: float = 1.0
     ViscosD: float = 1e-3
     Beyonce: float = 0.0
@@ -453,6 +455,32 @@ def _finish(b, pp, secs, with_bc):
             br_bc[base:base + len(degs)] = first[name]
     meta = {"sections": {k: (int(v[0]), [int(x) for x in v[1]]) for k, v in secs.items()}}
     return b.finish(nbr, br_chop, br_bc, bc_rows, meta)
+
+
+def forcing_vector(pp: PhysicsParams):
+    """Right-hand side of the forced problem, as the dense complex vector solve.py:211-216 makes of
+    B_forced.npz.  forcing = 7, libration in longitude as a boundary flow (assemble.py:278-329): two
+    entries, in the outer and inner boundary rows of the toroidal l = 1 block (m = 0, axial) or of the
+    poloidal l = 2 block (m = 2), no-slip boundaries, symm = 1."""
+    pp.check_supported()
+    if pp.forcing != 7:
+        raise NotImplementedError("forcing vector of forcing = %d" % pp.forcing)
+    if not (pp.symm == 1 and pp.bci == 1 and pp.bco == 1 and pp.m in (0, 2)):
+        raise ValueError("longitudinal libration needs m = 0 or 2, symm = 1 and no-slip boundaries")
+    secs = _sections(pp)
+    b = np.zeros(pp.sizmat, dtype=np.complex128)
+    w = pp.forcing_frequency
+    if pp.m == 0:
+        row = _block_of(secs["v"], 1) * pp.N1
+        b[row] = 1j * w * pp.forcing_amplitude_cmb / 2
+        b[row + 1] = 1j * w * pp.forcing_amplitude_icb * pp.ricb / 2
+    else:
+        l = 2
+        L = l * (l + 1)
+        row = _block_of(secs["u"], l) * pp.N1
+        b[row] = -w / L * pp.forcing_amplitude_cmb
+        b[row + 1] = -w / L * pp.forcing_amplitude_icb * (pp.ricb ** 2)
+    return b
 
 
 def frobenius_norm(values):

@@ -20,7 +20,8 @@ With `-kb_assemble` (or when there is no A.npz but the `*.mtx` radial operators 
 bin/submatrices.py are present) the run skips bin/assemble.py as well: the pencil is assembled on
 the GPU from the radial operators (kore_b200/assembly.py; hydrodynamic and Boussinesq thermal
 set-ups) -- the same matrices, bit for bit, without A.npz / B.npz ever being written or read.
-The forced right-hand side still comes from B_forced.npz.
+The forced right-hand side comes from B_forced.npz when it exists, else (forcing = 7, libration) it
+is formed here.
 """
 from __future__ import annotations
 
@@ -181,8 +182,11 @@ def main(argv=None, device=0):
         st = E.getStats()
         E.destroy()
     else:  # ------------------------------------------------------------- forced problem
-        b0 = load_csr("B_forced.npz")
-        bvec = np.asarray(b0[:, 0].todense()).ravel().astype(complex)
+        if on_device and not os.path.exists("B_forced.npz"):
+            bvec = _assembly.forcing_vector(asm_inputs[0])  # assemble.py:278-329 (libration)
+        else:
+            b0 = load_csr("B_forced.npz")
+            bvec = np.asarray(b0[:, 0].todense()).ravel().astype(complex)
         x = np.zeros(sizmat, dtype=complex)
         K = kb.KSP(device)
         K.create()

@@ -161,6 +161,7 @@ def test_forced_run_from_radial_operators(tmp_path, monkeypatch, lib):
     from kore_b200 import solve as drv
     c, d = write_operator_dir(tmp_path, "forced_small")
     monkeypatch.chdir(d)
+    os.remove("B_forced.npz")  # the libration forcing vector is formed by the driver (assemble.py:278-329)
     sys.modules.pop("parameters", None)
     assert drv.main(["-kb_assemble"]) == 0
     sys.modules.pop("parameters", None)
