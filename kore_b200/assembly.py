@@ -106,6 +106,8 @@ class PhysicsParams:
         return self.N1 * self.nb * (2 * self.hydro + 2 * self.magnetic + self.thermal + self.compositional)
 
     def check_supported(self):
+        if (self.lmax - self.m + 1) % 2:
+            raise ValueError("lmax - m + 1 must be even (parameters.py:301-303): lmax = %d, m = %d" % (self.lmax, self.m))
         bad = []
         if self.magnetic:
             bad.append("magnetic = 1")

@@ -29,6 +29,15 @@ NEW_CASES = {
                          ["bci=0", "bco=0", "bci_thermal=1", "N=40", "lmax=40"]),
     # internal heating
     "asm_internal": ("tests/dormy2004/params.dormy04", ["heating='internal'", "N=40", "lmax=40", "bco_thermal=1"]),
+    # corners of the parameter space at a small truncation (N = 24 / 48)
+    "asm_m0_antisym": ("tests/spinover/params.spinover", ["m=0", "symm=-1", "N=24"]),
+    "asm_thermal_m0": ("tests/dormy2004/params.dormy04", ["m=0", "symm=1", "N=24", "lmax=23"]),
+    "asm_fullsphere_antisym": ("tests/jones2000/params.jones", ["N=48", "lmax=32", "symm=-1", "Ra_gap=1e6"]),
+    "asm_mixed_bc": ("tests/spinover/params.spinover", ["bci=0", "bco=1", "N=24", "m=3", "symm=1"]),
+    "asm_forced_thermal": ("tests/dormy2004/params.dormy04",
+                           ["forcing=7", "m=2", "symm=1", "N=24", "lmax=25", "forcing_frequency=0.37"]),
+    "asm_fullsphere_stressfree": ("tests/jones2000/params.jones",
+                                  ["N=48", "lmax=32", "bco=0", "heating='differential'", "Ra_gap=1e6"]),
 }
 EXISTING = ["spinover", "dormy", "jones", "forced_small", "m0_small"]
 
