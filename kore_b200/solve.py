@@ -20,6 +20,8 @@ With `-kb_assemble` (or when there is no A.npz but the `*.mtx` radial operators 
 bin/submatrices.py are present) the run skips bin/assemble.py as well: the pencil is assembled on
 the GPU from the radial operators (kore_b200/assembly.py; hydrodynamic and Boussinesq thermal
 set-ups) -- the same matrices, bit for bit, without A.npz / B.npz ever being written or read.
+`-kb_diagnose` adds power_balance.dat (kore_b200/diagnostics.py), `-kb_npz` adds eigenpairs.npz
+(eigenvalues, the complex solution block and the row ranges of the fields, binary).
 The forced right-hand side comes from B_forced.npz when it exists, else (forcing = 7, libration) it
 is formed here.
 """
@@ -176,6 +178,10 @@ def main(argv=None, device=0):
             success = nconv
             if opts.hasName("kb_diagnose"):
                 write_power_balance(par, E._solver, vec, k[0])
+            if opts.hasName("kb_npz"):
+                # binary twin of eigenvalues0.dat + the field files: one uncompressed .npz, no text round trip
+                np.savez("eigenpairs.npz", eigenvalues=k[0], vectors=vec,
+                         fields=np.array([[nm, a, b] for nm, a, b in field_slices(par, n)], dtype=object).astype(str))
         else:
             print("No converged solution found")
             np.savetxt("no_conv_solution", [0])

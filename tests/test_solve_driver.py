@@ -141,7 +141,12 @@ def test_eigen_run_from_radial_operators_equals_run_from_matrices(tmp_path, monk
     c, d2 = write_operator_dir(tmp_path, "spinover")
     monkeypatch.chdir(d2)
     assert not os.path.exists("A.npz")
-    assert drv.main(["-st_type", "sinvert", "-kb_diagnose"]) == 0
+    assert drv.main(["-st_type", "sinvert", "-kb_diagnose", "-kb_npz"]) == 0
+    z = np.load("eigenpairs.npz")
+    assert z["vectors"].shape == (c.n, len(z["eigenvalues"])) and z["fields"].tolist() == [["flow", "0", str(c.n)]]
+    ev = np.loadtxt("eigenvalues0.dat").reshape(-1, 2)
+    assert np.array_equal(z["eigenvalues"], ev[:, 0] + 1j * ev[:, 1])
+    assert np.array_equal(z["vectors"][:, 0].real, np.loadtxt("real_flow.field").reshape(c.n, -1)[:, 0])
     sys.modules.pop("parameters", None)
     # -kb_diagnose: one row of energy / dissipation integrals and power-balance residuals per solution
     pb = np.loadtxt("power_balance.dat").reshape(-1, 8)
