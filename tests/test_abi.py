@@ -89,3 +89,29 @@ def test_defective_and_repeated_eigenvalues(lib):
     z = np.array([0j])
     assert L.kb_dbg_schur(m, H.ctypes.data, -1, z.ctypes.data, z.ctypes.data, T.ctypes.data, Q.ctypes.data) == 0
     assert np.linalg.norm(Q @ T @ Q.conj().T - H) < 1e-12
+
+
+def test_struct_layouts_match_the_header(lib, tmp_path):
+    # the ctypes mirrors of kb_stats / kb_asm_program / kb_diag_params against the header as a C compiler lays
+    # them out (gcc: sizeof and offsetof of every field)
+    import ctypes as C
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    structs = {"kb_stats": lib.KbStats, "kb_asm_program": lib.KbAsmProgram, "kb_diag_params": lib.KbDiagParams}
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "kore_b200.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        src.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for f, _ in cls._fields_:
+            src.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, f, cname, f))
+    src.append("return 0; }")
+    cfile = tmp_path / "layout.c"
+    cfile.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(cfile), "-o", str(exe)])
+    got = dict(line.split() for line in subprocess.check_output([str(exe)]).decode().splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for f, _ in cls._fields_:
+            assert int(got["%s.%s" % (cname, f)]) == getattr(cls, f).offset, (cname, f)
