@@ -15,8 +15,10 @@
 // (the reference differentiates in coefficient space and evaluates by Clenshaw; both are exact in
 // exact arithmetic, tests hold the difference below 1e-9 of the largest degree), forms the
 // integrands of utils4pp.py:221-296, 363-412 and the CTA sums them with the quadrature weights in a
-// fixed order (deterministic).  8.6 GFLOP at N = lmax = 600 for ten solutions: milliseconds against
-// the reference's minutes, and nowhere near a roofline worth chasing.
+// fixed order (deterministic).  FP64-pipe bound: 7.6e10 flops of recurrences and complex
+// accumulations at N = lmax = 600 for eleven solutions in 3.19 ms = 24 TFLOP/s, 0.64 of the measured
+// 37 TFLOP/s DFMA peak (profiles/r2B_ncu_launches_assembly_diagnostics.csv); the reference's pool
+// takes minutes.
 #include "kb_internal.cuh"
 
 namespace {
@@ -197,6 +199,9 @@ extern "C" int kb_diagnose(kb_handle h, const kb_diag_params* p, const double* n
   if (p->N < 2 || p->N1 < 1 || p->nb < 1 || p->N1 > p->N || p->m < 0)
     return kb_fail(h, KB_EINVAL, "kb_diagnose: bad sizes");
   if (p->thermal && !thermal) return kb_fail(h, KB_EINVAL, "kb_diagnose: thermal output missing");
+  if (2 * p->nb != p->lmax - p->m + 1) return kb_fail(h, KB_EINVAL, "kb_diagnose: nb does not match lmax and m");
+  if (p->heating != 0 && p->heating != 1) return kb_fail(h, KB_EINVAL, "kb_diagnose: heating must be 0 or 1");
+  if (p->symm != 1 && p->symm != -1) return kb_fail(h, KB_EINVAL, "kb_diagnose: symm must be +1 or -1");
   if (p->ricb < 0 || p->ricb >= p->rcmb) return kb_fail(h, KB_EINVAL, "kb_diagnose: bad radii");
   const bool full = p->ricb == 0.0;
   if (full ? (p->N1 != p->N / 2) : (p->N1 != p->N)) return kb_fail(h, KB_EINVAL, "kb_diagnose: N1 does not match N and ricb");
