@@ -245,6 +245,7 @@ class Solver:
         self._check(self.lib.kb_set_pencil(self.h, n, np.dtype(idx_dtype).itemsize, _ptr(ap), _ptr(ai),
                                            _ptr(av), _ptr(bp), _ptr(bi), _ptr(bv), bcomplex))
         self.n = n
+        self._b_complex = bool(bcomplex)
 
     def assemble(self, progA, progB=None):
         """Assemble the pencil on the GPU from assembly programs (kore_b200.assembly) instead of
@@ -257,6 +258,7 @@ class Solver:
         self._check(self.lib.kb_assemble(self.h, C.byref(sa) if sa is not None else None,
                                          C.byref(sb) if sb is not None else None))
         self.n = (progA if progA is not None else progB).n
+        self._b_complex = bool(progB.is_complex) if progB is not None else False
 
     def get_assembled(self, which="A"):
         """(indptr int64, indices int32, values) of the A or B held on the device in raw CSR form
