@@ -80,3 +80,38 @@ def eigen_sweep(A, B, targets, nev, perm, nodeptr, which="TM", device=0, rank=0,
             lam, X, info = s.eigs(nev, which=which, target=tau, **kw)
             out.append((tau, lam, X, info))
     return out
+
+
+def parameter_sweep(pp, operators, cases, nev, which="TM", device=0, rank=0, world=1, want_vectors=False,
+                    solver_factory=None, **kw):
+    """Eigenpairs of a family of pencils that differ in their physical parameters -- azimuthal wavenumber m,
+    symmetry, Rayleigh number (buoyancy factor), Ekman-number factors, boundary conditions -- on the same radial
+    truncation: `cases` is a list of dicts of `assembly.PhysicsParams` fields to override (plus the optional key
+    ``"tau"``: the shift / target of that case; default 0), dealt round-robin to the ranks.  Every pencil is
+    ASSEMBLED ON THE GPU (kore_b200.assembly) from the radial operators, which do not depend on m, symm or the
+    dimensionless numbers, so a survey over m that the reference runs as one assemble.py + solve.py job per value
+    (tools/subramp.sh-style loops; SURVEY.md 8e: "different azimuthal numbers m are different matrices") is here
+    one handle per GPU and, per case, a new assembly program, the layout, one factorisation and one eigensolve.
+
+    Returns [(case, eigenvalues, eigenvectors or None, info)] for this rank's cases."""
+    from . import assembly as _asm
+    from . import chain as _chain
+    make = solver_factory or _lib.Solver
+    out = []
+    with make(device) as s:
+        bnorm_of = {}
+        for case in deal(list(cases), rank, world):
+            fields = {k: v for k, v in case.items() if k != "tau"}
+            q = _asm.PhysicsParams.from_dict({**pp.__dict__, **fields})
+            q.check_supported()
+            tau = complex(case.get("tau", 0.0))
+            # B (and its norm) depends on the degrees present and the thermal set-up only
+            key = (q.m, q.lmax, q.symm, q.thermal, q.heating)
+            res = _asm.assemble(s, q, operators, bnorm=bnorm_of.get(key))
+            bnorm_of[key] = res["bnorm"]
+            perm, nodeptr = _chain.chain_from_params(q.N1, q.m, q.lmax, q.symm, -1, q.hydro, 0, q.thermal, 0)
+            s.set_chain(perm, nodeptr)
+            s.factor(tau)
+            lam, X, info = s.eigs(nev, which=which, target=tau, want_vectors=want_vectors, **kw)
+            out.append((case, lam, X, info))
+    return out

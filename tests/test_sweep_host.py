@@ -1,0 +1,75 @@
+"""Host logic of kore_b200.sweep.parameter_sweep (CPU): the cases are dealt to the ranks, every case gets its own
+assembly program / chain / shift, and B's norm is reused between cases that share B.  The solver is a stand-in
+that evaluates the programs with the NumPy model of the assembly kernels and solves with the CPU oracle."""
+import json
+import os
+
+import numpy as np
+
+import assembly_model as am
+import kore_oracle as ko
+from conftest import GOLDEN
+from kore_b200 import assembly as asm, sweep
+
+
+class OracleSolver:
+    log = []
+
+    def __init__(self, device=0):
+        self.M = {}
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+    def assemble(self, progA, progB=None):
+        OracleSolver.log.append(("assemble", progA is not None, progB is not None))
+        self.M = {}
+        if progA is not None:
+            self.M["A"] = am.evaluate(progA)
+        if progB is not None:
+            self.M["B"] = am.evaluate(progB)
+        self.n = (progA if progA is not None else progB).n
+
+    def get_assembled(self, which="A"):
+        M = self.M[which]
+        return M.indptr.astype(np.int64), M.indices.astype(np.int32), M.data
+
+    def set_chain(self, perm, nodeptr):
+        assert len(perm) == self.n and nodeptr[-1] == self.n
+        OracleSolver.log.append(("chain", len(nodeptr) - 1))
+
+    def factor(self, tau):
+        self.tau = tau
+
+    def eigs(self, nev, which="TM", target=None, want_vectors=False, **kw):
+        lam, X, info = ko.eigs(self.M["A"], self.M["B"], self.tau, nev, which)
+        return lam, (X if want_vectors else None), dict(nconv=len(lam))
+
+
+def test_parameter_sweep_over_m_and_symmetry():
+    d = os.path.join(GOLDEN, "m0_small")
+    pp = asm.PhysicsParams.from_dict(json.load(open(os.path.join(d, "asm_params.json"))))
+    ops = asm.load_operators_npz(os.path.join(d, "operators.npz"))
+    # the m0_small fixture itself (m = 0, symm = 1, lmax = 39) and two other members of the family
+    cases = [{"m": 0, "symm": 1, "lmax": 39, "tau": 1j}, {"m": 2, "symm": 1, "lmax": 41, "tau": 1j},
+             {"m": 2, "symm": 1, "lmax": 41, "tau": 0.5j}, {"m": 1, "symm": -1, "lmax": 40, "tau": 1j}]
+    OracleSolver.log = []
+    out = sweep.parameter_sweep(pp, ops, cases, nev=3, solver_factory=OracleSolver)
+    assert [c for c, *_ in out] == cases
+    # the norm of B is assembled once per distinct (m, lmax, symm): cases 1 and 2 share it
+    b_only = [e for e in OracleSolver.log if e == ("assemble", False, True)]
+    assert len(b_only) == 3
+    # case 0 is the committed fixture: same eigenvalues as the oracle on the reference-assembled matrices
+    A = ko.load_csr(os.path.join(d, "A.npz"))
+    B = ko.load_csr(os.path.join(d, "B.npz"))
+    lam_ref, _, _ = ko.eigs(A, B, 1j, 3, "TM")
+    assert np.max(np.abs(np.sort_complex(out[0][1]) - np.sort_complex(lam_ref))) < 1e-12
+    # round-robin over two ranks
+    r0 = sweep.parameter_sweep(pp, ops, cases, nev=3, rank=0, world=2, solver_factory=OracleSolver)
+    r1 = sweep.parameter_sweep(pp, ops, cases, nev=3, rank=1, world=2, solver_factory=OracleSolver)
+    assert [c for c, *_ in r0] == cases[0::2] and [c for c, *_ in r1] == cases[1::2]
+    for (c, lam, _, _), full in zip(r0 + r1, [out[0], out[2], out[1], out[3]]):
+        assert np.allclose(np.sort_complex(lam), np.sort_complex(full[1]), rtol=0, atol=1e-13)
