@@ -22,8 +22,8 @@ evaluators (the kernel, and the NumPy model in tests/assembly_model.py) perform 
 operations, so the assembled CSR equals the reference's bit for bit (tests/test_assembly.py).
 
 Scope: hydrodynamic (sections u, v) and Boussinesq thermal (section h) problems, viscous,
-with or without inner core, eigenvalue (forcing = 0) and forced (A only) runs -- BASELINE.json
-configs 1, 2, 3 and 5.  Magnetic, compositional, anelastic and inviscid set-ups raise
+with or without inner core, eigenvalue (forcing = 0) and forced runs (forcing = 7, 9, 10: the modes
+that work in the reference; A and the forcing vector) -- BASELINE.json configs 1, 2, 3 and 5.  Magnetic, compositional, anelastic and inviscid set-ups raise
 NotImplementedError (their pencils still enter through `kb_set_pencil`).
 
 The physics restated here (which operators enter which block with which coefficient):
@@ -119,8 +119,8 @@ class PhysicsParams:
             bad.append("Ek = 0 (inviscid)")
         if not self.hydro:
             bad.append("hydro = 0")
-        if self.forcing not in (0, 7):
-            bad.append("forcing = %d (boundary rows of that mode)" % self.forcing)
+        if self.forcing not in (0, 7, 9, 10):
+            bad.append("forcing = %d (the reference's own code for it refers to undefined names)" % self.forcing)
         if self.thermal and self.ThermaD <= 0:
             bad.append("thermal = 1 with ThermaD <= 0")
         if self.thermal and self.heating not in ("differential", "internal"):
@@ -319,9 +319,11 @@ def _block_of(sec, l):
     return None if k.size == 0 else base + int(k[0])
 
 
-def _boundary_rows(pp):
+def _boundary_rows(pp, l=None):
     """Dense boundary rows per section (assemble.py:1188-1345, non-anelastic: the log-density
-    terms vanish) and the number of them (= the rows submatrices.py:582-588 leaves empty)."""
+    terms vanish); their number is the number of rows submatrices.py:582-588 leaves empty.  Only the
+    radial boundary-flow forcing (forcing = 9) with a stress-free outer boundary makes them depend on
+    the degree `l` (assemble.py:1236-1241)."""
     ric = pp.ricb if pp.ricb > 0 else -pp.rcmb
     Ta = endpoint_table(-1, pp.N - 1, 4, ric, pp.rcmb)
     Tb = endpoint_table(1, pp.N - 1, 5, ric, pp.rcmb)
@@ -333,7 +335,11 @@ def _boundary_rows(pp):
         Tbu, Tbv, Tbh = Tb[ixu::2, :], Tb[ixv::2, :], Tb[ixu::2, :]
     rows = {}
     u = [Tbu[:, 0]]
-    u.append(pp.rcmb * Tbu[:, 2] - 0. * Tbu[:, 1] if pp.bco == 0 else Tbu[:, 1])
+    if pp.forcing == 9:
+        L = l * (l + 1)
+        u.append(Tbu[:, 2] - (2 - L) * Tbu[:, 0] / pp.rcmb ** 2 if pp.bco == 0 else Tbu[:, 1] + Tbu[:, 0])
+    else:
+        u.append(pp.rcmb * Tbu[:, 2] - 0. * Tbu[:, 1] if pp.bco == 0 else Tbu[:, 1])
     v = [-pp.rcmb * Tbv[:, 1] + (1 + pp.rcmb * 0.) * Tbv[:, 0] if pp.bco == 0 else Tbv[:, 0]]
     h = [Tbh[:, 0] if pp.bco_thermal == 0 else Tbh[:, 1]]
     if pp.ricb > 0:
@@ -443,7 +449,8 @@ def _finish(b, pp, secs, with_bc):
     br_bc = np.full(nbr, -1, dtype=np.int32)
     bc_rows = np.zeros((0, pp.N1))
     if with_bc:
-        rows = _boundary_rows(pp)
+        per_degree = pp.forcing == 9 and pp.bco == 0  # the only set-up whose boundary rows depend on l
+        rows = _boundary_rows(pp, 2)
         first = {}
         stack = []
         at = 0
@@ -451,10 +458,17 @@ def _finish(b, pp, secs, with_bc):
             first[name] = at
             stack.append(rows[name])
             at += rows[name].shape[0]
-        bc_rows = np.vstack(stack)
         for name, (base, degs) in secs.items():
             br_chop[base:base + len(degs)] = rows[name].shape[0]
             br_bc[base:base + len(degs)] = first[name]
+        if per_degree:
+            base, degs = secs["u"]
+            for k, l in enumerate(degs):
+                r = _boundary_rows(pp, int(l))["u"]
+                br_bc[base + k] = at
+                stack.append(r)
+                at += r.shape[0]
+        bc_rows = np.vstack(stack)
     meta = {"sections": {k: (int(v[0]), [int(x) for x in v[1]]) for k, v in secs.items()}}
     return b.finish(nbr, br_chop, br_bc, bc_rows, meta)
 
@@ -465,12 +479,23 @@ def forcing_vector(pp: PhysicsParams):
     entries, in the outer and inner boundary rows of the toroidal l = 1 block (m = 0, axial) or of the
     poloidal l = 2 block (m = 2), no-slip boundaries, symm = 1."""
     pp.check_supported()
+    secs = _sections(pp)
+    b = np.zeros(pp.sizmat, dtype=np.complex128)
+    if pp.forcing in (9, 10):
+        # radial velocity forcing at the boundaries, poloidal l = 2 (forcing = 9, m = 2: assemble.py:360-390) or
+        # l = m (forcing = 10, unit amplitude at the outer boundary: assemble.py:392-422)
+        if pp.symm != 1 or (pp.forcing == 9 and not (pp.m == 2 and pp.bci == 1)):
+            raise ValueError("radial boundary forcing needs symm = 1 (forcing = 9: also m = 2 and bci = 1)")
+        l = 2 if pp.forcing == 9 else pp.m
+        L = l * (l + 1)
+        row = _block_of(secs["u"], l) * pp.N1
+        b[row] = pp.forcing_amplitude_cmb * pp.rcmb / L if pp.forcing == 9 else 1. / L * 1.0
+        b[row + 1] = pp.forcing_amplitude_icb * pp.ricb / L if pp.forcing == 9 else 0.0
+        return b
     if pp.forcing != 7:
         raise NotImplementedError("forcing vector of forcing = %d" % pp.forcing)
     if not (pp.symm == 1 and pp.bci == 1 and pp.bco == 1 and pp.m in (0, 2)):
         raise ValueError("longitudinal libration needs m = 0 or 2, symm = 1 and no-slip boundaries")
-    secs = _sections(pp)
-    b = np.zeros(pp.sizmat, dtype=np.complex128)
     w = pp.forcing_frequency
     if pp.m == 0:
         row = _block_of(secs["v"], 1) * pp.N1

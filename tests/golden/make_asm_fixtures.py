@@ -38,6 +38,14 @@ NEW_CASES = {
                            ["forcing=7", "m=2", "symm=1", "N=24", "lmax=25", "forcing_frequency=0.37"]),
     "asm_fullsphere_stressfree": ("tests/jones2000/params.jones",
                                   ["N=48", "lmax=32", "bco=0", "heating='differential'", "Ra_gap=1e6"]),
+    # the other forcing modes that work in the reference: radial boundary-flow forcing
+    "asm_forcing9": ("tests/spinover/params.spinover",
+                     ["forcing=9", "m=2", "symm=1", "N=24", "forcing_amplitude_icb=0.7", "forcing_amplitude_cmb=1.3",
+                      "forcing_frequency=0.61"]),
+    "asm_forcing9_stressfree": ("tests/spinover/params.spinover",
+                                ["forcing=9", "m=2", "symm=1", "N=24", "bco=0", "forcing_amplitude_icb=0.7",
+                                 "forcing_frequency=0.61"]),
+    "asm_forcing10": ("tests/spinover/params.spinover", ["forcing=10", "m=3", "symm=1", "N=24", "forcing_frequency=-0.45"]),
 }
 EXISTING = ["spinover", "dormy", "jones", "forced_small", "m0_small"]
 
@@ -62,7 +70,7 @@ def main():
         os.makedirs(out, exist_ok=True)
         for fn in ("operators.npz", "asm_params.json"):
             shutil.copy(os.path.join(tmp, fn), os.path.join(out, fn))
-        for fn in ("A.npz", "B.npz"):
+        for fn in ("A.npz", "B.npz", "B_forced.npz"):
             src = os.path.join(tmp, fn)
             if not os.path.exists(src):
                 continue
