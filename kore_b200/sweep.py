@@ -115,3 +115,39 @@ def parameter_sweep(pp, operators, cases, nev, which="TM", device=0, rank=0, wor
             lam, X, info = s.eigs(nev, which=which, target=tau, want_vectors=want_vectors, **kw)
             out.append((case, lam, X, info))
     return out
+
+
+def track_mode(pp, operators, cases, tau0, nev=3, which="TM", device=0, solver_factory=None, **kw):
+    """Follow ONE eigenmode through a sequence of parameter sets (the reference's `track_target = 1` mechanism:
+    spin_doctor.py:323-331 writes the eigenvalue closest to the current target to the file `track_target`,
+    parameters.py:316-321 reads it back as the target of the next run of the shell loop, tools/subramp.sh:59-141).
+    `cases` as in `parameter_sweep` (without "tau"); the target of the first case is `tau0`, the target of every
+    later case is the eigenvalue tracked in the previous one; of the `nev` pairs computed around the target the one
+    closest to it is the tracked mode.  Every pencil is assembled on the GPU; a ramp in Ek, Ra or the boundary
+    conditions reuses the same radial operators throughout (the reference re-runs submatrices.py and
+    assemble.py at every step of the ramp).
+
+    Returns [(case, tracked eigenvalue, all eigenvalues, info)]."""
+    from . import assembly as _asm
+    from . import chain as _chain
+    make = solver_factory or _lib.Solver
+    out = []
+    tau = complex(tau0)
+    with make(device) as s:
+        bnorm_of = {}
+        for case in cases:
+            q = _asm.PhysicsParams.from_dict({**pp.__dict__, **case})
+            q.check_supported()
+            key = (q.m, q.lmax, q.symm, q.thermal, q.heating)
+            res = _asm.assemble(s, q, operators, bnorm=bnorm_of.get(key))
+            bnorm_of[key] = res["bnorm"]
+            perm, nodeptr = _chain.chain_from_params(q.N1, q.m, q.lmax, q.symm, -1, q.hydro, 0, q.thermal, 0)
+            s.set_chain(perm, nodeptr)
+            s.factor(tau)
+            lam, _, info = s.eigs(nev, which=which, target=tau, want_vectors=False, **kw)
+            if len(lam) == 0:
+                raise RuntimeError("no converged eigenpair at %r (target %r)" % (case, tau))
+            tracked = lam[int(np.argmin(np.abs(lam - tau)))]
+            out.append((case, tracked, lam, info))
+            tau = complex(tracked)
+    return out

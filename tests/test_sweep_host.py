@@ -73,3 +73,25 @@ def test_parameter_sweep_over_m_and_symmetry():
     assert [c for c, *_ in r0] == cases[0::2] and [c for c, *_ in r1] == cases[1::2]
     for (c, lam, _, _), full in zip(r0 + r1, [out[0], out[2], out[1], out[3]]):
         assert np.allclose(np.sort_complex(lam), np.sort_complex(full[1]), rtol=0, atol=1e-13)
+
+
+def test_track_mode_follows_the_spinover_mode_down_in_ekman_number():
+    # the spin-over mode of the spin-over fixture's physics at a small truncation, Ek from 1e-3 down to 4e-4: the
+    # same radial operators at every step, only the viscous factor changes; the tracked eigenvalue is the mode
+    # closest to the previous one and moves smoothly (damping ~ Ek^(1/2))
+    d = os.path.join(GOLDEN, "asm_mixed_bc")  # N = 24 operators (hydro)
+    ops = asm.load_operators_npz(os.path.join(d, "operators.npz"))
+    base = asm.PhysicsParams.from_dict(json.load(open(os.path.join(GOLDEN, "spinover", "asm_params.json"))))
+    pp = asm.PhysicsParams.from_dict({**base.__dict__, "N": 24, "lmax": 24})
+    eks = [1e-3, 8e-4, 6e-4, 4e-4]
+    cases = [{"Ek": e, "ViscosD": e} for e in eks]
+    lam_spin = complex(*json.load(open(os.path.join(GOLDEN, "spinover", "meta.json")))["reference_golden"]["eig"])
+    out = sweep.track_mode(pp, ops, cases, lam_spin, nev=3, solver_factory=OracleSolver)
+    tracked = np.array([t for _, t, _, _ in out])
+    # first step: the N = 24 truncation still has the N = 68 fixture's spin-over mode to 1e-5
+    assert abs(tracked[0] - lam_spin) < 1e-5 * abs(lam_spin)
+    # the damping falls with Ek, smoothly; the frequency stays near 1
+    assert np.all(np.diff(tracked.real) > 0) and np.all(tracked.real < 0)
+    assert np.all(np.abs(np.diff(tracked)) < 0.03) and np.all(np.abs(tracked.imag - 1.0) < 0.02)
+    ratio = tracked.real[-1] / tracked.real[0]
+    assert 0.55 < ratio < 0.75  # (4e-4 / 1e-3)^(1/2) = 0.63
