@@ -21,10 +21,12 @@ coefficient: a group is ``s_k * (... s_1 * ((c_0 x_0 + c_1 x_1) + c_2 x_2 ...))`
 evaluators (the kernel, and the NumPy model in tests/assembly_model.py) perform exactly these
 operations, so the assembled CSR equals the reference's bit for bit (tests/test_assembly.py).
 
-Scope: hydrodynamic (sections u, v) and Boussinesq thermal (section h) problems, viscous,
+Scope: hydrodynamic (sections u, v), Boussinesq thermal (section h) and -- to rounding, not to the
+bit, see `_magnetic_blocks` -- magnetic (sections f, g; axial or dipole background field, insulating
+boundaries) problems, viscous,
 with or without inner core, eigenvalue (forcing = 0) and forced runs (forcing = 7, 9, 10: the modes
-that work in the reference; A and the forcing vector) -- BASELINE.json configs 1, 2, 3 and 5.  Magnetic, compositional, anelastic and inviscid set-ups raise
-NotImplementedError (their pencils still enter through `kb_set_pencil`).
+that work in the reference; A and the forcing vector) -- BASELINE.json configs 1 to 5.  Other background fields and magnetic boundary conditions, compositional, anelastic
+and inviscid set-ups raise NotImplementedError (their pencils still enter through `kb_set_pencil`).
 
 The physics restated here (which operators enter which block with which coefficient):
 momentum equation operators.py:22-195, buoyancy :386-405, heat equation :699-775; block
@@ -72,6 +74,12 @@ class PhysicsParams:
     ViscosD: float = 1e-3
     Beyonce: float = 0.0
     ThermaD: float = 0.0
+    # magnetic runs (parameters.py:103-137, 275-278)
+    B0: str = "axial"
+    innercore: str = "insulator"
+    mantle: str = "insulator"
+    Hendrik: float = 0.0
+    MagnetD: float = 0.0
 
     @classmethod
     def from_modules(cls, par, ut=None):
@@ -105,12 +113,24 @@ class PhysicsParams:
     def sizmat(self):
         return self.N1 * self.nb * (2 * self.hydro + 2 * self.magnetic + self.thermal + self.compositional)
 
+    @property
+    def dipole(self):
+        """the background field whose equations carry two more powers of r (operators.py: `cdipole`)"""
+        return bool(self.magnetic) and self.B0 == "dipole"
+
     def check_supported(self):
         if (self.lmax - self.m + 1) % 2:
             raise ValueError("lmax - m + 1 must be even (parameters.py:301-303): lmax = %d, m = %d" % (self.lmax, self.m))
         bad = []
         if self.magnetic:
-            bad.append("magnetic = 1")
+            if self.B0 not in ("axial", "dipole"):
+                bad.append("B0 = %r" % (self.B0,))
+            if self.innercore != "insulator" or self.mantle != "insulator":
+                bad.append("innercore / mantle other than 'insulator'")
+            if self.ricb <= 0:
+                bad.append("magnetic = 1 without inner core")
+            if self.forcing != 0:
+                bad.append("magnetic = 1 with forcing")
         if self.compositional:
             bad.append("compositional = 1")
         if self.anelastic:
@@ -309,7 +329,7 @@ def _lin(b, *terms):
 
 
 def _sections(pp):
-    secs = section_degrees(pp.m, pp.lmax, pp.symm, -1, pp.hydro, 0, pp.thermal, 0)
+    secs = section_degrees(pp.m, pp.lmax, pp.symm, -1, pp.hydro, pp.magnetic, pp.thermal, 0)
     return {name: (base * pp.nb, np.asarray(degs)) for (name, base, degs) in secs}
 
 
@@ -348,6 +368,11 @@ def _boundary_rows(pp, l=None):
         v.append(-pp.ricb * Ta[:, 1] + (1 + pp.ricb * 0.) * Ta[:, 0] if pp.bci == 0 else Ta[:, 0])
         h.append(Ta[:, 0] if pp.bci_thermal == 0 else Ta[:, 1])
     rows["u"], rows["v"], rows["h"] = np.array(u), np.array(v), np.array(h)
+    if pp.magnetic:
+        # insulating inner core and mantle: the field matches a potential field on either side
+        # (assemble.py:1545-1572 inner row, 1479-1536 outer row); inner boundary first
+        rows["f"] = np.array([l * Ta[:, 0] - pp.ricb * Ta[:, 1], (l + 1) * Tb[:, 0] + pp.rcmb * Tb[:, 1]])
+        rows["g"] = np.array([Ta[:, 0], Tb[:, 0]])
     return rows
 
 
@@ -369,23 +394,27 @@ def build_program_A(pp: PhysicsParams, operators: dict) -> AsmProgram:
     m, wf = pp.m, pp.wf
     RE, IM = 0, 1
     G, V, Bf, Td = pp.Gaspard, pp.ViscosD, pp.Beyonce, pp.ThermaD
+    # with a dipole background field the momentum equations are multiplied by two (2curl) / three (1curl)
+    # more powers of r (operators.py:33-43 and every `cdipole` branch)
+    U = lambda k, d: "r%d_D%d_u" % (k + (2 if pp.dipole else 0), d)  # noqa: E731
+    W = lambda k, d: "r%d_D%d_v" % (k + (3 if pp.dipole else 0), d)  # noqa: E731
 
     for l in secs["u"][1]:  # ---- poloidal momentum (2curl) rows
         l = int(l)
         L = l * (l + 1)
         r = _block_of(secs["u"], l)
-        b.add(r, r, Group(IM, +1, [L, wf], _lin(b, (L, "r2_D0_u"), (-2, "r3_D1_u"), (-1, "r4_D2_u"))))
-        b.add(r, r, Group(IM, +1, [2 * m, G], _lin(b, (-L, "r2_D0_u"), (2, "r3_D1_u"), (1, "r4_D2_u"))))
-        b.add(r, r, Group(RE, -1, [L, V], _lin(b, (-L * (l + 2) * (l - 1), "r0_D0_u"), (2 * L, "r2_D2_u"),
-                                               (-4, "r3_D3_u"), (-1, "r4_D4_u"))))
+        b.add(r, r, Group(IM, +1, [L, wf], _lin(b, (L, U(2, 0)), (-2, U(3, 1)), (-1, U(4, 2)))))
+        b.add(r, r, Group(IM, +1, [2 * m, G], _lin(b, (-L, U(2, 0)), (2, U(3, 1)), (1, U(4, 2)))))
+        b.add(r, r, Group(RE, -1, [L, V], _lin(b, (-L * (l + 2) * (l - 1), U(0, 0)), (2 * L, U(2, 2)),
+                                               (-4, U(3, 3)), (-1, U(4, 4)))))
         c = _block_of(secs["v"], l - 1)
         if c is not None:
-            b.add(r, c, Group(RE, +1, [2 * _coriolis_down(l, m), G], _lin(b, (l - 1, "r3_D0_u"), (-1, "r4_D1_u"))))
+            b.add(r, c, Group(RE, +1, [2 * _coriolis_down(l, m), G], _lin(b, (l - 1, U(3, 0)), (-1, U(4, 1)))))
         c = _block_of(secs["v"], l + 1)
         if c is not None:
-            b.add(r, c, Group(RE, +1, [2 * _coriolis_up(l, m), G], _lin(b, (-(l + 2), "r3_D0_u"), (-1, "r4_D1_u"))))
+            b.add(r, c, Group(RE, +1, [2 * _coriolis_up(l, m), G], _lin(b, (-(l + 2), U(3, 0)), (-1, U(4, 1)))))
         if pp.thermal:
-            b.add(r, _block_of(secs["h"], l), Group(RE, +1, [L, Bf], _lin(b, (1, "r4_D0_u"))))
+            b.add(r, _block_of(secs["h"], l), Group(RE, +1, [L, Bf], _lin(b, (1, U(4, 0)))))
 
     for l in secs["v"][1]:  # ---- toroidal momentum (1curl) rows
         l = int(l)
@@ -393,13 +422,13 @@ def build_program_A(pp: PhysicsParams, operators: dict) -> AsmProgram:
         r = _block_of(secs["v"], l)
         c = _block_of(secs["u"], l - 1)
         if c is not None:
-            b.add(r, c, Group(RE, +1, [2 * _coriolis_down(l, m), G], _lin(b, (l - 1, "r1_D0_v"), (-1, "r2_D1_v"))))
+            b.add(r, c, Group(RE, +1, [2 * _coriolis_down(l, m), G], _lin(b, (l - 1, W(1, 0)), (-1, W(2, 1)))))
         c = _block_of(secs["u"], l + 1)
         if c is not None:
-            b.add(r, c, Group(RE, +1, [2 * _coriolis_up(l, m), G], _lin(b, (-(l + 2), "r1_D0_v"), (-1, "r2_D1_v"))))
-        b.add(r, r, Group(IM, +1, [L, wf], _lin(b, (1, "r2_D0_v"))))
-        b.add(r, r, Group(IM, +1, [-2 * m, G], _lin(b, (1, "r2_D0_v"))))
-        b.add(r, r, Group(RE, -1, [L, V], _lin(b, (-L, "r0_D0_v"), (2, "r1_D1_v"), (1, "r2_D2_v"))))
+            b.add(r, c, Group(RE, +1, [2 * _coriolis_up(l, m), G], _lin(b, (-(l + 2), W(1, 0)), (-1, W(2, 1)))))
+        b.add(r, r, Group(IM, +1, [L, wf], _lin(b, (1, W(2, 0)))))
+        b.add(r, r, Group(IM, +1, [-2 * m, G], _lin(b, (1, W(2, 0)))))
+        b.add(r, r, Group(RE, -1, [L, V], _lin(b, (-L, W(0, 0)), (2, W(1, 1)), (1, W(2, 2)))))
 
     if pp.thermal:  # ---- heat equation rows
         gap = pp.rcmb - pp.ricb
@@ -418,7 +447,121 @@ def build_program_A(pp: PhysicsParams, operators: dict) -> AsmProgram:
                 b.add(r, r, Group(RE, +1, [Td], _lin(b, (-L, "r0_D0_h"), (2, "r1_D1_h"), (1, "r2_D2_h"))))
                 b.add(r, r, Group(IM, -1, [wf], _lin(b, (1, "r2_D0_h"))))
 
+    if pp.magnetic:
+        _magnetic_blocks(b, pp, secs)
+
     return _finish(b, pp, secs, with_bc=True)
+
+
+def _magnetic_blocks(b, pp, secs):
+    """Lorentz force in the momentum rows, induction and magnetic diffusion in the field rows, for an
+    antisymmetric background field (axial or dipole): only the dipole-type couplings (degree l to l +- 1
+    across the families, l to l inside a family) exist (operators.py:198-384 lorentz, :433-468 b,
+    :471-643 induction, :646-692 magnetic_diffusion; placement assemble.py:640-668, 765-797, 820-1008).
+
+    NOT bit-compatible with the reference, unlike the rest of the program: the reference evaluates the
+    induction coefficients in numpy.float128 (operators.py:479) and nests its sums; here every block is
+    ONE left-to-right sum with double coefficients (the induction ones rounded from the same extended
+    precision products), which agrees with the reference's entries to a few ulp of the block's largest
+    term (tests: 1e-13 of the block maximum; eigenvalues to 1e-9)."""
+    m, wf = pp.m, pp.wf
+    RE, IM = 0, 1
+    H, Md = pp.Hendrik, pp.MagnetD
+    d2 = 2 if pp.dipole else 0   # extra powers of r in the 2curl momentum and in the poloidal induction rows
+    d3 = 3 if pp.dipole else 0   # ... in the 1curl momentum and in the toroidal induction rows
+    u_ = lambda k, h, d: "r%d_h%d_D%d_u" % (k + d2, h, d)  # noqa: E731
+    v_ = lambda k, h, d: "r%d_h%d_D%d_v" % (k + d3, h, d)  # noqa: E731
+    f_ = lambda k, h, d: "r%d_h%d_D%d_f" % (k + d2, h, d)  # noqa: E731
+    g_ = lambda k, h, d: "r%d_h%d_D%d_g" % (k + d3, h, d)  # noqa: E731
+    sq = np.sqrt
+
+    for l in secs["u"][1]:  # ---- Lorentz force, poloidal momentum rows
+        l = int(l)
+        L = l * (l + 1)
+        r = _block_of(secs["u"], l)
+        c = _block_of(secs["f"], l - 1)
+        if c is not None:
+            C = sq(l ** 2 - m ** 2) * (l ** 2 - 1) / (2 * l - 1)
+            b.add(r, c, Group(RE, +1, [C, H], _lin(
+                b, (-2 * (l ** 2 + 2), u_(1, 0, 1)), (-2 * (l - 2), u_(2, 1, 1)), (-(l - 4), u_(2, 0, 2)), (-(l - 2), u_(3, 1, 2)),
+                (L * (l + 2), u_(0, 0, 0)), (L * (l - 4), u_(1, 1, 0)), (l, u_(2, 2, 0)), (l, u_(3, 3, 0)), (2, u_(3, 0, 3)))))
+        c = _block_of(secs["f"], l + 1)
+        if c is not None:
+            C = sq((1 + l + m) * (1 + l - m)) * l * (l + 2) / (2 * l + 3)
+            b.add(r, c, Group(RE, +1, [C, H], _lin(
+                b, (-2 * (l ** 2 + 2 * l + 3), u_(1, 0, 1)), (2 * (l + 3), u_(2, 1, 1)), (l + 5, u_(2, 0, 2)), (l + 3, u_(3, 1, 2)),
+                (-L * (l - 1), u_(0, 0, 0)), (-L * (l + 5), u_(1, 1, 0)), (-(l + 1), u_(2, 2, 0)), (-(l + 1), u_(3, 3, 0)),
+                (2, u_(3, 0, 3)))))
+        c = _block_of(secs["g"], l)
+        b.add(r, c, Group(IM, +1, [2 * m, H], _lin(
+            b, (-1, u_(1, 0, 0)), (-(l ** 2 + l - 1), u_(2, 1, 0)), (1, u_(2, 0, 1)), (1, u_(3, 1, 1)), (1, u_(3, 0, 2)))))
+
+    for l in secs["v"][1]:  # ---- Lorentz force, toroidal momentum rows
+        l = int(l)
+        L = l * (l + 1)
+        r = _block_of(secs["v"], l)
+        c = _block_of(secs["f"], l)
+        b.add(r, c, Group(IM, +1, [m, H], _lin(
+            b, (4, v_(0, 0, 1)), (-2 * L, v_(0, 1, 0)), (-L, v_(1, 2, 0)), (2, v_(1, 0, 2)))))
+        c = _block_of(secs["g"], l - 1)
+        if c is not None:
+            C = sq((l - m) * (l + m)) * (l ** 2 - 1) / (2 * l - 1)
+            b.add(r, c, Group(RE, +1, [C, H], _lin(b, (l - 2, v_(0, 0, 0)), (l, v_(1, 1, 0)), (-2, v_(1, 0, 1)))))
+        c = _block_of(secs["g"], l + 1)
+        if c is not None:
+            C = -sq((l + m + 1) * (l + 1 - m)) * l * (l + 2) / (2 * l + 3)
+            b.add(r, c, Group(RE, +1, [C, H], _lin(b, (l + 3, v_(0, 0, 0)), (l + 1, v_(1, 1, 0)), (2, v_(1, 0, 1)))))
+
+    ld = np.longdouble
+
+    def ext(C, *terms):
+        # coefficients formed in extended precision as the reference does, then rounded once
+        return [(float(ld(C) * ld(c)), lab) for c, lab in terms]
+
+    eta = lambda k, p, d, s_: "r%d_eta%d_D%d_%s" % (k + (d2 if s_ == "f" else d3), p, d, s_)  # noqa: E731
+    for l in secs["f"][1]:  # ---- poloidal field rows: induction by the flow, diffusion, time derivative
+        l = int(l)
+        L = l * (l + 1)
+        lx = ld(l)
+        r = _block_of(secs["f"], l)
+        c = _block_of(secs["u"], l - 1)
+        if c is not None:
+            C = np.sqrt(lx ** 2 - m ** 2) * (lx ** 2 - 1) / (2 * lx - 1)
+            b.add(r, c, Group(RE, +1, [], _lin(b, *ext(C, (lx - 2, f_(0, 0, 0)), (lx, f_(1, 1, 0)), (-2, f_(1, 0, 1))))))
+        c = _block_of(secs["u"], l + 1)
+        if c is not None:
+            C = np.sqrt((lx + 1) ** 2 - m ** 2) * lx * (lx + 2) / (2 * lx + 3)
+            b.add(r, c, Group(RE, +1, [], _lin(b, *ext(C, (-(lx + 3), f_(0, 0, 0)), (-(lx + 1), f_(1, 1, 0)), (-2, f_(1, 0, 1))))))
+        c = _block_of(secs["v"], l)
+        b.add(r, c, Group(IM, +1, [], _lin(b, (-2 * m, f_(1, 0, 0)))))
+        b.add(r, r, Group(IM, +1, [L, wf], _lin(b, (1, "r%d_D0_f" % (2 + d2)))))
+        b.add(r, r, Group(RE, -1, [L, Md], _lin(b, (-L, eta(0, 0, 0, "f")), (2, eta(1, 0, 1, "f")), (1, eta(2, 0, 2, "f")))))
+
+    sg = -1 if pp.dipole else 1  # sign of the eta' terms of the toroidal diffusion (operators.py:684, 689)
+    for l in secs["g"][1]:  # ---- toroidal field rows
+        l = int(l)
+        L = l * (l + 1)
+        lx = ld(l)
+        r = _block_of(secs["g"], l)
+        c = _block_of(secs["u"], l)
+        if pp.dipole:
+            terms = ((1, g_(0, 0, 1)), (1, g_(1, 1, 1)), (-(lx ** 2 + lx + 1), g_(-1, 0, 0)), (1, g_(0, 1, 0)),
+                     (ld(L) / 2, g_(1, 2, 0)), (1, g_(1, 0, 2)))
+        else:
+            terms = ((1, g_(0, 0, 1)), (1, g_(1, 1, 1)), (-(ld(L) + 1), "q1_h0_D0_g"), (1, g_(0, 1, 0)),
+                     (ld(L) / 2, g_(1, 2, 0)), (1, g_(1, 0, 2)))
+        b.add(r, c, Group(IM, +1, [], _lin(b, *ext(2 * m, *terms))))
+        c = _block_of(secs["v"], l - 1)
+        if c is not None:
+            C = (lx ** 2 - 1) * np.sqrt(lx ** 2 - m ** 2) / (2 * lx - 1)
+            b.add(r, c, Group(RE, +1, [], _lin(b, *ext(C, (lx, g_(0, 0, 0)), (-2, g_(1, 0, 1)), (lx - 2, g_(1, 1, 0))))))
+        c = _block_of(secs["v"], l + 1)
+        if c is not None:
+            C = lx * (lx + 2) * np.sqrt((lx + 1) ** 2 - m ** 2) / (3 + 2 * lx)
+            b.add(r, c, Group(RE, +1, [], _lin(b, *ext(C, (-2, g_(1, 0, 1)), (-(lx + 1), g_(0, 0, 0)), (-(lx + 3), g_(1, 1, 0))))))
+        b.add(r, r, Group(IM, +1, [L, wf], _lin(b, (1, "r%d_D0_g" % (2 + d3)))))
+        b.add(r, r, Group(RE, -1, [L, Md], _lin(b, (2, eta(1, 0, 1, "g")), (-L, eta(0, 0, 0, "g")), (1, eta(2, 0, 2, "g")),
+                                                (sg, eta(1, 1, 0, "g")), (sg, eta(2, 1, 1, "g")))))
 
 
 def build_program_B(pp: PhysicsParams, operators: dict) -> AsmProgram:
@@ -430,11 +573,18 @@ def build_program_B(pp: PhysicsParams, operators: dict) -> AsmProgram:
         l = int(l)
         L = l * (l + 1)
         r = _block_of(secs["u"], l)
-        b.add(r, r, Group(0, -1, [L], _lin(b, (L, "r2_D0_u"), (-2, "r3_D1_u"), (-1, "r4_D2_u"))))
+        k = 2 if pp.dipole else 0
+        b.add(r, r, Group(0, -1, [L], _lin(b, (L, "r%d_D0_u" % (2 + k)), (-2, "r%d_D1_u" % (3 + k)), (-1, "r%d_D2_u" % (4 + k)))))
     for l in secs["v"][1]:
         l = int(l)
         r = _block_of(secs["v"], l)
-        b.add(r, r, Group(0, -1, [l * (l + 1)], _lin(b, (1, "r2_D0_v"))))
+        b.add(r, r, Group(0, -1, [l * (l + 1)], _lin(b, (1, "r%d_D0_v" % (5 if pp.dipole else 2)))))
+    if pp.magnetic:
+        for name, lab in (("f", "r%d_D0_f" % (4 if pp.dipole else 2)), ("g", "r%d_D0_g" % (5 if pp.dipole else 2))):
+            for l in secs[name][1]:
+                l = int(l)
+                r = _block_of(secs[name], l)
+                b.add(r, r, Group(0, -1, [l * (l + 1)], _lin(b, (1, lab))))
     if pp.thermal:
         lab = "r3_D0_h" if pp.heating == "differential" else "r2_D0_h"
         for l in secs["h"][1]:
@@ -449,7 +599,9 @@ def _finish(b, pp, secs, with_bc):
     br_bc = np.full(nbr, -1, dtype=np.int32)
     bc_rows = np.zeros((0, pp.N1))
     if with_bc:
-        per_degree = pp.forcing == 9 and pp.bco == 0  # the only set-up whose boundary rows depend on l
+        # sections whose boundary rows depend on the degree: u under forcing = 9 with a stress-free outer
+        # boundary, f (poloidal field) always
+        per_degree = (["u"] if pp.forcing == 9 and pp.bco == 0 else []) + (["f"] if pp.magnetic else [])
         rows = _boundary_rows(pp, 2)
         first = {}
         stack = []
@@ -461,10 +613,10 @@ def _finish(b, pp, secs, with_bc):
         for name, (base, degs) in secs.items():
             br_chop[base:base + len(degs)] = rows[name].shape[0]
             br_bc[base:base + len(degs)] = first[name]
-        if per_degree:
-            base, degs = secs["u"]
+        for name in per_degree:
+            base, degs = secs[name]
             for k, l in enumerate(degs):
-                r = _boundary_rows(pp, int(l))["u"]
+                r = _boundary_rows(pp, int(l))[name]
                 br_bc[base + k] = at
                 stack.append(r)
                 at += r.shape[0]

@@ -18,8 +18,8 @@ facades in kore_b200/eps.py; everything else keeps the reference's file formats.
 
 With `-kb_assemble` (or when there is no A.npz but the `*.mtx` radial operators of
 bin/submatrices.py are present) the run skips bin/assemble.py as well: the pencil is assembled on
-the GPU from the radial operators (kore_b200/assembly.py; hydrodynamic and Boussinesq thermal
-set-ups) -- the same matrices, bit for bit, without A.npz / B.npz ever being written or read.
+the GPU from the radial operators (kore_b200/assembly.py; hydrodynamic, Boussinesq thermal and
+axial / dipole magnetic set-ups) -- the same matrices, bit for bit, without A.npz / B.npz ever being written or read.
 `-kb_diagnose` adds power_balance.dat (kore_b200/diagnostics.py), `-kb_npz` adds eigenpairs.npz
 (eigenvalues, the complex solution block and the row ranges of the fields, binary).
 The forced right-hand side comes from B_forced.npz when it exists, else (forcing = 7, libration) it

@@ -46,8 +46,12 @@ NEW_CASES = {
                                 ["forcing=9", "m=2", "symm=1", "N=24", "bco=0", "forcing_amplitude_icb=0.7",
                                  "forcing_frequency=0.61"]),
     "asm_forcing10": ("tests/spinover/params.spinover", ["forcing=10", "m=3", "symm=1", "N=24", "forcing_frequency=-0.45"]),
+    # magnetic runs (axial and dipole background field, insulating boundaries): rounding-level, not bit-level, parity
+    "asm_magnetic_axial": ("tests/spinover/params.spinover", ["magnetic=1", "N=24", "m=2", "symm=1"]),
+    "asm_magnetic_dipole_thermal": ("tests/dormy2004/params.dormy04",
+                                    ["magnetic=1", "B0='dipole'", "N=24", "lmax=24", "m=3", "forcing=0"]),
 }
-EXISTING = ["spinover", "dormy", "jones", "forced_small", "m0_small"]
+EXISTING = ["spinover", "dormy", "jones", "forced_small", "m0_small", "magnetic_small"]
 
 
 def same_npz(a, b):

@@ -1,0 +1,132 @@
+"""Device-side assembly of MAGNETIC pencils (axial or dipole background field, insulating inner core and
+mantle; BASELINE.json config 4): kore_b200/assembly.py `_magnetic_blocks`.
+
+Parity here is to ROUNDING, not to the bit as for the hydrodynamic and thermal blocks (tests/test_assembly.py):
+the reference evaluates its induction coefficients in numpy.float128 (operators.py:479) and nests the sums of
+the Lorentz terms, the assembly program is one left-to-right double sum per block.  Bars: B bit for bit; every
+block of A within 1e-13 of its own largest entry (observed 4e-16; the hydrodynamic / thermal blocks of the same
+matrices stay bit-identical); eigenvalues of the assembled pencil within 1e-9 of the oracle's on the
+reference-assembled one.
+
+The GPU tests of this file were written after the round's GPU budget was spent: the kernels they run are the
+ones tests/test_assembly.py validates (the assembly kernel evaluates any program; these programs have more
+groups and longer sums, nothing new), but they have not themselves run on a GPU yet -- hence this file sorts
+last."""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import assembly_model as am
+from conftest import GOLDEN, load_case
+from kore_b200 import assembly as asm
+
+CASES = ["magnetic_small", "asm_magnetic_axial", "asm_magnetic_dipole_thermal"]
+
+
+def fixture(name):
+    d = os.path.join(GOLDEN, name)
+    pj = json.load(open(os.path.join(d, "asm_params.json")))
+    pp = asm.PhysicsParams.from_dict(pj)
+    ops = asm.load_operators_npz(os.path.join(d, "operators.npz"))
+
+    def csr(fn):
+        z = np.load(os.path.join(d, fn))
+        M = sp.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=tuple(z["shape"]))
+        M.sort_indices()
+        return M
+    return pj, pp, ops, csr("A.npz"), csr("B.npz")
+
+
+def block_relative_error(A, A_ref, N1):
+    """max over the N1 x N1 blocks of |A - A_ref| / (largest |A_ref| of the block); inf for a block the reference
+    does not have."""
+    D, R = (A - A_ref).tocoo(), A_ref.tocoo()
+    nbr = A.shape[0] // N1
+    mx = np.zeros((nbr, nbr))
+    np.maximum.at(mx, (R.row // N1, R.col // N1), np.abs(R.data))
+    er = np.zeros((nbr, nbr))
+    np.maximum.at(er, (D.row // N1, D.col // N1), np.abs(D.data))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.where(mx > 0, er / np.where(mx > 0, mx, 1.0), np.where(er > 0, np.inf, 0.0))
+
+
+def model_pencil(pj, pp, ops):
+    s = 1. / pj["Bnorm"]
+    return (am.evaluate(asm.build_program_A(pp, ops).with_final_scale(s)),
+            am.evaluate(asm.build_program_B(pp, ops).with_final_scale(s)))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_magnetic_program_matches_reference_to_rounding(name):
+    pj, pp, ops, A_ref, B_ref = fixture(name)
+    A, B = model_pencil(pj, pp, ops)
+    assert np.array_equal(B.indptr, B_ref.indptr) and np.array_equal(B.indices, B_ref.indices)
+    assert np.array_equal(B.data, B_ref.data)
+    rel = block_relative_error(A, A_ref, pp.N1)
+    assert rel.max() <= 1e-13, rel.max()
+    # only blocks that involve the field differ at all; the momentum / heat blocks are the bit-exact ones
+    nf = 2 * pp.nb  # block rows (= block columns) of u and v
+    hydro = np.zeros_like(rel, dtype=bool)
+    hydro[:nf, :nf] = True
+    if pp.thermal:
+        hydro[4 * pp.nb:, :nf] = hydro[4 * pp.nb:, 4 * pp.nb:] = hydro[:nf, 4 * pp.nb:] = True
+    assert rel[hydro].max() == 0.0
+    # entries present in one pattern only are cancellations to (almost) zero
+    assert abs(A.nnz - A_ref.nnz) <= 1e-3 * A_ref.nnz
+
+
+def test_magnetic_pencil_has_the_oracles_eigenvalues():
+    # magnetic_small (dipole, N = 40): the oracle on the model-assembled pencil against the fixture's eigenvalues
+    # (the oracle on the reference-assembled pencil)
+    import kore_oracle as ko
+    pj, pp, ops, A_ref, B_ref = fixture("magnetic_small")
+    case = load_case("magnetic_small")
+    A, B = model_pencil(pj, pp, ops)
+    lam, _, _ = ko.eigs(A, B, case.tau, case.meta["nev"], case.meta["which_eigenpairs"])
+    for z in case.oracle["eig"]:
+        assert np.min(np.abs(lam - z)) <= 1e-10 * abs(z)
+
+
+def test_other_magnetic_setups_are_refused():
+    pj, pp, ops, _, _ = fixture("asm_magnetic_axial")
+    for kw in (dict(B0="Luo_S2"), dict(innercore="TWA"), dict(mantle="TWA"), dict(ricb=0.0), dict(forcing=7)):
+        q = asm.PhysicsParams.from_dict({**pp.__dict__, **kw})
+        with pytest.raises(NotImplementedError):
+            asm.build_program_A(q, ops)
+
+
+# ---------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_device_assembles_the_magnetic_program_like_the_model(lib, name):
+    pj, pp, ops, A_ref, B_ref = fixture(name)
+    A_m, B_m = model_pencil(pj, pp, ops)
+    with lib.Solver(0) as s:
+        asm.assemble(s, pp, ops, bnorm=pj["Bnorm"])
+        ip, ix, v = s.get_assembled("A")
+        A = sp.csr_matrix((v, ix, ip), shape=A_m.shape)
+        ip, ix, v = s.get_assembled("B")
+        B = sp.csr_matrix((v, ix, ip), shape=B_m.shape)
+    # the kernel and its NumPy model perform the same operations: same bits
+    assert np.array_equal(A.indptr, A_m.indptr) and np.array_equal(A.indices, A_m.indices) and np.array_equal(A.data, A_m.data)
+    assert np.array_equal(B.data, B_ref.data)
+    assert block_relative_error(A, A_ref, pp.N1).max() <= 1e-13
+
+
+@pytest.mark.gpu
+def test_device_assembled_magnetic_pencil_against_the_oracle(lib):
+    case = load_case("magnetic_small")
+    pj, pp, ops, _, _ = fixture("magnetic_small")
+    m = case.meta
+    with lib.Solver(0) as s:
+        asm.assemble(s, pp, ops, bnorm=pj["Bnorm"])
+        s.set_chain(case.perm, case.nodeptr)
+        s.factor(case.tau)
+        lam, X, info = s.eigs(m["nev"], which=m["which_eigenpairs"], target=case.tau, tol=m["tol"], maxit=m["maxit"])
+    assert info["nconv"] >= m["nev"]
+    for z in case.oracle["eig"]:
+        assert np.min(np.abs(lam - z)) <= 1e-9 * abs(z), (z, lam)
+    assert np.all(info["resid"] <= 1e-10)
