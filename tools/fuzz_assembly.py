@@ -1,0 +1,101 @@
+#!/usr/bin/env python3
+"""Randomised parity sweep of the assembly programs against the UNMODIFIED reference assembler (build
+container only: needs /root/reference).  Every trial draws a parameter set (m, symmetry, boundary conditions,
+thermal on/off with its heating mode and boundary conditions, inner core or full sphere, Ekman number, forcing
+mode, truncation), runs the reference stages through tools/make_case.py --asm and compares what
+kore_b200.assembly + the NumPy model of the kernels (tests/assembly_model.py) produce with A.npz / B.npz:
+pattern and values, bit for bit.  Usage: tools/fuzz_assembly.py [ntrials] [seed]."""
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+import scipy.sparse as sp
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import assembly_model as am  # noqa: E402
+from kore_b200 import assembly as asm  # noqa: E402
+
+
+def load(fn):
+    z = np.load(fn)
+    M = sp.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=tuple(z["shape"]))
+    M.sort_indices()
+    return M
+
+
+def same(M, R):
+    return np.array_equal(M.indptr, R.indptr) and np.array_equal(M.indices, R.indices) and np.array_equal(M.data, R.data)
+
+
+def draw(rng):
+    thermal = int(rng.integers(0, 2))
+    full = int(rng.integers(0, 4) == 0)
+    params = "tests/dormy2004/params.dormy04" if thermal else "tests/spinover/params.spinover"
+    m = int(rng.integers(0, 6))
+    symm = int(rng.choice([-1, 1]))
+    N = int(rng.choice([16, 20, 24, 28])) * (2 if full else 1)
+    nl = 2 * int(rng.integers(4, 10))
+    lmax = nl + m - 1
+    ov = ["m=%d" % m, "symm=%d" % symm, "N=%d" % N, "lmax=%d" % lmax, "Ek=%g" % (10.0 ** rng.uniform(-6, -2)),
+          "bco=%d" % rng.integers(0, 2)]
+    if full:
+        ov.append("ricb=0")
+    else:
+        ov += ["ricb=%.3f" % rng.uniform(0.1, 0.8), "bci=%d" % rng.integers(0, 2)]
+    if thermal:
+        ov += ["heating='%s'" % rng.choice(["differential", "internal"] if not full else ["internal"]),
+               "bco_thermal=%d" % rng.integers(0, 2), "Ra_gap=%g" % (10.0 ** rng.uniform(4, 7))]
+        if not full:
+            ov.append("bci_thermal=%d" % rng.integers(0, 2))
+    forcing = int(rng.choice([0, 0, 0, 10, 7]))
+    if forcing == 10 and symm == 1 and m > 0:
+        ov += ["forcing=10", "forcing_frequency=%.3f" % rng.uniform(-1.5, 1.5)]
+    elif forcing == 7 and not full:
+        ov = [o for o in ov if not o.startswith(("m=", "symm=", "lmax=", "bci=", "bco="))]
+        m = int(rng.choice([0, 2]))
+        ov += ["m=%d" % m, "symm=1", "lmax=%d" % (nl + m - 1), "bci=1", "bco=1", "forcing=7",
+               "forcing_frequency=%.3f" % rng.uniform(-1.5, 1.5), "forcing_amplitude_icb=%.2f" % rng.uniform(0, 1)]
+    return params, ov
+
+
+def main():
+    ntrials = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+    rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+    bad = 0
+    for t in range(ntrials):
+        params, ov = draw(rng)
+        out = "/tmp/asmfuzz_%d_%d" % (os.getpid(), t)
+        shutil.rmtree(out, ignore_errors=True)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_case.py"), "--params", params, "--out", out,
+                            "--asm"] + ov, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0 or not os.path.exists(os.path.join(out, "A.npz")):
+            print("trial %d: the reference itself failed on %s (skipped)" % (t, " ".join(ov)))
+            continue
+        pp = asm.PhysicsParams.from_dict(json.load(open(os.path.join(out, "asm_params.json"))))
+        ops = asm.load_operators_npz(os.path.join(out, "operators.npz"))
+        pA = asm.build_program_A(pp, ops)
+        ok = True
+        if pp.forcing == 0:
+            pB = asm.build_program_B(pp, ops)
+            bn = asm.frobenius_norm(am.evaluate(pB).data)
+            ok &= same(am.evaluate(pB.with_final_scale(1. / bn)), load(os.path.join(out, "B.npz")))
+            pA = pA.with_final_scale(1. / bn)
+        else:
+            z = np.load(os.path.join(out, "B_forced.npz"))
+            ref = np.asarray(sp.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=tuple(z["shape"])).todense()).ravel()
+            ok &= np.array_equal(asm.forcing_vector(pp), ref)
+        ok &= same(am.evaluate(pA), load(os.path.join(out, "A.npz")))
+        bad += not ok
+        print("trial %d: %s  %s" % (t, "bit-identical" if ok else "MISMATCH", " ".join(ov)), flush=True)
+        shutil.rmtree(out, ignore_errors=True)
+    print("%d mismatches in %d trials" % (bad, ntrials))
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
