@@ -25,8 +25,9 @@ Scope: hydrodynamic (sections u, v), Boussinesq thermal (section h) and -- to ro
 bit, see `_magnetic_blocks` -- magnetic (sections f, g; axial or dipole background field, insulating
 boundaries) problems, viscous,
 with or without inner core, eigenvalue (forcing = 0) and forced runs (forcing = 7, 9, 10: the modes
-that work in the reference; A and the forcing vector) -- BASELINE.json configs 1 to 5.  Other background fields and magnetic boundary conditions, compositional, anelastic
-and inviscid set-ups raise NotImplementedError (their pencils still enter through `kb_set_pencil`).
+that work in the reference; A and the forcing vector) -- BASELINE.json configs 1 to 5 -- and anelastic (density-stratified) runs without variable viscosity, bit for bit.  Other
+background fields and magnetic boundary conditions, variable viscosity, compositional and inviscid set-ups
+raise NotImplementedError (their pencils still enter through `kb_set_pencil`).
 
 The physics restated here (which operators enter which block with which coefficient):
 momentum equation operators.py:22-195, buoyancy :386-405, heat equation :699-775; block
@@ -44,6 +45,7 @@ import numpy as np
 from .chain import section_degrees
 
 MAX_SCALES = 4
+MAX_BAND = 1023  # widest operator band (2 H + 1) the assembly kernel accepts (ka_check, csrc/kb_assemble.cu)
 
 
 @dataclass
@@ -54,6 +56,11 @@ class PhysicsParams:
     thermal: int = 0
     compositional: int = 0
     anelastic: int = 0
+    variable_viscosity: int = 0
+    # anelastic runs with stress-free boundaries: d(ln rho)/dr at the inner / outer boundary (assemble.py:1195-1198;
+    # `from_modules` evaluates them with the run's own radial_profiles.py when it is importable)
+    lho1_icb: float = None
+    lho1_cmb: float = None
     m: int = 1
     lmax: int = 8
     N: int = 8
@@ -90,6 +97,12 @@ class PhysicsParams:
                 kw[f] = getattr(par, f)
         if ut is not None and hasattr(ut, "rcmb"):
             kw["rcmb"] = ut.rcmb
+        if kw.get("anelastic") and ut is not None and 0 in (kw.get("bci", 1), kw.get("bco", 1)):
+            # the two numbers the stress-free rows of an anelastic run need, computed as the reference does
+            import bc_variables as bv
+            import radial_profiles as rap
+            lho = ut.chebco_f(rap.log_density, par.N, par.ricb, ut.rcmb, 1e-9)
+            kw["lho1_icb"], kw["lho1_cmb"] = float(np.dot(lho, bv.Ta[:, 1])), float(np.dot(lho, bv.Tb[:, 1]))
         return cls(**kw)
 
     @classmethod
@@ -134,7 +147,15 @@ class PhysicsParams:
         if self.compositional:
             bad.append("compositional = 1")
         if self.anelastic:
-            bad.append("anelastic = 1")
+            if self.variable_viscosity:
+                bad.append("variable_viscosity = 1")
+            if self.magnetic:
+                bad.append("anelastic = 1 with magnetic = 1")
+            if self.ricb <= 0:
+                bad.append("anelastic = 1 without inner core")
+            if (self.bci == 0 and self.lho1_icb is None) or (self.bco == 0 and self.lho1_cmb is None):
+                bad.append("anelastic = 1 with stress-free boundaries but without lho1_icb / lho1_cmb "
+                           "(d ln(rho) / dr at the boundaries; PhysicsParams.from_modules(par, ut) computes them)")
         if self.Ek == 0:
             bad.append("Ek = 0 (inviscid)")
         if not self.hydro:
@@ -281,7 +302,7 @@ class _Builder:
             if nz.any():
                 H = max(H, int(np.abs(M.col[nz] - M.row[nz]).max()))
             csr.append(M)
-        if 2 * H + 1 > 31:
+        if 2 * H + 1 > MAX_BAND:
             raise ValueError("radial operators wider than +-15 are not supported (found +-%d)" % H)
         W = 2 * H + 1
         ops = np.zeros((max(1, len(self.labels)), N1, W))
@@ -354,18 +375,20 @@ def _boundary_rows(pp, l=None):
         ixu, ixv = (pp.m + 1 - s) % 2, (pp.m + s) % 2
         Tbu, Tbv, Tbh = Tb[ixu::2, :], Tb[ixv::2, :], Tb[ixu::2, :]
     rows = {}
+    la = pp.lho1_icb if (pp.anelastic and pp.lho1_icb is not None) else 0.
+    lb = pp.lho1_cmb if (pp.anelastic and pp.lho1_cmb is not None) else 0.
     u = [Tbu[:, 0]]
     if pp.forcing == 9:
         L = l * (l + 1)
         u.append(Tbu[:, 2] - (2 - L) * Tbu[:, 0] / pp.rcmb ** 2 if pp.bco == 0 else Tbu[:, 1] + Tbu[:, 0])
     else:
-        u.append(pp.rcmb * Tbu[:, 2] - 0. * Tbu[:, 1] if pp.bco == 0 else Tbu[:, 1])
-    v = [-pp.rcmb * Tbv[:, 1] + (1 + pp.rcmb * 0.) * Tbv[:, 0] if pp.bco == 0 else Tbv[:, 0]]
+        u.append(pp.rcmb * Tbu[:, 2] - lb * Tbu[:, 1] if pp.bco == 0 else Tbu[:, 1])
+    v = [-pp.rcmb * Tbv[:, 1] + (1 + pp.rcmb * lb) * Tbv[:, 0] if pp.bco == 0 else Tbv[:, 0]]
     h = [Tbh[:, 0] if pp.bco_thermal == 0 else Tbh[:, 1]]
     if pp.ricb > 0:
         u.append(Ta[:, 0])
-        u.append(pp.ricb * Ta[:, 2] - 0. * Ta[:, 1] if pp.bci == 0 else Ta[:, 1])
-        v.append(-pp.ricb * Ta[:, 1] + (1 + pp.ricb * 0.) * Ta[:, 0] if pp.bci == 0 else Ta[:, 0])
+        u.append(pp.ricb * Ta[:, 2] - la * Ta[:, 1] if pp.bci == 0 else Ta[:, 1])
+        v.append(-pp.ricb * Ta[:, 1] + (1 + pp.ricb * la) * Ta[:, 0] if pp.bci == 0 else Ta[:, 0])
         h.append(Ta[:, 0] if pp.bci_thermal == 0 else Ta[:, 1])
     rows["u"], rows["v"], rows["h"] = np.array(u), np.array(v), np.array(h)
     if pp.magnetic:
@@ -405,8 +428,15 @@ def build_program_A(pp: PhysicsParams, operators: dict) -> AsmProgram:
         r = _block_of(secs["u"], l)
         b.add(r, r, Group(IM, +1, [L, wf], _lin(b, (L, U(2, 0)), (-2, U(3, 1)), (-1, U(4, 2)))))
         b.add(r, r, Group(IM, +1, [2 * m, G], _lin(b, (-L, U(2, 0)), (2, U(3, 1)), (1, U(4, 2)))))
-        b.add(r, r, Group(RE, -1, [L, V], _lin(b, (-L * (l + 2) * (l - 1), U(0, 0)), (2 * L, U(2, 2)),
-                                               (-4, U(3, 3)), (-1, U(4, 4)))))
+        if pp.anelastic:  # viscous force with the density stratification (operators.py:146-152)
+            b.add(r, r, Group(RE, -1, [L, V], _lin(
+                b, (-L * (l + 2) * (l - 1), "r0_D0_u"), (-(L + 2), "r1_lho1_D0_u"), (-2 * (L - 1), "r2_lho2_D0_u"),
+                (1, "r3_lho3_D0_u"), (-(L - 2), "r2_lho1_D1_u"), (6, "r3_lho2_D1_u"), (1, "r4_lho3_D1_u"),
+                (2 * L, "r2_D2_u"), (5, "r3_lho1_D2_u"), (2, "r4_lho2_D2_u"), (-4, "r3_D3_u"), (1, "r4_lho1_D3_u"),
+                (-1, "r4_D4_u"))))
+        else:
+            b.add(r, r, Group(RE, -1, [L, V], _lin(b, (-L * (l + 2) * (l - 1), U(0, 0)), (2 * L, U(2, 2)),
+                                                   (-4, U(3, 3)), (-1, U(4, 4)))))
         c = _block_of(secs["v"], l - 1)
         if c is not None:
             b.add(r, c, Group(RE, +1, [2 * _coriolis_down(l, m), G], _lin(b, (l - 1, U(3, 0)), (-1, U(4, 1)))))
@@ -414,7 +444,7 @@ def build_program_A(pp: PhysicsParams, operators: dict) -> AsmProgram:
         if c is not None:
             b.add(r, c, Group(RE, +1, [2 * _coriolis_up(l, m), G], _lin(b, (-(l + 2), U(3, 0)), (-1, U(4, 1)))))
         if pp.thermal:
-            b.add(r, _block_of(secs["h"], l), Group(RE, +1, [L, Bf], _lin(b, (1, U(4, 0)))))
+            b.add(r, _block_of(secs["h"], l), Group(RE, +1, [L, Bf], _lin(b, (1, "r3_buo0_D0_u" if pp.anelastic else U(4, 0)))))
 
     for l in secs["v"][1]:  # ---- toroidal momentum (1curl) rows
         l = int(l)
@@ -428,7 +458,11 @@ def build_program_A(pp: PhysicsParams, operators: dict) -> AsmProgram:
             b.add(r, c, Group(RE, +1, [2 * _coriolis_up(l, m), G], _lin(b, (-(l + 2), W(1, 0)), (-1, W(2, 1)))))
         b.add(r, r, Group(IM, +1, [L, wf], _lin(b, (1, W(2, 0)))))
         b.add(r, r, Group(IM, +1, [-2 * m, G], _lin(b, (1, W(2, 0)))))
-        b.add(r, r, Group(RE, -1, [L, V], _lin(b, (-L, W(0, 0)), (2, W(1, 1)), (1, W(2, 2)))))
+        if pp.anelastic:  # operators.py:176-179
+            b.add(r, r, Group(RE, -1, [L, V], _lin(b, (-L, "r0_D0_v"), (-3, "r1_lho1_D0_v"), (-1, "r2_lho2_D0_v"),
+                                                   (2, "r1_D1_v"), (-1, "r2_lho1_D1_v"), (1, "r2_D2_v"))))
+        else:
+            b.add(r, r, Group(RE, -1, [L, V], _lin(b, (-L, W(0, 0)), (2, W(1, 1)), (1, W(2, 2)))))
 
     if pp.thermal:  # ---- heat equation rows
         gap = pp.rcmb - pp.ricb
@@ -438,7 +472,12 @@ def build_program_A(pp: PhysicsParams, operators: dict) -> AsmProgram:
             L = l * (l + 1)
             r = _block_of(secs["h"], l)
             c = _block_of(secs["u"], l)
-            if diff:
+            if pp.anelastic:  # entropy equation (operators.py:709-711, 731-732, 765-768)
+                b.add(r, c, Group(RE, +1, [L], _lin(b, (-1, "r1_tds0_D0_h"))))
+                b.add(r, r, Group(RE, +1, [Td], _lin(b, (-L, "r0_krT0_D0_h"), (2, "r1_krT0_D1_h"), (1, "r2_krT1_D1_h"),
+                                                     (1, "r2_krT0_D2_h"))))
+                b.add(r, r, Group(IM, -1, [wf], _lin(b, (1, "r2_roT0_D0_h"))))
+            elif diff:
                 b.add(r, c, Group(RE, +1, [pp.ricb, 1. / gap, L], _lin(b, (1, "r0_D0_h"))))
                 b.add(r, r, Group(RE, +1, [Td], _lin(b, (-L, "r1_D0_h"), (2, "r2_D1_h"), (1, "r3_D2_h"))))
                 b.add(r, r, Group(IM, -1, [wf], _lin(b, (1, "r3_D0_h"))))
@@ -586,7 +625,7 @@ def build_program_B(pp: PhysicsParams, operators: dict) -> AsmProgram:
                 r = _block_of(secs[name], l)
                 b.add(r, r, Group(0, -1, [l * (l + 1)], _lin(b, (1, lab))))
     if pp.thermal:
-        lab = "r3_D0_h" if pp.heating == "differential" else "r2_D0_h"
+        lab = "r2_roT0_D0_h" if pp.anelastic else ("r3_D0_h" if pp.heating == "differential" else "r2_D0_h")
         for l in secs["h"][1]:
             r = _block_of(secs["h"], int(l))
             b.add(r, r, Group(0, +1, [], _lin(b, (1, lab))))

@@ -159,7 +159,7 @@ void ka_put(std::vector<unsigned char>& host, std::vector<size_t>& offs, const T
 }
 
 int ka_check(kb_context* h, const kb_asm_program* q, const char* name) {
-  if (q->N1 < 1 || q->nblockrows < 1 || q->H < 0 || 2 * q->H + 1 > 31)
+  if (q->N1 < 1 || q->nblockrows < 1 || q->H < 0 || 2 * q->H + 1 > 1023)
     return kb_fail(h, KB_EINVAL, "%s program: bad sizes (N1 %d, block rows %d, half band %d)", name, q->N1,
                    q->nblockrows, q->H);
   if ((int64_t)q->N1 * q->nblockrows > 0x7fffffff) return kb_fail(h, KB_EINVAL, "%s program: n out of range", name);

@@ -50,6 +50,11 @@ NEW_CASES = {
     "asm_magnetic_axial": ("tests/spinover/params.spinover", ["magnetic=1", "N=24", "m=2", "symm=1"]),
     "asm_magnetic_dipole_thermal": ("tests/dormy2004/params.dormy04",
                                     ["magnetic=1", "B0='dipole'", "N=24", "lmax=24", "m=3", "forcing=0"]),
+    # anelastic (polytropic background of the params file): wide profile operators; bit for bit again
+    "asm_anelastic": ("tests/dormy2004/params.dormy04", ["anelastic=1", "N=24", "lmax=24", "m=3"]),
+    "asm_anelastic_stressfree": ("tests/dormy2004/params.dormy04",
+                                 ["anelastic=1", "N=24", "lmax=24", "m=3", "bci=0", "bco=0", "bco_thermal=1"]),
+    "asm_anelastic_hydro": ("tests/dormy2004/params.dormy04", ["anelastic=1", "thermal=0", "N=24", "lmax=23", "m=0", "symm=-1"]),
 }
 EXISTING = ["spinover", "dormy", "jones", "forced_small", "m0_small", "magnetic_small"]
 

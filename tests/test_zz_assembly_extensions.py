@@ -130,3 +130,43 @@ def test_device_assembled_magnetic_pencil_against_the_oracle(lib):
     for z in case.oracle["eig"]:
         assert np.min(np.abs(lam - z)) <= 1e-9 * abs(z), (z, lam)
     assert np.all(info["resid"] <= 1e-10)
+
+
+# ------------------------------------------------------------------------------------ anelastic runs
+ANELASTIC = ["asm_anelastic", "asm_anelastic_stressfree", "asm_anelastic_hydro"]
+
+
+@pytest.mark.parametrize("name", ANELASTIC)
+def test_anelastic_program_reproduces_reference_assembly_bitwise(name):
+    # density-stratified (anelastic) runs: viscous force with the log-density profile operators, buoyancy and entropy
+    # equation with the background profiles, stress-free rows with d ln(rho)/dr (operators.py:146-152, 176-179, 393-395,
+    # 709-711, 731-732, 765-768; assemble.py:1195-1198, 1244, 1262, 1284, 1291).  Plain double arithmetic in the
+    # reference, so the bar is the bit again.  The profile operators are wide (+-17 at N = 24).
+    pj, pp, ops, A_ref, B_ref = fixture(name)
+    assert pp.anelastic == 1
+    A, B = model_pencil(pj, pp, ops)
+    assert asm.build_program_A(pp, ops).H > 15
+    for M, R in ((A, A_ref), (B, B_ref)):
+        assert np.array_equal(M.indptr, R.indptr) and np.array_equal(M.indices, R.indices) and np.array_equal(M.data, R.data)
+
+
+def test_anelastic_stressfree_needs_the_density_slopes():
+    pj, pp, ops, _, _ = fixture("asm_anelastic_stressfree")
+    assert pp.lho1_icb is not None and pp.lho1_cmb is not None
+    q = asm.PhysicsParams.from_dict({k: v for k, v in pp.__dict__.items() if k not in ("lho1_icb", "lho1_cmb")})
+    with pytest.raises(NotImplementedError):
+        asm.build_program_A(q, ops)
+    with pytest.raises(NotImplementedError):
+        asm.build_program_A(asm.PhysicsParams.from_dict({**pp.__dict__, "variable_viscosity": 1}), ops)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ANELASTIC)
+def test_device_assembles_the_anelastic_program_bitwise(lib, name):
+    pj, pp, ops, A_ref, B_ref = fixture(name)
+    with lib.Solver(0) as s:
+        asm.assemble(s, pp, ops, bnorm=pj["Bnorm"])
+        ip, ix, v = s.get_assembled("A")
+        jp, jx, w = s.get_assembled("B")
+    assert np.array_equal(ip, A_ref.indptr) and np.array_equal(ix, A_ref.indices) and np.array_equal(v, A_ref.data)
+    assert np.array_equal(jp, B_ref.indptr) and np.array_equal(jx, B_ref.indices) and np.array_equal(w, B_ref.data)

@@ -6,7 +6,7 @@ mode, truncation), runs the reference stages through tools/make_case.py --asm an
 kore_b200.assembly + the NumPy model of the kernels (tests/assembly_model.py) produce with A.npz / B.npz:
 pattern and values, bit for bit.  With a third argument `magnetic` the trials are magnetic runs (axial or dipole
 background field, insulating boundaries, with or without the heat equation) and the bar is the rounding-level one of
-tests/test_zz_magnetic_assembly.py: B bit for bit, every block of A within 1e-13 of its largest entry.
+tests/test_zz_assembly_extensions.py: B bit for bit, every block of A within 1e-13 of its largest entry.
 Usage: tools/fuzz_assembly.py [ntrials] [seed] [magnetic]."""
 import json
 import os

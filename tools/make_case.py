@@ -112,6 +112,10 @@ def main():
             [sys.executable, "-c",
              "import sys; sys.path.insert(0,'bin'); import parameters as p, utils as u, json;"
              "d={k:getattr(p,k) for k in %r if hasattr(p,k)}; d['rcmb']=u.rcmb;"
+             "import numpy as np;"
+             "exec('import bc_variables as bv, radial_profiles as rap\\n"
+             "lho=u.chebco_f(rap.log_density,p.N,p.ricb,u.rcmb,1e-9)\\n"
+             "d[\\'lho1_icb\\']=float(np.dot(lho,bv.Ta[:,1])); d[\\'lho1_cmb\\']=float(np.dot(lho,bv.Tb[:,1]))') if p.anelastic else None;"
              "print(json.dumps({k:(v.item() if hasattr(v,'item') else v) for k,v in d.items()}))" % (fields,)],
             cwd=work, env=env).decode().strip().splitlines()[-1]
         with open(os.path.join(a.out, "asm_params.json"), "w") as f:
