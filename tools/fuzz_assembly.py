@@ -7,7 +7,8 @@ kore_b200.assembly + the NumPy model of the kernels (tests/assembly_model.py) pr
 pattern and values, bit for bit.  With a third argument `magnetic` the trials are magnetic runs (axial or dipole
 background field, insulating boundaries, with or without the heat equation) and the bar is the rounding-level one of
 tests/test_zz_assembly_extensions.py: B bit for bit, every block of A within 1e-13 of its largest entry.
-Usage: tools/fuzz_assembly.py [ntrials] [seed] [magnetic]."""
+`anelastic` instead draws density-stratified runs (bit for bit again).
+Usage: tools/fuzz_assembly.py [ntrials] [seed] [magnetic | anelastic]."""
 import json
 import os
 import shutil
@@ -60,6 +61,19 @@ def draw_magnetic(rng):
     return params, ov
 
 
+def draw_anelastic(rng):
+    thermal = int(rng.integers(0, 2))
+    m = int(rng.integers(0, 5))
+    nl = 2 * int(rng.integers(4, 9))
+    ov = ["anelastic=1", "thermal=%d" % thermal, "m=%d" % m, "symm=%d" % rng.choice([-1, 1]), "N=%d" % rng.choice([20, 24, 28]),
+          "lmax=%d" % (nl + m - 1), "Ek=%g" % (10.0 ** rng.uniform(-5, -2)), "ricb=%.3f" % rng.uniform(0.2, 0.7),
+          "bci=%d" % rng.integers(0, 2), "bco=%d" % rng.integers(0, 2), "Nrho=%.2f" % rng.uniform(0.5, 4.0),
+          "polind=%.2f" % rng.uniform(1.0, 3.0), "forcing=0"]
+    if thermal:
+        ov += ["bci_thermal=%d" % rng.integers(0, 2), "bco_thermal=%d" % rng.integers(0, 2), "Ra_gap=%g" % (10.0 ** rng.uniform(4, 7))]
+    return "tests/dormy2004/params.dormy04", ov
+
+
 def draw(rng):
     thermal = int(rng.integers(0, 2))
     full = int(rng.integers(0, 4) == 0)
@@ -95,9 +109,10 @@ def main():
     ntrials = int(sys.argv[1]) if len(sys.argv) > 1 else 10
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
     magnetic = len(sys.argv) > 3 and sys.argv[3] == "magnetic"
+    anelastic = len(sys.argv) > 3 and sys.argv[3] == "anelastic"
     bad = 0
     for t in range(ntrials):
-        params, ov = draw_magnetic(rng) if magnetic else draw(rng)
+        params, ov = draw_magnetic(rng) if magnetic else (draw_anelastic(rng) if anelastic else draw(rng))
         out = "/tmp/asmfuzz_%d_%d" % (os.getpid(), t)
         shutil.rmtree(out, ignore_errors=True)
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_case.py"), "--params", params, "--out", out,
