@@ -191,7 +191,7 @@ int kb_savetxt(const char* path, const double* data, int64_t rows, int64_t cols,
  * rows assemble.py:1188-1345) for hydrodynamic and Boussinesq thermal set-ups.  An assembly
  * program describes every N1 x N1 block of a matrix whose rows and columns are `nblockrows`
  * blocks of N1 radial coefficients in Kore's own (section-major) ordering:
- *   - radial operators as bands: ops[(k*N1 + i)*(2H+1) + d] = R_k[i][i + d - H] (0 where absent);
+ *   - radial operators as bands: ops[(k*N1 + i)*(2H+1) + d] = R_k[i][i + d - H] (0 where absent; 2H+1 <= 1023);
  *   - block row r has the blocks blk_ptr[r] .. blk_ptr[r+1]-1, block b in block column blk_col[b]
  *     (ascending inside a block row); its first br_chop[r] rows are boundary rows: dense rows
  *     bc[(br_bc[r] + q)*N1 + j] of the diagonal block, nothing elsewhere;
