@@ -87,6 +87,7 @@ class PhysicsParams:
     mantle: str = "insulator"
     Hendrik: float = 0.0
     MagnetD: float = 0.0
+    cnorm: object = "mag_energy"  # normalisation of the background field (parameters.py:144-155; radial.py only)
 
     @classmethod
     def from_modules(cls, par, ut=None):

@@ -1,0 +1,664 @@
+"""Radial operators of Kore's equations.
+
+Replaces /root/reference/bin/submatrices.py:28-590 and the functions of bin/utils.py it calls
+(chebco :251-270, Dlam :893-905, Slam :908-922, csl0 / csl / Mlam :925-1062, labelit :130-157,
+decode_label :85-127, remroco :187-197) for the set-ups the device-side assembly covers
+(kore_b200/assembly.py): every operator ``r^X D^Y`` (and, through `profiles`, ``r^X f(r) D^Y``)
+of a section is the product
+
+    (C^(Y) -> C^(g) basis change)  x  (multiplication by r^X [f(r)] in the C^(Y) basis)  x  D^Y
+
+with g the Gegenbauer order of the section, cut to its parity for a full sphere, its last `chop`
+rows dropped and `chop` empty boundary rows put on top.  The result feeds `assembly.assemble`
+directly (a dict label -> CSR, what `assembly.load_operators` returns for a directory of the
+reference's ``.mtx`` files) or is written as ``.mtx`` for the reference's own assemble.py.
+
+What is different from the reference.  Its multiplication matrices are filled entry by entry by
+an interpreted triple loop -- for every entry (j, k) of the band an O(k) product for the first
+linearisation coefficient c_s^lambda(j, k) and an O(k) recursion for the others, although the
+Chebyshev coefficients of r^X they multiply vanish beyond degree X (minutes beyond N = 676,
+utils.py:1006-1026).  Here
+
+  * the first coefficients come from four tables of running products (`_Tables`): the products of
+    csl0 depend on (k), (|j - k|, k) and (j, |j - k|) only, so a table row is built once by the
+    same left-to-right sequence of IEEE operations and read by every entry that needs it;
+  * the recursion runs for all entries of the band at once (NumPy arrays over the entries) and
+    stops after the last term whose Chebyshev coefficient is non-zero;
+  * basis changes and derivatives are dense row operations (`_Upper`) whose terms are accumulated
+    in the order scipy's CSR product of the reference accumulates them -- the STORAGE order of
+    the left factor's rows, which is not ascending for a product of products.
+
+Every floating-point operation of the reference is performed, on the same operands and in the same
+order, so the operators are the reference's to the bit -- with one caveat the reference has itself:
+its band entries are `numpy.dot` products, whose summation order belongs to the host BLAS.
+``dot="blas"`` (default) makes the same call on the same vectors (same bits as the reference run on
+the same machine: the committed fixtures in this container); ``dot="ordered"`` sums left to right,
+machine independent, and differs from the former by an ulp in a few entries of the widest bands.
+tests/test_radial.py compares with the operators the unmodified reference wrote for every fixture
+under tests/golden/.
+"""
+import math
+import os
+
+import numpy as np
+
+from .assembly import PhysicsParams
+
+TOL = 1e-9  # submatrices.py:55
+
+
+# ---------------------------------------------------------------------------
+# Chebyshev coefficients of the radial functions
+# ---------------------------------------------------------------------------
+def _nodes(N, ricb, rcmb):
+    """radii of the N Chebyshev-Gauss points (utils.py:257-263)"""
+    i = np.arange(0, N)
+    xi = np.cos(np.pi * (i + 0.5) / N)
+    if ricb == 0:
+        return rcmb * xi
+    return ricb + (rcmb - ricb) * (xi + 1) / 2.
+
+
+def _dct_coefficients(samples, N, tol):
+    """first N Chebyshev coefficients of the function sampled on the Gauss points, small ones
+    set to zero (utils.py:266-270)"""
+    import scipy.fft as sfft
+    out = sfft.dct(samples, type=2) / N
+    out[0] = out[0] / 2.
+    out[np.absolute(out) <= tol] = 0.
+    return out
+
+
+def chebco(powr, N, tol, ricb, rcmb):
+    """Chebyshev coefficients of r**powr on [ricb, rcmb] (or [-rcmb, rcmb] without inner core)."""
+    return _dct_coefficients(_nodes(N, ricb, rcmb) ** powr, N, tol)
+
+
+def chebco_function(func, N, tol, ricb, rcmb, rpower=0):
+    """Chebyshev coefficients of r**rpower * func(r) (utils.py:200-247)."""
+    r = _nodes(N, ricb, rcmb)
+    return _dct_coefficients(func(r) if rpower == 0 else r ** rpower * func(r), N, tol)
+
+
+# ---------------------------------------------------------------------------
+# basis changes and derivatives (dense, N x N)
+# ---------------------------------------------------------------------------
+def basis_change(lamb, N):
+    """C^(lamb) -> C^(lamb+1) coefficients: diagonals 0 and +2 (utils.py:908-922)."""
+    S = np.zeros((N, N))
+    i = np.arange(N)
+    if lamb == 0:
+        d0 = 0.5 * np.ones(N)
+        d0[0] = 1.
+        d1 = -0.5 * np.ones(N - 2)
+    else:
+        t = np.arange(0., N)
+        d0 = lamb / (lamb + t)
+        d1 = -lamb / (lamb + t[2:])
+    S[i, i] = d0
+    S[i[:-2], i[:-2] + 2] = d1
+    return S
+
+
+def derivative_diagonal(lamb, N, ricb, rcmb):
+    """The one diagonal (offset +lamb) of the order-lamb derivative, C^(0) -> C^(lamb)
+    (utils.py:893-905): scale * (lamb + i), i = 0 .. N-lamb-1."""
+    if ricb == 0:
+        const1 = (1 / rcmb) ** lamb
+    else:
+        const1 = (2. / (rcmb - ricb)) ** lamb
+    const2 = float(math.factorial(lamb - 1)) * 2 ** (lamb - 1.)
+    return (const1 * const2) * (lamb + np.arange(0, N - lamb)).astype(float)
+
+
+def times_derivative(M, lamb, N, ricb, rcmb):
+    """M @ D^lamb: column k of the result is column k - lamb of M times the diagonal entry."""
+    if lamb == 0:
+        return M
+    d = derivative_diagonal(lamb, N, ricb, rcmb)
+    out = np.zeros_like(M)
+    out[:, lamb:] = M[:, : N - lamb] * d[None, :]
+    return out
+
+
+# ---------------------------------------------------------------------------
+# multiplication matrices
+# ---------------------------------------------------------------------------
+class _Tables:
+    """Running products of csl0 (utils.py:925-941) for one Gegenbauer order and truncation.
+
+    csl0(s, lamb, j, k) multiplies four products; in the two ways Mlam calls it (s = 0, or s = k)
+    they are P[c] = prod_{t<c} (lamb+t)/(1+t), Q[d][c] = prod_{t<c} (d+1+t)/(d+lamb+t) and
+    R[j][e] = prod_{t<e} (2 lamb+j+t)/(lamb+j+t), each advanced as ``p = p*num/float(den)``."""
+
+    def __init__(self, lamb, N, reach):
+        self.lamb, self.N, self.reach = lamb, N, reach
+        P = np.ones(N + 1)
+        for t in range(N):
+            P[t + 1] = P[t] * (lamb + t) / float(1 + t)
+        self.P = P
+        d = np.arange(reach + 1, dtype=float)
+        Q = np.ones((reach + 1, N + 1))
+        for t in range(N):
+            Q[:, t + 1] = Q[:, t] * (d + 1 + t) / (d + lamb + t)
+        self.Q = Q
+        j = np.arange(N, dtype=float)
+        R = np.ones((N, reach + 1))
+        for t in range(reach):
+            R[:, t + 1] = R[:, t] * (2 * lamb + j + t) / (lamb + j + t)
+        self.R = R
+
+
+_table_cache = {}
+
+
+def _tables(lamb, N, reach):
+    key = (lamb, N)
+    t = _table_cache.get(key)
+    if t is None or t.reach < reach:
+        t = _table_cache[key] = _Tables(lamb, N, reach)
+    return t
+
+
+def multiplication(a0, lamb, vector_parity, dot="blas"):
+    """Matrix of the multiplication by the series sum_i a0[i] C_i^(lamb) in the C^(lamb) basis
+    (utils.py:962-1062); `vector_parity` as there (0 with an inner core).  Dense N x N."""
+    a0 = np.asarray(a0, dtype=float)
+    N = a0.size
+    if not np.sum(abs(a0)) > 0:
+        return None
+    nzi = np.nonzero(a0)[0]
+    bw = int(nzi.max())
+
+    idj = idk = 0
+    if vector_parity != 0:
+        rpower_parity = 1 - 2 * (int(nzi[-1]) % 2)
+        lamb_parity = 1 - 2 * (lamb % 2)
+        overall_parity = vector_parity * rpower_parity * lamb_parity
+        idj = int((1 - overall_parity) / 2)
+        idk = int((1 - vector_parity * lamb_parity) / 2)
+
+    if lamb == 0:
+        # Chebyshev basis: half of Toeplitz + Hankel (utils.py:1030-1049)
+        a2 = np.copy(a0)
+        a2[0] = 2 * a2[0]
+        i = np.arange(N)
+        T = a2[np.abs(i[:, None] - i[None, :])]
+        ij = i[:, None] + i[None, :]
+        H = np.where(ij < N, a2[np.minimum(ij, N - 1)], 0.0)
+        H[0, :] = 0.0
+        out = 0.5 * (T + H)
+        if vector_parity != 0:
+            out[int((1 + overall_parity) / 2)::2, :] = 0.0
+            out[:, int((1 + vector_parity * lamb_parity) / 2)::2] = 0.0
+        return out
+
+    # entries of the band: |k - j| <= bw + 1, parities as asked
+    step = 2 if vector_parity != 0 else 1
+    jr = np.arange(idj, N, step, dtype=np.int64)
+    off = np.arange(-bw - 1, bw + 2, dtype=np.int64)
+    J = np.repeat(jr, off.size)
+    K = J + np.tile(off, jr.size)
+    keep = (K >= 0) & (K < N)
+    if vector_parity != 0:
+        keep &= (K % 2) == idk
+    J, K = J[keep], K[keep]
+    E = K - J
+    D = np.abs(E)
+    up = E > 0                                   # s0 = k - j > 0: csl(s, lamb, k, k - j)
+    s0 = np.where(up, E, 0)
+    nterm = np.minimum(np.where(D <= bw, (bw - D) // 2 + 1, 0), K - s0 + 1)
+    L = int(nterm.max()) if nterm.size else 0
+
+    tb = _tables(lamb, N, bw + 1)
+    Jf, Kf = J.astype(float), K.astype(float)
+    # first coefficient, csl0(s0, lamb, k, |j - k|): ((((p1*p2)*p3)*p4)*(j'+k'+lamb-2 s))/(j'+k'+lamb-s)
+    lo = ~up
+    c = np.empty(J.size)
+    c[lo] = ((tb.P[K[lo]] * tb.Q[D[lo], K[lo]]) * (Jf[lo] + lamb)) / (Jf[lo] + lamb)
+    c[up] = ((((tb.P[E[up]] * tb.P[J[up]]) * tb.R[J[up], E[up]]) * tb.Q[0, J[up]]) * (Jf[up] + lamb)) / (Kf[up] + lamb)
+
+    C = np.zeros((J.size, max(L, 1)))
+    C[:, 0] = c
+    jj, kk, s = K.copy(), D.copy(), s0.copy()    # csl's j, k, s (utils.py:944-958), int64 as there
+    for i in range(1, L):
+        tmp1 = (jj + kk + lamb - s) * (lamb + s) * (jj - s) * (2 * lamb + jj + kk - s) * (kk - s + lamb)
+        tmp2 = (jj + kk + lamb - s + 1) * (s + 1) * (lamb + jj - s - 1) * (lamb + jj + kk - s) * (kk - s + 1)
+        live = i < nterm
+        nxt = np.zeros(J.size)
+        nxt[live] = C[live, i - 1] * tmp1[live].astype(float) / tmp2[live].astype(float)
+        C[:, i] = nxt
+        kk = kk + 2
+        s = s + 1
+
+    # the Chebyshev coefficients each term multiplies: a1[2 s + j - k] = a0[|j - k| + 2 i]
+    a1 = np.zeros(2 * N + 2 * max(L, 1))
+    a1[:N] = a0
+    A = a1[D[:, None] + 2 * np.arange(max(L, 1))[None, :]]
+    A[np.arange(max(L, 1))[None, :] >= nterm[:, None]] = 0.0
+
+    out = np.zeros((N, N))
+    if dot == "ordered":
+        acc = np.zeros(J.size)
+        for i in range(L):
+            acc = acc + A[:, i] * C[:, i]
+        out[J, K] = acc
+    else:
+        # numpy.dot on vectors of the reference's lengths (k + 1 - s0): the summation order of the
+        # host BLAS depends on the length and on where in the vector a term sits
+        full = K - s0 + 1
+        za = np.zeros(N + 1)
+        zc = np.zeros(N + 1)
+        vals = np.empty(J.size)
+        for e in range(J.size):
+            n, f = int(nterm[e]), int(full[e])
+            za[:n] = A[e, :n]
+            zc[:n] = C[e, :n]
+            vals[e] = np.dot(za[:f], zc[:f])
+            za[:n] = 0.0
+            zc[:n] = 0.0
+        out[J, K] = vals
+    return out
+
+
+# ---------------------------------------------------------------------------
+# products in scipy's accumulation order
+# ---------------------------------------------------------------------------
+class _Upper:
+    """An upper-banded N x N matrix as scipy holds it after ``A * B``: dense values plus the order
+    in which a row stores its diagonals.  The reference multiplies its basis changes with
+    scipy.sparse, whose CSR product (sparsetools csr_matmat) accumulates an entry of the result
+    over the left factor's row in STORAGE order and stores a result row in reverse order of first
+    touch -- so S3*S2*S1*S0 is not summed in ascending column order, and the last bit shows it."""
+
+    def __init__(self, val, order):
+        self.val, self.order = val, list(order)
+
+    def __matmul__(self, other):
+        if isinstance(other, _Upper):
+            touched = []
+            for a in self.order:
+                for b in other.order:
+                    if a + b not in touched:
+                        touched.append(a + b)
+            return _Upper(self.apply(other.val), touched[::-1])
+        return self.apply(other)
+
+    def apply(self, M):
+        """self @ M for a dense matrix or vector M, terms in storage order, sums from zero"""
+        N = self.val.shape[0]
+        out = np.zeros(M.shape)
+        for a in self.order:
+            g = np.diagonal(self.val, a)
+            if M.ndim == 1:
+                out[: N - a] += g * M[a:]
+            else:
+                out[: N - a, :] += g[:, None] * M[a:, :]
+        return out
+
+
+class GegenbauerBases:
+    """The basis changes of submatrices.py:138-170: S[d] takes C^(0) coefficients to C^(d),
+    G[g][g - d] takes C^(d) to C^(g); `None` stands for the identity."""
+
+    def __init__(self, N):
+        S0, S1, S2, S3 = (_Upper(basis_change(k, N), (0, 2)) for k in range(4))
+        S10 = S1 @ S0
+        S21 = S2 @ S1
+        S210 = S2 @ S10
+        S32 = S3 @ S2
+        S321 = S32 @ S1
+        S3210 = S321 @ S0
+        self.S = [None, S0, S10, S210, S3210]
+        self.G = [[None], [None, S0], [None, S1, S10], [None, S2, S21, S210], [None, S3, S32, S321, S3210]]
+
+
+# ---------------------------------------------------------------------------
+# which operators a run needs (submatrices.py:200-443)
+# ---------------------------------------------------------------------------
+def _labelit(labels, section, rplus=0):
+    """utils.py:130-157: section suffix, power of r raised by rplus ('q1' is r**-1)"""
+    out = []
+    for lab in labels:
+        if rplus > 0:
+            old = lab[:2]
+            power = -1 if old == "q1" else int(old[1])
+            lab = "r" + str(power + rplus) + lab[2:]
+        out.append(lab + "_" + section)
+    return out
+
+
+def operator_labels(pp: PhysicsParams):
+    """(labels, vector parities) of the radial operators of a run, in the reference's order."""
+    vP = int((1 - 2 * (pp.m % 2)) * pp.symm)
+    vT = -vP
+    labels, par = [], []
+    dip = pp.dipole and pp.ricb > 0
+    vF = -vP                                     # background fields covered here are equatorially antisymmetric
+    vG = -vF
+    vS = vP                                      # entropy perturbation
+    if pp.compositional or pp.variable_viscosity or (pp.anelastic and pp.magnetic):
+        raise NotImplementedError("radial operators of compositional / variable-viscosity / anelastic magnetic runs")
+    if pp.magnetic and pp.B0 not in BACKGROUND_FIELDS:
+        raise NotImplementedError("B0 = %r" % (pp.B0,))
+    if pp.hydro:
+        u = ["r2_D0", "r3_D1", "r4_D2"] + ["r3_D0", "r4_D1"] + ["r0_D0", "r2_D2", "r3_D3", "r4_D4"]
+        par += [vP, vP, vP, vT, vT, vP, vP, vP, vP]
+        if pp.anelastic:
+            u += ["r1_lho1_D0", "r2_lho2_D0", "r3_lho3_D0", "r2_lho1_D1", "r3_lho2_D1",
+                  "r3_lho1_D2", "r4_lho2_D2", "r4_lho3_D1", "r4_lho1_D3"]
+            par += [vP] * 9
+        if pp.magnetic:
+            u += ["r1_h0_D1", "r2_h1_D1", "r2_h0_D2", "r3_h1_D2", "r0_h0_D0", "r1_h1_D0", "r2_h2_D0",
+                  "r3_h3_D0", "r3_h0_D3", "r1_h0_D0", "r2_h1_D0", "r2_h0_D1", "r3_h1_D1", "r3_h0_D2"]
+            par += [vF] * 9 + [vG] * 5
+        if pp.thermal:
+            u += ["r3_buo0_D0"] if pp.anelastic else ["r4_D0"]
+            par += [vS if pp.anelastic else vP]
+        labels += _labelit(u, "u", 2 * dip)
+        v = ["r2_D0"] + ["r1_D0", "r2_D1"] + ["r0_D0", "r1_D1", "r2_D2"]
+        par += [vT, vP, vP, vT, vT, vT]
+        if pp.anelastic:
+            v += ["r1_lho1_D0", "r2_lho2_D0", "r2_lho1_D1"]
+            par += [vT] * 3
+        if pp.magnetic:
+            v += ["r0_h0_D1", "r0_h1_D0", "r1_h2_D0", "r1_h0_D2", "r0_h0_D0", "r1_h1_D0", "r1_h0_D1"]
+            par += [vF] * 4 + [vG] * 3
+        labels += _labelit(v, "v", 3 * dip)
+    if pp.magnetic:
+        f = ["r2_D0"] + ["r0_h0_D0", "r1_h1_D0", "r1_h0_D1", "r1_h0_D0"] + ["r0_eta0_D0", "r1_eta0_D1", "r2_eta0_D2"]
+        par += [vF, vP, vP, vP, vT, vF, vF, vF]
+        labels += _labelit(f, "f", 2 * dip)
+        g = (["r2_D0"] + ["r0_h0_D1", "r1_h1_D1", "q1_h0_D0", "r0_h1_D0", "r1_h2_D0", "r1_h0_D2",
+                         "r0_h0_D0", "r1_h0_D1", "r1_h1_D0"]
+             + ["r0_eta0_D0", "r1_eta0_D1", "r2_eta0_D2", "r1_eta1_D0", "r2_eta1_D1"])
+        par += [vG] + [vP] * 6 + [vT] * 3 + [vG] * 5
+        labels += _labelit(g, "g", 3 * dip)
+    if pp.thermal and pp.anelastic:
+        h = ["r2_roT0_D0", "r1_tds0_D0"]
+        par += [vS, vP]
+        if pp.ThermaD > 0:
+            h += ["r0_krT0_D0", "r1_krT0_D1", "r2_krT1_D1", "r2_krT0_D2"]
+            par += [vS] * 4
+        labels += _labelit(h, "h", 0)
+    elif pp.thermal:
+        if pp.heating == "differential":
+            h = ["r0_D0", "r3_D0"]
+            par += [vP, vP]
+            if pp.ThermaD > 0:
+                h += ["r1_D0", "r2_D1", "r3_D2"]
+                par += [vP, vP, vP]
+        elif pp.heating == "internal":
+            h = ["r2_D0"]
+            par += [vP]
+            if pp.ThermaD > 0:
+                h += ["r0_D0", "r1_D1", "r2_D2"]
+                par += [vP, vP, vP]
+        else:
+            raise NotImplementedError("heating = %r needs the run's radial_profiles.py" % (pp.heating,))
+        labels += _labelit(h, "h", 0)
+    if pp.ricb > 0:
+        par = [0] * len(labels)
+    return labels, par
+
+
+def gegenbauer_orders(pp: PhysicsParams):
+    """Gegenbauer order of every section = number of boundary rows with an inner core
+    (submatrices.py:167-179)."""
+    g = {"u": 4, "v": 2, "f": 2, "g": 2, "h": 2, "i": 2}
+    if pp.magnetic and "conductor" in pp.innercore:
+        g["f"] = 3
+    if (pp.Ek == 0 or pp.ViscosD == 0) and pp.ricb == 0:
+        g["u"], g["v"] = 2, 1
+    if pp.ThermaD == 0:
+        g["h"] = 0
+    return g
+
+
+# ---------------------------------------------------------------------------
+# background magnetic field (utils.py:555-797, 800-890)
+# ---------------------------------------------------------------------------
+def _field_axial(r, rp, d):
+    return [lambda: (1 / 2) * r ** (1 + rp), lambda: (1 / 2) * r ** rp,
+            lambda: np.zeros_like(r), lambda: np.zeros_like(r)][d]()
+
+
+def _field_dipole(r, rp, d):
+    return [lambda: (1 / 2) * r ** (-2 + rp), lambda: -r ** (-3 + rp),
+            lambda: 3 * r ** (-4 + rp), lambda: -12 * r ** (-5 + rp)][d]()
+
+
+def _field_g21(r, rp, d):
+    return [lambda: (1 / 6) * r ** (1 + rp) - (1 / 10) * r ** (3 + rp), lambda: (1 / 6) * r ** rp - (3 / 10) * r ** (2 + rp),
+            lambda: (6 / 10) * r ** (1 + rp), lambda: (6 / 10) * r ** rp][d]()
+
+
+def _field_luo_s1(r, rp, d):
+    return [lambda: (5 - 3 * r ** 2) * r ** (1 + rp), lambda: (5 - 9 * r ** 2) * r ** rp,
+            lambda: -18 * r ** (1 + rp), lambda: -18 * r ** rp][d]()
+
+
+# r**rp times the d-th derivative of the poloidal scalar h(r) of the background field, all of degree l = 1
+BACKGROUND_FIELDS = {"axial": _field_axial, "dipole": _field_dipole, "G21 dipole": _field_g21, "Luo_S1": _field_luo_s1}
+
+
+def background_field(r, kind, rp, d):
+    """h0 .. h3 of utils.py on radii r > 0 (inner core present)"""
+    if np.any(r <= 0):
+        raise NotImplementedError("background field without inner core")
+    return BACKGROUND_FIELDS[kind](r, rp, d)
+
+
+def field_normalisation(pp: PhysicsParams):
+    """utils.py:837-890 (B0_norm) for a degree-1 background field"""
+    l, L = 1, 2
+    kind, ricb = pp.B0, pp.ricb
+    if pp.cnorm == "rms_cmb":
+        return (np.sqrt(2 * l + 1) / (l * (l + 1) * background_field(np.array([1.0]), kind, 0, 0)))[0]
+    if pp.cnorm in ("mag_energy", "Schmitt2012"):
+        N = 240
+        i = np.arange(0, N)
+        xk = np.cos((i + 0.5) * np.pi / N)
+        sqx = np.sqrt(1 - xk ** 2)
+        rk = 0.5 * (1 - ricb) * (xk + 1) + ricb
+        r2 = rk ** 2
+        y0 = background_field(rk, kind, 0, 0)
+        y1 = background_field(rk, kind, 0, 1)
+        f0 = 4 * np.pi * L / (2 * l + 1)
+        f1 = (L + 1) * y0 ** 2
+        f2 = 2 * rk * y0 * y1
+        f3 = r2 * y1 ** 2
+        integ = (np.pi / N) * ((1 - ricb) / 2) * np.sum(sqx * f0 * (f1 + f2 + f3))
+        return (1 if pp.cnorm == "mag_energy" else 2) / np.sqrt(integ)
+    return pp.cnorm
+
+
+def chebyshev_derivative(ck, ricb, rcmb):
+    """Chebyshev coefficients of the r-derivative of a Chebyshev series (utils.py:273-294)"""
+    c = np.copy(ck)
+    c[0] = 2. * c[0]
+    s = np.size(c)
+    out = np.zeros_like(c)
+    out[-2] = 2. * (s - 1.) * c[-1]
+    for k in range(s - 3, -1, -1):
+        out[k] = out[k + 2] + 2. * (k + 1) * ck[k + 1]
+    out[0] = out[0] / 2.
+    return out / rcmb if ricb == 0 else 2 * out / (rcmb - ricb)
+
+
+def profile_table(func, order, N, ricb, rcmb, tol=TOL):
+    """Columns: Chebyshev coefficients of func(r) and of its first `order` derivatives
+    (utils.py:317-328, chebify)."""
+    cols = [chebco_function(func, N, tol, ricb, rcmb)]
+    for _ in range(order):
+        cols.append(chebyshev_derivative(cols[-1], ricb, rcmb))
+    return np.stack(cols, axis=1)
+
+
+def profile_tables(pp: PhysicsParams, rap):
+    """The tables compute_profiles.py:39-91 stores in radProfs.mat, from a module `rap` with the
+    run's radial functions (radial_profiles.py: density, log_density, viscosity, krT, roT,
+    log_temperature, kappa_rho, tds, buoFac, magnetic_diffusivity)."""
+    N, ricb, rcmb = pp.N, pp.ricb, pp.rcmb
+    t = {}
+    if pp.anelastic:
+        for key, name, order in (("cd_rho", "density", 2), ("cd_lho", "log_density", 4), ("cd_vsc", "viscosity", 2),
+                                 ("cd_krT", "krT", 1), ("cd_roT", "roT", 0)):
+            t[key] = profile_table(getattr(rap, name), order, N, ricb, rcmb)
+        if pp.thermal:
+            for key, name, order in (("cd_lnT", "log_temperature", 1), ("cd_kho", "kappa_rho", 1), ("cd_tds", "tds", 0),
+                                     ("cd_buo", "buoFac", 0)):
+                t[key] = profile_table(getattr(rap, name), order, N, ricb, rcmb)
+    if pp.magnetic:
+        t["cd_eta"] = profile_table(rap.magnetic_diffusivity, 1, N, ricb, rcmb)
+    return t
+
+
+def series_product(ck1, ck2, tol=TOL):
+    """Chebyshev coefficients of the product of two Chebyshev series (utils.py:342-348)"""
+    out = _rows_times_vector(multiplication(ck1, 0, 0), ck2)
+    out[np.absolute(out) <= tol] = 0.0
+    return out
+
+
+def _rows_times_vector(M, x):
+    """M @ x as scipy's CSR product forms it: every row summed over its non-zero entries in
+    ascending column order, from zero"""
+    out = np.zeros(M.shape[0])
+    for k in range(M.shape[1]):
+        col = M[:, k]
+        nz = col != 0.0
+        out[nz] += col[nz] * x[k]
+    return out
+
+
+def _decode(label):
+    """(index of the power of r, derivative order of h or None, (profile, its derivative order) or
+    None, derivative order of the operator, section) -- utils.py:85-127"""
+    parts = label.split("_")
+    rx = 6 if parts[0] == "q1" else int(parts[0][1])
+    hx, prof = None, None
+    for q in parts[1:-2]:
+        if q[0] == "h" and len(q) == 2:
+            hx = int(q[1])
+        else:
+            prof = (q[:3], int(q[3]))
+    return rx, hx, prof, int(parts[-2][1]), parts[-1]
+
+
+RPOWERS = [0, 1, 2, 3, 4, 5, -1]  # submatrices.py:119: powers of r that go with h (index 6 is 1/r)
+
+
+def radial_operators(pp: PhysicsParams, radprofs=None, dot="blas", dense=False):
+    """Every radial operator of the run, label -> CSR (N1 x N1, boundary rows empty, the
+    reference's ``<label>.mtx``), from the parameters alone.  `radprofs`: the tables of
+    compute_profiles.py (``cd_eta``, ``cd_lho`` ... -- `profile_tables` makes them from a run's
+    radial_profiles module); needed for anelastic runs, and for magnetic ones whose conductivity is
+    not the uniform one radial_profiles.py ships with."""
+    import scipy.sparse as sp
+    N, ricb, rcmb = pp.N, pp.ricb, pp.rcmb
+    labels, parities = operator_labels(pp)
+    bases = GegenbauerBases(N)
+    gorder = gegenbauer_orders(pp)
+    radprofs = dict(radprofs or {})
+    if pp.magnetic and "cd_eta" not in radprofs:
+        # radial_profiles.py:252-262 as shipped: uniform conductivity
+        radprofs["cd_eta"] = profile_table(lambda r: 1. / np.ones_like(r), 1, N, ricb, rcmb)
+    if pp.anelastic and "cd_lho" not in radprofs:
+        raise ValueError("anelastic = 1: pass radprofs=profile_tables(pp, <the run's radial_profiles module>)")
+    cnorm = field_normalisation(pp) if pp.magnetic else None
+    rp, rdh = {}, {}
+
+    def rpower(rx):
+        if rx not in rp:
+            rp[rx] = chebco(rx, N, TOL, ricb, rcmb)
+        return rp[rx]
+
+    def c0_series(rx, hx, prof):
+        if hx is not None:
+            if (rx, hx) not in rdh:
+                rdh[rx, hx] = cnorm * _dct_coefficients(background_field(_nodes(N, ricb, rcmb), pp.B0, RPOWERS[rx], hx), N, TOL)
+            return rdh[rx, hx]
+        if prof is not None:
+            ck = radprofs["cd_" + prof[0]][:, prof[1]]
+            return ck if rx == 0 else series_product(rpower(rx), ck)
+        return rpower(rx)
+
+    mult = {}
+    out = {}
+    for lab, vp in zip(labels, parities):
+        rx, hx, prof, dx, sec = _decode(lab)
+        key = (lab[:-2], vp)
+        if key not in mult:
+            c0 = c0_series(rx, hx, prof)
+            mult[key] = multiplication(c0 if dx == 0 else bases.S[dx].apply(c0), dx, vp, dot=dot)
+        M = mult[key]
+        gb = gorder[sec]
+        G = bases.G[gb][gb - dx]
+        if M is None:
+            # a vanishing series (second derivative of an axial field ...): the reference's 0 * D
+            M = np.zeros((N, N))
+        M = times_derivative(M if G is None else G.apply(M), dx, N, ricb, rcmb)
+        if ricb == 0:
+            if hx is not None or prof is not None:
+                raise NotImplementedError("profile operators without inner core")
+            operator_parity = 1 - ((rx + dx) % 2) * 2
+            overall = vp * operator_parity
+            M = M[int((1 - overall) / 2)::2, int((1 - vp) / 2)::2]
+            chop = gb // 2
+        else:
+            chop = gb
+        if chop > 0:
+            M = np.vstack([np.zeros((chop, M.shape[1])), M[:-chop, :]])
+        out[lab] = M if dense else sp.csr_matrix(M)
+    return out
+
+
+def run_profiles(pp: PhysicsParams):
+    """The profile tables of the run in the current directory: from its radProfs.mat when
+    compute_profiles.py has been run, else from its radial_profiles module (bin/ is on sys.path
+    once the driver has imported `parameters`); None when the run needs none."""
+    if not (pp.anelastic or pp.magnetic):
+        return None
+    if os.path.exists("radProfs.mat"):
+        import scipy.io as sio
+        return {k: v for k, v in sio.loadmat("radProfs.mat").items() if k.startswith("cd_")}
+    try:
+        import radial_profiles as rap
+    except ImportError:
+        if pp.anelastic:
+            raise
+        return None  # magnetic, Boussinesq: the uniform conductivity radial_profiles.py ships with
+    return profile_tables(pp, rap)
+
+
+def write_mtx(directory, operators):
+    """``<label>.mtx`` files as submatrices.py:588 writes them (for the reference's assemble.py)."""
+    import scipy.io as sio
+    import scipy.sparse as sp
+    for lab, M in operators.items():
+        sio.mmwrite(os.path.join(directory, lab + ".mtx"), sp.csr_matrix(M))
+
+
+def main(argv=None):
+    """``python -m kore_b200.radial [ncpus]`` in a run directory: the ``.mtx`` files of
+    ``./bin/submatrices.py ncpus`` (the argument is accepted and ignored: one core, a second or so)."""
+    import sys
+    from timeit import default_timer as timer
+    from .solve import import_parameters
+    tic = timer()
+    par = import_parameters(os.getcwd())
+    try:
+        import utils as ut
+    except ImportError:
+        ut = None
+    pp = PhysicsParams.from_modules(par, ut)
+    print("N =", pp.N, ", lmax =", pp.lmax)
+    ops = radial_operators(pp, radprofs=run_profiles(pp))
+    write_mtx(".", ops)
+    print("Submatrices generated and written to disk in", timer() - tic, "seconds")
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

@@ -20,6 +20,8 @@ With `-kb_assemble` (or when there is no A.npz but the `*.mtx` radial operators 
 bin/submatrices.py are present) the run skips bin/assemble.py as well: the pencil is assembled on
 the GPU from the radial operators (kore_b200/assembly.py; hydrodynamic, Boussinesq thermal and
 axial / dipole magnetic set-ups) -- the same matrices, bit for bit, without A.npz / B.npz ever being written or read.
+When the `*.mtx` files are absent too (or with `-kb_operators`), bin/submatrices.py is skipped as
+well: the radial operators come from parameters.py alone (kore_b200/radial.py).
 `-kb_diagnose` adds power_balance.dat (kore_b200/diagnostics.py), `-kb_npz` adds eigenpairs.npz
 (eigenvalues, the complex solution block and the row ranges of the fields, binary).
 The forced right-hand side comes from B_forced.npz when it exists, else (forcing = 7, libration) it
@@ -129,13 +131,19 @@ def main(argv=None, device=0):
     N1, n, sizmat, symmB0 = kore_sizes(par)
 
     import glob
-    on_device = opts.hasName("kb_assemble") or (not os.path.exists("A.npz") and bool(glob.glob("*.mtx")))
+    on_device = (opts.hasName("kb_assemble") or opts.hasName("kb_operators")
+                 or (not os.path.exists("A.npz") and bool(glob.glob("*.mtx"))))
     A = asm_inputs = None
     if on_device:
         from . import assembly as _assembly
         pp = _assembly.PhysicsParams.from_modules(par)
         pp.check_supported()
-        asm_inputs = (pp, _assembly.load_operators("."))
+        if opts.hasName("kb_operators") or not glob.glob("*.mtx"):
+            from . import radial as _radial
+            operators = _radial.radial_operators(pp, radprofs=_radial.run_profiles(pp))
+        else:
+            operators = _assembly.load_operators(".")
+        asm_inputs = (pp, operators)
         layout = kb.ChainLayout.from_params(N1, par.m, par.lmax, par.symm, symmB0, par.hydro, par.magnetic,
                                             par.thermal, par.compositional)
     else:

@@ -79,6 +79,8 @@ def main():
         os.makedirs(out, exist_ok=True)
         for fn in ("operators.npz", "asm_params.json"):
             shutil.copy(os.path.join(tmp, fn), os.path.join(out, fn))
+        if os.path.exists(os.path.join(tmp, "radprofs.npz")):
+            shutil.copy(os.path.join(tmp, "radprofs.npz"), os.path.join(out, "radprofs.npz"))
         for fn in ("A.npz", "B.npz", "B_forced.npz"):
             src = os.path.join(tmp, fn)
             if not os.path.exists(src):

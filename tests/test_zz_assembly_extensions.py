@@ -170,3 +170,29 @@ def test_device_assembles_the_anelastic_program_bitwise(lib, name):
         jp, jx, w = s.get_assembled("B")
     assert np.array_equal(ip, A_ref.indptr) and np.array_equal(ix, A_ref.indices) and np.array_equal(v, A_ref.data)
     assert np.array_equal(jp, B_ref.indptr) and np.array_equal(jx, B_ref.indices) and np.array_equal(w, B_ref.data)
+
+
+# ------------------------------------------------------------- from the parameter file alone (radial.py)
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["spinover", "dormy"])
+def test_pencil_from_the_parameters_alone_against_the_oracle(lib, name):
+    # no submatrices.py, no assemble.py: radial operators on the host (kore_b200/radial.py, bit for bit the
+    # reference's: tests/test_radial.py), the pencil assembled on the GPU, the reference's golden eigenvalue
+    # (tests/spinover/reference.eig through the pinned oracle values of the fixture)
+    from kore_b200 import radial
+    case = load_case(name)
+    pj, pp, ops_ref, A_ref, _ = fixture(name)
+    ops = radial.radial_operators(pp)
+    assert sorted(ops) == sorted(ops_ref)
+    m = case.meta
+    with lib.Solver(0) as s:
+        asm.assemble(s, pp, ops)
+        ip, ix, v = s.get_assembled("A")
+        assert np.array_equal(ip, A_ref.indptr) and np.array_equal(ix, A_ref.indices)
+        assert np.max(np.abs(v - A_ref.data)) <= 1e-13 * np.max(np.abs(A_ref.data))
+        s.set_chain(case.perm, case.nodeptr)
+        s.factor(case.tau)
+        lam, X, info = s.eigs(m["nev"], which=m["which_eigenpairs"], target=case.tau, tol=m["tol"], maxit=m["maxit"])
+    assert info["nconv"] >= m["nev"]
+    for z in case.oracle["eig"]:
+        assert np.min(np.abs(lam - z)) <= 1e-9 * abs(z), (z, lam)

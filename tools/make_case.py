@@ -120,6 +120,12 @@ def main():
             cwd=work, env=env).decode().strip().splitlines()[-1]
         with open(os.path.join(a.out, "asm_params.json"), "w") as f:
             json.dump(json.loads(probe), f, indent=1, sort_keys=True)
+    if a.asm and os.path.exists(os.path.join(work, "radProfs.mat")):
+        # the tables compute_profiles.py handed to submatrices.py (kore_b200/radial.py takes them as `radprofs`)
+        import numpy as np
+        import scipy.io as sio
+        prof = {k: v for k, v in sio.loadmat(os.path.join(work, "radProfs.mat")).items() if k.startswith("cd_")}
+        np.savez_compressed(os.path.join(a.out, "radprofs.npz"), **prof)
     if a.keep:
         print("scratch kept at", work)
     else:
