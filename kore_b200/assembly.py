@@ -22,7 +22,7 @@ evaluators (the kernel, and the NumPy model in tests/assembly_model.py) perform 
 operations, so the assembled CSR equals the reference's bit for bit (tests/test_assembly.py).
 
 Scope: hydrodynamic (sections u, v), Boussinesq thermal (section h) and -- to rounding, not to the
-bit, see `_magnetic_blocks` -- magnetic (sections f, g; axial or dipole background field, insulating
+bit, see `_magnetic_blocks` -- magnetic (sections f, g; any degree-1 background field, insulating
 boundaries) problems, viscous,
 with or without inner core, eigenvalue (forcing = 0) and forced runs (forcing = 7, 9, 10: the modes
 that work in the reference; A and the forcing vector) -- BASELINE.json configs 1 to 5 -- and anelastic (density-stratified) runs without variable viscosity, bit for bit.  Other
@@ -83,6 +83,8 @@ class PhysicsParams:
     ThermaD: float = 0.0
     # magnetic runs (parameters.py:103-137, 275-278)
     B0: str = "axial"
+    B0_l: int = 1                 # degree of the free-decay-mode field (parameters.py:113)
+    beta: float = 3.0             # guess for its radial wavenumber (parameters.py:112)
     innercore: str = "insulator"
     mantle: str = "insulator"
     Hendrik: float = 0.0
@@ -137,12 +139,15 @@ class PhysicsParams:
             raise ValueError("lmax - m + 1 must be even (parameters.py:301-303): lmax = %d, m = %d" % (self.lmax, self.m))
         bad = []
         if self.magnetic:
-            if self.B0 not in ("axial", "dipole"):
+            # every degree-1 field of the reference shares the axial field's block structure; only the radial
+            # operators r^X h^(j) D^Y differ (operators.py:225-228, 249-252, 285-287, 318-320 ...)
+            if self.B0 not in ("axial", "dipole", "G21 dipole", "Luo_S1", "FDM") or (
+                    self.B0 == "FDM" and self.B0_l != 1):
                 bad.append("B0 = %r" % (self.B0,))
             if self.innercore != "insulator" or self.mantle != "insulator":
                 bad.append("innercore / mantle other than 'insulator'")
-            if self.ricb <= 0:
-                bad.append("magnetic = 1 without inner core")
+            if self.ricb <= 0 and self.B0 == "dipole":
+                bad.append("B0 = %r without inner core" % (self.B0,))
             if self.forcing != 0:
                 bad.append("magnetic = 1 with forcing")
         if self.compositional:
@@ -395,8 +400,15 @@ def _boundary_rows(pp, l=None):
     if pp.magnetic:
         # insulating inner core and mantle: the field matches a potential field on either side
         # (assemble.py:1545-1572 inner row, 1479-1536 outer row); inner boundary first
-        rows["f"] = np.array([l * Ta[:, 0] - pp.ricb * Ta[:, 1], (l + 1) * Tb[:, 0] + pp.rcmb * Tb[:, 1]])
-        rows["g"] = np.array([Ta[:, 0], Tb[:, 0]])
+        if pp.ricb > 0:
+            rows["f"] = np.array([l * Ta[:, 0] - pp.ricb * Ta[:, 1], (l + 1) * Tb[:, 0] + pp.rcmb * Tb[:, 1]])
+            rows["g"] = np.array([Ta[:, 0], Tb[:, 0]])
+        else:
+            # full sphere: the outer row only, on the Chebyshev polynomials of the section's parity -- the field
+            # induced by an antisymmetric background field has the opposite one to the flow's (assemble.py:1479-1492)
+            Tbf, Tbg = Tb[(pp.m + s) % 2::2, :], Tb[(pp.m + 1 - s) % 2::2, :]
+            rows["f"] = np.array([(l + 1) * Tbf[:, 0] + pp.rcmb * Tbf[:, 1]])
+            rows["g"] = np.array([Tbg[:, 0]])
     return rows
 
 

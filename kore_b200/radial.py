@@ -339,8 +339,9 @@ def operator_labels(pp: PhysicsParams):
     vS = vP                                      # entropy perturbation
     if pp.compositional or pp.variable_viscosity or (pp.anelastic and pp.magnetic):
         raise NotImplementedError("radial operators of compositional / variable-viscosity / anelastic magnetic runs")
-    if pp.magnetic and pp.B0 not in BACKGROUND_FIELDS:
-        raise NotImplementedError("B0 = %r" % (pp.B0,))
+    if pp.magnetic and (pp.B0 not in BACKGROUND_FIELDS or (pp.B0 == "FDM" and pp.B0_l != 1)
+                        or (pp.B0 == "dipole" and pp.ricb <= 0)):
+        raise NotImplementedError("B0 = %r%s" % (pp.B0, "" if pp.ricb > 0 else " without inner core"))
     if pp.hydro:
         u = ["r2_D0", "r3_D1", "r4_D2"] + ["r3_D0", "r4_D1"] + ["r0_D0", "r2_D2", "r3_D3", "r4_D4"]
         par += [vP, vP, vP, vT, vT, vP, vP, vP, vP]
@@ -438,15 +439,122 @@ def _field_luo_s1(r, rp, d):
             lambda: -18 * r ** (1 + rp), lambda: -18 * r ** rp][d]()
 
 
+def _bessel_j(l, x, d):
+    """spherical Bessel function of the first kind (d = 0) or its derivative (d = 1); three-term
+    series below 1e-3 (utils.py:433-473)"""
+    import scipy.special as scsp
+    x = np.asarray(x, dtype=float)
+    out = np.zeros_like(x)
+    small = x < 1e-3
+    if np.any(small):
+        xs = x[small]
+        c1 = (2 ** l) * scsp.factorial(l) / scsp.factorial(2 * l + 1)
+        c2 = -(2 ** l) * scsp.factorial(l + 1) / scsp.factorial(2 * l + 3)
+        c3 = (2 ** l) * scsp.factorial(l + 2) / (2 * scsp.factorial(2 * l + 5))
+        if d == 0:
+            out[small] = c1 * xs ** l + c2 * xs ** (l + 2) + c3 * xs ** (l + 4)
+        else:
+            out[small] = c1 * l * xs ** (l - 1) + c2 * (l + 2) * xs ** (l + 1) + c3 * (l + 4) * xs ** (l + 3)
+    out[~small] = scsp.spherical_jn(l, x[~small], derivative=d)
+    return out
+
+
+def _bessel_j_series(l, x, d):
+    """second (d = 2) and third (d = 3) derivative of j_l for small arguments, l = 1 (utils.py:450-461)"""
+    import scipy.special as scsp
+    c2 = -(2 ** l) * scsp.factorial(l + 1) / scsp.factorial(2 * l + 3)
+    c3 = (2 ** l) * scsp.factorial(l + 2) / (2 * scsp.factorial(2 * l + 5))
+    if d == 2:
+        return c2 * (l + 2) * (l + 1) * x ** l + c3 * (l + 4) * (l + 3) * x ** (l + 2)
+    return c2 * (l + 2) * (l + 1) * l * x ** (l - 1) + c3 * (l + 4) * (l + 3) * (l + 2) * x ** (l + 1)
+
+
+def _bessel_y(l, x, d):
+    import scipy.special as scsp
+    return scsp.spherical_yn(l, x, derivative=d)
+
+
+_beta_cache = {}
+
+
+def decay_mode_wavenumber(beta0, l, ricb):
+    """Radial wavenumber of the poloidal free-decay mode of degree l in a shell with insulating
+    boundaries (Zhang & Fearn 1995; utils.py:530-550): the root next to the guess beta0."""
+    key = (beta0, l, ricb)
+    if key not in _beta_cache:
+        import scipy.optimize as so
+
+        def f0(x, ric, l):
+            if ric == 0:
+                return _bessel_j(l - 1, x, 0)            # Gubbins & Roberts (1987)
+            return _bessel_j(l + 1, x * ric, 0) * _bessel_y(l - 1, x, 0) - _bessel_j(l - 1, x, 0) * _bessel_y(l + 1, x * ric, 0)
+        _beta_cache[key] = so.root(f0, beta0, args=(ricb, l)).x[0]
+    return _beta_cache[key]
+
+
+def _field_decay_mode(r, rp, d, b):
+    """free-decay mode of degree 1 with an inner core (utils.py:588-597, 640-646, 697-698, 772-776)"""
+    j, y = _bessel_j, _bessel_y
+    x = b * r
+    y0b, j0b = y(0, b, 0), j(0, b, 0)
+    if d == 0:
+        return (j(1, x, 0) * y0b - j0b * y(1, x, 0)) * r ** rp
+    if d == 1:
+        return (b * (j(1, x, 1) * y0b - j0b * y(1, x, 1))) * r ** rp
+    if d == 2:
+        return ((x ** 2 * j(0, x, 1) + 2 * (j(1, x, 0) - x * j(1, x, 1))) * y0b
+                - j0b * (x ** 2 * y(0, x, 1) + 2 * (y(1, x, 0) - b * r * y(1, x, 1)))) * r ** (-2 + rp)
+    return (-2 * b ** 2 * r ** 2 * j(0, b * r, 1) * y0b - 8 * j(1, b * r, 0) * y0b + 8 * b * r * j(1, b * r, 1) * y0b
+            - b ** 3 * r ** 3 * j(1, b * r, 1) * y0b + 2 * b ** 2 * r ** 2 * j0b * y(0, b * r, 1) + 8 * j0b * y(1, b * r, 0)
+            - 8 * b * r * j0b * y(1, b * r, 1) + b ** 3 * r ** 3 * j0b * y(1, b * r, 1)) * r ** (-3 + rp)
+
+
+def _field_decay_mode_sphere(r, rp, d, b):
+    """free-decay mode of degree 1 of a full sphere (utils.py:586-587, 637-638, 685-691, 759-766)"""
+    j = _bessel_j
+    x = b * r
+    if d == 0:
+        return j(1, x, 0) * r ** rp
+    if d == 1:
+        return b * j(1, x, 1) * r ** rp
+    k = x < 1e-3
+    x0, x1 = x[k], x[~k]
+    out = np.zeros_like(r)
+    if d == 2:
+        out[k] = b ** 2 * _bessel_j_series(1, x0, 2) * r[k] ** rp
+        out[~k] = b ** 2 * j(0, x1, 1) * r[~k] ** rp + (2 * (j(1, x1, 0) - x1 * j(1, x1, 1))) * r[~k] ** (-2 + rp)
+    else:
+        out[k] = b ** 3 * _bessel_j_series(1, x0, 3) * r[k] ** rp
+        out[~k] = (-2 * x1 ** 2 * j(0, x1, 1) - 8 * j(1, x1, 0) + x1 * (8 - x1 ** 2) * j(1, x1, 1)) * r[~k] ** (-3 + rp)
+    return out
+
+
 # r**rp times the d-th derivative of the poloidal scalar h(r) of the background field, all of degree l = 1
-BACKGROUND_FIELDS = {"axial": _field_axial, "dipole": _field_dipole, "G21 dipole": _field_g21, "Luo_S1": _field_luo_s1}
+BACKGROUND_FIELDS = {"axial": _field_axial, "dipole": _field_dipole, "G21 dipole": _field_g21, "Luo_S1": _field_luo_s1,
+                     "FDM": _field_decay_mode}
 
 
-def background_field(r, kind, rp, d):
-    """h0 .. h3 of utils.py on radii r > 0 (inner core present)"""
-    if np.any(r <= 0):
-        raise NotImplementedError("background field without inner core")
-    return BACKGROUND_FIELDS[kind](r, rp, d)
+def background_field(r, kind, rp, d, pp=None):
+    """h0 .. h3 of utils.py:555-797: r**rp times the d-th derivative of h.  Without inner core the
+    Chebyshev nodes cover [-rcmb, rcmb]: the values on r < 0 are the mirror image with the parity
+    of the function, (-1)**(l + rp) for even d and (-1)**(l - 1 + rp) for odd d, l = 1."""
+    r = np.asarray(r, dtype=float)
+    pos = r > 0
+    if kind == "FDM":
+        if pp is None or pp.B0_l != 1:
+            raise NotImplementedError("free-decay modes of degree l > 1")
+        mode = _field_decay_mode if pp.ricb > 0 else _field_decay_mode_sphere
+        vals = mode(r[pos], rp, d, decay_mode_wavenumber(pp.beta, pp.B0_l, pp.ricb))
+    elif kind == "dipole" and (pp is None or pp.ricb <= 0):
+        raise NotImplementedError("a dipole (singular at the origin) without inner core")
+    else:
+        vals = BACKGROUND_FIELDS[kind](r[pos], rp, d)
+    out = np.zeros_like(r)
+    out[pos] = vals
+    neg = r < 0
+    if pp is not None and pp.ricb == 0 and np.count_nonzero(pos) == np.count_nonzero(neg):
+        out[neg] = np.flipud(vals) * (-1) ** (1 - (d % 2) + rp)
+    return out
 
 
 def field_normalisation(pp: PhysicsParams):
@@ -454,7 +562,7 @@ def field_normalisation(pp: PhysicsParams):
     l, L = 1, 2
     kind, ricb = pp.B0, pp.ricb
     if pp.cnorm == "rms_cmb":
-        return (np.sqrt(2 * l + 1) / (l * (l + 1) * background_field(np.array([1.0]), kind, 0, 0)))[0]
+        return (np.sqrt(2 * l + 1) / (l * (l + 1) * background_field(np.array([1.0]), kind, 0, 0, pp)))[0]
     if pp.cnorm in ("mag_energy", "Schmitt2012"):
         N = 240
         i = np.arange(0, N)
@@ -462,8 +570,8 @@ def field_normalisation(pp: PhysicsParams):
         sqx = np.sqrt(1 - xk ** 2)
         rk = 0.5 * (1 - ricb) * (xk + 1) + ricb
         r2 = rk ** 2
-        y0 = background_field(rk, kind, 0, 0)
-        y1 = background_field(rk, kind, 0, 1)
+        y0 = background_field(rk, kind, 0, 0, pp)
+        y1 = background_field(rk, kind, 0, 1, pp)
         f0 = 4 * np.pi * L / (2 * l + 1)
         f1 = (L + 1) * y0 ** 2
         f2 = 2 * rk * y0 * y1
@@ -577,7 +685,7 @@ def radial_operators(pp: PhysicsParams, radprofs=None, dot="blas", dense=False):
     def c0_series(rx, hx, prof):
         if hx is not None:
             if (rx, hx) not in rdh:
-                rdh[rx, hx] = cnorm * _dct_coefficients(background_field(_nodes(N, ricb, rcmb), pp.B0, RPOWERS[rx], hx), N, TOL)
+                rdh[rx, hx] = cnorm * _dct_coefficients(background_field(_nodes(N, ricb, rcmb), pp.B0, RPOWERS[rx], hx, pp), N, TOL)
             return rdh[rx, hx]
         if prof is not None:
             ck = radprofs["cd_" + prof[0]][:, prof[1]]
@@ -600,9 +708,15 @@ def radial_operators(pp: PhysicsParams, radprofs=None, dot="blas", dense=False):
             M = np.zeros((N, N))
         M = times_derivative(M if G is None else G.apply(M), dx, N, ricb, rcmb)
         if ricb == 0:
-            if hx is not None or prof is not None:
-                raise NotImplementedError("profile operators without inner core")
-            operator_parity = 1 - ((rx + dx) % 2) * 2
+            # parity of the operator as a function of r (submatrices.py:548-567)
+            if hx is not None:
+                operator_parity = (-1) ** (hx + 1 + RPOWERS[rx] + dx)       # h of an antisymmetric field is odd
+            elif prof is not None:
+                if prof[0] not in ("eta", "roT", "krT"):
+                    raise NotImplementedError("operators of the profile %r without inner core" % prof[0])
+                operator_parity = 1 - ((rx + prof[1] + dx) % 2) * 2         # even profiles
+            else:
+                operator_parity = 1 - ((rx + dx) % 2) * 2
             overall = vp * operator_parity
             M = M[int((1 - overall) / 2)::2, int((1 - vp) / 2)::2]
             chop = gb // 2

@@ -19,7 +19,7 @@ facades in kore_b200/eps.py; everything else keeps the reference's file formats.
 With `-kb_assemble` (or when there is no A.npz but the `*.mtx` radial operators of
 bin/submatrices.py are present) the run skips bin/assemble.py as well: the pencil is assembled on
 the GPU from the radial operators (kore_b200/assembly.py; hydrodynamic, Boussinesq thermal and
-axial / dipole magnetic set-ups) -- the same matrices, bit for bit, without A.npz / B.npz ever being written or read.
+degree-1 magnetic and anelastic set-ups) -- the same matrices, bit for bit, without A.npz / B.npz ever being written or read.
 When the `*.mtx` files are absent too (or with `-kb_operators`), bin/submatrices.py is skipped as
 well: the radial operators come from parameters.py alone (kore_b200/radial.py).
 `-kb_diagnose` adds power_balance.dat (kore_b200/diagnostics.py), `-kb_npz` adds eigenpairs.npz

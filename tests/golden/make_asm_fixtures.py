@@ -50,6 +50,12 @@ NEW_CASES = {
     "asm_magnetic_axial": ("tests/spinover/params.spinover", ["magnetic=1", "N=24", "m=2", "symm=1"]),
     "asm_magnetic_dipole_thermal": ("tests/dormy2004/params.dormy04",
                                     ["magnetic=1", "B0='dipole'", "N=24", "lmax=24", "m=3", "forcing=0"]),
+    # the other degree-1 background fields: the axial field's block structure, other radial operators
+    "asm_magnetic_g21": ("tests/spinover/params.spinover", ["magnetic=1", "B0='G21 dipole'", "N=24", "lmax=17", "m=2", "symm=1"]),
+    "asm_magnetic_luo_s1": ("tests/spinover/params.spinover", ["magnetic=1", "B0='Luo_S1'", "N=24", "lmax=18", "m=1", "symm=-1"]),
+    "asm_magnetic_fdm": ("tests/spinover/params.spinover", ["magnetic=1", "B0='FDM'", "N=24", "lmax=17", "m=0", "symm=1"]),
+    # magnetic full sphere (no inner boundary rows, parity-reduced radial basis), with the heat equation
+    "asm_magnetic_fullsphere": ("tests/jones2000/params.jones", ["magnetic=1", "B0='G21 dipole'", "N=48", "lmax=17", "m=2", "symm=-1"]),
     # anelastic (polytropic background of the params file): wide profile operators; bit for bit again
     "asm_anelastic": ("tests/dormy2004/params.dormy04", ["anelastic=1", "N=24", "lmax=24", "m=3"]),
     "asm_anelastic_stressfree": ("tests/dormy2004/params.dormy04",

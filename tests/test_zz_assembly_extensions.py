@@ -23,7 +23,12 @@ import assembly_model as am
 from conftest import GOLDEN, load_case
 from kore_b200 import assembly as asm
 
-CASES = ["magnetic_small", "asm_magnetic_axial", "asm_magnetic_dipole_thermal"]
+CASES = ["magnetic_small", "asm_magnetic_axial", "asm_magnetic_dipole_thermal",
+         # the other degree-1 fields (Gerick's dipole, Luo & Jackson's S1, a free-decay mode; m = 2, 1, 0): the axial
+         # field's programs on other radial operators
+         "asm_magnetic_g21", "asm_magnetic_luo_s1", "asm_magnetic_fdm",
+         # full sphere (G21 dipole, internal heating, m = 2 antisymmetric): outer boundary rows only, parity-reduced basis
+         "asm_magnetic_fullsphere"]
 
 
 def fixture(name):
@@ -92,7 +97,7 @@ def test_magnetic_pencil_has_the_oracles_eigenvalues():
 
 def test_other_magnetic_setups_are_refused():
     pj, pp, ops, _, _ = fixture("asm_magnetic_axial")
-    for kw in (dict(B0="Luo_S2"), dict(innercore="TWA"), dict(mantle="TWA"), dict(ricb=0.0), dict(forcing=7)):
+    for kw in (dict(B0="Luo_S2"), dict(B0="FDM", B0_l=2), dict(innercore="TWA"), dict(mantle="TWA"), dict(ricb=0.0, B0="dipole"), dict(forcing=7)):
         q = asm.PhysicsParams.from_dict({**pp.__dict__, **kw})
         with pytest.raises(NotImplementedError):
             asm.build_program_A(q, ops)

@@ -4,10 +4,12 @@ container only: needs /root/reference).  Every trial draws a parameter set (m, s
 thermal on/off with its heating mode and boundary conditions, inner core or full sphere, Ekman number, forcing
 mode, truncation), runs the reference stages through tools/make_case.py --asm and compares what
 kore_b200.assembly + the NumPy model of the kernels (tests/assembly_model.py) produce with A.npz / B.npz:
-pattern and values, bit for bit.  With a third argument `magnetic` the trials are magnetic runs (axial or dipole
-background field, insulating boundaries, with or without the heat equation) and the bar is the rounding-level one of
+pattern and values, bit for bit.  With a third argument `magnetic` the trials are magnetic runs (any degree-1
+background field, shell or full sphere, insulating boundaries, with or without the heat equation) and the bar is the rounding-level one of
 tests/test_zz_assembly_extensions.py: B bit for bit, every block of A within 1e-13 of its largest entry.
-`anelastic` instead draws density-stratified runs (bit for bit again).
+`anelastic` instead draws density-stratified runs (bit for bit again).  In every trial the radial operators are also
+generated from the parameters alone (kore_b200/radial.py, with the trial's radProfs tables) and compared with the ones
+the reference's submatrices.py wrote: label set and every entry, bit for bit.
 Usage: tools/fuzz_assembly.py [ntrials] [seed] [magnetic | anelastic]."""
 import json
 import os
@@ -23,6 +25,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import assembly_model as am  # noqa: E402
 from kore_b200 import assembly as asm  # noqa: E402
+from kore_b200 import radial  # noqa: E402
 
 
 def load(fn):
@@ -49,15 +52,17 @@ def block_relative_error(A, A_ref, N1):
 
 def draw_magnetic(rng):
     thermal = int(rng.integers(0, 2))
+    full = int(rng.integers(0, 4) == 0)
     params = "tests/dormy2004/params.dormy04" if thermal else "tests/spinover/params.spinover"
     m = int(rng.integers(0, 5))
     nl = 2 * int(rng.integers(4, 9))
-    ov = ["magnetic=1", "B0='%s'" % rng.choice(["axial", "dipole"]), "m=%d" % m, "symm=%d" % rng.choice([-1, 1]),
-          "N=%d" % rng.choice([16, 20, 24]), "lmax=%d" % (nl + m - 1), "Ek=%g" % (10.0 ** rng.uniform(-5, -2)),
-          "ricb=%.3f" % rng.uniform(0.2, 0.7), "bci=%d" % rng.integers(0, 2), "bco=%d" % rng.integers(0, 2),
+    fields = ["axial", "G21 dipole", "Luo_S1", "FDM"] + ([] if full else ["dipole"])
+    ov = ["magnetic=1", "B0='%s'" % rng.choice(fields), "m=%d" % m, "symm=%d" % rng.choice([-1, 1]),
+          "N=%d" % (rng.choice([16, 20, 24]) * (2 if full else 1)), "lmax=%d" % (nl + m - 1), "Ek=%g" % (10.0 ** rng.uniform(-5, -2)),
+          "ricb=%s" % ("0" if full else "%.3f" % rng.uniform(0.2, 0.7)), "bci=%d" % rng.integers(0, 2), "bco=%d" % rng.integers(0, 2),
           "Lambda=%g" % (10.0 ** rng.uniform(-2, 0.5)), "Pm=%g" % (10.0 ** rng.uniform(-4, -1)), "forcing=0"]
     if thermal:
-        ov += ["heating='%s'" % rng.choice(["differential", "internal"]), "Ra_gap=%g" % (10.0 ** rng.uniform(4, 7))]
+        ov += ["heating='%s'" % rng.choice(["internal"] if full else ["differential", "internal"]), "Ra_gap=%g" % (10.0 ** rng.uniform(4, 7))]
     return params, ov
 
 
@@ -124,6 +129,10 @@ def main():
         ops = asm.load_operators_npz(os.path.join(out, "operators.npz"))
         pA = asm.build_program_A(pp, ops)
         ok = True
+        rpf = os.path.join(out, "radprofs.npz")
+        mine = radial.radial_operators(pp, radprofs=dict(np.load(rpf)) if os.path.exists(rpf) else None)
+        ops_ok = sorted(mine) == sorted(ops) and all(np.array_equal(mine[k].toarray(), ops[k].toarray()) for k in ops)
+        ok &= ops_ok
         if pp.forcing == 0:
             pB = asm.build_program_B(pp, ops)
             bn = asm.frobenius_norm(am.evaluate(pB).data)
@@ -141,7 +150,8 @@ def main():
         else:
             ok &= same(am.evaluate(pA), load(os.path.join(out, "A.npz")))
         bad += not ok
-        print("trial %d: %s  %s" % (t, note if ok else "MISMATCH", " ".join(ov)), flush=True)
+        note += "; %d radial operators %s" % (len(ops), "bit-identical" if ops_ok else "DIFFER")
+        print("trial %d: %s  %s" % (t, note if ok else "MISMATCH " + note, " ".join(ov)), flush=True)
         shutil.rmtree(out, ignore_errors=True)
     print("%d mismatches in %d trials" % (bad, ntrials))
     return 1 if bad else 0
