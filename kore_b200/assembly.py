@@ -89,6 +89,12 @@ class PhysicsParams:
     mantle: str = "insulator"
     Hendrik: float = 0.0
     MagnetD: float = 0.0
+    # thin conducting layer on the fluid side of a boundary ('TWA'; parameters.py:115-131)
+    mu: float = 1.0
+    c_icb: float = 0.0
+    c1_icb: float = 0.0
+    c_cmb: float = 0.0
+    c1_cmb: float = 0.0
     cnorm: object = "mag_energy"  # normalisation of the background field (parameters.py:144-155; radial.py only)
 
     @classmethod
@@ -144,8 +150,8 @@ class PhysicsParams:
             if self.B0 not in ("axial", "dipole", "G21 dipole", "Luo_S1", "FDM") or (
                     self.B0 == "FDM" and self.B0_l != 1):
                 bad.append("B0 = %r" % (self.B0,))
-            if self.innercore != "insulator" or self.mantle != "insulator":
-                bad.append("innercore / mantle other than 'insulator'")
+            if self.innercore not in ("insulator", "TWA") or self.mantle not in ("insulator", "TWA"):
+                bad.append("innercore / mantle other than 'insulator' or 'TWA'")
             if self.ricb <= 0 and self.B0 == "dipole":
                 bad.append("B0 = %r without inner core" % (self.B0,))
             if self.forcing != 0:
@@ -155,10 +161,11 @@ class PhysicsParams:
         if self.anelastic:
             if self.variable_viscosity:
                 bad.append("variable_viscosity = 1")
-            if self.magnetic:
-                bad.append("anelastic = 1 with magnetic = 1")
             if self.ricb <= 0:
                 bad.append("anelastic = 1 without inner core")
+            if self.dipole:
+                bad.append("anelastic = 1 with a dipole field (the reference's viscous terms then refer to operators "
+                           "submatrices.py does not generate)")
             if (self.bci == 0 and self.lho1_icb is None) or (self.bco == 0 and self.lho1_cmb is None):
                 bad.append("anelastic = 1 with stress-free boundaries but without lho1_icb / lho1_cmb "
                            "(d ln(rho) / dr at the boundaries; PhysicsParams.from_modules(par, ut) computes them)")
@@ -398,17 +405,36 @@ def _boundary_rows(pp, l=None):
         h.append(Ta[:, 0] if pp.bci_thermal == 0 else Ta[:, 1])
     rows["u"], rows["v"], rows["h"] = np.array(u), np.array(v), np.array(h)
     if pp.magnetic:
-        # insulating inner core and mantle: the field matches a potential field on either side
-        # (assemble.py:1545-1572 inner row, 1479-1536 outer row); inner boundary first
         if pp.ricb > 0:
-            rows["f"] = np.array([l * Ta[:, 0] - pp.ricb * Ta[:, 1], (l + 1) * Tb[:, 0] + pp.rcmb * Tb[:, 1]])
-            rows["g"] = np.array([Ta[:, 0], Tb[:, 0]])
+            Tbf = Tbg = Tb
         else:
             # full sphere: the outer row only, on the Chebyshev polynomials of the section's parity -- the field
             # induced by an antisymmetric background field has the opposite one to the flow's (assemble.py:1479-1492)
             Tbf, Tbg = Tb[(pp.m + s) % 2::2, :], Tb[(pp.m + 1 - s) % 2::2, :]
-            rows["f"] = np.array([(l + 1) * Tbf[:, 0] + pp.rcmb * Tbf[:, 1]])
-            rows["g"] = np.array([Tbg[:, 0]])
+
+        def thin_layer(T, Tg, rj, eps, c, c1):
+            # a thin conducting layer between the fluid and the insulator (assemble.py:1383-1467)
+            mu_vf = 1 / pp.mu
+            F, F1, F2 = rj * T[:, 0], rj * T[:, 1] + T[:, 0], 2 * T[:, 1] + rj * T[:, 2]
+            G, G1 = rj * Tg[:, 0], rj * Tg[:, 1] + Tg[:, 0]
+            kj = (l + 0.5) * eps - 0.5
+            nabF = F2 - l * (l + 1) * F / rj
+            return (mu_vf * F1 + (kj / rj) * F + eps * kj * c * F1 + eps * c1 * rj * (mu_vf + 0.5 * eps * kj * c) * nabF,
+                    G + eps * rj * c1 * G1)
+        # insulating inner core and mantle: the field matches a potential field on either side
+        # (assemble.py:1545-1572 inner row, 1479-1536 outer row); inner boundary first
+        if pp.mantle == "TWA":
+            fo, go = thin_layer(Tbf, Tbg, pp.rcmb, 1, pp.c_cmb, pp.c1_cmb)
+        else:
+            fo, go = (l + 1) * Tbf[:, 0] + pp.rcmb * Tbf[:, 1], Tbg[:, 0]
+        if pp.ricb > 0:
+            if pp.innercore == "TWA":
+                fi, gi = thin_layer(Ta, Ta, pp.ricb, -1, pp.c_icb, pp.c1_icb)
+            else:
+                fi, gi = l * Ta[:, 0] - pp.ricb * Ta[:, 1], Ta[:, 0]
+            rows["f"], rows["g"] = np.array([fi, fo]), np.array([gi, go])
+        else:
+            rows["f"], rows["g"] = np.array([fo]), np.array([go])
     return rows
 
 
@@ -570,7 +596,16 @@ def _magnetic_blocks(b, pp, secs):
         # coefficients formed in extended precision as the reference does, then rounded once
         return [(float(ld(C) * ld(c)), lab) for c, lab in terms]
 
-    eta = lambda k, p, d, s_: "r%d_eta%d_D%d_%s" % (k + (d2 if s_ == "f" else d3), p, d, s_)  # noqa: E731
+    # anelastic runs: the field equations carry the density (operators.py:445-462, 660-689) and the toroidal
+    # induction three more terms with d ln(rho)/dr (:571-629)
+    rho = "rho0_" if pp.anelastic else ""
+
+    def eta(k, p, d, s_):
+        k += d2 if s_ == "f" else d3
+        if not pp.anelastic:
+            return "r%d_eta%d_D%d_%s" % (k, p, d, s_)
+        return ("r%d_eho0_D%d_%s" % (k, d, s_)) if p == 0 else ("r%d_eta1_rho0_D%d_%s" % (k, d, s_))
+    gl_ = lambda k, h, d: "r%d_h%d_lho1_D%d_g" % (k + d3, h, d)  # noqa: E731
     for l in secs["f"][1]:  # ---- poloidal field rows: induction by the flow, diffusion, time derivative
         l = int(l)
         L = l * (l + 1)
@@ -586,7 +621,7 @@ def _magnetic_blocks(b, pp, secs):
             b.add(r, c, Group(RE, +1, [], _lin(b, *ext(C, (-(lx + 3), f_(0, 0, 0)), (-(lx + 1), f_(1, 1, 0)), (-2, f_(1, 0, 1))))))
         c = _block_of(secs["v"], l)
         b.add(r, c, Group(IM, +1, [], _lin(b, (-2 * m, f_(1, 0, 0)))))
-        b.add(r, r, Group(IM, +1, [L, wf], _lin(b, (1, "r%d_D0_f" % (2 + d2)))))
+        b.add(r, r, Group(IM, +1, [L, wf], _lin(b, (1, "r%d_%sD0_f" % (2 + d2, rho)))))
         b.add(r, r, Group(RE, -1, [L, Md], _lin(b, (-L, eta(0, 0, 0, "f")), (2, eta(1, 0, 1, "f")), (1, eta(2, 0, 2, "f")))))
 
     sg = -1 if pp.dipole else 1  # sign of the eta' terms of the toroidal diffusion (operators.py:684, 689)
@@ -603,15 +638,22 @@ def _magnetic_blocks(b, pp, secs):
             terms = ((1, g_(0, 0, 1)), (1, g_(1, 1, 1)), (-(ld(L) + 1), "q1_h0_D0_g"), (1, g_(0, 1, 0)),
                      (ld(L) / 2, g_(1, 2, 0)), (1, g_(1, 0, 2)))
         b.add(r, c, Group(IM, +1, [], _lin(b, *ext(2 * m, *terms))))
+        if pp.anelastic:
+            half = (lx ** 2 + lx + 2) if pp.dipole else (ld(L) + 2)
+            b.add(r, c, Group(IM, +1, [], _lin(b, *ext(2 * m, (-ld(L) / 2, gl_(1, 1, 0)), (-half / 2, gl_(0, 0, 0)), (-1, gl_(1, 0, 1))))))
         c = _block_of(secs["v"], l - 1)
         if c is not None:
             C = (lx ** 2 - 1) * np.sqrt(lx ** 2 - m ** 2) / (2 * lx - 1)
             b.add(r, c, Group(RE, +1, [], _lin(b, *ext(C, (lx, g_(0, 0, 0)), (-2, g_(1, 0, 1)), (lx - 2, g_(1, 1, 0))))))
+            if pp.anelastic:
+                b.add(r, c, Group(RE, +1, [], _lin(b, *ext(2 * C, (1, gl_(1, 0, 0))))))
         c = _block_of(secs["v"], l + 1)
         if c is not None:
             C = lx * (lx + 2) * np.sqrt((lx + 1) ** 2 - m ** 2) / (3 + 2 * lx)
             b.add(r, c, Group(RE, +1, [], _lin(b, *ext(C, (-2, g_(1, 0, 1)), (-(lx + 1), g_(0, 0, 0)), (-(lx + 3), g_(1, 1, 0))))))
-        b.add(r, r, Group(IM, +1, [L, wf], _lin(b, (1, "r%d_D0_g" % (2 + d3)))))
+            if pp.anelastic:
+                b.add(r, c, Group(RE, +1, [], _lin(b, *ext(2 * C, (1, gl_(1, 0, 0))))))
+        b.add(r, r, Group(IM, +1, [L, wf], _lin(b, (1, "r%d_%sD0_g" % (2 + d3, rho)))))
         b.add(r, r, Group(RE, -1, [L, Md], _lin(b, (2, eta(1, 0, 1, "g")), (-L, eta(0, 0, 0, "g")), (1, eta(2, 0, 2, "g")),
                                                 (sg, eta(1, 1, 0, "g")), (sg, eta(2, 1, 1, "g")))))
 
@@ -632,7 +674,8 @@ def build_program_B(pp: PhysicsParams, operators: dict) -> AsmProgram:
         r = _block_of(secs["v"], l)
         b.add(r, r, Group(0, -1, [l * (l + 1)], _lin(b, (1, "r%d_D0_v" % (5 if pp.dipole else 2)))))
     if pp.magnetic:
-        for name, lab in (("f", "r%d_D0_f" % (4 if pp.dipole else 2)), ("g", "r%d_D0_g" % (5 if pp.dipole else 2))):
+        rho = "rho0_" if pp.anelastic else ""
+        for name, lab in (("f", "r%d_%sD0_f" % (4 if pp.dipole else 2, rho)), ("g", "r%d_%sD0_g" % (5 if pp.dipole else 2, rho))):
             for l in secs[name][1]:
                 l = int(l)
                 r = _block_of(secs[name], l)

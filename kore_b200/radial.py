@@ -337,8 +337,8 @@ def operator_labels(pp: PhysicsParams):
     vF = -vP                                     # background fields covered here are equatorially antisymmetric
     vG = -vF
     vS = vP                                      # entropy perturbation
-    if pp.compositional or pp.variable_viscosity or (pp.anelastic and pp.magnetic):
-        raise NotImplementedError("radial operators of compositional / variable-viscosity / anelastic magnetic runs")
+    if pp.compositional or pp.variable_viscosity:
+        raise NotImplementedError("radial operators of compositional / variable-viscosity runs")
     if pp.magnetic and (pp.B0 not in BACKGROUND_FIELDS or (pp.B0 == "FDM" and pp.B0_l != 1)
                         or (pp.B0 == "dipole" and pp.ricb <= 0)):
         raise NotImplementedError("B0 = %r%s" % (pp.B0, "" if pp.ricb > 0 else " without inner core"))
@@ -367,13 +367,20 @@ def operator_labels(pp: PhysicsParams):
             par += [vF] * 4 + [vG] * 3
         labels += _labelit(v, "v", 3 * dip)
     if pp.magnetic:
-        f = ["r2_D0"] + ["r0_h0_D0", "r1_h1_D0", "r1_h0_D1", "r1_h0_D0"] + ["r0_eta0_D0", "r1_eta0_D1", "r2_eta0_D2"]
+        b0 = "r2_rho0_D0" if pp.anelastic else "r2_D0"
+        dif = "eho" if pp.anelastic else "eta"
+        f = [b0] + ["r0_h0_D0", "r1_h1_D0", "r1_h0_D1", "r1_h0_D0"] + ["r0_%s0_D0" % dif, "r1_%s0_D1" % dif, "r2_%s0_D2" % dif]
         par += [vF, vP, vP, vP, vT, vF, vF, vF]
         labels += _labelit(f, "f", 2 * dip)
-        g = (["r2_D0"] + ["r0_h0_D1", "r1_h1_D1", "q1_h0_D0", "r0_h1_D0", "r1_h2_D0", "r1_h0_D2",
-                         "r0_h0_D0", "r1_h0_D1", "r1_h1_D0"]
-             + ["r0_eta0_D0", "r1_eta0_D1", "r2_eta0_D2", "r1_eta1_D0", "r2_eta1_D1"])
-        par += [vG] + [vP] * 6 + [vT] * 3 + [vG] * 5
+        g = [b0] + ["r0_h0_D1", "r1_h1_D1", "q1_h0_D0", "r0_h1_D0", "r1_h2_D0", "r1_h0_D2", "r0_h0_D0", "r1_h0_D1", "r1_h1_D0"]
+        par += [vG] + [vP] * 6 + [vT] * 3
+        if pp.anelastic:
+            g += ["r0_h0_lho1_D0", "r1_h1_lho1_D0", "r1_h0_lho1_D0", "r1_h0_lho1_D1"]
+            par += [vP, vT, vT, vT]
+            g += ["r0_eho0_D0", "r1_eho0_D1", "r2_eho0_D2", "r1_eta1_rho0_D0", "r2_eta1_rho0_D1"]
+        else:
+            g += ["r0_eta0_D0", "r1_eta0_D1", "r2_eta0_D2", "r1_eta1_D0", "r2_eta1_D1"]
+        par += [vG] * 5
         labels += _labelit(g, "g", 3 * dip)
     if pp.thermal and pp.anelastic:
         h = ["r2_roT0_D0", "r1_tds0_D0"]
@@ -619,14 +626,23 @@ def profile_tables(pp: PhysicsParams, rap):
                 t[key] = profile_table(getattr(rap, name), order, N, ricb, rcmb)
     if pp.magnetic:
         t["cd_eta"] = profile_table(rap.magnetic_diffusivity, 1, N, ricb, rcmb)
+        if pp.anelastic:
+            t["cd_eho"] = profile_table(rap.eta_rho, 1, N, ricb, rcmb)
     return t
 
 
 def series_product(ck1, ck2, tol=TOL):
     """Chebyshev coefficients of the product of two Chebyshev series (utils.py:342-348)"""
-    out = _rows_times_vector(multiplication(ck1, 0, 0), ck2)
+    M = multiplication(ck1, 0, 0)
+    out = np.zeros_like(ck2) if M is None else _rows_times_vector(M, ck2)
     out[np.absolute(out) <= tol] = 0.0
     return out
+
+
+def _rows_times_vector_or_zero(ck1, ck2):
+    """the inner product of utils.cheb3Product (:332-339), not thresholded: Mlam(ck1, 0, 0) * ck2"""
+    M = multiplication(ck1, 0, 0)
+    return np.zeros_like(ck2) if M is None else _rows_times_vector(M, ck2)
 
 
 def _rows_times_vector(M, x):
@@ -641,16 +657,16 @@ def _rows_times_vector(M, x):
 
 
 def _decode(label):
-    """(index of the power of r, derivative order of h or None, (profile, its derivative order) or
-    None, derivative order of the operator, section) -- utils.py:85-127"""
+    """(index of the power of r, derivative order of h or None, [(profile, its derivative order) ...],
+    derivative order of the operator, section) -- utils.py:85-127"""
     parts = label.split("_")
     rx = 6 if parts[0] == "q1" else int(parts[0][1])
-    hx, prof = None, None
+    hx, prof = None, []
     for q in parts[1:-2]:
         if q[0] == "h" and len(q) == 2:
             hx = int(q[1])
         else:
-            prof = (q[:3], int(q[3]))
+            prof.append((q[:3], int(q[3])))
     return rx, hx, prof, int(parts[-2][1]), parts[-1]
 
 
@@ -683,13 +699,16 @@ def radial_operators(pp: PhysicsParams, radprofs=None, dot="blas", dense=False):
         return rp[rx]
 
     def c0_series(rx, hx, prof):
+        # submatrices.py:461-508: the series the multiplication matrix is made of
+        cks = [radprofs["cd_" + name][:, order] for name, order in prof]
         if hx is not None:
             if (rx, hx) not in rdh:
                 rdh[rx, hx] = cnorm * _dct_coefficients(background_field(_nodes(N, ricb, rcmb), pp.B0, RPOWERS[rx], hx, pp), N, TOL)
-            return rdh[rx, hx]
-        if prof is not None:
-            ck = radprofs["cd_" + prof[0]][:, prof[1]]
-            return ck if rx == 0 else series_product(rpower(rx), ck)
+            return series_product(rdh[rx, hx], cks[0]) if cks else rdh[rx, hx]
+        if len(cks) == 2:
+            return series_product(rpower(rx), _rows_times_vector_or_zero(cks[0], cks[1]))
+        if len(cks) == 1:
+            return cks[0] if rx == 0 else series_product(rpower(rx), cks[0])
         return rpower(rx)
 
     mult = {}
@@ -711,10 +730,10 @@ def radial_operators(pp: PhysicsParams, radprofs=None, dot="blas", dense=False):
             # parity of the operator as a function of r (submatrices.py:548-567)
             if hx is not None:
                 operator_parity = (-1) ** (hx + 1 + RPOWERS[rx] + dx)       # h of an antisymmetric field is odd
-            elif prof is not None:
-                if prof[0] not in ("eta", "roT", "krT"):
-                    raise NotImplementedError("operators of the profile %r without inner core" % prof[0])
-                operator_parity = 1 - ((rx + prof[1] + dx) % 2) * 2         # even profiles
+            elif prof:
+                if len(prof) > 1 or prof[0][0] not in ("eta", "roT", "krT"):
+                    raise NotImplementedError("operators of the profiles %r without inner core" % (prof,))
+                operator_parity = 1 - ((rx + prof[0][1] + dx) % 2) * 2      # even profiles
             else:
                 operator_parity = 1 - ((rx + dx) % 2) * 2
             overall = vp * operator_parity

@@ -56,6 +56,14 @@ NEW_CASES = {
     "asm_magnetic_fdm": ("tests/spinover/params.spinover", ["magnetic=1", "B0='FDM'", "N=24", "lmax=17", "m=0", "symm=1"]),
     # magnetic full sphere (no inner boundary rows, parity-reduced radial basis), with the heat equation
     "asm_magnetic_fullsphere": ("tests/jones2000/params.jones", ["magnetic=1", "B0='G21 dipole'", "N=48", "lmax=17", "m=2", "symm=-1"]),
+    # thin conducting layers on both boundaries (Roberts, Glatzmaier & Clune 2010), dipole field, axisymmetric
+    "asm_magnetic_thinwall": ("tests/spinover/params.spinover",
+                              ["magnetic=1", "innercore='TWA'", "mantle='TWA'", "B0='dipole'", "N=24", "lmax=17", "m=0", "symm=1",
+                               "c_cmb=0.1", "c1_cmb=0.05", "c_icb=0.2", "c1_icb=0.07", "mu=0.8"]),
+    # anelastic and magnetic: the density enters the field equations, d ln(rho)/dr the toroidal induction (with a
+    # dipole the reference's own viscous terms refer to operators it never generates)
+    "asm_anelastic_magnetic": ("tests/dormy2004/params.dormy04",
+                               ["anelastic=1", "magnetic=1", "B0='Luo_S1'", "N=24", "lmax=20", "m=3", "forcing=0", "Nrho=2.5"]),
     # anelastic (polytropic background of the params file): wide profile operators; bit for bit again
     "asm_anelastic": ("tests/dormy2004/params.dormy04", ["anelastic=1", "N=24", "lmax=24", "m=3"]),
     "asm_anelastic_stressfree": ("tests/dormy2004/params.dormy04",

@@ -28,7 +28,12 @@ CASES = ["magnetic_small", "asm_magnetic_axial", "asm_magnetic_dipole_thermal",
          # field's programs on other radial operators
          "asm_magnetic_g21", "asm_magnetic_luo_s1", "asm_magnetic_fdm",
          # full sphere (G21 dipole, internal heating, m = 2 antisymmetric): outer boundary rows only, parity-reduced basis
-         "asm_magnetic_fullsphere"]
+         "asm_magnetic_fullsphere",
+         # thin conducting layers at both boundaries (innercore = mantle = 'TWA'), dipole field, m = 0
+         "asm_magnetic_thinwall",
+         # density-stratified AND magnetic (Luo_S1 field, heat equation): rho in the field equations, d ln(rho)/dr
+         # in the toroidal induction (operators.py:445-462, 571-629, 660-689)
+         "asm_anelastic_magnetic"]
 
 
 def fixture(name):
@@ -97,7 +102,7 @@ def test_magnetic_pencil_has_the_oracles_eigenvalues():
 
 def test_other_magnetic_setups_are_refused():
     pj, pp, ops, _, _ = fixture("asm_magnetic_axial")
-    for kw in (dict(B0="Luo_S2"), dict(B0="FDM", B0_l=2), dict(innercore="TWA"), dict(mantle="TWA"), dict(ricb=0.0, B0="dipole"), dict(forcing=7)):
+    for kw in (dict(B0="Luo_S2"), dict(B0="FDM", B0_l=2), dict(innercore="perfect conductor, material"), dict(mantle="conducting"), dict(ricb=0.0, B0="dipole"), dict(forcing=7)):
         q = asm.PhysicsParams.from_dict({**pp.__dict__, **kw})
         with pytest.raises(NotImplementedError):
             asm.build_program_A(q, ops)

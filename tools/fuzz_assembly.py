@@ -63,6 +63,14 @@ def draw_magnetic(rng):
           "Lambda=%g" % (10.0 ** rng.uniform(-2, 0.5)), "Pm=%g" % (10.0 ** rng.uniform(-4, -1)), "forcing=0"]
     if thermal:
         ov += ["heating='%s'" % rng.choice(["internal"] if full else ["differential", "internal"]), "Ra_gap=%g" % (10.0 ** rng.uniform(4, 7))]
+    if rng.integers(0, 3) == 0:  # thin conducting layer below the mantle
+        ov += ["mantle='TWA'", "c_cmb=%.3f" % rng.uniform(0, 0.5), "c1_cmb=%.3f" % rng.uniform(0, 0.5), "mu=%.2f" % rng.uniform(0.5, 2)]
+    if not full and rng.integers(0, 3) == 0:  # ... and on top of the inner core
+        ov += ["innercore='TWA'", "c_icb=%.3f" % rng.uniform(0, 0.5), "c1_icb=%.3f" % rng.uniform(0, 0.5)]
+    if not full and rng.integers(0, 3) == 0:  # density-stratified background
+        params = "tests/dormy2004/params.dormy04"
+        ov = [o.replace("'dipole'", "'axial'") for o in ov if not o.startswith("heating=")]  # the reference fails with a dipole
+        ov += ["anelastic=1", "thermal=%d" % thermal, "Nrho=%.2f" % rng.uniform(0.5, 4.0), "polind=%.2f" % rng.uniform(1.0, 3.0)]
     return params, ov
 
 
