@@ -124,12 +124,16 @@ class AssembledPencil:
     assemble.py -- tens of seconds -- and writes / re-reads A.npz for every trial).
 
     ``pp``: `assembly.PhysicsParams` of the run; ``operators``: the radial operators
-    (`assembly.load_operators`); ``factor_of``: Ra -> the buoyancy factor (`buoyancy_factor`).
+    (`assembly.load_operators`), or None to generate them from ``pp`` (kore_b200/radial.py: no
+    submatrices.py run either); ``factor_of``: Ra -> the buoyancy factor (`buoyancy_factor`).
     B does not depend on Ra: its norm is computed at the first trial and reused."""
 
     def __init__(self, pp, operators, factor_of, bnorm=None):
         from . import assembly as _asm
         self._asm = _asm
+        if operators is None:
+            from . import radial as _radial
+            operators = _radial.radial_operators(pp, radprofs=_radial.run_profiles(pp))
         self.pp, self.ops, self.factor_of = pp, operators, factor_of
         self.progB = _asm.build_program_B(pp, operators)
         self.bnorm = bnorm

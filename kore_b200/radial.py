@@ -747,6 +747,36 @@ def radial_operators(pp: PhysicsParams, radprofs=None, dot="blas", dense=False):
     return out
 
 
+def resolution_rule(Ek, m, ncpus=4, g=1.0):
+    """(N, lmax) Kore gives a run of Ekman number Ek by default (parameters.py:6-16, 296-301):
+    N = max(48, even(int(17 Ek^-0.2))), lmax - m + 1 the multiple of 2 ncpus next below g N."""
+    out = int(17 * Ek ** -0.2) if Ek != 0 else 48
+    N = max(48, out + out % 2)
+    return N, int(2 * ncpus * (np.floor_divide(g * N, 2 * ncpus)) + m - 1)
+
+
+class OperatorCache:
+    """Radial operators by what they depend on: the truncation, the radii, which equations are on,
+    the background field and profiles -- and, without inner core only, the parities that go with
+    (m, symm).  A sweep over m, symmetry, Rayleigh / Ekman factors or boundary conditions at fixed
+    resolution generates them once; a ramp whose resolution follows `resolution_rule` generates
+    them once per truncation (the reference re-runs submatrices.py at every step)."""
+
+    def __init__(self, radprofs=None, dot="blas"):
+        self.radprofs, self.dot, self.store = radprofs, dot, {}
+
+    def key(self, pp):
+        labels, parities = operator_labels(pp)
+        field = (pp.B0, pp.B0_l, pp.beta, str(pp.cnorm)) if pp.magnetic else None
+        return (pp.N, pp.ricb, pp.rcmb, tuple(labels), tuple(parities), field, tuple(sorted(gegenbauer_orders(pp).items())))
+
+    def get(self, pp):
+        k = self.key(pp)
+        if k not in self.store:
+            self.store[k] = radial_operators(pp, radprofs=self.radprofs, dot=self.dot)
+        return self.store[k]
+
+
 def run_profiles(pp: PhysicsParams):
     """The profile tables of the run in the current directory: from its radProfs.mat when
     compute_profiles.py has been run, else from its radial_profiles module (bin/ is on sys.path

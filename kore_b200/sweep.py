@@ -82,14 +82,29 @@ def eigen_sweep(A, B, targets, nev, perm, nodeptr, which="TM", device=0, rank=0,
     return out
 
 
+_generated = {}
+
+
+def _operators_of(operators, q):
+    """(radial operators of the parameter set q, a key that tells two sets of operators apart): the dict the
+    caller holds, or operators generated from the parameters (one `radial.OperatorCache` per process when the
+    caller passes None)."""
+    if isinstance(operators, dict):
+        return operators, None
+    from . import radial as _radial
+    cache = operators if operators is not None else _generated.setdefault("cache", _radial.OperatorCache())
+    return cache.get(q), cache.key(q)
+
+
 def parameter_sweep(pp, operators, cases, nev, which="TM", device=0, rank=0, world=1, want_vectors=False,
                     solver_factory=None, **kw):
     """Eigenpairs of a family of pencils that differ in their physical parameters -- azimuthal wavenumber m,
     symmetry, Rayleigh number (buoyancy factor), Ekman-number factors, boundary conditions -- on the same radial
     truncation: `cases` is a list of dicts of `assembly.PhysicsParams` fields to override (plus the optional key
     ``"tau"``: the shift / target of that case; default 0), dealt round-robin to the ranks.  Every pencil is
-    ASSEMBLED ON THE GPU (kore_b200.assembly) from the radial operators, which do not depend on m, symm or the
-    dimensionless numbers, so a survey over m that the reference runs as one assemble.py + solve.py job per value
+    ASSEMBLED ON THE GPU (kore_b200.assembly) from the radial operators (`operators`: a dict as
+    `assembly.load_operators` returns, or None / a `radial.OperatorCache` to generate them from the parameters,
+    once per truncation), which do not depend on m, symm or the dimensionless numbers, so a survey over m that the reference runs as one assemble.py + solve.py job per value
     (tools/subramp.sh-style loops; SURVEY.md 8e: "different azimuthal numbers m are different matrices") is here
     one handle per GPU and, per case, a new assembly program, the layout, one factorisation and one eigensolve.
 
@@ -105,11 +120,12 @@ def parameter_sweep(pp, operators, cases, nev, which="TM", device=0, rank=0, wor
             q = _asm.PhysicsParams.from_dict({**pp.__dict__, **fields})
             q.check_supported()
             tau = complex(case.get("tau", 0.0))
-            # B (and its norm) depends on the degrees present and the thermal set-up only
-            key = (q.m, q.lmax, q.symm, q.thermal, q.heating)
-            res = _asm.assemble(s, q, operators, bnorm=bnorm_of.get(key))
+            ops, okey = _operators_of(operators, q)
+            # B (and its norm) depends on the degrees present, the equations that are on and the radial operators only
+            key = (q.m, q.lmax, q.symm, q.thermal, q.heating, q.magnetic, okey)
+            res = _asm.assemble(s, q, ops, bnorm=bnorm_of.get(key))
             bnorm_of[key] = res["bnorm"]
-            perm, nodeptr = _chain.chain_from_params(q.N1, q.m, q.lmax, q.symm, -1, q.hydro, 0, q.thermal, 0)
+            perm, nodeptr = _chain.chain_from_params(q.N1, q.m, q.lmax, q.symm, -1, q.hydro, q.magnetic, q.thermal, 0)
             s.set_chain(perm, nodeptr)
             s.factor(tau)
             lam, X, info = s.eigs(nev, which=which, target=tau, want_vectors=want_vectors, **kw)
@@ -125,7 +141,9 @@ def track_mode(pp, operators, cases, tau0, nev=3, which="TM", device=0, solver_f
     later case is the eigenvalue tracked in the previous one; of the `nev` pairs computed around the target the one
     closest to it is the tracked mode.  Every pencil is assembled on the GPU; a ramp in Ek, Ra or the boundary
     conditions reuses the same radial operators throughout (the reference re-runs submatrices.py and
-    assemble.py at every step of the ramp).
+    assemble.py at every step of the ramp).  With ``operators=None`` (or a `radial.OperatorCache`) the operators are
+    generated from the parameters (kore_b200/radial.py), so a case may change the truncation too -- the usual ramp
+    in Ekman number with ``N, lmax = radial.resolution_rule(Ek, m)`` at every step.
 
     Returns [(case, tracked eigenvalue, all eigenvalues, info)]."""
     from . import assembly as _asm
@@ -138,10 +156,11 @@ def track_mode(pp, operators, cases, tau0, nev=3, which="TM", device=0, solver_f
         for case in cases:
             q = _asm.PhysicsParams.from_dict({**pp.__dict__, **case})
             q.check_supported()
-            key = (q.m, q.lmax, q.symm, q.thermal, q.heating)
-            res = _asm.assemble(s, q, operators, bnorm=bnorm_of.get(key))
+            ops, okey = _operators_of(operators, q)
+            key = (q.m, q.lmax, q.symm, q.thermal, q.heating, q.magnetic, okey)
+            res = _asm.assemble(s, q, ops, bnorm=bnorm_of.get(key))
             bnorm_of[key] = res["bnorm"]
-            perm, nodeptr = _chain.chain_from_params(q.N1, q.m, q.lmax, q.symm, -1, q.hydro, 0, q.thermal, 0)
+            perm, nodeptr = _chain.chain_from_params(q.N1, q.m, q.lmax, q.symm, -1, q.hydro, q.magnetic, q.thermal, 0)
             s.set_chain(perm, nodeptr)
             s.factor(tau)
             lam, _, info = s.eigs(nev, which=which, target=tau, want_vectors=False, **kw)

@@ -95,3 +95,24 @@ def test_track_mode_follows_the_spinover_mode_down_in_ekman_number():
     assert np.all(np.abs(np.diff(tracked)) < 0.03) and np.all(np.abs(tracked.imag - 1.0) < 0.02)
     ratio = tracked.real[-1] / tracked.real[0]
     assert 0.55 < ratio < 0.75  # (4e-4 / 1e-3)^(1/2) = 0.63
+
+
+def test_track_mode_with_kores_resolution_rule_from_the_parameters_alone():
+    # no operator files: every step takes N, lmax from Kore's own rule (parameters.py:6-16, 296-301) and its radial
+    # operators from kore_b200/radial.py.  Ek = 1e-3 gives N = 68, lmax = 64 -- the spin-over fixture itself, so the
+    # first tracked eigenvalue is the reference's golden value (tests/spinover/reference.eig, rtol 1e-8 there)
+    from kore_b200 import radial
+    base = asm.PhysicsParams.from_dict(json.load(open(os.path.join(GOLDEN, "spinover", "asm_params.json"))))
+    assert radial.resolution_rule(1e-3, 1) == (68, 64) and radial.resolution_rule(1e-8, 1) == (676, 672)
+    assert radial.resolution_rule(1e-7, 1)[0] == 428 and radial.resolution_rule(1e-9, 1)[0] == 1072
+    cases = []
+    for ek in (1e-3, 7e-4):
+        N, lmax = radial.resolution_rule(ek, base.m)
+        cases.append({"Ek": ek, "ViscosD": ek, "N": N, "lmax": lmax})
+    assert (cases[1]["N"], cases[1]["lmax"]) == (72, 72)
+    golden = complex(*json.load(open(os.path.join(GOLDEN, "spinover", "meta.json")))["reference_golden"]["eig"])
+    cache = radial.OperatorCache()
+    out = sweep.track_mode(base, cache, cases, golden, nev=3, solver_factory=OracleSolver)
+    assert len(cache.store) == 2                              # one set of operators per truncation
+    assert abs(out[0][1] - golden) <= 1e-8 * abs(golden)
+    assert out[1][1].real > out[0][1].real and abs(out[1][1] - out[0][1]) < 0.03

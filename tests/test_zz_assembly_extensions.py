@@ -206,3 +206,29 @@ def test_pencil_from_the_parameters_alone_against_the_oracle(lib, name):
     assert info["nconv"] >= m["nev"]
     for z in case.oracle["eig"]:
         assert np.min(np.abs(lam - z)) <= 1e-9 * abs(z), (z, lam)
+
+
+@pytest.mark.gpu
+def test_twin_driver_from_the_parameter_file_alone(tmp_path, monkeypatch, lib):
+    # `python -m kore_b200.solve -kb_operators` in a directory that holds bin/parameters.py and nothing else: no
+    # submatrices.py, no assemble.py, no matrix file -- and the reference's golden eigenvalue (tests/spinover/reference.eig,
+    # rtol 1e-8 in tests/test_spinover.py:21-29) in eigenvalues0.dat
+    import glob
+    import sys
+    from kore_b200 import solve as drv
+    from test_solve_driver import write_operator_dir
+    c, d = write_operator_dir(tmp_path, "spinover")
+    for fn in glob.glob(str(d / "*.mtx")):
+        os.remove(fn)
+    monkeypatch.chdir(d)
+    sys.modules.pop("parameters", None)
+    try:
+        assert drv.main(["-st_type", "sinvert", "-kb_operators"]) == 0
+    finally:
+        sys.modules.pop("parameters", None)
+    assert not glob.glob("*.mtx") and not os.path.exists("A.npz")
+    ev = np.loadtxt("eigenvalues0.dat").reshape(-1, 2)
+    best = ev[np.argmax(ev[:, 0])]                        # test_spinover.py:23: the least damped mode
+    golden = c.meta["reference_golden"]["eig"]
+    assert np.allclose(best, golden, rtol=1e-8, atol=0)
+    assert np.loadtxt("real_flow.field").reshape(2 * c.meta["n"], -1).shape[1] == ev.shape[0]
