@@ -154,8 +154,6 @@ class PhysicsParams:
                 bad.append("innercore / mantle other than 'insulator' or 'TWA'")
             if self.ricb <= 0 and self.B0 == "dipole":
                 bad.append("B0 = %r without inner core" % (self.B0,))
-            if self.forcing != 0:
-                bad.append("magnetic = 1 with forcing")
         if self.compositional:
             bad.append("compositional = 1")
         if self.anelastic:

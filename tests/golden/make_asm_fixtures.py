@@ -60,6 +60,10 @@ NEW_CASES = {
     "asm_magnetic_thinwall": ("tests/spinover/params.spinover",
                               ["magnetic=1", "innercore='TWA'", "mantle='TWA'", "B0='dipole'", "N=24", "lmax=17", "m=0", "symm=1",
                                "c_cmb=0.1", "c1_cmb=0.05", "c_icb=0.2", "c1_icb=0.07", "mu=0.8"]),
+    # libration-forced magnetic run (dipole field)
+    "asm_magnetic_forced": ("tests/spinover/params.spinover",
+                            ["magnetic=1", "B0='dipole'", "forcing=7", "m=2", "symm=1", "N=24", "lmax=15",
+                             "forcing_amplitude_icb=0.7", "forcing_frequency=0.61"]),
     # anelastic and magnetic: the density enters the field equations, d ln(rho)/dr the toroidal induction (with a
     # dipole the reference's own viscous terms refer to operators it never generates)
     "asm_anelastic_magnetic": ("tests/dormy2004/params.dormy04",

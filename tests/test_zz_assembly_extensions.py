@@ -100,9 +100,33 @@ def test_magnetic_pencil_has_the_oracles_eigenvalues():
         assert np.min(np.abs(lam - z)) <= 1e-10 * abs(z)
 
 
+def forced_fixture(name="asm_magnetic_forced"):
+    d = os.path.join(GOLDEN, name)
+    pj = json.load(open(os.path.join(d, "asm_params.json")))
+    pp = asm.PhysicsParams.from_dict(pj)
+    ops = asm.load_operators_npz(os.path.join(d, "operators.npz"))
+    z = np.load(os.path.join(d, "A.npz"))
+    A_ref = sp.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=tuple(z["shape"]))
+    A_ref.sort_indices()
+    z = np.load(os.path.join(d, "B_forced.npz"))
+    rhs = np.asarray(sp.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=tuple(z["shape"])).todense()).ravel()
+    return pp, ops, A_ref, rhs
+
+
+def test_forced_magnetic_program():
+    # libration (forcing = 7) of a magnetic run: A un-normalised with the forcing frequency in every time derivative,
+    # the field's included; the forcing vector is the hydrodynamic one (assemble.py:278-329)
+    pp, ops, A_ref, rhs = forced_fixture()
+    assert pp.magnetic == 1 and pp.forcing == 7
+    A = am.evaluate(asm.build_program_A(pp, ops))
+    assert block_relative_error(A, A_ref, pp.N1).max() <= 1e-13
+    assert abs(A.nnz - A_ref.nnz) <= 1e-3 * A_ref.nnz
+    assert np.array_equal(asm.forcing_vector(pp), rhs)
+
+
 def test_other_magnetic_setups_are_refused():
     pj, pp, ops, _, _ = fixture("asm_magnetic_axial")
-    for kw in (dict(B0="Luo_S2"), dict(B0="FDM", B0_l=2), dict(innercore="perfect conductor, material"), dict(mantle="conducting"), dict(ricb=0.0, B0="dipole"), dict(forcing=7)):
+    for kw in (dict(B0="Luo_S2"), dict(B0="FDM", B0_l=2), dict(innercore="perfect conductor, material"), dict(mantle="conducting"), dict(ricb=0.0, B0="dipole"), dict(forcing=8)):
         q = asm.PhysicsParams.from_dict({**pp.__dict__, **kw})
         with pytest.raises(NotImplementedError):
             asm.build_program_A(q, ops)
@@ -124,6 +148,22 @@ def test_device_assembles_the_magnetic_program_like_the_model(lib, name):
     assert np.array_equal(A.indptr, A_m.indptr) and np.array_equal(A.indices, A_m.indices) and np.array_equal(A.data, A_m.data)
     assert np.array_equal(B.data, B_ref.data)
     assert block_relative_error(A, A_ref, pp.N1).max() <= 1e-13
+
+
+@pytest.mark.gpu
+def test_device_forced_magnetic_solve_against_superlu(lib):
+    # the forced magnetic pencil assembled on the device and solved there, against SuperLU on the reference's A
+    import scipy.sparse.linalg as spl
+    from kore_b200 import chain
+    pp, ops, A_ref, rhs = forced_fixture()
+    x_ref = spl.splu(A_ref.tocsc()).solve(rhs)
+    perm, nodeptr = chain.chain_from_params(pp.N1, pp.m, pp.lmax, pp.symm, -1, pp.hydro, pp.magnetic, pp.thermal, 0)
+    with lib.Solver(0) as s:
+        asm.assemble(s, pp, ops)
+        s.set_chain(perm, nodeptr)
+        s.factor(0.0)
+        x = s.solve(rhs)
+    assert np.linalg.norm(x - x_ref) <= 1e-9 * np.linalg.norm(x_ref)
 
 
 @pytest.mark.gpu

@@ -67,6 +67,11 @@ def draw_magnetic(rng):
         ov += ["mantle='TWA'", "c_cmb=%.3f" % rng.uniform(0, 0.5), "c1_cmb=%.3f" % rng.uniform(0, 0.5), "mu=%.2f" % rng.uniform(0.5, 2)]
     if not full and rng.integers(0, 3) == 0:  # ... and on top of the inner core
         ov += ["innercore='TWA'", "c_icb=%.3f" % rng.uniform(0, 0.5), "c1_icb=%.3f" % rng.uniform(0, 0.5)]
+    if not full and rng.integers(0, 4) == 0:  # libration forcing of a magnetic run (boundary flow, no-slip)
+        mm = int(rng.choice([0, 2]))
+        ov = [o for o in ov if not o.startswith(("m=", "symm=", "lmax=", "bci=", "bco=", "forcing="))]
+        ov += ["m=%d" % mm, "symm=1", "lmax=%d" % (nl + mm - 1), "bci=1", "bco=1", "forcing=7",
+               "forcing_frequency=%.3f" % rng.uniform(-1.5, 1.5), "forcing_amplitude_icb=%.2f" % rng.uniform(0, 1)]
     if not full and rng.integers(0, 3) == 0:  # density-stratified background
         params = "tests/dormy2004/params.dormy04"
         ov = [o.replace("'dipole'", "'axial'") for o in ov if not o.startswith("heating=")]  # the reference fails with a dipole
@@ -154,7 +159,7 @@ def main():
         if magnetic:
             rel = block_relative_error(am.evaluate(pA), load(os.path.join(out, "A.npz")), pp.N1).max()
             ok &= rel <= 1e-13
-            note = "B bit-identical, A within %.1e of the block maxima" % rel
+            note = "%s bit-identical, A within %.1e of the block maxima" % ("B" if pp.forcing == 0 else "forcing vector", rel)
         else:
             ok &= same(am.evaluate(pA), load(os.path.join(out, "A.npz")))
         bad += not ok
