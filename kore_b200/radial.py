@@ -334,7 +334,8 @@ def operator_labels(pp: PhysicsParams):
     vT = -vP
     labels, par = [], []
     dip = pp.dipole and pp.ricb > 0
-    vF = -vP                                     # background fields covered here are equatorially antisymmetric
+    quadrupole = bool(pp.magnetic) and field_degree(pp) == 2
+    vF = vP if quadrupole else -vP               # the induced field has the flow's parity times the background field's
     vG = -vF
     vS = vP                                      # entropy perturbation
     if pp.compositional or pp.variable_viscosity:
@@ -353,6 +354,9 @@ def operator_labels(pp: PhysicsParams):
             u += ["r1_h0_D1", "r2_h1_D1", "r2_h0_D2", "r3_h1_D2", "r0_h0_D0", "r1_h1_D0", "r2_h2_D0",
                   "r3_h3_D0", "r3_h0_D3", "r1_h0_D0", "r2_h1_D0", "r2_h0_D1", "r3_h1_D1", "r3_h0_D2"]
             par += [vF] * 9 + [vG] * 5
+            if quadrupole:
+                u += ["r3_h2_D1", "r3_h2_D0"]
+                par += [vF, vG]
         if pp.thermal:
             u += ["r3_buo0_D0"] if pp.anelastic else ["r4_D0"]
             par += [vS if pp.anelastic else vP]
@@ -446,6 +450,11 @@ def _field_luo_s1(r, rp, d):
             lambda: -18 * r ** (1 + rp), lambda: -18 * r ** rp][d]()
 
 
+def _field_luo_s2(r, rp, d):
+    return [lambda: (157 - 296 * r ** 2 + 143 * r ** 4) * r ** (2 + rp), lambda: 2 * r ** (1 + rp) * (157 - 592 * r ** 2 + 429 * r ** 4),
+            lambda: 2 * r ** rp * (157 - 1776 * r ** 2 + 2145 * r ** 4), lambda: 24 * r ** (1 + rp) * (-296 + 715 * r ** 2)][d]()
+
+
 def _bessel_j(l, x, d):
     """spherical Bessel function of the first kind (d = 0) or its derivative (d = 1); three-term
     series below 1e-3 (utils.py:433-473)"""
@@ -536,15 +545,20 @@ def _field_decay_mode_sphere(r, rp, d, b):
     return out
 
 
-# r**rp times the d-th derivative of the poloidal scalar h(r) of the background field, all of degree l = 1
+# r**rp times the d-th derivative of the poloidal scalar h(r) of the background field; degree l = 1 but for Luo_S2
 BACKGROUND_FIELDS = {"axial": _field_axial, "dipole": _field_dipole, "G21 dipole": _field_g21, "Luo_S1": _field_luo_s1,
-                     "FDM": _field_decay_mode}
+                     "FDM": _field_decay_mode, "Luo_S2": _field_luo_s2}
+
+
+def field_degree(pp):
+    """degree l of the background field (utils.py:45-55); its equatorial symmetry is (-1)**l"""
+    return 2 if pp.B0 == "Luo_S2" else (pp.B0_l if pp.B0 == "FDM" else 1)
 
 
 def background_field(r, kind, rp, d, pp=None):
     """h0 .. h3 of utils.py:555-797: r**rp times the d-th derivative of h.  Without inner core the
     Chebyshev nodes cover [-rcmb, rcmb]: the values on r < 0 are the mirror image with the parity
-    of the function, (-1)**(l + rp) for even d and (-1)**(l - 1 + rp) for odd d, l = 1."""
+    of the function, (-1)**(l + rp) for even d and (-1)**(l - 1 + rp) for odd d."""
     r = np.asarray(r, dtype=float)
     pos = r > 0
     if kind == "FDM":
@@ -560,13 +574,14 @@ def background_field(r, kind, rp, d, pp=None):
     out[pos] = vals
     neg = r < 0
     if pp is not None and pp.ricb == 0 and np.count_nonzero(pos) == np.count_nonzero(neg):
-        out[neg] = np.flipud(vals) * (-1) ** (1 - (d % 2) + rp)
+        out[neg] = np.flipud(vals) * (-1) ** (field_degree(pp) - (d % 2) + rp)
     return out
 
 
 def field_normalisation(pp: PhysicsParams):
-    """utils.py:837-890 (B0_norm) for a degree-1 background field"""
-    l, L = 1, 2
+    """utils.py:837-890 (B0_norm)"""
+    l = field_degree(pp)
+    L = l * (l + 1)
     kind, ricb = pp.B0, pp.ricb
     if pp.cnorm == "rms_cmb":
         return (np.sqrt(2 * l + 1) / (l * (l + 1) * background_field(np.array([1.0]), kind, 0, 0, pp)))[0]
@@ -729,7 +744,7 @@ def radial_operators(pp: PhysicsParams, radprofs=None, dot="blas", dense=False):
         if ricb == 0:
             # parity of the operator as a function of r (submatrices.py:548-567)
             if hx is not None:
-                operator_parity = (-1) ** (hx + 1 + RPOWERS[rx] + dx)       # h of an antisymmetric field is odd
+                operator_parity = (-1) ** (hx + field_degree(pp) + RPOWERS[rx] + dx)  # h has the parity of its degree
             elif prof:
                 if len(prof) > 1 or prof[0][0] not in ("eta", "roT", "krT"):
                     raise NotImplementedError("operators of the profiles %r without inner core" % (prof,))

@@ -42,7 +42,7 @@ def ulp_distance(a, b):
 
 
 def test_fixtures_cover_the_parameter_space():
-    assert len(CASES) >= 30
+    assert len(CASES) >= 35
     kinds = set()
     for name in CASES:
         pp, _, _ = load_case(name)
@@ -155,7 +155,7 @@ def test_unsupported_runs_are_refused():
     with pytest.raises(NotImplementedError):
         radial.radial_operators(pp)
     pp, _, _ = load_case("asm_magnetic_axial")
-    pp.B0 = "Luo_S2"
+    pp.B0, pp.B0_l = "FDM", 2
     with pytest.raises(NotImplementedError):
         radial.radial_operators(pp)
 
