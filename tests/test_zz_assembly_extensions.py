@@ -272,3 +272,22 @@ def test_twin_driver_from_the_parameter_file_alone(tmp_path, monkeypatch, lib):
     golden = c.meta["reference_golden"]["eig"]
     assert np.allclose(best, golden, rtol=1e-8, atol=0)
     assert np.loadtxt("real_flow.field").reshape(2 * c.meta["n"], -1).shape[1] == ev.shape[0]
+
+
+@pytest.mark.gpu
+def test_gpu_jones_search_from_the_parameter_file_alone(lib, tmp_path):
+    # the reference's third test (tests/test_convection_bouss.py:10-25, find_Rac.py) from params.jones alone: radial
+    # operators generated, every trial pencil assembled on the device, golden row of reference.jones digit for digit
+    from kore_b200 import rac
+    from test_rac import JONES_RA_MIN, JONES_ROW, _jones_from_parameters
+    c = load_case("jones")
+    m = c.meta
+    pp, pen = _jones_from_parameters()
+    with rac.GrowthRate(pen, c.perm, c.nodeptr, c.tau, m["nev"], m["which_eigenpairs"], tol=m["tol"],
+                        maxit=m["maxit"]) as g:
+        Ra_c, omega_c, sigma_c = rac.find_rac(g, JONES_RA_MIN)
+        assert 3 <= len(g.history) < 20
+    p = tmp_path / "critical_params.dat"
+    rac.write_critical_params(p, m["Ek"], m["ricb"], Ra_c, m["m"], omega_c)
+    assert p.read_text().strip() == JONES_ROW
+    assert abs(sigma_c) < 1e-6 * abs(omega_c)
