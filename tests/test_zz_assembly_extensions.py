@@ -238,8 +238,10 @@ def test_pencil_from_the_parameters_alone_against_the_oracle(lib, name):
     with lib.Solver(0) as s:
         asm.assemble(s, pp, ops)
         ip, ix, v = s.get_assembled("A")
-        assert np.array_equal(ip, A_ref.indptr) and np.array_equal(ix, A_ref.indices)
-        assert np.max(np.abs(v - A_ref.data)) <= 1e-13 * np.max(np.abs(A_ref.data))
+        # (not the pattern: the last bit of a generated operator is this host's BLAS's, and an entry of A that
+        # cancels to an exact zero on the machine that wrote the fixture may be 1e-17 here)
+        A = sp.csr_matrix((v, ix, ip), shape=A_ref.shape)
+        assert abs(A - A_ref).max() <= 1e-13 * np.max(np.abs(A_ref.data))
         s.set_chain(case.perm, case.nodeptr)
         s.factor(case.tau)
         lam, X, info = s.eigs(m["nev"], which=m["which_eigenpairs"], target=case.tau, tol=m["tol"], maxit=m["maxit"])
