@@ -293,3 +293,12 @@ def test_gpu_jones_search_from_the_parameter_file_alone(lib, tmp_path):
     rac.write_critical_params(p, m["Ek"], m["ricb"], Ra_c, m["m"], omega_c)
     assert p.read_text().strip() == JONES_ROW
     assert abs(sigma_c) < 1e-6 * abs(omega_c)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["asm_forcing9", "asm_forcing9_stressfree", "asm_forcing10"])
+def test_device_assembly_bitwise_of_the_boundary_flow_forcings(lib, name):
+    # forcing = 9 / 10 (assemble.py:360-426): with a stress-free outer boundary the poloidal boundary rows depend on
+    # the degree, one table entry per block row
+    import test_assembly as ta
+    ta.test_device_assembly_bitwise(lib, name)
