@@ -6,7 +6,8 @@ programs with the NumPy model of the assembly kernel (tests/assembly_model.py) a
 It proves nothing about the kernels -- those are covered by the GPU runs of the other test files -- but it
 does catch what a cross-compile cannot: wrong attribute names, shapes, file names, tolerances that the
 reference data cannot meet.  Test infrastructure; never imported by the package.
-Usage: tools/dryrun_gpu_tests.py [test name substring ...]"""
+Usage: tools/dryrun_gpu_tests.py [-m test_module] [test name substring ...]   (default module: the last-sorted
+tests/test_zz_assembly_extensions.py; other modules' GPU tests may need calls the stand-in does not offer)"""
 import inspect
 import os
 import pathlib
@@ -95,12 +96,17 @@ class MonkeyPatch:
 
 def main():
     only = sys.argv[1:]
+    module = "test_zz_assembly_extensions"
+    if only[:1] == ["-m"]:
+        module, only = only[1], only[2:]
     real_lib.Solver = StandInSolver          # kore_b200.eps / rac / sweep construct their solvers through the module
     real_lib.savetxt = lambda path, X, part="real", append=False, nthreads=0: np.savetxt(
         path, (np.asarray(X).real if part == "real" else np.asarray(X).imag) if np.iscomplexobj(X) else X)
     import kore_b200.eps as eps
     eps.savetxt = real_lib.savetxt
-    import test_zz_assembly_extensions as T
+    import importlib
+    StandInLib.KoreB200Error = real_lib.KoreB200Error
+    T = importlib.import_module(module)
     ran = failed = 0
     cwd = os.getcwd()
     for name, fn in sorted(vars(T).items()):
