@@ -60,6 +60,10 @@ NEW_CASES = {
     "asm_magnetic_thinwall": ("tests/spinover/params.spinover",
                               ["magnetic=1", "innercore='TWA'", "mantle='TWA'", "B0='dipole'", "N=24", "lmax=17", "m=0", "symm=1",
                                "c_cmb=0.1", "c1_cmb=0.05", "c_icb=0.2", "c1_icb=0.07", "mu=0.8"]),
+    # radially varying conductivity (the user's radial_profiles.conductivity; PROFILES below): the eta' terms of the
+    # toroidal diffusion, which vanish in every other magnetic fixture
+    "asm_magnetic_conductivity": ("tests/dormy2004/params.dormy04",
+                                  ["magnetic=1", "B0='axial'", "N=24", "lmax=18", "m=1", "symm=-1", "forcing=0"]),
     # libration-forced magnetic run (dipole field)
     "asm_magnetic_forced": ("tests/spinover/params.spinover",
                             ["magnetic=1", "B0='dipole'", "forcing=7", "m=2", "symm=1", "N=24", "lmax=15",
@@ -77,6 +81,7 @@ NEW_CASES = {
                                  ["anelastic=1", "N=24", "lmax=24", "m=3", "bci=0", "bco=0", "bco_thermal=1"]),
     "asm_anelastic_hydro": ("tests/dormy2004/params.dormy04", ["anelastic=1", "thermal=0", "N=24", "lmax=23", "m=0", "symm=-1"]),
 }
+PROFILES = {"asm_magnetic_conductivity": "def conductivity(r):\n    return 1 + 0.5*r**2"}
 EXISTING = ["spinover", "dormy", "jones", "forced_small", "m0_small", "magnetic_small"]
 
 
@@ -96,7 +101,8 @@ def main():
         tmp = "/tmp/asmfix_" + name
         shutil.rmtree(tmp, ignore_errors=True)
         subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "make_case.py"),
-                               "--params", params, "--out", tmp, "--asm"] + ov)
+                               "--params", params, "--out", tmp, "--asm"]
+                              + (["--profiles", PROFILES[name]] if name in PROFILES else []) + ov)
         os.makedirs(out, exist_ok=True)
         for fn in ("operators.npz", "asm_params.json"):
             shutil.copy(os.path.join(tmp, fn), os.path.join(out, fn))

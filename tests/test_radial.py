@@ -42,7 +42,7 @@ def ulp_distance(a, b):
 
 
 def test_fixtures_cover_the_parameter_space():
-    assert len(CASES) >= 35
+    assert len(CASES) >= 36
     kinds = set()
     for name in CASES:
         pp, _, _ = load_case(name)
@@ -143,6 +143,11 @@ def test_profile_tables_and_uniform_conductivity():
     rap = types.SimpleNamespace(magnetic_diffusivity=lambda r: 1. / np.ones_like(r))
     t = radial.profile_tables(pp, rap)
     assert list(t) == ["cd_eta"] and np.array_equal(t["cd_eta"], radprofs["cd_eta"])
+    # a run with its own conductivity profile (tools/make_case.py --profiles; radial_profiles.py:252-262)
+    pp, _, radprofs = load_case("asm_magnetic_conductivity")
+    rap = types.SimpleNamespace(magnetic_diffusivity=lambda r: 1. / (1 + 0.5 * r ** 2))
+    assert np.array_equal(radial.profile_tables(pp, rap)["cd_eta"], radprofs["cd_eta"])
+    assert np.count_nonzero(radprofs["cd_eta"][:, 1]) > 5
     # a derivative column differentiates: d/dr of r^3 = 3 r^2
     tab = radial.profile_table(lambda r: r ** 3, 2, 24, 0.35, 1.0)
     assert np.allclose(tab[:, 1], 3 * radial.chebco(2, 24, 0.0, 0.35, 1.0), atol=1e-9)

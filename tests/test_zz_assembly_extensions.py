@@ -33,7 +33,9 @@ CASES = ["magnetic_small", "asm_magnetic_axial", "asm_magnetic_dipole_thermal",
          "asm_magnetic_thinwall",
          # density-stratified AND magnetic (Luo_S1 field, heat equation): rho in the field equations, d ln(rho)/dr
          # in the toroidal induction (operators.py:445-462, 571-629, 660-689)
-         "asm_anelastic_magnetic"]
+         "asm_anelastic_magnetic",
+         # radially varying conductivity (axial field, heat equation): non-zero eta' terms in the toroidal diffusion
+         "asm_magnetic_conductivity"]
 
 
 def fixture(name):

@@ -52,6 +52,10 @@ def main():
     ap.add_argument("--asm", action="store_true",
                     help="also store the radial operators (operators.npz) and the physics parameters "
                          "(asm_params.json) the device-side assembly needs (kore_b200/assembly.py)")
+    ap.add_argument("--profiles", default=None,
+                    help="Python source appended to the scratch copy of bin/radial_profiles.py: the run's own "
+                         "background profiles (the file is the user's to edit in the reference), e.g. "
+                         "'def conductivity(r): return 1 + 0.5*r**2'")
     ap.add_argument("overrides", nargs="*")
     a = ap.parse_args()
 
@@ -69,6 +73,9 @@ def main():
     with open(os.path.join(work, "bin", "parameters.py"), "w") as f:
         f.write(ptxt)
 
+    if a.profiles:
+        with open(os.path.join(work, "bin", "radial_profiles.py"), "a") as f:
+            f.write("\n\n# --- appended by tools/make_case.py --profiles\n" + a.profiles.replace("\\n", "\n") + "\n")
     env = dict(os.environ)
     env["PYTHONPATH"] = os.path.abspath(STANDIN) + os.pathsep + env.get("PYTHONPATH", "")
     env["PYTHONWARNINGS"] = "ignore"
@@ -99,6 +106,8 @@ def main():
         src = os.path.join(work, fn)
         if os.path.exists(src):
             shutil.copy(src, os.path.join(a.out, fn))
+    if a.profiles:
+        meta["profiles_appended"] = a.profiles
     with open(os.path.join(a.out, "meta.json"), "w") as f:
         json.dump(meta, f, indent=1, sort_keys=True)
     with open(os.path.join(a.out, "parameters.py"), "w") as f:
