@@ -25,8 +25,8 @@ Scope: hydrodynamic (sections u, v), Boussinesq thermal (section h) and -- to ro
 bit, see `_magnetic_blocks` -- magnetic (sections f, g; any degree-1 background field, insulating
 boundaries) problems, viscous,
 with or without inner core, eigenvalue (forcing = 0) and forced runs (forcing = 7, 9, 10: the modes
-that work in the reference; A and the forcing vector) -- BASELINE.json configs 1 to 5 -- and anelastic (density-stratified) runs without variable viscosity, bit for bit.  Other
-background fields and magnetic boundary conditions, variable viscosity, compositional and inviscid set-ups
+that work in the reference; A and the forcing vector) -- BASELINE.json configs 1 to 5 -- and anelastic (density-stratified) runs, bit for bit (with a viscosity profile: its two viscous blocks to rounding).  Quadrupolar
+background fields, conducting inner cores, compositional and inviscid set-ups
 raise NotImplementedError (their pencils still enter through `kb_set_pencil`).
 
 The physics restated here (which operators enter which block with which coefficient):
@@ -157,8 +157,6 @@ class PhysicsParams:
         if self.compositional:
             bad.append("compositional = 1")
         if self.anelastic:
-            if self.variable_viscosity:
-                bad.append("variable_viscosity = 1")
             if self.ricb <= 0:
                 bad.append("anelastic = 1 without inner core")
             if self.dipole:
@@ -465,7 +463,19 @@ def build_program_A(pp: PhysicsParams, operators: dict) -> AsmProgram:
         r = _block_of(secs["u"], l)
         b.add(r, r, Group(IM, +1, [L, wf], _lin(b, (L, U(2, 0)), (-2, U(3, 1)), (-1, U(4, 2)))))
         b.add(r, r, Group(IM, +1, [2 * m, G], _lin(b, (-L, U(2, 0)), (2, U(3, 1)), (1, U(4, 2)))))
-        if pp.anelastic:  # viscous force with the density stratification (operators.py:146-152)
+        if pp.anelastic and pp.variable_viscosity:
+            # ... and a viscosity profile nu(r) (operators.py:154-168).  The reference nests two of the sums
+            # (2(L-1)(a + b), 6(a + b)); here they are distributed, so this block agrees to rounding, not to the bit
+            b.add(r, r, Group(RE, -1, [L, V], _lin(
+                b, (L * (2 - L), "r0_vsc0_D0_u"), (-(L + 2), "r1_vsc0_lho1_D0_u"), (-2 * (L + 1), "r1_vsc1_D0_u"),
+                (-2 * (L - 1), "r2_vsc0_lho2_D0_u"), (-2 * (L - 1), "r2_vsc1_lho1_D0_u"), (2 - L, "r2_vsc2_D0_u"),
+                (1, "r3_vsc0_lho3_D0_u"), (2, "r3_vsc1_lho2_D0_u"), (1, "r3_vsc2_lho1_D0_u"),
+                (2 - L, "r2_vsc0_lho1_D1_u"), (6, "r3_vsc0_lho2_D1_u"), (6, "r3_vsc1_lho1_D1_u"),
+                (1, "r4_vsc0_lho3_D1_u"), (2, "r4_vsc1_lho2_D1_u"), (1, "r4_vsc2_lho1_D1_u"), (2 * (L + 1), "r2_vsc1_D1_u"),
+                (2 * L, "r2_vsc0_D2_u"), (5, "r3_vsc0_lho1_D2_u"), (-4, "r3_vsc1_D2_u"), (2, "r4_vsc0_lho2_D2_u"),
+                (2, "r4_vsc1_lho1_D2_u"), (-1, "r4_vsc2_D2_u"),
+                (-4, "r3_vsc0_D3_u"), (1, "r4_vsc0_lho1_D3_u"), (-2, "r4_vsc1_D3_u"), (-1, "r4_vsc0_D4_u"))))
+        elif pp.anelastic:  # viscous force with the density stratification (operators.py:146-152)
             b.add(r, r, Group(RE, -1, [L, V], _lin(
                 b, (-L * (l + 2) * (l - 1), "r0_D0_u"), (-(L + 2), "r1_lho1_D0_u"), (-2 * (L - 1), "r2_lho2_D0_u"),
                 (1, "r3_lho3_D0_u"), (-(L - 2), "r2_lho1_D1_u"), (6, "r3_lho2_D1_u"), (1, "r4_lho3_D1_u"),
@@ -495,7 +505,11 @@ def build_program_A(pp: PhysicsParams, operators: dict) -> AsmProgram:
             b.add(r, c, Group(RE, +1, [2 * _coriolis_up(l, m), G], _lin(b, (-(l + 2), W(1, 0)), (-1, W(2, 1)))))
         b.add(r, r, Group(IM, +1, [L, wf], _lin(b, (1, W(2, 0)))))
         b.add(r, r, Group(IM, +1, [-2 * m, G], _lin(b, (1, W(2, 0)))))
-        if pp.anelastic:  # operators.py:176-179
+        if pp.anelastic and pp.variable_viscosity:  # operators.py:181-185
+            b.add(r, r, Group(RE, -1, [L, V], _lin(
+                b, (-L, "r0_vsc0_D0_v"), (-3, "r1_vsc0_lho1_D0_v"), (-1, "r2_vsc1_lho1_D0_v"), (-1, "r2_vsc0_lho2_D0_v"),
+                (-1, "r1_vsc1_D0_v"), (2, "r1_vsc0_D1_v"), (-1, "r2_vsc0_lho1_D1_v"), (1, "r2_vsc1_D1_v"), (1, "r2_vsc0_D2_v"))))
+        elif pp.anelastic:  # operators.py:176-179
             b.add(r, r, Group(RE, -1, [L, V], _lin(b, (-L, "r0_D0_v"), (-3, "r1_lho1_D0_v"), (-1, "r2_lho2_D0_v"),
                                                    (2, "r1_D1_v"), (-1, "r2_lho1_D1_v"), (1, "r2_D2_v"))))
         else:

@@ -338,8 +338,8 @@ def operator_labels(pp: PhysicsParams):
     vF = vP if quadrupole else -vP               # the induced field has the flow's parity times the background field's
     vG = -vF
     vS = vP                                      # entropy perturbation
-    if pp.compositional or pp.variable_viscosity:
-        raise NotImplementedError("radial operators of compositional / variable-viscosity runs")
+    if pp.compositional:
+        raise NotImplementedError("radial operators of compositional runs")
     if pp.magnetic and (pp.B0 not in BACKGROUND_FIELDS or (pp.B0 == "FDM" and pp.B0_l != 1)
                         or (pp.B0 == "dipole" and pp.ricb <= 0)):
         raise NotImplementedError("B0 = %r%s" % (pp.B0, "" if pp.ricb > 0 else " without inner core"))
@@ -350,6 +350,14 @@ def operator_labels(pp: PhysicsParams):
             u += ["r1_lho1_D0", "r2_lho2_D0", "r3_lho3_D0", "r2_lho1_D1", "r3_lho2_D1",
                   "r3_lho1_D2", "r4_lho2_D2", "r4_lho3_D1", "r4_lho1_D3"]
             par += [vP] * 9
+            if pp.variable_viscosity:  # viscosity profile and its first two derivatives (submatrices.py:230-237)
+                w = ["r0_vsc0_D0", "r1_vsc0_lho1_D0", "r1_vsc1_D0", "r2_vsc0_D2", "r2_vsc0_lho1_D1", "r2_vsc0_lho2_D0",
+                     "r2_vsc1_lho1_D0", "r2_vsc1_D1", "r2_vsc2_D0", "r3_vsc0_D3", "r3_vsc0_lho1_D2", "r3_vsc0_lho2_D1",
+                     "r3_vsc0_lho3_D0", "r3_vsc1_D2", "r3_vsc1_lho1_D1", "r3_vsc1_lho2_D0", "r3_vsc2_lho1_D0", "r4_vsc0_D4",
+                     "r4_vsc0_lho1_D3", "r4_vsc0_lho2_D2", "r4_vsc0_lho3_D1", "r4_vsc1_D3", "r4_vsc1_lho1_D2",
+                     "r4_vsc1_lho2_D1", "r4_vsc2_D2", "r4_vsc2_lho1_D1"]
+                u += w
+                par += [vP] * len(w)
         if pp.magnetic:
             u += ["r1_h0_D1", "r2_h1_D1", "r2_h0_D2", "r3_h1_D2", "r0_h0_D0", "r1_h1_D0", "r2_h2_D0",
                   "r3_h3_D0", "r3_h0_D3", "r1_h0_D0", "r2_h1_D0", "r2_h0_D1", "r3_h1_D1", "r3_h0_D2"]
@@ -366,6 +374,11 @@ def operator_labels(pp: PhysicsParams):
         if pp.anelastic:
             v += ["r1_lho1_D0", "r2_lho2_D0", "r2_lho1_D1"]
             par += [vT] * 3
+            if pp.variable_viscosity:
+                w = ["r0_vsc0_D0", "r1_vsc0_D1", "r1_vsc0_lho1_D0", "r2_vsc0_D2", "r2_vsc0_lho1_D1", "r2_vsc1_D1",
+                     "r2_vsc1_lho1_D0", "r2_vsc0_lho2_D0", "r1_vsc1_D0"]
+                v += w
+                par += [vT] * len(w)
         if pp.magnetic:
             v += ["r0_h0_D1", "r0_h1_D0", "r1_h2_D0", "r1_h0_D2", "r0_h0_D0", "r1_h1_D0", "r1_h0_D1"]
             par += [vF] * 4 + [vG] * 3

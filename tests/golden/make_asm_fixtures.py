@@ -64,6 +64,9 @@ NEW_CASES = {
     # toroidal diffusion, which vanish in every other magnetic fixture
     "asm_magnetic_conductivity": ("tests/dormy2004/params.dormy04",
                                   ["magnetic=1", "B0='axial'", "N=24", "lmax=18", "m=1", "symm=-1", "forcing=0"]),
+    # anelastic with a viscosity profile (PROFILES below; the shipped radial_profiles.viscosity is identically zero)
+    "asm_anelastic_viscosity": ("tests/dormy2004/params.dormy04",
+                                ["anelastic=1", "variable_viscosity=1", "N=24", "lmax=22", "m=3", "bci=0", "bco=1"]),
     # libration-forced magnetic run (dipole field)
     "asm_magnetic_forced": ("tests/spinover/params.spinover",
                             ["magnetic=1", "B0='dipole'", "forcing=7", "m=2", "symm=1", "N=24", "lmax=15",
@@ -81,7 +84,8 @@ NEW_CASES = {
                                  ["anelastic=1", "N=24", "lmax=24", "m=3", "bci=0", "bco=0", "bco_thermal=1"]),
     "asm_anelastic_hydro": ("tests/dormy2004/params.dormy04", ["anelastic=1", "thermal=0", "N=24", "lmax=23", "m=0", "symm=-1"]),
 }
-PROFILES = {"asm_magnetic_conductivity": "def conductivity(r):\n    return 1 + 0.5*r**2"}
+PROFILES = {"asm_magnetic_conductivity": "def conductivity(r):\n    return 1 + 0.5*r**2",
+            "asm_anelastic_viscosity": "def viscosity(r):\n    return 1 + 0.3*r**2"}
 EXISTING = ["spinover", "dormy", "jones", "forced_small", "m0_small", "magnetic_small"]
 
 

@@ -202,14 +202,41 @@ def test_anelastic_program_reproduces_reference_assembly_bitwise(name):
         assert np.array_equal(M.indptr, R.indptr) and np.array_equal(M.indices, R.indices) and np.array_equal(M.data, R.data)
 
 
+def test_variable_viscosity_program_matches_reference_to_rounding():
+    # anelastic with a viscosity profile nu(r) (operators.py:154-168, 181-185): 26 + 9 operators with nu, nu', nu''
+    # and the log-density derivatives.  The reference nests two sums of the poloidal block, the program distributes
+    # them: the two viscous blocks agree to rounding, everything else (and B) to the bit
+    pj, pp, ops, A_ref, B_ref = fixture("asm_anelastic_viscosity")
+    assert pp.anelastic == 1 and pp.variable_viscosity == 1 and pp.bci == 0
+    A, B = model_pencil(pj, pp, ops)
+    assert np.array_equal(B.indptr, B_ref.indptr) and np.array_equal(B.indices, B_ref.indices) and np.array_equal(B.data, B_ref.data)
+    rel = block_relative_error(A, A_ref, pp.N1)
+    assert rel.max() <= 1e-13
+    off = ~np.eye(rel.shape[0], dtype=bool)
+    assert rel[off].max() == 0.0 and rel[2 * pp.nb:, 2 * pp.nb:].max() == 0.0
+    assert A.nnz == A_ref.nnz
+
+
 def test_anelastic_stressfree_needs_the_density_slopes():
     pj, pp, ops, _, _ = fixture("asm_anelastic_stressfree")
     assert pp.lho1_icb is not None and pp.lho1_cmb is not None
     q = asm.PhysicsParams.from_dict({k: v for k, v in pp.__dict__.items() if k not in ("lho1_icb", "lho1_cmb")})
     with pytest.raises(NotImplementedError):
         asm.build_program_A(q, ops)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(KeyError):  # a viscosity profile needs its own radial operators
         asm.build_program_A(asm.PhysicsParams.from_dict({**pp.__dict__, "variable_viscosity": 1}), ops)
+
+
+@pytest.mark.gpu
+def test_device_assembles_the_variable_viscosity_program_like_the_model(lib):
+    pj, pp, ops, A_ref, B_ref = fixture("asm_anelastic_viscosity")
+    A_m, B_m = model_pencil(pj, pp, ops)
+    with lib.Solver(0) as s:
+        asm.assemble(s, pp, ops, bnorm=pj["Bnorm"])
+        ip, ix, v = s.get_assembled("A")
+        jp, jx, w = s.get_assembled("B")
+    assert np.array_equal(ip, A_m.indptr) and np.array_equal(ix, A_m.indices) and np.array_equal(v, A_m.data)
+    assert np.array_equal(jp, B_ref.indptr) and np.array_equal(jx, B_ref.indices) and np.array_equal(w, B_ref.data)
 
 
 @pytest.mark.gpu

@@ -7,7 +7,8 @@ kore_b200.assembly + the NumPy model of the kernels (tests/assembly_model.py) pr
 pattern and values, bit for bit.  With a third argument `magnetic` the trials are magnetic runs (any degree-1
 background field, shell or full sphere, insulating boundaries, with or without the heat equation) and the bar is the rounding-level one of
 tests/test_zz_assembly_extensions.py: B bit for bit, every block of A within 1e-13 of its largest entry.
-`anelastic` instead draws density-stratified runs (bit for bit again).  In every trial the radial operators are also
+`anelastic` instead draws density-stratified runs (bit for bit again; one in three with a viscosity profile,
+whose nested sums put its two viscous blocks at the rounding-level bar).  In every trial the radial operators are also
 generated from the parameters alone (kore_b200/radial.py, with the trial's radProfs tables) and compared with the ones
 the reference's submatrices.py wrote: label set and every entry, bit for bit.
 Usage: tools/fuzz_assembly.py [ntrials] [seed] [magnetic | anelastic]."""
@@ -26,6 +27,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import assembly_model as am  # noqa: E402
 from kore_b200 import assembly as asm  # noqa: E402
 from kore_b200 import radial  # noqa: E402
+
+
+PROFILES = {}  # overrides of a trial -> source appended to its radial_profiles.py (make_case.py --profiles)
 
 
 def load(fn):
@@ -89,6 +93,9 @@ def draw_anelastic(rng):
           "polind=%.2f" % rng.uniform(1.0, 3.0), "forcing=0"]
     if thermal:
         ov += ["bci_thermal=%d" % rng.integers(0, 2), "bco_thermal=%d" % rng.integers(0, 2), "Ra_gap=%g" % (10.0 ** rng.uniform(4, 7))]
+    if rng.integers(0, 3) == 0:  # a viscosity profile of the run's own (the shipped one is identically zero)
+        ov.append("variable_viscosity=1")
+        PROFILES[tuple(ov)] = "def viscosity(r):\n    return %.2f + %.2f*r**2" % (rng.uniform(0.5, 2), rng.uniform(-0.4, 0.8))
     return "tests/dormy2004/params.dormy04", ov
 
 
@@ -133,8 +140,10 @@ def main():
         params, ov = draw_magnetic(rng) if magnetic else (draw_anelastic(rng) if anelastic else draw(rng))
         out = "/tmp/asmfuzz_%d_%d" % (os.getpid(), t)
         shutil.rmtree(out, ignore_errors=True)
+        prof = PROFILES.get(tuple(ov))
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_case.py"), "--params", params, "--out", out,
-                            "--asm"] + ov, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                            "--asm"] + (["--profiles", prof] if prof else []) + ov,
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0 or not os.path.exists(os.path.join(out, "A.npz")):
             print("trial %d: the reference itself failed on %s (skipped)" % (t, " ".join(ov)))
             continue
@@ -156,7 +165,7 @@ def main():
             ref = np.asarray(sp.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=tuple(z["shape"])).todense()).ravel()
             ok &= np.array_equal(asm.forcing_vector(pp), ref)
         note = "bit-identical"
-        if magnetic:
+        if magnetic or pp.variable_viscosity:
             rel = block_relative_error(am.evaluate(pA), load(os.path.join(out, "A.npz")), pp.N1).max()
             ok &= rel <= 1e-13
             note = "%s bit-identical, A within %.1e of the block maxima" % ("B" if pp.forcing == 0 else "forcing vector", rel)
