@@ -73,6 +73,7 @@ class PhysicsParams:
     bci_thermal: int = 0
     bco_thermal: int = 0
     heating: str = "differential"
+    args: object = None           # [rc, h, rsy] of the 'two zone' temperature gradient (parameters.py:203-206)
     forcing: int = 0
     forcing_frequency: float = 0.0
     forcing_amplitude_cmb: float = 0.0
@@ -173,7 +174,7 @@ class PhysicsParams:
             bad.append("forcing = %d (the reference's own code for it refers to undefined names)" % self.forcing)
         if self.thermal and self.ThermaD <= 0:
             bad.append("thermal = 1 with ThermaD <= 0")
-        if self.thermal and self.heating not in ("differential", "internal"):
+        if self.thermal and self.heating not in ("differential", "internal", "two zone", "user defined"):
             bad.append("heating = %r" % (self.heating,))
         if bad:
             raise NotImplementedError("device-side assembly does not cover: " + ", ".join(bad)
@@ -533,7 +534,10 @@ def build_program_A(pp: PhysicsParams, operators: dict) -> AsmProgram:
                 b.add(r, r, Group(RE, +1, [Td], _lin(b, (-L, "r1_D0_h"), (2, "r2_D1_h"), (1, "r3_D2_h"))))
                 b.add(r, r, Group(IM, -1, [wf], _lin(b, (1, "r3_D0_h"))))
             else:
-                b.add(r, c, Group(RE, +1, [L], _lin(b, (1, "r2_D0_h"))))
+                # internal heating, or a background gradient of the run's own (r dT/dr in radial_profiles.twozone /
+                # BVprof, operators.py:737-738)
+                own = pp.heating in ("two zone", "user defined")
+                b.add(r, c, Group(RE, +1, [L], _lin(b, (-1, "r0_drS0_D0_h") if own else (1, "r2_D0_h"))))
                 b.add(r, r, Group(RE, +1, [Td], _lin(b, (-L, "r0_D0_h"), (2, "r1_D1_h"), (1, "r2_D2_h"))))
                 b.add(r, r, Group(IM, -1, [wf], _lin(b, (1, "r2_D0_h"))))
 

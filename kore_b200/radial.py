@@ -413,14 +413,17 @@ def operator_labels(pp: PhysicsParams):
             if pp.ThermaD > 0:
                 h += ["r1_D0", "r2_D1", "r3_D2"]
                 par += [vP, vP, vP]
-        elif pp.heating == "internal":
+        elif pp.heating in ("internal", "two zone", "user defined"):
             h = ["r2_D0"]
             par += [vP]
             if pp.ThermaD > 0:
                 h += ["r0_D0", "r1_D1", "r2_D2"]
                 par += [vP, vP, vP]
+            if pp.heating != "internal":
+                h += ["r0_drS0_D0"]                   # r dT/dr of the run's own background (cd_ent)
+                par += [vP]
         else:
-            raise NotImplementedError("heating = %r needs the run's radial_profiles.py" % (pp.heating,))
+            raise NotImplementedError("heating = %r" % (pp.heating,))
         labels += _labelit(h, "h", 0)
     if pp.ricb > 0:
         par = [0] * len(labels)
@@ -652,6 +655,9 @@ def profile_tables(pp: PhysicsParams, rap):
             for key, name, order in (("cd_lnT", "log_temperature", 1), ("cd_kho", "kappa_rho", 1), ("cd_tds", "tds", 0),
                                      ("cd_buo", "buoFac", 0)):
                 t[key] = profile_table(getattr(rap, name), order, N, ricb, rcmb)
+    if pp.thermal and not pp.anelastic and pp.heating in ("two zone", "user defined"):
+        f = rap.twozone if pp.heating == "two zone" else rap.BVprof
+        t["cd_ent"] = chebco_function(lambda r: f(r, pp.args), N, TOL, ricb, rcmb, rpower=1).reshape([N, 1])
     if pp.magnetic:
         t["cd_eta"] = profile_table(rap.magnetic_diffusivity, 1, N, ricb, rcmb)
         if pp.anelastic:
@@ -718,6 +724,8 @@ def radial_operators(pp: PhysicsParams, radprofs=None, dot="blas", dense=False):
         radprofs["cd_eta"] = profile_table(lambda r: 1. / np.ones_like(r), 1, N, ricb, rcmb)
     if pp.anelastic and "cd_lho" not in radprofs:
         raise ValueError("anelastic = 1: pass radprofs=profile_tables(pp, <the run's radial_profiles module>)")
+    if pp.thermal and not pp.anelastic and pp.heating in ("two zone", "user defined") and "cd_ent" not in radprofs:
+        raise ValueError("heating = %r: pass radprofs=profile_tables(pp, <the run's radial_profiles module>)" % (pp.heating,))
     cnorm = field_normalisation(pp) if pp.magnetic else None
     rp, rdh = {}, {}
 
@@ -728,7 +736,7 @@ def radial_operators(pp: PhysicsParams, radprofs=None, dot="blas", dense=False):
 
     def c0_series(rx, hx, prof):
         # submatrices.py:461-508: the series the multiplication matrix is made of
-        cks = [radprofs["cd_" + name][:, order] for name, order in prof]
+        cks = [radprofs["cd_ent" if name == "drS" else "cd_" + name][:, order] for name, order in prof]
         if hx is not None:
             if (rx, hx) not in rdh:
                 rdh[rx, hx] = cnorm * _dct_coefficients(background_field(_nodes(N, ricb, rcmb), pp.B0, RPOWERS[rx], hx, pp), N, TOL)
@@ -758,6 +766,8 @@ def radial_operators(pp: PhysicsParams, radprofs=None, dot="blas", dense=False):
             # parity of the operator as a function of r (submatrices.py:548-567)
             if hx is not None:
                 operator_parity = (-1) ** (hx + field_degree(pp) + RPOWERS[rx] + dx)  # h has the parity of its degree
+            elif prof and prof[0][0] == "drS":
+                operator_parity = 1                                         # the run's gradient is to make an even operator
             elif prof:
                 if len(prof) > 1 or prof[0][0] not in ("eta", "roT", "krT"):
                     raise NotImplementedError("operators of the profiles %r without inner core" % (prof,))
@@ -809,7 +819,8 @@ def run_profiles(pp: PhysicsParams):
     """The profile tables of the run in the current directory: from its radProfs.mat when
     compute_profiles.py has been run, else from its radial_profiles module (bin/ is on sys.path
     once the driver has imported `parameters`); None when the run needs none."""
-    if not (pp.anelastic or pp.magnetic):
+    own_gradient = pp.thermal and pp.heating in ("two zone", "user defined")
+    if not (pp.anelastic or pp.magnetic or own_gradient):
         return None
     if os.path.exists("radProfs.mat"):
         import scipy.io as sio
@@ -817,7 +828,7 @@ def run_profiles(pp: PhysicsParams):
     try:
         import radial_profiles as rap
     except ImportError:
-        if pp.anelastic:
+        if pp.anelastic or own_gradient:
             raise
         return None  # magnetic, Boussinesq: the uniform conductivity radial_profiles.py ships with
     return profile_tables(pp, rap)

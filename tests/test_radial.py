@@ -42,7 +42,7 @@ def ulp_distance(a, b):
 
 
 def test_fixtures_cover_the_parameter_space():
-    assert len(CASES) >= 36
+    assert len(CASES) >= 38
     kinds = set()
     for name in CASES:
         pp, _, _ = load_case(name)
@@ -148,6 +148,19 @@ def test_profile_tables_and_uniform_conductivity():
     rap = types.SimpleNamespace(magnetic_diffusivity=lambda r: 1. / (1 + 0.5 * r ** 2))
     assert np.array_equal(radial.profile_tables(pp, rap)["cd_eta"], radprofs["cd_eta"])
     assert np.count_nonzero(radprofs["cd_eta"][:, 1]) > 5
+    # the run's own background temperature gradient (heating = 'two zone'; radial_profiles.py:6-23 is the user's file)
+    pp, _, radprofs = load_case("asm_twozone")
+
+    def twozone(r, args):
+        rc, h, sym = args
+        out = np.zeros_like(r)
+        for i, x in enumerate(r):
+            out[i] = (1 if x >= 0 else sym) * (1 + np.tanh(2 * (abs(x) - rc) / h)) / 2
+        return out
+    pp.args = [0.7, 0.1, -1]                              # parameters.py:203-206
+    t = radial.profile_tables(pp, types.SimpleNamespace(twozone=twozone))
+    assert list(t) == ["cd_ent"] and t["cd_ent"].shape == radprofs["cd_ent"].shape
+    assert np.max(np.abs(t["cd_ent"] - radprofs["cd_ent"])) <= 1e-15
     # a derivative column differentiates: d/dr of r^3 = 3 r^2
     tab = radial.profile_table(lambda r: r ** 3, 2, 24, 0.35, 1.0)
     assert np.allclose(tab[:, 1], 3 * radial.chebco(2, 24, 0.0, 0.35, 1.0), atol=1e-9)

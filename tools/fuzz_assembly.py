@@ -115,7 +115,7 @@ def draw(rng):
     else:
         ov += ["ricb=%.3f" % rng.uniform(0.1, 0.8), "bci=%d" % rng.integers(0, 2)]
     if thermal:
-        ov += ["heating='%s'" % rng.choice(["differential", "internal"] if not full else ["internal"]),
+        ov += ["heating='%s'" % rng.choice(["differential", "internal", "two zone", "user defined"] if not full else ["internal", "two zone"]),
                "bco_thermal=%d" % rng.integers(0, 2), "Ra_gap=%g" % (10.0 ** rng.uniform(4, 7))]
         if not full:
             ov.append("bci_thermal=%d" % rng.integers(0, 2))

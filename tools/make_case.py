@@ -96,7 +96,7 @@ def main():
         cwd=work, env=env).decode().strip().splitlines()[-1]
     meta = json.loads(probe)
 
-    if meta["magnetic"] == 1 or meta["anelastic"] == 1:
+    if meta["magnetic"] == 1 or meta["anelastic"] == 1 or "heating='two zone'" in a.overrides or "heating='user defined'" in a.overrides:
         run(sys.executable, "bin/compute_profiles.py")
     run(sys.executable, "bin/submatrices.py", str(a.ncpus))
     run(sys.executable, "bin/assemble.py")
