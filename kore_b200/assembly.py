@@ -172,8 +172,10 @@ class PhysicsParams:
             bad.append("hydro = 0")
         if self.forcing not in (0, 7, 9, 10):
             bad.append("forcing = %d (the reference's own code for it refers to undefined names)" % self.forcing)
-        if self.thermal and self.ThermaD <= 0:
-            bad.append("thermal = 1 with ThermaD <= 0")
+        if self.thermal and self.ThermaD < 0:
+            bad.append("thermal = 1 with ThermaD < 0")
+        if self.thermal and self.ThermaD == 0 and self.anelastic:
+            bad.append("anelastic = 1 without thermal diffusion")
         if self.thermal and self.heating not in ("differential", "internal", "two zone", "user defined"):
             bad.append("heating = %r" % (self.heating,))
         if bad:
@@ -400,7 +402,9 @@ def _boundary_rows(pp, l=None):
         u.append(pp.ricb * Ta[:, 2] - la * Ta[:, 1] if pp.bci == 0 else Ta[:, 1])
         v.append(-pp.ricb * Ta[:, 1] + (1 + pp.ricb * la) * Ta[:, 0] if pp.bci == 0 else Ta[:, 0])
         h.append(Ta[:, 0] if pp.bci_thermal == 0 else Ta[:, 1])
-    rows["u"], rows["v"], rows["h"] = np.array(u), np.array(v), np.array(h)
+    if pp.ThermaD == 0:
+        h = []  # no thermal diffusion: a first-order equation in the C^(0) basis, no boundary rows (submatrices.py:177-178)
+    rows["u"], rows["v"], rows["h"] = np.array(u), np.array(v), np.array(h).reshape(len(h), len(u[0]) if len(h) == 0 else -1)
     if pp.magnetic:
         if pp.ricb > 0:
             Tbf = Tbg = Tb
@@ -531,14 +535,16 @@ def build_program_A(pp: PhysicsParams, operators: dict) -> AsmProgram:
                 b.add(r, r, Group(IM, -1, [wf], _lin(b, (1, "r2_roT0_D0_h"))))
             elif diff:
                 b.add(r, c, Group(RE, +1, [pp.ricb, 1. / gap, L], _lin(b, (1, "r0_D0_h"))))
-                b.add(r, r, Group(RE, +1, [Td], _lin(b, (-L, "r1_D0_h"), (2, "r2_D1_h"), (1, "r3_D2_h"))))
+                if Td > 0:
+                    b.add(r, r, Group(RE, +1, [Td], _lin(b, (-L, "r1_D0_h"), (2, "r2_D1_h"), (1, "r3_D2_h"))))
                 b.add(r, r, Group(IM, -1, [wf], _lin(b, (1, "r3_D0_h"))))
             else:
                 # internal heating, or a background gradient of the run's own (r dT/dr in radial_profiles.twozone /
                 # BVprof, operators.py:737-738)
                 own = pp.heating in ("two zone", "user defined")
                 b.add(r, c, Group(RE, +1, [L], _lin(b, (-1, "r0_drS0_D0_h") if own else (1, "r2_D0_h"))))
-                b.add(r, r, Group(RE, +1, [Td], _lin(b, (-L, "r0_D0_h"), (2, "r1_D1_h"), (1, "r2_D2_h"))))
+                if Td > 0:
+                    b.add(r, r, Group(RE, +1, [Td], _lin(b, (-L, "r0_D0_h"), (2, "r1_D1_h"), (1, "r2_D2_h"))))
                 b.add(r, r, Group(IM, -1, [wf], _lin(b, (1, "r2_D0_h"))))
 
     if pp.magnetic:

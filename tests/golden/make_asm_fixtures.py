@@ -40,6 +40,8 @@ NEW_CASES = {
                                   ["N=48", "lmax=32", "bco=0", "heating='differential'", "Ra_gap=1e6"]),
     # a background temperature gradient of the run's own (radial_profiles.twozone, Vidal & Schaeffer 2015): full sphere
     "asm_twozone": ("tests/jones2000/params.jones", ["heating='two zone'", "N=48", "lmax=16", "m=1", "symm=-1"]),
+    # no thermal diffusion: heat equation of first order in the C^(0) basis, no thermal boundary rows
+    "asm_no_thermal_diffusion": ("tests/dormy2004/params.dormy04", ["ThermaD=0", "N=24", "lmax=20", "m=3"]),
     # the other forcing modes that work in the reference: radial boundary-flow forcing
     "asm_forcing9": ("tests/spinover/params.spinover",
                      ["forcing=9", "m=2", "symm=1", "N=24", "forcing_amplitude_icb=0.7", "forcing_amplitude_cmb=1.3",

@@ -119,6 +119,8 @@ def draw(rng):
                "bco_thermal=%d" % rng.integers(0, 2), "Ra_gap=%g" % (10.0 ** rng.uniform(4, 7))]
         if not full:
             ov.append("bci_thermal=%d" % rng.integers(0, 2))
+        if rng.integers(0, 6) == 0:
+            ov.append("ThermaD=0")
     forcing = int(rng.choice([0, 0, 0, 10, 7]))
     if forcing == 10 and symm == 1 and m > 0:
         ov += ["forcing=10", "forcing_frequency=%.3f" % rng.uniform(-1.5, 1.5)]
