@@ -26,7 +26,7 @@ bit, see `_magnetic_blocks` -- magnetic (sections f, g; any degree-1 background 
 boundaries) problems, viscous,
 with or without inner core, eigenvalue (forcing = 0) and forced runs (forcing = 7, 9, 10: the modes
 that work in the reference; A and the forcing vector) -- BASELINE.json configs 1 to 5 -- and anelastic (density-stratified) runs, bit for bit (with a viscosity profile: its two viscous blocks to rounding).  Quadrupolar
-background fields, conducting inner cores, compositional and inviscid set-ups
+background fields, conducting inner cores and compositional set-ups
 raise NotImplementedError (their pencils still enter through `kb_set_pencil`).
 
 The physics restated here (which operators enter which block with which coefficient):
@@ -166,8 +166,9 @@ class PhysicsParams:
             if (self.bci == 0 and self.lho1_icb is None) or (self.bco == 0 and self.lho1_cmb is None):
                 bad.append("anelastic = 1 with stress-free boundaries but without lho1_icb / lho1_cmb "
                            "(d ln(rho) / dr at the boundaries; PhysicsParams.from_modules(par, ut) computes them)")
-        if self.Ek == 0:
-            bad.append("Ek = 0 (inviscid)")
+        if (self.Ek == 0 or self.ViscosD == 0) and not (self.Ek == 0 and self.ViscosD == 0 and self.ricb == 0
+                                                        and not self.magnetic and not self.anelastic):
+            bad.append("Ek = 0 or ViscosD = 0 other than the inviscid full sphere (Ek = ViscosD = 0, ricb = 0)")
         if not self.hydro:
             bad.append("hydro = 0")
         if self.forcing not in (0, 7, 9, 10):
@@ -397,6 +398,8 @@ def _boundary_rows(pp, l=None):
         u.append(pp.rcmb * Tbu[:, 2] - lb * Tbu[:, 1] if pp.bco == 0 else Tbu[:, 1])
     v = [-pp.rcmb * Tbv[:, 1] + (1 + pp.rcmb * lb) * Tbv[:, 0] if pp.bco == 0 else Tbv[:, 0]]
     h = [Tbh[:, 0] if pp.bco_thermal == 0 else Tbh[:, 1]]
+    if pp.Ek == 0:
+        u, v = [Tbu[:, 0]], []  # inviscid (full sphere): no penetration, nothing on the toroidal scalar (assemble.py:1205-1227, 1266)
     if pp.ricb > 0:
         u.append(Ta[:, 0])
         u.append(pp.ricb * Ta[:, 2] - la * Ta[:, 1] if pp.bci == 0 else Ta[:, 1])
@@ -404,7 +407,8 @@ def _boundary_rows(pp, l=None):
         h.append(Ta[:, 0] if pp.bci_thermal == 0 else Ta[:, 1])
     if pp.ThermaD == 0:
         h = []  # no thermal diffusion: a first-order equation in the C^(0) basis, no boundary rows (submatrices.py:177-178)
-    rows["u"], rows["v"], rows["h"] = np.array(u), np.array(v), np.array(h).reshape(len(h), len(u[0]) if len(h) == 0 else -1)
+    width = len(u[0])
+    rows["u"], rows["v"], rows["h"] = np.array(u), np.array(v).reshape(len(v), width), np.array(h).reshape(len(h), width)
     if pp.magnetic:
         if pp.ricb > 0:
             Tbf = Tbg = Tb

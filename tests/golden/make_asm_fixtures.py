@@ -42,6 +42,9 @@ NEW_CASES = {
     "asm_twozone": ("tests/jones2000/params.jones", ["heating='two zone'", "N=48", "lmax=16", "m=1", "symm=-1"]),
     # no thermal diffusion: heat equation of first order in the C^(0) basis, no thermal boundary rows
     "asm_no_thermal_diffusion": ("tests/dormy2004/params.dormy04", ["ThermaD=0", "N=24", "lmax=20", "m=3"]),
+    # inviscid full sphere (Ek = 0): C^(2) / C^(1) bases for the momentum equations, one no-penetration row, none
+    # for the toroidal scalar
+    "asm_inviscid": ("tests/spinover/params.spinover", ["Ek=0", "ricb=0", "N=48", "lmax=16", "m=1", "symm=-1"]),
     # the other forcing modes that work in the reference: radial boundary-flow forcing
     "asm_forcing9": ("tests/spinover/params.spinover",
                      ["forcing=9", "m=2", "symm=1", "N=24", "forcing_amplitude_icb=0.7", "forcing_amplitude_cmb=1.3",
