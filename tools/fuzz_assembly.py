@@ -112,6 +112,8 @@ def draw(rng):
           "bco=%d" % rng.integers(0, 2)]
     if full:
         ov.append("ricb=0")
+        if rng.integers(0, 4) == 0:  # inviscid full sphere
+            ov = [o for o in ov if not o.startswith("Ek=")] + ["Ek=0"]
     else:
         ov += ["ricb=%.3f" % rng.uniform(0.1, 0.8), "bci=%d" % rng.integers(0, 2)]
     if thermal:
