@@ -188,7 +188,8 @@ int kb_savetxt(const char* path, const double* data, int64_t rows, int64_t cols,
 
 /* Device-side assembly: replaces the host loops of bin/assemble.py:432-1171
  * (B: :432-590, A: :600-1171; block formulas bin/operators.py:22-195, 386-405, 699-775; boundary
- * rows assemble.py:1188-1345) for hydrodynamic and Boussinesq thermal set-ups.  An assembly
+ * rows assemble.py:1188-1345); which set-ups have programs is kore_b200/assembly.py's business
+ * (hydrodynamic, thermal, anelastic and degree-1 magnetic ones: DESIGN.md section 4b).  An assembly
  * program describes every N1 x N1 block of a matrix whose rows and columns are `nblockrows`
  * blocks of N1 radial coefficients in Kore's own (section-major) ordering:
  *   - radial operators as bands: ops[(k*N1 + i)*(2H+1) + d] = R_k[i][i + d - H] (0 where absent; 2H+1 <= 1023);

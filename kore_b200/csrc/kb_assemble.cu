@@ -1,7 +1,8 @@
 // Device-side assembly of Kore's pencil from an assembly program.
 //
-// Replaces /root/reference/bin/assemble.py:432-1171 for the hydrodynamic and Boussinesq thermal
-// set-ups: the host (kore_b200/assembly.py) writes down what every N1 x N1 block of A and B is
+// Replaces /root/reference/bin/assemble.py:432-1171 for every set-up kore_b200/assembly.py writes a
+// program for (hydrodynamic, thermal, anelastic, degree-1 magnetic): the host writes down what every
+// N1 x N1 block of A and B is
 // -- groups of (coefficient, radial operator) terms with their scalar factors, plus the dense
 // boundary-condition rows -- and the kernels below evaluate that program straight into the raw
 // CSR (original Kore ordering, canonical: rows and columns ascending, exact zeros dropped as

@@ -2,9 +2,14 @@
 
 Replaces /root/reference/bin/submatrices.py:28-590 and the functions of bin/utils.py it calls
 (chebco :251-270, Dlam :893-905, Slam :908-922, csl0 / csl / Mlam :925-1062, labelit :130-157,
-decode_label :85-127, remroco :187-197) for the set-ups the device-side assembly covers
-(kore_b200/assembly.py): every operator ``r^X D^Y`` (and, through `profiles`, ``r^X f(r) D^Y``)
-of a section is the product
+decode_label :85-127, remroco :187-197; h0 .. h3 / chebco_h / B0_norm :555-890 for the background
+fields; compute_profiles.py for the profile tables) for every set-up the reference itself can run
+but compositional ones and the free-decay mode of degree 2: hydrodynamic, Boussinesq (differential,
+internal or the run's own background gradient; with or without thermal diffusion) and anelastic
+(also with a viscosity profile) runs, shell or full sphere, viscous or the inviscid full sphere,
+magnetic with an axial, dipole, G21, Luo_S1, Luo_S2 or l = 1 free-decay background field and any
+conductivity profile.  Every operator ``r^X D^Y`` (and ``r^X h^(j)(r) D^Y``, ``r^X f(r) [g(r)] D^Y``
+with the field's scalar h or the run's profiles f, g) of a section is the product
 
     (C^(Y) -> C^(g) basis change)  x  (multiplication by r^X [f(r)] in the C^(Y) basis)  x  D^Y
 
