@@ -26,7 +26,7 @@ bit, see `_magnetic_blocks` -- magnetic (sections f, g; any degree-1 background 
 boundaries) problems, viscous,
 with or without inner core, eigenvalue (forcing = 0) and forced runs (forcing = 7, 9, 10: the modes
 that work in the reference; A and the forcing vector) -- BASELINE.json configs 1 to 5 -- and anelastic (density-stratified) runs, bit for bit (with a viscosity profile: its two viscous blocks to rounding).  Quadrupolar
-background fields, conducting inner cores and compositional set-ups
+background fields and conducting inner cores
 raise NotImplementedError (their pencils still enter through `kb_set_pencil`).
 
 The physics restated here (which operators enter which block with which coefficient):
@@ -82,6 +82,13 @@ class PhysicsParams:
     ViscosD: float = 1e-3
     Beyonce: float = 0.0
     ThermaD: float = 0.0
+    # compositional runs (parameters.py:228-271; OmgTau is commented out in every shipped file and has to be set)
+    comp_background: str = "internal"
+    OmgTau: float = None
+    BV2_comp: float = 0.0
+    Schmidt: float = 1.0
+    bci_compositional: int = 1
+    bco_compositional: int = 1
     # magnetic runs (parameters.py:103-137, 275-278)
     B0: str = "axial"
     B0_l: int = 1                 # degree of the free-decay-mode field (parameters.py:113)
@@ -156,7 +163,11 @@ class PhysicsParams:
             if self.ricb <= 0 and self.B0 == "dipole":
                 bad.append("B0 = %r without inner core" % (self.B0,))
         if self.compositional:
-            bad.append("compositional = 1")
+            if self.OmgTau is None:
+                bad.append("compositional = 1 without OmgTau (parameters.py:268-271 leaves it commented out; "
+                           "operators.py:423, 824 need it)")
+            if self.anelastic or self.comp_background not in ("internal", "differential"):
+                bad.append("compositional = 1 with anelastic = 1 or comp_background = %r" % (self.comp_background,))
         if self.anelastic:
             if self.ricb <= 0:
                 bad.append("anelastic = 1 without inner core")
@@ -363,7 +374,7 @@ def _lin(b, *terms):
 
 
 def _sections(pp):
-    secs = section_degrees(pp.m, pp.lmax, pp.symm, -1, pp.hydro, pp.magnetic, pp.thermal, 0)
+    secs = section_degrees(pp.m, pp.lmax, pp.symm, -1, pp.hydro, pp.magnetic, pp.thermal, pp.compositional)
     return {name: (base * pp.nb, np.asarray(degs)) for (name, base, degs) in secs}
 
 
@@ -407,6 +418,11 @@ def _boundary_rows(pp, l=None):
         h.append(Ta[:, 0] if pp.bci_thermal == 0 else Ta[:, 1])
     if pp.ThermaD == 0:
         h = []  # no thermal diffusion: a first-order equation in the C^(0) basis, no boundary rows (submatrices.py:177-178)
+    if pp.compositional:  # assemble.py:1345-1380
+        ci = [Tbh[:, 0] if pp.bco_compositional == 0 else Tbh[:, 1]]
+        if pp.ricb > 0:
+            ci.append(Ta[:, 0] if pp.bci_compositional == 0 else Ta[:, 1])
+        rows["i"] = np.array(ci)
     width = len(u[0])
     rows["u"], rows["v"], rows["h"] = np.array(u), np.array(v).reshape(len(v), width), np.array(h).reshape(len(h), width)
     if pp.magnetic:
@@ -501,6 +517,8 @@ def build_program_A(pp: PhysicsParams, operators: dict) -> AsmProgram:
             b.add(r, c, Group(RE, +1, [2 * _coriolis_up(l, m), G], _lin(b, (-(l + 2), U(3, 0)), (-1, U(4, 1)))))
         if pp.thermal:
             b.add(r, _block_of(secs["h"], l), Group(RE, +1, [L, Bf], _lin(b, (1, "r3_buo0_D0_u" if pp.anelastic else U(4, 0)))))
+        if pp.compositional:  # operators.py:408-423
+            b.add(r, _block_of(secs["i"], l), Group(RE, +1, [L, pp.OmgTau ** 2 * pp.BV2_comp], _lin(b, (1, U(4, 0)))))
 
     for l in secs["v"][1]:  # ---- toroidal momentum (1curl) rows
         l = int(l)
@@ -550,6 +568,21 @@ def build_program_A(pp: PhysicsParams, operators: dict) -> AsmProgram:
                 if Td > 0:
                     b.add(r, r, Group(RE, +1, [Td], _lin(b, (-L, "r0_D0_h"), (2, "r1_D1_h"), (1, "r2_D2_h"))))
                 b.add(r, r, Group(IM, -1, [wf], _lin(b, (1, "r2_D0_h"))))
+
+    if pp.compositional:  # ---- composition equation rows (operators.py:776-824; no frequency term in A, as there)
+        gap = pp.rcmb - pp.ricb
+        for l in secs["i"][1]:
+            l = int(l)
+            L = l * (l + 1)
+            r = _block_of(secs["i"], l)
+            c = _block_of(secs["u"], l)
+            Dc = [pp.OmgTau, pp.Ek, 1. / pp.Schmidt]
+            if pp.comp_background == "differential":
+                b.add(r, c, Group(RE, +1, [pp.ricb, 1. / gap, L], _lin(b, (1, "r0_D0_i"))))
+                b.add(r, r, Group(RE, +1, Dc, _lin(b, (-L, "r1_D0_i"), (2, "r2_D1_i"), (1, "r3_D2_i"))))
+            else:
+                b.add(r, c, Group(RE, +1, [L], _lin(b, (1, "r2_D0_i"))))
+                b.add(r, r, Group(RE, +1, Dc, _lin(b, (-L, "r0_D0_i"), (2, "r1_D1_i"), (1, "r2_D2_i"))))
 
     if pp.magnetic:
         _magnetic_blocks(b, pp, secs)
@@ -710,6 +743,11 @@ def build_program_B(pp: PhysicsParams, operators: dict) -> AsmProgram:
         lab = "r2_roT0_D0_h" if pp.anelastic else ("r3_D0_h" if pp.heating == "differential" else "r2_D0_h")
         for l in secs["h"][1]:
             r = _block_of(secs["h"], int(l))
+            b.add(r, r, Group(0, +1, [], _lin(b, (1, lab))))
+    if pp.compositional:
+        lab = "r3_D0_i" if pp.comp_background == "differential" else "r2_D0_i"
+        for l in secs["i"][1]:
+            r = _block_of(secs["i"], int(l))
             b.add(r, r, Group(0, +1, [], _lin(b, (1, lab))))
     return _finish(b, pp, secs, with_bc=False)
 

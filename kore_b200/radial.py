@@ -4,9 +4,9 @@ Replaces /root/reference/bin/submatrices.py:28-590 and the functions of bin/util
 (chebco :251-270, Dlam :893-905, Slam :908-922, csl0 / csl / Mlam :925-1062, labelit :130-157,
 decode_label :85-127, remroco :187-197; h0 .. h3 / chebco_h / B0_norm :555-890 for the background
 fields; compute_profiles.py for the profile tables) for every set-up the reference itself can run
-but compositional ones and the free-decay mode of degree 2: hydrodynamic, Boussinesq (differential,
+but the free-decay mode of degree 2: hydrodynamic, Boussinesq (differential,
 internal or the run's own background gradient; with or without thermal diffusion) and anelastic
-(also with a viscosity profile) runs, shell or full sphere, viscous or the inviscid full sphere,
+(also with a viscosity profile) runs, with or without the composition equation, shell or full sphere, viscous or the inviscid full sphere,
 magnetic with an axial, dipole, G21, Luo_S1, Luo_S2 or l = 1 free-decay background field and any
 conductivity profile.  Every operator ``r^X D^Y`` (and ``r^X h^(j)(r) D^Y``, ``r^X f(r) [g(r)] D^Y``
 with the field's scalar h or the run's profiles f, g) of a section is the product
@@ -343,8 +343,6 @@ def operator_labels(pp: PhysicsParams):
     vF = vP if quadrupole else -vP               # the induced field has the flow's parity times the background field's
     vG = -vF
     vS = vP                                      # entropy perturbation
-    if pp.compositional:
-        raise NotImplementedError("radial operators of compositional runs")
     if pp.magnetic and (pp.B0 not in BACKGROUND_FIELDS or (pp.B0 == "FDM" and pp.B0_l != 1)
                         or (pp.B0 == "dipole" and pp.ricb <= 0)):
         raise NotImplementedError("B0 = %r%s" % (pp.B0, "" if pp.ricb > 0 else " without inner core"))
@@ -370,7 +368,7 @@ def operator_labels(pp: PhysicsParams):
             if quadrupole:
                 u += ["r3_h2_D1", "r3_h2_D0"]
                 par += [vF, vG]
-        if pp.thermal:
+        if pp.thermal or pp.compositional:
             u += ["r3_buo0_D0"] if pp.anelastic else ["r4_D0"]
             par += [vS if pp.anelastic else vP]
         labels += _labelit(u, "u", 2 * dip)
@@ -430,6 +428,13 @@ def operator_labels(pp: PhysicsParams):
         else:
             raise NotImplementedError("heating = %r" % (pp.heating,))
         labels += _labelit(h, "h", 0)
+    if pp.compositional:
+        if pp.comp_background == "differential":
+            ci = ["r0_D0", "r1_D0", "r2_D1", "r3_D2", "r3_D0"]
+        else:
+            ci = ["r2_D0", "r0_D0", "r1_D1", "r2_D2"]
+        par += [vP] * len(ci)
+        labels += _labelit(ci, "i", 0)
     if pp.ricb > 0:
         par = [0] * len(labels)
     return labels, par

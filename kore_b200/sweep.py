@@ -125,7 +125,7 @@ def parameter_sweep(pp, operators, cases, nev, which="TM", device=0, rank=0, wor
             key = (q.m, q.lmax, q.symm, q.thermal, q.heating, q.magnetic, okey)
             res = _asm.assemble(s, q, ops, bnorm=bnorm_of.get(key))
             bnorm_of[key] = res["bnorm"]
-            perm, nodeptr = _chain.chain_from_params(q.N1, q.m, q.lmax, q.symm, -1, q.hydro, q.magnetic, q.thermal, 0)
+            perm, nodeptr = _chain.chain_from_params(q.N1, q.m, q.lmax, q.symm, -1, q.hydro, q.magnetic, q.thermal, q.compositional)
             s.set_chain(perm, nodeptr)
             s.factor(tau)
             lam, X, info = s.eigs(nev, which=which, target=tau, want_vectors=want_vectors, **kw)
@@ -160,7 +160,7 @@ def track_mode(pp, operators, cases, tau0, nev=3, which="TM", device=0, solver_f
             key = (q.m, q.lmax, q.symm, q.thermal, q.heating, q.magnetic, okey)
             res = _asm.assemble(s, q, ops, bnorm=bnorm_of.get(key))
             bnorm_of[key] = res["bnorm"]
-            perm, nodeptr = _chain.chain_from_params(q.N1, q.m, q.lmax, q.symm, -1, q.hydro, q.magnetic, q.thermal, 0)
+            perm, nodeptr = _chain.chain_from_params(q.N1, q.m, q.lmax, q.symm, -1, q.hydro, q.magnetic, q.thermal, q.compositional)
             s.set_chain(perm, nodeptr)
             s.factor(tau)
             lam, _, info = s.eigs(nev, which=which, target=tau, want_vectors=False, **kw)

@@ -45,6 +45,10 @@ NEW_CASES = {
     # inviscid full sphere (Ek = 0): C^(2) / C^(1) bases for the momentum equations, one no-penetration row, none
     # for the toroidal scalar
     "asm_inviscid": ("tests/spinover/params.spinover", ["Ek=0", "ricb=0", "N=48", "lmax=16", "m=1", "symm=-1"]),
+    # double-diffusive: heat and composition equations (APPEND below sets the OmgTau every shipped params file
+    # leaves commented out, and a compositional Rayleigh number)
+    "asm_compositional": ("tests/dormy2004/params.dormy04",
+                          ["compositional=1", "N=24", "lmax=20", "m=3", "bci_compositional=0", "comp_background='differential'"]),
     # the other forcing modes that work in the reference: radial boundary-flow forcing
     "asm_forcing9": ("tests/spinover/params.spinover",
                      ["forcing=9", "m=2", "symm=1", "N=24", "forcing_amplitude_icb=0.7", "forcing_amplitude_cmb=1.3",
@@ -93,6 +97,7 @@ NEW_CASES = {
 }
 PROFILES = {"asm_magnetic_conductivity": "def conductivity(r):\n    return 1 + 0.5*r**2",
             "asm_anelastic_viscosity": "def viscosity(r):\n    return 1 + 0.3*r**2"}
+APPEND = {"asm_compositional": "OmgTau = 1\nSchmidt = 0.3\nBV2_comp = -3.7e6 * Ek**2 / Schmidt"}
 EXISTING = ["spinover", "dormy", "jones", "forced_small", "m0_small", "magnetic_small"]
 
 
@@ -113,7 +118,8 @@ def main():
         shutil.rmtree(tmp, ignore_errors=True)
         subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "make_case.py"),
                                "--params", params, "--out", tmp, "--asm"]
-                              + (["--profiles", PROFILES[name]] if name in PROFILES else []) + ov)
+                              + (["--profiles", PROFILES[name]] if name in PROFILES else [])
+                              + (["--append-params", APPEND[name]] if name in APPEND else []) + ov)
         os.makedirs(out, exist_ok=True)
         for fn in ("operators.npz", "asm_params.json"):
             shutil.copy(os.path.join(tmp, fn), os.path.join(out, fn))

@@ -42,7 +42,7 @@ def ulp_distance(a, b):
 
 
 def test_fixtures_cover_the_parameter_space():
-    assert len(CASES) >= 38
+    assert len(CASES) >= 41
     kinds = set()
     for name in CASES:
         pp, _, _ = load_case(name)
@@ -171,8 +171,8 @@ def test_unsupported_runs_are_refused():
     pp, _, _ = load_case("asm_anelastic")
     with pytest.raises(ValueError):
         radial.radial_operators(pp)                       # anelastic without the run's profiles
-    pp, _, _ = load_case("spinover")
-    pp.compositional = 1
+    pp, _, _ = load_case("dormy")
+    pp.heating = "something else"
     with pytest.raises(NotImplementedError):
         radial.radial_operators(pp)
     pp, _, _ = load_case("asm_magnetic_axial")

@@ -326,7 +326,7 @@ def test_gpu_jones_search_from_the_parameter_file_alone(lib, tmp_path):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["asm_forcing9", "asm_forcing9_stressfree", "asm_forcing10", "asm_twozone",
-                                  "asm_no_thermal_diffusion", "asm_inviscid"])
+                                  "asm_no_thermal_diffusion", "asm_inviscid", "asm_compositional"])
 def test_device_assembly_bitwise_of_the_boundary_flow_forcings(lib, name):
     # forcing = 9 / 10 (assemble.py:360-426): with a stress-free outer boundary the poloidal boundary rows depend on
     # the degree, one table entry per block row

@@ -29,6 +29,7 @@ from kore_b200 import assembly as asm  # noqa: E402
 from kore_b200 import radial  # noqa: E402
 
 
+APPEND = {}  # overrides of a trial -> source appended to its parameters.py (make_case.py --append-params)
 PROFILES = {}  # overrides of a trial -> source appended to its radial_profiles.py (make_case.py --profiles)
 
 
@@ -123,6 +124,12 @@ def draw(rng):
             ov.append("bci_thermal=%d" % rng.integers(0, 2))
         if rng.integers(0, 6) == 0:
             ov.append("ThermaD=0")
+    append_src = None
+    if rng.integers(0, 5) == 0:  # composition equation (needs the OmgTau the shipped params files leave commented out)
+        ov += ["compositional=1", "comp_background='%s'" % rng.choice(["internal"] if full else ["internal", "differential"]),
+               "bco_compositional=%d" % rng.integers(0, 2)] + ([] if full else ["bci_compositional=%d" % rng.integers(0, 2)])
+        append_src = "OmgTau = %.2f\nSchmidt = %.2f\nBV2_comp = -%.3g * Ek**2 / Schmidt" % (
+            rng.uniform(0.5, 2), rng.uniform(0.1, 5), 10.0 ** rng.uniform(4, 7))
     forcing = int(rng.choice([0, 0, 0, 10, 7]))
     if forcing == 10 and symm == 1 and m > 0:
         ov += ["forcing=10", "forcing_frequency=%.3f" % rng.uniform(-1.5, 1.5)]
@@ -131,6 +138,8 @@ def draw(rng):
         m = int(rng.choice([0, 2]))
         ov += ["m=%d" % m, "symm=1", "lmax=%d" % (nl + m - 1), "bci=1", "bco=1", "forcing=7",
                "forcing_frequency=%.3f" % rng.uniform(-1.5, 1.5), "forcing_amplitude_icb=%.2f" % rng.uniform(0, 1)]
+    if append_src:
+        APPEND[tuple(ov)] = append_src
     return params, ov
 
 
@@ -146,7 +155,8 @@ def main():
         shutil.rmtree(out, ignore_errors=True)
         prof = PROFILES.get(tuple(ov))
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_case.py"), "--params", params, "--out", out,
-                            "--asm"] + (["--profiles", prof] if prof else []) + ov,
+                            "--asm"] + (["--profiles", prof] if prof else [])
+                           + (["--append-params", APPEND[tuple(ov)]] if tuple(ov) in APPEND else []) + ov,
                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0 or not os.path.exists(os.path.join(out, "A.npz")):
             print("trial %d: the reference itself failed on %s (skipped)" % (t, " ".join(ov)))

@@ -56,6 +56,9 @@ def main():
                     help="Python source appended to the scratch copy of bin/radial_profiles.py: the run's own "
                          "background profiles (the file is the user's to edit in the reference), e.g. "
                          "'def conductivity(r): return 1 + 0.5*r**2'")
+    ap.add_argument("--append-params", default=None,
+                    help="Python source appended to the derived parameters.py (e.g. 'OmgTau = 1', which every shipped "
+                         "params file leaves commented out although compositional runs need it)")
     ap.add_argument("overrides", nargs="*")
     a = ap.parse_args()
 
@@ -70,6 +73,8 @@ def main():
     with open(os.path.join(REF, a.params)) as f:
         ptxt = f.read()
     ptxt = patch_params(ptxt, ov)
+    if a.append_params:
+        ptxt += "\n# --- appended by tools/make_case.py --append-params\n" + a.append_params.replace("\\n", "\n") + "\n"
     with open(os.path.join(work, "bin", "parameters.py"), "w") as f:
         f.write(ptxt)
 
