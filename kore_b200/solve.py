@@ -53,6 +53,23 @@ def import_parameters(rundir):
     return par
 
 
+def run_utils(rundir):
+    """The run's own bin/utils.py (rcmb; for anelastic runs with stress-free boundaries the density slopes are
+    evaluated through it and the run's radial_profiles.py, as assemble.py:1195-1198 does), or None when the
+    directory holds a bare parameters.py."""
+    for d in (os.path.join(rundir, "bin"), rundir):
+        if os.path.exists(os.path.join(d, "parameters.py")):
+            if not os.path.exists(os.path.join(d, "utils.py")):
+                return None
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("utils", os.path.join(d, "utils.py"))
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules.setdefault("utils", mod)     # radial_profiles.py / bc_variables.py do `import utils`
+            spec.loader.exec_module(mod)
+            return mod
+    return None
+
+
 def kore_sizes(par):
     """N1, n, sizmat, symmB0 as bin/utils.py:26-57 derives them from parameters."""
     N, ricb = int(par.N), par.ricb
@@ -136,7 +153,7 @@ def main(argv=None, device=0):
     A = asm_inputs = None
     if on_device:
         from . import assembly as _assembly
-        pp = _assembly.PhysicsParams.from_modules(par)
+        pp = _assembly.PhysicsParams.from_modules(par, run_utils(rundir))
         pp.check_supported()
         if opts.hasName("kb_operators") or not glob.glob("*.mtx"):
             from . import radial as _radial
