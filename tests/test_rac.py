@@ -178,30 +178,37 @@ JONES_ROW = "6.325e-05 0.00 4.66986e+06 9 -1.93444e-02"  # tests/jones2000/refer
 JONES_RA_MIN = 4.6e6  # tests/jones2000/find_Rac.py:21
 
 
-def _jones_from_parameters():
-    """Full sphere, internal heating (tests/test_convection_bouss.py:10-25): the physics parameters of
-    params.jones as the reference's parameters.py evaluates them -- and nothing else: the radial operators come
-    from kore_b200/radial.py, every trial pencil from the assembly programs."""
+def _pencil_from_parameters(name):
+    """The physics parameters of the reference's params file as its parameters.py evaluates them -- and nothing
+    else: the radial operators come from kore_b200/radial.py, every trial pencil from the assembly programs."""
     import json
     from kore_b200 import assembly as asm
     from kore_b200 import rac
-    pp = asm.PhysicsParams.from_dict(json.load(open(os.path.join(GOLDEN, "jones", "asm_params.json"))))
+    pp = asm.PhysicsParams.from_dict(json.load(open(os.path.join(GOLDEN, name, "asm_params.json"))))
     return pp, rac.AssembledPencil(pp, None, lambda Ra: rac.buoyancy_factor(Ra, pp.Ek, pp.ricb, 1))
 
 
-def test_jones_search_from_the_parameter_file_alone(tmp_path):
-    """tests/jones2000/find_Rac.py end to end on the CPU stand-ins (assembly programs evaluated by the NumPy model
-    of the kernel, eigenvalues by the oracle): the golden row of reference.jones, digit for digit."""
+def _jones_from_parameters():
+    """Full sphere, internal heating (tests/test_convection_bouss.py:10-25)"""
+    return _pencil_from_parameters("jones")
+
+
+@pytest.mark.parametrize("name, ra_min, row", [("jones", JONES_RA_MIN, JONES_ROW), ("dormy", RA_MIN, GOLDEN_ROW)])
+def test_search_from_the_parameter_file_alone(tmp_path, name, ra_min, row):
+    """tests/jones2000/find_Rac.py and tests/dormy2004/find_Rac.py end to end on the CPU stand-ins (assembly programs
+    evaluated by the NumPy model of the kernel, eigenvalues by the oracle): the golden rows of reference.jones and
+    reference.dormy04, digit for digit."""
     import kore_oracle as ko
     from kore_b200 import rac
     from test_assembly import ModelSolver
-    c = load_case("jones")
+    c = load_case(name)
     m = c.meta
-    pp, pen = _jones_from_parameters()
+    pp, pen = _pencil_from_parameters(name)
     s = ModelSolver()
 
     class Growth:
-        cache = {}
+        def __init__(self):
+            self.cache = {}
 
         def __call__(self, x):
             Ra = 10.0 ** x
@@ -212,9 +219,9 @@ def test_jones_search_from_the_parameter_file_alone(tmp_path):
             return self.cache[Ra].real
 
     g = Growth()
-    Ra_c, omega_c, sigma_c = rac.find_rac(g, JONES_RA_MIN)
+    Ra_c, omega_c, sigma_c = rac.find_rac(g, ra_min)
     assert len(g.cache) < 20
     p = tmp_path / "critical_params.dat"
     rac.write_critical_params(p, m["Ek"], m["ricb"], Ra_c, m["m"], omega_c)
-    assert p.read_text().strip() == JONES_ROW
+    assert p.read_text().strip() == row
     assert abs(sigma_c) < 1e-6 * abs(omega_c)

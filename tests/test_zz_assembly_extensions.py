@@ -306,21 +306,24 @@ def test_twin_driver_from_the_parameter_file_alone(tmp_path, monkeypatch, lib):
 
 
 @pytest.mark.gpu
-def test_gpu_jones_search_from_the_parameter_file_alone(lib, tmp_path):
-    # the reference's third test (tests/test_convection_bouss.py:10-25, find_Rac.py) from params.jones alone: radial
-    # operators generated, every trial pencil assembled on the device, golden row of reference.jones digit for digit
+@pytest.mark.parametrize("name", ["jones", "dormy"])
+def test_gpu_search_from_the_parameter_file_alone(lib, tmp_path, name):
+    # the reference's convection tests (tests/test_convection_bouss.py, find_Rac.py) from params.jones / params.dormy04
+    # alone: radial operators generated, every trial pencil assembled on the device, golden rows of reference.jones /
+    # reference.dormy04 digit for digit
     from kore_b200 import rac
-    from test_rac import JONES_RA_MIN, JONES_ROW, _jones_from_parameters
-    c = load_case("jones")
+    import test_rac as tr
+    ra_min, row = {"jones": (tr.JONES_RA_MIN, tr.JONES_ROW), "dormy": (tr.RA_MIN, tr.GOLDEN_ROW)}[name]
+    c = load_case(name)
     m = c.meta
-    pp, pen = _jones_from_parameters()
+    pp, pen = tr._pencil_from_parameters(name)
     with rac.GrowthRate(pen, c.perm, c.nodeptr, c.tau, m["nev"], m["which_eigenpairs"], tol=m["tol"],
                         maxit=m["maxit"]) as g:
-        Ra_c, omega_c, sigma_c = rac.find_rac(g, JONES_RA_MIN)
+        Ra_c, omega_c, sigma_c = rac.find_rac(g, ra_min)
         assert 3 <= len(g.history) < 20
     p = tmp_path / "critical_params.dat"
     rac.write_critical_params(p, m["Ek"], m["ricb"], Ra_c, m["m"], omega_c)
-    assert p.read_text().strip() == JONES_ROW
+    assert p.read_text().strip() == row
     assert abs(sigma_c) < 1e-6 * abs(omega_c)
 
 
