@@ -6,8 +6,8 @@ energy, viscous dissipation, buoyancy power, thermal energy / dissipation / adve
 in a multiprocessing pool, and the sums enter the power-balance residuals the physicists use as their
 own correctness check (spin_doctor.py:227-242).  Here the integrals are one kernel launch for all
 degrees and all solutions (`kb_diagnose`, csrc/kb_diag.cu); this module prepares the quadrature
-nodes, calls it and forms the same sums and residuals.  Hydrodynamic and Boussinesq thermal
-solutions (no Lorentz / compositional terms).
+nodes, calls it and forms the same sums and residuals.  Hydrodynamic, Boussinesq thermal and
+double-diffusive (thermal + compositional) solutions; no Lorentz terms.
 """
 from __future__ import annotations
 
@@ -55,7 +55,54 @@ def diagnose(solver, X, N, lmax, m, symm, ricb, thermal=0, heating="differential
     return flow, therm, _chain.ell(m, lmax, symm)
 
 
-def power_balance(flow, therm, degrees, lam, Ek, ViscosD=None, Beyonce=0.0, ThermaD=0.0, pss=0.0):
+def diagnose_double_diffusive(solver, X, N, lmax, m, symm, ricb, thermal=1, heating="differential",
+                              comp_background="differential", rcmb=1.0, Ra=None, Rb=None):
+    """`diagnose` for runs with the composition equation (par.compositional = 1): the columns of X are
+    [u | v | h | c] (or [u | v | c] without the heat equation, solve.py:262-273 / assemble.py:442-534
+    section order).
+
+    The reference integrates the compositional field with the thermal worker itself (utils4pp.py:846-850:
+    `thermal_worker(..., csol2, ..., 'compositional')`; the buoyancy power of the composition is
+    `buoyancy_power` with `clm0` in the place of `hlm0`, utils4pp.py:452-466), the background being
+    `par.comp_background` instead of `par.heating` (utils4pp.py:414-419).  So the same kernel runs once
+    per scalar field on [u | v | field]: no second code path on the device.
+
+    Returns (flow[nsol, n_l, 6], therm[nsol, nb, 3], comp[nsol, nb, 3], degrees): `flow` with BOTH buoyancy
+    columns of `udgn` (4: thermal, 5: compositional), `therm` = `tdgn`, `comp` = `cdgn`."""
+    if comp_background not in ("differential", "internal"):
+        raise NotImplementedError("comp_background = %r" % (comp_background,))
+    N1 = N if ricb > 0 else N // 2
+    nb = (lmax - m + 1) // 2
+    n = N1 * nb
+    X = np.asarray(X, dtype=np.complex128)
+    if X.ndim == 1:
+        X = X.reshape(-1, 1)
+    want = n * (3 + int(bool(thermal)))
+    if X.shape[0] != want:
+        raise ValueError("solutions have %d rows, the parameters imply %d (hydro%s + compositional)"
+                         % (X.shape[0], want, " + thermal" if thermal else ""))
+    kw = dict(rcmb=rcmb, Ra=Ra, Rb=Rb)
+    c0 = want - n
+    flow_c, comp, degrees = diagnose(solver, np.vstack([X[:2 * n], X[c0:]]), N, lmax, m, symm, ricb, thermal=1,
+                                     heating=comp_background, **kw)
+    if thermal:
+        flow, therm, _ = diagnose(solver, X[:3 * n], N, lmax, m, symm, ricb, thermal=1, heating=heating, **kw)
+    else:
+        flow, therm = flow_c.copy(), np.zeros_like(comp)
+        flow[:, :, 4] = 0.0
+    flow[:, :, 5] = flow_c[:, :, 4]
+    return flow, therm, comp, degrees
+
+
+def differential_gradient_factor(ricb, rcmb=1.0):
+    """ricb / (rcmb - ricb): the constant of the 'differential' background gradient that the advection
+    operators carry (operators.py:736, 802) and utils4pp.thermal_advect leaves out (utils4pp.py:409, 419);
+    `power_balance(advect_scale_thm=..., advect_scale_cmp=...)` takes it when the balance is to close."""
+    return ricb / (rcmb - ricb)
+
+
+def power_balance(flow, therm, degrees, lam, Ek, ViscosD=None, Beyonce=0.0, ThermaD=0.0, pss=0.0, comp=None,
+                  CompBuoy=0.0, CompD=0.0, advect_scale_thm=1.0, advect_scale_cmp=1.0):
     """The sums and residuals of spin_doctor.py:148-242 for ONE solution: `flow` [n_l, 6], `therm`
     [nb, 3], `lam` its eigenvalue (growth rate = real part; 0 for a forced solution).
 
@@ -66,18 +113,31 @@ def power_balance(flow, therm, degrees, lam, Ek, ViscosD=None, Beyonce=0.0, Ther
         resid0: Dint + Dkin - pss = 0            (internal vs kinetic dissipation)
         resid1: 2 sigma KE - ViscosD Dkin + Beyonce Wthm = 0
         resid3: 2 sigma TE - ThermaD Dthm - Wadv = 0
-    each divided by its largest term."""
+    each divided by its largest term.  With a compositional field (`comp` = `cdgn` [nb, 3];
+    spin_doctor.py:155, 183-186): `CompBuoy` = OmgTau^2 BV2_comp (operators.py:423) enters resid1 with
+    column 5 of `flow`, `CompD` = OmgTau Ek / Schmidt (operators.py:824) scales the dissipation, and
+        resid4: 2 sigma CE - CompD Dcmp - Wadv_cmp = 0
+    is the compositional twin of resid3 (the reference prints CE, Dcmp, Wadv_cmp and forms no residual
+    of them).  `advect_scale_*` multiply the advection integrals before the residuals (default 1: what
+    the reference computes; see `differential_gradient_factor`)."""
     lp, lt, ll = degrees
     ll = np.asarray(ll)
     ViscosD = Ek if ViscosD is None else ViscosD
     sigma = complex(lam).real
-    KE, Dkin0, Dint0, _, Wthm0, _ = flow.sum(axis=0)
+    KE, Dkin0, Dint0, _, Wthm0, Wcmp0 = flow.sum(axis=0)
     out = {"KE": KE, "KP": flow[np.isin(ll, lp), 0].sum(), "KT": flow[np.isin(ll, lt), 0].sum(),
-           "Dkin": ViscosD * Dkin0, "Dint": ViscosD * Dint0, "Wthm": Beyonce * Wthm0}
+           "Dkin": ViscosD * Dkin0, "Dint": ViscosD * Dint0, "Wthm": Beyonce * Wthm0, "Wcmp": CompBuoy * Wcmp0}
     out["resid0"] = abs(Dint0 + Dkin0 - pss) / max(abs(Dint0), abs(Dkin0), abs(pss))
-    out["resid1"] = abs(2 * sigma * KE - out["Dkin"] + out["Wthm"]) / max(abs(2 * sigma * KE), abs(out["Dkin"]), abs(out["Wthm"]))
+    out["resid1"] = abs(2 * sigma * KE - out["Dkin"] + out["Wthm"] + out["Wcmp"]) / max(
+        abs(2 * sigma * KE), abs(out["Dkin"]), abs(out["Wthm"]), abs(out["Wcmp"]))
     if therm is not None and therm.size and np.any(therm):
         TE, Dthm0, Wadv = therm.sum(axis=0)
+        Wadv = advect_scale_thm * Wadv
         out.update(TE=TE, Dthm=ThermaD * Dthm0, Wadv_thm=Wadv)
         out["resid3"] = abs(2 * sigma * TE - out["Dthm"] - Wadv) / max(abs(2 * sigma * TE), abs(out["Dthm"]), abs(Wadv))
+    if comp is not None and comp.size and np.any(comp):
+        CE, Dcmp0, Wadv = comp.sum(axis=0)
+        Wadv = advect_scale_cmp * Wadv
+        out.update(CE=CE, Dcmp=CompD * Dcmp0, Wadv_cmp=Wadv)
+        out["resid4"] = abs(2 * sigma * CE - out["Dcmp"] - Wadv) / max(abs(2 * sigma * CE), abs(out["Dcmp"]), abs(Wadv))
     return out

@@ -119,20 +119,32 @@ def write_power_balance(par, solver, vec, lam):
     """`-kb_diagnose`: the energy / dissipation / power integrals spin_doctor.py:119-242 derives from
     the field files, computed on the GPU straight from the solutions (kore_b200/diagnostics.py) and
     written to power_balance.dat, one row per solution:
-    KE KP KT Dkin Dint Wthm resid0 resid1 [TE Dthm Wadv_thm resid3]."""
+    KE KP KT Dkin Dint Wthm resid0 resid1 [TE Dthm Wadv_thm resid3] [Wcmp CE Dcmp Wadv_cmp resid4]
+    (the last group for runs with the composition equation, spin_doctor.py:155, 183-186)."""
     from . import diagnostics as dg
-    if par.magnetic or par.compositional or not par.hydro or getattr(par, "anelastic", 0):
-        print("-kb_diagnose covers hydrodynamic and Boussinesq thermal runs only; skipped")
+    if par.magnetic or not par.hydro or getattr(par, "anelastic", 0):
+        print("-kb_diagnose covers hydrodynamic, Boussinesq thermal and double-diffusive runs only; skipped")
         return
-    flow, therm, degs = dg.diagnose(solver, vec, int(par.N), par.lmax, par.m, par.symm, par.ricb,
-                                    thermal=par.thermal, heating=getattr(par, "heating", "differential"))
+    geom = (int(par.N), par.lmax, par.m, par.symm, par.ricb)
+    heating = getattr(par, "heating", "differential")
+    comp, extra = None, {}
+    if par.compositional:
+        flow, therm, comp, degs = dg.diagnose_double_diffusive(
+            solver, vec, *geom, thermal=par.thermal, heating=heating,
+            comp_background=getattr(par, "comp_background", "differential"))
+        extra = dict(CompBuoy=par.OmgTau ** 2 * par.BV2_comp, CompD=par.OmgTau * par.Ek / par.Schmidt)
+    else:
+        flow, therm, degs = dg.diagnose(solver, vec, *geom, thermal=par.thermal, heating=heating)
     rows = []
     for i in range(vec.shape[1]):
         pb = dg.power_balance(flow[i], therm[i] if par.thermal else None, degs, lam[i], par.Ek,
-                              getattr(par, "ViscosD", par.Ek), getattr(par, "Beyonce", 0.0), getattr(par, "ThermaD", 0.0))
+                              getattr(par, "ViscosD", par.Ek), getattr(par, "Beyonce", 0.0), getattr(par, "ThermaD", 0.0),
+                              comp=None if comp is None else comp[i], **extra)
         keys = ["KE", "KP", "KT", "Dkin", "Dint", "Wthm", "resid0", "resid1"]
         if par.thermal:
             keys += ["TE", "Dthm", "Wadv_thm", "resid3"]
+        if par.compositional:
+            keys += ["Wcmp", "CE", "Dcmp", "Wadv_cmp", "resid4"]
         rows.append([pb[k] for k in keys])
     np.savetxt("power_balance.dat", np.asarray(rows))
 

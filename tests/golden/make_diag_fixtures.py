@@ -20,8 +20,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
 sys.path.insert(0, HERE)
 from make_golden import CASES  # noqa: E402
+from make_asm_fixtures import NEW_CASES, APPEND  # noqa: E402
 
-DIAG_CASES = ["spinover", "dormy", "jones"]
+DIAG_CASES = ["spinover", "dormy", "jones", "asm_compositional"]
 
 WORKER = r'''
 import sys, json
@@ -37,9 +38,12 @@ x = X[:, i]
 n = ut.n
 u2 = upp.expand_reshape_sol(x[:2 * n], par.symm)
 t2 = upp.expand_reshape_sol(x[2 * n:3 * n], par.symm) if par.thermal else 0
-udgn, bdgn, tdgn, cdgn = upp.diagnose(u2, 0, t2, 0, par.ricb, ut.rcmb, 4)
+c0 = (2 + par.thermal) * n
+c2 = upp.expand_reshape_sol(x[c0:c0 + n], par.symm) if par.compositional else 0
+udgn, bdgn, tdgn, cdgn = upp.diagnose(u2, 0, t2, c2, par.ricb, ut.rcmb, 4)
+extra = dict(comp=np.asarray(cdgn, dtype=float)) if par.compositional else {}
 np.savez_compressed("diagnostics.npz", x=x, lam=np.array([lam[i]]), flow=np.asarray(udgn, dtype=float),
-                    thermal=np.asarray(tdgn, dtype=float) if par.thermal else np.zeros((0, 3)))
+                    thermal=np.asarray(tdgn, dtype=float) if par.thermal else np.zeros((0, 3)), **extra)
 print("ok", lam[i], np.sum(udgn, 0))
 '''
 
@@ -49,7 +53,9 @@ def main():
     for name in DIAG_CASES:
         if only and name not in only:
             continue
-        params, ov = CASES[name]
+        params, ov = CASES[name] if name in CASES else NEW_CASES[name]
+        if name in APPEND:
+            ov = ["--append-params", APPEND[name]] + list(ov)
         out = "/tmp/diagfix_" + name
         shutil.rmtree(out, ignore_errors=True)
         log = subprocess.check_output([sys.executable, os.path.join(ROOT, "tools", "make_case.py"),

@@ -63,6 +63,74 @@ def test_power_balance_of_the_reference_integrals(name, heating):
         assert pb["resid3"] < 1e-9
 
 
+class ModelSolver:
+    """Stand-in for lib.Solver.diagnose on CPU: the NumPy model of the kernel (tests/diag_model.py) behind the
+    same call, so that the HOST logic of kore_b200/diagnostics.py runs in the CPU suite."""
+
+    def diagnose(self, p, nodes, X):
+        meta = dict(N=p.N, N1=p.N1, n=p.N1 * p.nb, ricb=p.ricb, m=p.m, lmax=p.lmax, symm=p.symm, thermal=p.thermal)
+        out = [dm.diagnose(X[:, k], meta, "differential" if p.heating == 0 else "internal") for k in range(X.shape[1])]
+        return np.stack([o[0] for o in out]), np.stack([o[1] for o in out])
+
+
+def test_double_diffusive_integrals_match_reference():
+    # [u | v | h | c]: utils4pp.diagnose with csol2 (thermal_worker with the 'compositional' flag, the second
+    # buoyancy column of flow_worker) on the eigenvector of the reference-assembled double-diffusive pencil
+    meta, pj, z = golden("asm_compositional")
+    assert meta["sizmat"] == 4 * meta["n"] and z["comp"].shape == z["thermal"].shape
+    flow, therm, comp, degs = dg.diagnose_double_diffusive(
+        ModelSolver(), z["x"], meta["N"], meta["lmax"], meta["m"], meta["symm"], meta["ricb"], thermal=1,
+        heating=pj["heating"], comp_background=pj["comp_background"])
+    assert flow.shape == (1,) + z["flow"].shape and np.all(z["flow"][:, 5][np.isin(degs[2], degs[0])] != 0)
+    assert close(flow[0], z["flow"], 1e-12)
+    assert close(therm[0], z["thermal"], 1e-12) and close(comp[0], z["comp"], 1e-12)
+    # without the heat equation: [u | v | c]
+    n = meta["n"]
+    x3 = np.concatenate([z["x"][:2 * n], z["x"][3 * n:]])
+    f3, t3, c3, _ = dg.diagnose_double_diffusive(ModelSolver(), x3, meta["N"], meta["lmax"], meta["m"], meta["symm"],
+                                                 meta["ricb"], thermal=0, comp_background=pj["comp_background"])
+    assert close(c3[0], z["comp"], 1e-12) and not np.any(t3) and not np.any(f3[0][:, 4])
+    assert close(f3[0][:, [0, 1, 2, 5]], z["flow"][:, [0, 1, 2, 5]], 1e-12)
+    with pytest.raises(ValueError):
+        dg.diagnose_double_diffusive(ModelSolver(), x3, meta["N"], meta["lmax"], meta["m"], meta["symm"], meta["ricb"])
+
+
+def test_double_diffusive_power_balance_closes():
+    # momentum: both buoyancy powers enter; heat and composition: 2 sigma E = D + W once the advection carries the
+    # ricb / gap of the 'differential' gradient that operators.py:736, 802 has and utils4pp.py:409, 419 leaves out
+    meta, pj, z = golden("asm_compositional")
+    degs = chain.ell(meta["m"], meta["lmax"], meta["symm"])
+    kw = dict(comp=z["comp"], CompBuoy=pj["OmgTau"] ** 2 * pj["BV2_comp"], CompD=pj["OmgTau"] * pj["Ek"] / pj["Schmidt"])
+    pb = dg.power_balance(z["flow"], z["thermal"], degs, z["lam"][0], pj["Ek"], pj["ViscosD"], pj["Beyonce"],
+                          pj["ThermaD"], **kw)
+    assert pb["resid1"] < 1e-2 and pb["Wcmp"] != 0 and pb["Wthm"] != 0
+    # ... and the momentum balance does NOT close without the compositional power
+    assert dg.power_balance(z["flow"], z["thermal"], degs, z["lam"][0], pj["Ek"], pj["ViscosD"], pj["Beyonce"],
+                            pj["ThermaD"])["resid1"] > 0.5
+    assert pb["resid3"] > 0.1 and pb["resid4"] > 0.1      # the reference's own numbers (no gradient constant)
+    g = dg.differential_gradient_factor(meta["ricb"])
+    pb = dg.power_balance(z["flow"], z["thermal"], degs, z["lam"][0], pj["Ek"], pj["ViscosD"], pj["Beyonce"],
+                          pj["ThermaD"], advect_scale_thm=g, advect_scale_cmp=g, **kw)
+    assert pb["resid3"] < 1e-4 and pb["resid4"] < 1e-4, (pb["resid3"], pb["resid4"])  # 1.5e-6, 1.4e-5 at N = 24
+
+
+def test_driver_writes_the_double_diffusive_power_balance(tmp_path, monkeypatch):
+    # solve.py -kb_diagnose on a run with the composition equation: one row per solution, 17 columns
+    import types
+    from kore_b200 import solve
+    meta, pj, z = golden("asm_compositional")
+    par = types.SimpleNamespace(**{k: v for k, v in pj.items() if not isinstance(v, (list, dict))})
+    monkeypatch.chdir(tmp_path)
+    solve.write_power_balance(par, ModelSolver(), np.stack([z["x"], -z["x"]], axis=1), [z["lam"][0]] * 2)
+    rows = np.loadtxt("power_balance.dat")
+    assert rows.shape == (2, 17) and np.array_equal(rows[0], rows[1])
+    KE, Wthm, resid1, TE, Wcmp, CE, Dcmp = rows[0][[0, 5, 7, 8, 12, 13, 14]]
+    assert np.isclose(KE, z["flow"][:, 0].sum(), rtol=1e-12) and np.isclose(TE, z["thermal"][:, 0].sum(), rtol=1e-12)
+    assert np.isclose(CE, z["comp"][:, 0].sum(), rtol=1e-12) and resid1 < 1e-2
+    assert np.isclose(Wcmp, pj["BV2_comp"] * z["flow"][:, 5].sum(), rtol=1e-12)
+    assert np.isclose(Dcmp, pj["Ek"] / pj["Schmidt"] * z["comp"][:, 1].sum(), rtol=1e-12)
+
+
 # ---------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,heating", CASES)

@@ -335,3 +335,35 @@ def test_device_assembly_bitwise_of_the_boundary_flow_forcings(lib, name):
     # the degree, one table entry per block row
     import test_assembly as ta
     ta.test_device_assembly_bitwise(lib, name)
+
+
+# ------------------------------------------------------------------ double-diffusive diagnostics
+@pytest.mark.gpu
+def test_device_double_diffusive_integrals_match_reference(lib):
+    # kb_diagnose once per scalar field on [u | v | field] (kore_b200/diagnostics.py:diagnose_double_diffusive)
+    # against utils4pp.diagnose with csol2 on the reference-assembled double-diffusive pencil's eigenvector
+    # (tests/golden/asm_compositional/diagnostics.npz, make_diag_fixtures.py); CPU twin on the kernel's model:
+    # tests/test_diagnostics.py::test_double_diffusive_integrals_match_reference
+    from kore_b200 import diagnostics as dg
+    meta = json.load(open(os.path.join(GOLDEN, "asm_compositional", "meta.json")))
+    pj = json.load(open(os.path.join(GOLDEN, "asm_compositional", "asm_params.json")))
+    z = np.load(os.path.join(GOLDEN, "asm_compositional", "diagnostics.npz"))
+
+    def close(a, b, tol):
+        scale = np.max(np.abs(b), axis=0)
+        scale[scale == 0] = 1.0
+        return np.max(np.abs(a - b) / scale) <= tol
+
+    X = np.stack([z["x"], 2j * z["x"]], axis=1)
+    with lib.Solver(0) as s:
+        flow, therm, comp, degs = dg.diagnose_double_diffusive(
+            s, X, meta["N"], meta["lmax"], meta["m"], meta["symm"], meta["ricb"], thermal=1, heating=pj["heating"],
+            comp_background=pj["comp_background"])
+    assert flow.shape == (2,) + z["flow"].shape and comp.shape == (2,) + z["comp"].shape
+    assert close(flow[0], z["flow"], 1e-9) and close(therm[0], z["thermal"], 1e-9) and close(comp[0], z["comp"], 1e-9)
+    assert close(flow[1], 4 * flow[0], 1e-13) and close(comp[1], 4 * comp[0], 1e-13)
+    g = dg.differential_gradient_factor(meta["ricb"])
+    pb = dg.power_balance(flow[0], therm[0], degs, z["lam"][0], pj["Ek"], pj["ViscosD"], pj["Beyonce"], pj["ThermaD"],
+                          comp=comp[0], CompBuoy=pj["OmgTau"] ** 2 * pj["BV2_comp"],
+                          CompD=pj["OmgTau"] * pj["Ek"] / pj["Schmidt"], advect_scale_thm=g, advect_scale_cmp=g)
+    assert pb["resid1"] < 1e-2 and pb["resid3"] < 1e-4 and pb["resid4"] < 1e-4, pb

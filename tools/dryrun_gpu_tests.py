@@ -80,6 +80,14 @@ class StandInSolver:
         return lam, (X if want_vectors else None), dict(nconv=len(lam), its=1, ncv=ncv or max(2 * nev, nev + 15),
                                                         resid=res, factor_ms=0.0, eigs_ms=0.0)
 
+    def diagnose(self, p, nodes, X):
+        # the NumPy model of kb_diagnose (tests/diag_model.py), whole radial domain as the tests use it
+        import diag_model as dm
+        X = np.asarray(X, dtype=complex).reshape(-1, 1) if np.ndim(X) == 1 else np.asarray(X, dtype=complex)
+        meta = dict(N=p.N, N1=p.N1, n=p.N1 * p.nb, ricb=p.ricb, m=p.m, lmax=p.lmax, symm=p.symm, thermal=p.thermal)
+        out = [dm.diagnose(X[:, k], meta, "differential" if p.heating == 0 else "internal") for k in range(X.shape[1])]
+        return np.stack([o[0] for o in out]), np.stack([o[1] for o in out])
+
     def stats(self):
         return {}
 
