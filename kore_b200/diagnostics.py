@@ -141,3 +141,76 @@ def power_balance(flow, therm, degrees, lam, Ek, ViscosD=None, Beyonce=0.0, Ther
         out.update(CE=CE, Dcmp=CompD * Dcmp0, Wadv_cmp=Wadv)
         out["resid4"] = abs(2 * sigma * CE - out["Dcmp"] - Wadv) / max(abs(2 * sigma * CE), abs(out["Dcmp"]), abs(Wadv))
     return out
+
+
+def viscous_torques(X, N, lmax, m, symm, ricb, Ek, rcmb=1.0):
+    """(vtorq[nsol], vtorq_icb[nsol]): the viscous torques on the mantle and on the inner core as
+    spin_doctor.py:164-166 forms them, `Ek * gamma . u` with the row vectors of utils.py:1288-1399 for
+    SPHERICAL boundaries (the only call the reference makes is `gamma_visc(0, 0, 0)`).
+
+    Only the degree-1 toroidal scalar T carries a torque through a sphere of radius R:
+    (8 pi / 3) R^2 (R T'(R) - T(R)), axial for m = 0 (equatorially symmetric flow; mantle and inner core),
+    equatorial with a further sqrt(2) for m = 1 (antisymmetric flow; mantle only in the reference).  Boundary
+    values of the Chebyshev series: T_k(+-1) = (+-1)^k, dT_k/dr(+-1) = (+-1)^(k+1) k^2 * 2 / (rcmb - r0)
+    (utils.py:1261-1285)."""
+    X = np.asarray(X, dtype=np.complex128)
+    if X.ndim == 1:
+        X = X.reshape(-1, 1)
+    zero = np.zeros(X.shape[1], dtype=complex)
+    _, lt, _ = _chain.ell(m, lmax, symm)
+    if not ((m == 0 and symm == 1) or (m == 1 and len(lt) and lt[0] == 1)):
+        return zero, zero.copy()
+    N1 = N if ricb > 0 else N // 2
+    n = N1 * ((lmax - m + 1) // 2)
+    # Chebyshev orders held by the degree-1 toroidal block (every other one in a full sphere, utils4pp.py:67-107)
+    s = (symm + 1) // 2
+    k = np.arange(N, dtype=float) if ricb > 0 else (m + s) % 2 + 2.0 * np.arange(N1)
+    r0 = ricb if ricb > 0 else -rcmb
+    scale = 2.0 / (rcmb - r0)
+    T1 = X[n:n + N1]  # first toroidal degree is l = 1 in both cases
+
+    def gamma(x, R):
+        return (8 * np.pi / 3) * R ** 2 * (R * x ** (k + 1) * k ** 2 * scale - x ** k)
+
+    vt = Ek * (np.sqrt(2.0) if m == 1 else 1.0) * (gamma(1.0, 1.0) @ T1)
+    vi = Ek * (gamma(-1.0, ricb) @ T1) if (m == 0 and ricb > 0) else zero
+    return vt, vi
+
+
+def spin_doctor_tables(flow, therm, comp, degrees, lam, Ek, OmgTau, BV2=0.0, BV2_comp=0.0, Etherm=0.0, Ecomp=0.0,
+                       vtorq=None, vtorq_icb=None, pss=0.0):
+    """The rows spin_doctor.py:370-396 appends to flow.dat, thermal.dat and compositional.dat, one per
+    solution, from the per-degree integrals of `diagnose` / `diagnose_double_diffusive` -- with the
+    reference's OWN scalings (`par.OmgTau`, `par.BV2`, `par.Etherm`, `par.Ecomp`, spin_doctor.py:158-186) and
+    its own residuals (:227-242: resid1 without the compositional power), unlike `power_balance`.
+    flow.dat: KE KP KT Dkin Dint Wlor Wthm Wcmp resid0 resid1 Re/Im vtorq Re/Im vtorq_icb (Wlor = 0: no
+    magnetic runs here); thermal.dat: TE Wadv_thm Dthm resid3; compositional.dat: CE Wadv_cmp Dcmp."""
+    lp, lt, ll = degrees
+    ll = np.asarray(ll)
+    nsol = flow.shape[0]
+    lam = np.asarray(lam, dtype=complex).reshape(-1)
+    vtorq = np.zeros(nsol, dtype=complex) if vtorq is None else vtorq
+    vtorq_icb = np.zeros(nsol, dtype=complex) if vtorq_icb is None else vtorq_icb
+    out = {"flow": np.zeros((nsol, 14))}
+    if therm is not None:
+        out["thermal"] = np.zeros((nsol, 4))
+    if comp is not None:
+        out["compositional"] = np.zeros((nsol, 3))
+    for i in range(nsol):
+        sigma = lam[i].real
+        KE, Dkin0, Dint0, _, Wthm0, Wcmp0 = flow[i].sum(axis=0)
+        KP, KT = flow[i][np.isin(ll, lp), 0].sum(), flow[i][np.isin(ll, lt), 0].sum()
+        Dkin, Dint = OmgTau * Ek * Dkin0, OmgTau * Ek * Dint0
+        Wlor, Wthm, Wcmp = 0.0, OmgTau ** 2 * BV2 * Wthm0, OmgTau ** 2 * BV2_comp * Wcmp0
+        resid0 = abs(Dint0 + Dkin0 - pss) / max(abs(Dint0), abs(Dkin0), abs(pss)) if Ek != 0 else np.nan
+        resid1 = abs(2 * sigma * KE - Dkin - Wlor + Wthm) / max(abs(2 * sigma * KE), abs(Dkin), abs(Wlor), abs(Wthm))
+        out["flow"][i] = [KE, KP, KT, Dkin, Dint, Wlor, Wthm, Wcmp, resid0, resid1, vtorq[i].real, vtorq[i].imag,
+                          vtorq_icb[i].real, vtorq_icb[i].imag]
+        if therm is not None:
+            TE, Dthm0, Wadv = therm[i].sum(axis=0)
+            Dthm = Dthm0 * Etherm
+            out["thermal"][i] = [TE, Wadv, Dthm, abs(2 * sigma * TE - Dthm - Wadv) / max(abs(2 * sigma * TE), abs(Dthm), abs(Wadv))]
+        if comp is not None:
+            CE, Dcmp0, Wadv = comp[i].sum(axis=0)
+            out["compositional"][i] = [CE, Wadv, Dcmp0 * Ecomp]
+    return out

@@ -22,7 +22,8 @@ the GPU from the radial operators (kore_b200/assembly.py; hydrodynamic, Boussine
 degree-1 magnetic and anelastic set-ups) -- the same matrices, bit for bit, without A.npz / B.npz ever being written or read.
 When the `*.mtx` files are absent too (or with `-kb_operators`), bin/submatrices.py is skipped as
 well: the radial operators come from parameters.py alone (kore_b200/radial.py).
-`-kb_diagnose` adds power_balance.dat (kore_b200/diagnostics.py), `-kb_npz` adds eigenpairs.npz
+`-kb_diagnose` adds power_balance.dat and spin_doctor.py's flow.dat / thermal.dat / compositional.dat
+(kore_b200/diagnostics.py), `-kb_npz` adds eigenpairs.npz
 (eigenvalues, the complex solution block and the row ranges of the fields, binary).
 The forced right-hand side comes from B_forced.npz when it exists, else (forcing = 7, libration) it
 is formed here.
@@ -147,6 +148,18 @@ def write_power_balance(par, solver, vec, lam):
             keys += ["Wcmp", "CE", "Dcmp", "Wadv_cmp", "resid4"]
         rows.append([pb[k] for k in keys])
     np.savetxt("power_balance.dat", np.asarray(rows))
+    # the files spin_doctor.py itself leaves behind (flow.dat, thermal.dat, compositional.dat; appended to, as
+    # there: spin_doctor.py:370-396), with the reference's own scalings -- which need par.OmgTau
+    if getattr(par, "OmgTau", None) is None:
+        print("-kb_diagnose: parameters.py does not define OmgTau (spin_doctor.py needs it): flow.dat / thermal.dat not written")
+        return
+    vt, vi = dg.viscous_torques(vec, *geom, par.Ek)
+    tables = dg.spin_doctor_tables(flow, therm if par.thermal else None, comp, degs, lam, par.Ek, par.OmgTau,
+                                   getattr(par, "BV2", 0.0), getattr(par, "BV2_comp", 0.0), getattr(par, "Etherm", 0.0),
+                                   getattr(par, "Ecomp", 0.0), vt, vi)
+    for name, rows in tables.items():
+        with open(name + ".dat", "ab") as f:
+            np.savetxt(f, rows)
 
 
 def main(argv=None, device=0):

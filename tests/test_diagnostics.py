@@ -129,6 +129,77 @@ def test_driver_writes_the_double_diffusive_power_balance(tmp_path, monkeypatch)
     assert np.isclose(CE, z["comp"][:, 0].sum(), rtol=1e-12) and resid1 < 1e-2
     assert np.isclose(Wcmp, pj["BV2_comp"] * z["flow"][:, 5].sum(), rtol=1e-12)
     assert np.isclose(Dcmp, pj["Ek"] / pj["Schmidt"] * z["comp"][:, 1].sum(), rtol=1e-12)
+    # ... and spin_doctor.py's own files, appended to on a second call as the reference does
+    zs, p = sd_golden("asm_compositional")
+    par.BV2, par.Etherm, par.Ecomp = p["BV2"], p["Etherm"], p["Ecomp"]
+    for f in ("flow.dat", "thermal.dat", "compositional.dat"):
+        os.remove(f)
+    for _ in range(2):
+        solve.write_power_balance(par, ModelSolver(), zs["X"], zs["lam"])
+    nsol = len(zs["lam"])
+    tables = {k: np.loadtxt(k + ".dat") for k in ("flow", "thermal", "compositional")}
+    assert all(t.shape[0] == 2 * nsol and np.array_equal(t[:nsol], t[nsol:]) for t in tables.values())
+    check_sd_tables({k: t[:nsol] for k, t in tables.items()}, zs, 1e-11)
+
+
+SD_CASES = ["asm_compositional", "sd_spinover_thermal", "sd_m0_thermal"]
+
+
+def sd_golden(name):
+    z = np.load(os.path.join(GOLDEN, name, "spin_doctor.npz"))
+    return z, json.loads(str(z["params"]))
+
+
+def sd_tables(solver, z, p):
+    geom = (p["N"], p["lmax"], p["m"], p["symm"], p["ricb"])
+    comp = None
+    if p["compositional"]:
+        flow, therm, comp, degs = dg.diagnose_double_diffusive(solver, z["X"], *geom, thermal=p["thermal"],
+                                                               heating=p["heating"], comp_background=p["comp_background"])
+    else:
+        flow, therm, degs = dg.diagnose(solver, z["X"], *geom, thermal=p["thermal"], heating=p["heating"])
+    vt, vi = dg.viscous_torques(z["X"], *geom, p["Ek"])
+    return dg.spin_doctor_tables(flow, therm, comp, degs, z["lam"], p["Ek"], p["OmgTau"], p["BV2"], p["BV2_comp"],
+                                 p["Etherm"], p["Ecomp"], vt, vi)
+
+
+def check_sd_tables(tables, z, tol):
+    # flow.dat / thermal.dat / compositional.dat as the UNMODIFIED bin/spin_doctor.py wrote them for the same
+    # solutions (tests/golden/make_spin_doctor_fixtures.py); residual columns are differences of nearly equal
+    # terms, so their bar is absolute
+    for k, cols_abs in (("flow", [8, 9]), ("thermal", [3]), ("compositional", [])):
+        if k + "_dat" not in z:
+            assert k not in tables
+            continue
+        ref, got = z[k + "_dat"], tables[k]
+        assert got.shape == ref.shape
+        scale = np.maximum(np.max(np.abs(ref), axis=0), 1e-300)
+        err = np.abs(got - ref) / scale
+        rel = [c for c in range(ref.shape[1]) if c not in cols_abs]
+        assert err[:, rel].max() <= tol, (k, err.max(axis=0))
+        if cols_abs:
+            assert np.max(np.abs(got[:, cols_abs] - ref[:, cols_abs])) <= max(tol, 1e-9), k
+
+
+@pytest.mark.parametrize("name", SD_CASES)
+def test_spin_doctor_files_match_reference(name):
+    z, p = sd_golden(name)
+    check_sd_tables(sd_tables(ModelSolver(), z, p), z, 1e-11)
+
+
+def test_viscous_torques_of_the_reference_cases():
+    # m = 1 antisymmetric: equatorial torque on the mantle only; m = 0 symmetric: axial torques on mantle and inner
+    # core; any other m: none (utils.py:1288-1399 through spin_doctor.py:164-166)
+    z, p = sd_golden("sd_spinover_thermal")
+    assert np.all(np.abs(z["flow_dat"][:, 10:12]).sum(axis=1) > 0) and not np.any(z["flow_dat"][:, 12:])
+    z, p = sd_golden("sd_m0_thermal")
+    assert np.all(np.abs(z["flow_dat"][:, 10:]).min(axis=1) > 0)
+    vt, vi = dg.viscous_torques(z["X"], p["N"], p["lmax"], p["m"], p["symm"], p["ricb"], p["Ek"])
+    assert np.allclose(vt, z["flow_dat"][:, 10] + 1j * z["flow_dat"][:, 11], rtol=1e-11, atol=0)
+    assert np.allclose(vi, z["flow_dat"][:, 12] + 1j * z["flow_dat"][:, 13], rtol=1e-11, atol=0)
+    z, p = sd_golden("asm_compositional")
+    vt, vi = dg.viscous_torques(z["X"], p["N"], p["lmax"], p["m"], p["symm"], p["ricb"], p["Ek"])
+    assert not np.any(vt) and not np.any(vi) and not np.any(z["flow_dat"][:, 10:])
 
 
 # ---------------------------------------------------------------------------------------- GPU

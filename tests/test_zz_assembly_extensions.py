@@ -367,3 +367,16 @@ def test_device_double_diffusive_integrals_match_reference(lib):
                           comp=comp[0], CompBuoy=pj["OmgTau"] ** 2 * pj["BV2_comp"],
                           CompD=pj["OmgTau"] * pj["Ek"] / pj["Schmidt"], advect_scale_thm=g, advect_scale_cmp=g)
     assert pb["resid1"] < 1e-2 and pb["resid3"] < 1e-4 and pb["resid4"] < 1e-4, pb
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["asm_compositional", "sd_spinover_thermal", "sd_m0_thermal"])
+def test_device_spin_doctor_files_match_reference(lib, name):
+    # flow.dat / thermal.dat / compositional.dat rows (energies, dissipations, powers, residuals, viscous torques) from
+    # kb_diagnose against what the UNMODIFIED bin/spin_doctor.py wrote for the same solutions
+    # (tests/golden/make_spin_doctor_fixtures.py); CPU twin on the kernel's model in tests/test_diagnostics.py
+    import test_diagnostics as td
+    z, p = td.sd_golden(name)
+    with lib.Solver(0) as s:
+        tables = td.sd_tables(s, z, p)
+    td.check_sd_tables(tables, z, 1e-9)
