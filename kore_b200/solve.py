@@ -160,6 +160,9 @@ def write_power_balance(par, solver, vec, lam):
     for name, rows in tables.items():
         with open(name + ".dat", "ab") as f:
             np.savetxt(f, rows)
+    if par.forcing == 0:  # spin_doctor.py:400-402: the running list of eigenvalues next to the per-run eigenvalues0.dat
+        with open("eigenvalues.dat", "ab") as f:
+            np.savetxt(f, np.c_[np.real(lam), np.imag(lam)])
 
 
 def main(argv=None, device=0):

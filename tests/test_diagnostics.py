@@ -132,7 +132,7 @@ def test_driver_writes_the_double_diffusive_power_balance(tmp_path, monkeypatch)
     # ... and spin_doctor.py's own files, appended to on a second call as the reference does
     zs, p = sd_golden("asm_compositional")
     par.BV2, par.Etherm, par.Ecomp = p["BV2"], p["Etherm"], p["Ecomp"]
-    for f in ("flow.dat", "thermal.dat", "compositional.dat"):
+    for f in ("flow.dat", "thermal.dat", "compositional.dat", "eigenvalues.dat"):
         os.remove(f)
     for _ in range(2):
         solve.write_power_balance(par, ModelSolver(), zs["X"], zs["lam"])
@@ -140,6 +140,8 @@ def test_driver_writes_the_double_diffusive_power_balance(tmp_path, monkeypatch)
     tables = {k: np.loadtxt(k + ".dat") for k in ("flow", "thermal", "compositional")}
     assert all(t.shape[0] == 2 * nsol and np.array_equal(t[:nsol], t[nsol:]) for t in tables.values())
     check_sd_tables({k: t[:nsol] for k, t in tables.items()}, zs, 1e-11)
+    ev = np.loadtxt("eigenvalues.dat")
+    assert ev.shape == (2 * nsol, 2) and np.array_equal(ev[:nsol, 0] + 1j * ev[:nsol, 1], zs["lam"])
 
 
 SD_CASES = ["asm_compositional", "sd_spinover_thermal", "sd_m0_thermal"]
