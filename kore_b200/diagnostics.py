@@ -7,7 +7,8 @@ in a multiprocessing pool, and the sums enter the power-balance residuals the ph
 own correctness check (spin_doctor.py:227-242).  Here the integrals are one kernel launch for all
 degrees and all solutions (`kb_diagnose`, csrc/kb_diag.cu); this module prepares the quadrature
 nodes, calls it and forms the same sums and residuals.  Hydrodynamic, Boussinesq thermal and
-double-diffusive (thermal + compositional) solutions; no Lorentz terms.
+double-diffusive (thermal + compositional) solutions; of magnetic solutions the energy and diffusion
+of the induced field only (no Lorentz / induction powers).
 """
 from __future__ import annotations
 
@@ -92,6 +93,21 @@ def diagnose_double_diffusive(solver, X, N, lmax, m, symm, ricb, thermal=1, heat
         flow[:, :, 4] = 0.0
     flow[:, :, 5] = flow_c[:, :, 4]
     return flow, therm, comp, degrees
+
+
+def diagnose_magnetic_energy(solver, Xb, N, lmax, m, bsymm, ricb, rcmb=1.0, Ra=None, Rb=None):
+    """Magnetic energy and magnetic diffusion of the induced field, degree by degree: columns 0 and 1 of the
+    `bdgn` of utils4pp.diagnose (magnetic_worker, utils4pp.py:491-533).  Their integrands are the kinetic ones
+    (`energy_pol/tor`, `diffus_pol/tor`) applied to the poloidal / toroidal scalars [f | g] of b with the
+    degrees of `bsymm = symm * symmB0` (utils.py:56), so it is the flow pass of `kb_diagnose` on the magnetic
+    block `Xb = X[2n:4n]` of a solution.  Column 2 (the induction power) is NaN: it needs the coupling of u
+    with the background field (induction4pp, utils4pp.py:678-775, written for a quadrupolar field only -- on
+    the degree-1 fields the assembly covers the reference itself returns 0 there), as does the Lorentz power
+    of the momentum balance.  Returns (mag[nsol, n_l, 3], degrees of b)."""
+    flow, _, degrees = diagnose(solver, Xb, N, lmax, m, bsymm, ricb, thermal=0, rcmb=rcmb, Ra=Ra, Rb=Rb)
+    mag = np.full(flow.shape[:2] + (3,), np.nan)
+    mag[:, :, :2] = flow[:, :, :2]
+    return mag, degrees
 
 
 def differential_gradient_factor(ricb, rcmb=1.0):

@@ -22,7 +22,7 @@ sys.path.insert(0, HERE)
 from make_golden import CASES  # noqa: E402
 from make_asm_fixtures import NEW_CASES, APPEND  # noqa: E402
 
-DIAG_CASES = ["spinover", "dormy", "jones", "asm_compositional"]
+DIAG_CASES = ["spinover", "dormy", "jones", "asm_compositional", "magnetic_small"]
 
 WORKER = r'''
 import sys, json
@@ -37,11 +37,15 @@ i = int(np.argmax(lam.real))
 x = X[:, i]
 n = ut.n
 u2 = upp.expand_reshape_sol(x[:2 * n], par.symm)
-t2 = upp.expand_reshape_sol(x[2 * n:3 * n], par.symm) if par.thermal else 0
-c0 = (2 + par.thermal) * n
+b2 = upp.expand_reshape_sol(x[2 * n:4 * n], ut.bsymm) if par.magnetic else 0
+t0 = (2 + 2 * par.magnetic) * n
+t2 = upp.expand_reshape_sol(x[t0:t0 + n], par.symm) if par.thermal else 0
+c0 = (2 + 2 * par.magnetic + par.thermal) * n
 c2 = upp.expand_reshape_sol(x[c0:c0 + n], par.symm) if par.compositional else 0
-udgn, bdgn, tdgn, cdgn = upp.diagnose(u2, 0, t2, c2, par.ricb, ut.rcmb, 4)
+udgn, bdgn, tdgn, cdgn = upp.diagnose(u2, b2, t2, c2, par.ricb, ut.rcmb, 4)
 extra = dict(comp=np.asarray(cdgn, dtype=float)) if par.compositional else {}
+if par.magnetic:
+    extra.update(magnetic=np.asarray(bdgn, dtype=float), bsymm=np.array([ut.bsymm]))
 np.savez_compressed("diagnostics.npz", x=x, lam=np.array([lam[i]]), flow=np.asarray(udgn, dtype=float),
                     thermal=np.asarray(tdgn, dtype=float) if par.thermal else np.zeros((0, 3)), **extra)
 print("ok", lam[i], np.sum(udgn, 0))

@@ -204,6 +204,20 @@ def test_viscous_torques_of_the_reference_cases():
     assert not np.any(vt) and not np.any(vi) and not np.any(z["flow_dat"][:, 10:])
 
 
+def test_magnetic_energy_and_diffusion_match_reference():
+    # bdgn[:, 0:2] of utils4pp.diagnose on the eigenvector of the reference-assembled dipole-field pencil
+    # ([u | v | f | g], bsymm = symm * symmB0 = +1), and the flow columns of the same solution
+    meta, pj, z = golden("magnetic_small")
+    n, bsymm = meta["n"], int(z["bsymm"][0])
+    assert bsymm == meta["symm"] * meta["symmB0"] and z["magnetic"].shape == (meta["lmax"] - meta["m"] + 1, 3)
+    geom = (meta["N"], meta["lmax"], meta["m"])
+    mag, degs = dg.diagnose_magnetic_energy(ModelSolver(), z["x"][2 * n:4 * n], *geom, bsymm, meta["ricb"])
+    assert close(mag[0][:, :2], z["magnetic"][:, :2], 1e-12) and np.all(np.isnan(mag[0][:, 2]))
+    assert np.all(z["magnetic"][:, 0] > 0)
+    flow, _, _ = dg.diagnose(ModelSolver(), z["x"][:2 * n], *geom, meta["symm"], meta["ricb"])
+    assert close(flow[0][:, :3], z["flow"][:, :3], 1e-12)
+
+
 # ---------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,heating", CASES)

@@ -380,3 +380,17 @@ def test_device_spin_doctor_files_match_reference(lib, name):
     with lib.Solver(0) as s:
         tables = td.sd_tables(s, z, p)
     td.check_sd_tables(tables, z, 1e-9)
+
+
+@pytest.mark.gpu
+def test_device_magnetic_energy_and_diffusion_match_reference(lib):
+    # the flow pass of kb_diagnose on the magnetic block [f | g] with the degrees of bsymm: magnetic energy and
+    # diffusion per degree against bdgn[:, 0:2] of utils4pp.diagnose (tests/golden/magnetic_small/diagnostics.npz)
+    import test_diagnostics as td
+    from kore_b200 import diagnostics as dg
+    meta, pj, z = td.golden("magnetic_small")
+    n = meta["n"]
+    with lib.Solver(0) as s:
+        mag, degs = dg.diagnose_magnetic_energy(s, z["x"][2 * n:4 * n], meta["N"], meta["lmax"], meta["m"],
+                                                int(z["bsymm"][0]), meta["ricb"])
+    assert td.close(mag[0][:, :2], z["magnetic"][:, :2], 1e-9) and np.all(np.isnan(mag[0][:, 2]))
