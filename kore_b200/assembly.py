@@ -327,7 +327,7 @@ class _Builder:
                 H = max(H, int(np.abs(M.col[nz] - M.row[nz]).max()))
             csr.append(M)
         if 2 * H + 1 > MAX_BAND:
-            raise ValueError("radial operators wider than +-15 are not supported (found +-%d)" % H)
+            raise ValueError("radial operators wider than +-%d are not supported (found +-%d)" % ((MAX_BAND - 1) // 2, H))
         W = 2 * H + 1
         ops = np.zeros((max(1, len(self.labels)), N1, W))
         for k, M in enumerate(csr):
