@@ -33,13 +33,27 @@ def quadrature_nodes(N, ricb, rcmb=1.0, Ra=None, Rb=None):
     return np.vstack([x0, rk, w])
 
 
-def diagnose(solver, X, N, lmax, m, symm, ricb, thermal=0, heating="differential", rcmb=1.0, Ra=None, Rb=None):
+def diagnose(solver, X, N, lmax, m, symm, ricb, thermal=0, heating="differential", rcmb=1.0, Ra=None, Rb=None,
+             gradient_series=None):
     """Per-degree integrals of the solutions in the columns of X (Kore ordering [u | v | h]).
 
     Returns (flow, therm, degrees): flow[nsol, n_l, 6] with the columns of the reference's `udgn`
     (kinetic energy, kinetic dissipation, internal dissipation, 0, buoyancy power, 0), therm[nsol, nb, 3]
-    (`tdgn`: thermal energy, dissipation, advection), degrees = (poloidal, toroidal, all)."""
-    if heating not in ("differential", "internal"):
+    (`tdgn`: thermal energy, dissipation, advection), degrees = (poloidal, toroidal, all).
+
+    heating = 'two zone' / 'user defined': the advection integrand carries `fr = r * twozone(r, args)` (or
+    `r * BVprof(r, args)`, utils4pp.py:410-413) instead of r^2 or 1/r; `gradient_series` are the Chebyshev
+    coefficients of exactly that function on the solution's radial domain -- the `cd_ent` table the radial
+    operators of such a run are built from (kore_b200/radial.py:profile_tables, submatrices.py:407) -- and the
+    integral comes from a second launch of the same kernel with the quadrature weights scaled by fr / r^2 under
+    'internal' heating (the weights enter every integrand as a plain factor).  The reference itself cannot run
+    this branch (it calls `ut.twozone`, which lives in radial_profiles.py), so there is no golden; the sign is
+    the one utils4pp.py writes down, and since the heat equation carries the gradient with a minus
+    (operators.py:738) the thermal balance closes with `power_balance(advect_scale_thm=-1)`."""
+    own_gradient = heating in ("two zone", "user defined")
+    if own_gradient and thermal and gradient_series is None:
+        raise ValueError("heating = %r needs gradient_series (the cd_ent profile table)" % (heating,))
+    if heating not in ("differential", "internal") and not own_gradient:
         raise NotImplementedError("heating = %r" % (heating,))
     N1 = N if ricb > 0 else N // 2
     nb = (lmax - m + 1) // 2
@@ -52,7 +66,13 @@ def diagnose(solver, X, N, lmax, m, symm, ricb, thermal=0, heating="differential
     if X.shape[0] != want:
         raise ValueError("solutions have %d rows, the parameters imply %d (hydro%s only)"
                          % (X.shape[0], want, " + thermal" if thermal else ""))
-    flow, therm = solver.diagnose(p, quadrature_nodes(N, ricb, rcmb, Ra, Rb), X)
+    nodes = quadrature_nodes(N, ricb, rcmb, Ra, Rb)
+    flow, therm = solver.diagnose(p, nodes, X)
+    if own_gradient and thermal:
+        fr = np.polynomial.chebyshev.chebval(nodes[0], np.asarray(gradient_series, dtype=float).ravel())
+        scaled = nodes.copy()
+        scaled[2] = nodes[2] * fr / nodes[1] ** 2
+        therm[:, :, 2] = solver.diagnose(p, scaled, X)[1][:, :, 2]
     return flow, therm, _chain.ell(m, lmax, symm)
 
 

@@ -128,6 +128,12 @@ def write_power_balance(par, solver, vec, lam):
         return
     geom = (int(par.N), par.lmax, par.m, par.symm, par.ricb)
     heating = getattr(par, "heating", "differential")
+    grad = {}
+    if par.thermal and heating in ("two zone", "user defined"):
+        # the run's own background gradient: the cd_ent table its radial operators are built from
+        from . import assembly as _assembly, radial as _radial
+        pp = _assembly.PhysicsParams.from_modules(par, run_utils(os.getcwd()))
+        grad = dict(gradient_series=np.asarray(_radial.run_profiles(pp)["cd_ent"]).ravel())
     comp, extra = None, {}
     if par.compositional:
         flow, therm, comp, degs = dg.diagnose_double_diffusive(
@@ -135,7 +141,16 @@ def write_power_balance(par, solver, vec, lam):
             comp_background=getattr(par, "comp_background", "differential"))
         extra = dict(CompBuoy=par.OmgTau ** 2 * par.BV2_comp, CompD=par.OmgTau * par.Ek / par.Schmidt)
     else:
-        flow, therm, degs = dg.diagnose(solver, vec, *geom, thermal=par.thermal, heating=heating)
+        flow, therm, degs = dg.diagnose(solver, vec, *geom, thermal=par.thermal, heating=heating, **grad)
+    # power_balance.dat is this driver's own file: its thermal / compositional balances carry the constant of the
+    # background gradient that the heat equation has and utils4pp.thermal_advect leaves out (ricb / gap for
+    # 'differential', operators.py:736, 802; the minus of operators.py:738 for a gradient of the run's own), so
+    # that resid3 / resid4 close; flow.dat / thermal.dat below keep the reference's numbers
+    def scale(background):
+        if background == "differential":
+            return dg.differential_gradient_factor(par.ricb) if par.ricb > 0 else 1.0
+        return -1.0 if background in ("two zone", "user defined") else 1.0
+    extra.update(advect_scale_thm=scale(heating), advect_scale_cmp=scale(getattr(par, "comp_background", "internal")))
     rows = []
     for i in range(vec.shape[1]):
         pb = dg.power_balance(flow[i], therm[i] if par.thermal else None, degs, lam[i], par.Ek,

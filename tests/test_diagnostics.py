@@ -129,6 +129,7 @@ def test_driver_writes_the_double_diffusive_power_balance(tmp_path, monkeypatch)
     assert np.isclose(CE, z["comp"][:, 0].sum(), rtol=1e-12) and resid1 < 1e-2
     assert np.isclose(Wcmp, pj["BV2_comp"] * z["flow"][:, 5].sum(), rtol=1e-12)
     assert np.isclose(Dcmp, pj["Ek"] / pj["Schmidt"] * z["comp"][:, 1].sum(), rtol=1e-12)
+    assert rows[0][11] < 1e-4 and rows[0][16] < 1e-4   # resid3, resid4: the driver's own file closes the balances
     # ... and spin_doctor.py's own files, appended to on a second call as the reference does
     zs, p = sd_golden("asm_compositional")
     par.BV2, par.Etherm, par.Ecomp = p["BV2"], p["Etherm"], p["Ecomp"]
@@ -216,6 +217,51 @@ def test_magnetic_energy_and_diffusion_match_reference():
     assert np.all(z["magnetic"][:, 0] > 0)
     flow, _, _ = dg.diagnose(ModelSolver(), z["x"][:2 * n], *geom, meta["symm"], meta["ricb"])
     assert close(flow[0][:, :3], z["flow"][:, :3], 1e-12)
+
+
+def twozone_case():
+    import kore_oracle as ko
+    d = os.path.join(GOLDEN, "asm_twozone")
+    meta, pj = json.load(open(os.path.join(d, "meta.json"))), json.load(open(os.path.join(d, "asm_params.json")))
+    lam, X, info = ko.eigs(ko.load_csr(os.path.join(d, "A.npz")), ko.load_csr(os.path.join(d, "B.npz")),
+                           complex(meta["rtau"], meta["itau"]), meta["nev"], meta["which_eigenpairs"])
+    return meta, pj, lam, X, np.load(os.path.join(d, "radprofs.npz"))["cd_ent"][:, 0]
+
+
+def check_twozone_balance(solver):
+    # 'two zone' heating (a background gradient of the run's own): utils4pp.py:410-411 cannot run in the reference
+    # (ut.twozone does not exist), so the check is the physics: on eigenvectors of the reference-assembled pencil
+    # 2 sigma TE = ThermaD Dthm + Wadv closes with the sign of operators.py:738, and does not with the other one
+    meta, pj, lam, X, cd_ent = twozone_case()
+    assert pj["heating"] == "two zone"
+    geom = (meta["N"], meta["lmax"], meta["m"], meta["symm"], meta["ricb"])
+    with pytest.raises(ValueError):
+        dg.diagnose(solver, X, *geom, thermal=1, heating="two zone")
+    flow, therm, degs = dg.diagnose(solver, X, *geom, thermal=1, heating="two zone", gradient_series=cd_ent)
+    ref, _, _ = dg.diagnose(solver, X, *geom, thermal=1, heating="internal")
+    assert np.array_equal(flow, ref)      # only the advection column depends on the gradient
+    for i in range(len(lam)):
+        r = [dg.power_balance(flow[i], therm[i], degs, lam[i], pj["Ek"], pj["ViscosD"], pj["Beyonce"], pj["ThermaD"],
+                              advect_scale_thm=sc)["resid3"] for sc in (-1.0, 1.0)]
+        assert r[0] < 1.5e-2 and r[1] > 2 * r[0], (i, r)   # N = 48, lmax = 16: resid1 itself is 2-5e-2 here
+
+
+def test_own_heating_gradient_closes_the_thermal_balance():
+    check_twozone_balance(ModelSolver())
+
+
+def test_driver_takes_the_gradient_from_the_runs_profile_tables(tmp_path, monkeypatch):
+    # solve.py -kb_diagnose under 'two zone' heating: cd_ent from the run's radProfs.mat (compute_profiles.py) through
+    # radial.run_profiles, resid3 of power_balance.dat closes
+    import types
+    import scipy.io as sio
+    from kore_b200 import solve
+    meta, pj, lam, X, cd_ent = twozone_case()
+    monkeypatch.chdir(tmp_path)
+    sio.savemat("radProfs.mat", {"cd_ent": cd_ent.reshape(-1, 1)})
+    solve.write_power_balance(types.SimpleNamespace(**pj), ModelSolver(), X, lam)
+    rows = np.loadtxt("power_balance.dat")
+    assert rows.shape == (len(lam), 12) and rows[:, 11].max() < 1.5e-2 and not os.path.exists("flow.dat")
 
 
 # ---------------------------------------------------------------------------------------- GPU

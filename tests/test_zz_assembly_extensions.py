@@ -394,3 +394,12 @@ def test_device_magnetic_energy_and_diffusion_match_reference(lib):
         mag, degs = dg.diagnose_magnetic_energy(s, z["x"][2 * n:4 * n], meta["N"], meta["lmax"], meta["m"],
                                                 int(z["bsymm"][0]), meta["ricb"])
     assert td.close(mag[0][:, :2], z["magnetic"][:, :2], 1e-9) and np.all(np.isnan(mag[0][:, 2]))
+
+
+@pytest.mark.gpu
+def test_device_own_heating_gradient_closes_the_thermal_balance(lib):
+    # 'two zone' heating: the advection integral from a second kb_diagnose launch with scaled quadrature weights
+    # (kore_b200/diagnostics.py:diagnose, gradient_series); CPU twin on the kernel's model in tests/test_diagnostics.py
+    import test_diagnostics as td
+    with lib.Solver(0) as s:
+        td.check_twozone_balance(s)
