@@ -245,7 +245,11 @@ int kb_get_assembled(kb_handle h, int which, int64_t* nnz, int64_t* indptr, int3
  * dissipation, internal dissipation, 0 (Lorentz), buoyancy power, 0 (compositional)} -- the columns of
  * the reference's `udgn`; thermal[nb][3] for the poloidal degrees = {thermal energy, dissipation,
  * advection} (`tdgn`; may be NULL when thermal == 0).  heating: 0 differential, 1 internal
- * (utils4pp.py:404-411). */
+ * (utils4pp.py:404-411).  The host side (kore_b200/diagnostics.py) gets the rest out of this one entry
+ * point: the compositional field of double-diffusive runs is a second call on [u | v | c] (the reference
+ * uses the thermal worker for it, utils4pp.py:846-850), a background gradient of the run's own
+ * ('two zone' / 'user defined' heating) a second call with the weights scaled by fr / r^2 under
+ * heating = 1, the magnetic energy and diffusion the flow pass on [f | g] with the symmetry of b. */
 typedef struct {
   int32_t N, N1, nb, m, lmax, symm, thermal, heating;
   double ricb, rcmb;

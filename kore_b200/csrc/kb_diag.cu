@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(KD_THREADS) kd_degree(KdParams q) {
     f[2] = red[2][0];
     f[3] = 0.0;  // Lorentz power: magnetic runs are not covered
     f[4] = withH ? red[3][0] : 0.0;
-    f[5] = 0.0;  // compositional buoyancy: not covered
+    f[5] = 0.0;  // compositional buoyancy: the host runs this kernel a second time on [u | v | c] (diagnostics.py)
     if (withH) {
       double* t = q.therm + ((size_t)sol * q.nb + idx) * 3;
       t[0] = red[4][0];
