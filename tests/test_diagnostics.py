@@ -264,6 +264,30 @@ def test_driver_takes_the_gradient_from_the_runs_profile_tables(tmp_path, monkey
     assert rows.shape == (len(lam), 12) and rows[:, 11].max() < 1.5e-2 and not os.path.exists("flow.dat")
 
 
+@pytest.mark.parametrize("ricb", [0.35, 0.0])
+def test_viscous_torque_is_the_boundary_value_of_the_series(ricb):
+    # independent of the reference: (8 pi / 3) R^2 (R T'(R) - T(R)) of the degree-1 toroidal scalar, with T and T'
+    # from numpy's Chebyshev class on the solution's radial domain; full sphere: odd polynomials only (m = 0,
+    # symmetric flow: toroidal parity (m + s) % 2 = 1)
+    from numpy.polynomial import chebyshev as C
+    rng = np.random.default_rng(5)
+    N, lmax, m, symm, Ek = 24, 8, 0, 1, 1e-3
+    N1 = N if ricb > 0 else N // 2
+    n = N1 * ((lmax - m + 1) // 2)
+    X = rng.standard_normal((2 * n, 2)) + 1j * rng.standard_normal((2 * n, 2))
+    vt, vi = dg.viscous_torques(X, N, lmax, m, symm, ricb, Ek)
+    for k in range(2):
+        c = X[n:n + N1, k]
+        if ricb == 0:
+            full = np.zeros(N, dtype=complex)
+            full[1::2] = c
+            c = full
+        T = C.Chebyshev(c, domain=[ricb if ricb > 0 else -1.0, 1.0])
+        for got, R in ((vt[k], 1.0), (vi[k], ricb)):
+            want = Ek * (8 * np.pi / 3) * R ** 2 * (R * T.deriv()(R) - T(R)) if R > 0 else 0.0
+            assert abs(got - want) <= 1e-11 * max(1.0, abs(want)), (ricb, R, got, want)
+
+
 # ---------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,heating", CASES)
