@@ -77,7 +77,7 @@ def diagnose(solver, X, N, lmax, m, symm, ricb, thermal=0, heating="differential
 
 
 def diagnose_double_diffusive(solver, X, N, lmax, m, symm, ricb, thermal=1, heating="differential",
-                              comp_background="differential", rcmb=1.0, Ra=None, Rb=None):
+                              comp_background="differential", rcmb=1.0, Ra=None, Rb=None, gradient_series=None):
     """`diagnose` for runs with the composition equation (par.compositional = 1): the columns of X are
     [u | v | h | c] (or [u | v | c] without the heat equation, solve.py:262-273 / assemble.py:442-534
     section order).
@@ -107,7 +107,8 @@ def diagnose_double_diffusive(solver, X, N, lmax, m, symm, ricb, thermal=1, heat
     flow_c, comp, degrees = diagnose(solver, np.vstack([X[:2 * n], X[c0:]]), N, lmax, m, symm, ricb, thermal=1,
                                      heating=comp_background, **kw)
     if thermal:
-        flow, therm, _ = diagnose(solver, X[:3 * n], N, lmax, m, symm, ricb, thermal=1, heating=heating, **kw)
+        flow, therm, _ = diagnose(solver, X[:3 * n], N, lmax, m, symm, ricb, thermal=1, heating=heating,
+                                  gradient_series=gradient_series, **kw)
     else:
         flow, therm = flow_c.copy(), np.zeros_like(comp)
         flow[:, :, 4] = 0.0

@@ -138,7 +138,7 @@ def write_power_balance(par, solver, vec, lam):
     if par.compositional:
         flow, therm, comp, degs = dg.diagnose_double_diffusive(
             solver, vec, *geom, thermal=par.thermal, heating=heating,
-            comp_background=getattr(par, "comp_background", "differential"))
+            comp_background=getattr(par, "comp_background", "differential"), **grad)
         extra = dict(CompBuoy=par.OmgTau ** 2 * par.BV2_comp, CompD=par.OmgTau * par.Ek / par.Schmidt)
     else:
         flow, therm, degs = dg.diagnose(solver, vec, *geom, thermal=par.thermal, heating=heating, **grad)
